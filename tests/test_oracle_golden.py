@@ -1,0 +1,55 @@
+"""Pins the CPU oracle against fixtures produced by the UNMODIFIED reference (oracle/make_golden.py)."""
+import pytest
+import torch
+
+from oracle import model, noise
+from tests import helpers as H
+
+
+@pytest.mark.parametrize('tag', ['small', 'canon'])
+@pytest.mark.parametrize('kind', H.KINDS)
+def test_oracle_matches_reference_fixture(kind, tag):
+    fx = H.load_fixture(tag, kind)
+    sd, imgs, labs, caps, lens = H.fixture_inputs(fx)
+    assert len(sd) == fx['state_dict_keys']
+    with torch.no_grad():
+        enc = model.encode(kind, sd, imgs, labs)
+        assert H.rel_err(enc[0], fx['emb']) < 1e-5
+        if kind == 'xfmr':
+            assert H.rel_err(enc[1], fx['spatial']) < 1e-5
+        logits = model.forward(kind, sd, fx['hp'], imgs, caps[:, :-1],
+                               lens if kind.startswith('lstm') else None, labs)
+        assert tuple(logits.shape) == fx['logits_shape']
+        assert H.rel_err(logits[..., :fx['logits'].shape[-1]], fx['logits']) < 1e-5
+        assert H.rel_err(logits.double().sum(-1), fx['logits_rowsum']) < 1e-4
+        T = min(logits.shape[1], caps.shape[1])
+        pp = float(model.perplexity(logits[:, :T], caps[:, :T], lens))
+        assert abs(pp - fx['perplexity']) / fx['perplexity'] < 1e-4
+        for g in fx['gen']:
+            assert g['oracle_agrees']
+            prefix = caps[:1, :g['prefix_len']] if g['prefix_len'] else None
+            ids, ln = model.generate_batch(kind, sd, fx['hp'], None, labs, max_len=fx['max_len'], encoded=enc,
+                                           caption=prefix, beam_size=g['beam_size'], top_k=g['top_k'],
+                                           temperature=g['temperature'], noise=noise.Noise(g['mode'], g['noise_seed']))
+            H.compare_ids(ids, ln, g, f"{kind} {g['mode']} B={g['beam_size']}")
+
+
+def test_noise_is_exp1_and_keyed():
+    q = noise.exp_noise(3, 5, 7, noise.CALL_TOKEN, 2, 200000)
+    assert abs(float(q.mean()) - 1.0) < 0.01 and abs(float(q.var()) - 1.0) < 0.03 and float(q.min()) > 0
+    assert not torch.equal(q[:100], noise.exp_noise(3, 5, 7, noise.CALL_PRUNE, 2, 100))
+    assert torch.equal(q[:100], noise.exp_noise(3, 5, 7, noise.CALL_TOKEN, 2, 100))
+
+
+def test_all_neg_inf_row_raises_like_reference():
+    # top_k=1 and argmax == <unk> -> whole row -inf -> RuntimeError from multinomial
+    logits = torch.zeros(1, 10)
+    logits[0, 1] = 5.0
+    with pytest.raises(RuntimeError):
+        model.select_tokens(logits, 1, 1.0, 1, 1, None, None)
+
+
+def test_filter_top_k_keeps_ties_and_counts_unk():
+    logits = torch.tensor([[3.0, 9.0, 2.0, 2.0, 1.0, 0.0]])
+    out = model.filter_top_k(logits, 3, 1)          # k-th value = 2.0 (unk counted), ties at 2.0 kept
+    assert out[0].tolist() == [3.0, float('-inf'), 2.0, 2.0, float('-inf'), float('-inf')]
