@@ -1,0 +1,104 @@
+"""ctypes binding of libdeephumor_sm100.so, generated from include/deephumor_b200.h.
+
+The prototypes are parsed from the header so the Python side can never drift from the C ABI.  There is no
+fallback: if the shared library is missing (or a symbol is), loading raises.
+"""
+import ctypes
+import os
+import re
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HEADER = os.path.join(os.path.dirname(HERE), 'include', 'deephumor_b200.h')
+LIB_PATH = os.path.join(HERE, 'libdeephumor_sm100.so')
+
+_SCALARS = {
+    'int': ctypes.c_int, 'float': ctypes.c_float, 'long long': ctypes.c_longlong,
+    'unsigned long long': ctypes.c_ulonglong, 'cudaStream_t': ctypes.c_void_p,
+}
+
+
+class BeamState(ctypes.Structure):
+    """struct dh_beam_state (include/deephumor_b200.h)."""
+    _fields_ = [('seq', ctypes.c_void_p), ('seq_ld', ctypes.c_longlong), ('val', ctypes.c_void_p),
+                ('ended', ctypes.c_void_p), ('done', ctypes.c_void_p), ('final_len', ctypes.c_void_p),
+                ('last_tok', ctypes.c_void_p), ('parent_state', ctypes.c_void_p), ('src', ctypes.c_void_p),
+                ('S_alloc', ctypes.c_int)]
+
+
+def parse_header(path=HEADER):
+    """Returns {name: (restype, [argtypes], [argnames])} for every function the header declares."""
+    text = open(path).read()
+    text = re.sub(r'/\*.*?\*/', ' ', text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r'\b(int|const char\s*\*)\s+(dh_\w+)\s*\(([^;{}]*?)\)\s*;', text, flags=re.S):
+        ret, name, args = m.group(1), m.group(2), ' '.join(m.group(3).split())
+        restype = ctypes.c_int if ret == 'int' else ctypes.c_char_p
+        argtypes, argnames = [], []
+        if args and args != 'void':
+            for a in args.split(','):
+                a = a.strip()
+                pm = re.match(r'^(.*?)(\w+)$', a)
+                ty, nm = pm.group(1).strip(), pm.group(2)
+                if '*' in ty:
+                    argtypes.append(ctypes.c_void_p)
+                else:
+                    ty = ty.replace('const ', '').strip()
+                    argtypes.append(_SCALARS[ty])
+                argnames.append(nm)
+        protos[name] = (restype, argtypes, argnames)
+    return protos
+
+
+class DeepHumorLibError(RuntimeError):
+    pass
+
+
+class _Lib:
+    def __init__(self):
+        self._dll = None
+        self.protos = parse_header()
+        self.launches = 0          # number of kernel-launching C-ABI calls made (bench reports it)
+
+    def load(self):
+        if self._dll is not None:
+            return self._dll
+        if not os.path.exists(LIB_PATH):
+            raise DeepHumorLibError(
+                f'{LIB_PATH} is missing: build it with `python -m deephumor_b200.build` '
+                '(there is no CPU or PyTorch fallback for the caption path)')
+        dll = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes, _) in self.protos.items():
+            try:
+                fn = getattr(dll, name)
+            except AttributeError as e:
+                raise DeepHumorLibError(f'{LIB_PATH} does not export {name} declared in {HEADER}') from e
+            fn.restype, fn.argtypes = restype, argtypes
+        if dll.dh_version() != self._header_version():
+            raise DeepHumorLibError('libdeephumor_sm100.so is stale (DH_VERSION mismatch); rebuild')
+        self._dll = dll
+        return dll
+
+    def _header_version(self):
+        return int(re.search(r'#define DH_VERSION (\d+)', open(HEADER).read()).group(1))
+
+    def call(self, name, *args):
+        dll = self.load()
+        rc = getattr(dll, name)(*args)
+        self.launches += 1
+        if rc != 0:
+            msg = dll.dh_last_error().decode(errors='replace')
+            kind = 'argument error' if rc < 0 else f'CUDA error {rc}'
+            raise DeepHumorLibError(f'{name} failed ({kind}): {msg}')
+
+
+LIB = _Lib()
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,468 @@
+// Token selection and beam bookkeeping (reference: models/beam.py:32-108 and the generate() loops in
+// models/rnn_models.py:84-143, models/transformers.py:531-579 / 778-825).
+//
+//  dh_select_tokens : per logits row -- exact k-th-largest threshold (ties kept, <unk> masked but counted,
+//                     Q3), softmax(l/T), Exp(1)-race draw of B ids without replacement (Q2), score =
+//                     log_softmax over the B picked raw logits (Q4).  One CTA per row; the row is staged
+//                     once in shared memory (V*4 B <= 220 KB) so HBM sees exactly one read of the logits.
+//  dh_beam_init     : first-step state (sequences, scores, ended flags, KV slot table).
+//  dh_beam_step     : one warp per image -- candidate expansion (Q6), stochastic pruning (Q7), sequence /
+//                     score / ended write-back, parent indices for recurrent state (LSTM: the reference's
+//                     misaligned f // B, Q8; transformer: true parent), "frozen at break" (Q11/Q10).
+//  dh_beam_final    : final pick (Q13) and padded [n_img, max_len] output + lengths.
+//  dh_token_logprob : log_softmax(logits)[target] per row (experiments/metrics.py:5).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kSelThreads = 256;
+constexpr int kMaxBeam = 16;
+constexpr int kSurvCap = 4096;
+constexpr int kMaxSlots = 160;   // max cached positions per beam (S_alloc)
+
+__device__ __forceinline__ unsigned int order_key(float x) {
+  unsigned int u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+struct SelParams {
+  const float* logits; long long ld;
+  int R, V, B, top_k, unk, rpi;
+  float T;
+  int noise_mode; unsigned long long seed; long long image_base; int step;
+  const unsigned char* done;   // [n_img] rows of frozen images are skipped (may be null)
+  int* ind; float* val;        // [R, B]
+  int* status;
+};
+
+__global__ void __launch_bounds__(kSelThreads) select_tokens_kernel(SelParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* vals = reinterpret_cast<float*>(smem_raw);                       // [V]
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned int s_prefix, s_krem;
+  __shared__ int s_nsurv;
+  __shared__ int surv_idx[kSurvCap];
+  __shared__ float surv_score[kSurvCap];
+  __shared__ float red_f[kSelThreads / 32];
+  __shared__ int red_i[kSelThreads / 32];
+  __shared__ float s_bcast;
+  __shared__ int pick_idx[kMaxBeam];
+  __shared__ float pick_logit[kMaxBeam];
+
+  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int img = r / p.rpi;
+  if (p.done && p.done[img]) return;
+  const float* row = p.logits + (long long)r * p.ld;
+  for (int i = tid; i < p.V; i += kSelThreads) vals[i] = row[i];
+  if (tid == 0) { s_prefix = 0u; s_krem = (unsigned)p.top_k; s_nsurv = 0; }
+  __syncthreads();
+
+  // ---- exact k-th largest by 4x8-bit radix select on the order-preserving key
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    hist[tid] = 0u;
+    __syncthreads();
+    const unsigned int prefix = s_prefix;
+    const unsigned int mask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+    for (int i = tid; i < p.V; i += kSelThreads) {
+      unsigned int k = order_key(vals[i]);
+      if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned int krem = s_krem, acc = 0u;
+      int bin = 255;
+      for (; bin > 0; --bin) {
+        if (acc + hist[bin] >= krem) break;
+        acc += hist[bin];
+      }
+      s_krem = krem - acc;
+      s_prefix = prefix | ((unsigned int)bin << shift);
+    }
+    __syncthreads();
+  }
+  const unsigned int kth_key = s_prefix;
+
+  // ---- survivors: value >= k-th largest (ties kept) and id != <unk>
+  for (int i = tid; i < p.V; i += kSelThreads) {
+    if (order_key(vals[i]) >= kth_key && i != p.unk && vals[i] > -INFINITY) {
+      int slot = atomicAdd(&s_nsurv, 1);
+      if (slot < kSurvCap) surv_idx[slot] = i;
+    }
+  }
+  __syncthreads();
+  int ns = s_nsurv;
+  if (ns > kSurvCap) {
+    if (tid == 0) atomicOr(p.status, DH_STATUS_TOO_MANY_TIES);
+    ns = kSurvCap;
+  }
+  if (ns == 0) {   // whole row filtered: torch.multinomial raises (Q3)
+    if (tid == 0) atomicOr(p.status, DH_STATUS_EMPTY_ROW);
+    if (tid < p.B) { p.ind[(long long)r * p.B + tid] = 0; p.val[(long long)r * p.B + tid] = 0.f; }
+    return;
+  }
+
+  // ---- softmax(l / T) over survivors (everything else has p == 0 exactly)
+  float mx = -INFINITY;
+  for (int s = tid; s < ns; s += kSelThreads) mx = fmaxf(mx, vals[surv_idx[s]] / p.T);
+  mx = dh_warp_max(mx);
+  if (lane == 0) red_f[warp] = mx;
+  __syncthreads();
+  if (tid == 0) { float m = red_f[0]; for (int w = 1; w < kSelThreads / 32; ++w) m = fmaxf(m, red_f[w]); s_bcast = m; }
+  __syncthreads();
+  mx = s_bcast;
+  float sum = 0.f;
+  for (int s = tid; s < ns; s += kSelThreads) {
+    float e = expf(vals[surv_idx[s]] / p.T - mx);
+    surv_score[s] = e;
+    sum += e;
+  }
+  sum = dh_warp_sum(sum);
+  __syncthreads();
+  if (lane == 0) red_f[warp] = sum;
+  __syncthreads();
+  if (tid == 0) { float t = 0.f; for (int w = 0; w < kSelThreads / 32; ++w) t += red_f[w]; s_bcast = t; }
+  __syncthreads();
+  sum = s_bcast;
+  const unsigned long long rk = dh_noise_row_key(p.seed, (unsigned long long)(p.image_base + img), (unsigned long long)p.step,
+                                                 DH_CALL_TOKEN, (unsigned long long)(r % p.rpi));
+  for (int s = tid; s < ns; s += kSelThreads) {
+    float pr = surv_score[s] / sum;
+    if (p.noise_mode == DH_NOISE_INJECTED) pr = pr / dh_exp_noise(rk, (unsigned long long)surv_idx[s]);
+    surv_score[s] = pr;
+  }
+  __syncthreads();
+
+  // ---- B rounds of block arg-max on (score desc, id asc)
+  const int npick = ns < p.B ? ns : p.B;
+  for (int j = 0; j < npick; ++j) {
+    float best = -1.f; int bi = 0x7fffffff, bs = -1;
+    for (int s = tid; s < ns; s += kSelThreads) {
+      float sc = surv_score[s]; int id = surv_idx[s];
+      if (sc > best || (sc == best && sc >= 0.f && id < bi)) { best = sc; bi = id; bs = s; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      int os = __shfl_xor_sync(0xffffffffu, bs, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; bs = os; }
+    }
+    if (lane == 0) { red_f[warp] = best; red_i[warp] = bs; }
+    __syncthreads();
+    if (tid == 0) {
+      float b2 = -1.f; int s2 = -1, i2 = 0x7fffffff;
+      for (int w = 0; w < kSelThreads / 32; ++w) {
+        int s = red_i[w];
+        if (s < 0) continue;
+        int id = surv_idx[s];
+        if (red_f[w] > b2 || (red_f[w] == b2 && id < i2)) { b2 = red_f[w]; s2 = s; i2 = id; }
+      }
+      pick_idx[j] = i2;
+      pick_logit[j] = vals[i2];
+      surv_score[s2] = -2.f;   // taken
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    // fewer survivors than B: multinomial continues with zero-probability ids; stable order = lowest ids
+    int next = 0;
+    for (int j = npick; j < p.B; ++j) {
+      for (;; ++next) {
+        bool used = false;
+        for (int q = 0; q < j; ++q) used |= (pick_idx[q] == next);
+        if (!used) break;
+      }
+      pick_idx[j] = next;
+      pick_logit[j] = -INFINITY;
+      ++next;
+    }
+    // score = log_softmax over the B picked (filtered, un-tempered) logits (Q4)
+    float m2 = -INFINITY;
+    for (int j = 0; j < p.B; ++j) m2 = fmaxf(m2, pick_logit[j]);
+    float se = 0.f;
+    for (int j = 0; j < p.B; ++j) se += expf(pick_logit[j] - m2);
+    float lse = logf(se);
+    for (int j = 0; j < p.B; ++j) {
+      p.ind[(long long)r * p.B + j] = pick_idx[j];
+      p.val[(long long)r * p.B + j] = pick_logit[j] - m2 - lse;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ beam state
+struct BeamState {
+  int* seq;            // [n_img, B, seq_ld]
+  long long seq_ld;
+  float* val;          // [n_img, B]
+  unsigned char* ended;  // [n_img, B]
+  unsigned char* done;   // [n_img]
+  int* final_len;      // [n_img]
+  int* last_tok;       // [n_img * B]
+  int* parent_state;   // [n_img * B] row to gather recurrent state from
+  int* src;            // [n_img, B, S_alloc] KV slot table (transformer) or null
+  int S_alloc;
+};
+
+__global__ void beam_init_kernel(BeamState st, const int* __restrict__ ind0, const float* __restrict__ val0,
+                                 const int* __restrict__ prefix, long long prefix_ld, int prefix_rows, int p0, int n_img,
+                                 int B, int eos, int lstm_semantics) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_img * B) return;
+  int img = i / B, b = i % B;
+  int* s = st.seq + (long long)i * st.seq_ld;
+  for (int t = 0; t < p0; ++t) s[t] = prefix[(long long)(prefix_rows == 1 ? 0 : img) * prefix_ld + t];
+  int tok = ind0[i];
+  s[p0] = tok;
+  for (long long t = p0 + 1; t < st.seq_ld; ++t) s[t] = 0;
+  st.val[i] = val0[i];
+  st.ended[i] = (unsigned char)(lstm_semantics ? (tok == eos) : 0);   // Q9
+  st.last_tok[i] = tok;
+  st.parent_state[i] = img;                                             // expand the 1-row-per-image state
+  if (st.src) {
+    int* sr = st.src + (long long)i * st.S_alloc;
+    for (int t = 0; t < st.S_alloc; ++t) sr[t] = (t <= p0) ? 0 : b;     // positions 0..p0 live in slot 0
+  }
+  if (b == 0) { st.done[img] = 0; st.final_len[img] = 0; }
+}
+
+struct StepParams {
+  const int* new_ind; const float* new_val;   // [n_img*B, B]
+  int n_img, B, step, max_len, eos, lstm_semantics;
+  float T; int noise_mode; unsigned long long seed; long long image_base;
+};
+
+__global__ void __launch_bounds__(32) beam_step_kernel(BeamState st, StepParams p) {
+  extern __shared__ int s_seq[];                 // [B, seq_ld]
+  __shared__ float s_score[kMaxBeam * kMaxBeam];
+  __shared__ float s_cval[kMaxBeam * kMaxBeam];
+  __shared__ int s_ctok[kMaxBeam * kMaxBeam];
+  __shared__ unsigned char s_cend[kMaxBeam * kMaxBeam], s_cpar[kMaxBeam * kMaxBeam];
+  __shared__ int s_f[kMaxBeam];
+  __shared__ int s_src[kMaxBeam][kMaxSlots];
+  const int img = blockIdx.x, lane = threadIdx.x, B = p.B;
+  if (st.done[img]) return;
+  const long long base = (long long)img * B;
+  // --- candidate layout (beam.py:83-102): ended row -> 1 copy, live row -> B copies
+  int e = 0, copies = 0;
+  float v = 0.f;
+  if (lane < B) { e = st.ended[base + lane]; copies = e ? 1 : B; v = st.val[base + lane]; }
+  int off = copies;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, off, o); if (lane >= o) off += t; }
+  const int N = __shfl_sync(0xffffffffu, off, 31);
+  off -= copies;
+  if (lane < B) {
+    for (int j = 0; j < copies; ++j) {
+      int c = off + j;
+      int tok = e ? 0 : p.new_ind[(base + lane) * B + j];
+      float dv = e ? 0.f : p.new_val[(base + lane) * B + j];
+      s_cval[c] = v + dv;
+      s_ctok[c] = tok;
+      s_cend[c] = (unsigned char)(e | (tok == p.eos));
+      s_cpar[c] = (unsigned char)lane;
+    }
+  }
+  // stage old sequences (and slot table) before they are overwritten
+  for (long long i = lane; i < (long long)B * st.seq_ld; i += 32) s_seq[i] = st.seq[base * st.seq_ld + i];
+  if (st.src)
+    for (int i = lane; i < B * st.S_alloc; i += 32) s_src[i / st.S_alloc][i % st.S_alloc] = st.src[base * st.S_alloc + i];
+  __syncwarp();
+  // --- pruning draw: sample B of N from softmax(cand_val / T) (Q7)
+  float mx = -INFINITY;
+  for (int c = lane; c < N; c += 32) mx = fmaxf(mx, s_cval[c] / p.T);
+  mx = dh_warp_max(mx);
+  float sum = 0.f;
+  for (int c = lane; c < N; c += 32) { float ex = expf(s_cval[c] / p.T - mx); s_score[c] = ex; sum += ex; }
+  sum = dh_warp_sum(sum);
+  const unsigned long long rk = dh_noise_row_key(p.seed, (unsigned long long)(p.image_base + img), (unsigned long long)p.step,
+                                                 DH_CALL_PRUNE, 0ull);
+  for (int c = lane; c < N; c += 32) {
+    float pr = s_score[c] / sum;
+    if (p.noise_mode == DH_NOISE_INJECTED) pr = pr / dh_exp_noise(rk, (unsigned long long)c);
+    s_score[c] = pr;
+  }
+  __syncwarp();
+  for (int j = 0; j < B; ++j) {
+    float best = -1.f; int bc = 0x7fffffff;
+    for (int c = lane; c < N; c += 32) {
+      float sc = s_score[c];
+      if (sc > best || (sc == best && sc >= 0.f && c < bc)) { best = sc; bc = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+      if (ob > best || (ob == best && oc < bc)) { best = ob; bc = oc; }
+    }
+    if (lane == 0) { s_f[j] = bc; s_score[bc] = -2.f; }
+    __syncwarp();
+  }
+  // --- write back
+  int all_ended = 1;
+  if (lane < B) {
+    const int f = s_f[lane];
+    const int par = s_cpar[f];
+    const int tok = s_ctok[f];
+    st.val[base + lane] = s_cval[f];
+    st.ended[base + lane] = s_cend[f];
+    all_ended = s_cend[f];
+    st.last_tok[base + lane] = tok;
+    st.parent_state[base + lane] = (int)base + (p.lstm_semantics ? (f / B) : par);   // Q8
+  }
+  all_ended = __all_sync(0xffffffffu, all_ended);
+  for (int j = 0; j < B; ++j) {
+    const int f = s_f[j], par = s_cpar[f];
+    int* dst = st.seq + (base + j) * st.seq_ld;
+    for (int t = lane; t < st.seq_ld; t += 32) {
+      int x = s_seq[(long long)par * st.seq_ld + t];
+      if (t == p.step && p.step < p.max_len) x = s_ctok[f];      // column `step`; no-op at step == max_len (Q10)
+      dst[t] = x;
+    }
+    if (st.src) {
+      int* sr = st.src + (base + j) * st.S_alloc;
+      for (int t = lane; t < st.S_alloc; t += 32) sr[t] = (t <= p.step) ? s_src[par][t] : j;
+    }
+  }
+  if (lane == 0 && all_ended) {
+    st.done[img] = 1;                                              // reference `break` (rnn_models.py:131)
+    st.final_len[img] = p.lstm_semantics ? p.step + 1 : p.step;    // Q11 / Q10
+  }
+}
+
+__global__ void __launch_bounds__(32) beam_final_kernel(BeamState st, int n_img, int B, float T, int noise_mode,
+                                                        unsigned long long seed, long long image_base, int final_step,
+                                                        int len_if_running, int pad, int max_len,
+                                                        long long* __restrict__ out_ids, long long* __restrict__ out_len) {
+  const int img = blockIdx.x, lane = threadIdx.x;
+  const long long base = (long long)img * B;
+  float x = lane < B ? st.val[base + lane] / T : -INFINITY;
+  float mx = dh_warp_max(x);
+  float ex = lane < B ? expf(x - mx) : 0.f;
+  float sum = dh_warp_sum(ex);
+  float sc = ex / sum;
+  if (lane < B && noise_mode == DH_NOISE_INJECTED) {
+    unsigned long long rk = dh_noise_row_key(seed, (unsigned long long)(image_base + img), (unsigned long long)final_step,
+                                             DH_CALL_FINAL, 0ull);
+    sc = sc / dh_exp_noise(rk, (unsigned long long)lane);
+  }
+  if (lane >= B) sc = -1.f;
+  int bi = lane;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ob = __shfl_xor_sync(0xffffffffu, sc, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > sc || (ob == sc && oi < bi)) { sc = ob; bi = oi; }
+  }
+  const int len = st.done[img] ? st.final_len[img] : len_if_running;
+  const int* s = st.seq + (base + bi) * st.seq_ld;
+  for (int t = lane; t < max_len; t += 32) out_ids[(long long)img * max_len + t] = (t < len) ? (long long)s[t] : (long long)pad;
+  if (lane == 0) out_len[img] = len;
+}
+
+// ------------------------------------------------------------------------------------------------ log-prob
+__global__ void __launch_bounds__(256) token_logprob_kernel(const float* __restrict__ logits, long long ld, int V,
+                                                            const long long* __restrict__ targets, float* __restrict__ out) {
+  __shared__ float red[8];
+  __shared__ float s_b;
+  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* row = logits + (long long)r * ld;
+  float mx = -INFINITY;
+  for (int i = tid; i < V; i += 256) mx = fmaxf(mx, row[i]);
+  mx = dh_warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (tid == 0) { float m = red[0]; for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]); s_b = m; }
+  __syncthreads();
+  mx = s_b;
+  float sum = 0.f;
+  for (int i = tid; i < V; i += 256) sum += expf(row[i] - mx);
+  sum = dh_warp_sum(sum);
+  __syncthreads();
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    out[r] = row[targets[r]] - mx - logf(t);
+  }
+}
+
+}  // namespace
+
+extern "C" int dh_select_tokens(const float* logits, long long ld, int rows, int V, int beam, int top_k, float temperature,
+                                int unk, int rows_per_image, int noise_mode, unsigned long long seed, long long image_base,
+                                int step, const unsigned char* done, int* ind, float* val, int* status, cudaStream_t s) {
+  DH_ARG(logits && ind && val && status && rows >= 0 && V > 0);
+  DH_ARG(beam >= 1 && beam <= kMaxBeam && top_k >= 1 && top_k <= V && beam <= top_k && temperature > 0.f);
+  DH_ARG(rows_per_image >= 1 && (noise_mode == DH_NOISE_DETERMINISTIC || noise_mode == DH_NOISE_INJECTED));
+  if (rows == 0) return DH_OK;
+  size_t smem = (size_t)V * sizeof(float);
+  DH_ARG(smem <= 180 * 1024);   // row staged in shared memory; V <= 46080
+  static bool attr_set = false;
+  if (!attr_set) {
+    DH_CUDA(cudaFuncSetAttribute(select_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
+    attr_set = true;
+  }
+  SelParams p{logits, ld, rows, V, beam, top_k, unk, rows_per_image, temperature, noise_mode, seed, image_base, step,
+              done, ind, val, status};
+  select_tokens_kernel<<<rows, kSelThreads, smem, s>>>(p);
+  DH_LAUNCH_OK();
+  return DH_OK;
+}
+
+static int check_state(const dh_beam_state* st, int n_img, int beam) {
+  if (!st || !st->seq || !st->val || !st->ended || !st->done || !st->final_len || !st->last_tok || !st->parent_state) return 0;
+  if (n_img < 0 || beam < 1 || beam > kMaxBeam || st->seq_ld < 1) return 0;
+  if (st->src && (st->S_alloc < 1 || st->S_alloc > kMaxSlots)) return 0;
+  return 1;
+}
+static BeamState to_state(const dh_beam_state* st) {
+  return BeamState{st->seq, st->seq_ld, st->val, st->ended, st->done, st->final_len, st->last_tok, st->parent_state,
+                   st->src, st->S_alloc};
+}
+
+extern "C" int dh_beam_init(const dh_beam_state* st, const int* ind0, const float* val0, const int* prefix,
+                            long long prefix_ld, int prefix_rows, int prefix_len, int n_img, int beam, int eos,
+                            int lstm_semantics, cudaStream_t s) {
+  DH_ARG(check_state(st, n_img, beam) && ind0 && val0 && prefix_len >= 0 && prefix_len < st->seq_ld);
+  DH_ARG(prefix_len == 0 || (prefix && (prefix_rows == 1 || prefix_rows == n_img)));
+  if (n_img == 0) return DH_OK;
+  int total = n_img * beam;
+  beam_init_kernel<<<dh_cdiv(total, 128), 128, 0, s>>>(to_state(st), ind0, val0, prefix, prefix_ld, prefix_rows, prefix_len,
+                                                      n_img, beam, eos, lstm_semantics);
+  DH_LAUNCH_OK();
+  return DH_OK;
+}
+
+extern "C" int dh_beam_step(const dh_beam_state* st, const int* new_ind, const float* new_val, int n_img, int beam,
+                            int step, int max_len, int eos, int lstm_semantics, float temperature, int noise_mode,
+                            unsigned long long seed, long long image_base, cudaStream_t s) {
+  DH_ARG(check_state(st, n_img, beam) && new_ind && new_val && temperature > 0.f && step >= 1);
+  DH_ARG(st->seq_ld >= max_len && (size_t)beam * st->seq_ld * sizeof(int) <= 40 * 1024);
+  if (n_img == 0) return DH_OK;
+  StepParams p{new_ind, new_val, n_img, beam, step, max_len, eos, lstm_semantics, temperature, noise_mode, seed, image_base};
+  beam_step_kernel<<<n_img, 32, (size_t)beam * st->seq_ld * sizeof(int), s>>>(to_state(st), p);
+  DH_LAUNCH_OK();
+  return DH_OK;
+}
+
+extern "C" int dh_beam_final(const dh_beam_state* st, int n_img, int beam, float temperature, int noise_mode,
+                             unsigned long long seed, long long image_base, int final_step, int len_if_running, int pad,
+                             int max_len, long long* out_ids, long long* out_len, cudaStream_t s) {
+  DH_ARG(check_state(st, n_img, beam) && out_ids && out_len && temperature > 0.f && max_len <= st->seq_ld);
+  if (n_img == 0) return DH_OK;
+  beam_final_kernel<<<n_img, 32, 0, s>>>(to_state(st), n_img, beam, temperature, noise_mode, seed, image_base, final_step,
+                                        len_if_running, pad, max_len, out_ids, out_len);
+  DH_LAUNCH_OK();
+  return DH_OK;
+}
+
+extern "C" int dh_token_logprob(const float* logits, long long ld, int rows, int V, const long long* targets, float* out,
+                                cudaStream_t s) {
+  DH_ARG(logits && targets && out && rows >= 0 && V > 0);
+  if (rows == 0) return DH_OK;
+  token_logprob_kernel<<<rows, 256, 0, s>>>(logits, ld, V, targets, out);
+  DH_LAUNCH_OK();
+  return DH_OK;
+}

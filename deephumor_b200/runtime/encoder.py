@@ -1,0 +1,128 @@
+"""Encoder runtime: packed ResNet-50 trunk + embedding heads on the C-ABI kernels.
+
+Reference: models/encoders.py:22-70 (ImageEncoder), :96-106 (LabelEncoder), :129-144 (ImageLabelEncoder);
+torchvision resnet.py:143-163,197-204,266-279.  Packing (one-time, torch ops on the device): eval-mode BN folded
+into conv weights and a bias, OIHW -> [Cout][kh][kw][Cin] for NHWC implicit GEMM,
+BatchNorm1d folded into the global head, cast to the storage type of the precision mode.
+"""
+import torch
+
+from . import ops
+
+RESNET_BLOCKS = (3, 4, 6, 3)
+EPS = 1e-5
+
+
+def _fold_bn(sd, conv, bn):
+    w = sd[conv + '.weight'].float()
+    g, b = sd[bn + '.weight'].float(), sd[bn + '.bias'].float()
+    m, v = sd[bn + '.running_mean'].float(), sd[bn + '.running_var'].float()
+    s = g / torch.sqrt(v + EPS)
+    return w * s.view(-1, 1, 1, 1), b - m * s
+
+
+class PackedConv:
+    __slots__ = ('w', 'bias', 'stride', 'pad', 'cout', 'kh')
+
+    def __init__(self, sd, conv, bn, stride, pad, dtype, device, cin_pad=None):
+        w, bias = _fold_bn(sd, conv, bn)
+        w = w.permute(0, 2, 3, 1)                                # [Cout, kh, kw, Cin]
+        if cin_pad is not None and cin_pad > w.shape[3]:
+            w = torch.nn.functional.pad(w, (0, cin_pad - w.shape[3]))
+        self.w = w.contiguous().to(device=device, dtype=dtype)
+        self.bias = bias.contiguous().to(device=device, dtype=torch.float32)
+        self.stride, self.pad, self.cout, self.kh = stride, pad, w.shape[0], w.shape[1]
+
+
+class EncoderRT:
+    """prefix = 'encoder' (ImageEncoder) or 'encoder.image_encoder' (inside ImageLabelEncoder)."""
+
+    def __init__(self, sd, prefix, dtype, device, spatial=False, label_prefix=None, fuse_prefix=None, chunk=256):
+        self.dtype, self.device, self.spatial, self.chunk = dtype, device, spatial, chunk
+        p = prefix + '.resnet'
+        mk = lambda conv, bn, s, pad, cin_pad=None: PackedConv(sd, conv, bn, s, pad, dtype, device, cin_pad)
+        self.stem = mk(p + '.0', p + '.1', 2, 3, cin_pad=4)
+        self.blocks = []
+        for li, nblk in enumerate(RESNET_BLOCKS):
+            for b in range(nblk):
+                q = f'{p}.{4 + li}.{b}'
+                stride = 2 if (b == 0 and li > 0) else 1
+                self.blocks.append(dict(
+                    c1=mk(q + '.conv1', q + '.bn1', 1, 0), c2=mk(q + '.conv2', q + '.bn2', stride, 1),
+                    c3=mk(q + '.conv3', q + '.bn3', 1, 0),
+                    down=mk(q + '.downsample.0', q + '.downsample.1', stride, 0) if b == 0 else None))
+        W = sd[prefix + '.linear.weight'].float()
+        b = sd[prefix + '.linear.bias'].float()
+        g, be = sd[prefix + '.bn.weight'].float(), sd[prefix + '.bn.bias'].float()
+        m, v = sd[prefix + '.bn.running_mean'].float(), sd[prefix + '.bn.running_var'].float()
+        s = g / torch.sqrt(v + EPS)
+        to = lambda t, dt=dtype: t.contiguous().to(device=device, dtype=dt)
+        self.Wg, self.bg = to(W * s.view(-1, 1)), to((b - m) * s + be, torch.float32)      # Linear + BN1d (eval)
+        self.Wsp, self.bsp = to(W), to(b, torch.float32)                                      # spatial: no BN (Q20)
+        self.E = W.shape[0]
+        self.label_table = self.Wl = self.bl = None
+        if label_prefix is not None:
+            self.label_table = to(sd[label_prefix + '.embedding.weight'].float())
+            self.Wl, self.bl = to(sd[fuse_prefix + '.linear.weight'].float()), to(sd[fuse_prefix + '.linear.bias'].float(),
+                                                                                 torch.float32)
+        self._ws = {}
+
+    # ---------------------------------------------------------------- trunk
+    def _buf(self, name, shape, dtype=None):
+        key = (name, tuple(shape), dtype or self.dtype)
+        t = self._ws.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype or self.dtype, device=self.device)
+            self._ws[key] = t
+        return t
+
+    def _conv(self, name, x, pc, relu, residual=None):
+        n, H, W, _ = x.shape
+        Ho = (H + 2 * pc.pad - pc.kh) // pc.stride + 1
+        y = self._buf(name, (n, Ho, Ho, pc.cout))
+        ops.conv2d(x, pc.w, pc.bias, y, pc.stride, pc.pad, relu, residual)
+        return y
+
+    def trunk(self, images):
+        """images [n,3,224,224] fp32 NCHW (device) -> features [n,7,7,2048] NHWC in the storage dtype."""
+        n, _, H, W = images.shape
+        x = self._buf('in', (n, H, W, 4))
+        ops.nchw_to_nhwc4(images, x, halo=0)
+        x = self._conv('stem', x, self.stem, True)
+        y = self._buf('pool', (n, x.shape[1] // 2, x.shape[2] // 2, 64))
+        ops.maxpool3x3s2(x, y)
+        x = y
+        for i, blk in enumerate(self.blocks):
+            y1 = self._conv(f'b{i}c1', x, blk['c1'], True)
+            y2 = self._conv(f'b{i}c2', y1, blk['c2'], True)
+            idn = self._conv(f'b{i}ds', x, blk['down'], False) if blk['down'] is not None else x
+            x = self._conv(f'b{i}c3', y2, blk['c3'], True, residual=idn)
+        return x
+
+    # ---------------------------------------------------------------- heads
+    def forward(self, images, labels=None):
+        """-> (start_emb fp32 [N,E], spatial [N*49,E] storage dtype or None).  Processes `chunk` images at a time."""
+        N = images.shape[0]
+        E = self.E
+        start = torch.empty(N, E, dtype=torch.float32, device=self.device)
+        sp = torch.empty(N * 49, E, dtype=self.dtype, device=self.device) if self.spatial else None
+        for i0 in range(0, N, self.chunk):
+            img = images[i0:i0 + self.chunk]
+            n = img.shape[0]
+            feat = self.trunk(img.contiguous())
+            hw = feat.shape[1] * feat.shape[2]
+            pooled = self._buf('pooled', (n, 2048))
+            ops.avgpool(feat.view(n, hw, 2048), pooled)
+            if self.label_table is None:
+                if self.dtype == torch.float32:
+                    ops.gemm(pooled, self.Wg, start[i0:i0 + n], bias=self.bg)
+                else:
+                    ops.gemm(pooled, self.Wg, start[i0:i0 + n], bias=self.bg)
+            else:
+                cat = self._buf('cat', (n, 2 * E))
+                ops.gemm(pooled, self.Wg, cat[:, :E], bias=self.bg)
+                ops.embed_mean(self.label_table, labels[i0:i0 + n].contiguous(), cat[:, E:])
+                ops.gemm(cat, self.Wl, start[i0:i0 + n], bias=self.bl)
+            if self.spatial:
+                ops.gemm(feat.view(n * hw, 2048), self.Wsp, sp[i0 * 49:(i0 + n) * 49], bias=self.bsp)
+        return start, sp

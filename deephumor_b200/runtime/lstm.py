@@ -1,0 +1,129 @@
+"""LSTM decoder runtime: batched stochastic-beam generation and teacher-forced forward.
+
+Reference: models/rnn_models.py:28-46 (forward), :48-143 (generate); SURVEY.md Appendix A.2.
+Per layer the gate product is ONE contraction over K = in+H against [W_ih | W_hh] (bias = b_ih + b_hh), the
+cell update reads c through the beam-parent index (the reference's h/c regather, incl. its f // B misalignment,
+Q8, is folded into loads), and the loop has a fixed trip count with per-image frozen-at-break flags on the
+device, so there is no host synchronisation inside it (Q12).
+"""
+import torch
+
+from . import ops
+
+
+class LSTMDecoderRT:
+    def __init__(self, sd, prefix, dtype, device):
+        self.dtype, self.device = dtype, device
+        to = lambda t, dt=dtype: t.float().contiguous().to(device=device, dtype=dt)
+        self.table = to(sd[prefix + '.embedding.weight'])
+        self.V, self.E = self.table.shape
+        self.L = 0
+        self.Wcat, self.bias = [], []
+        while f'{prefix}.lstm.weight_ih_l{self.L}' in sd:
+            l = self.L
+            self.Wcat.append(to(torch.cat([sd[f'{prefix}.lstm.weight_ih_l{l}'].float(),
+                                           sd[f'{prefix}.lstm.weight_hh_l{l}'].float()], dim=1)))
+            self.bias.append(to(sd[f'{prefix}.lstm.bias_ih_l{l}'].float() + sd[f'{prefix}.lstm.bias_hh_l{l}'].float(),
+                                torch.float32))
+            self.L += 1
+        self.H = self.Wcat[0].shape[0] // 4
+        self.Wc, self.bc = to(sd[prefix + '.classifier.weight']), to(sd[prefix + '.classifier.bias'], torch.float32)
+        self.ldv = (self.V + 3) // 4 * 4
+
+    def _alloc(self, rows):
+        d, dev, H, E, L = self.dtype, self.device, self.H, self.E, self.L
+        ws = dict(
+            A=[torch.zeros(rows, (E if l == 0 else H) + H, dtype=d, device=dev) for l in range(L)],
+            gates=torch.empty(rows, 4 * H, dtype=torch.float32, device=dev),
+            c=[torch.zeros(L, rows, H, dtype=torch.float32, device=dev) for _ in range(2)],
+            hs=torch.zeros(L, rows, H, dtype=d, device=dev),
+            top=torch.empty(rows, H, dtype=d, device=dev),
+            logits=torch.empty(rows, self.ldv, dtype=torch.float32, device=dev))
+        return ws
+
+    def _step(self, ws, rows, cur, parent):
+        """One LSTM time step over `rows` rows; A[l][:, in:] must already hold the (gathered) recurrent h."""
+        L, H = self.L, self.H
+        for l in range(L):
+            A = ws['A'][l][:rows]
+            gates = ws['gates'][:rows]
+            ops.gemm(A, self.Wcat[l], gates, bias=self.bias[l])
+            nxt = ws['A'][l + 1][:rows, :H] if l + 1 < L else ws['top'][:rows]
+            ops.lstm_cell(gates, ws['c'][cur][l], parent, ws['c'][1 - cur][l][:rows], nxt, ws['hs'][l][:rows])
+        ops.gemm(ws['top'][:rows], self.Wc, ws['logits'][:rows, :self.V], bias=self.bc)
+
+    def _recur(self, ws, rows, parent):
+        """A[l][:, in:] <- hs[l][parent] for every layer (recurrent operand of the next step)."""
+        for l in range(self.L):
+            in_l = self.E if l == 0 else self.H
+            ops.gather_rows(ws['hs'][l], parent, ws['A'][l][:rows, in_l:])
+
+    def generate(self, start_emb, caption, max_len, temperature, beam_size, top_k, eos_index, unk_index, noise_mode,
+                 seed, image_base, pad_index=0):
+        """start_emb fp32 [N,E]; caption int32 [N or 1, p] or None -> (ids int64 [N,max_len], lengths int64 [N], status)."""
+        N, B, dev = start_emb.shape[0], beam_size, self.device
+        R = N * B
+        ws = self._alloc(max(R, N))
+        p0 = 0 if caption is None else caption.shape[1]
+        beam = ops.Beam(N, B, max(max_len, p0 + 1), dev)
+        ind = torch.empty(R, B, dtype=torch.int32, device=dev)
+        val = torch.empty(R, B, dtype=torch.float32, device=dev)
+        # ---- prefix phase: 1 row per image (rnn_models.py:73-81)
+        cur = 0
+        ops.gather_rows(start_emb, None, ws['A'][0][:N, :self.E])
+        for t in range(p0 + 1):
+            if t > 0:
+                tok = caption[:, t - 1].contiguous() if caption.shape[0] == N else caption[:, t - 1].expand(N).contiguous()
+                ops.gather_rows(self.table, tok, ws['A'][0][:N, :self.E])
+                self._recur(ws, N, None)
+            self._step(ws, N, cur, None)
+            cur = 1 - cur
+        ops.select_tokens(ws['logits'][:N, :self.V], self.V, B, top_k, temperature, unk_index, 1, noise_mode, seed,
+                          image_base, p0, None, ind, val, beam.status)
+        beam.init(ind, val, caption, eos_index, True)
+        # ---- beam phase (rnn_models.py:105-137): fixed trip count, frozen-at-break on the device
+        for i in range(p0 + 1, max_len):
+            ops.gather_rows(self.table, beam.last_tok, ws['A'][0][:R, :self.E])
+            self._recur(ws, R, beam.parent_state)
+            self._step(ws, R, cur, beam.parent_state)
+            cur = 1 - cur
+            ops.select_tokens(ws['logits'][:R, :self.V], self.V, B, top_k, temperature, unk_index, B, noise_mode, seed,
+                              image_base, i, beam.done, ind, val, beam.status)
+            beam.step(ind, val, i, max_len, eos_index, True, temperature, noise_mode, seed, image_base)
+        out_ids = torch.empty(N, max_len, dtype=torch.int64, device=dev)
+        out_len = torch.empty(N, dtype=torch.int64, device=dev)
+        beam.final(temperature, noise_mode, seed, image_base, max_len + 1, max(p0 + 1, max_len), pad_index,
+                   max(max_len, p0 + 1) if False else max_len, out_ids, out_len)
+        return out_ids, out_len, beam.status
+
+    def forward(self, image_emb, captions, lengths=None):
+        """Teacher-forced logits [N, max(lengths), V] fp32 (rnn_models.py:28-46; packed-sequence semantics, Q24)."""
+        N, T = captions.shape
+        dev, H = self.device, self.H
+        S = T + 1
+        if lengths is None:
+            lengths = torch.full((N,), S, dtype=torch.int64, device=dev)
+        lengths = lengths.to(dev)
+        tmax = int(lengths.max())
+        ws = self._alloc(N)
+        tops = torch.zeros(N, tmax, H, dtype=self.dtype, device=dev)
+        cap32 = captions.to(device=dev, dtype=torch.int32)
+        cur = 0
+        for t in range(tmax):
+            if t == 0:
+                ops.gather_rows(image_emb, None, ws['A'][0][:N, :self.E])
+            else:
+                ops.gather_rows(self.table, cap32[:, t - 1].contiguous(), ws['A'][0][:N, :self.E])
+                self._recur(ws, N, None)
+            L = self.L
+            for l in range(L):
+                ops.gemm(ws['A'][l][:N], self.Wcat[l], ws['gates'][:N], bias=self.bias[l])
+                nxt = ws['A'][l + 1][:N, :H] if l + 1 < L else tops[:, t]
+                ops.lstm_cell(ws['gates'][:N], ws['c'][cur][l], None, ws['c'][1 - cur][l][:N], nxt, ws['hs'][l][:N])
+            cur = 1 - cur
+        # pad_packed_sequence zero-fills outputs at t >= length before the classifier (rnn_models.py:41-44)
+        keep = (torch.arange(tmax, device=dev).unsqueeze(0) < lengths.unsqueeze(1)).unsqueeze(-1)
+        tops = tops * keep.to(tops.dtype)
+        logits = torch.empty(N, tmax, self.V, dtype=torch.float32, device=dev)
+        ops.gemm(tops.view(N * tmax, H), self.Wc, logits.view(N * tmax, self.V), bias=self.bc)
+        return logits

@@ -1,0 +1,193 @@
+"""Typed wrappers over the C ABI (include/deephumor_b200.h): torch tensors in, kernel launches out.
+
+torch is used for device memory and streams only; every call below launches hand-written CUDA from
+libdeephumor_sm100.so on torch's current stream.
+"""
+import torch
+
+from .._lib import LIB, BeamState, ptr, stream
+
+F32, BF16 = 0, 1
+NOISE = {'deterministic': 0, 'injected': 1}
+
+
+def code(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f'unsupported dtype {t.dtype}')
+
+
+def torch_dtype(c):
+    return torch.float32 if c == F32 else torch.bfloat16
+
+
+def _rows(t):
+    assert t.dim() == 2 and t.stride(1) == 1, 'expect a row-major 2-D view'
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def synth_images(out, seed, first_index):
+    n, _, size, _ = out.shape
+    assert out.is_contiguous() and out.dtype == torch.float32
+    LIB.call('dh_synth_images', ptr(out), seed, first_index, n, size, stream())
+
+
+def nchw_to_nhwc4(images, out, halo=0):
+    n, c, H, W = images.shape
+    assert c == 3 and images.is_contiguous() and images.dtype == torch.float32 and out.is_contiguous()
+    LIB.call('dh_nchw_to_nhwc4', ptr(images), ptr(out), n, H, W, halo, code(out), stream())
+
+
+def conv2d(x, w, bias, y, stride, pad, relu, residual=None):
+    """x [n,H,W,Cin], w [Cout,kh,kw,Cin], y [n,Ho,Wo,Cout] (all contiguous NHWC)."""
+    n, H, W, Cin = x.shape
+    Cout, kh, kw, _ = w.shape
+    assert x.is_contiguous() and w.is_contiguous() and y.is_contiguous() and w.shape[3] == Cin
+    if x.dtype == torch.float32:
+        LIB.call('dh_conv2d_f32', ptr(x), ptr(w), ptr(bias), ptr(residual), ptr(y), n, H, W, Cin, Cout, kh, kw,
+                 stride, pad, int(relu), stream())
+    else:
+        LIB.call('dh_conv2d_bf16', ptr(x), ptr(w), ptr(bias), ptr(residual), ptr(y), n, H, W, Cin, Cout, kh, kw,
+                 stride, pad, int(relu), stream())
+
+
+def maxpool3x3s2(x, y):
+    n, H, W, C = x.shape
+    LIB.call('dh_maxpool3x3s2', ptr(x), ptr(y), n, H, W, C, code(x), stream())
+
+
+def avgpool(x, out):
+    """x [n,HW,C] contiguous -> out [n,C] (row-major view)."""
+    n, HW, C = x.shape
+    assert x.is_contiguous()
+    LIB.call('dh_avgpool', ptr(x), ptr(out), _rows(out), n, HW, C, code(x), code(out), stream())
+
+
+def embed_mean(table, ids, out):
+    n, L = ids.shape
+    assert ids.dtype == torch.int64 and ids.is_contiguous()
+    LIB.call('dh_embed_mean', ptr(table), _rows(table), ptr(ids), L, ptr(out), _rows(out), n, table.shape[1],
+             code(table), code(out), stream())
+
+
+def gemm(A, W, out, bias=None, residual=None, relu=False):
+    """out[M,N] = act(A[M,K] @ W[N,K]^T + bias + residual).  fp32 operands -> FFMA check kernel (fp32 out);
+    bf16 operands -> tcgen05 kernel (out fp32 or bf16)."""
+    M, K = A.shape
+    N = W.shape[0]
+    assert W.shape[1] == K and out.shape[0] == M and out.shape[1] == N
+    if M == 0:
+        return
+    if A.dtype == torch.float32:
+        assert W.dtype == torch.float32 and out.dtype == torch.float32
+        assert residual is None or residual.dtype == torch.float32
+        LIB.call('dh_gemm_f32', ptr(A), _rows(A), ptr(W), _rows(W), ptr(bias), ptr(residual),
+                 0 if residual is None else _rows(residual), ptr(out), _rows(out), M, N, K, int(relu), stream())
+    else:
+        assert W.dtype == torch.bfloat16
+        LIB.call('dh_gemm_bf16', ptr(A), _rows(A), ptr(W), _rows(W), ptr(bias), ptr(residual),
+                 0 if residual is None else _rows(residual), 0 if residual is None else code(residual),
+                 ptr(out), _rows(out), code(out), M, N, K, int(relu), stream())
+
+
+def gather_rows(src, idx, dst, width=None):
+    """dst[r, :width] = src[idx[r] (or r), :width] with dtype conversion."""
+    rows = dst.shape[0]
+    width = dst.shape[1] if width is None else width
+    assert idx is None or idx.dtype == torch.int32
+    LIB.call('dh_gather_rows', ptr(src), _rows(src), src.shape[0], ptr(idx), ptr(dst), _rows(dst), rows, width,
+             code(src), code(dst), stream())
+
+
+def lstm_cell(gates, c_prev, parent, c_out, h_out0, h_out1):
+    rows, H4 = gates.shape
+    H = H4 // 4
+    assert gates.dtype == torch.float32 and c_out.is_contiguous() and (c_prev is None or c_prev.is_contiguous())
+    h = h_out0 if h_out0 is not None else h_out1
+    LIB.call('dh_lstm_cell', ptr(gates), _rows(gates), ptr(c_prev), ptr(parent), ptr(c_out),
+             ptr(h_out0), 0 if h_out0 is None else _rows(h_out0), ptr(h_out1), 0 if h_out1 is None else _rows(h_out1),
+             rows, H, code(h), stream())
+
+
+def add_layernorm(x, y, gamma, beta, out):
+    rows, D = x.shape
+    LIB.call('dh_add_layernorm', ptr(x), _rows(x), ptr(y), 0 if y is None else _rows(y), ptr(gamma), ptr(beta),
+             ptr(out), _rows(out), rows, D, code(x), stream())
+
+
+def xfmr_embed(tok_table, pos_table, start, rows_per_start, tokens, positions, pos_const, scale, out):
+    rows, D = out.shape
+    assert start.dtype == torch.float32 and tok_table.dtype == pos_table.dtype == out.dtype
+    LIB.call('dh_xfmr_embed', ptr(tok_table), ptr(pos_table), _rows(tok_table), ptr(start), _rows(start),
+             rows_per_start, ptr(tokens), ptr(positions), pos_const, float(scale), ptr(out), _rows(out), rows, D,
+             code(out), stream())
+
+
+def cast(src, dst):
+    assert src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel()
+    LIB.call('dh_cast', ptr(src), ptr(dst), src.numel(), code(src), code(dst), stream())
+
+
+def attention(q, K, V, out, n_heads, rows_per_image, slots, S_alloc, scale, src=None, slot_shared=False, n_keys=0,
+              causal_full=False, seq=None, seq_per_image=False, pad=0, enc_mask=None):
+    rows, D = q.shape
+    LIB.call('dh_attention', ptr(q), _rows(q), ptr(K), ptr(V), ptr(out), _rows(out), rows, D, n_heads, rows_per_image,
+             slots, S_alloc, ptr(src), int(slot_shared), n_keys, int(causal_full), ptr(seq),
+             0 if seq is None else _rows(seq), int(seq_per_image), pad, ptr(enc_mask), float(scale), code(q), stream())
+
+
+def enc_mask(spatial, mask):
+    rows, D = spatial.shape
+    LIB.call('dh_enc_mask', ptr(spatial), ptr(mask), rows, D, code(spatial), stream())
+
+
+def select_tokens(logits, V, beam, top_k, temperature, unk, rows_per_image, noise_mode, seed, image_base, step, done,
+                  ind, val, status):
+    rows = logits.shape[0]
+    assert logits.dtype == torch.float32
+    LIB.call('dh_select_tokens', ptr(logits), _rows(logits), rows, V, beam, top_k, float(temperature), unk,
+             rows_per_image, noise_mode, seed, image_base, step, ptr(done), ptr(ind), ptr(val), ptr(status), stream())
+
+
+class Beam:
+    """Device-side beam state for n_img images x beam rows (struct dh_beam_state)."""
+
+    def __init__(self, n_img, beam, seq_ld, device, kv_slots=0):
+        i32 = dict(dtype=torch.int32, device=device)
+        self.n_img, self.beam = n_img, beam
+        self.seq = torch.zeros(n_img * beam, seq_ld, **i32)
+        self.val = torch.zeros(n_img * beam, dtype=torch.float32, device=device)
+        self.ended = torch.zeros(n_img * beam, dtype=torch.uint8, device=device)
+        self.done = torch.zeros(n_img, dtype=torch.uint8, device=device)
+        self.final_len = torch.zeros(n_img, **i32)
+        self.last_tok = torch.zeros(n_img * beam, **i32)
+        self.parent_state = torch.zeros(n_img * beam, **i32)
+        self.src = torch.zeros(n_img * beam, kv_slots, **i32) if kv_slots else None
+        self.status = torch.zeros(1, **i32)
+        self.c = BeamState(ptr(self.seq), seq_ld, ptr(self.val), ptr(self.ended), ptr(self.done), ptr(self.final_len),
+                           ptr(self.last_tok), ptr(self.parent_state), ptr(self.src), kv_slots)
+
+    def init(self, ind0, val0, prefix, eos, lstm_semantics):
+        import ctypes
+        plen = 0 if prefix is None else prefix.shape[1]
+        LIB.call('dh_beam_init', ctypes.byref(self.c), ptr(ind0), ptr(val0), ptr(prefix),
+                 0 if prefix is None else prefix.stride(0), 1 if prefix is None else prefix.shape[0], plen,
+                 self.n_img, self.beam, eos, int(lstm_semantics), stream())
+
+    def step(self, new_ind, new_val, step, max_len, eos, lstm_semantics, temperature, noise_mode, seed, image_base):
+        import ctypes
+        LIB.call('dh_beam_step', ctypes.byref(self.c), ptr(new_ind), ptr(new_val), self.n_img, self.beam, step, max_len,
+                 eos, int(lstm_semantics), float(temperature), noise_mode, seed, image_base, stream())
+
+    def final(self, temperature, noise_mode, seed, image_base, final_step, len_if_running, pad, max_len, out_ids, out_len):
+        import ctypes
+        LIB.call('dh_beam_final', ctypes.byref(self.c), self.n_img, self.beam, float(temperature), noise_mode, seed,
+                 image_base, final_step, len_if_running, pad, max_len, ptr(out_ids), ptr(out_len), stream())
+
+
+def token_logprob(logits, targets, out):
+    rows, V = logits.shape
+    assert logits.dtype == torch.float32 and targets.dtype == torch.int64
+    LIB.call('dh_token_logprob', ptr(logits), _rows(logits), rows, V, ptr(targets), ptr(out), stream())

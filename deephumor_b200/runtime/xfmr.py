@@ -1,0 +1,172 @@
+"""Transformer decoder runtime: incremental (KV-cached) stochastic-beam generation and teacher-forced forward.
+
+Reference: models/transformers.py:432-490 / 694-738 (forward), :492-579 / 740-825 (generate);
+SURVEY.md Appendix A.3.  The reference re-runs the whole decoder every step; logits at position i depend only
+on tokens < i (Q14), so each step here processes ONE new position per row against a KV cache.  Beam reorder
+never copies the cache: a per-image slot table maps (beam, position) -> physical slot (dh_beam_step).
+Cross-attention K/V over the 49 spatial tokens are projected once per image and shared by its beams.
+"""
+import torch
+
+from . import ops
+
+
+class XfmrDecoderRT:
+    def __init__(self, sd, prefix, hp, cross, dtype, device):
+        self.dtype, self.device, self.cross = dtype, device, cross
+        self.D, self.n_heads, self.L = hp['hid_dim'], hp['n_heads'], hp['n_layers']
+        self.pad = hp['pad_index']
+        to = lambda t, dt=dtype: t.float().contiguous().to(device=device, dtype=dt)
+        f32 = torch.float32
+        self.tok, self.pos = to(sd[prefix + '.tok_embedding.weight']), to(sd[prefix + '.pos_embedding.weight'])
+        self.V = self.tok.shape[0]
+        self.scale = float(sd[prefix + '.scale'])
+        self.layers = []
+        for l in range(self.L):
+            q = f'{prefix}.layers.{l}'
+            lay = {}
+            for att in (('self_attn', 'enc_attn') if cross else ('self_attn',)):
+                for n in ('fc_q', 'fc_k', 'fc_v', 'fc_o'):
+                    lay[f'{att}.{n}.w'] = to(sd[f'{q}.{att}.{n}.weight'])
+                    lay[f'{att}.{n}.b'] = to(sd[f'{q}.{att}.{n}.bias'], f32)
+                lay[f'{att}.scale'] = float(sd[f'{q}.{att}.scale'])
+                lay[f'{att}_ln.g'] = to(sd[f'{q}.{att}_ln.weight'], f32)
+                lay[f'{att}_ln.b'] = to(sd[f'{q}.{att}_ln.bias'], f32)
+            for n in ('fc_1', 'fc_2'):
+                lay[f'pf.{n}.w'], lay[f'pf.{n}.b'] = to(sd[f'{q}.pf.{n}.weight']), to(sd[f'{q}.pf.{n}.bias'], f32)
+            lay['pf_ln.g'], lay['pf_ln.b'] = to(sd[f'{q}.pf_ln.weight'], f32), to(sd[f'{q}.pf_ln.bias'], f32)
+            self.layers.append(lay)
+        self.pf = self.layers[0]['pf.fc_1.w'].shape[0]
+        self.Wc, self.bc = to(sd[prefix + '.classifier.weight']), to(sd[prefix + '.classifier.bias'], f32)
+        self.ldv = (self.V + 3) // 4 * 4
+
+    # ------------------------------------------------------------------ shared layer pieces
+    def _cross_kv(self, spatial, n_img):
+        """K/V of the 49 spatial tokens per layer: [n_img*49, D] each + the any-zero-feature mask (Q16)."""
+        kv = []
+        for lay in self.layers:
+            K = torch.empty(n_img * 49, self.D, dtype=self.dtype, device=self.device)
+            V = torch.empty_like(K)
+            ops.gemm(spatial, lay['enc_attn.fc_k.w'], K, bias=lay['enc_attn.fc_k.b'])
+            ops.gemm(spatial, lay['enc_attn.fc_v.w'], V, bias=lay['enc_attn.fc_v.b'])
+            kv.append((K, V))
+        mask = torch.empty(n_img * 49, dtype=torch.uint8, device=self.device)
+        ops.enc_mask(spatial, mask)
+        return kv, mask
+
+    def _post_attn(self, lay, att, x, attn, tmp, rows):
+        """x <- LN(x + fc_o(attn))."""
+        ops.gemm(attn[:rows], lay[f'{att}.fc_o.w'], tmp[:rows], bias=lay[f'{att}.fc_o.b'], residual=x[:rows])
+        ops.add_layernorm(tmp[:rows], None, lay[f'{att}_ln.g'], lay[f'{att}_ln.b'], x[:rows])
+
+    def _ffn(self, lay, x, h1, tmp, rows):
+        ops.gemm(x[:rows], lay['pf.fc_1.w'], h1[:rows], bias=lay['pf.fc_1.b'], relu=True)
+        ops.gemm(h1[:rows], lay['pf.fc_2.w'], tmp[:rows], bias=lay['pf.fc_2.b'], residual=x[:rows])
+        ops.add_layernorm(tmp[:rows], None, lay['pf_ln.g'], lay['pf_ln.b'], x[:rows])
+
+    # ------------------------------------------------------------------ generation
+    def generate(self, start_emb, spatial, caption, max_len, temperature, beam_size, top_k, eos_index, unk_index,
+                 noise_mode, seed, image_base):
+        """start_emb fp32 [N,D]; spatial [N*49,D] (cross) or None; caption int32 [N or 1,p] or None."""
+        N, B, D, dev, dt = start_emb.shape[0], beam_size, self.D, self.device, self.dtype
+        R = N * B
+        p0 = 0 if caption is None else caption.shape[1]
+        S = max_len + 1                                          # cached positions 0..max_len
+        need = max(S, 49) if self.cross else S                   # reference pads to max(T+1, 49) (Q15, Q19)
+        if need > self.pos.shape[0]:
+            raise IndexError('index out of range in self')       # what nn.Embedding raises in the reference (Q19)
+        if caption is not None and caption.shape[0] != N:
+            caption = caption.expand(N, p0).contiguous()
+        rows_alloc = max(R, N)
+        x = torch.empty(rows_alloc, D, dtype=dt, device=dev)
+        qb = torch.empty_like(x)
+        attn = torch.empty_like(x)
+        tmp = torch.empty_like(x)
+        h1 = torch.empty(rows_alloc, self.pf, dtype=dt, device=dev)
+        logits = torch.empty(rows_alloc, self.ldv, dtype=torch.float32, device=dev)
+        Kc = [torch.zeros(R, S, D, dtype=dt, device=dev) for _ in range(self.L)]
+        Vc = [torch.zeros(R, S, D, dtype=dt, device=dev) for _ in range(self.L)]
+        xkv, emask = self._cross_kv(spatial, N) if self.cross else (None, None)
+        beam = ops.Beam(N, B, max_len, dev, kv_slots=S)
+        ind = torch.empty(R, B, dtype=torch.int32, device=dev)
+        val = torch.empty(R, B, dtype=torch.float32, device=dev)
+
+        def step(rows, rpi, pos, tokens, seq, src):
+            """One new position `pos` for `rows` rows (rpi rows per image)."""
+            ops.xfmr_embed(self.tok, self.pos, start_emb, rpi, tokens, None, pos, self.scale, x[:rows])
+            slot_stride = (B if rpi == 1 else 1)                 # prefix phase writes slot 0 of each image
+            for l, lay in enumerate(self.layers):
+                kdst = Kc[l].view(R * S, D)[pos::S * slot_stride][:rows]
+                vdst = Vc[l].view(R * S, D)[pos::S * slot_stride][:rows]
+                ops.gemm(x[:rows], lay['self_attn.fc_q.w'], qb[:rows], bias=lay['self_attn.fc_q.b'])
+                ops.gemm(x[:rows], lay['self_attn.fc_k.w'], kdst, bias=lay['self_attn.fc_k.b'])
+                ops.gemm(x[:rows], lay['self_attn.fc_v.w'], vdst, bias=lay['self_attn.fc_v.b'])
+                ops.attention(qb[:rows], Kc[l], Vc[l], attn[:rows], self.n_heads, rpi, B, S, lay['self_attn.scale'],
+                              src=src, slot_shared=(rpi == 1), n_keys=pos + 1, seq=seq, seq_per_image=False,
+                              pad=self.pad)
+                self._post_attn(lay, 'self_attn', x, attn, tmp, rows)
+                if self.cross:
+                    ops.gemm(x[:rows], lay['enc_attn.fc_q.w'], qb[:rows], bias=lay['enc_attn.fc_q.b'])
+                    ops.attention(qb[:rows], xkv[l][0], xkv[l][1], attn[:rows], self.n_heads, rpi, 1, 49,
+                                  lay['enc_attn.scale'], slot_shared=True, n_keys=49, enc_mask=emask)
+                    self._post_attn(lay, 'enc_attn', x, attn, tmp, rows)
+                self._ffn(lay, x, h1, tmp, rows)
+            ops.gemm(x[:rows], self.Wc, logits[:rows, :self.V], bias=self.bc)
+
+        # ---- prefix phase: positions 0..p0, one row per image (transformers.py:517-529)
+        for t in range(p0 + 1):
+            tok = None if t == 0 else caption[:, t - 1].contiguous()
+            step(N, 1, t, tok, caption, None)
+        ops.select_tokens(logits[:N, :self.V], self.V, B, top_k, temperature, unk_index, 1, noise_mode, seed,
+                          image_base, p0, None, ind, val, beam.status)
+        beam.init(ind, val, caption, eos_index, False)
+        # ---- beam phase: i = p0+1 .. max_len inclusive (Q10); fixed trip count, frozen-at-break on the device
+        for i in range(p0 + 1, max_len + 1):
+            step(R, B, i, beam.last_tok, beam.seq, beam.src)
+            ops.select_tokens(logits[:R, :self.V], self.V, B, top_k, temperature, unk_index, B, noise_mode, seed,
+                              image_base, i, beam.done, ind, val, beam.status)
+            beam.step(ind, val, i, max_len, eos_index, False, temperature, noise_mode, seed, image_base)
+        out_ids = torch.empty(N, max_len, dtype=torch.int64, device=dev)
+        out_len = torch.empty(N, dtype=torch.int64, device=dev)
+        beam.final(temperature, noise_mode, seed, image_base, max_len + 1, max_len, self.pad, max_len, out_ids, out_len)
+        return out_ids, out_len, beam.status
+
+    # ------------------------------------------------------------------ teacher-forced forward
+    def hidden(self, start_emb, spatial, captions):
+        """captions int64 [N,T] -> hidden [N*S, D] with S = T+1 (Base) or max(T+1, 49) (cross; Q15)."""
+        N, T = captions.shape
+        D, dev, dt = self.D, self.device, self.dtype
+        S = max(T + 1, 49) if self.cross else T + 1
+        if S > self.pos.shape[0]:
+            raise IndexError('index out of range in self')
+        toks = torch.full((N, S), self.pad, dtype=torch.int32, device=dev)     # column s = token feeding position s
+        toks[:, 1:T + 1] = captions.to(device=dev, dtype=torch.int32)
+        positions = torch.arange(S, dtype=torch.int32, device=dev).repeat(N)
+        keyseq = toks[:, 1:].contiguous()                                       # key t>=1 masked iff token t-1 == pad
+        rows = N * S
+        x = torch.empty(rows, D, dtype=dt, device=dev)
+        qb, kb, vb, attn, tmp = (torch.empty_like(x) for _ in range(5))
+        h1 = torch.empty(rows, self.pf, dtype=dt, device=dev)
+        ops.xfmr_embed(self.tok, self.pos, start_emb, S, toks.view(-1), positions, 0, self.scale, x)
+        xkv, emask = self._cross_kv(spatial, N) if self.cross else (None, None)
+        for l, lay in enumerate(self.layers):
+            ops.gemm(x, lay['self_attn.fc_q.w'], qb, bias=lay['self_attn.fc_q.b'])
+            ops.gemm(x, lay['self_attn.fc_k.w'], kb, bias=lay['self_attn.fc_k.b'])
+            ops.gemm(x, lay['self_attn.fc_v.w'], vb, bias=lay['self_attn.fc_v.b'])
+            ops.attention(qb, kb, vb, attn, self.n_heads, S, 1, S, lay['self_attn.scale'], slot_shared=True,
+                          causal_full=True, seq=keyseq, seq_per_image=True, pad=self.pad)
+            self._post_attn(lay, 'self_attn', x, attn, tmp, rows)
+            if self.cross:
+                ops.gemm(x, lay['enc_attn.fc_q.w'], qb, bias=lay['enc_attn.fc_q.b'])
+                ops.attention(qb, xkv[l][0], xkv[l][1], attn, self.n_heads, S, 1, 49, lay['enc_attn.scale'],
+                              slot_shared=True, n_keys=49, enc_mask=emask)
+                self._post_attn(lay, 'enc_attn', x, attn, tmp, rows)
+            self._ffn(lay, x, h1, tmp, rows)
+        return x, S
+
+    def forward(self, start_emb, spatial, captions):
+        N = captions.shape[0]
+        x, S = self.hidden(start_emb, spatial, captions)
+        logits = torch.empty(N, S, self.V, dtype=torch.float32, device=self.device)
+        ops.gemm(x, self.Wc, logits.view(N * S, self.V), bias=self.bc)
+        return logits

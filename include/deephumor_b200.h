@@ -1,0 +1,140 @@
+/* deephumor_b200.h -- C ABI of libdeephumor_sm100.so (hand-written sm_100a CUDA for the DeepHumor
+ * caption-generation path).
+ *
+ * The reference (ilya16/deephumor) has no FFI layer: its boundary for this path is the Python model-class
+ * API.  The classes in deephumor_b200/models mirror that API and bind the entry
+ * points below through ctypes (deephumor_b200/_lib.py); INTEGRATION.md shows the stub a maintainer of the
+ * reference would add.  Each entry cites the reference call site(s) it replaces, as
+ * /root/reference/deephumor/<file>:<line> (torchvision lines are site-packages/torchvision/models/resnet.py).
+ *
+ * Conventions: every pointer is a DEVICE pointer unless it is a struct passed by pointer (host); sizes are
+ * explicit; every launch goes to the given cudaStream_t; nothing allocates or frees caller memory; return
+ * value 0 = ok, negative = DH_ERR_*, positive = cudaError_t; dh_last_error() gives text for the calling
+ * thread.  dtype arguments are DH_F32 (fp32 check mode) or DH_BF16 (tensor-core mode).  Matrices are
+ * row-major with explicit leading dimensions in elements.
+ */
+#ifndef DEEPHUMOR_B200_H_
+#define DEEPHUMOR_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define DH_VERSION 100
+
+#define DH_OK 0
+#define DH_ERR_ARG (-1)
+#define DH_ERR_DEVICE (-2)
+#define DH_ERR_UNSUPPORTED (-3)
+
+#define DH_F32 0
+#define DH_BF16 1
+
+/* noise model of the stochastic decoder (models/beam.py:39-48 uses torch.multinomial == topk(p / Exp(1))) */
+#define DH_NOISE_DETERMINISTIC 0 /* q == 1: classical top-k / beam with the reference's scoring */
+#define DH_NOISE_INJECTED 1      /* counter-based Exp(1) noise keyed on (seed, image, step, call, row, col) */
+#define DH_CALL_TOKEN 0ull
+#define DH_CALL_PRUNE 1ull
+#define DH_CALL_FINAL 2ull
+
+/* bits OR-ed into the int status word by the decode kernels */
+#define DH_STATUS_EMPTY_ROW 1     /* a logits row was entirely filtered: the reference raises RuntimeError (beam.py:32-46) */
+#define DH_STATUS_TOO_MANY_TIES 2 /* more than 4096 values tie at the top-k threshold */
+
+const char* dh_last_error(void);
+int dh_version(void);
+int dh_check_device(int device);
+
+/* ------------------------------------------------------------------------------------------ synthetic inputs */
+/* images [count,3,size,size] fp32 keyed by GLOBAL image index (bit-identical to deephumor_b200/utils/synth.py). */
+int dh_synth_images(float* out_nchw, unsigned long long seed, long long first_index, int count, int size,
+                    cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------ encoder
+ * models/encoders.py:46-70 (ImageEncoder.forward), :96-106 (LabelEncoder), :129-144 (ImageLabelEncoder);
+ * torchvision resnet.py:143-163,266-279 (Bottleneck / trunk).  BN is folded into the conv weights by the
+ * host packer; activations are NHWC. */
+int dh_nchw_to_nhwc4(const float* images_nchw, void* out_nhwc4, int n, int H, int W, int halo, int dtype,
+                     cudaStream_t stream);
+/* fp32 check mode: y = act(conv(x, w) + bias + residual); w is [Cout][kh][kw][Cin], Cin % 4 == 0. */
+int dh_conv2d_f32(const float* x, const float* w, const float* bias, const float* residual, float* y, int n, int H,
+                  int W, int Cin, int Cout, int kh, int kw, int stride, int pad, int relu, cudaStream_t stream);
+int dh_maxpool3x3s2(const void* x, void* y, int n, int H, int W, int C, int dtype, cudaStream_t stream);
+int dh_avgpool(const void* x, void* out, long long ldo, int n, int HW, int C, int dtype, int out_dtype,
+               cudaStream_t stream);
+int dh_embed_mean(const void* table, long long ldt, const long long* ids, int L, void* out, long long ldo, int n, int E,
+                  int dtype, int out_dtype, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------ contractions
+ * C[M,N] = act(A[M,K] * W[N,K]^T + bias[N] + residual[M,N]).  Replaces every nn.Linear on the path
+ * (encoders.py:61,67,142; rnn_models.py:81,109; transformers.py:97,127,162-163,488,736) and, with [x|h]
+ * concatenated along K, the nn.LSTM gate products (rnn_models.py:80,108). */
+int dh_gemm_f32(const float* A, long long lda, const float* W, long long ldw, const float* bias, const float* residual,
+                long long ldr, float* C, long long ldc, int M, int N, int K, int relu, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------ row-wise kernels */
+int dh_gather_rows(const void* src, long long lds, long long n_src_rows, const int* idx, void* dst, long long ldd,
+                   int rows, int width, int src_dtype, int dst_dtype, cudaStream_t stream);
+/* nn.LSTM cell update, gate order i,f,g,o (rnn_models.py:23-24,80,108); c_prev rows read through parent[]
+ * which folds the beam reorder of rnn_models.py:135-137 into the load. */
+int dh_lstm_cell(const float* gates, long long ldg, const float* c_prev, const int* parent, float* c_out, void* h_out0,
+                 long long ldh0, void* h_out1, long long ldh1, int rows, int H, int dtype, cudaStream_t stream);
+/* out = LayerNorm(x + y), eps 1e-5 (transformers.py:360,368,375,627,634). y may be null. */
+int dh_add_layernorm(const void* x, long long ldx, const void* y, long long ldy, const float* gamma, const float* beta,
+                     void* out, long long ldo, int rows, int D, int dtype, cudaStream_t stream);
+/* (start_emb | tok_embedding[token]) / scale + pos_embedding[pos]  (transformers.py:455-470, 706-722). */
+int dh_xfmr_embed(const void* tok_table, const void* pos_table, long long ldt, const float* start, long long lds,
+                  int rows_per_start, const int* tokens, const int* positions, int pos_const, float scale, void* out,
+                  long long ldo, int rows, int D, int dtype, cudaStream_t stream);
+int dh_cast(const void* src, void* dst, long long n, int src_dtype, int dst_dtype, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------ attention
+ * MultiHeadAttentionLayer.forward core (transformers.py:100-121) on cached K/V: one call covers incremental
+ * self-attention with beam slot indirection, cross-attention over the 49 spatial tokens, and teacher-forced
+ * causal attention (causal_full).  See csrc/attention.cu for the addressing rules. */
+int dh_attention(const void* q, long long ldq, const void* K, const void* V, void* out, long long ldo, int rows, int D,
+                 int n_heads, int rows_per_image, int slots, int S_alloc, const int* src, int slot_shared, int n_keys,
+                 int causal_full, const int* seq, long long seq_ld, int seq_per_image, int pad,
+                 const unsigned char* enc_mask, float scale, int dtype, cudaStream_t stream);
+/* enc_mask[row] = any(spatial[row,:] == 0)  (transformers.py:480-481). */
+int dh_enc_mask(const void* spatial, unsigned char* mask, int rows, int D, int dtype, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------ selection / beam
+ * BeamSearchHelper (models/beam.py:32-108) and the generate() loops (rnn_models.py:84-143,
+ * transformers.py:531-579, 778-825), batched over images with per-image "frozen at break" semantics. */
+typedef struct dh_beam_state {
+  int* seq;               /* [n_img, beam, seq_ld] token ids */
+  long long seq_ld;
+  float* val;             /* [n_img, beam] cumulative scores */
+  unsigned char* ended;   /* [n_img, beam] */
+  unsigned char* done;    /* [n_img] image has hit the reference's `break` */
+  int* final_len;         /* [n_img] output length recorded at the break */
+  int* last_tok;          /* [n_img*beam] next input token per row */
+  int* parent_state;      /* [n_img*beam] row to gather recurrent state / KV from */
+  int* src;               /* [n_img, beam, S_alloc] KV-cache slot table, or NULL (LSTM) */
+  int S_alloc;
+} dh_beam_state;
+
+int dh_select_tokens(const float* logits, long long ld, int rows, int V, int beam, int top_k, float temperature, int unk,
+                     int rows_per_image, int noise_mode, unsigned long long seed, long long image_base, int step,
+                     const unsigned char* done, int* ind, float* val, int* status, cudaStream_t stream);
+int dh_beam_init(const dh_beam_state* st, const int* ind0, const float* val0, const int* prefix, long long prefix_ld,
+                 int prefix_rows, int prefix_len, int n_img, int beam, int eos, int lstm_semantics, cudaStream_t stream);
+int dh_beam_step(const dh_beam_state* st, const int* new_ind, const float* new_val, int n_img, int beam, int step,
+                 int max_len, int eos, int lstm_semantics, float temperature, int noise_mode, unsigned long long seed,
+                 long long image_base, cudaStream_t stream);
+int dh_beam_final(const dh_beam_state* st, int n_img, int beam, float temperature, int noise_mode,
+                  unsigned long long seed, long long image_base, int final_step, int len_if_running, int pad, int max_len,
+                  long long* out_ids, long long* out_len, cudaStream_t stream);
+/* log_softmax(logits)[target] per row (experiments/metrics.py:5). */
+int dh_token_logprob(const float* logits, long long ld, int rows, int V, const long long* targets, float* out,
+                     cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPHUMOR_B200_H_ */

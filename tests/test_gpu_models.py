@@ -1,0 +1,80 @@
+"""Model-level parity of the CUDA path (through the drop-in classes) in fp32 check mode:
+fixtures produced by the unmodified reference (tests/golden) + the live oracle on the same seeded inputs."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from deephumor_b200 import models
+from deephumor_b200.experiments import perplexity
+from oracle import model as omodel
+from tests import helpers as H
+
+CLS = {'lstm': models.CaptioningLSTM, 'lstm_labels': models.CaptioningLSTMWithLabels,
+       'xfmr_base': models.CaptioningTransformerBase, 'xfmr': models.CaptioningTransformer}
+DEV = 'cuda'
+
+
+def build(fx, precision='fp32'):
+    sd, imgs, labs, caps, lens = H.fixture_inputs(fx)
+    m = CLS[fx['kind']](**fx['hp'])
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval().set_precision(precision)
+    return m, sd, imgs, labs, caps, lens
+
+
+@pytest.mark.parametrize('tag', ['small', 'canon'])
+@pytest.mark.parametrize('kind', H.KINDS)
+def test_fp32_mode_matches_reference_fixture(kind, tag):
+    fx = H.load_fixture(tag, kind)
+    m, sd, imgs, labs, caps, lens = build(fx)
+    with torch.no_grad():
+        enc = m.encoder(imgs.cuda(), labs.cuda()) if kind == 'lstm_labels' else m.encoder(imgs.cuda())
+        emb = enc[0] if kind == 'xfmr' else enc
+        assert H.rel_err(emb, fx['emb']) < H.TOL_FP32
+        if kind == 'xfmr':
+            assert H.rel_err(enc[1], fx['spatial']) < H.TOL_FP32
+        args = (imgs.cuda(), caps[:, :-1].cuda(), lens.cuda()) + ((labs.cuda(),) if kind == 'lstm_labels' else ())
+        logits = m(*args)
+        assert tuple(logits.shape) == fx['logits_shape']
+        assert H.rel_err(logits[..., :fx['logits'].shape[-1]], fx['logits']) < H.TOL_FP32
+        T = min(logits.shape[1], caps.shape[1])
+        pp = float(perplexity(logits[:, :T], caps[:, :T].cuda(), lens.cuda()))
+        assert abs(pp - fx['perplexity']) / fx['perplexity'] < 1e-3
+        excused = []
+        for g in fx['gen']:
+            prefix = caps[:1, :g['prefix_len']] if g['prefix_len'] else None
+            kw = dict(caption=prefix, max_len=fx['max_len'], temperature=g['temperature'], beam_size=g['beam_size'],
+                      top_k=g['top_k'], noise=g['mode'], seed=g['noise_seed'])
+            out = m.generate(imgs.cuda(), labs.cuda(), **kw) if kind == 'lstm_labels' else m.generate(imgs.cuda(), **kw)
+            ids, ln = out
+            excused += H.compare_ids(ids, ln, g, f"{kind} {g['mode']} B={g['beam_size']} K={g['top_k']}")
+        assert len(excused) <= 2, f'too many near-tie excuses: {excused}'
+
+
+@pytest.mark.parametrize('kind', H.KINDS)
+def test_batch1_returns_reference_shape(kind):
+    fx = H.load_fixture('small', kind)
+    m, sd, imgs, labs, caps, lens = build(fx)
+    g = fx['gen'][0]
+    kw = dict(max_len=fx['max_len'], temperature=g['temperature'], beam_size=g['beam_size'], top_k=g['top_k'],
+              noise=g['mode'], seed=g['noise_seed'])
+    with torch.no_grad():
+        for n in range(2):
+            a = (imgs[n:n + 1].cuda(),) + ((labs[n:n + 1].cuda(),) if kind == 'lstm_labels' else ())
+            out = m.generate(*a, image_base=n, **kw)
+            assert out.dim() == 1 and out.dtype == torch.int64
+            if float(g['gaps'][n]) > H.NEAR_TIE:
+                assert out.cpu().tolist() == g['ids'][n, :int(g['lengths'][n])].tolist()
+
+
+def test_empty_row_raises_like_reference():
+    fx = H.load_fixture('small', 'lstm')
+    m, sd, imgs, *_ = build(fx)
+    with torch.no_grad():
+        m.decoder.classifier.bias[1] = 1e4          # <unk> always the arg-max; top_k=1 filters the whole row (Q3)
+        m.invalidate()
+        with pytest.raises(RuntimeError):
+            m.generate(imgs[:2].cuda(), max_len=6, beam_size=1, top_k=1, noise='deterministic')
+    with pytest.raises(AssertionError):
+        m.generate(imgs[:1].cuda(), beam_size=5, top_k=3)
