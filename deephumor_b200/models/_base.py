@@ -27,9 +27,9 @@ class RTModule(nn.Module):
     precision = DEFAULT_PRECISION
 
     def _rt_cache(self):
-        if '_rt' not in self.__dict__:
-            self.__dict__['_rt'] = {}
-        return self.__dict__['_rt']
+        if '_rt_store' not in self.__dict__:
+            self.__dict__['_rt_store'] = {}
+        return self.__dict__['_rt_store']
 
     def invalidate(self):
         """Drop packed weights (call after mutating parameters in place)."""

@@ -109,7 +109,8 @@ class EncoderRT:
         for i0 in range(0, N, self.chunk):
             img = images[i0:i0 + self.chunk]
             n = img.shape[0]
-            feat = self.trunk(img.contiguous())
+            with ops.PROFILE.range('encoder_trunk', 8.174e9 * n):
+                feat = self.trunk(img.contiguous())
             hw = feat.shape[1] * feat.shape[2]
             pooled = self._buf('pooled', (n, 2048))
             ops.avgpool(feat.view(n, hw, 2048), pooled)

@@ -50,7 +50,8 @@ class LSTMDecoderRT:
             ops.gemm(A, self.Wcat[l], gates, bias=self.bias[l])
             nxt = ws['A'][l + 1][:rows, :H] if l + 1 < L else ws['top'][:rows]
             ops.lstm_cell(gates, ws['c'][cur][l], parent, ws['c'][1 - cur][l][:rows], nxt, ws['hs'][l][:rows])
-        ops.gemm(ws['top'][:rows], self.Wc, ws['logits'][:rows, :self.V], bias=self.bc)
+        with ops.PROFILE.range('vocab_gemm', 2.0 * rows * self.V * H):
+            ops.gemm(ws['top'][:rows], self.Wc, ws['logits'][:rows, :self.V], bias=self.bc)
 
     def _recur(self, ws, rows, parent):
         """A[l][:, in:] <- hs[l][parent] for every layer (recurrent operand of the next step)."""
@@ -87,9 +88,10 @@ class LSTMDecoderRT:
             self._recur(ws, R, beam.parent_state)
             self._step(ws, R, cur, beam.parent_state)
             cur = 1 - cur
-            ops.select_tokens(ws['logits'][:R, :self.V], self.V, B, top_k, temperature, unk_index, B, noise_mode, seed,
-                              image_base, i, beam.done, ind, val, beam.status)
-            beam.step(ind, val, i, max_len, eos_index, True, temperature, noise_mode, seed, image_base)
+            with ops.PROFILE.range('select_beam'):
+                ops.select_tokens(ws['logits'][:R, :self.V], self.V, B, top_k, temperature, unk_index, B, noise_mode,
+                                  seed, image_base, i, beam.done, ind, val, beam.status)
+                beam.step(ind, val, i, max_len, eos_index, True, temperature, noise_mode, seed, image_base)
         out_ids = torch.empty(N, max_len, dtype=torch.int64, device=dev)
         out_len = torch.empty(N, dtype=torch.int64, device=dev)
         beam.final(temperature, noise_mode, seed, image_base, max_len + 1, max(p0 + 1, max_len), pad_index,

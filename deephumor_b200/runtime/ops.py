@@ -11,6 +11,48 @@ F32, BF16 = 0, 1
 NOISE = {'deterministic': 0, 'injected': 1}
 
 
+class _Profile:
+    """Optional CUDA-event ranges on torch's current stream (bench.py: per-stage time and the roofline kernel)."""
+
+    def __init__(self):
+        self.on, self.ev = False, []
+
+    def start(self):
+        self.on, self.ev = True, []
+
+    class _Range:
+        def __init__(self, prof, tag, flops):
+            self.prof, self.tag, self.flops = prof, tag, flops
+
+        def __enter__(self):
+            if self.prof.on:
+                self.e0 = torch.cuda.Event(enable_timing=True)
+                self.e1 = torch.cuda.Event(enable_timing=True)
+                self.e0.record()
+
+        def __exit__(self, *a):
+            if self.prof.on:
+                self.e1.record()
+                self.prof.ev.append((self.tag, self.e0, self.e1, self.flops))
+
+    def range(self, tag, flops=0.0):
+        return self._Range(self, tag, flops)
+
+    def stop(self):
+        """-> {tag: (count, total_ms, total_flops)}"""
+        self.on = False
+        torch.cuda.synchronize()
+        out = {}
+        for tag, e0, e1, fl in self.ev:
+            n, ms, f = out.get(tag, (0, 0.0, 0.0))
+            out[tag] = (n + 1, ms + e0.elapsed_time(e1), f + fl)
+        self.ev = []
+        return out
+
+
+PROFILE = _Profile()
+
+
 def code(t):
     if t.dtype == torch.float32:
         return F32

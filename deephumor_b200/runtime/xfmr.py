@@ -111,7 +111,8 @@ class XfmrDecoderRT:
                                   lay['enc_attn.scale'], slot_shared=True, n_keys=49, enc_mask=emask)
                     self._post_attn(lay, 'enc_attn', x, attn, tmp, rows)
                 self._ffn(lay, x, h1, tmp, rows)
-            ops.gemm(x[:rows], self.Wc, logits[:rows, :self.V], bias=self.bc)
+            with ops.PROFILE.range('vocab_gemm', 2.0 * rows * self.V * D):
+                ops.gemm(x[:rows], self.Wc, logits[:rows, :self.V], bias=self.bc)
 
         # ---- prefix phase: positions 0..p0, one row per image (transformers.py:517-529)
         for t in range(p0 + 1):
