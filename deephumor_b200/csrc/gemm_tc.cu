@@ -1,0 +1,478 @@
+// Tensor-core contraction kernel for sm_100a: C[M,N] = act(A[M,K] * W[N,K]^T + bias[N] + residual[M,N]).
+//
+// One persistent, warp-specialised kernel serves every nn.Linear on the caption path (vocab projection,
+// LSTM gate products, attention / FFN projections, embedding heads) and -- with the A operand fetched by
+// im2col-mode TMA straight from the NHWC activation tensor -- every convolution of the ResNet-50 trunk
+// (implicit GEMM: M = n*Ho*Wo output pixels, N = Cout, K = kh*kw*Cin; BN folded, bias/ReLU/residual fused).
+//
+//   warp 0 (1 lane)  : TMA producer.  A tile 128 x 64 bf16 and W tile BN x 64 bf16 per stage, 128B-swizzled,
+//                      completion on an mbarrier (cp.async.bulk.tensor, tiled or im2col mode).
+//   warp 1 (1 lane)  : MMA issuer.  tcgen05.mma.cta_group::1.kind::f16, UMMA 128 x BN x 16, fp32 accumulators
+//                      in TMEM, double-buffered (2 x BN columns) so the epilogue of tile i overlaps tile i+1.
+//   warp 2           : TMEM allocator / deallocator.
+//   warps 4..7       : epilogue.  tcgen05.ld (32 lanes x 32 columns per warp) -> padded smem transpose ->
+//                      coalesced 16 B global stores with bias / residual / ReLU, fp32 or bf16 output.
+//
+// Tiles are scheduled statically (tile = blockIdx.x + i * gridDim.x, n fastest so CTAs running together
+// share the A rows through L2); grid = min(tiles, #SMs).  M / N / K tails rely on TMA zero fill.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BK = 64;
+constexpr int kThreads = 256;
+constexpr int kStageLd = 36;             // floats per staged row (32 + 4: conflict-free for 16 B accesses)
+constexpr int kSmemBudget = 196608;      // bytes of A/B ring
+
+struct TcParams {
+  int M, N, K;
+  int m_blocks, n_blocks, k_chunks;
+  int conv;                               // 0: A via tiled TMA {K, M}; 1: A via im2col TMA {C, W, H, N}
+  int HoWo, Wo, c_chunks, kw, stride, pad;
+  const float* bias;
+  const void* res; long long ldr; int res_dtype;
+  void* out; long long ldc; int out_dtype;
+  int relu;
+  int* error;                             // device flag set before a watchdog trap
+};
+
+// ------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {
+      if (error) atomicExch(error, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w, int h,
+                                                int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile (rows of 64 bf16 = 128 B, 8-row atoms of 1024 B):
+// start address >> 4 | SBO = 1024 B (bits 32..45) | descriptor version 1 (bits 46..47) | SWIZZLE_128B (bits 61..63).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+}
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = bn.
+__device__ __forceinline__ uint32_t umma_idesc(int bn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int kStageBytes = (BM + BN) * BK * 2;
+  static constexpr int kStages = kSmemBudget / kStageBytes;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kStagingBytes = 4 * 32 * kStageLd * 4;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStagingBytes + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t ring = base;
+  float* staging = reinterpret_cast<float*>(gen_base + C::kStages * C::kStageBytes);
+  const uint32_t bars = base + C::kStages * C::kStageBytes + C::kStagingBytes;
+  // barrier slots (8 B each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]; then the TMEM base word
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (C::kStages + s); };
+  auto tfull_bar = [&](int s) { return bars + 8u * (2 * C::kStages + s); };
+  auto tempty_bar = [&](int s) { return bars + 8u * (2 * C::kStages + 2 + s); };
+  uint32_t* tmem_word = reinterpret_cast<uint32_t*>(gen_base + C::kStages * C::kStageBytes + C::kStagingBytes +
+                                                    8 * (2 * C::kStages + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  } else if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_word)),
+                 "r"((uint32_t)C::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_word);
+  const int tiles = p.m_blocks * p.n_blocks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================================================================== TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.n_blocks) * BM, n0 = (tile % p.n_blocks) * BN;
+        int img = 0, ph = 0, qw = 0;
+        if (p.conv) {
+          img = m0 / p.HoWo;
+          const int rem = m0 - img * p.HoWo;
+          ph = rem / p.Wo;
+          qw = rem - ph * p.Wo;
+        }
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, p.error, 1);
+          const uint32_t sa = ring + stage * C::kStageBytes, sb = sa + BM * BK * 2;
+          mbar_expect_tx(full_bar(stage), C::kStageBytes);
+          if (p.conv) {
+            const int tap = kc / p.c_chunks, c0 = (kc - tap * p.c_chunks) * BK;
+            const int r = tap / p.kw, s = tap - r * p.kw;
+            tma_load_im2col(sa, &map_a, full_bar(stage), c0, qw * p.stride - p.pad, ph * p.stride - p.pad, img,
+                            (uint16_t)s, (uint16_t)r);
+          } else {
+            tma_load_2d(sa, &map_a, full_bar(stage), kc * BK, m0);
+          }
+          tma_load_2d(sb, &map_b, full_bar(stage), kc * BK, n0);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================================================================== MMA issuer
+      const uint32_t idesc = umma_idesc(BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        mbar_wait(tempty_bar(as), ((it >> 1) & 1) ^ 1u, p.error, 2);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(full_bar(stage), phase, p.error, 3);
+          tc_fence_after();
+          const uint32_t sa = ring + stage * C::kStageBytes, sb = sa + BM * BK * 2;
+          const uint64_t da = umma_desc(sa), db = umma_desc(sb);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)   // +32 B per UMMA_K step inside the 128 B swizzle row
+            tc_mma(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
+          tc_commit(empty_bar(stage));         // frees the smem slot once these MMAs have read it
+          if (kc == p.k_chunks - 1) tc_commit(tfull_bar(as));
+          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================================================================= epilogue
+    const int ew = warp - 4;                      // == warp % 4: TMEM lane quadrant this warp may read
+    float* st = staging + ew * 32 * kStageLd;
+    const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+    const bool res_vec = p.res && (p.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const int m0 = (tile / p.n_blocks) * BM, n0 = (tile % p.n_blocks) * BN;
+      const int as = it & 1;
+      mbar_wait(tfull_bar(as), (it >> 1) & 1, p.error, 4);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        if (n0 + c * 32 >= p.N) break;
+        uint32_t v[32];
+        tc_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN + c * 32), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(st + lane * kStageLd + j * 4) =
+              make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                          __uint_as_float(v[4 * j + 3]));
+        __syncwarp();
+        const int col = n0 + c * 32 + (lane & 7) * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = i * 4 + (lane >> 3);
+          const long long row = (long long)m0 + ew * 32 + rl;
+          if (row >= p.M || col >= p.N) continue;
+          float4 a = *reinterpret_cast<const float4*>(st + rl * kStageLd + (lane & 7) * 4);
+          float x[4] = {a.x, a.y, a.z, a.w};
+          const int nv = min(4, p.N - col);
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (e < nv && p.bias) x[e] += __ldg(p.bias + col + e);
+          if (p.res) {
+            if (p.res_dtype == DH_F32) {
+              const float* rp = reinterpret_cast<const float*>(p.res) + row * p.ldr + col;
+              if (res_vec && nv == 4) {
+                float4 r4 = *reinterpret_cast<const float4*>(rp);
+                x[0] += r4.x; x[1] += r4.y; x[2] += r4.z; x[3] += r4.w;
+              } else {
+                for (int e = 0; e < nv; ++e) x[e] += rp[e];
+              }
+            } else {
+              const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + row * p.ldr + col;
+              if (res_vec && nv == 4) {
+                uint2 r2 = *reinterpret_cast<const uint2*>(rp);
+                __nv_bfloat162 lo = *reinterpret_cast<__nv_bfloat162*>(&r2.x), hi = *reinterpret_cast<__nv_bfloat162*>(&r2.y);
+                x[0] += __low2float(lo); x[1] += __high2float(lo); x[2] += __low2float(hi); x[3] += __high2float(hi);
+              } else {
+                for (int e = 0; e < nv; ++e) x[e] += __bfloat162float(rp[e]);
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
+          }
+          if (p.out_dtype == DH_F32) {
+            float* op = reinterpret_cast<float*>(p.out) + row * p.ldc + col;
+            if (vec_ok && nv == 4) *reinterpret_cast<float4*>(op) = make_float4(x[0], x[1], x[2], x[3]);
+            else for (int e = 0; e < nv; ++e) op[e] = x[e];
+          } else {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + col;
+            if (vec_ok && nv == 4) {
+              __nv_bfloat162 lo = __floats2bfloat162_rn(x[0], x[1]), hi = __floats2bfloat162_rn(x[2], x[3]);
+              uint2 o;
+              o.x = *reinterpret_cast<uint32_t*>(&lo);
+              o.y = *reinterpret_cast<uint32_t*>(&hi);
+              *reinterpret_cast<uint2*>(op) = o;
+            } else {
+              for (int e = 0; e < nv; ++e) op[e] = __float2bfloat16_rn(x[e]);
+            }
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::kTmemCols)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn g_encode_tiled = nullptr;
+EncodeIm2colFn g_encode_im2col = nullptr;
+int g_num_sms = 0;
+int* g_error_flag = nullptr;
+
+int tc_init() {
+  if (g_encode_tiled) return DH_OK;
+  cudaDriverEntryPointQueryResult q;
+  void* fn = nullptr;
+  DH_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  if (!fn || q != cudaDriverEntryPointSuccess) return dh_fail(DH_ERR_DEVICE, "cuTensorMapEncodeTiled unavailable", __FILE__, __LINE__);
+  void* fn2 = nullptr;
+  DH_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn2, cudaEnableDefault, &q));
+  if (!fn2 || q != cudaDriverEntryPointSuccess) return dh_fail(DH_ERR_DEVICE, "cuTensorMapEncodeIm2col unavailable", __FILE__, __LINE__);
+  int dev = 0;
+  DH_CUDA(cudaGetDevice(&dev));
+  DH_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  DH_CUDA(cudaMalloc(&g_error_flag, sizeof(int)));
+  DH_CUDA(cudaMemset(g_error_flag, 0, sizeof(int)));
+  g_encode_im2col = (EncodeIm2colFn)fn2;
+  g_encode_tiled = (EncodeTiledFn)fn;
+  return DH_OK;
+}
+
+// 2-D bf16 row-major [rows, cols] with leading dimension ld (elements); box = {64 cols, box_rows}, 128B swizzle.
+int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return dh_fail(DH_ERR_ARG, "cuTensorMapEncodeTiled rejected the operand (alignment / stride)", __FILE__, __LINE__);
+  return DH_OK;
+}
+
+template <int BN>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, TcParams& p, cudaStream_t s) {
+  using C = Cfg<BN>;
+  static bool attr = false;
+  if (!attr) {
+    DH_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr = true;
+  }
+  p.n_blocks = dh_cdiv(p.N, BN);
+  p.m_blocks = dh_cdiv(p.M, BM);
+  const int tiles = p.m_blocks * p.n_blocks;
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  gemm_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, s>>>(ma, mb, p);
+  DH_LAUNCH_OK();
+  return DH_OK;
+}
+
+int pick_bn(int M, int N) {
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  // prefer 256-wide tiles when that still gives every SM work
+  const long long t256 = (long long)dh_cdiv(M, BM) * dh_cdiv(N, 256);
+  return (t256 >= 2ll * (g_num_sms ? g_num_sms : 148) || N % 256 == 0 && t256 >= (g_num_sms ? g_num_sms : 148)) ? 256 : 128;
+}
+
+int dispatch(const CUtensorMap& ma, const void* W, long long ldw, TcParams& p, int bn, cudaStream_t s) {
+  CUtensorMap mb;
+  int rc = make_map_2d(&mb, W, p.N, p.K, ldw, bn);
+  if (rc) return rc;
+  p.error = g_error_flag;
+  if (bn == 64) return launch<64>(ma, mb, p, s);
+  if (bn == 128) return launch<128>(ma, mb, p, s);
+  return launch<256>(ma, mb, p, s);
+}
+
+}  // namespace
+
+extern "C" int dh_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const float* bias, const void* residual,
+                            long long ldr, int res_dtype, void* C, long long ldc, int out_dtype, int M, int N, int K, int relu,
+                            int tile_n, cudaStream_t stream) {
+  DH_ARG(A && W && C && M >= 0 && N > 0 && K > 0);
+  DH_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0);
+  DH_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0);
+  DH_ARG(out_dtype == DH_F32 || out_dtype == DH_BF16);
+  DH_ARG(!residual || res_dtype == DH_F32 || res_dtype == DH_BF16);
+  DH_ARG(tile_n == 0 || tile_n == 64 || tile_n == 128 || tile_n == 256);
+  if (M == 0) return DH_OK;
+  int rc = tc_init();
+  if (rc) return rc;
+  TcParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.k_chunks = dh_cdiv(K, BK);
+  p.conv = 0;
+  p.bias = bias; p.res = residual; p.ldr = ldr; p.res_dtype = res_dtype;
+  p.out = C; p.ldc = ldc; p.out_dtype = out_dtype; p.relu = relu;
+  CUtensorMap ma;
+  rc = make_map_2d(&ma, A, M, K, lda, BM);
+  if (rc) return rc;
+  return dispatch(ma, W, ldw, p, tile_n ? tile_n : pick_bn(M, N), stream);
+}
+
+// x [n,H,W,Cin] NHWC bf16 (Cin % 64 == 0), w [Cout][kh][kw][Cin] bf16 (BN folded), y [n,Ho,Wo,Cout] bf16.
+extern "C" int dh_conv2d_bf16(const void* x, const void* w, const float* bias, const void* residual, void* y, int n, int H,
+                              int W, int Cin, int Cout, int kh, int kw, int stride, int pad, int relu, int tile_n,
+                              cudaStream_t stream) {
+  DH_ARG(x && w && y && n >= 0 && Cin > 0 && Cin % 64 == 0 && Cout > 0 && Cout % 4 == 0 && stride > 0 && kh > 0 && kw > 0);
+  DH_ARG(((uintptr_t)x % 16) == 0 && ((uintptr_t)w % 16) == 0);
+  DH_ARG(tile_n == 0 || tile_n == 64 || tile_n == 128 || tile_n == 256);
+  if (n == 0) return DH_OK;
+  int rc = tc_init();
+  if (rc) return rc;
+  const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+  const long long M = (long long)n * Ho * Wo;
+  DH_ARG(M < (1ll << 31) && Ho > 0 && Wo > 0);
+  TcParams p{};
+  p.M = (int)M; p.N = Cout; p.K = kh * kw * Cin;
+  p.k_chunks = p.K / BK;
+  p.conv = 1; p.HoWo = Ho * Wo; p.Wo = Wo; p.c_chunks = Cin / BK; p.kw = kw; p.stride = stride; p.pad = pad;
+  p.bias = bias; p.res = residual; p.ldr = Cout; p.res_dtype = DH_BF16;
+  p.out = y; p.ldc = Cout; p.out_dtype = DH_BF16; p.relu = relu;
+  CUtensorMap ma;
+  cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+  int lower[2] = {-pad, -pad};
+  int upper[2] = {pad - (kw - 1), pad - (kh - 1)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = g_encode_im2col(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, lower, upper,
+                               (cuuint32_t)BK, (cuuint32_t)BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return dh_fail(DH_ERR_ARG, "cuTensorMapEncodeIm2col rejected the activation tensor", __FILE__, __LINE__);
+  return dispatch(ma, w, p.K, p, tile_n ? tile_n : pick_bn(p.M, Cout), stream);
+}
+
+// Non-zero after a watchdog trap inside gemm_tc_kernel: 1 producer, 2 MMA/accumulator, 3 MMA/operands, 4 epilogue.
+extern "C" int dh_tc_error_flag(int* out_host) {
+  DH_ARG(out_host);
+  *out_host = 0;
+  if (!g_error_flag) return DH_OK;
+  DH_CUDA(cudaMemcpy(out_host, g_error_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  return DH_OK;
+}

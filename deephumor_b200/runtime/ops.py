@@ -82,7 +82,7 @@ def nchw_to_nhwc4(images, out, halo=0):
     LIB.call('dh_nchw_to_nhwc4', ptr(images), ptr(out), n, H, W, halo, code(out), stream())
 
 
-def conv2d(x, w, bias, y, stride, pad, relu, residual=None):
+def conv2d(x, w, bias, y, stride, pad, relu, residual=None, tile_n=0):
     """x [n,H,W,Cin], w [Cout,kh,kw,Cin], y [n,Ho,Wo,Cout] (all contiguous NHWC)."""
     n, H, W, Cin = x.shape
     Cout, kh, kw, _ = w.shape
@@ -92,7 +92,20 @@ def conv2d(x, w, bias, y, stride, pad, relu, residual=None):
                  stride, pad, int(relu), stream())
     else:
         LIB.call('dh_conv2d_bf16', ptr(x), ptr(w), ptr(bias), ptr(residual), ptr(y), n, H, W, Cin, Cout, kh, kw,
-                 stride, pad, int(relu), stream())
+                 stride, pad, int(relu), tile_n, stream())
+
+
+def im2col_stem(images, A, kh, kw, stride, pad):
+    """images [n,3,H,W] fp32 NCHW -> A [n*Ho*Wo, Kp] bf16, k = (r*kw+s)*3 + c, zero padded."""
+    n, c, H, W = images.shape
+    assert c == 3 and images.is_contiguous() and images.dtype == torch.float32 and A.is_contiguous()
+    LIB.call('dh_im2col_stem', ptr(images), ptr(A), n, H, W, kh, kw, stride, pad, A.shape[1], stream())
+
+
+def im2col_nhwc(x, A, kh, kw, stride, pad):
+    n, H, W, C = x.shape
+    assert x.is_contiguous() and A.is_contiguous() and x.dtype == torch.bfloat16
+    LIB.call('dh_im2col_nhwc', ptr(x), ptr(A), n, H, W, C, kh, kw, stride, pad, stream())
 
 
 def maxpool3x3s2(x, y):
@@ -114,7 +127,7 @@ def embed_mean(table, ids, out):
              code(table), code(out), stream())
 
 
-def gemm(A, W, out, bias=None, residual=None, relu=False):
+def gemm(A, W, out, bias=None, residual=None, relu=False, tile_n=0):
     """out[M,N] = act(A[M,K] @ W[N,K]^T + bias + residual).  fp32 operands -> FFMA check kernel (fp32 out);
     bf16 operands -> tcgen05 kernel (out fp32 or bf16)."""
     M, K = A.shape
@@ -131,7 +144,7 @@ def gemm(A, W, out, bias=None, residual=None, relu=False):
         assert W.dtype == torch.bfloat16
         LIB.call('dh_gemm_bf16', ptr(A), _rows(A), ptr(W), _rows(W), ptr(bias), ptr(residual),
                  0 if residual is None else _rows(residual), 0 if residual is None else code(residual),
-                 ptr(out), _rows(out), code(out), M, N, K, int(relu), stream())
+                 ptr(out), _rows(out), code(out), M, N, K, int(relu), tile_n, stream())
 
 
 def gather_rows(src, idx, dst, width=None):
