@@ -15,7 +15,7 @@
 
 namespace {
 
-constexpr int kSelThreads = 256;
+constexpr int kSelThreads = 512;
 constexpr int kMaxBeam = 16;
 constexpr int kSurvCap = 4096;
 constexpr int kMaxSlots = 160;   // max cached positions per beam (S_alloc)
@@ -35,14 +35,40 @@ struct SelParams {
   int* status;
 };
 
+// Block-wide helpers (kSelThreads threads).
+__device__ __forceinline__ float block_max(float v, float* red, float* bcast) {
+  v = dh_warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) { float m = red[0]; for (int w = 1; w < kSelThreads / 32; ++w) m = fmaxf(m, red[w]); *bcast = m; }
+  __syncthreads();
+  return *bcast;
+}
+__device__ __forceinline__ float block_sum(float v, float* red, float* bcast) {
+  v = dh_warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) { float t = 0.f; for (int w = 0; w < kSelThreads / 32; ++w) t += red[w]; *bcast = t; }
+  __syncthreads();
+  return *bcast;
+}
+
+// One CTA per logits row, two streaming passes over the row (the second one hits L2), no row staging:
+//   pass 1  every thread keeps the maximum of its strided slice; the top_k-th largest of those kSelThreads
+//           distinct elements is a lower bound t0 of the row's k-th largest value;
+//   pass 2  elements >= t0 (a few more than top_k) are compacted into shared memory;
+//   then    the exact k-th largest (ties kept), the <unk> mask, softmax(l/T), the Exp(1)-race draw of B ids
+//           and the log_softmax scores are computed on that short list.
 __global__ void __launch_bounds__(kSelThreads) select_tokens_kernel(SelParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* vals = reinterpret_cast<float*>(smem_raw);                       // [V]
-  __shared__ unsigned int hist[256];
-  __shared__ unsigned int s_prefix, s_krem;
-  __shared__ int s_nsurv;
-  __shared__ int surv_idx[kSurvCap];
-  __shared__ float surv_score[kSurvCap];
+  int* surv_idx = reinterpret_cast<int*>(smem_raw);                  // [kSurvCap]
+  float* surv_val = reinterpret_cast<float*>(surv_idx + kSurvCap);   // [kSurvCap] raw logits
+  float* surv_score = surv_val + kSurvCap;                           // [kSurvCap]
+  __shared__ float lm[kSelThreads];
+  __shared__ int s_ncand, s_nsurv;
+  __shared__ float s_t0, s_kth;
   __shared__ float red_f[kSelThreads / 32];
   __shared__ int red_i[kSelThreads / 32];
   __shared__ float s_bcast;
@@ -53,49 +79,81 @@ __global__ void __launch_bounds__(kSelThreads) select_tokens_kernel(SelParams p)
   const int img = r / p.rpi;
   if (p.done && p.done[img]) return;
   const float* row = p.logits + (long long)r * p.ld;
-  for (int i = tid; i < p.V; i += kSelThreads) vals[i] = row[i];
-  if (tid == 0) { s_prefix = 0u; s_krem = (unsigned)p.top_k; s_nsurv = 0; }
-  __syncthreads();
+  const bool vec = (p.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.logits) & 15) == 0);
+  const int V4 = vec ? (p.V >> 2) : 0;
 
-  // ---- exact k-th largest by 4x8-bit radix select on the order-preserving key
-  for (int pass = 0; pass < 4; ++pass) {
-    const int shift = 24 - 8 * pass;
-    hist[tid] = 0u;
-    __syncthreads();
-    const unsigned int prefix = s_prefix;
-    const unsigned int mask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
-    for (int i = tid; i < p.V; i += kSelThreads) {
-      unsigned int k = order_key(vals[i]);
-      if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
-    }
-    __syncthreads();
-    if (tid == 0) {
-      unsigned int krem = s_krem, acc = 0u;
-      int bin = 255;
-      for (; bin > 0; --bin) {
-        if (acc + hist[bin] >= krem) break;
-        acc += hist[bin];
-      }
-      s_krem = krem - acc;
-      s_prefix = prefix | ((unsigned int)bin << shift);
-    }
-    __syncthreads();
+  // ---- pass 1: per-thread maximum
+  float mx = -INFINITY;
+  for (int i = tid; i < V4; i += kSelThreads) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(row) + i);
+    mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
   }
-  const unsigned int kth_key = s_prefix;
-
-  // ---- survivors: value >= k-th largest (ties kept) and id != <unk>
-  for (int i = tid; i < p.V; i += kSelThreads) {
-    if (order_key(vals[i]) >= kth_key && i != p.unk && vals[i] > -INFINITY) {
-      int slot = atomicAdd(&s_nsurv, 1);
-      if (slot < kSurvCap) surv_idx[slot] = i;
+  for (int i = V4 * 4 + tid; i < p.V; i += kSelThreads) mx = fmaxf(mx, row[i]);
+  lm[tid] = mx;
+  if (tid == 0) { s_ncand = 0; s_nsurv = 0; s_t0 = -INFINITY; }
+  __syncthreads();
+  if (p.top_k <= kSelThreads) {
+    int rank = 0;
+    for (int j = 0; j < kSelThreads; ++j) {
+      const float o = lm[j];
+      rank += (o > mx) || (o == mx && j < tid);
     }
+    if (rank == p.top_k - 1) s_t0 = mx;     // exactly one thread has this rank
   }
   __syncthreads();
-  int ns = s_nsurv;
-  if (ns > kSurvCap) {
+  const float t0 = s_t0;                     // -inf when top_k > kSelThreads (every finite element is a candidate)
+
+  // ---- pass 2: compact candidates
+  auto push = [&](float x, int i) {
+    if (x >= t0 && x > -INFINITY) {
+      const int slot = atomicAdd(&s_ncand, 1);
+      if (slot < kSurvCap) { surv_idx[slot] = i; surv_val[slot] = x; }
+    }
+  };
+  for (int i = tid; i < V4; i += kSelThreads) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(row) + i);
+    push(v.x, 4 * i); push(v.y, 4 * i + 1); push(v.z, 4 * i + 2); push(v.w, 4 * i + 3);
+  }
+  for (int i = V4 * 4 + tid; i < p.V; i += kSelThreads) push(row[i], i);
+  __syncthreads();
+  int nc = s_ncand;
+  if (nc > kSurvCap) {
     if (tid == 0) atomicOr(p.status, DH_STATUS_TOO_MANY_TIES);
-    ns = kSurvCap;
+    nc = kSurvCap;
   }
+
+  // ---- exact k-th largest among the candidates: #{> v} < top_k <= #{>= v}
+  if (tid == 0) s_kth = -INFINITY;           // fewer than top_k finite values: everything survives
+  __syncthreads();
+  for (int c = tid; c < nc; c += kSelThreads) {
+    const float v = surv_val[c];
+    int gt = 0, ge = 0;
+    for (int j = 0; j < nc; ++j) { const float o = surv_val[j]; gt += o > v; ge += o >= v; }
+    if (gt < p.top_k && p.top_k <= ge) s_kth = v;   // all writers hold the same value
+  }
+  __syncthreads();
+  const float kth = s_kth;
+  // ---- survivors: value >= k-th largest (ties kept) and id != <unk>; compact in place (stable order not needed:
+  //      every later choice is by (score desc, id asc))
+  // two-phase in-place compaction: read own slots first, then rewrite
+  const int per = (nc + kSelThreads - 1) / kSelThreads;
+  int my_n = 0;
+  int my_idx[8]; float my_val[8];
+  for (int q = 0; q < per && q < 8; ++q) {
+    const int c = tid + q * kSelThreads;
+    if (c < nc) {
+      const float v = surv_val[c]; const int id = surv_idx[c];
+      if (v >= kth && id != p.unk) { my_idx[my_n] = id; my_val[my_n] = v; ++my_n; }
+    }
+  }
+  __syncthreads();
+  for (int q = 0; q < my_n; ++q) {
+    const int slot = atomicAdd(&s_nsurv, 1);
+    surv_idx[slot] = my_idx[q];
+    surv_val[slot] = my_val[q];
+  }
+  __syncthreads();
+  const int ns = s_nsurv;
   if (ns == 0) {   // whole row filtered: torch.multinomial raises (Q3)
     if (tid == 0) atomicOr(p.status, DH_STATUS_EMPTY_ROW);
     if (tid < p.B) { p.ind[(long long)r * p.B + tid] = 0; p.val[(long long)r * p.B + tid] = 0.f; }
@@ -103,27 +161,16 @@ __global__ void __launch_bounds__(kSelThreads) select_tokens_kernel(SelParams p)
   }
 
   // ---- softmax(l / T) over survivors (everything else has p == 0 exactly)
-  float mx = -INFINITY;
-  for (int s = tid; s < ns; s += kSelThreads) mx = fmaxf(mx, vals[surv_idx[s]] / p.T);
-  mx = dh_warp_max(mx);
-  if (lane == 0) red_f[warp] = mx;
-  __syncthreads();
-  if (tid == 0) { float m = red_f[0]; for (int w = 1; w < kSelThreads / 32; ++w) m = fmaxf(m, red_f[w]); s_bcast = m; }
-  __syncthreads();
-  mx = s_bcast;
+  float m2 = -INFINITY;
+  for (int s = tid; s < ns; s += kSelThreads) m2 = fmaxf(m2, surv_val[s] / p.T);
+  m2 = block_max(m2, red_f, &s_bcast);
   float sum = 0.f;
   for (int s = tid; s < ns; s += kSelThreads) {
-    float e = expf(vals[surv_idx[s]] / p.T - mx);
+    const float e = expf(surv_val[s] / p.T - m2);
     surv_score[s] = e;
     sum += e;
   }
-  sum = dh_warp_sum(sum);
-  __syncthreads();
-  if (lane == 0) red_f[warp] = sum;
-  __syncthreads();
-  if (tid == 0) { float t = 0.f; for (int w = 0; w < kSelThreads / 32; ++w) t += red_f[w]; s_bcast = t; }
-  __syncthreads();
-  sum = s_bcast;
+  sum = block_sum(sum, red_f, &s_bcast);
   const unsigned long long rk = dh_noise_row_key(p.seed, (unsigned long long)(p.image_base + img), (unsigned long long)p.step,
                                                  DH_CALL_TOKEN, (unsigned long long)(r % p.rpi));
   for (int s = tid; s < ns; s += kSelThreads) {
@@ -159,7 +206,7 @@ __global__ void __launch_bounds__(kSelThreads) select_tokens_kernel(SelParams p)
         if (red_f[w] > b2 || (red_f[w] == b2 && id < i2)) { b2 = red_f[w]; s2 = s; i2 = id; }
       }
       pick_idx[j] = i2;
-      pick_logit[j] = vals[i2];
+      pick_logit[j] = surv_val[s2];
       surv_score[s2] = -2.f;   // taken
     }
     __syncthreads();
@@ -178,14 +225,14 @@ __global__ void __launch_bounds__(kSelThreads) select_tokens_kernel(SelParams p)
       ++next;
     }
     // score = log_softmax over the B picked (filtered, un-tempered) logits (Q4)
-    float m2 = -INFINITY;
-    for (int j = 0; j < p.B; ++j) m2 = fmaxf(m2, pick_logit[j]);
+    float m3 = -INFINITY;
+    for (int j = 0; j < p.B; ++j) m3 = fmaxf(m3, pick_logit[j]);
     float se = 0.f;
-    for (int j = 0; j < p.B; ++j) se += expf(pick_logit[j] - m2);
+    for (int j = 0; j < p.B; ++j) se += expf(pick_logit[j] - m3);
     float lse = logf(se);
     for (int j = 0; j < p.B; ++j) {
       p.ind[(long long)r * p.B + j] = pick_idx[j];
-      p.val[(long long)r * p.B + j] = pick_logit[j] - m2 - lse;
+      p.val[(long long)r * p.B + j] = pick_logit[j] - m3 - lse;
     }
   }
 }
@@ -396,12 +443,12 @@ extern "C" int dh_select_tokens(const float* logits, long long ld, int rows, int
   DH_ARG(logits && ind && val && status && rows >= 0 && V > 0);
   DH_ARG(beam >= 1 && beam <= kMaxBeam && top_k >= 1 && top_k <= V && beam <= top_k && temperature > 0.f);
   DH_ARG(rows_per_image >= 1 && (noise_mode == DH_NOISE_DETERMINISTIC || noise_mode == DH_NOISE_INJECTED));
+  DH_ARG(top_k <= kSelThreads || V <= kSurvCap);   // candidate list is bounded by per-thread maxima
   if (rows == 0) return DH_OK;
-  size_t smem = (size_t)V * sizeof(float);
-  DH_ARG(smem <= 180 * 1024);   // row staged in shared memory; V <= 46080
+  size_t smem = (size_t)kSurvCap * 12;
   static bool attr_set = false;
   if (!attr_set) {
-    DH_CUDA(cudaFuncSetAttribute(select_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
+    DH_CUDA(cudaFuncSetAttribute(select_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   SelParams p{logits, ld, rows, V, beam, top_k, unk, rows_per_image, temperature, noise_mode, seed, image_base, step,

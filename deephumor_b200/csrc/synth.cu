@@ -10,7 +10,12 @@ __global__ void synth_images_kernel(float* __restrict__ out, unsigned long long 
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long img = i / per_image, e = i % per_image;
     uint64_t key = dh_fold(dh_fold(dh_key0(seed), 0x494D47ull), (uint64_t)(first_index + img));
-    out[i] = dh_sym_uniform(key, (uint64_t)e, 1.7320508f);
+    // per-image, per-channel style (synth.py::image_style): gain = 1 + 0.75*s, offset = 0.5*s'
+    const uint64_t c = (uint64_t)(e / (per_image / 3));
+    const uint64_t skey = dh_fold(key, 0x5354594Cull);
+    const float gain = __fadd_rn(1.0f, __fmul_rn(0.75f, dh_sym_uniform(skey, c, 1.0f)));
+    const float offset = __fmul_rn(0.5f, dh_sym_uniform(skey, 3ull + c, 1.0f));
+    out[i] = __fadd_rn(__fmul_rn(dh_sym_uniform(key, (uint64_t)e, 1.7320508f), gain), offset);
   }
 }
 }  // namespace

@@ -42,6 +42,12 @@ class EncoderRT:
         p = prefix + '.resnet'
         mk = lambda conv, bn, s, pad, cin_pad=None: PackedConv(sd, conv, bn, s, pad, dtype, device, cin_pad)
         self.stem = mk(p + '.0', p + '.1', 2, 3, cin_pad=4)
+        if dtype == torch.bfloat16:
+            # tensor-core mode: stem as an explicit (r,s,c) gather + contraction, K = 147 zero-padded to 192
+            w, _ = _fold_bn(sd, p + '.0', p + '.1')
+            wp = torch.zeros(w.shape[0], 192)
+            wp[:, :147] = w.permute(0, 2, 3, 1).reshape(w.shape[0], 147)
+            self.stem_w = wp.contiguous().to(device=device, dtype=dtype)
         self.blocks = []
         for li, nblk in enumerate(RESNET_BLOCKS):
             for b in range(nblk):
@@ -86,9 +92,16 @@ class EncoderRT:
     def trunk(self, images):
         """images [n,3,224,224] fp32 NCHW (device) -> features [n,7,7,2048] NHWC in the storage dtype."""
         n, _, H, W = images.shape
-        x = self._buf('in', (n, H, W, 4))
-        ops.nchw_to_nhwc4(images, x, halo=0)
-        x = self._conv('stem', x, self.stem, True)
+        if self.dtype == torch.bfloat16:
+            Ho = (H + 6 - 7) // 2 + 1
+            A = self._buf('stemA', (n * Ho * Ho, 192))
+            ops.im2col_stem(images, A, 7, 7, 2, 3)
+            x = self._buf('stem', (n, Ho, Ho, 64))
+            ops.gemm(A, self.stem_w, x.view(n * Ho * Ho, 64), bias=self.stem.bias, relu=True)
+        else:
+            x = self._buf('in', (n, H, W, 4))
+            ops.nchw_to_nhwc4(images, x, halo=0)
+            x = self._conv('stem', x, self.stem, True)
         y = self._buf('pool', (n, x.shape[1] // 2, x.shape[2] // 2, 64))
         ops.maxpool3x3s2(x, y)
         x = y
