@@ -1,6 +1,7 @@
 // Shared helpers for libdeephumor_sm100.so (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -31,7 +32,9 @@ static inline int dh_cdiv(long long a, long long b) { return (int)((a + b - 1) /
 template <typename T> __device__ __forceinline__ float dh_to_f(T v);
 template <> __device__ __forceinline__ float dh_to_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ float dh_to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float dh_to_f<__half>(__half v) { return __half2float(v); }
 template <typename T> __device__ __forceinline__ T dh_from_f(float v);
+template <> __device__ __forceinline__ __half dh_from_f<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ float dh_from_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 dh_from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 

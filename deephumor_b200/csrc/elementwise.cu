@@ -193,6 +193,7 @@ __global__ void cast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, lo
   do {                                                                  \
     if ((dtype) == DH_F32) { using T = float; __VA_ARGS__; }            \
     else if ((dtype) == DH_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+    else if ((dtype) == DH_F16) { using T = __half; __VA_ARGS__; }      \
     else return dh_fail(DH_ERR_ARG, "dtype", __FILE__, __LINE__);       \
   } while (0)
 
@@ -306,6 +307,10 @@ extern "C" int dh_cast(const void* src, void* dst, long long n, int src_dtype, i
     cast_kernel<float, __nv_bfloat16><<<g, kThreads, 0, s>>>((const float*)src, (__nv_bfloat16*)dst, n);
   else if (src_dtype == DH_BF16 && dst_dtype == DH_F32)
     cast_kernel<__nv_bfloat16, float><<<g, kThreads, 0, s>>>((const __nv_bfloat16*)src, (float*)dst, n);
+  else if (src_dtype == DH_F32 && dst_dtype == DH_F16)
+    cast_kernel<float, __half><<<g, kThreads, 0, s>>>((const float*)src, (__half*)dst, n);
+  else if (src_dtype == DH_F16 && dst_dtype == DH_F32)
+    cast_kernel<__half, float><<<g, kThreads, 0, s>>>((const __half*)src, (float*)dst, n);
   else if (src_dtype == DH_F32 && dst_dtype == DH_F32)
     cast_kernel<float, float><<<g, kThreads, 0, s>>>((const float*)src, (float*)dst, n);
   else

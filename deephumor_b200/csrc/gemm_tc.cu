@@ -35,6 +35,7 @@ struct TcParams {
   const void* res; long long ldr; int res_dtype;
   void* out; long long ldc; int out_dtype;
   int relu;
+  int ab_dtype;                           // DH_BF16 or DH_F16 operands
   int* error;                             // device flag set before a watchdog trap
 };
 
@@ -122,9 +123,10 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
 }
-// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = bn.
-__device__ __forceinline__ uint32_t umma_idesc(int bn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// kind::f16 instruction descriptor: D fp32, A/B bf16 (format 1) or f16 (format 0), both K-major, M = 128, N = bn.
+__device__ __forceinline__ uint32_t umma_idesc(int bn, int ab_dtype) {
+  const uint32_t fmt = ab_dtype == DH_BF16 ? 1u : 0u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 template <int BN>
@@ -215,7 +217,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp == 1) {
     if (lane == 0) {
       // ===================================================================== MMA issuer
-      const uint32_t idesc = umma_idesc(BN);
+      const uint32_t idesc = umma_idesc(BN, p.ab_dtype);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -282,6 +284,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               } else {
                 for (int e = 0; e < nv; ++e) x[e] += rp[e];
               }
+            } else if (p.res_dtype == DH_F16) {
+              const __half* rp = reinterpret_cast<const __half*>(p.res) + row * p.ldr + col;
+              if (res_vec && nv == 4) {
+                uint2 r2 = *reinterpret_cast<const uint2*>(rp);
+                __half2 lo = *reinterpret_cast<__half2*>(&r2.x), hi = *reinterpret_cast<__half2*>(&r2.y);
+                x[0] += __low2float(lo); x[1] += __high2float(lo); x[2] += __low2float(hi); x[3] += __high2float(hi);
+              } else {
+                for (int e = 0; e < nv; ++e) x[e] += __half2float(rp[e]);
+              }
             } else {
               const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + row * p.ldr + col;
               if (res_vec && nv == 4) {
@@ -301,6 +312,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             float* op = reinterpret_cast<float*>(p.out) + row * p.ldc + col;
             if (vec_ok && nv == 4) *reinterpret_cast<float4*>(op) = make_float4(x[0], x[1], x[2], x[3]);
             else for (int e = 0; e < nv; ++e) op[e] = x[e];
+          } else if (p.out_dtype == DH_F16) {
+            __half* op = reinterpret_cast<__half*>(p.out) + row * p.ldc + col;
+            if (vec_ok && nv == 4) {
+              __half2 lo = __floats2half2_rn(x[0], x[1]), hi = __floats2half2_rn(x[2], x[3]);
+              uint2 o;
+              o.x = *reinterpret_cast<uint32_t*>(&lo);
+              o.y = *reinterpret_cast<uint32_t*>(&hi);
+              *reinterpret_cast<uint2*>(op) = o;
+            } else {
+              for (int e = 0; e < nv; ++e) op[e] = __float2half_rn(x[e]);
+            }
           } else {
             __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + col;
             if (vec_ok && nv == 4) {
@@ -363,12 +385,13 @@ int tc_init() {
 }
 
 // 2-D bf16 row-major [rows, cols] with leading dimension ld (elements); box = {64 cols, box_rows}, 128B swizzle.
-int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows, int dtype) {
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = g_encode_tiled(map, dtype == DH_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                              const_cast<void*>(ptr), dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return dh_fail(DH_ERR_ARG, "cuTensorMapEncodeTiled rejected the operand (alignment / stride)", __FILE__, __LINE__);
@@ -402,7 +425,7 @@ int pick_bn(int M, int N) {
 
 int dispatch(const CUtensorMap& ma, const void* W, long long ldw, TcParams& p, int bn, cudaStream_t s) {
   CUtensorMap mb;
-  int rc = make_map_2d(&mb, W, p.N, p.K, ldw, bn);
+  int rc = make_map_2d(&mb, W, p.N, p.K, ldw, bn, p.ab_dtype);
   if (rc) return rc;
   p.error = g_error_flag;
   if (bn == 64) return launch<64>(ma, mb, p, s);
@@ -412,14 +435,15 @@ int dispatch(const CUtensorMap& ma, const void* W, long long ldw, TcParams& p, i
 
 }  // namespace
 
-extern "C" int dh_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const float* bias, const void* residual,
-                            long long ldr, int res_dtype, void* C, long long ldc, int out_dtype, int M, int N, int K, int relu,
-                            int tile_n, cudaStream_t stream) {
+extern "C" int dh_gemm_tc(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias,
+                          const void* residual, long long ldr, int res_dtype, void* C, long long ldc, int out_dtype, int M, int N,
+                          int K, int relu, int tile_n, cudaStream_t stream) {
   DH_ARG(A && W && C && M >= 0 && N > 0 && K > 0);
   DH_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0);
   DH_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0);
-  DH_ARG(out_dtype == DH_F32 || out_dtype == DH_BF16);
-  DH_ARG(!residual || res_dtype == DH_F32 || res_dtype == DH_BF16);
+  DH_ARG(ab_dtype == DH_BF16 || ab_dtype == DH_F16);
+  DH_ARG(out_dtype == DH_F32 || out_dtype == DH_BF16 || out_dtype == DH_F16);
+  DH_ARG(!residual || res_dtype == DH_F32 || res_dtype == DH_BF16 || res_dtype == DH_F16);
   DH_ARG(tile_n == 0 || tile_n == 64 || tile_n == 128 || tile_n == 256);
   if (M == 0) return DH_OK;
   int rc = tc_init();
@@ -428,18 +452,20 @@ extern "C" int dh_gemm_bf16(const void* A, long long lda, const void* W, long lo
   p.M = M; p.N = N; p.K = K;
   p.k_chunks = dh_cdiv(K, BK);
   p.conv = 0;
+  p.ab_dtype = ab_dtype;
   p.bias = bias; p.res = residual; p.ldr = ldr; p.res_dtype = res_dtype;
   p.out = C; p.ldc = ldc; p.out_dtype = out_dtype; p.relu = relu;
   CUtensorMap ma;
-  rc = make_map_2d(&ma, A, M, K, lda, BM);
+  rc = make_map_2d(&ma, A, M, K, lda, BM, ab_dtype);
   if (rc) return rc;
   return dispatch(ma, W, ldw, p, tile_n ? tile_n : pick_bn(M, N), stream);
 }
 
-// x [n,H,W,Cin] NHWC bf16 (Cin % 64 == 0), w [Cout][kh][kw][Cin] bf16 (BN folded), y [n,Ho,Wo,Cout] bf16.
-extern "C" int dh_conv2d_bf16(const void* x, const void* w, const float* bias, const void* residual, void* y, int n, int H,
-                              int W, int Cin, int Cout, int kh, int kw, int stride, int pad, int relu, int tile_n,
-                              cudaStream_t stream) {
+// x [n,H,W,Cin] NHWC (Cin % 64 == 0), w [Cout][kh][kw][Cin] (BN folded), y [n,Ho,Wo,Cout]; all bf16 or all f16.
+extern "C" int dh_conv2d_tc(const void* x, const void* w, const float* bias, const void* residual, void* y, int n, int H,
+                            int W, int Cin, int Cout, int kh, int kw, int stride, int pad, int relu, int dtype, int tile_n,
+                            cudaStream_t stream) {
+  DH_ARG(dtype == DH_BF16 || dtype == DH_F16);
   DH_ARG(x && w && y && n >= 0 && Cin > 0 && Cin % 64 == 0 && Cout > 0 && Cout % 4 == 0 && stride > 0 && kh > 0 && kw > 0);
   DH_ARG(((uintptr_t)x % 16) == 0 && ((uintptr_t)w % 16) == 0);
   DH_ARG(tile_n == 0 || tile_n == 64 || tile_n == 128 || tile_n == 256);
@@ -453,15 +479,17 @@ extern "C" int dh_conv2d_bf16(const void* x, const void* w, const float* bias, c
   p.M = (int)M; p.N = Cout; p.K = kh * kw * Cin;
   p.k_chunks = p.K / BK;
   p.conv = 1; p.HoWo = Ho * Wo; p.Wo = Wo; p.c_chunks = Cin / BK; p.kw = kw; p.stride = stride; p.pad = pad;
-  p.bias = bias; p.res = residual; p.ldr = Cout; p.res_dtype = DH_BF16;
-  p.out = y; p.ldc = Cout; p.out_dtype = DH_BF16; p.relu = relu;
+  p.ab_dtype = dtype;
+  p.bias = bias; p.res = residual; p.ldr = Cout; p.res_dtype = dtype;
+  p.out = y; p.ldc = Cout; p.out_dtype = dtype; p.relu = relu;
   CUtensorMap ma;
   cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
   cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
   int lower[2] = {-pad, -pad};
   int upper[2] = {pad - (kw - 1), pad - (kh - 1)};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-  CUresult r = g_encode_im2col(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, lower, upper,
+  CUresult r = g_encode_im2col(&ma, dtype == DH_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                               const_cast<void*>(x), dims, strides, lower, upper,
                                (cuuint32_t)BK, (cuuint32_t)BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return dh_fail(DH_ERR_ARG, "cuTensorMapEncodeIm2col rejected the activation tensor", __FILE__, __LINE__);

@@ -7,7 +7,8 @@
 namespace {
 
 // A[m, k] with m = (img, oh, ow), k = (r*KW + s)*3 + c for k < 147, zero for 147 <= k < Kp.  One thread = 8 k's (16 B).
-__global__ void im2col_stem_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ A, int n, int H, int W, int Ho,
+template <typename T>
+__global__ void im2col_stem_kernel(const float* __restrict__ img, T* __restrict__ A, int n, int H, int W, int Ho,
                                    int Wo, int KH, int KW, int stride, int pad, int Kp) {
   const int chunks = Kp / 8;
   const long long total = (long long)n * Ho * Wo * chunks;
@@ -19,7 +20,7 @@ __global__ void im2col_stem_kernel(const float* __restrict__ img, __nv_bfloat16*
     long long t = m / Wo;
     const int oh = (int)(t % Ho);
     const int im = (int)(t / Ho);
-    __align__(16) __nv_bfloat16 v[8];
+    __align__(16) T v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int k = ch * 8 + e;
@@ -30,7 +31,7 @@ __global__ void im2col_stem_kernel(const float* __restrict__ img, __nv_bfloat16*
         const int ih = oh * stride + r - pad, iw = ow * stride + s - pad;
         if (ih >= 0 && ih < H && iw >= 0 && iw < W) x = __ldg(img + (((long long)im * 3 + c) * H + ih) * W + iw);
       }
-      v[e] = __float2bfloat16_rn(x);
+      v[e] = dh_from_f<T>(x);
     }
     *reinterpret_cast<uint4*>(A + m * Kp + ch * 8) = *reinterpret_cast<const uint4*>(v);
   }
@@ -68,12 +69,17 @@ inline int grid_for(long long items) {
 }  // namespace
 
 extern "C" int dh_im2col_stem(const float* images_nchw, void* A, int n, int H, int W, int kh, int kw, int stride, int pad,
-                              int k_padded, cudaStream_t s) {
+                              int k_padded, int out_dtype, cudaStream_t s) {
   DH_ARG(images_nchw && A && n >= 0 && k_padded % 8 == 0 && k_padded >= kh * kw * 3 && ((uintptr_t)A % 16) == 0);
   if (n == 0) return DH_OK;
   const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
   const long long total = (long long)n * Ho * Wo * (k_padded / 8);
-  im2col_stem_kernel<<<grid_for(total), 256, 0, s>>>(images_nchw, (__nv_bfloat16*)A, n, H, W, Ho, Wo, kh, kw, stride, pad, k_padded);
+  if (out_dtype == DH_BF16)
+    im2col_stem_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, s>>>(images_nchw, (__nv_bfloat16*)A, n, H, W, Ho, Wo, kh, kw, stride, pad, k_padded);
+  else if (out_dtype == DH_F16)
+    im2col_stem_kernel<__half><<<grid_for(total), 256, 0, s>>>(images_nchw, (__half*)A, n, H, W, Ho, Wo, kh, kw, stride, pad, k_padded);
+  else
+    return dh_fail(DH_ERR_ARG, "out_dtype", __FILE__, __LINE__);
   DH_LAUNCH_OK();
   return DH_OK;
 }

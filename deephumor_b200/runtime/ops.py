@@ -7,7 +7,7 @@ import torch
 
 from .._lib import LIB, BeamState, ptr, stream
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 NOISE = {'deterministic': 0, 'injected': 1}
 
 
@@ -58,11 +58,13 @@ def code(t):
         return F32
     if t.dtype == torch.bfloat16:
         return BF16
+    if t.dtype == torch.float16:
+        return F16
     raise TypeError(f'unsupported dtype {t.dtype}')
 
 
 def torch_dtype(c):
-    return torch.float32 if c == F32 else torch.bfloat16
+    return {F32: torch.float32, BF16: torch.bfloat16, F16: torch.float16}[c]
 
 
 def _rows(t):
@@ -91,20 +93,21 @@ def conv2d(x, w, bias, y, stride, pad, relu, residual=None, tile_n=0):
         LIB.call('dh_conv2d_f32', ptr(x), ptr(w), ptr(bias), ptr(residual), ptr(y), n, H, W, Cin, Cout, kh, kw,
                  stride, pad, int(relu), stream())
     else:
-        LIB.call('dh_conv2d_bf16', ptr(x), ptr(w), ptr(bias), ptr(residual), ptr(y), n, H, W, Cin, Cout, kh, kw,
-                 stride, pad, int(relu), tile_n, stream())
+        assert x.dtype == w.dtype == y.dtype and (residual is None or residual.dtype == x.dtype)
+        LIB.call('dh_conv2d_tc', ptr(x), ptr(w), ptr(bias), ptr(residual), ptr(y), n, H, W, Cin, Cout, kh, kw,
+                 stride, pad, int(relu), code(x), tile_n, stream())
 
 
 def im2col_stem(images, A, kh, kw, stride, pad):
     """images [n,3,H,W] fp32 NCHW -> A [n*Ho*Wo, Kp] bf16, k = (r*kw+s)*3 + c, zero padded."""
     n, c, H, W = images.shape
     assert c == 3 and images.is_contiguous() and images.dtype == torch.float32 and A.is_contiguous()
-    LIB.call('dh_im2col_stem', ptr(images), ptr(A), n, H, W, kh, kw, stride, pad, A.shape[1], stream())
+    LIB.call('dh_im2col_stem', ptr(images), ptr(A), n, H, W, kh, kw, stride, pad, A.shape[1], code(A), stream())
 
 
 def im2col_nhwc(x, A, kh, kw, stride, pad):
     n, H, W, C = x.shape
-    assert x.is_contiguous() and A.is_contiguous() and x.dtype == torch.bfloat16
+    assert x.is_contiguous() and A.is_contiguous() and x.dtype in (torch.bfloat16, torch.float16)
     LIB.call('dh_im2col_nhwc', ptr(x), ptr(A), n, H, W, C, kh, kw, stride, pad, stream())
 
 
@@ -129,7 +132,7 @@ def embed_mean(table, ids, out):
 
 def gemm(A, W, out, bias=None, residual=None, relu=False, tile_n=0):
     """out[M,N] = act(A[M,K] @ W[N,K]^T + bias + residual).  fp32 operands -> FFMA check kernel (fp32 out);
-    bf16 operands -> tcgen05 kernel (out fp32 or bf16)."""
+    bf16 / f16 operands -> tcgen05 kernel (out fp32, bf16 or f16)."""
     M, K = A.shape
     N = W.shape[0]
     assert W.shape[1] == K and out.shape[0] == M and out.shape[1] == N
@@ -141,8 +144,8 @@ def gemm(A, W, out, bias=None, residual=None, relu=False, tile_n=0):
         LIB.call('dh_gemm_f32', ptr(A), _rows(A), ptr(W), _rows(W), ptr(bias), ptr(residual),
                  0 if residual is None else _rows(residual), ptr(out), _rows(out), M, N, K, int(relu), stream())
     else:
-        assert W.dtype == torch.bfloat16
-        LIB.call('dh_gemm_bf16', ptr(A), _rows(A), ptr(W), _rows(W), ptr(bias), ptr(residual),
+        assert W.dtype == A.dtype
+        LIB.call('dh_gemm_tc', ptr(A), _rows(A), ptr(W), _rows(W), code(A), ptr(bias), ptr(residual),
                  0 if residual is None else _rows(residual), 0 if residual is None else code(residual),
                  ptr(out), _rows(out), code(out), M, N, K, int(relu), tile_n, stream())
 

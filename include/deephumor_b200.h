@@ -24,7 +24,7 @@ extern "C" {
 typedef struct CUstream_st* cudaStream_t;
 #endif
 
-#define DH_VERSION 101
+#define DH_VERSION 102
 
 #define DH_OK 0
 #define DH_ERR_ARG (-1)
@@ -33,6 +33,7 @@ typedef struct CUstream_st* cudaStream_t;
 
 #define DH_F32 0
 #define DH_BF16 1
+#define DH_F16 2
 
 /* noise model of the stochastic decoder (models/beam.py:39-48 uses torch.multinomial == topk(p / Exp(1))) */
 #define DH_NOISE_DETERMINISTIC 0 /* q == 1: classical top-k / beam with the reference's scoring */
@@ -76,19 +77,22 @@ int dh_embed_mean(const void* table, long long ldt, const long long* ids, int L,
 int dh_gemm_f32(const float* A, long long lda, const float* W, long long ldw, const float* bias, const float* residual,
                 long long ldr, float* C, long long ldc, int M, int N, int K, int relu, cudaStream_t stream);
 
-/* bf16 tensor-core mode (tcgen05 / TMEM / TMA, csrc/gemm_tc.cu): same contract, A and W bf16, fp32 accumulate,
- * residual and output fp32 or bf16.  tile_n = 0 lets the library pick the N tile (64 / 128 / 256). */
-int dh_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const float* bias, const void* residual,
-                 long long ldr, int res_dtype, void* C, long long ldc, int out_dtype, int M, int N, int K, int relu,
-                 int tile_n, cudaStream_t stream);
-/* Implicit-GEMM convolution (torchvision resnet.py:143-163 conv+BN+ReLU(+identity)): x NHWC bf16, Cin % 64 == 0,
- * w [Cout][kh][kw][Cin] bf16 with BN folded, residual / y NHWC bf16.  The A operand is fetched by im2col-mode TMA. */
-int dh_conv2d_bf16(const void* x, const void* w, const float* bias, const void* residual, void* y, int n, int H, int W,
-                   int Cin, int Cout, int kh, int kw, int stride, int pad, int relu, int tile_n, cudaStream_t stream);
-/* Explicit gathers: the C_in = 3 stem straight from the NCHW fp32 image into A[n*Ho*Wo, k_padded] bf16 with
+/* Tensor-core mode (tcgen05 / TMEM / TMA, csrc/gemm_tc.cu): same contract, A and W both ab_dtype (DH_BF16 or
+ * DH_F16), fp32 accumulate, residual and output DH_F32 / DH_BF16 / DH_F16.  tile_n = 0 lets the library pick the
+ * N tile (64 / 128 / 256). */
+int dh_gemm_tc(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias,
+               const void* residual, long long ldr, int res_dtype, void* C, long long ldc, int out_dtype, int M, int N,
+               int K, int relu, int tile_n, cudaStream_t stream);
+/* Implicit-GEMM convolution (torchvision resnet.py:143-163 conv+BN+ReLU(+identity)): x NHWC, Cin % 64 == 0,
+ * w [Cout][kh][kw][Cin] with BN folded, residual / y NHWC, all of dtype (DH_BF16 or DH_F16).  The A operand is
+ * fetched by im2col-mode TMA. */
+int dh_conv2d_tc(const void* x, const void* w, const float* bias, const void* residual, void* y, int n, int H, int W,
+                 int Cin, int Cout, int kh, int kw, int stride, int pad, int relu, int dtype, int tile_n,
+                 cudaStream_t stream);
+/* Explicit gathers: the C_in = 3 stem straight from the NCHW fp32 image into A[n*Ho*Wo, k_padded] (bf16 / f16) with
  * k = (r*kw + s)*3 + c (encoders.py:56 -> resnet.py:197 conv1), and a generic NHWC gather A[m, (r*kw+s)*C + c]. */
 int dh_im2col_stem(const float* images_nchw, void* A, int n, int H, int W, int kh, int kw, int stride, int pad,
-                   int k_padded, cudaStream_t stream);
+                   int k_padded, int out_dtype, cudaStream_t stream);
 int dh_im2col_nhwc(const void* x, void* A, int n, int H, int W, int C, int kh, int kw, int stride, int pad,
                    cudaStream_t stream);
 /* watchdog code left by gemm_tc_kernel before it traps (0 = none). */

@@ -61,37 +61,39 @@ CONV_SHAPES = [  # n, H, Cin, Cout, k, stride, pad
 ]
 
 
+@pytest.mark.parametrize('dt', [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize('n,H_,Cin,Cout,k,s,p', CONV_SHAPES)
-def test_conv2d_bf16_im2col_tma(n, H_, Cin, Cout, k, s, p):
-    x, w, b = bf(rnd(n, Cin, H_, H_, seed=1)), bf(rnd(Cout, Cin, k, k, seed=2, scale=0.05)), rnd(Cout, seed=3)
+def test_conv2d_tc_im2col_tma(n, H_, Cin, Cout, k, s, p, dt):
+    x, w, b = rnd(n, Cin, H_, H_, seed=1).to(dt), rnd(Cout, Cin, k, k, seed=2, scale=0.05).to(dt), rnd(Cout, seed=3)
     ref = F.conv2d(x.double(), w.double(), b.double(), s, p)
-    res = bf(rnd(*ref.shape, seed=4))
+    res = rnd(*ref.shape, seed=4).to(dt)
     ref = F.relu(ref + res.double()).float().permute(0, 2, 3, 1).contiguous()
     xd = x.permute(0, 2, 3, 1).contiguous().to(DEV)
     wd = w.permute(0, 2, 3, 1).contiguous().to(DEV)
     rd = res.permute(0, 2, 3, 1).contiguous().to(DEV)
-    y = torch.empty(ref.shape, dtype=torch.bfloat16, device=DEV)
+    y = torch.empty(ref.shape, dtype=dt, device=DEV)
     ops.conv2d(xd, wd, b.to(DEV), y, s, p, True, residual=rd)
-    assert H.rel_err(y.float(), ref) < 4e-3
+    assert H.rel_err(y.float(), ref) < (4e-3 if dt == torch.bfloat16 else 5e-4)
     # the explicit-gather route through the same contraction kernel must agree with the TMA route bit for bit
     Ho = ref.shape[1]
-    A = torch.empty(n * Ho * Ho, k * k * Cin, dtype=torch.bfloat16, device=DEV)
+    A = torch.empty(n * Ho * Ho, k * k * Cin, dtype=dt, device=DEV)
     ops.im2col_nhwc(xd, A, k, k, s, p)
-    y2 = torch.empty(n * Ho * Ho, Cout, dtype=torch.bfloat16, device=DEV)
+    y2 = torch.empty(n * Ho * Ho, Cout, dtype=dt, device=DEV)
     ops.gemm(A, wd.view(Cout, -1), y2, bias=b.to(DEV), residual=rd.view(-1, Cout), relu=True)
     assert torch.equal(y2.view_as(y), y)
 
 
-def test_stem_im2col_gemm():
+@pytest.mark.parametrize('dt', [torch.bfloat16, torch.float16])
+def test_stem_im2col_gemm(dt):
     n, H_ = 2, 64
     img = rnd(n, 3, H_, H_, seed=1)
     w, b = rnd(64, 3, 7, 7, seed=2, scale=0.1), rnd(64, seed=3)
     Ho = (H_ + 6 - 7) // 2 + 1
-    A = torch.empty(n * Ho * Ho, 192, dtype=torch.bfloat16, device=DEV)
+    A = torch.empty(n * Ho * Ho, 192, dtype=dt, device=DEV)
     ops.im2col_stem(img.to(DEV), A, 7, 7, 2, 3)
     wp = torch.zeros(64, 192)
     wp[:, :147] = w.permute(0, 2, 3, 1).reshape(64, 147)
-    y = torch.empty(n * Ho * Ho, 64, dtype=torch.bfloat16, device=DEV)
-    ops.gemm(A, bf(wp).to(DEV), y, bias=b.to(DEV), relu=True)
-    ref = F.relu(F.conv2d(bf(img).double(), bf(w).double(), b.double(), 2, 3)).float().permute(0, 2, 3, 1).reshape(-1, 64)
-    assert H.rel_err(y.float(), ref) < 4e-3
+    y = torch.empty(n * Ho * Ho, 64, dtype=dt, device=DEV)
+    ops.gemm(A, wp.to(dt).to(DEV), y, bias=b.to(DEV), relu=True)
+    ref = F.relu(F.conv2d(img.to(dt).double(), w.to(dt).double(), b.double(), 2, 3)).float().permute(0, 2, 3, 1).reshape(-1, 64)
+    assert H.rel_err(y.float(), ref) < (4e-3 if dt == torch.bfloat16 else 5e-4)
