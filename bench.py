@@ -187,6 +187,12 @@ def run_ours(args):
             dist.barrier()
         return float(ms.item()), _lib.LIB.launches - l0, prof
 
+    if args.profile_mode:       # under ncu: one warm-up + one step, nothing else
+        step(images, labels)
+        torch.cuda.synchronize()
+        step(images, labels)
+        torch.cuda.synchronize()
+        return
     for _ in range(max(args.warmup, 3)):
         step(images, labels)
     sampler = ClockSampler(local)
@@ -300,6 +306,7 @@ def main():
     ap.add_argument('--batch', type=int, default=0, help='override images per GPU')
     ap.add_argument('--cpu-images', type=int, default=8, help='bounded CPU sample size')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile-mode', action='store_true', help='1 warm-up + 1 step only (for ncu launch lists)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

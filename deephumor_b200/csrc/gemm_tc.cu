@@ -16,6 +16,7 @@
 // Tiles are scheduled statically (tile = blockIdx.x + i * gridDim.x, n fastest so CTAs running together
 // share the A rows through L2); grid = min(tiles, #SMs).  M / N / K tails rely on TMA zero fill.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -36,6 +37,8 @@ struct TcParams {
   void* out; long long ldc; int out_dtype;
   int relu;
   int ab_dtype;                           // DH_BF16 or DH_F16 operands
+  int tma_store;                          // 1: epilogue stages 128 B-wide row slabs in smem and stores them by TMA
+  int res_chunks;                         // > 0: residual added on the tensor core as BN/64 extra K chunks (R x I)
   int* error;                             // device flag set before a watchdog trap
 };
 
@@ -134,13 +137,15 @@ struct Cfg {
   static constexpr int kStageBytes = (BM + BN) * BK * 2;
   static constexpr int kStages = kSmemBudget / kStageBytes;
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kStagingBytes = 4 * 32 * kStageLd * 4;
+  static constexpr int kStagingBytes = 2 * BM * 128;   // two 128-row x 128 B slabs (TMA store) / transpose scratch
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStagingBytes + 256;
 };
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
+               const __grid_constant__ CUtensorMap map_i, const TcParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -160,6 +165,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    if (p.tma_store) tma_prefetch_desc(&map_c);
+    if (p.res_chunks) { tma_prefetch_desc(&map_r); tma_prefetch_desc(&map_i); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -212,6 +219,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tma_load_2d(sb, &map_b, full_bar(stage), kc * BK, n0);
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
+        // residual as extra K chunks: D += R[m0:m0+128, n0+64j : +64] x I[:, 64j : +64]^T  (exact in fp32 accumulate)
+        for (int j = 0; j < p.res_chunks; ++j) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, p.error, 1);
+          const uint32_t sa = ring + stage * C::kStageBytes, sb = sa + BM * BK * 2;
+          mbar_expect_tx(full_bar(stage), C::kStageBytes);
+          tma_load_2d(sa, &map_r, full_bar(stage), n0 + j * BK, m0);
+          tma_load_2d(sb, &map_i, full_bar(stage), j * BK, 0);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -226,7 +242,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_wait(tempty_bar(as), ((it >> 1) & 1) ^ 1u, p.error, 2);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
+        const int chunks = p.k_chunks + p.res_chunks;
+        for (int kc = 0; kc < chunks; ++kc) {
           mbar_wait(full_bar(stage), phase, p.error, 3);
           tc_fence_after();
           const uint32_t sa = ring + stage * C::kStageBytes, sb = sa + BM * BK * 2;
@@ -235,7 +252,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int k = 0; k < BK / 16; ++k)   // +32 B per UMMA_K step inside the 128 B swizzle row
             tc_mma(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
           tc_commit(empty_bar(stage));         // frees the smem slot once these MMAs have read it
-          if (kc == p.k_chunks - 1) tc_commit(tfull_bar(as));
+          if (kc == chunks - 1) tc_commit(tfull_bar(as));
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -243,6 +260,103 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp >= 4) {
     // ======================================================================= epilogue
     const int ew = warp - 4;                      // == warp % 4: TMEM lane quadrant this warp may read
+    if (p.tma_store) {
+      // ---- slab epilogue: each thread owns one accumulator row; a round covers 128 B of every row (32 fp32 or
+      // 64 half columns), written 128B-swizzled into one of two 16 KB slabs and stored by one TMA instruction.
+      const uint32_t slabs = base + C::kStages * C::kStageBytes;
+      const bool out32 = p.out_dtype == DH_F32;
+      const int cpr = out32 ? 32 : 64;
+      const int row_l = ew * 32 + lane;
+      const uint32_t swz = (uint32_t)(row_l & 7);
+      const bool elected = (warp == 4 && lane == 0);
+      const bool bias_vec = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+      uint32_t round_ctr = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        const int m0 = (tile / p.n_blocks) * BM, n0 = (tile % p.n_blocks) * BN;
+        const int as = it & 1;
+        mbar_wait(tfull_bar(as), (it >> 1) & 1, p.error, 4);
+        tc_fence_after();
+        const uint32_t tmem_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+        for (int rd = 0; rd < BN / 32; ++rd) {
+          const int col0 = n0 + rd * cpr;
+          if (rd * cpr >= BN || col0 >= p.N) break;
+          const uint32_t slab = slabs + (round_ctr & 1u) * (BM * 128);
+          if (elected && round_ctr >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const uint32_t srow = slab + (uint32_t)row_l * 128u;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (out32 && h == 1) break;
+            uint32_t v[32];
+            tc_ld32(tmem_row + (uint32_t)(rd * cpr + h * 32), v);
+            float x[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+            if (p.bias) {
+              const int cb = col0 + h * 32;
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                if (bias_vec && cb + 4 * g + 4 <= p.N) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cb + 4 * g));
+                  x[4 * g] += b4.x; x[4 * g + 1] += b4.y; x[4 * g + 2] += b4.z; x[4 * g + 3] += b4.w;
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e)
+                    if (cb + 4 * g + e < p.N) x[4 * g + e] += __ldg(p.bias + cb + 4 * g + e);
+                }
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+            }
+            if (out32) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (((uint32_t)j ^ swz) << 4)),
+                             "f"(x[4 * j]), "f"(x[4 * j + 1]), "f"(x[4 * j + 2]), "f"(x[4 * j + 3])
+                             : "memory");
+            } else {
+              uint32_t w[16];
+              if (p.out_dtype == DH_BF16) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  __nv_bfloat162 t = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
+                  w[j] = *reinterpret_cast<uint32_t*>(&t);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  __half2 t = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+                  w[j] = *reinterpret_cast<uint32_t*>(&t);
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (((uint32_t)(h * 4 + j) ^ swz) << 4)),
+                             "r"(w[4 * j]), "r"(w[4 * j + 1]), "r"(w[4 * j + 2]), "r"(w[4 * j + 3])
+                             : "memory");
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (elected) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(&map_c)),
+                         "r"(slab), "r"(col0), "r"(m0)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          ++round_ctr;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+      }
+      if (elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    } else {
     float* st = staging + ew * 32 * kStageLd;
     const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
     const bool res_vec = p.res && (p.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0);
@@ -342,6 +456,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
     }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -364,6 +479,13 @@ EncodeTiledFn g_encode_tiled = nullptr;
 EncodeIm2colFn g_encode_im2col = nullptr;
 int g_num_sms = 0;
 int* g_error_flag = nullptr;
+void* g_identity[3] = {nullptr, nullptr, nullptr};   // [DH_BF16], [DH_F16]: 256 x 256 identity, row-major
+
+template <typename T>
+__global__ void identity_kernel(T* I, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * n) I[i] = dh_from_f<T>((i / n) == (i % n) ? 1.f : 0.f);
+}
 
 int tc_init() {
   if (g_encode_tiled) return DH_OK;
@@ -379,19 +501,26 @@ int tc_init() {
   DH_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   DH_CUDA(cudaMalloc(&g_error_flag, sizeof(int)));
   DH_CUDA(cudaMemset(g_error_flag, 0, sizeof(int)));
+  DH_CUDA(cudaMalloc(&g_identity[DH_BF16], 256 * 256 * 2));
+  DH_CUDA(cudaMalloc(&g_identity[DH_F16], 256 * 256 * 2));
+  identity_kernel<<<256, 256>>>((__nv_bfloat16*)g_identity[DH_BF16], 256);
+  identity_kernel<<<256, 256>>>((__half*)g_identity[DH_F16], 256);
+  DH_CUDA(cudaDeviceSynchronize());
   g_encode_im2col = (EncodeIm2colFn)fn2;
   g_encode_tiled = (EncodeTiledFn)fn;
   return DH_OK;
 }
 
-// 2-D bf16 row-major [rows, cols] with leading dimension ld (elements); box = {64 cols, box_rows}, 128B swizzle.
+// 2-D row-major [rows, cols] with leading dimension ld (elements); box = {128 B of columns, box_rows}, 128B swizzle.
 int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows, int dtype) {
+  const int esize = dtype == DH_F32 ? 4 : 2;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * esize};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esize), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode_tiled(map, dtype == DH_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
-                              const_cast<void*>(ptr), dims, strides, box, estr,
+  const CUtensorMapDataType ty = dtype == DH_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : dtype == DH_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = g_encode_tiled(map, ty, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return dh_fail(DH_ERR_ARG, "cuTensorMapEncodeTiled rejected the operand (alignment / stride)", __FILE__, __LINE__);
@@ -399,7 +528,8 @@ int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long col
 }
 
 template <int BN>
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, TcParams& p, cudaStream_t s) {
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mr, const CUtensorMap& mi,
+           TcParams& p, cudaStream_t s) {
   using C = Cfg<BN>;
   static bool attr = false;
   if (!attr) {
@@ -410,7 +540,8 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, TcParams& p, cudaStream
   p.m_blocks = dh_cdiv(p.M, BM);
   const int tiles = p.m_blocks * p.n_blocks;
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, s>>>(ma, mb, p);
+  if (p.res_chunks) p.res_chunks = BN / BK;
+  gemm_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, s>>>(ma, mb, mc, mr, mi, p);
   DH_LAUNCH_OK();
   return DH_OK;
 }
@@ -424,13 +555,32 @@ int pick_bn(int M, int N) {
 }
 
 int dispatch(const CUtensorMap& ma, const void* W, long long ldw, TcParams& p, int bn, cudaStream_t s) {
-  CUtensorMap mb;
+  CUtensorMap mb, mc = ma, mr = ma, mi = ma;
   int rc = make_map_2d(&mb, W, p.N, p.K, ldw, bn, p.ab_dtype);
   if (rc) return rc;
   p.error = g_error_flag;
-  if (bn == 64) return launch<64>(ma, mb, p, s);
-  if (bn == 128) return launch<128>(ma, mb, p, s);
-  return launch<256>(ma, mb, p, s);
+  // TMA-store epilogue when the output rows are 16 B aligned; the residual then rides the tensor core (R x I) if it
+  // has the operand dtype and 16 B aligned rows.  Anything else takes the direct-store epilogue.
+  const int osize = p.out_dtype == DH_F32 ? 4 : 2;
+  const bool out_ok = ((uintptr_t)p.out % 16 == 0) && ((p.ldc * osize) % 16 == 0) && !getenv("DH_TC_DIRECT_EPILOGUE");
+  const bool res_ok = !p.res || (p.res_dtype == p.ab_dtype && (uintptr_t)p.res % 16 == 0 && (p.ldr * 2) % 16 == 0);
+  p.tma_store = 0;
+  p.res_chunks = 0;
+  if (out_ok && res_ok) {
+    rc = make_map_2d(&mc, p.out, p.M, p.N, p.ldc, BM, p.out_dtype);
+    if (rc) return rc;
+    p.tma_store = 1;
+    if (p.res) {
+      rc = make_map_2d(&mr, p.res, p.M, p.N, p.ldr, BM, p.ab_dtype);
+      if (rc) return rc;
+      rc = make_map_2d(&mi, g_identity[p.ab_dtype], 256, 256, 256, bn, p.ab_dtype);
+      if (rc) return rc;
+      p.res_chunks = 1;   // launch<> sets BN / 64
+    }
+  }
+  if (bn == 64) return launch<64>(ma, mb, mc, mr, mi, p, s);
+  if (bn == 128) return launch<128>(ma, mb, mc, mr, mi, p, s);
+  return launch<256>(ma, mb, mc, mr, mi, p, s);
 }
 
 }  // namespace
