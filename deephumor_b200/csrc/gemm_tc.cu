@@ -138,7 +138,8 @@ struct Cfg {
   static constexpr int kStages = kSmemBudget / kStageBytes;
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kStagingBytes = 2 * BM * 128;   // two 128-row x 128 B slabs (TMA store) / transpose scratch
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStagingBytes + 256;
+  static constexpr int kBiasBytes = 1024;              // bias slice of the current tile (BN <= 256 floats)
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStagingBytes + kBiasBytes + 256;
 };
 
 template <int BN>
@@ -152,14 +153,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t ring = base;
   float* staging = reinterpret_cast<float*>(gen_base + C::kStages * C::kStageBytes);
-  const uint32_t bars = base + C::kStages * C::kStageBytes + C::kStagingBytes;
+  float* bias_s = reinterpret_cast<float*>(gen_base + C::kStages * C::kStageBytes + C::kStagingBytes);
+  const uint32_t bars = base + C::kStages * C::kStageBytes + C::kStagingBytes + C::kBiasBytes;
   // barrier slots (8 B each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]; then the TMEM base word
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (C::kStages + s); };
   auto tfull_bar = [&](int s) { return bars + 8u * (2 * C::kStages + s); };
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * C::kStages + 2 + s); };
   uint32_t* tmem_word = reinterpret_cast<uint32_t*>(gen_base + C::kStages * C::kStageBytes + C::kStagingBytes +
-                                                    8 * (2 * C::kStages + 4));
+                                                    C::kBiasBytes + 8 * (2 * C::kStages + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -269,7 +271,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int row_l = ew * 32 + lane;
       const uint32_t swz = (uint32_t)(row_l & 7);
       const bool elected = (warp == 4 && lane == 0);
-      const bool bias_vec = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
       uint32_t round_ctr = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
@@ -278,6 +279,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_wait(tfull_bar(as), (it >> 1) & 1, p.error, 4);
         tc_fence_after();
         const uint32_t tmem_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
+        // bias slice of this tile -> smem (all readers of the previous slice are past their last round barrier)
+        if (p.bias)
+          for (int i = row_l; i < BN; i += 128) bias_s[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
 #pragma unroll 1
         for (int rd = 0; rd < BN / 32; ++rd) {
           const int col0 = n0 + rd * cpr;
@@ -295,17 +299,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
             if (p.bias) {
-              const int cb = col0 + h * 32;
+              const float4* bs = reinterpret_cast<const float4*>(bias_s + rd * cpr + h * 32);   // warp-uniform: broadcast
 #pragma unroll
               for (int g = 0; g < 8; ++g) {
-                if (bias_vec && cb + 4 * g + 4 <= p.N) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cb + 4 * g));
-                  x[4 * g] += b4.x; x[4 * g + 1] += b4.y; x[4 * g + 2] += b4.z; x[4 * g + 3] += b4.w;
-                } else {
-#pragma unroll
-                  for (int e = 0; e < 4; ++e)
-                    if (cb + 4 * g + e < p.N) x[4 * g + e] += __ldg(p.bias + cb + 4 * g + e);
-                }
+                const float4 b4 = bs[g];
+                x[4 * g] += b4.x; x[4 * g + 1] += b4.y; x[4 * g + 2] += b4.z; x[4 * g + 3] += b4.w;
               }
             }
             if (p.relu) {

@@ -33,6 +33,7 @@ struct SelParams {
   const unsigned char* done;   // [n_img] rows of frozen images are skipped (may be null)
   int* ind; float* val;        // [R, B]
   int* status;
+  const long long* dyn;        // nullable: {seed, image_base} overriding the by-value fields
 };
 
 // Block-wide helpers (kSelThreads threads).
@@ -171,7 +172,9 @@ __global__ void __launch_bounds__(kSelThreads) select_tokens_kernel(SelParams p)
     sum += e;
   }
   sum = block_sum(sum, red_f, &s_bcast);
-  const unsigned long long rk = dh_noise_row_key(p.seed, (unsigned long long)(p.image_base + img), (unsigned long long)p.step,
+  const unsigned long long seed = p.dyn ? (unsigned long long)p.dyn[0] : p.seed;
+  const long long image_base = p.dyn ? p.dyn[1] : p.image_base;
+  const unsigned long long rk = dh_noise_row_key(seed, (unsigned long long)(image_base + img), (unsigned long long)p.step,
                                                  DH_CALL_TOKEN, (unsigned long long)(r % p.rpi));
   for (int s = tid; s < ns; s += kSelThreads) {
     float pr = surv_score[s] / sum;
@@ -276,7 +279,7 @@ __global__ void beam_init_kernel(BeamState st, const int* __restrict__ ind0, con
 struct StepParams {
   const int* new_ind; const float* new_val;   // [n_img*B, B]
   int n_img, B, step, max_len, eos, lstm_semantics;
-  float T; int noise_mode; unsigned long long seed; long long image_base;
+  float T; int noise_mode; unsigned long long seed; long long image_base; const long long* dyn;
 };
 
 __global__ void __launch_bounds__(32) beam_step_kernel(BeamState st, StepParams p) {
@@ -322,7 +325,9 @@ __global__ void __launch_bounds__(32) beam_step_kernel(BeamState st, StepParams 
   float sum = 0.f;
   for (int c = lane; c < N; c += 32) { float ex = expf(s_cval[c] / p.T - mx); s_score[c] = ex; sum += ex; }
   sum = dh_warp_sum(sum);
-  const unsigned long long rk = dh_noise_row_key(p.seed, (unsigned long long)(p.image_base + img), (unsigned long long)p.step,
+  const unsigned long long seed = p.dyn ? (unsigned long long)p.dyn[0] : p.seed;
+  const long long image_base = p.dyn ? p.dyn[1] : p.image_base;
+  const unsigned long long rk = dh_noise_row_key(seed, (unsigned long long)(image_base + img), (unsigned long long)p.step,
                                                  DH_CALL_PRUNE, 0ull);
   for (int c = lane; c < N; c += 32) {
     float pr = s_score[c] / sum;
@@ -380,7 +385,9 @@ __global__ void __launch_bounds__(32) beam_step_kernel(BeamState st, StepParams 
 __global__ void __launch_bounds__(32) beam_final_kernel(BeamState st, int n_img, int B, float T, int noise_mode,
                                                         unsigned long long seed, long long image_base, int final_step,
                                                         int len_if_running, int pad, int max_len,
-                                                        long long* __restrict__ out_ids, long long* __restrict__ out_len) {
+                                                        long long* __restrict__ out_ids, long long* __restrict__ out_len,
+                                                        const long long* __restrict__ dyn) {
+  if (dyn) { seed = (unsigned long long)dyn[0]; image_base = dyn[1]; }
   const int img = blockIdx.x, lane = threadIdx.x;
   const long long base = (long long)img * B;
   float x = lane < B ? st.val[base + lane] / T : -INFINITY;
@@ -439,7 +446,8 @@ __global__ void __launch_bounds__(256) token_logprob_kernel(const float* __restr
 
 extern "C" int dh_select_tokens(const float* logits, long long ld, int rows, int V, int beam, int top_k, float temperature,
                                 int unk, int rows_per_image, int noise_mode, unsigned long long seed, long long image_base,
-                                int step, const unsigned char* done, int* ind, float* val, int* status, cudaStream_t s) {
+                                int step, const unsigned char* done, int* ind, float* val, int* status, const long long* dyn,
+                                cudaStream_t s) {
   DH_ARG(logits && ind && val && status && rows >= 0 && V > 0);
   DH_ARG(beam >= 1 && beam <= kMaxBeam && top_k >= 1 && top_k <= V && beam <= top_k && temperature > 0.f);
   DH_ARG(rows_per_image >= 1 && (noise_mode == DH_NOISE_DETERMINISTIC || noise_mode == DH_NOISE_INJECTED));
@@ -452,7 +460,7 @@ extern "C" int dh_select_tokens(const float* logits, long long ld, int rows, int
     attr_set = true;
   }
   SelParams p{logits, ld, rows, V, beam, top_k, unk, rows_per_image, temperature, noise_mode, seed, image_base, step,
-              done, ind, val, status};
+              done, ind, val, status, dyn};
   select_tokens_kernel<<<rows, kSelThreads, smem, s>>>(p);
   DH_LAUNCH_OK();
   return DH_OK;
@@ -484,11 +492,11 @@ extern "C" int dh_beam_init(const dh_beam_state* st, const int* ind0, const floa
 
 extern "C" int dh_beam_step(const dh_beam_state* st, const int* new_ind, const float* new_val, int n_img, int beam,
                             int step, int max_len, int eos, int lstm_semantics, float temperature, int noise_mode,
-                            unsigned long long seed, long long image_base, cudaStream_t s) {
+                            unsigned long long seed, long long image_base, const long long* dyn, cudaStream_t s) {
   DH_ARG(check_state(st, n_img, beam) && new_ind && new_val && temperature > 0.f && step >= 1);
   DH_ARG(st->seq_ld >= max_len && (size_t)beam * st->seq_ld * sizeof(int) <= 40 * 1024);
   if (n_img == 0) return DH_OK;
-  StepParams p{new_ind, new_val, n_img, beam, step, max_len, eos, lstm_semantics, temperature, noise_mode, seed, image_base};
+  StepParams p{new_ind, new_val, n_img, beam, step, max_len, eos, lstm_semantics, temperature, noise_mode, seed, image_base, dyn};
   beam_step_kernel<<<n_img, 32, (size_t)beam * st->seq_ld * sizeof(int), s>>>(to_state(st), p);
   DH_LAUNCH_OK();
   return DH_OK;
@@ -496,11 +504,11 @@ extern "C" int dh_beam_step(const dh_beam_state* st, const int* new_ind, const f
 
 extern "C" int dh_beam_final(const dh_beam_state* st, int n_img, int beam, float temperature, int noise_mode,
                              unsigned long long seed, long long image_base, int final_step, int len_if_running, int pad,
-                             int max_len, long long* out_ids, long long* out_len, cudaStream_t s) {
+                             int max_len, long long* out_ids, long long* out_len, const long long* dyn, cudaStream_t s) {
   DH_ARG(check_state(st, n_img, beam) && out_ids && out_len && temperature > 0.f && max_len <= st->seq_ld);
   if (n_img == 0) return DH_OK;
   beam_final_kernel<<<n_img, 32, 0, s>>>(to_state(st), n_img, beam, temperature, noise_mode, seed, image_base, final_step,
-                                        len_if_running, pad, max_len, out_ids, out_len);
+                                        len_if_running, pad, max_len, out_ids, out_len, dyn);
   DH_LAUNCH_OK();
   return DH_OK;
 }

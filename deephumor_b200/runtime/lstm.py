@@ -29,6 +29,7 @@ class LSTMDecoderRT:
         self.H = self.Wcat[0].shape[0] // 4
         self.Wc, self.bc = to(sd[prefix + '.classifier.weight']), to(sd[prefix + '.classifier.bias'], torch.float32)
         self.ldv = (self.V + 3) // 4 * 4
+        self._plans = {}
 
     def _alloc(self, rows):
         d, dev, H, E, L = self.dtype, self.device, self.H, self.E, self.L
@@ -59,28 +60,28 @@ class LSTMDecoderRT:
             in_l = self.E if l == 0 else self.H
             ops.gather_rows(ws['hs'][l], parent, ws['A'][l][:rows, in_l:])
 
-    def generate(self, start_emb, caption, max_len, temperature, beam_size, top_k, eos_index, unk_index, noise_mode,
-                 seed, image_base, pad_index=0):
-        """start_emb fp32 [N,E]; caption int32 [N or 1, p] or None -> (ids int64 [N,max_len], lengths int64 [N], status)."""
-        N, B, dev = start_emb.shape[0], beam_size, self.device
+    def _decode(self, pl, p0, max_len, temperature, B, top_k, eos_index, unk_index, noise_mode, pad_index):
+        """Launches the whole decode (prefix phase, first selection, beam loop, final pick) on static buffers of plan
+        `pl`; fixed trip count and no host synchronisation, so it can be captured in a CUDA graph."""
+        ws, beam, ind, val, dyn, N = pl['ws'], pl['beam'], pl['ind'], pl['val'], pl['dyn'], pl['N']
+        start_emb, caption = pl['start'], pl['caption']
         R = N * B
-        ws = self._alloc(max(R, N))
-        p0 = 0 if caption is None else caption.shape[1]
-        beam = ops.Beam(N, B, max(max_len, p0 + 1), dev)
-        ind = torch.empty(R, B, dtype=torch.int32, device=dev)
-        val = torch.empty(R, B, dtype=torch.float32, device=dev)
+        beam.status.zero_()
+        for c in ws['c']:
+            c.zero_()
         # ---- prefix phase: 1 row per image (rnn_models.py:73-81)
         cur = 0
         ops.gather_rows(start_emb, None, ws['A'][0][:N, :self.E])
+        for l in range(self.L):
+            ws['A'][l][:N, (self.E if l == 0 else self.H):].zero_()
         for t in range(p0 + 1):
             if t > 0:
-                tok = caption[:, t - 1].contiguous() if caption.shape[0] == N else caption[:, t - 1].expand(N).contiguous()
-                ops.gather_rows(self.table, tok, ws['A'][0][:N, :self.E])
+                ops.gather_rows(self.table, caption[:, t - 1].contiguous(), ws['A'][0][:N, :self.E])
                 self._recur(ws, N, None)
             self._step(ws, N, cur, None)
             cur = 1 - cur
-        ops.select_tokens(ws['logits'][:N, :self.V], self.V, B, top_k, temperature, unk_index, 1, noise_mode, seed,
-                          image_base, p0, None, ind, val, beam.status)
+        ops.select_tokens(ws['logits'][:N, :self.V], self.V, B, top_k, temperature, unk_index, 1, noise_mode, 0, 0,
+                          p0, None, ind, val, beam.status, dyn)
         beam.init(ind, val, caption, eos_index, True)
         # ---- beam phase (rnn_models.py:105-137): fixed trip count, frozen-at-break on the device
         for i in range(p0 + 1, max_len):
@@ -90,13 +91,53 @@ class LSTMDecoderRT:
             cur = 1 - cur
             with ops.PROFILE.range('select_beam'):
                 ops.select_tokens(ws['logits'][:R, :self.V], self.V, B, top_k, temperature, unk_index, B, noise_mode,
-                                  seed, image_base, i, beam.done, ind, val, beam.status)
-                beam.step(ind, val, i, max_len, eos_index, True, temperature, noise_mode, seed, image_base)
-        out_ids = torch.empty(N, max_len, dtype=torch.int64, device=dev)
-        out_len = torch.empty(N, dtype=torch.int64, device=dev)
-        beam.final(temperature, noise_mode, seed, image_base, max_len + 1, max(p0 + 1, max_len), pad_index,
-                   max(max_len, p0 + 1) if False else max_len, out_ids, out_len)
-        return out_ids, out_len, beam.status
+                                  0, 0, i, beam.done, ind, val, beam.status, dyn)
+                beam.step(ind, val, i, max_len, eos_index, True, temperature, noise_mode, 0, 0, dyn)
+        beam.final(temperature, noise_mode, 0, 0, max_len + 1, max(p0 + 1, max_len), pad_index, max_len, pl['ids'],
+                   pl['lens'], dyn)
+
+    def generate(self, start_emb, caption, max_len, temperature, beam_size, top_k, eos_index, unk_index, noise_mode,
+                 seed, image_base, pad_index=0):
+        """start_emb fp32 [N,E]; caption int32 [N or 1, p] or None -> (ids int64 [N,max_len], lengths int64 [N], status).
+
+        The decode loop is captured once per (batch, beam, lengths, sampling parameters) into a CUDA graph over
+        static buffers and replayed; seed / image_base reach the kernels through a device word pair."""
+        N, B, dev = start_emb.shape[0], beam_size, self.device
+        p0 = 0 if caption is None else caption.shape[1]
+        key = (N, B, p0, max_len, float(temperature), top_k, eos_index, unk_index, noise_mode, pad_index)
+        pl = self._plans.get(key)
+        if pl is None:
+            if len(self._plans) >= 2:
+                self._plans.clear()
+            R = N * B
+            pl = dict(N=N, ws=self._alloc(max(R, N)), beam=ops.Beam(N, B, max(max_len, p0 + 1), dev),
+                      ind=torch.empty(R, B, dtype=torch.int32, device=dev),
+                      val=torch.empty(R, B, dtype=torch.float32, device=dev),
+                      dyn=torch.zeros(2, dtype=torch.int64, device=dev),
+                      dyn_host=torch.zeros(2, dtype=torch.int64).pin_memory(),
+                      start=torch.empty(N, self.E, dtype=torch.float32, device=dev),
+                      caption=None if caption is None else torch.empty(N, p0, dtype=torch.int32, device=dev),
+                      ids=torch.empty(N, max_len, dtype=torch.int64, device=dev),
+                      lens=torch.empty(N, dtype=torch.int64, device=dev), graph=None)
+            self._plans[key] = pl
+        pl['start'].copy_(start_emb)
+        if caption is not None:
+            pl['caption'].copy_(caption.expand(N, p0))
+        pl['dyn_host'][0], pl['dyn_host'][1] = seed, image_base
+        pl['dyn'].copy_(pl['dyn_host'], non_blocking=True)
+        args = (pl, p0, max_len, temperature, B, top_k, eos_index, unk_index, noise_mode, pad_index)
+        if ops.PROFILE.on or not ops.USE_GRAPHS:
+            self._decode(*args)
+        else:
+            if pl['graph'] is None:
+                self._decode(*args)                     # eager warm-up (lazy one-time initialisation in the library)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._decode(*args)
+                pl['graph'] = g
+            pl['graph'].replay()
+        return pl['ids'].clone(), pl['lens'].clone(), pl['beam'].status.clone()
 
     def forward(self, image_emb, captions, lengths=None):
         """Teacher-forced logits [N, max(lengths), V] fp32 (rnn_models.py:28-46; packed-sequence semantics, Q24)."""

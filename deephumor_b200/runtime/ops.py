@@ -3,6 +3,8 @@
 torch is used for device memory and streams only; every call below launches hand-written CUDA from
 libdeephumor_sm100.so on torch's current stream.
 """
+import os
+
 import torch
 
 from .._lib import LIB, BeamState, ptr, stream
@@ -51,6 +53,7 @@ class _Profile:
 
 
 PROFILE = _Profile()
+USE_GRAPHS = os.environ.get('DH_NO_GRAPH', '') == ''   # capture decode loops into CUDA graphs
 
 
 def code(t):
@@ -202,11 +205,12 @@ def enc_mask(spatial, mask):
 
 
 def select_tokens(logits, V, beam, top_k, temperature, unk, rows_per_image, noise_mode, seed, image_base, step, done,
-                  ind, val, status):
+                  ind, val, status, dyn=None):
     rows = logits.shape[0]
     assert logits.dtype == torch.float32
     LIB.call('dh_select_tokens', ptr(logits), _rows(logits), rows, V, beam, top_k, float(temperature), unk,
-             rows_per_image, noise_mode, seed, image_base, step, ptr(done), ptr(ind), ptr(val), ptr(status), stream())
+             rows_per_image, noise_mode, seed, image_base, step, ptr(done), ptr(ind), ptr(val), ptr(status), ptr(dyn),
+             stream())
 
 
 class Beam:
@@ -234,15 +238,17 @@ class Beam:
                  0 if prefix is None else prefix.stride(0), 1 if prefix is None else prefix.shape[0], plen,
                  self.n_img, self.beam, eos, int(lstm_semantics), stream())
 
-    def step(self, new_ind, new_val, step, max_len, eos, lstm_semantics, temperature, noise_mode, seed, image_base):
+    def step(self, new_ind, new_val, step, max_len, eos, lstm_semantics, temperature, noise_mode, seed, image_base,
+             dyn=None):
         import ctypes
         LIB.call('dh_beam_step', ctypes.byref(self.c), ptr(new_ind), ptr(new_val), self.n_img, self.beam, step, max_len,
-                 eos, int(lstm_semantics), float(temperature), noise_mode, seed, image_base, stream())
+                 eos, int(lstm_semantics), float(temperature), noise_mode, seed, image_base, ptr(dyn), stream())
 
-    def final(self, temperature, noise_mode, seed, image_base, final_step, len_if_running, pad, max_len, out_ids, out_len):
+    def final(self, temperature, noise_mode, seed, image_base, final_step, len_if_running, pad, max_len, out_ids, out_len,
+              dyn=None):
         import ctypes
         LIB.call('dh_beam_final', ctypes.byref(self.c), self.n_img, self.beam, float(temperature), noise_mode, seed,
-                 image_base, final_step, len_if_running, pad, max_len, ptr(out_ids), ptr(out_len), stream())
+                 image_base, final_step, len_if_running, pad, max_len, ptr(out_ids), ptr(out_len), ptr(dyn), stream())
 
 
 def token_logprob(logits, targets, out):

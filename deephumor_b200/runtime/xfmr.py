@@ -39,6 +39,7 @@ class XfmrDecoderRT:
         self.pf = self.layers[0]['pf.fc_1.w'].shape[0]
         self.Wc, self.bc = to(sd[prefix + '.classifier.weight']), to(sd[prefix + '.classifier.bias'], f32)
         self.ldv = (self.V + 3) // 4 * 4
+        self._plans = {}
 
     # ------------------------------------------------------------------ shared layer pieces
     def _cross_kv(self, spatial, n_img):
@@ -65,31 +66,15 @@ class XfmrDecoderRT:
         ops.add_layernorm(tmp[:rows], None, lay['pf_ln.g'], lay['pf_ln.b'], x[:rows])
 
     # ------------------------------------------------------------------ generation
-    def generate(self, start_emb, spatial, caption, max_len, temperature, beam_size, top_k, eos_index, unk_index,
-                 noise_mode, seed, image_base):
-        """start_emb fp32 [N,D]; spatial [N*49,D] (cross) or None; caption int32 [N or 1,p] or None."""
-        N, B, D, dev, dt = start_emb.shape[0], beam_size, self.D, self.device, self.dtype
-        R = N * B
-        p0 = 0 if caption is None else caption.shape[1]
-        S = max_len + 1                                          # cached positions 0..max_len
-        need = max(S, 49) if self.cross else S                   # reference pads to max(T+1, 49) (Q15, Q19)
-        if need > self.pos.shape[0]:
-            raise IndexError('index out of range in self')       # what nn.Embedding raises in the reference (Q19)
-        if caption is not None and caption.shape[0] != N:
-            caption = caption.expand(N, p0).contiguous()
-        rows_alloc = max(R, N)
-        x = torch.empty(rows_alloc, D, dtype=dt, device=dev)
-        qb = torch.empty_like(x)
-        attn = torch.empty_like(x)
-        tmp = torch.empty_like(x)
-        h1 = torch.empty(rows_alloc, self.pf, dtype=dt, device=dev)
-        logits = torch.empty(rows_alloc, self.ldv, dtype=torch.float32, device=dev)
-        Kc = [torch.zeros(R, S, D, dtype=dt, device=dev) for _ in range(self.L)]
-        Vc = [torch.zeros(R, S, D, dtype=dt, device=dev) for _ in range(self.L)]
+    def _decode(self, pl, p0, max_len, temperature, B, top_k, eos_index, unk_index, noise_mode):
+        """Whole incremental decode on the static buffers of plan `pl` (no host sync: CUDA-graph capturable)."""
+        N, D = pl['N'], self.D
+        R, S = N * B, max_len + 1
+        start_emb, spatial, caption = pl['start'], pl['spatial'], pl['caption']
+        x, qb, attn, tmp, h1, logits = pl['x'], pl['qb'], pl['attn'], pl['tmp'], pl['h1'], pl['logits']
+        Kc, Vc, beam, ind, val, dyn = pl['Kc'], pl['Vc'], pl['beam'], pl['ind'], pl['val'], pl['dyn']
+        beam.status.zero_()
         xkv, emask = self._cross_kv(spatial, N) if self.cross else (None, None)
-        beam = ops.Beam(N, B, max_len, dev, kv_slots=S)
-        ind = torch.empty(R, B, dtype=torch.int32, device=dev)
-        val = torch.empty(R, B, dtype=torch.float32, device=dev)
 
         def step(rows, rpi, pos, tokens, seq, src):
             """One new position `pos` for `rows` rows (rpi rows per image)."""
@@ -118,19 +103,67 @@ class XfmrDecoderRT:
         for t in range(p0 + 1):
             tok = None if t == 0 else caption[:, t - 1].contiguous()
             step(N, 1, t, tok, caption, None)
-        ops.select_tokens(logits[:N, :self.V], self.V, B, top_k, temperature, unk_index, 1, noise_mode, seed,
-                          image_base, p0, None, ind, val, beam.status)
+        ops.select_tokens(logits[:N, :self.V], self.V, B, top_k, temperature, unk_index, 1, noise_mode, 0, 0, p0, None,
+                          ind, val, beam.status, dyn)
         beam.init(ind, val, caption, eos_index, False)
         # ---- beam phase: i = p0+1 .. max_len inclusive (Q10); fixed trip count, frozen-at-break on the device
         for i in range(p0 + 1, max_len + 1):
             step(R, B, i, beam.last_tok, beam.seq, beam.src)
-            ops.select_tokens(logits[:R, :self.V], self.V, B, top_k, temperature, unk_index, B, noise_mode, seed,
-                              image_base, i, beam.done, ind, val, beam.status)
-            beam.step(ind, val, i, max_len, eos_index, False, temperature, noise_mode, seed, image_base)
-        out_ids = torch.empty(N, max_len, dtype=torch.int64, device=dev)
-        out_len = torch.empty(N, dtype=torch.int64, device=dev)
-        beam.final(temperature, noise_mode, seed, image_base, max_len + 1, max_len, self.pad, max_len, out_ids, out_len)
-        return out_ids, out_len, beam.status
+            with ops.PROFILE.range('select_beam'):
+                ops.select_tokens(logits[:R, :self.V], self.V, B, top_k, temperature, unk_index, B, noise_mode, 0, 0, i,
+                                  beam.done, ind, val, beam.status, dyn)
+                beam.step(ind, val, i, max_len, eos_index, False, temperature, noise_mode, 0, 0, dyn)
+        beam.final(temperature, noise_mode, 0, 0, max_len + 1, max_len, self.pad, max_len, pl['ids'], pl['lens'], dyn)
+
+    def generate(self, start_emb, spatial, caption, max_len, temperature, beam_size, top_k, eos_index, unk_index,
+                 noise_mode, seed, image_base):
+        """start_emb fp32 [N,D]; spatial [N*49,D] (cross) or None; caption int32 [N or 1,p] or None.
+        The decode is captured once per configuration into a CUDA graph over static buffers and replayed."""
+        N, B, D, dev, dt = start_emb.shape[0], beam_size, self.D, self.device, self.dtype
+        R = N * B
+        p0 = 0 if caption is None else caption.shape[1]
+        S = max_len + 1                                          # cached positions 0..max_len
+        need = max(S, 49) if self.cross else S                   # reference pads to max(T+1, 49) (Q15, Q19)
+        if need > self.pos.shape[0]:
+            raise IndexError('index out of range in self')       # what nn.Embedding raises in the reference (Q19)
+        key = (N, B, p0, max_len, float(temperature), top_k, eos_index, unk_index, noise_mode)
+        pl = self._plans.get(key)
+        if pl is None:
+            self._plans.clear()
+            rows_alloc = max(R, N)
+            mk = lambda *shape, dtype=dt: torch.empty(*shape, dtype=dtype, device=dev)
+            pl = dict(N=N, x=mk(rows_alloc, D), qb=mk(rows_alloc, D), attn=mk(rows_alloc, D), tmp=mk(rows_alloc, D),
+                      h1=mk(rows_alloc, self.pf), logits=mk(rows_alloc, self.ldv, dtype=torch.float32),
+                      Kc=[torch.zeros(R, S, D, dtype=dt, device=dev) for _ in range(self.L)],
+                      Vc=[torch.zeros(R, S, D, dtype=dt, device=dev) for _ in range(self.L)],
+                      beam=ops.Beam(N, B, max_len, dev, kv_slots=S),
+                      ind=mk(R, B, dtype=torch.int32), val=mk(R, B, dtype=torch.float32),
+                      dyn=torch.zeros(2, dtype=torch.int64, device=dev),
+                      dyn_host=torch.zeros(2, dtype=torch.int64).pin_memory(),
+                      start=mk(N, D, dtype=torch.float32), spatial=mk(N * 49, D) if self.cross else None,
+                      caption=None if caption is None else mk(N, p0, dtype=torch.int32),
+                      ids=mk(N, max_len, dtype=torch.int64), lens=mk(N, dtype=torch.int64), graph=None)
+            self._plans[key] = pl
+        pl['start'].copy_(start_emb)
+        if self.cross:
+            pl['spatial'].copy_(spatial)
+        if caption is not None:
+            pl['caption'].copy_(caption.expand(N, p0))
+        pl['dyn_host'][0], pl['dyn_host'][1] = seed, image_base
+        pl['dyn'].copy_(pl['dyn_host'], non_blocking=True)
+        args = (pl, p0, max_len, temperature, B, top_k, eos_index, unk_index, noise_mode)
+        if ops.PROFILE.on or not ops.USE_GRAPHS:
+            self._decode(*args)
+        else:
+            if pl['graph'] is None:
+                self._decode(*args)                     # eager warm-up (lazy one-time initialisation in the library)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._decode(*args)
+                pl['graph'] = g
+            pl['graph'].replay()
+        return pl['ids'].clone(), pl['lens'].clone(), pl['beam'].status.clone()
 
     # ------------------------------------------------------------------ teacher-forced forward
     def hidden(self, start_emb, spatial, captions):

@@ -24,7 +24,7 @@ extern "C" {
 typedef struct CUstream_st* cudaStream_t;
 #endif
 
-#define DH_VERSION 102
+#define DH_VERSION 103
 
 #define DH_OK 0
 #define DH_ERR_ARG (-1)
@@ -141,17 +141,20 @@ typedef struct dh_beam_state {
   int S_alloc;
 } dh_beam_state;
 
+/* dyn (device, nullable): {seed, image_base} read at run time instead of the by-value arguments, so a captured CUDA
+ * graph of the whole decode loop can be replayed with a new noise seed / shard offset. */
 int dh_select_tokens(const float* logits, long long ld, int rows, int V, int beam, int top_k, float temperature, int unk,
                      int rows_per_image, int noise_mode, unsigned long long seed, long long image_base, int step,
-                     const unsigned char* done, int* ind, float* val, int* status, cudaStream_t stream);
+                     const unsigned char* done, int* ind, float* val, int* status, const long long* dyn,
+                     cudaStream_t stream);
 int dh_beam_init(const dh_beam_state* st, const int* ind0, const float* val0, const int* prefix, long long prefix_ld,
                  int prefix_rows, int prefix_len, int n_img, int beam, int eos, int lstm_semantics, cudaStream_t stream);
 int dh_beam_step(const dh_beam_state* st, const int* new_ind, const float* new_val, int n_img, int beam, int step,
                  int max_len, int eos, int lstm_semantics, float temperature, int noise_mode, unsigned long long seed,
-                 long long image_base, cudaStream_t stream);
+                 long long image_base, const long long* dyn, cudaStream_t stream);
 int dh_beam_final(const dh_beam_state* st, int n_img, int beam, float temperature, int noise_mode,
                   unsigned long long seed, long long image_base, int final_step, int len_if_running, int pad, int max_len,
-                  long long* out_ids, long long* out_len, cudaStream_t stream);
+                  long long* out_ids, long long* out_len, const long long* dyn, cudaStream_t stream);
 /* log_softmax(logits)[target] per row (experiments/metrics.py:5). */
 int dh_token_logprob(const float* logits, long long ld, int rows, int V, const long long* targets, float* out,
                      cudaStream_t stream);

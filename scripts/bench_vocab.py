@@ -1,0 +1,32 @@
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from deephumor_b200.runtime import ops
+dev='cuda'
+M,N,K=2560,36541,512
+A=torch.randn(M,K,device=dev).to(torch.bfloat16); W=(torch.randn(N,K,device=dev)*0.5).to(torch.bfloat16)
+b=torch.randn(N,device=dev)
+ldc=(N+3)//4*4
+out=torch.empty(M,ldc,device=dev)
+ind=torch.empty(M,5,dtype=torch.int32,device=dev); val=torch.empty(M,5,device=dev); status=torch.zeros(1,dtype=torch.int32,device=dev)
+def t(fn,it=10,flush=True):
+    fn(); torch.cuda.synchronize()
+    fl=torch.empty(256*1024*1024,dtype=torch.uint8,device=dev)
+    ts=[]
+    for _ in range(it):
+        if flush: fl.zero_()
+        e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1)*1e3)
+    return min(ts), sum(ts)/len(ts)
+print('nobias', t(lambda: ops.gemm(A,W,out[:,:N])))
+print('bias  ', t(lambda: ops.gemm(A,W,out[:,:N],bias=b)))
+print('bias noflush', t(lambda: ops.gemm(A,W,out[:,:N],bias=b),flush=False))
+for tn in (64,128,256):
+    print('bias tile',tn, t(lambda: ops.gemm(A,W,out[:,:N],bias=b,tile_n=tn)))
+print('select', t(lambda: ops.select_tokens(out[:,:N],N,5,50,1.0,1,5,1,1,0,3,None,ind,val,status)))
+def both():
+    ops.gemm(A,W,out[:,:N],bias=b); ops.select_tokens(out[:,:N],N,5,50,1.0,1,5,1,1,0,3,None,ind,val,status)
+print('gemm+select', t(both))
+# bf16 logits variant
+out16=torch.empty(M,ldc+(-ldc)%8,dtype=torch.bfloat16,device=dev)
+print('bf16 out', t(lambda: ops.gemm(A,W,out16[:,:N],bias=b)))
