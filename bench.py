@@ -135,7 +135,7 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     from deephumor_b200 import _lib
-    from deephumor_b200.runtime import ops
+    from deephumor_b200.runtime import ops, shard
     from deephumor_b200.utils import synth
     kind, batch, beam, top_k, desc = WORKLOADS[args.workload]
     if args.batch:
@@ -149,17 +149,15 @@ def run_ours(args):
     host_images = torch.empty(batch, 3, 224, 224, pin_memory=True)
     host_images.copy_(images)
     host_labels = labels.cpu().pin_memory() if labels is not None else None
-    gathered = [torch.empty(batch, MAX_LEN, dtype=torch.int64, device=dev) for _ in range(world)] if world > 1 else None
     gen_kw = dict(max_len=MAX_LEN, temperature=1.0, beam_size=beam, top_k=top_k, noise='injected', seed=1234,
                   image_base=first)
 
     def step(img, lab):
         with torch.no_grad():
             out = model.generate(img, lab, **gen_kw) if lab is not None else model.generate(img, **gen_kw)
-        ids, lens = out if isinstance(out, tuple) else (out.view(1, -1), None)
-        if world > 1:
-            dist.all_gather(gathered, ids.contiguous())          # the path's only collective
-        return ids, lens
+        ids, lens = out if isinstance(out, tuple) else (out.view(1, -1), torch.tensor([out.numel()], device=dev))
+        # the path's only collective: one all-gather of ids (+lengths) per step; identity at N=1
+        return shard.gather_captions(ids, lens, total=batch * world)
 
     def step_e2e():
         img = host_images.to(dev, non_blocking=True)
