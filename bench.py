@@ -185,11 +185,15 @@ def run_ours(args):
             dist.barrier()
         return float(ms.item()), _lib.LIB.launches - l0, prof
 
-    if args.profile_mode:       # under ncu: one warm-up + one step, nothing else
+    if args.profile_mode:       # under `ncu --profile-from-start off`: warm-up, then ONE eagerly launched step
+        step(images, labels)
         step(images, labels)
         torch.cuda.synchronize()
+        ops.USE_GRAPHS = False
+        torch.cuda.profiler.start()
         step(images, labels)
         torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
         return
     for _ in range(max(args.warmup, 3)):
         step(images, labels)

@@ -40,6 +40,11 @@ struct TcParams {
   int tma_store;                          // 1: epilogue stages 128 B-wide row slabs in smem and stores them by TMA
   int res_chunks;                         // > 0: residual added on the tensor core as BN/64 extra K chunks (R x I)
   int* error;                             // device flag set before a watchdog trap
+  // Vocab-projection epilogues that keep the logits out of HBM (dh_vocab_groupmax / dh_vocab_candidates):
+  int epi_mode;                           // 0: store C; 1: maxima of 32-column groups; 2: compact logits >= thresh[row]
+  float* gmax; long long ld_gmax;         // [M, ld_gmax] group maxima (mode 1)
+  const float* thresh;                    // [M] lower bound of the row's top_k-th largest logit (mode 2)
+  int* cand_count; int* cand_idx; float* cand_val; int cand_cap;   // [M], [M, cap], [M, cap]
 };
 
 // ------------------------------------------------------------------------------------------- PTX wrappers
@@ -262,7 +267,62 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp >= 4) {
     // ======================================================================= epilogue
     const int ew = warp - 4;                      // == warp % 4: TMEM lane quadrant this warp may read
-    if (p.tma_store) {
+    if (p.epi_mode) {
+      // ---- selection epilogues: every thread owns one accumulator row; nothing of the [M,N] product is stored.
+      const int row_l = ew * 32 + lane;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        const int m0 = (tile / p.n_blocks) * BM, n0 = (tile % p.n_blocks) * BN;
+        const int as = it & 1;
+        mbar_wait(tfull_bar(as), (it >> 1) & 1, p.error, 4);
+        tc_fence_after();
+        const uint32_t tmem_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
+        asm volatile("bar.sync 1, 128;" ::: "memory");          // readers of the previous bias slice are done
+        for (int i = row_l; i < BN; i += 128) bias_s[i] = (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const long long row = (long long)m0 + row_l;
+        const bool row_ok = row < p.M;
+        const float t0 = (p.epi_mode == 2 && row_ok) ? __ldg(p.thresh + row) : INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int col0 = n0 + c * 32;
+          if (col0 >= p.N) break;                                 // warp-uniform
+          uint32_t v[32];
+          tc_ld32(tmem_row + (uint32_t)(c * 32), v);
+          float x[32];
+          const float4* bs = reinterpret_cast<const float4*>(bias_s + c * 32);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 b4 = bs[g];
+            x[4 * g] = __uint_as_float(v[4 * g]) + b4.x;
+            x[4 * g + 1] = __uint_as_float(v[4 * g + 1]) + b4.y;
+            x[4 * g + 2] = __uint_as_float(v[4 * g + 2]) + b4.z;
+            x[4 * g + 3] = __uint_as_float(v[4 * g + 3]) + b4.w;
+          }
+          const int nv = p.N - col0;                              // valid columns in this group (>= 1)
+          float mx = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, j < nv ? x[j] : -INFINITY);
+          if (p.epi_mode == 1) {
+            if (row_ok) p.gmax[row * p.ld_gmax + (col0 >> 5)] = mx;
+          } else if (mx >= t0 && mx > -INFINITY) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < nv && x[j] >= t0 && x[j] > -INFINITY) {
+                const int slot = atomicAdd(p.cand_count + row, 1);
+                if (slot < p.cand_cap) {
+                  p.cand_idx[row * p.cand_cap + slot] = col0 + j;
+                  p.cand_val[row * p.cand_cap + slot] = x[j];
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+      }
+    } else if (p.tma_store) {
       // ---- slab epilogue: each thread owns one accumulator row; a round covers 128 B of every row (32 fp32 or
       // 64 half columns), written 128B-swizzled into one of two 16 KB slabs and stored by one TMA instruction.
       const uint32_t slabs = base + C::kStages * C::kStageBytes;
@@ -564,7 +624,9 @@ int dispatch(const CUtensorMap& ma, const void* W, long long ldw, TcParams& p, i
   const bool res_ok = !p.res || (p.res_dtype == p.ab_dtype && (uintptr_t)p.res % 16 == 0 && (p.ldr * 2) % 16 == 0);
   p.tma_store = 0;
   p.res_chunks = 0;
-  if (out_ok && res_ok) {
+  if (p.epi_mode) {
+    // selection epilogues store nothing of C
+  } else if (out_ok && res_ok) {
     rc = make_map_2d(&mc, p.out, p.M, p.N, p.ldc, BM, p.out_dtype);
     if (rc) return rc;
     p.tma_store = 1;
@@ -607,6 +669,47 @@ extern "C" int dh_gemm_tc(const void* A, long long lda, const void* W, long long
   rc = make_map_2d(&ma, A, M, K, lda, BM, ab_dtype);
   if (rc) return rc;
   return dispatch(ma, W, ldw, p, tile_n ? tile_n : pick_bn(M, N), stream);
+}
+
+// Vocab projection with the logits kept on chip (models/rnn_models.py:81,109 and models/transformers.py:488,736 feeding
+// models/beam.py:32-37): pass 1 stores the maximum of every 32-column group of logits[M,N] = A W^T + bias, pass 2
+// recomputes the identical product and appends (column, logit) of every logit >= thresh[row] to the row's candidate list.
+static int vocab_pass(int mode, const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias,
+                      int M, int N, int K, float* gmax, long long ld_gmax, const float* thresh, int* cand_count,
+                      int* cand_idx, float* cand_val, int cand_cap, cudaStream_t stream) {
+  DH_ARG(A && W && M >= 0 && N > 0 && K > 0);
+  DH_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0);
+  DH_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0);
+  DH_ARG(ab_dtype == DH_BF16 || ab_dtype == DH_F16);
+  if (M == 0) return DH_OK;
+  int rc = tc_init();
+  if (rc) return rc;
+  TcParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.k_chunks = dh_cdiv(K, BK);
+  p.ab_dtype = ab_dtype;
+  p.bias = bias;
+  p.epi_mode = mode;
+  p.gmax = gmax; p.ld_gmax = ld_gmax;
+  p.thresh = thresh; p.cand_count = cand_count; p.cand_idx = cand_idx; p.cand_val = cand_val; p.cand_cap = cand_cap;
+  CUtensorMap ma;
+  rc = make_map_2d(&ma, A, M, K, lda, BM, ab_dtype);
+  if (rc) return rc;
+  return dispatch(ma, W, ldw, p, N <= 64 ? 64 : N <= 128 ? 128 : 256, stream);
+}
+
+extern "C" int dh_vocab_groupmax(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias,
+                                 int M, int N, int K, float* gmax, long long ld_gmax, cudaStream_t stream) {
+  DH_ARG(gmax && ld_gmax >= dh_cdiv(N, 32));
+  return vocab_pass(1, A, lda, W, ldw, ab_dtype, bias, M, N, K, gmax, ld_gmax, nullptr, nullptr, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int dh_vocab_candidates(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias,
+                                   int M, int N, int K, const float* thresh, int* cand_count, int* cand_idx, float* cand_val,
+                                   int cand_cap, cudaStream_t stream) {
+  DH_ARG(thresh && cand_count && cand_idx && cand_val && cand_cap > 0);
+  return vocab_pass(2, A, lda, W, ldw, ab_dtype, bias, M, N, K, nullptr, 0, thresh, cand_count, cand_idx, cand_val, cand_cap,
+                    stream);
 }
 
 // x [n,H,W,Cin] NHWC (Cin % 64 == 0), w [Cout][kh][kw][Cin] (BN folded), y [n,Ho,Wo,Cout]; all bf16 or all f16.

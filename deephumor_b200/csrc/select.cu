@@ -36,97 +36,46 @@ struct SelParams {
   const long long* dyn;        // nullable: {seed, image_base} overriding the by-value fields
 };
 
-// Block-wide helpers (kSelThreads threads).
+// Block-wide helpers (NT threads).
+template <int NT>
 __device__ __forceinline__ float block_max(float v, float* red, float* bcast) {
   v = dh_warp_max(v);
   __syncthreads();
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
-  if (threadIdx.x == 0) { float m = red[0]; for (int w = 1; w < kSelThreads / 32; ++w) m = fmaxf(m, red[w]); *bcast = m; }
+  if (threadIdx.x == 0) { float m = red[0]; for (int w = 1; w < NT / 32; ++w) m = fmaxf(m, red[w]); *bcast = m; }
   __syncthreads();
   return *bcast;
 }
+template <int NT>
 __device__ __forceinline__ float block_sum(float v, float* red, float* bcast) {
   v = dh_warp_sum(v);
   __syncthreads();
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
-  if (threadIdx.x == 0) { float t = 0.f; for (int w = 0; w < kSelThreads / 32; ++w) t += red[w]; *bcast = t; }
+  if (threadIdx.x == 0) { float t = 0.f; for (int w = 0; w < NT / 32; ++w) t += red[w]; *bcast = t; }
   __syncthreads();
   return *bcast;
 }
 
-// One CTA per logits row, two streaming passes over the row (the second one hits L2), no row staging:
-//   pass 1  every thread keeps the maximum of its strided slice; the top_k-th largest of those kSelThreads
-//           distinct elements is a lower bound t0 of the row's k-th largest value;
-//   pass 2  elements >= t0 (a few more than top_k) are compacted into shared memory;
-//   then    the exact k-th largest (ties kept), the <unk> mask, softmax(l/T), the Exp(1)-race draw of B ids
-//           and the log_softmax scores are computed on that short list.
-__global__ void __launch_bounds__(kSelThreads) select_tokens_kernel(SelParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  int* surv_idx = reinterpret_cast<int*>(smem_raw);                  // [kSurvCap]
-  float* surv_val = reinterpret_cast<float*>(surv_idx + kSurvCap);   // [kSurvCap] raw logits
-  float* surv_score = surv_val + kSurvCap;                           // [kSurvCap]
-  __shared__ float lm[kSelThreads];
-  __shared__ int s_ncand, s_nsurv;
-  __shared__ float s_t0, s_kth;
-  __shared__ float red_f[kSelThreads / 32];
-  __shared__ int red_i[kSelThreads / 32];
+// Shared tail of both selection kernels.  surv_idx / surv_val hold nc candidates that include every logit >= the row's
+// top_k-th largest value; this computes that exact value (ties kept), masks <unk>, softmax(l/T), the Exp(1)-race draw of
+// B ids and the log_softmax scores (models/beam.py:32-53,79).  All NT threads of the CTA must call it.
+template <int NT>
+__device__ void select_tail(const SelParams& p, int r, int img, int nc, int* surv_idx, float* surv_val, float* surv_score,
+                            int cap) {
+  __shared__ int s_nsurv;
+  __shared__ float s_kth;
+  __shared__ float red_f[NT / 32];
+  __shared__ int red_i[NT / 32];
   __shared__ float s_bcast;
   __shared__ int pick_idx[kMaxBeam];
   __shared__ float pick_logit[kMaxBeam];
-
-  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int img = r / p.rpi;
-  if (p.done && p.done[img]) return;
-  const float* row = p.logits + (long long)r * p.ld;
-  const bool vec = (p.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.logits) & 15) == 0);
-  const int V4 = vec ? (p.V >> 2) : 0;
-
-  // ---- pass 1: per-thread maximum
-  float mx = -INFINITY;
-  for (int i = tid; i < V4; i += kSelThreads) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(row) + i);
-    mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
-  }
-  for (int i = V4 * 4 + tid; i < p.V; i += kSelThreads) mx = fmaxf(mx, row[i]);
-  lm[tid] = mx;
-  if (tid == 0) { s_ncand = 0; s_nsurv = 0; s_t0 = -INFINITY; }
-  __syncthreads();
-  if (p.top_k <= kSelThreads) {
-    int rank = 0;
-    for (int j = 0; j < kSelThreads; ++j) {
-      const float o = lm[j];
-      rank += (o > mx) || (o == mx && j < tid);
-    }
-    if (rank == p.top_k - 1) s_t0 = mx;     // exactly one thread has this rank
-  }
-  __syncthreads();
-  const float t0 = s_t0;                     // -inf when top_k > kSelThreads (every finite element is a candidate)
-
-  // ---- pass 2: compact candidates
-  auto push = [&](float x, int i) {
-    if (x >= t0 && x > -INFINITY) {
-      const int slot = atomicAdd(&s_ncand, 1);
-      if (slot < kSurvCap) { surv_idx[slot] = i; surv_val[slot] = x; }
-    }
-  };
-  for (int i = tid; i < V4; i += kSelThreads) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(row) + i);
-    push(v.x, 4 * i); push(v.y, 4 * i + 1); push(v.z, 4 * i + 2); push(v.w, 4 * i + 3);
-  }
-  for (int i = V4 * 4 + tid; i < p.V; i += kSelThreads) push(row[i], i);
-  __syncthreads();
-  int nc = s_ncand;
-  if (nc > kSurvCap) {
-    if (tid == 0) atomicOr(p.status, DH_STATUS_TOO_MANY_TIES);
-    nc = kSurvCap;
-  }
-
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // ---- exact k-th largest among the candidates: #{> v} < top_k <= #{>= v}
-  if (tid == 0) s_kth = -INFINITY;           // fewer than top_k finite values: everything survives
+  if (tid == 0) { s_kth = -INFINITY; s_nsurv = 0; }  // fewer than top_k finite values: everything survives
   __syncthreads();
-  for (int c = tid; c < nc; c += kSelThreads) {
+  for (int c = tid; c < nc; c += NT) {
     const float v = surv_val[c];
     int gt = 0, ge = 0;
     for (int j = 0; j < nc; ++j) { const float o = surv_val[j]; gt += o > v; ge += o >= v; }
@@ -134,25 +83,14 @@ __global__ void __launch_bounds__(kSelThreads) select_tokens_kernel(SelParams p)
   }
   __syncthreads();
   const float kth = s_kth;
-  // ---- survivors: value >= k-th largest (ties kept) and id != <unk>; compact in place (stable order not needed:
-  //      every later choice is by (score desc, id asc))
-  // two-phase in-place compaction: read own slots first, then rewrite
-  const int per = (nc + kSelThreads - 1) / kSelThreads;
-  int my_n = 0;
-  int my_idx[8]; float my_val[8];
-  for (int q = 0; q < per && q < 8; ++q) {
-    const int c = tid + q * kSelThreads;
-    if (c < nc) {
-      const float v = surv_val[c]; const int id = surv_idx[c];
-      if (v >= kth && id != p.unk) { my_idx[my_n] = id; my_val[my_n] = v; ++my_n; }
-    }
+  // ---- survivors: value >= k-th largest (ties kept) and id != <unk>; the others are flagged in place (id = -1)
+  int mine = 0;
+  for (int c = tid; c < nc; c += NT) {
+    const bool keep = surv_val[c] >= kth && surv_idx[c] != p.unk;
+    if (!keep) surv_idx[c] = -1;
+    mine += keep;
   }
-  __syncthreads();
-  for (int q = 0; q < my_n; ++q) {
-    const int slot = atomicAdd(&s_nsurv, 1);
-    surv_idx[slot] = my_idx[q];
-    surv_val[slot] = my_val[q];
-  }
+  if (mine) atomicAdd(&s_nsurv, mine);
   __syncthreads();
   const int ns = s_nsurv;
   if (ns == 0) {   // whole row filtered: torch.multinomial raises (Q3)
@@ -163,22 +101,26 @@ __global__ void __launch_bounds__(kSelThreads) select_tokens_kernel(SelParams p)
 
   // ---- softmax(l / T) over survivors (everything else has p == 0 exactly)
   float m2 = -INFINITY;
-  for (int s = tid; s < ns; s += kSelThreads) m2 = fmaxf(m2, surv_val[s] / p.T);
-  m2 = block_max(m2, red_f, &s_bcast);
+  for (int s = tid; s < nc; s += NT)
+    if (surv_idx[s] >= 0) m2 = fmaxf(m2, surv_val[s] / p.T);
+  m2 = block_max<NT>(m2, red_f, &s_bcast);
   float sum = 0.f;
-  for (int s = tid; s < ns; s += kSelThreads) {
-    const float e = expf(surv_val[s] / p.T - m2);
+  for (int s = tid; s < nc; s += NT) {
+    const float e = surv_idx[s] >= 0 ? expf(surv_val[s] / p.T - m2) : 0.f;
     surv_score[s] = e;
     sum += e;
   }
-  sum = block_sum(sum, red_f, &s_bcast);
+  sum = block_sum<NT>(sum, red_f, &s_bcast);
   const unsigned long long seed = p.dyn ? (unsigned long long)p.dyn[0] : p.seed;
   const long long image_base = p.dyn ? p.dyn[1] : p.image_base;
   const unsigned long long rk = dh_noise_row_key(seed, (unsigned long long)(image_base + img), (unsigned long long)p.step,
                                                  DH_CALL_TOKEN, (unsigned long long)(r % p.rpi));
-  for (int s = tid; s < ns; s += kSelThreads) {
-    float pr = surv_score[s] / sum;
-    if (p.noise_mode == DH_NOISE_INJECTED) pr = pr / dh_exp_noise(rk, (unsigned long long)surv_idx[s]);
+  for (int s = tid; s < nc; s += NT) {
+    float pr = -2.f;                                     // not a survivor: never picked
+    if (surv_idx[s] >= 0) {
+      pr = surv_score[s] / sum;
+      if (p.noise_mode == DH_NOISE_INJECTED) pr = pr / dh_exp_noise(rk, (unsigned long long)surv_idx[s]);
+    }
     surv_score[s] = pr;
   }
   __syncthreads();
@@ -187,7 +129,7 @@ __global__ void __launch_bounds__(kSelThreads) select_tokens_kernel(SelParams p)
   const int npick = ns < p.B ? ns : p.B;
   for (int j = 0; j < npick; ++j) {
     float best = -1.f; int bi = 0x7fffffff, bs = -1;
-    for (int s = tid; s < ns; s += kSelThreads) {
+    for (int s = tid; s < nc; s += NT) {
       float sc = surv_score[s]; int id = surv_idx[s];
       if (sc > best || (sc == best && sc >= 0.f && id < bi)) { best = sc; bi = id; bs = s; }
     }
@@ -202,7 +144,7 @@ __global__ void __launch_bounds__(kSelThreads) select_tokens_kernel(SelParams p)
     __syncthreads();
     if (tid == 0) {
       float b2 = -1.f; int s2 = -1, i2 = 0x7fffffff;
-      for (int w = 0; w < kSelThreads / 32; ++w) {
+      for (int w = 0; w < NT / 32; ++w) {
         int s = red_i[w];
         if (s < 0) continue;
         int id = surv_idx[s];
@@ -238,6 +180,154 @@ __global__ void __launch_bounds__(kSelThreads) select_tokens_kernel(SelParams p)
       p.val[(long long)r * p.B + j] = pick_logit[j] - m3 - lse;
     }
   }
+}
+
+// One CTA per logits row, two streaming passes over the row (the second one hits L2), no row staging:
+//   pass 1  every thread keeps the maximum of its strided slice; the top_k-th largest of those kSelThreads
+//           distinct elements is a lower bound t0 of the row's k-th largest value;
+//   pass 2  elements >= t0 (a few more than top_k) are compacted into shared memory;
+//   then    select_tail on that short list.
+__global__ void __launch_bounds__(kSelThreads) select_tokens_kernel(SelParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int* surv_idx = reinterpret_cast<int*>(smem_raw);                  // [kSurvCap]
+  float* surv_val = reinterpret_cast<float*>(surv_idx + kSurvCap);   // [kSurvCap] raw logits
+  float* surv_score = surv_val + kSurvCap;                           // [kSurvCap]
+  __shared__ float lm[kSelThreads];
+  __shared__ int s_ncand;
+  __shared__ float s_t0;
+
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const int img = r / p.rpi;
+  if (p.done && p.done[img]) return;
+  const float* row = p.logits + (long long)r * p.ld;
+  const bool vec = (p.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.logits) & 15) == 0);
+  const int V4 = vec ? (p.V >> 2) : 0;
+
+  // ---- pass 1: per-thread maximum
+  float mx = -INFINITY;
+  for (int i = tid; i < V4; i += kSelThreads) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(row) + i);
+    mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+  for (int i = V4 * 4 + tid; i < p.V; i += kSelThreads) mx = fmaxf(mx, row[i]);
+  lm[tid] = mx;
+  if (tid == 0) { s_ncand = 0; s_t0 = -INFINITY; }
+  __syncthreads();
+  if (p.top_k <= kSelThreads) {
+    int rank = 0;
+    for (int j = 0; j < kSelThreads; ++j) {
+      const float o = lm[j];
+      rank += (o > mx) || (o == mx && j < tid);
+    }
+    if (rank == p.top_k - 1) s_t0 = mx;     // exactly one thread has this rank
+  }
+  __syncthreads();
+  const float t0 = s_t0;                     // -inf when top_k > kSelThreads (every finite element is a candidate)
+
+  // ---- pass 2: compact candidates
+  auto push = [&](float x, int i) {
+    if (x >= t0 && x > -INFINITY) {
+      const int slot = atomicAdd(&s_ncand, 1);
+      if (slot < kSurvCap) { surv_idx[slot] = i; surv_val[slot] = x; }
+    }
+  };
+  for (int i = tid; i < V4; i += kSelThreads) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(row) + i);
+    push(v.x, 4 * i); push(v.y, 4 * i + 1); push(v.z, 4 * i + 2); push(v.w, 4 * i + 3);
+  }
+  for (int i = V4 * 4 + tid; i < p.V; i += kSelThreads) push(row[i], i);
+  __syncthreads();
+  int nc = s_ncand;
+  if (nc > kSurvCap) {
+    if (tid == 0) atomicOr(p.status, DH_STATUS_TOO_MANY_TIES);
+    nc = kSurvCap;
+  }
+  select_tail<kSelThreads>(p, r, img, nc, surv_idx, surv_val, surv_score, kSurvCap);
+}
+
+// ------------------------------------------------------------------------------------------------ fused vocab path
+// t0[row] = top_k-th largest of the row's 32-column group maxima (a lower bound of the row's top_k-th largest logit:
+// the group maxima are n_groups distinct logits).  At most top_k groups have a maximum > t0, so -- ties aside -- at most
+// 32 * top_k logits are >= t0 and the candidate capacity 32 * top_k of dh_vocab_candidates cannot overflow.
+// One CTA (kThrThreads) per row: per-thread maxima give a first bound, group maxima above it are ranked exactly.
+constexpr int kThrThreads = 128;
+constexpr int kThrCap = 1024;
+__global__ void __launch_bounds__(kThrThreads) vocab_threshold_kernel(const float* __restrict__ gmax, long long ld, int n_groups,
+                                                                     int top_k, float* __restrict__ thresh,
+                                                                     int* __restrict__ cand_count) {
+  __shared__ float lm[kThrThreads];
+  __shared__ float cand[kThrCap];
+  __shared__ int s_n;
+  __shared__ float s_t1, s_t0;
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const float* row = gmax + (long long)r * ld;
+  float mx = -INFINITY;
+  for (int i = tid; i < n_groups; i += kThrThreads) mx = fmaxf(mx, row[i]);
+  lm[tid] = mx;
+  if (tid == 0) { s_n = 0; s_t1 = -INFINITY; s_t0 = -INFINITY; }
+  __syncthreads();
+  if (top_k <= kThrThreads && top_k <= n_groups) {
+    int rank = 0;
+    for (int j = 0; j < kThrThreads; ++j) { const float o = lm[j]; rank += (o > mx) || (o == mx && j < tid); }
+    if (rank == top_k - 1) s_t1 = mx;
+  }
+  __syncthreads();
+  const float t1 = s_t1;
+  if (top_k <= n_groups) {
+    for (int i = tid; i < n_groups; i += kThrThreads) {
+      const float x = row[i];
+      if (x >= t1) { const int slot = atomicAdd(&s_n, 1); if (slot < kThrCap) cand[slot] = x; }
+    }
+    __syncthreads();
+    const int n = s_n;
+    if (n <= kThrCap) {
+      for (int c = tid; c < n; c += kThrThreads) {
+        const float v = cand[c];
+        int gt = 0, ge = 0;
+        for (int j = 0; j < n; ++j) { const float o = cand[j]; gt += o > v; ge += o >= v; }
+        if (gt < top_k && top_k <= ge) s_t0 = v;
+      }
+    } else if (tid == 0) {
+      s_t0 = t1;      // too many ties to rank: fall back to the looser (still valid) bound
+    }
+  }
+  __syncthreads();
+  if (tid == 0) { thresh[r] = s_t0; cand_count[r] = 0; }
+}
+
+// Selection from the candidate lists written by dh_vocab_candidates (unordered: the slots were handed out by atomics;
+// they are sorted by column first so that every floating-point reduction below is run-to-run deterministic).
+constexpr int kCandThreads = 128;
+__global__ void __launch_bounds__(kCandThreads) select_candidates_kernel(SelParams p, const int* __restrict__ cand_count,
+                                                                        const int* __restrict__ cand_idx,
+                                                                        const float* __restrict__ cand_val, int cap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int scap = cap < kSurvCap ? cap : kSurvCap;
+  int* surv_idx = reinterpret_cast<int*>(smem_raw);             // [scap]
+  float* surv_val = reinterpret_cast<float*>(surv_idx + scap);  // [scap]
+  float* surv_score = surv_val + scap;                          // [scap]
+  int* tmp_idx = reinterpret_cast<int*>(surv_score);            // sort scratch aliases the score array + tail
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const int img = r / p.rpi;
+  if (p.done && p.done[img]) return;
+  int nc = cand_count[r];
+  if (nc > scap) {
+    if (tid == 0) atomicOr(p.status, DH_STATUS_TOO_MANY_TIES);
+    nc = scap;
+  }
+  const int* gi = cand_idx + (long long)r * cap;
+  const float* gv = cand_val + (long long)r * cap;
+  for (int c = tid; c < nc; c += kCandThreads) tmp_idx[c] = gi[c];
+  __syncthreads();
+  for (int c = tid; c < nc; c += kCandThreads) {
+    const int id = tmp_idx[c];
+    int pos = 0;
+    for (int j = 0; j < nc; ++j) pos += tmp_idx[j] < id;
+    surv_idx[pos] = id;
+    surv_val[pos] = gv[c];
+  }
+  __syncthreads();
+  select_tail<kCandThreads>(p, r, img, nc, surv_idx, surv_val, surv_score, scap);
 }
 
 // ------------------------------------------------------------------------------------------------ beam state
@@ -462,6 +552,37 @@ extern "C" int dh_select_tokens(const float* logits, long long ld, int rows, int
   SelParams p{logits, ld, rows, V, beam, top_k, unk, rows_per_image, temperature, noise_mode, seed, image_base, step,
               done, ind, val, status, dyn};
   select_tokens_kernel<<<rows, kSelThreads, smem, s>>>(p);
+  DH_LAUNCH_OK();
+  return DH_OK;
+}
+
+extern "C" int dh_vocab_threshold(const float* gmax, long long ld_gmax, int rows, int n_groups, int top_k, float* thresh,
+                                  int* cand_count, cudaStream_t s) {
+  DH_ARG(gmax && thresh && cand_count && rows >= 0 && n_groups > 0 && ld_gmax >= n_groups && top_k >= 1);
+  if (rows == 0) return DH_OK;
+  vocab_threshold_kernel<<<rows, kThrThreads, 0, s>>>(gmax, ld_gmax, n_groups, top_k, thresh, cand_count);
+  DH_LAUNCH_OK();
+  return DH_OK;
+}
+
+extern "C" int dh_select_candidates(const int* cand_count, const int* cand_idx, const float* cand_val, int cand_cap, int rows,
+                                    int beam, int top_k, float temperature, int unk, int rows_per_image, int noise_mode,
+                                    unsigned long long seed, long long image_base, int step, const unsigned char* done,
+                                    int* ind, float* val, int* status, const long long* dyn, cudaStream_t s) {
+  DH_ARG(cand_count && cand_idx && cand_val && cand_cap > 0 && ind && val && status && rows >= 0);
+  DH_ARG(beam >= 1 && beam <= kMaxBeam && top_k >= 1 && beam <= top_k && temperature > 0.f);
+  DH_ARG(rows_per_image >= 1 && (noise_mode == DH_NOISE_DETERMINISTIC || noise_mode == DH_NOISE_INJECTED));
+  if (rows == 0) return DH_OK;
+  const int scap = cand_cap < kSurvCap ? cand_cap : kSurvCap;
+  size_t smem = (size_t)scap * 12;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DH_CUDA(cudaFuncSetAttribute(select_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSurvCap * 12));
+    attr_set = true;
+  }
+  SelParams p{nullptr, 0, rows, 0, beam, top_k, unk, rows_per_image, temperature, noise_mode, seed, image_base, step,
+              done, ind, val, status, dyn};
+  select_candidates_kernel<<<rows, kCandThreads, smem, s>>>(p, cand_count, cand_idx, cand_val, cand_cap);
   DH_LAUNCH_OK();
   return DH_OK;
 }

@@ -31,7 +31,7 @@ class LSTMDecoderRT:
         self.ldv = (self.V + 3) // 4 * 4
         self._plans = {}
 
-    def _alloc(self, rows):
+    def _alloc(self, rows, logits=True):
         d, dev, H, E, L = self.dtype, self.device, self.H, self.E, self.L
         ws = dict(
             A=[torch.zeros(rows, (E if l == 0 else H) + H, dtype=d, device=dev) for l in range(L)],
@@ -39,10 +39,10 @@ class LSTMDecoderRT:
             c=[torch.zeros(L, rows, H, dtype=torch.float32, device=dev) for _ in range(2)],
             hs=torch.zeros(L, rows, H, dtype=d, device=dev),
             top=torch.empty(rows, H, dtype=d, device=dev),
-            logits=torch.empty(rows, self.ldv, dtype=torch.float32, device=dev))
+            logits=torch.empty(rows, self.ldv, dtype=torch.float32, device=dev) if logits else None)
         return ws
 
-    def _step(self, ws, rows, cur, parent):
+    def _step(self, ws, rows, cur, parent, logits=True):
         """One LSTM time step over `rows` rows; A[l][:, in:] must already hold the (gathered) recurrent h."""
         L, H = self.L, self.H
         for l in range(L):
@@ -51,8 +51,21 @@ class LSTMDecoderRT:
             ops.gemm(A, self.Wcat[l], gates, bias=self.bias[l])
             nxt = ws['A'][l + 1][:rows, :H] if l + 1 < L else ws['top'][:rows]
             ops.lstm_cell(gates, ws['c'][cur][l], parent, ws['c'][1 - cur][l][:rows], nxt, ws['hs'][l][:rows])
-        with ops.PROFILE.range('vocab_gemm', 2.0 * rows * self.V * H):
-            ops.gemm(ws['top'][:rows], self.Wc, ws['logits'][:rows, :self.V], bias=self.bc)
+        if logits:
+            with ops.PROFILE.range('vocab_gemm', 2.0 * rows * self.V * H):
+                ops.gemm(ws['top'][:rows], self.Wc, ws['logits'][:rows, :self.V], bias=self.bc)
+
+    def _select(self, pl, rows, rpi, step, done, B, top_k, temperature, unk_index, noise_mode):
+        """classifier + BeamSearchHelper selection for `rows` rows (rnn_models.py:81,87-92,109-113): fused two-pass
+        vocab projection (logits never stored) in tensor-core mode, materialised fp32 logits in check mode."""
+        ws, beam = pl['ws'], pl['beam']
+        if pl['vsel'] is not None:
+            pl['vsel'].run(ws['top'][:rows], self.Wc, self.bc, B, temperature, unk_index, rpi, noise_mode, step, done,
+                           pl['ind'], pl['val'], beam.status, pl['dyn'])
+        else:
+            with ops.PROFILE.range('select_beam'):
+                ops.select_tokens(ws['logits'][:rows, :self.V], self.V, B, top_k, temperature, unk_index, rpi, noise_mode,
+                                  0, 0, step, done, pl['ind'], pl['val'], beam.status, pl['dyn'])
 
     def _recur(self, ws, rows, parent):
         """A[l][:, in:] <- hs[l][parent] for every layer (recurrent operand of the next step)."""
@@ -66,6 +79,7 @@ class LSTMDecoderRT:
         ws, beam, ind, val, dyn, N = pl['ws'], pl['beam'], pl['ind'], pl['val'], pl['dyn'], pl['N']
         start_emb, caption = pl['start'], pl['caption']
         R = N * B
+        fused = pl['vsel'] is not None
         beam.status.zero_()
         for c in ws['c']:
             c.zero_()
@@ -78,20 +92,18 @@ class LSTMDecoderRT:
             if t > 0:
                 ops.gather_rows(self.table, caption[:, t - 1].contiguous(), ws['A'][0][:N, :self.E])
                 self._recur(ws, N, None)
-            self._step(ws, N, cur, None)
+            self._step(ws, N, cur, None, logits=(not fused) and t == p0)
             cur = 1 - cur
-        ops.select_tokens(ws['logits'][:N, :self.V], self.V, B, top_k, temperature, unk_index, 1, noise_mode, 0, 0,
-                          p0, None, ind, val, beam.status, dyn)
+        self._select(pl, N, 1, p0, None, B, top_k, temperature, unk_index, noise_mode)
         beam.init(ind, val, caption, eos_index, True)
         # ---- beam phase (rnn_models.py:105-137): fixed trip count, frozen-at-break on the device
         for i in range(p0 + 1, max_len):
             ops.gather_rows(self.table, beam.last_tok, ws['A'][0][:R, :self.E])
             self._recur(ws, R, beam.parent_state)
-            self._step(ws, R, cur, beam.parent_state)
+            self._step(ws, R, cur, beam.parent_state, logits=not fused)
             cur = 1 - cur
+            self._select(pl, R, B, i, beam.done, B, top_k, temperature, unk_index, noise_mode)
             with ops.PROFILE.range('select_beam'):
-                ops.select_tokens(ws['logits'][:R, :self.V], self.V, B, top_k, temperature, unk_index, B, noise_mode,
-                                  0, 0, i, beam.done, ind, val, beam.status, dyn)
                 beam.step(ind, val, i, max_len, eos_index, True, temperature, noise_mode, 0, 0, dyn)
         beam.final(temperature, noise_mode, 0, 0, max_len + 1, max(p0 + 1, max_len), pad_index, max_len, pl['ids'],
                    pl['lens'], dyn)
@@ -110,7 +122,9 @@ class LSTMDecoderRT:
             if len(self._plans) >= 2:
                 self._plans.clear()
             R = N * B
-            pl = dict(N=N, ws=self._alloc(max(R, N)), beam=ops.Beam(N, B, max(max_len, p0 + 1), dev),
+            fused = ops.FUSED_VOCAB and ops.VocabSelect.supported(self.Wc, self.V, top_k)
+            pl = dict(N=N, ws=self._alloc(max(R, N), logits=not fused),
+                      vsel=ops.VocabSelect(max(R, N), self.V, top_k, dev) if fused else None, beam=ops.Beam(N, B, max(max_len, p0 + 1), dev),
                       ind=torch.empty(R, B, dtype=torch.int32, device=dev),
                       val=torch.empty(R, B, dtype=torch.float32, device=dev),
                       dyn=torch.zeros(2, dtype=torch.int64, device=dev),

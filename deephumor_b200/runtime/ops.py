@@ -54,6 +54,7 @@ class _Profile:
 
 PROFILE = _Profile()
 USE_GRAPHS = os.environ.get('DH_NO_GRAPH', '') == ''   # capture decode loops into CUDA graphs
+FUSED_VOCAB = os.environ.get('DH_NO_FUSED_VOCAB', '') == ''   # two-pass vocab projection, logits never stored
 
 
 def code(t):
@@ -211,6 +212,42 @@ def select_tokens(logits, V, beam, top_k, temperature, unk, rows_per_image, nois
     LIB.call('dh_select_tokens', ptr(logits), _rows(logits), rows, V, beam, top_k, float(temperature), unk,
              rows_per_image, noise_mode, seed, image_base, step, ptr(done), ptr(ind), ptr(val), ptr(status), ptr(dyn),
              stream())
+
+
+class VocabSelect:
+    """Vocab projection fused with token selection for `rows` rows: two bit-identical tcgen05 passes over
+    logits = A W^T + bias (group maxima -> threshold, then candidate compaction), logits never stored."""
+
+    def __init__(self, rows, V, top_k, device):
+        self.rows, self.V, self.top_k = rows, V, top_k
+        self.n_groups = (V + 31) // 32
+        self.cap = min((V + 31) // 32 * 32, 32 * top_k)
+        f32, i32 = dict(dtype=torch.float32, device=device), dict(dtype=torch.int32, device=device)
+        self.gmax = torch.empty(rows, self.n_groups, **f32)
+        self.thresh = torch.empty(rows, **f32)
+        self.count = torch.zeros(rows, **i32)
+        self.idx = torch.empty(rows, self.cap, **i32)
+        self.val = torch.empty(rows, self.cap, **f32)
+
+    @staticmethod
+    def supported(A, V, top_k):
+        return A.dtype in (torch.bfloat16, torch.float16) and top_k <= (V + 31) // 32
+
+    def run(self, A, W, bias, beam, temperature, unk, rows_per_image, noise_mode, step, done, ind, val, status, dyn,
+            seed=0, image_base=0):
+        rows, K = A.shape
+        assert rows <= self.rows and W.shape == (self.V, K) and W.dtype == A.dtype
+        args = (ptr(A), _rows(A), ptr(W), _rows(W), code(A), ptr(bias), rows, self.V, K)
+        with PROFILE.range('vocab_gemm', 2.0 * 2.0 * rows * self.V * K):
+            LIB.call('dh_vocab_groupmax', *args, ptr(self.gmax), self.n_groups, stream())
+            LIB.call('dh_vocab_threshold', ptr(self.gmax), self.n_groups, rows, self.n_groups, self.top_k,
+                     ptr(self.thresh), ptr(self.count), stream())
+            LIB.call('dh_vocab_candidates', *args, ptr(self.thresh), ptr(self.count), ptr(self.idx), ptr(self.val),
+                     self.cap, stream())
+        with PROFILE.range('select_beam'):
+            LIB.call('dh_select_candidates', ptr(self.count), ptr(self.idx), ptr(self.val), self.cap, rows, beam,
+                     self.top_k, float(temperature), unk, rows_per_image, noise_mode, seed, image_base, step, ptr(done), ptr(ind),
+                     ptr(val), ptr(status), ptr(dyn), stream())
 
 
 class Beam:

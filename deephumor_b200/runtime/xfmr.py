@@ -76,6 +76,21 @@ class XfmrDecoderRT:
         beam.status.zero_()
         xkv, emask = self._cross_kv(spatial, N) if self.cross else (None, None)
 
+        vsel = pl['vsel']
+
+        def select(rows, rpi, step_i, done):
+            """classifier + BeamSearchHelper selection (transformers.py:488/736 -> beam.py:32-53): fused two-pass vocab
+            projection in tensor-core mode (logits never stored), materialised fp32 logits in check mode."""
+            if vsel is not None:
+                vsel.run(x[:rows], self.Wc, self.bc, B, temperature, unk_index, rpi, noise_mode, step_i, done, ind, val,
+                         beam.status, dyn)
+            else:
+                with ops.PROFILE.range('vocab_gemm', 2.0 * rows * self.V * D):
+                    ops.gemm(x[:rows], self.Wc, logits[:rows, :self.V], bias=self.bc)
+                with ops.PROFILE.range('select_beam'):
+                    ops.select_tokens(logits[:rows, :self.V], self.V, B, top_k, temperature, unk_index, rpi, noise_mode,
+                                      0, 0, step_i, done, ind, val, beam.status, dyn)
+
         def step(rows, rpi, pos, tokens, seq, src):
             """One new position `pos` for `rows` rows (rpi rows per image)."""
             ops.xfmr_embed(self.tok, self.pos, start_emb, rpi, tokens, None, pos, self.scale, x[:rows])
@@ -96,22 +111,18 @@ class XfmrDecoderRT:
                                   lay['enc_attn.scale'], slot_shared=True, n_keys=49, enc_mask=emask)
                     self._post_attn(lay, 'enc_attn', x, attn, tmp, rows)
                 self._ffn(lay, x, h1, tmp, rows)
-            with ops.PROFILE.range('vocab_gemm', 2.0 * rows * self.V * D):
-                ops.gemm(x[:rows], self.Wc, logits[:rows, :self.V], bias=self.bc)
 
         # ---- prefix phase: positions 0..p0, one row per image (transformers.py:517-529)
         for t in range(p0 + 1):
             tok = None if t == 0 else caption[:, t - 1].contiguous()
             step(N, 1, t, tok, caption, None)
-        ops.select_tokens(logits[:N, :self.V], self.V, B, top_k, temperature, unk_index, 1, noise_mode, 0, 0, p0, None,
-                          ind, val, beam.status, dyn)
+        select(N, 1, p0, None)
         beam.init(ind, val, caption, eos_index, False)
         # ---- beam phase: i = p0+1 .. max_len inclusive (Q10); fixed trip count, frozen-at-break on the device
         for i in range(p0 + 1, max_len + 1):
             step(R, B, i, beam.last_tok, beam.seq, beam.src)
+            select(R, B, i, beam.done)
             with ops.PROFILE.range('select_beam'):
-                ops.select_tokens(logits[:R, :self.V], self.V, B, top_k, temperature, unk_index, B, noise_mode, 0, 0, i,
-                                  beam.done, ind, val, beam.status, dyn)
                 beam.step(ind, val, i, max_len, eos_index, False, temperature, noise_mode, 0, 0, dyn)
         beam.final(temperature, noise_mode, 0, 0, max_len + 1, max_len, self.pad, max_len, pl['ids'], pl['lens'], dyn)
 
@@ -132,8 +143,9 @@ class XfmrDecoderRT:
             self._plans.clear()
             rows_alloc = max(R, N)
             mk = lambda *shape, dtype=dt: torch.empty(*shape, dtype=dtype, device=dev)
-            pl = dict(N=N, x=mk(rows_alloc, D), qb=mk(rows_alloc, D), attn=mk(rows_alloc, D), tmp=mk(rows_alloc, D),
-                      h1=mk(rows_alloc, self.pf), logits=mk(rows_alloc, self.ldv, dtype=torch.float32),
+            fused = ops.FUSED_VOCAB and ops.VocabSelect.supported(self.Wc, self.V, top_k)
+            pl = dict(N=N, vsel=ops.VocabSelect(rows_alloc, self.V, top_k, dev) if fused else None, x=mk(rows_alloc, D), qb=mk(rows_alloc, D), attn=mk(rows_alloc, D), tmp=mk(rows_alloc, D),
+                      h1=mk(rows_alloc, self.pf), logits=None if fused else mk(rows_alloc, self.ldv, dtype=torch.float32),
                       Kc=[torch.zeros(R, S, D, dtype=dt, device=dev) for _ in range(self.L)],
                       Vc=[torch.zeros(R, S, D, dtype=dt, device=dev) for _ in range(self.L)],
                       beam=ops.Beam(N, B, max_len, dev, kv_slots=S),

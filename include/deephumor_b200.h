@@ -24,7 +24,7 @@ extern "C" {
 typedef struct CUstream_st* cudaStream_t;
 #endif
 
-#define DH_VERSION 103
+#define DH_VERSION 104
 
 #define DH_OK 0
 #define DH_ERR_ARG (-1)
@@ -147,6 +147,23 @@ int dh_select_tokens(const float* logits, long long ld, int rows, int V, int bea
                      int rows_per_image, int noise_mode, unsigned long long seed, long long image_base, int step,
                      const unsigned char* done, int* ind, float* val, int* status, const long long* dyn,
                      cudaStream_t stream);
+/* Vocab projection fused with the selection, logits never stored (rnn_models.py:81,109 / transformers.py:488,736 ->
+ * beam.py:32-53).  logits[M,N] = A[M,K] W[N,K]^T + bias (tcgen05, A / W ab_dtype) are produced twice, bit-identically:
+ *   dh_vocab_groupmax    gmax[m, g] = max of logits[m, 32g .. 32g+31]                       (pass 1)
+ *   dh_vocab_threshold   thresh[m] = top_k-th largest of gmax[m, :] (<= the top_k-th largest logit); cand_count[m] = 0
+ *   dh_vocab_candidates  appends (column, logit) of every logit >= thresh[m] to row m's list     (pass 2)
+ *   dh_select_candidates dh_select_tokens on those lists (cand_cap >= min(N, 32 * top_k) cannot overflow, ties aside). */
+int dh_vocab_groupmax(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias, int M,
+                      int N, int K, float* gmax, long long ld_gmax, cudaStream_t stream);
+int dh_vocab_threshold(const float* gmax, long long ld_gmax, int rows, int n_groups, int top_k, float* thresh,
+                       int* cand_count, cudaStream_t stream);
+int dh_vocab_candidates(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias, int M,
+                        int N, int K, const float* thresh, int* cand_count, int* cand_idx, float* cand_val, int cand_cap,
+                        cudaStream_t stream);
+int dh_select_candidates(const int* cand_count, const int* cand_idx, const float* cand_val, int cand_cap, int rows,
+                         int beam, int top_k, float temperature, int unk, int rows_per_image, int noise_mode,
+                         unsigned long long seed, long long image_base, int step, const unsigned char* done, int* ind,
+                         float* val, int* status, const long long* dyn, cudaStream_t stream);
 int dh_beam_init(const dh_beam_state* st, const int* ind0, const float* val0, const int* prefix, long long prefix_ld,
                  int prefix_rows, int prefix_len, int n_img, int beam, int eos, int lstm_semantics, cudaStream_t stream);
 int dh_beam_step(const dh_beam_state* st, const int* new_ind, const float* new_val, int n_img, int beam, int step,

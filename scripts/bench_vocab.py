@@ -30,3 +30,17 @@ print('gemm+select', t(both))
 # bf16 logits variant
 out16=torch.empty(M,ldc+(-ldc)%8,dtype=torch.bfloat16,device=dev)
 print('bf16 out', t(lambda: ops.gemm(A,W,out16[:,:N],bias=b)))
+# fused two-pass path (logits never stored)
+from deephumor_b200._lib import LIB, ptr, stream
+vs = ops.VocabSelect(M, N, 50, dev)
+Ab = A
+args = (ptr(Ab), K, ptr(W), K, 1, ptr(b), M, N, K)
+print('pass1 groupmax', t(lambda: LIB.call('dh_vocab_groupmax', *args, ptr(vs.gmax), vs.n_groups, stream())))
+print('threshold     ', t(lambda: LIB.call('dh_vocab_threshold', ptr(vs.gmax), vs.n_groups, M, vs.n_groups, 50, ptr(vs.thresh), ptr(vs.count), stream())))
+def p2():
+    vs.count.zero_()
+    LIB.call('dh_vocab_candidates', *args, ptr(vs.thresh), ptr(vs.count), ptr(vs.idx), ptr(vs.val), vs.cap, stream())
+print('pass2 candidates (+zero)', t(p2))
+print('select_candidates', t(lambda: LIB.call('dh_select_candidates', ptr(vs.count), ptr(vs.idx), ptr(vs.val), vs.cap, M, 5, 50, 1.0, 1, 5, 1, 1, 0, 3, None, ptr(ind), ptr(val), ptr(status), None, stream())))
+print('fused total', t(lambda: vs.run(A, W, b, 5, 1.0, 1, 5, 1, 3, None, ind, val, status, None, seed=1)))
+print('candidates per row: mean %.1f max %d' % (float(vs.count.float().mean()), int(vs.count.max())))

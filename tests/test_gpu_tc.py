@@ -97,3 +97,43 @@ def test_stem_im2col_gemm(dt):
     ops.gemm(A, wp.to(dt).to(DEV), y, bias=b.to(DEV), relu=True)
     ref = F.relu(F.conv2d(img.to(dt).double(), w.to(dt).double(), b.double(), 2, 3)).float().permute(0, 2, 3, 1).reshape(-1, 64)
     assert H.rel_err(y.float(), ref) < (4e-3 if dt == torch.bfloat16 else 5e-4)
+
+
+@pytest.mark.parametrize('mode', ['deterministic', 'injected'])
+@pytest.mark.parametrize('rows,V,K_,B,top_k,T', [(300, 36541, 512, 5, 50, 1.0), (7, 1000, 64, 3, 10, 0.8), (130, 4099, 128, 1, 1, 1.3),
+                                                 (64, 2048, 256, 4, 64, 1.0), (5, 71, 64, 2, 2, 1.0), (5, 100, 64, 1, 1, 1.0)])
+def test_fused_vocab_select_matches_materialised_logits(mode, rows, V, K_, B, top_k, T):
+    """Two-pass vocab projection (group maxima -> threshold -> candidate compaction, logits never stored) picks
+    exactly what dh_select_tokens and the CPU oracle pick on the materialised logits of the same tcgen05 product."""
+    from oracle import model as omodel, noise as onoise
+    g = torch.Generator().manual_seed(V + rows)
+    A = (torch.randn(rows, K_, generator=g) * 0.5).to(torch.bfloat16).to(DEV)
+    W = (torch.randn(V, K_, generator=g) * 0.2).to(torch.bfloat16).to(DEV)
+    bias = torch.randn(V, generator=g).to(DEV)
+    if top_k > 1 or rows == 5:
+        bias[1] = 50.0                                    # <unk> is always in the top-k: masked but counted (Q3)
+    rpi = 1 if rows % B else B
+    ldv = (V + 3) // 4 * 4
+    logits = torch.empty(rows, ldv, device=DEV)
+    ops.gemm(A, W, logits[:, :V], bias=bias)
+    mk = lambda: (torch.empty(rows, B, dtype=torch.int32, device=DEV), torch.empty(rows, B, device=DEV),
+                  torch.zeros(1, dtype=torch.int32, device=DEV))
+    ind0, val0, st0 = mk()
+    ops.select_tokens(logits[:, :V], V, B, top_k, T, 1, rpi, ops.NOISE[mode], 11, 5, 3, None, ind0, val0, st0)
+    assert ops.VocabSelect.supported(A, V, top_k)
+    vs = ops.VocabSelect(rows, V, top_k, DEV)
+    ind1, val1, st1 = mk()
+    vs.run(A, W, bias, B, T, 1, rpi, ops.NOISE[mode], 3, None, ind1, val1, st1, None, seed=11, image_base=5)
+    torch.cuda.synchronize()
+    assert int(st0.item()) == int(st1.item())
+    if top_k == 1 and rows == 5:
+        assert int(st1.item()) & 1                        # every row filtered (arg-max is <unk>): EMPTY_ROW like Q3
+        return
+    assert torch.equal(ind0, ind1) and torch.equal(val0, val1)
+    assert int(vs.count.max()) <= vs.cap and int(vs.count.min()) >= min(top_k, V)
+    lc = logits[:, :V].cpu()
+    for r in range(0, rows, max(1, rows // 7)):
+        q = None if mode == 'deterministic' else torch.stack([onoise.exp_noise(11, 5 + r // rpi, 3, 0, r % rpi, V)])
+        oi, ov = omodel.select_tokens(lc[r:r + 1], B, T, top_k, 1, q, None)
+        assert ind1[r].cpu().tolist() == oi[0].tolist()
+        assert torch.allclose(val1[r].cpu(), ov[0], atol=1e-5)
