@@ -1,0 +1,305 @@
+// Fused ResNet-50 stem for sm_100a: conv 7x7/2 (3 -> 64, BN folded) + ReLU + maxpool 3x3/2, straight from the NCHW fp32
+// image to the NHWC 56x56x64 tensor that layer1 reads (torchvision resnet.py:197-200,268-271 <- encoders.py:56).
+//
+// The stem's A operand cannot come from im2col-mode TMA (a pixel is 3 channels = 6 B, below TMA's 16 B granule) and
+// materialising it in HBM costs 4.8 MB/image.  Here the CTA builds it in shared memory itself:
+//
+//   work item   = one image x two pooled rows (112 pooled pixels = the 128 TMEM lanes of one accumulator, 16 idle)
+//   input band  = the 15 input rows those pixels depend on, fp32 -> half, pixel-interleaved [row][col][rgb] in smem
+//   tap (dy,dx) = the conv output at (2py-1+dy, 2px-1+dx) of EVERY lane's pooled pixel: one 128 x 64 x 192 UMMA
+//                 (tcgen05.mma kind::f16, fp32 accumulators in TMEM) whose A tile the 256 threads gather from the band
+//                 with 4-byte loads and write 128B-swizzled (K layout: 7 kernel rows x 22 slots = 21 (s,c) values + one
+//                 junk value that meets a zero weight; padded to 192 with zeros)
+//   pooling     = max over the 9 taps' accumulators of a lane, in registers (+bias, ReLU after the max: both monotone);
+//                 taps that fall into the pool's padding are skipped per lane.
+//
+// Computing each conv pixel once per pooling window costs 2.25x the conv FLOPs (0.53 GFLOP/image on a >1 PFLOP/s pipe)
+// and removes every intermediate from HBM: the kernel reads 602 KB and writes 401 KB per image.
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kPitch = 696;                 // halves per band row: (5 + 224 + 2 pad pixels) * 3 channels + junk, even
+constexpr int kBandRows = 15;
+constexpr int kKp = 192;                    // padded K: 7 * 22 = 154 real slots
+constexpr int kABytes = 3 * 128 * 128;      // A tile: 3 K-chunks of [128 rows x 128 B]
+constexpr int kWBytes = 3 * 64 * 128;       // W tile: 3 K-chunks of [64 rows x 128 B]
+constexpr int kBandBytes = kBandRows * kPitch * 2;
+constexpr int kSmemBytes = 1024 + 2 * kABytes + kWBytes + ((kBandBytes + 127) / 128) * 128 + 256 + 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity))
+    if (clock64() - t0 > 4000000000ll) __trap();   // a protocol bug must fail the launch, never hang the GPU
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// K-major, 128B-swizzled operand tile: start >> 4 | SBO = 1024 B | descriptor version 1 | SWIZZLE_128B (see gemm_tc.cu).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <typename T> struct Pack2;
+template <> struct Pack2<__half> {
+  static __device__ __forceinline__ uint32_t f(float a, float b) { __half2 t = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&t); }
+};
+template <> struct Pack2<__nv_bfloat16> {
+  static __device__ __forceinline__ uint32_t f(float a, float b) { __nv_bfloat162 t = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&t); }
+};
+
+// images [n,3,224,224] fp32; wp [64][192] T (k = r*22 + s*3 + c, zero elsewhere); bias [64]; out [n,56,56,64] T.
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+stem_pool_kernel(const float* __restrict__ images, const T* __restrict__ wp, const float* __restrict__ bias,
+                 T* __restrict__ out, int n_img) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t a_buf[2] = {base, base + (uint32_t)kABytes};
+  const uint32_t w_buf = base + 2u * kABytes;
+  T* band = reinterpret_cast<T*>(gbase + 2 * kABytes + kWBytes);
+  constexpr int kBandPad = ((kBandBytes + 127) / 128) * 128;
+  float* bias_s = reinterpret_cast<float*>(gbase + 2 * kABytes + kWBytes + kBandPad);
+  const uint32_t bars = base + 2u * kABytes + kWBytes + kBandPad + 256u;     // a_free[2], grp_done[3]
+  uint32_t* tmem_word = reinterpret_cast<uint32_t*>(gbase + 2 * kABytes + kWBytes + kBandPad + 256 + 64);
+  auto a_free = [&](int b) { return bars + 8u * b; };
+  auto grp_done = [&](int g) { return bars + 8u * (2 + g); };
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // ---- one-time setup: barriers, TMEM, zeroed A tiles / band (pad columns, K padding and idle rows stay zero), weights
+  if (tid == 0) {
+    for (int i = 0; i < 5; ++i) mbar_init(bars + 8u * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_word)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i < (2 * kABytes + kWBytes + kBandPad) / 16; i += kThreads)
+    *reinterpret_cast<uint4*>(gbase + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+  if (tid < 64) bias_s[tid] = bias[tid];
+  __syncthreads();
+  for (int i = tid; i < 64 * (kKp / 8); i += kThreads) {     // 16 B chunks of wp -> swizzled K-major tiles
+    const int row = i / (kKp / 8), c = i % (kKp / 8);
+    const uint4 v = *reinterpret_cast<const uint4*>(wp + row * kKp + c * 8);
+    sts128(w_buf + (uint32_t)((c >> 3) * 64 * 128 + row * 128 + (((c & 7) ^ (row & 7)) << 4)), v.x, v.y, v.z, v.w);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_word);
+  // kind::f16 instruction descriptor: D fp32, A/B half (0) or bf16 (1), K-major, N = 64, M = 128
+  const uint32_t fmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
+  const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+  // builder role: row m of the A tile, half 0 = kernel rows 0..3 (chunks 0..10), half 1 = rows 4..6 (chunks 11..19)
+  const int m = tid & 127, half = tid >> 7;
+  const int m_py = m / 56, m_px = m - m_py * 56;
+  const bool m_ok = m < 112;
+  // epilogue role: TMEM lane quadrant q, channel half ch0
+  const int q = warp & 3, ch0 = (warp >> 2) * 32;
+  const int e_m = q * 32 + lane;
+  const int e_py = e_m / 56, e_px = e_m - e_py * 56;
+  const bool e_ok = e_m < 112;
+
+  const int items = n_img * 28;
+  uint32_t uses[2] = {0u, 0u};      // completed-use counters of the two A buffers (uniform across the CTA)
+  uint32_t it = 0;
+  for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+    const int img = item / 28, py0 = (item - img * 28) * 2;
+    // ---- input band: rows 4*py0-5 .. 4*py0+9, fp32 NCHW -> T [row][5 + col][rgb]   (previous item's MMAs are all
+    //      complete: its last accumulator group was drained before this point, so the band may be overwritten)
+    const float* src = images + (long long)img * 3 * 224 * 224;
+    for (int i = tid; i < 3 * kBandRows * 56; i += kThreads) {
+      const int c4 = i % 56, rr = (i / 56) % kBandRows, c = i / (56 * kBandRows);
+      const int gr = 4 * py0 - 5 + rr;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gr >= 0 && gr < 224) v = __ldg(reinterpret_cast<const float4*>(src + ((long long)c * 224 + gr) * 224) + c4);
+      T* d = band + rr * kPitch + (5 + 4 * c4) * 3 + c;
+      d[0] = dh_from_f<T>(v.x); d[3] = dh_from_f<T>(v.y); d[6] = dh_from_f<T>(v.z); d[9] = dh_from_f<T>(v.w);
+    }
+    __syncthreads();
+
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = -INFINITY;
+    auto drain = [&](int slot, int dy, int dx) {
+      uint32_t v[32];
+      tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 64 + ch0), v);
+      const bool valid = !((dy == 0 && py0 + e_py == 0) || (dx == 0 && e_px == 0));   // pool padding (-inf) is skipped
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], __uint_as_float(v[j]));
+      }
+    };
+
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+      const int dy = tap / 3, dx = tap - dy * 3;
+      const int b = tap & 1;
+      if (uses[b] > 0) mbar_wait(a_free(b), (uses[b] - 1) & 1u);     // MMAs of the previous use have read the buffer
+      if (tap == 8) {
+        // accumulator slots 0..3 (taps 0..3) are reused by tap 8: drain them first
+        mbar_wait(grp_done(0), it & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int s = 0; s < 4; ++s) drain(s, s / 3, s % 3);
+        tc_fence_before();
+      }
+      if (m_ok) {
+        const uint32_t* rowp = reinterpret_cast<const uint32_t*>(band + (4 * m_py + 2 * dy) * kPitch + 12 * m_px + 6 * dx);
+        const uint32_t arow = a_buf[b] + (uint32_t)(m * 128);
+        const uint32_t sw = (uint32_t)(m & 7);
+        if (half == 0) {
+          uint32_t w[44];
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int j = 0; j < 11; ++j) w[r * 11 + j] = rowp[r * (kPitch / 2) + j];
+#pragma unroll
+          for (int c = 0; c < 11; ++c)
+            sts128(arow + (uint32_t)((c >> 3) * 128 * 128) + ((((uint32_t)c & 7u) ^ sw) << 4), w[4 * c], w[4 * c + 1],
+                   w[4 * c + 2], w[4 * c + 3]);
+        } else {
+          uint32_t w[36];
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int j = 0; j < 11; ++j) w[r * 11 + j] = rowp[(4 + r) * (kPitch / 2) + j];
+          w[33] = 0u; w[34] = 0u; w[35] = 0u;
+#pragma unroll
+          for (int c = 0; c < 9; ++c) {
+            const int cc = 11 + c;
+            sts128(arow + (uint32_t)((cc >> 3) * 128 * 128) + ((((uint32_t)cc & 7u) ^ sw) << 4), w[4 * c], w[4 * c + 1],
+                   w[4 * c + 2], w[4 * c + 3]);
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t slot = tap == 8 ? 0u : (uint32_t)tap;
+        const uint32_t tmem_d = tmem_base + slot * 64u;
+#pragma unroll
+        for (int kc = 0; kc < 3; ++kc) {
+          const uint64_t da = umma_desc(a_buf[b] + (uint32_t)(kc * 128 * 128));
+          const uint64_t db = umma_desc(w_buf + (uint32_t)(kc * 64 * 128));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
+        }
+        tc_commit(a_free(b));
+        if (tap == 3) tc_commit(grp_done(0));
+        if (tap == 7) tc_commit(grp_done(1));
+        if (tap == 8) tc_commit(grp_done(2));
+      }
+      ++uses[b];
+    }
+    // ---- drain taps 4..7 and 8, then bias + ReLU + store (32 channels = 64 B per thread)
+    mbar_wait(grp_done(1), it & 1u);
+    tc_fence_after();
+#pragma unroll
+    for (int s = 4; s < 8; ++s) drain(s, s / 3, s % 3);
+    mbar_wait(grp_done(2), it & 1u);
+    tc_fence_after();
+    drain(0, 2, 2);
+    tc_fence_before();
+    if (e_ok) {
+      uint32_t o[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        o[j] = Pack2<T>::f(fmaxf(acc[2 * j] + bias_s[ch0 + 2 * j], 0.f), fmaxf(acc[2 * j + 1] + bias_s[ch0 + 2 * j + 1], 0.f));
+      T* dst = out + (((long long)img * 56 + py0 + e_py) * 56 + e_px) * 64 + ch0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(dst + 8 * j) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    }
+    __syncthreads();     // every warp is past its TMEM reads and band reads before the next item overwrites them
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+int g_sms = 0;
+
+}  // namespace
+
+// images [n,3,224,224] fp32 NCHW; w_packed [64][192] (k = r*22 + s*3 + c, BN folded, zeros elsewhere) and out
+// [n,56,56,64] NHWC of dtype (DH_F16 / DH_BF16); bias fp32 [64].
+extern "C" int dh_stem_pool_tc(const float* images_nchw, const void* w_packed, const float* bias, void* out, int n, int H,
+                               int W, int dtype, cudaStream_t stream) {
+  DH_ARG(images_nchw && w_packed && bias && out && n >= 0);
+  DH_ARG(H == 224 && W == 224);
+  DH_ARG(dtype == DH_F16 || dtype == DH_BF16);
+  DH_ARG(((uintptr_t)images_nchw % 16) == 0 && ((uintptr_t)w_packed % 16) == 0 && ((uintptr_t)out % 16) == 0);
+  if (n == 0) return DH_OK;
+  if (!g_sms) {
+    int dev = 0;
+    DH_CUDA(cudaGetDevice(&dev));
+    DH_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+    DH_CUDA(cudaFuncSetAttribute(stem_pool_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    DH_CUDA(cudaFuncSetAttribute(stem_pool_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  }
+  const int items = n * 28;
+  const int grid = items < g_sms ? items : g_sms;
+  if (dtype == DH_F16)
+    stem_pool_kernel<__half><<<grid, kThreads, kSmemBytes, stream>>>(images_nchw, (const __half*)w_packed, bias, (__half*)out, n);
+  else
+    stem_pool_kernel<__nv_bfloat16><<<grid, kThreads, kSmemBytes, stream>>>(images_nchw, (const __nv_bfloat16*)w_packed, bias,
+                                                                            (__nv_bfloat16*)out, n);
+  DH_LAUNCH_OK();
+  return DH_OK;
+}

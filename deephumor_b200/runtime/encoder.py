@@ -53,6 +53,12 @@ class EncoderRT:
             wp = torch.zeros(w.shape[0], 192)
             wp[:, :147] = w.permute(0, 2, 3, 1).reshape(w.shape[0], 147)
             self.stem_w = wp.contiguous().to(device=device, dtype=tdtype)
+            # fused stem + maxpool kernel: K slot r*22 + s*3 + c (csrc/stem_tc.cu)
+            wf = torch.zeros(w.shape[0], 7, 22)
+            wf[:, :, :21] = w.permute(0, 2, 3, 1).reshape(w.shape[0], 7, 21)
+            wq = torch.zeros(w.shape[0], 192)
+            wq[:, :154] = wf.reshape(w.shape[0], 154)
+            self.stem_wq = wq.contiguous().to(device=device, dtype=tdtype)
         self.blocks = []
         for li, nblk in enumerate(RESNET_BLOCKS):
             for b in range(nblk):
@@ -100,6 +106,10 @@ class EncoderRT:
     def trunk(self, images):
         """images [n,3,224,224] fp32 NCHW (device) -> features [n,7,7,2048] NHWC in the trunk storage dtype."""
         n, _, H, W = images.shape
+        if self.tdtype != torch.float32 and H == 224 and W == 224 and ops.FUSED_STEM:
+            x = self._buf('pool', (n, 56, 56, 64))
+            ops.stem_pool(images, self.stem_wq, self.stem.bias, x)
+            return self._layers(x)
         if self.tdtype != torch.float32:
             Ho = (H + 6 - 7) // 2 + 1
             A = self._buf('stemA', (n * Ho * Ho, 192))
@@ -112,7 +122,9 @@ class EncoderRT:
             x = self._conv('stem', x, self.stem, True)
         y = self._buf('pool', (n, x.shape[1] // 2, x.shape[2] // 2, 64))
         ops.maxpool3x3s2(x, y)
-        x = y
+        return self._layers(y)
+
+    def _layers(self, x):
         for i, blk in enumerate(self.blocks):
             y1 = self._conv(f'b{i}c1', x, blk['c1'], True)
             y2 = self._conv(f'b{i}c2', y1, blk['c2'], True)

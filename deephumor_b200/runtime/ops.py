@@ -54,6 +54,7 @@ class _Profile:
 
 PROFILE = _Profile()
 USE_GRAPHS = os.environ.get('DH_NO_GRAPH', '') == ''   # capture decode loops into CUDA graphs
+FUSED_STEM = os.environ.get('DH_NO_FUSED_STEM', '') == ''     # conv1 + ReLU + maxpool in one tcgen05 kernel
 FUSED_VOCAB = os.environ.get('DH_NO_FUSED_VOCAB', '') == ''   # two-pass vocab projection, logits never stored
 
 
@@ -113,6 +114,14 @@ def im2col_nhwc(x, A, kh, kw, stride, pad):
     n, H, W, C = x.shape
     assert x.is_contiguous() and A.is_contiguous() and x.dtype in (torch.bfloat16, torch.float16)
     LIB.call('dh_im2col_nhwc', ptr(x), ptr(A), n, H, W, C, kh, kw, stride, pad, stream())
+
+
+def stem_pool(images, w_packed, bias, out):
+    """images [n,3,224,224] fp32 NCHW -> out [n,56,56,64] NHWC (conv 7x7/2 + BN + ReLU + maxpool 3x3/2, fused)."""
+    n, c, H, W = images.shape
+    assert c == 3 and images.is_contiguous() and images.dtype == torch.float32 and out.is_contiguous()
+    assert w_packed.shape == (64, 192) and w_packed.dtype == out.dtype and w_packed.is_contiguous()
+    LIB.call('dh_stem_pool_tc', ptr(images), ptr(w_packed), ptr(bias), ptr(out), n, H, W, code(out), stream())
 
 
 def maxpool3x3s2(x, y):

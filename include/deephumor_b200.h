@@ -24,7 +24,7 @@ extern "C" {
 typedef struct CUstream_st* cudaStream_t;
 #endif
 
-#define DH_VERSION 104
+#define DH_VERSION 105
 
 #define DH_OK 0
 #define DH_ERR_ARG (-1)
@@ -95,6 +95,12 @@ int dh_im2col_stem(const float* images_nchw, void* A, int n, int H, int W, int k
                    int k_padded, int out_dtype, cudaStream_t stream);
 int dh_im2col_nhwc(const void* x, void* A, int n, int H, int W, int C, int kh, int kw, int stride, int pad,
                    cudaStream_t stream);
+/* Fused stem (encoders.py:56 -> torchvision resnet.py:197-200,268-271): conv 7x7/2 pad 3 (3 -> 64, BN folded) + ReLU +
+ * maxpool 3x3/2 pad 1 from the NCHW fp32 image to NHWC [n,56,56,64] of dtype (DH_F16 / DH_BF16); the im2col operand is
+ * built in shared memory and contracted on tcgen05, pooling happens on the accumulators.  H = W = 224 only.
+ * w_packed [64][192] of dtype: element [o][r*22 + s*3 + c] = folded weight [o][c][r][s], zero elsewhere. */
+int dh_stem_pool_tc(const float* images_nchw, const void* w_packed, const float* bias, void* out, int n, int H, int W,
+                    int dtype, cudaStream_t stream);
 /* watchdog code left by gemm_tc_kernel before it traps (0 = none). */
 int dh_tc_error_flag(int* out_host);
 

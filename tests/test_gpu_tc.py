@@ -137,3 +137,33 @@ def test_fused_vocab_select_matches_materialised_logits(mode, rows, V, K_, B, to
         oi, ov = omodel.select_tokens(lc[r:r + 1], B, T, top_k, 1, q, None)
         assert ind1[r].cpu().tolist() == oi[0].tolist()
         assert torch.allclose(val1[r].cpu(), ov[0], atol=1e-5)
+
+
+def _pack_stem(w, dt):
+    wf = torch.zeros(64, 7, 22)
+    wf[:, :, :21] = w.permute(0, 2, 3, 1).reshape(64, 7, 21)
+    wq = torch.zeros(64, 192)
+    wq[:, :154] = wf.reshape(64, 154)
+    return wq.to(dt).to(DEV)
+
+
+@pytest.mark.parametrize('n', [1, 3, 160])
+@pytest.mark.parametrize('dt', [torch.float16, torch.bfloat16])
+def test_fused_stem_pool(dt, n):
+    """conv 7x7/2 + bias + ReLU + maxpool 3x3/2 in one tcgen05 kernel (im2col built in smem, pooling on the
+    accumulators) against torch on the same half-rounded image / weights; edges exercise both paddings."""
+    img = rnd(n, 3, 224, 224, seed=n)
+    img[0, :, :4, :] = 3.0                                 # make the top/left borders matter
+    img[0, :, :, :4] = -2.0
+    w, b = rnd(64, 3, 7, 7, seed=2, scale=0.1), rnd(64, seed=3)
+    out = torch.empty(n, 56, 56, 64, dtype=dt, device=DEV)
+    ops.stem_pool(img.to(DEV), _pack_stem(w, dt), b.to(DEV), out)
+    torch.cuda.synchronize()
+    k = min(n, 4)
+    sel = list(range(k - 1)) + [n - 1]
+    x = img[sel].to(dt).to(DEV).double()
+    ref = F.max_pool2d(F.relu(F.conv2d(x, w.to(dt).to(DEV).double(), b.to(DEV).double(), 2, 3)), 3, 2, 1)
+    ref = ref.float().permute(0, 2, 3, 1)
+    got = out[sel].float()
+    assert H.rel_err(got, ref) < (4e-3 if dt == torch.bfloat16 else 5e-4)
+    assert float((got - ref).abs().max()) < (0.05 if dt == torch.bfloat16 else 0.01)
