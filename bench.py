@@ -160,9 +160,10 @@ def run_ours(args):
         return shard.gather_captions(ids, lens, total=batch * world)
 
     def step_e2e():
-        img = host_images.to(dev, non_blocking=True)
+        # the user-facing call with HOST buffers: generate() streams the pinned images to the device in chunks
+        # (copy of chunk k+1 overlapping the trunk of chunk k) and the ids / lengths are read back
         lab = host_labels.to(dev, non_blocking=True) if host_labels is not None else None
-        ids, lens = step(img, lab)
+        ids, lens = step(host_images, lab)
         return ids.cpu(), (lens.cpu() if lens is not None else None)
 
     def timed(fn, steps, profile=False):

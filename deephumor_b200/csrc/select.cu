@@ -249,85 +249,218 @@ __global__ void __launch_bounds__(kSelThreads) select_tokens_kernel(SelParams p)
 // t0[row] = top_k-th largest of the row's 32-column group maxima (a lower bound of the row's top_k-th largest logit:
 // the group maxima are n_groups distinct logits).  At most top_k groups have a maximum > t0, so -- ties aside -- at most
 // 32 * top_k logits are >= t0 and the candidate capacity 32 * top_k of dh_vocab_candidates cannot overflow.
-// One CTA (kThrThreads) per row: per-thread maxima give a first bound, group maxima above it are ranked exactly.
-constexpr int kThrThreads = 128;
-constexpr int kThrCap = 1024;
-__global__ void __launch_bounds__(kThrThreads) vocab_threshold_kernel(const float* __restrict__ gmax, long long ld, int n_groups,
-                                                                     int top_k, float* __restrict__ thresh,
-                                                                     int* __restrict__ cand_count) {
-  __shared__ float lm[kThrThreads];
-  __shared__ float cand[kThrCap];
-  __shared__ int s_n;
-  __shared__ float s_t1, s_t0;
-  const int r = blockIdx.x, tid = threadIdx.x;
+// One WARP per row, no block-level synchronisation: the two largest values of every lane's strided slice are 64
+// distinct group maxima whose top_k-th largest is a first bound t1 (top_k <= 64); group maxima >= t1 (a few more than
+// top_k) are then compacted per warp and ranked exactly.
+constexpr int kThrWarps = 8;
+constexpr int kThrCap = 256;
+__global__ void __launch_bounds__(kThrWarps * 32) vocab_threshold_kernel(const float* __restrict__ gmax, long long ld, int rows,
+                                                                        int n_groups, int top_k, float* __restrict__ thresh,
+                                                                        int* __restrict__ cand_count) {
+  __shared__ float s_top[kThrWarps][64];
+  __shared__ float s_cand[kThrWarps][kThrCap];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * kThrWarps + w;
+  if (r >= rows) return;
   const float* row = gmax + (long long)r * ld;
-  float mx = -INFINITY;
-  for (int i = tid; i < n_groups; i += kThrThreads) mx = fmaxf(mx, row[i]);
-  lm[tid] = mx;
-  if (tid == 0) { s_n = 0; s_t1 = -INFINITY; s_t0 = -INFINITY; }
-  __syncthreads();
-  if (top_k <= kThrThreads && top_k <= n_groups) {
-    int rank = 0;
-    for (int j = 0; j < kThrThreads; ++j) { const float o = lm[j]; rank += (o > mx) || (o == mx && j < tid); }
-    if (rank == top_k - 1) s_t1 = mx;
-  }
-  __syncthreads();
-  const float t1 = s_t1;
+  float t0 = -INFINITY;
   if (top_k <= n_groups) {
-    for (int i = tid; i < n_groups; i += kThrThreads) {
-      const float x = row[i];
-      if (x >= t1) { const int slot = atomicAdd(&s_n, 1); if (slot < kThrCap) cand[slot] = x; }
-    }
-    __syncthreads();
-    const int n = s_n;
-    if (n <= kThrCap) {
-      for (int c = tid; c < n; c += kThrThreads) {
-        const float v = cand[c];
-        int gt = 0, ge = 0;
-        for (int j = 0; j < n; ++j) { const float o = cand[j]; gt += o > v; ge += o >= v; }
-        if (gt < top_k && top_k <= ge) s_t0 = v;
+    float t1 = -INFINITY;
+    if (top_k <= 64) {
+      float m1 = -INFINITY, m2 = -INFINITY;
+      for (int i0 = 0; i0 < n_groups; i0 += 256) {       // 8 independent loads in flight per lane
+        float x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * 32 + lane;
+          x[u] = i < n_groups ? __ldg(row + i) : -INFINITY;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float hi = fmaxf(m1, x[u]);
+          m2 = fmaxf(m2, fminf(m1, x[u]));
+          m1 = hi;
+        }
       }
-    } else if (tid == 0) {
-      s_t0 = t1;      // too many ties to rank: fall back to the looser (still valid) bound
+      s_top[w][lane] = m1;
+      s_top[w][32 + lane] = m2;
+      __syncwarp();
+      int r1 = 0, r2 = 0;
+      for (int j = 0; j < 64; ++j) {
+        const float o = s_top[w][j];
+        r1 += (o > m1) || (o == m1 && j < lane);
+        r2 += (o > m2) || (o == m2 && j < 32 + lane);
+      }
+      if (r1 == top_k - 1) t1 = m1;
+      if (r2 == top_k - 1) t1 = m2;
+      t1 = dh_warp_max(t1);            // exactly one slot has that rank; if it holds -inf (n_groups < 64) t1 stays -inf
+    }
+    int n = 0;
+    for (int i0 = 0; i0 < n_groups; i0 += 256) {
+      float x[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * 32 + lane;
+        x[u] = i < n_groups ? __ldg(row + i) : -INFINITY;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const bool keep = (i0 + u * 32 + lane) < n_groups && x[u] >= t1;
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+          const int pos = n + __popc(mask & ((1u << lane) - 1u));
+          if (pos < kThrCap) s_cand[w][pos] = x[u];
+        }
+        n += __popc(mask);
+      }
+    }
+    __syncwarp();
+    if (n <= kThrCap) {
+      for (int c = lane; c < n; c += 32) {
+        const float v = s_cand[w][c];
+        int gt = 0, ge = 0;
+        for (int j = 0; j < n; ++j) { const float o = s_cand[w][j]; gt += o > v; ge += o >= v; }
+        if (gt < top_k && top_k <= ge) t0 = v;
+      }
+      t0 = dh_warp_max(t0);
+    } else {
+      t0 = t1;        // too many to rank here (large top_k or massive ties): the looser bound is still valid
     }
   }
-  __syncthreads();
-  if (tid == 0) { thresh[r] = s_t0; cand_count[r] = 0; }
+  if (lane == 0) { thresh[r] = t0; cand_count[r] = 0; }
 }
 
-// Selection from the candidate lists written by dh_vocab_candidates (unordered: the slots were handed out by atomics;
-// they are sorted by column first so that every floating-point reduction below is run-to-run deterministic).
-constexpr int kCandThreads = 128;
-__global__ void __launch_bounds__(kCandThreads) select_candidates_kernel(SelParams p, const int* __restrict__ cand_count,
-                                                                        const int* __restrict__ cand_idx,
-                                                                        const float* __restrict__ cand_val, int cap) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int scap = cap < kSurvCap ? cap : kSurvCap;
-  int* surv_idx = reinterpret_cast<int*>(smem_raw);             // [scap]
-  float* surv_val = reinterpret_cast<float*>(surv_idx + scap);  // [scap]
-  float* surv_score = surv_val + scap;                          // [scap]
-  int* tmp_idx = reinterpret_cast<int*>(surv_score);            // sort scratch aliases the score array + tail
-  const int r = blockIdx.x, tid = threadIdx.x;
-  const int img = r / p.rpi;
-  if (p.done && p.done[img]) return;
-  int nc = cand_count[r];
-  if (nc > scap) {
-    if (tid == 0) atomicOr(p.status, DH_STATUS_TOO_MANY_TIES);
-    nc = scap;
+// Warp-level selection from a row's candidate list (written by dh_vocab_candidates in atomic-slot order): exact top_k-th
+// largest (ties kept, Q3), survivors compacted and sorted by column so every floating-point reduction is run-to-run
+// deterministic, softmax(l/T), Exp(1)-race draw of B ids, log_softmax scores over the picks (models/beam.py:32-53,79).
+constexpr int kWarpCap = 256;
+struct WarpSel {
+  int* a_idx; float* a_val;     // [kWarpCap] staged raw candidates, later the survivors sorted by column
+  int* t_idx; float* t_val;     // [kWarpCap] unsorted survivors
+  float* score;                 // [kWarpCap]
+  int* pick_idx; float* pick_logit;   // [kMaxBeam]
+};
+constexpr int kWarpSelBytes = 5 * kWarpCap * 4 + 2 * kMaxBeam * 4;
+
+__device__ void warp_select(const SelParams& p, int r, int img, int nc_total, const int* __restrict__ gi,
+                            const float* __restrict__ gv, int cap, WarpSel w) {
+  const int lane = threadIdx.x & 31;
+  int nc = nc_total;
+  if (nc > cap) {
+    if (lane == 0) atomicOr(p.status, DH_STATUS_TOO_MANY_TIES);
+    nc = cap;
   }
-  const int* gi = cand_idx + (long long)r * cap;
-  const float* gv = cand_val + (long long)r * cap;
-  for (int c = tid; c < nc; c += kCandThreads) tmp_idx[c] = gi[c];
-  __syncthreads();
-  for (int c = tid; c < nc; c += kCandThreads) {
-    const int id = tmp_idx[c];
+  const bool staged = nc <= kWarpCap;
+  if (staged)
+    for (int c = lane; c < nc; c += 32) { w.a_idx[c] = gi[c]; w.a_val[c] = gv[c]; }
+  __syncwarp();
+  const int* ii = staged ? w.a_idx : gi;
+  const float* vv = staged ? w.a_val : gv;
+  // ---- exact k-th largest among the candidates: #{> v} < top_k <= #{>= v}; -inf if fewer than top_k candidates
+  float kth = -INFINITY;
+  for (int c = lane; c < nc; c += 32) {
+    const float v = vv[c];
+    int gt = 0, ge = 0;
+    for (int j = 0; j < nc; ++j) { const float o = vv[j]; gt += o > v; ge += o >= v; }
+    if (gt < p.top_k && p.top_k <= ge) kth = v;
+  }
+  kth = dh_warp_max(kth);
+  // ---- survivors: value >= k-th largest (ties kept) and id != <unk>
+  int ns = 0;
+  for (int c0 = 0; c0 < nc; c0 += 32) {
+    const int c = c0 + lane;
+    const bool keep = c < nc && vv[c] >= kth && ii[c] != p.unk;
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const int pos = ns + __popc(mask & ((1u << lane) - 1u));
+      if (pos < kWarpCap) { w.t_idx[pos] = ii[c]; w.t_val[pos] = vv[c]; }
+    }
+    ns += __popc(mask);
+  }
+  if (ns > kWarpCap) {
+    if (lane == 0) atomicOr(p.status, DH_STATUS_TOO_MANY_TIES);
+    ns = kWarpCap;
+  }
+  __syncwarp();
+  if (ns == 0) {   // whole row filtered: torch.multinomial raises (Q3)
+    if (lane == 0) atomicOr(p.status, DH_STATUS_EMPTY_ROW);
+    if (lane < p.B) { p.ind[(long long)r * p.B + lane] = 0; p.val[(long long)r * p.B + lane] = 0.f; }
+    return;
+  }
+  for (int c = lane; c < ns; c += 32) {          // sort by column (ids are distinct)
+    const int id = w.t_idx[c];
     int pos = 0;
-    for (int j = 0; j < nc; ++j) pos += tmp_idx[j] < id;
-    surv_idx[pos] = id;
-    surv_val[pos] = gv[c];
+    for (int j = 0; j < ns; ++j) pos += w.t_idx[j] < id;
+    w.a_idx[pos] = id;
+    w.a_val[pos] = w.t_val[c];
   }
-  __syncthreads();
-  select_tail<kCandThreads>(p, r, img, nc, surv_idx, surv_val, surv_score, scap);
+  __syncwarp();
+  // ---- softmax(l / T) over survivors (everything else has p == 0 exactly), noise, B rounds of arg-max
+  float m2 = -INFINITY;
+  for (int s = lane; s < ns; s += 32) m2 = fmaxf(m2, w.a_val[s] / p.T);
+  m2 = dh_warp_max(m2);
+  float sum = 0.f;
+  for (int s = lane; s < ns; s += 32) {
+    const float e = expf(w.a_val[s] / p.T - m2);
+    w.score[s] = e;
+    sum += e;
+  }
+  sum = dh_warp_sum(sum);
+  const unsigned long long seed = p.dyn ? (unsigned long long)p.dyn[0] : p.seed;
+  const long long image_base = p.dyn ? p.dyn[1] : p.image_base;
+  const unsigned long long rk = dh_noise_row_key(seed, (unsigned long long)(image_base + img), (unsigned long long)p.step,
+                                                 DH_CALL_TOKEN, (unsigned long long)(r % p.rpi));
+  for (int s = lane; s < ns; s += 32) {
+    float pr = w.score[s] / sum;
+    if (p.noise_mode == DH_NOISE_INJECTED) pr = pr / dh_exp_noise(rk, (unsigned long long)w.a_idx[s]);
+    w.score[s] = pr;
+  }
+  __syncwarp();
+  const int npick = ns < p.B ? ns : p.B;
+  for (int j = 0; j < npick; ++j) {
+    float best = -1.f; int bi = 0x7fffffff, bs = -1;
+    for (int s = lane; s < ns; s += 32) {
+      const float sc = w.score[s]; const int id = w.a_idx[s];
+      if (sc > best || (sc == best && sc >= 0.f && id < bi)) { best = sc; bi = id; bs = s; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; bs = os; }
+    }
+    if (lane == 0) {
+      w.pick_idx[j] = bi;
+      w.pick_logit[j] = w.a_val[bs];
+      w.score[bs] = -2.f;   // taken
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    // fewer survivors than B: multinomial continues with zero-probability ids; stable order = lowest ids
+    int next = 0;
+    for (int j = npick; j < p.B; ++j) {
+      for (;; ++next) {
+        bool used = false;
+        for (int q = 0; q < j; ++q) used |= (w.pick_idx[q] == next);
+        if (!used) break;
+      }
+      w.pick_idx[j] = next;
+      w.pick_logit[j] = -INFINITY;
+      ++next;
+    }
+    // score = log_softmax over the B picked (filtered, un-tempered) logits (Q4)
+    float m3 = -INFINITY;
+    for (int j = 0; j < p.B; ++j) m3 = fmaxf(m3, w.pick_logit[j]);
+    float se = 0.f;
+    for (int j = 0; j < p.B; ++j) se += expf(w.pick_logit[j] - m3);
+    const float lse = logf(se);
+    for (int j = 0; j < p.B; ++j) {
+      p.ind[(long long)r * p.B + j] = w.pick_idx[j];
+      p.val[(long long)r * p.B + j] = w.pick_logit[j] - m3 - lse;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ beam state
@@ -372,15 +505,15 @@ struct StepParams {
   float T; int noise_mode; unsigned long long seed; long long image_base; const long long* dyn;
 };
 
-__global__ void __launch_bounds__(32) beam_step_kernel(BeamState st, StepParams p) {
-  extern __shared__ int s_seq[];                 // [B, seq_ld]
+// One warp per image; s_seq is B * seq_ld ints of shared memory.
+__device__ void beam_step_body(const BeamState& st, const StepParams& p, int img, int* s_seq) {
   __shared__ float s_score[kMaxBeam * kMaxBeam];
   __shared__ float s_cval[kMaxBeam * kMaxBeam];
   __shared__ int s_ctok[kMaxBeam * kMaxBeam];
   __shared__ unsigned char s_cend[kMaxBeam * kMaxBeam], s_cpar[kMaxBeam * kMaxBeam];
   __shared__ int s_f[kMaxBeam];
   __shared__ int s_src[kMaxBeam][kMaxSlots];
-  const int img = blockIdx.x, lane = threadIdx.x, B = p.B;
+  const int lane = threadIdx.x & 31, B = p.B;
   if (st.done[img]) return;
   const long long base = (long long)img * B;
   // --- candidate layout (beam.py:83-102): ended row -> 1 copy, live row -> B copies
@@ -472,6 +605,37 @@ __global__ void __launch_bounds__(32) beam_step_kernel(BeamState st, StepParams 
   }
 }
 
+__global__ void __launch_bounds__(32) beam_step_kernel(BeamState st, StepParams p) {
+  extern __shared__ int dyn_smem[];                 // [B, seq_ld]
+  beam_step_body(st, p, blockIdx.x, dyn_smem);
+}
+
+// One CTA per image, one warp per logits row of the image: warp_select on every row's candidate list, then (do_beam)
+// warp 0 runs the beam step of the image on the picks -- selection and beam bookkeeping of one decode step in ONE launch.
+__global__ void __launch_bounds__(32 * kMaxBeam) select_beam_kernel(SelParams p, const int* __restrict__ cand_count,
+                                                                   const int* __restrict__ cand_idx,
+                                                                   const float* __restrict__ cand_val, int cap, int do_beam,
+                                                                   BeamState st, StepParams sp) {
+  extern __shared__ int dyn_smem[];
+  const int img = blockIdx.x, warp = threadIdx.x >> 5;
+  if (p.done && p.done[img]) return;
+  unsigned char* base = reinterpret_cast<unsigned char*>(dyn_smem) + (size_t)warp * kWarpSelBytes;
+  WarpSel w;
+  w.a_idx = reinterpret_cast<int*>(base);
+  w.a_val = reinterpret_cast<float*>(base + kWarpCap * 4);
+  w.t_idx = reinterpret_cast<int*>(base + 2 * kWarpCap * 4);
+  w.t_val = reinterpret_cast<float*>(base + 3 * kWarpCap * 4);
+  w.score = reinterpret_cast<float*>(base + 4 * kWarpCap * 4);
+  w.pick_idx = reinterpret_cast<int*>(base + 5 * kWarpCap * 4);
+  w.pick_logit = reinterpret_cast<float*>(base + 5 * kWarpCap * 4 + kMaxBeam * 4);
+  const int r = img * p.rpi + warp;
+  warp_select(p, r, img, cand_count[r], cand_idx + (long long)r * cap, cand_val + (long long)r * cap, cap, w);
+  if (!do_beam) return;
+  __syncthreads();                                   // the picks of all rows (global memory) are visible to warp 0
+  if (warp == 0)
+    beam_step_body(st, sp, img, reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(dyn_smem) + (size_t)p.rpi * kWarpSelBytes));
+}
+
 __global__ void __launch_bounds__(32) beam_final_kernel(BeamState st, int n_img, int B, float T, int noise_mode,
                                                         unsigned long long seed, long long image_base, int final_step,
                                                         int len_if_running, int pad, int max_len,
@@ -560,29 +724,8 @@ extern "C" int dh_vocab_threshold(const float* gmax, long long ld_gmax, int rows
                                   int* cand_count, cudaStream_t s) {
   DH_ARG(gmax && thresh && cand_count && rows >= 0 && n_groups > 0 && ld_gmax >= n_groups && top_k >= 1);
   if (rows == 0) return DH_OK;
-  vocab_threshold_kernel<<<rows, kThrThreads, 0, s>>>(gmax, ld_gmax, n_groups, top_k, thresh, cand_count);
-  DH_LAUNCH_OK();
-  return DH_OK;
-}
-
-extern "C" int dh_select_candidates(const int* cand_count, const int* cand_idx, const float* cand_val, int cand_cap, int rows,
-                                    int beam, int top_k, float temperature, int unk, int rows_per_image, int noise_mode,
-                                    unsigned long long seed, long long image_base, int step, const unsigned char* done,
-                                    int* ind, float* val, int* status, const long long* dyn, cudaStream_t s) {
-  DH_ARG(cand_count && cand_idx && cand_val && cand_cap > 0 && ind && val && status && rows >= 0);
-  DH_ARG(beam >= 1 && beam <= kMaxBeam && top_k >= 1 && beam <= top_k && temperature > 0.f);
-  DH_ARG(rows_per_image >= 1 && (noise_mode == DH_NOISE_DETERMINISTIC || noise_mode == DH_NOISE_INJECTED));
-  if (rows == 0) return DH_OK;
-  const int scap = cand_cap < kSurvCap ? cand_cap : kSurvCap;
-  size_t smem = (size_t)scap * 12;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DH_CUDA(cudaFuncSetAttribute(select_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSurvCap * 12));
-    attr_set = true;
-  }
-  SelParams p{nullptr, 0, rows, 0, beam, top_k, unk, rows_per_image, temperature, noise_mode, seed, image_base, step,
-              done, ind, val, status, dyn};
-  select_candidates_kernel<<<rows, kCandThreads, smem, s>>>(p, cand_count, cand_idx, cand_val, cand_cap);
+  vocab_threshold_kernel<<<dh_cdiv(rows, kThrWarps), kThrWarps * 32, 0, s>>>(gmax, ld_gmax, rows, n_groups, top_k, thresh,
+                                                                            cand_count);
   DH_LAUNCH_OK();
   return DH_OK;
 }
@@ -641,4 +784,50 @@ extern "C" int dh_token_logprob(const float* logits, long long ld, int rows, int
   token_logprob_kernel<<<rows, 256, 0, s>>>(logits, ld, V, targets, out);
   DH_LAUNCH_OK();
   return DH_OK;
+}
+
+static int launch_select_beam(const SelParams& p, const int* cand_count, const int* cand_idx, const float* cand_val, int cap,
+                              int n_img, int do_beam, const BeamState& st, const StepParams& sp, size_t seq_bytes,
+                              cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DH_CUDA(cudaFuncSetAttribute(select_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kMaxBeam * kWarpSelBytes + 40 * 1024));
+    attr_set = true;
+  }
+  const size_t smem = (size_t)p.rpi * kWarpSelBytes + (do_beam ? seq_bytes : 0);
+  select_beam_kernel<<<n_img, 32 * p.rpi, smem, s>>>(p, cand_count, cand_idx, cand_val, cap, do_beam, st, sp);
+  DH_LAUNCH_OK();
+  return DH_OK;
+}
+
+extern "C" int dh_select_candidates(const int* cand_count, const int* cand_idx, const float* cand_val, int cand_cap, int rows,
+                                    int beam, int top_k, float temperature, int unk, int rows_per_image, int noise_mode,
+                                    unsigned long long seed, long long image_base, int step, const unsigned char* done,
+                                    int* ind, float* val, int* status, const long long* dyn, cudaStream_t s) {
+  DH_ARG(cand_count && cand_idx && cand_val && cand_cap > 0 && ind && val && status && rows >= 0);
+  DH_ARG(beam >= 1 && beam <= kMaxBeam && top_k >= 1 && beam <= top_k && temperature > 0.f);
+  DH_ARG(rows_per_image >= 1 && rows_per_image <= kMaxBeam && rows % rows_per_image == 0);
+  DH_ARG(noise_mode == DH_NOISE_DETERMINISTIC || noise_mode == DH_NOISE_INJECTED);
+  if (rows == 0) return DH_OK;
+  SelParams p{nullptr, 0, rows, 0, beam, top_k, unk, rows_per_image, temperature, noise_mode, seed, image_base, step,
+              done, ind, val, status, dyn};
+  return launch_select_beam(p, cand_count, cand_idx, cand_val, cand_cap, rows / rows_per_image, 0, BeamState{}, StepParams{}, 0, s);
+}
+
+extern "C" int dh_select_beam_step(const int* cand_count, const int* cand_idx, const float* cand_val, int cand_cap,
+                                   const dh_beam_state* st, int* ind, float* val, int* status, int n_img, int beam, int top_k,
+                                   float temperature, int unk, int step, int max_len, int eos, int lstm_semantics,
+                                   int noise_mode, unsigned long long seed, long long image_base, const long long* dyn,
+                                   cudaStream_t s) {
+  DH_ARG(cand_count && cand_idx && cand_val && cand_cap > 0 && ind && val && status);
+  DH_ARG(check_state(st, n_img, beam) && top_k >= 1 && beam <= top_k && temperature > 0.f && step >= 1);
+  DH_ARG(st->seq_ld >= max_len && (size_t)beam * st->seq_ld * sizeof(int) <= 40 * 1024);
+  DH_ARG(noise_mode == DH_NOISE_DETERMINISTIC || noise_mode == DH_NOISE_INJECTED);
+  if (n_img == 0) return DH_OK;
+  SelParams p{nullptr, 0, n_img * beam, 0, beam, top_k, unk, beam, temperature, noise_mode, seed, image_base, step,
+              st->done, ind, val, status, dyn};
+  StepParams sp{ind, val, n_img, beam, step, max_len, eos, lstm_semantics, temperature, noise_mode, seed, image_base, dyn};
+  return launch_select_beam(p, cand_count, cand_idx, cand_val, cand_cap, n_img, 1, to_state(st), sp,
+                            (size_t)beam * st->seq_ld * sizeof(int), s);
 }

@@ -10,6 +10,15 @@ from ..runtime.encoder import EncoderRT, RESNET_BLOCKS
 from ._base import RTModule, prefixed
 
 
+def _stage(images, device):
+    """Device fp32 images; a pinned fp32 HOST batch is passed through as is: the encoder runtime streams it in
+    chunks so the host->device copy overlaps the trunk (an extension -- the reference takes device tensors only)."""
+    if images.device.type == 'cpu' and images.dtype == torch.float32 and images.is_contiguous() \
+            and images.is_pinned() and images.shape[0] > 64:
+        return images
+    return images.to(device, torch.float32).contiguous()
+
+
 class _Bottleneck(nn.Module):
     """Parameter container matching torchvision's Bottleneck attribute names (never executed by torch)."""
 
@@ -64,7 +73,7 @@ class ImageEncoder(RTModule):
 
     def forward(self, images):
         rt = self._rt()
-        start, sp = rt.forward(images.to(self._device(), torch.float32).contiguous())
+        start, sp = rt.forward(_stage(images, self._device()))
         if self.spatial_features:
             return start, sp.float().view(images.shape[0], 49, -1)
         return start
@@ -102,5 +111,5 @@ class ImageLabelEncoder(RTModule):
 
     def forward(self, images, labels):
         dev = self._device()
-        start, _ = self._rt().forward(images.to(dev, torch.float32).contiguous(), labels.to(dev))
+        start, _ = self._rt().forward(_stage(images, dev), labels.to(dev))
         return start

@@ -5,6 +5,8 @@ torchvision resnet.py:143-163,197-204,266-279.  Packing (one-time, torch ops on 
 into conv weights and a bias, OIHW -> [Cout][kh][kw][Cin] for NHWC implicit GEMM,
 BatchNorm1d folded into the global head, cast to the storage type of the precision mode.
 """
+import os
+
 import torch
 
 from . import ops
@@ -132,6 +134,28 @@ class EncoderRT:
             x = self._conv(f'b{i}c3', y2, blk['c3'], True, residual=idn)
         return x
 
+    def _host_chunks(self, images, chunk=int(os.environ.get('DH_H2D_CHUNK', '128'))):
+        """Pinned HOST images -> device chunks, copied on a side stream into two staging buffers so the H2D transfer
+        of chunk k+1 overlaps the trunk of chunk k (yields (first index, device chunk, event to record when consumed))."""
+        N = images.shape[0]
+        main = torch.cuda.current_stream()
+        if not hasattr(self, '_copy_stream'):
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._copied = [torch.cuda.Event(), torch.cuda.Event()]
+            self._consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        cs = self._copy_stream
+        bufs = [self._buf(f'h2d{b}', (chunk,) + tuple(images.shape[1:]), torch.float32) for b in range(2)]
+        cs.wait_stream(main)                           # earlier readers of the staging buffers are done
+        for k, i0 in enumerate(range(0, N, chunk)):
+            b, n = k & 1, min(chunk, N - i0)
+            with torch.cuda.stream(cs):
+                if k >= 2:
+                    cs.wait_event(self._consumed[b])
+                bufs[b][:n].copy_(images[i0:i0 + n], non_blocking=True)
+                self._copied[b].record(cs)
+            main.wait_event(self._copied[b])
+            yield i0, bufs[b][:n], self._consumed[b]
+
     # ---------------------------------------------------------------- heads
     def forward(self, images, labels=None):
         """-> (start_emb fp32 [N,E], spatial [N*49,E] storage dtype or None).  Processes `chunk` images at a time."""
@@ -139,21 +163,26 @@ class EncoderRT:
         E = self.E
         start = torch.empty(N, E, dtype=torch.float32, device=self.device)
         sp = torch.empty(N * 49, E, dtype=self.dtype, device=self.device) if self.spatial else None
-        for i0 in range(0, N, self.chunk):
-            img = images[i0:i0 + self.chunk]
+        pooled = self._buf('pooled', (N, 2048), torch.float32)
+        chunks = self._host_chunks(images) if not images.is_cuda else \
+            ((i0, images[i0:i0 + self.chunk], None) for i0 in range(0, N, self.chunk))
+        for i0, img, consumed in chunks:
             n = img.shape[0]
             with ops.PROFILE.range('encoder_trunk', 8.174e9 * n):
                 feat = self.trunk(img.contiguous())
+            if consumed is not None:
+                consumed.record()                      # the staging buffer may be overwritten by the next-but-one copy
             hw = feat.shape[1] * feat.shape[2]
-            pooled = self._buf('pooled', (n, 2048), torch.float32)
-            ops.avgpool(feat.view(n, hw, 2048), pooled)
-            if self.label_table is None:
-                ops.gemm(pooled, self.Wg, start[i0:i0 + n], bias=self.bg)
-            else:
-                cat = self._buf('cat', (n, 2 * E), torch.float32)
-                ops.gemm(pooled, self.Wg, cat[:, :E], bias=self.bg)
-                ops.embed_mean(self.label_table, labels[i0:i0 + n].contiguous(), cat[:, E:])
-                ops.gemm(cat, self.Wl, start[i0:i0 + n], bias=self.bl)
+            ops.avgpool(feat.view(n, hw, 2048), pooled[i0:i0 + n])
             if self.spatial:
                 ops.gemm(feat.view(n * hw, 2048), self.Wsp, sp[i0 * 49:(i0 + n) * 49], bias=self.bsp)
+        # global heads once for the whole batch (fp32 FFMA, 64x64 tiles)
+        with ops.PROFILE.range('encoder_heads'):
+            if self.label_table is None:
+                ops.gemm(pooled, self.Wg, start, bias=self.bg)
+            else:
+                cat = self._buf('cat', (N, 2 * E), torch.float32)
+                ops.gemm(pooled, self.Wg, cat[:, :E], bias=self.bg)
+                ops.embed_mean(self.label_table, labels.contiguous(), cat[:, E:])
+                ops.gemm(cat, self.Wl, start, bias=self.bl)
         return start, sp

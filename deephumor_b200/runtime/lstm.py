@@ -55,17 +55,22 @@ class LSTMDecoderRT:
             with ops.PROFILE.range('vocab_gemm', 2.0 * rows * self.V * H):
                 ops.gemm(ws['top'][:rows], self.Wc, ws['logits'][:rows, :self.V], bias=self.bc)
 
-    def _select(self, pl, rows, rpi, step, done, B, top_k, temperature, unk_index, noise_mode):
+    def _select(self, pl, rows, rpi, step, done, B, top_k, temperature, unk_index, noise_mode, beam_step=None):
         """classifier + BeamSearchHelper selection for `rows` rows (rnn_models.py:81,87-92,109-113): fused two-pass
         vocab projection (logits never stored) in tensor-core mode, materialised fp32 logits in check mode."""
         ws, beam = pl['ws'], pl['beam']
         if pl['vsel'] is not None:
             pl['vsel'].run(ws['top'][:rows], self.Wc, self.bc, B, temperature, unk_index, rpi, noise_mode, step, done,
-                           pl['ind'], pl['val'], beam.status, pl['dyn'])
+                           pl['ind'], pl['val'], beam.status, pl['dyn'],
+                           beam_step=None if beam_step is None else (beam,) + beam_step)
         else:
             with ops.PROFILE.range('select_beam'):
                 ops.select_tokens(ws['logits'][:rows, :self.V], self.V, B, top_k, temperature, unk_index, rpi, noise_mode,
                                   0, 0, step, done, pl['ind'], pl['val'], beam.status, pl['dyn'])
+                if beam_step is not None:
+                    max_len, eos_index, lstm_sem = beam_step
+                    beam.step(pl['ind'], pl['val'], step, max_len, eos_index, lstm_sem, temperature, noise_mode, 0, 0,
+                              pl['dyn'])
 
     def _recur(self, ws, rows, parent):
         """A[l][:, in:] <- hs[l][parent] for every layer (recurrent operand of the next step)."""
@@ -102,9 +107,8 @@ class LSTMDecoderRT:
             self._recur(ws, R, beam.parent_state)
             self._step(ws, R, cur, beam.parent_state, logits=not fused)
             cur = 1 - cur
-            self._select(pl, R, B, i, beam.done, B, top_k, temperature, unk_index, noise_mode)
-            with ops.PROFILE.range('select_beam'):
-                beam.step(ind, val, i, max_len, eos_index, True, temperature, noise_mode, 0, 0, dyn)
+            self._select(pl, R, B, i, beam.done, B, top_k, temperature, unk_index, noise_mode,
+                         beam_step=(max_len, eos_index, True))
         beam.final(temperature, noise_mode, 0, 0, max_len + 1, max(p0 + 1, max_len), pad_index, max_len, pl['ids'],
                    pl['lens'], dyn)
 

@@ -243,7 +243,9 @@ class VocabSelect:
         return A.dtype in (torch.bfloat16, torch.float16) and top_k <= (V + 31) // 32
 
     def run(self, A, W, bias, beam, temperature, unk, rows_per_image, noise_mode, step, done, ind, val, status, dyn,
-            seed=0, image_base=0):
+            seed=0, image_base=0, beam_step=None):
+        """beam_step = (Beam, max_len, eos, lstm_semantics): also run that image's beam step in the same launch."""
+        import ctypes
         rows, K = A.shape
         assert rows <= self.rows and W.shape == (self.V, K) and W.dtype == A.dtype
         args = (ptr(A), _rows(A), ptr(W), _rows(W), code(A), ptr(bias), rows, self.V, K)
@@ -254,9 +256,17 @@ class VocabSelect:
             LIB.call('dh_vocab_candidates', *args, ptr(self.thresh), ptr(self.count), ptr(self.idx), ptr(self.val),
                      self.cap, stream())
         with PROFILE.range('select_beam'):
-            LIB.call('dh_select_candidates', ptr(self.count), ptr(self.idx), ptr(self.val), self.cap, rows, beam,
-                     self.top_k, float(temperature), unk, rows_per_image, noise_mode, seed, image_base, step, ptr(done), ptr(ind),
-                     ptr(val), ptr(status), ptr(dyn), stream())
+            if beam_step is None:
+                LIB.call('dh_select_candidates', ptr(self.count), ptr(self.idx), ptr(self.val), self.cap, rows, beam,
+                         self.top_k, float(temperature), unk, rows_per_image, noise_mode, seed, image_base, step,
+                         ptr(done), ptr(ind), ptr(val), ptr(status), ptr(dyn), stream())
+            else:
+                bm, max_len, eos, lstm_sem = beam_step
+                assert rows == bm.n_img * bm.beam and rows_per_image == bm.beam == beam
+                LIB.call('dh_select_beam_step', ptr(self.count), ptr(self.idx), ptr(self.val), self.cap,
+                         ctypes.byref(bm.c), ptr(ind), ptr(val), ptr(status), bm.n_img, beam, self.top_k,
+                         float(temperature), unk, step, max_len, eos, int(lstm_sem), noise_mode, seed, image_base,
+                         ptr(dyn), stream())
 
 
 class Beam:

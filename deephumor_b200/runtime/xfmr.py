@@ -78,18 +78,20 @@ class XfmrDecoderRT:
 
         vsel = pl['vsel']
 
-        def select(rows, rpi, step_i, done):
+        def select(rows, rpi, step_i, done, beam_step=False):
             """classifier + BeamSearchHelper selection (transformers.py:488/736 -> beam.py:32-53): fused two-pass vocab
             projection in tensor-core mode (logits never stored), materialised fp32 logits in check mode."""
             if vsel is not None:
                 vsel.run(x[:rows], self.Wc, self.bc, B, temperature, unk_index, rpi, noise_mode, step_i, done, ind, val,
-                         beam.status, dyn)
+                         beam.status, dyn, beam_step=(beam, max_len, eos_index, False) if beam_step else None)
             else:
                 with ops.PROFILE.range('vocab_gemm', 2.0 * rows * self.V * D):
                     ops.gemm(x[:rows], self.Wc, logits[:rows, :self.V], bias=self.bc)
                 with ops.PROFILE.range('select_beam'):
                     ops.select_tokens(logits[:rows, :self.V], self.V, B, top_k, temperature, unk_index, rpi, noise_mode,
                                       0, 0, step_i, done, ind, val, beam.status, dyn)
+                    if beam_step:
+                        beam.step(ind, val, step_i, max_len, eos_index, False, temperature, noise_mode, 0, 0, dyn)
 
         def step(rows, rpi, pos, tokens, seq, src):
             """One new position `pos` for `rows` rows (rpi rows per image)."""
@@ -121,9 +123,7 @@ class XfmrDecoderRT:
         # ---- beam phase: i = p0+1 .. max_len inclusive (Q10); fixed trip count, frozen-at-break on the device
         for i in range(p0 + 1, max_len + 1):
             step(R, B, i, beam.last_tok, beam.seq, beam.src)
-            select(R, B, i, beam.done)
-            with ops.PROFILE.range('select_beam'):
-                beam.step(ind, val, i, max_len, eos_index, False, temperature, noise_mode, 0, 0, dyn)
+            select(R, B, i, beam.done, beam_step=True)
         beam.final(temperature, noise_mode, 0, 0, max_len + 1, max_len, self.pad, max_len, pl['ids'], pl['lens'], dyn)
 
     def generate(self, start_emb, spatial, caption, max_len, temperature, beam_size, top_k, eos_index, unk_index,

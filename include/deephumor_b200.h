@@ -24,7 +24,7 @@ extern "C" {
 typedef struct CUstream_st* cudaStream_t;
 #endif
 
-#define DH_VERSION 105
+#define DH_VERSION 106
 
 #define DH_OK 0
 #define DH_ERR_ARG (-1)
@@ -170,6 +170,12 @@ int dh_select_candidates(const int* cand_count, const int* cand_idx, const float
                          int beam, int top_k, float temperature, int unk, int rows_per_image, int noise_mode,
                          unsigned long long seed, long long image_base, int step, const unsigned char* done, int* ind,
                          float* val, int* status, const long long* dyn, cudaStream_t stream);
+/* dh_select_candidates for the beam rows of every image followed by dh_beam_step of that image, in one launch
+ * (one CTA per image, one warp per row).  ind / val [n_img*beam, beam] receive the picks as in dh_select_tokens. */
+int dh_select_beam_step(const int* cand_count, const int* cand_idx, const float* cand_val, int cand_cap,
+                        const dh_beam_state* st, int* ind, float* val, int* status, int n_img, int beam, int top_k,
+                        float temperature, int unk, int step, int max_len, int eos, int lstm_semantics, int noise_mode,
+                        unsigned long long seed, long long image_base, const long long* dyn, cudaStream_t stream);
 int dh_beam_init(const dh_beam_state* st, const int* ind0, const float* val0, const int* prefix, long long prefix_ld,
                  int prefix_rows, int prefix_len, int n_img, int beam, int eos, int lstm_semantics, cudaStream_t stream);
 int dh_beam_step(const dh_beam_state* st, const int* new_ind, const float* new_val, int n_img, int beam, int step,

@@ -108,3 +108,65 @@ def test_bf16_mode_within_tolerance(kind, tag):
         # first generated token: the deterministic arg-max of the first logits row, robust unless near-tied
         agree = sum(int(ids[n, 0]) == int(g['ids'][n, 0]) for n in range(ids.shape[0]))
         assert agree >= ids.shape[0] - 1 - ids.shape[0] // 4
+
+
+@pytest.mark.parametrize('kind', H.KINDS)
+def test_fused_vocab_path_generates_the_same_tokens_as_materialised_logits(kind):
+    """Tensor-core mode: the two-pass vocab projection + warp-level select/beam-step launch must pick the same
+    tokens as the materialised-logits path (same tcgen05 product, dh_select_tokens + dh_beam_step)."""
+    from deephumor_b200.runtime import ops
+    fx = H.load_fixture('canon', kind)
+    m, sd, imgs, labs, caps, lens = build(fx, 'bf16')
+    outs = []
+    for g in (fx['gen'][0], fx['gen'][-1]):
+        kw = dict(max_len=fx['max_len'], temperature=g['temperature'], beam_size=g['beam_size'], top_k=g['top_k'],
+                  noise=g['mode'], seed=g['noise_seed'])
+        res = []
+        for fused in (True, False):
+            ops.FUSED_VOCAB = fused
+            m.invalidate()
+            try:
+                with torch.no_grad():
+                    a = (imgs.cuda(), labs.cuda()) if kind == 'lstm_labels' else (imgs.cuda(),)
+                    res.append(m.generate(*a, **kw))
+            finally:
+                ops.FUSED_VOCAB = True
+        (i0, l0), (i1, l1) = res
+        same = [bool((i0[n] == i1[n]).all()) and int(l0[n]) == int(l1[n]) for n in range(i0.shape[0])]
+        assert sum(same) >= len(same) - 1, f'{kind} {g["mode"]}: fused vs materialised differ on {same}'
+
+
+@pytest.mark.parametrize('kind,n_img,beam', [('lstm_labels', 512, 5), ('xfmr', 256, 5), ('xfmr_base', 256, 1)])
+def test_full_size_generation_is_shard_invariant(kind, n_img, beam):
+    """BASELINE-size property (configs[1]: 512 images, beam 5, top-k 50, 32 tokens, V = 36 541, tensor-core mode):
+    generating the batch in one call equals generating two shards with image_base offsets, bit for bit -- the
+    per-image results depend on the GLOBAL image index only (world-size independence); every image
+    has a well-formed caption (ids in range, pad after the recorded length)."""
+    from deephumor_b200.runtime import ops
+    from deephumor_b200.utils import synth, synth_weights
+    V = 36541
+    hp = synth_weights.default_hp(kind, V)
+    sd = synth_weights.make_state_dict(kind, hp, seed=0)
+    m = CLS[kind](**hp)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval().set_precision('bf16')
+    images = torch.empty(n_img, 3, 224, 224, device=DEV)
+    ops.synth_images(images, 0, 1000)
+    labs = synth.labels(0, 1000, n_img, V).cuda() if kind == 'lstm_labels' else None
+    kw = dict(max_len=32, temperature=1.0, beam_size=beam, top_k=50, noise='injected', seed=99)
+
+    def gen(lo, hi):
+        a = (images[lo:hi],) + ((labs[lo:hi],) if labs is not None else ())
+        with torch.no_grad():
+            return m.generate(*a, image_base=1000 + lo, **kw)
+
+    ids, lens = gen(0, n_img)
+    h = n_img // 2 + 3
+    ids_a, lens_a = gen(0, h)
+    ids_b, lens_b = gen(h, n_img)
+    assert torch.equal(ids, torch.cat([ids_a, ids_b])) and torch.equal(lens, torch.cat([lens_a, lens_b]))
+    assert ids.shape == (n_img, 32) and int(ids.min()) >= 0 and int(ids.max()) < V
+    assert int(lens.min()) >= 1 and int(lens.max()) <= 32
+    pos = torch.arange(32, device=DEV).unsqueeze(0)
+    assert bool((ids[pos.expand_as(ids) >= lens.unsqueeze(1)] == 0).all())
+    assert len({tuple(r.tolist()) for r in ids.cpu()}) > n_img // 2      # captions depend on the image
