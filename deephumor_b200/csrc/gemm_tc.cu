@@ -45,6 +45,9 @@ struct TcParams {
   float* gmax; long long ld_gmax;         // [M, ld_gmax] group maxima (mode 1)
   const float* thresh;                    // [M] lower bound of the row's top_k-th largest logit (mode 2)
   int* cand_count; int* cand_idx; float* cand_val; int cand_cap;   // [M], [M, cap], [M, cap]
+  // LSTM cell epilogue (epi_mode 3, dh_lstm_layer_tc): the N axis is packed per 64 hidden units as [i | f | g | o]
+  const float* c_prev; const int* parent; float* c_out;            // [*, H] fp32, parent[M] (nullable), [M, H] fp32
+  void* h0; long long ldh0; void* h1; long long ldh1; int H;       // bf16 h to up to two destinations
 };
 
 // ------------------------------------------------------------------------------------------- PTX wrappers
@@ -125,6 +128,22 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile (rows of 64 bf16 = 128 B, 8-row atoms of 1024 B):
 // start address >> 4 | SBO = 1024 B (bits 32..45) | descriptor version 1 (bits 46..47) | SWIZZLE_128B (bits 61..63).
@@ -267,7 +286,91 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp >= 4) {
     // ======================================================================= epilogue
     const int ew = warp - 4;                      // == warp % 4: TMEM lane quadrant this warp may read
-    if (p.epi_mode) {
+    if (p.epi_mode == 3) {
+      // ---- LSTM cell epilogue (BN == 256): a tile holds the i, f, g, o pre-activations of 64 hidden units for 128 rows;
+      // each thread owns one row: c = sig(f) c_prev[parent] + sig(i) tanh(g), h = sig(o) tanh(c) (nn.LSTM gate order).
+      if (BN == 256) {
+        const int row_l = ew * 32 + lane;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+          const int m0 = (tile / p.n_blocks) * BM, n0 = (tile % p.n_blocks) * BN;
+          const int as = it & 1;
+          mbar_wait(tfull_bar(as), (it >> 1) & 1, p.error, 4);
+          tc_fence_after();
+          const uint32_t tmem_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int i = row_l; i < BN; i += 128) bias_s[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const long long row = (long long)m0 + row_l;
+          const bool row_ok = row < p.M;
+          const int unit0 = (n0 >> 8) * 64;
+          const long long prow = row_ok ? (p.parent ? (long long)__ldg(p.parent + row) : row) : 0;
+          const float* cp = p.c_prev ? p.c_prev + prow * p.H + unit0 : nullptr;
+#pragma unroll 1
+          for (int u0 = 0; u0 < 64; u0 += 16) {
+            uint32_t vi[16], vf[16], vg[16], vo[16];
+            tc_ld16(tmem_row + (uint32_t)u0, vi);
+            tc_ld16(tmem_row + (uint32_t)(64 + u0), vf);
+            tc_ld16(tmem_row + (uint32_t)(128 + u0), vg);
+            tc_ld16(tmem_row + (uint32_t)(192 + u0), vo);
+            float cprev[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) cprev[j] = 0.f;
+            if (row_ok && cp) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const float4 c4 = __ldg(reinterpret_cast<const float4*>(cp + u0) + g);
+                cprev[4 * g] = c4.x; cprev[4 * g + 1] = c4.y; cprev[4 * g + 2] = c4.z; cprev[4 * g + 3] = c4.w;
+              }
+            }
+            tc_wait_ld();
+            float c2[16];
+            uint32_t hw[8];
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              float h2[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const float gi = __uint_as_float(vi[j + e]) + bias_s[u0 + j + e];
+                const float gf = __uint_as_float(vf[j + e]) + bias_s[64 + u0 + j + e];
+                const float gg = __uint_as_float(vg[j + e]) + bias_s[128 + u0 + j + e];
+                const float go = __uint_as_float(vo[j + e]) + bias_s[192 + u0 + j + e];
+                // MUFU.TANH (rel. error 2^-11, far inside the bf16 rounding of h): sigmoid(x) = 0.5 + 0.5 tanh(x / 2)
+                const float si = fmaf(0.5f, tanh_fast(0.5f * gi), 0.5f), sf = fmaf(0.5f, tanh_fast(0.5f * gf), 0.5f);
+                const float so = fmaf(0.5f, tanh_fast(0.5f * go), 0.5f);
+                c2[j + e] = fmaf(sf, cprev[j + e], si * tanh_fast(gg));
+                h2[e] = so * tanh_fast(c2[j + e]);
+              }
+              if (p.out_dtype == DH_BF16) {
+                __nv_bfloat162 t = __floats2bfloat162_rn(h2[0], h2[1]);
+                hw[j >> 1] = *reinterpret_cast<uint32_t*>(&t);
+              } else {
+                __half2 t = __floats2half2_rn(h2[0], h2[1]);
+                hw[j >> 1] = *reinterpret_cast<uint32_t*>(&t);
+              }
+            }
+            if (row_ok) {
+              float4* co = reinterpret_cast<float4*>(p.c_out + row * p.H + unit0 + u0);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) co[g] = make_float4(c2[4 * g], c2[4 * g + 1], c2[4 * g + 2], c2[4 * g + 3]);
+              if (p.h0) {
+                uint4* d = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.h0) + row * p.ldh0 + unit0 + u0);
+                d[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                d[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+              }
+              if (p.h1) {
+                uint4* d = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.h1) + row * p.ldh1 + unit0 + u0);
+                d[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                d[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(as));
+        }
+      }
+    } else if (p.epi_mode) {
       // ---- selection epilogues: every thread owns one accumulator row; nothing of the [M,N] product is stored.
       const int row_l = ew * 32 + lane;
       int it = 0;
@@ -696,6 +799,36 @@ static int vocab_pass(int mode, const void* A, long long lda, const void* W, lon
   rc = make_map_2d(&ma, A, M, K, lda, BM, ab_dtype);
   if (rc) return rc;
   return dispatch(ma, W, ldw, p, N <= 64 ? 64 : N <= 128 ? 128 : 256, stream);
+}
+
+// One nn.LSTM layer step on tensor cores with the cell update in the epilogue (rnn_models.py:80,108): gates = A [x | h]
+// times the gate-packed [W_ih | W_hh] (rows ordered per 64 hidden units as i, f, g, o; bias = b_ih + b_hh packed alike).
+extern "C" int dh_lstm_layer_tc(const void* A, long long lda, const void* Wp, long long ldw, int ab_dtype, const float* bias_p,
+                                const float* c_prev, const int* parent, float* c_out, void* h_out0, long long ldh0,
+                                void* h_out1, long long ldh1, int rows, int H, int K, cudaStream_t stream) {
+  DH_ARG(A && Wp && c_out && rows >= 0 && H > 0 && H % 64 == 0 && K > 0);
+  DH_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0);
+  DH_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)Wp % 16) == 0 && ((uintptr_t)c_out % 16) == 0);
+  DH_ARG(!c_prev || ((uintptr_t)c_prev % 16) == 0);
+  DH_ARG(!h_out0 || (((uintptr_t)h_out0 % 16) == 0 && ldh0 % 8 == 0));
+  DH_ARG(!h_out1 || (((uintptr_t)h_out1 % 16) == 0 && ldh1 % 8 == 0));
+  DH_ARG(ab_dtype == DH_BF16 || ab_dtype == DH_F16);
+  if (rows == 0) return DH_OK;
+  int rc = tc_init();
+  if (rc) return rc;
+  TcParams p{};
+  p.M = rows; p.N = 4 * H; p.K = K;
+  p.k_chunks = dh_cdiv(K, BK);
+  p.ab_dtype = ab_dtype;
+  p.out_dtype = ab_dtype;
+  p.bias = bias_p;
+  p.epi_mode = 3;
+  p.c_prev = c_prev; p.parent = parent; p.c_out = c_out;
+  p.h0 = h_out0; p.ldh0 = ldh0; p.h1 = h_out1; p.ldh1 = ldh1; p.H = H;
+  CUtensorMap ma;
+  rc = make_map_2d(&ma, A, rows, K, lda, BM, ab_dtype);
+  if (rc) return rc;
+  return dispatch(ma, Wp, ldw, p, 256, stream);
 }
 
 extern "C" int dh_vocab_groupmax(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias,

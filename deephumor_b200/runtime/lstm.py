@@ -27,6 +27,11 @@ class LSTMDecoderRT:
                                 torch.float32))
             self.L += 1
         self.H = self.Wcat[0].shape[0] // 4
+        # tensor-core mode: gate-packed copies for the fused cell epilogue (csrc/gemm_tc.cu, epi_mode 3)
+        self.fused_cell = ops.FUSED_LSTM and dtype != torch.float32 and self.H % 64 == 0
+        if self.fused_cell:
+            self.Wpk = [ops.pack_lstm_gates(w, self.H) for w in self.Wcat]
+            self.bpk = [ops.pack_lstm_gates(b, self.H) for b in self.bias]
         self.Wc, self.bc = to(sd[prefix + '.classifier.weight']), to(sd[prefix + '.classifier.bias'], torch.float32)
         self.ldv = (self.V + 3) // 4 * 4
         self._plans = {}
@@ -47,10 +52,14 @@ class LSTMDecoderRT:
         L, H = self.L, self.H
         for l in range(L):
             A = ws['A'][l][:rows]
-            gates = ws['gates'][:rows]
-            ops.gemm(A, self.Wcat[l], gates, bias=self.bias[l])
             nxt = ws['A'][l + 1][:rows, :H] if l + 1 < L else ws['top'][:rows]
-            ops.lstm_cell(gates, ws['c'][cur][l], parent, ws['c'][1 - cur][l][:rows], nxt, ws['hs'][l][:rows])
+            if self.fused_cell:
+                ops.lstm_layer_tc(A, self.Wpk[l], self.bpk[l], ws['c'][cur][l], parent, ws['c'][1 - cur][l][:rows], nxt,
+                                  ws['hs'][l][:rows])
+            else:
+                gates = ws['gates'][:rows]
+                ops.gemm(A, self.Wcat[l], gates, bias=self.bias[l])
+                ops.lstm_cell(gates, ws['c'][cur][l], parent, ws['c'][1 - cur][l][:rows], nxt, ws['hs'][l][:rows])
         if logits:
             with ops.PROFILE.range('vocab_gemm', 2.0 * rows * self.V * H):
                 ops.gemm(ws['top'][:rows], self.Wc, ws['logits'][:rows, :self.V], bias=self.bc)

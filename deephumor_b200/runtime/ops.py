@@ -55,6 +55,7 @@ class _Profile:
 PROFILE = _Profile()
 USE_GRAPHS = os.environ.get('DH_NO_GRAPH', '') == ''   # capture decode loops into CUDA graphs
 FUSED_STEM = os.environ.get('DH_NO_FUSED_STEM', '') == ''     # conv1 + ReLU + maxpool in one tcgen05 kernel
+FUSED_LSTM = os.environ.get('DH_NO_FUSED_LSTM', '') == ''     # LSTM cell update in the gate GEMM's epilogue
 FUSED_VOCAB = os.environ.get('DH_NO_FUSED_VOCAB', '') == ''   # two-pass vocab projection, logits never stored
 
 
@@ -180,6 +181,24 @@ def lstm_cell(gates, c_prev, parent, c_out, h_out0, h_out1):
     LIB.call('dh_lstm_cell', ptr(gates), _rows(gates), ptr(c_prev), ptr(parent), ptr(c_out),
              ptr(h_out0), 0 if h_out0 is None else _rows(h_out0), ptr(h_out1), 0 if h_out1 is None else _rows(h_out1),
              rows, H, code(h), stream())
+
+
+def lstm_layer_tc(A, Wp, bias_p, c_prev, parent, c_out, h_out0, h_out1):
+    """One LSTM layer step: gate contraction on tcgen05 with the cell update in the epilogue (Wp / bias_p gate-packed
+    per 64 hidden units, see pack_lstm_gates)."""
+    rows, K = A.shape
+    H = Wp.shape[0] // 4
+    assert Wp.shape[1] == K and Wp.dtype == A.dtype and c_out.is_contiguous() and (c_prev is None or c_prev.is_contiguous())
+    assert all(h is None or h.dtype == A.dtype for h in (h_out0, h_out1))
+    LIB.call('dh_lstm_layer_tc', ptr(A), _rows(A), ptr(Wp), _rows(Wp), code(A), ptr(bias_p), ptr(c_prev), ptr(parent),
+             ptr(c_out), ptr(h_out0), 0 if h_out0 is None else _rows(h_out0), ptr(h_out1),
+             0 if h_out1 is None else _rows(h_out1), rows, H, K, stream())
+
+
+def pack_lstm_gates(t, H):
+    """[4H, ...] in nn.LSTM gate order (i, f, g, o) -> rows grouped per 64 hidden units as [i | f | g | o] blocks."""
+    rest = t.shape[1:]
+    return t.view(4, H // 64, 64, *rest).transpose(0, 1).reshape(4 * H, *rest).contiguous()
 
 
 def add_layernorm(x, y, gamma, beta, out):

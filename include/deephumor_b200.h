@@ -24,7 +24,7 @@ extern "C" {
 typedef struct CUstream_st* cudaStream_t;
 #endif
 
-#define DH_VERSION 106
+#define DH_VERSION 107
 
 #define DH_OK 0
 #define DH_ERR_ARG (-1)
@@ -111,6 +111,14 @@ int dh_gather_rows(const void* src, long long lds, long long n_src_rows, const i
  * which folds the beam reorder of rnn_models.py:135-137 into the load. */
 int dh_lstm_cell(const float* gates, long long ldg, const float* c_prev, const int* parent, float* c_out, void* h_out0,
                  long long ldh0, void* h_out1, long long ldh1, int rows, int H, int dtype, cudaStream_t stream);
+/* Tensor-core nn.LSTM layer step with the cell update fused into the contraction's epilogue (rnn_models.py:80,108):
+ * gates = A[rows,K] Wp[4H,K]^T + bias_p with A = [x | h_prev], Wp = [W_ih | W_hh] whose rows are re-ordered per 64
+ * hidden units as (i, f, g, o) blocks (bias_p = b_ih + b_hh likewise); c_prev is read through parent[] (nullable:
+ * identity; c_prev nullable: zeros), c_out fp32 [rows,H], h (ab_dtype) goes to up to two row-major destinations.
+ * The gate pre-activations never reach HBM.  H % 64 == 0. */
+int dh_lstm_layer_tc(const void* A, long long lda, const void* Wp, long long ldw, int ab_dtype, const float* bias_p,
+                     const float* c_prev, const int* parent, float* c_out, void* h_out0, long long ldh0, void* h_out1,
+                     long long ldh1, int rows, int H, int K, cudaStream_t stream);
 /* out = LayerNorm(x + y), eps 1e-5 (transformers.py:360,368,375,627,634). y may be null. */
 int dh_add_layernorm(const void* x, long long ldx, const void* y, long long ldy, const float* gamma, const float* beta,
                      void* out, long long ldo, int rows, int D, int dtype, cudaStream_t stream);

@@ -167,3 +167,34 @@ def test_fused_stem_pool(dt, n):
     got = out[sel].float()
     assert H.rel_err(got, ref) < (4e-3 if dt == torch.bfloat16 else 5e-4)
     assert float((got - ref).abs().max()) < (0.05 if dt == torch.bfloat16 else 0.01)
+
+
+@pytest.mark.parametrize('rows,H_,in_,use_parent', [(2560, 512, 512, True), (37, 64, 32, False), (300, 128, 256, True)])
+def test_lstm_layer_fused_cell_epilogue(rows, H_, in_, use_parent):
+    """Gate contraction with the cell update in the tcgen05 epilogue (MUFU.TANH activations, rel. error 2^-11) against
+    dh_gemm_tc + dh_lstm_cell (precise expf / tanhf) and nn.LSTMCell on the same bf16-rounded operands: c within 1e-3,
+    h within the bf16 rounding of the output."""
+    g = torch.Generator().manual_seed(rows)
+    K_ = in_ + H_
+    A = (torch.randn(rows, K_, generator=g) * 0.5).to(torch.bfloat16).to(DEV)
+    W = (torch.randn(4 * H_, K_, generator=g) * 0.1).to(torch.bfloat16).to(DEV)
+    b = torch.randn(4 * H_, generator=g).to(DEV)
+    c_prev = torch.randn(rows, H_, generator=g).to(DEV)
+    parent = torch.randint(0, rows, (rows,), generator=g).to(torch.int32).to(DEV) if use_parent else None
+    gates = torch.empty(rows, 4 * H_, device=DEV)
+    ops.gemm(A, W, gates, bias=b)
+    c0, h0a, h0b = torch.empty(rows, H_, device=DEV), torch.empty(rows, H_ + 8, dtype=torch.bfloat16, device=DEV), \
+        torch.empty(rows, H_, dtype=torch.bfloat16, device=DEV)
+    ops.lstm_cell(gates, c_prev, parent, c0, h0a[:, :H_], h0b)
+    c1, h1a, h1b = torch.empty_like(c0), torch.empty_like(h0a), torch.empty_like(h0b)
+    ops.lstm_layer_tc(A, ops.pack_lstm_gates(W, H_), ops.pack_lstm_gates(b, H_), c_prev, parent, c1, h1a[:, :H_], h1b)
+    torch.cuda.synchronize()
+    assert torch.equal(h1a[:, :H_], h1b)
+    assert H.rel_err(c1, c0) < 1e-3 and H.rel_err(h1b.float(), h0b.float()) < 4e-3
+    cell = torch.nn.LSTMCell(in_, H_).double()
+    with torch.no_grad():
+        cell.weight_ih.copy_(W[:, :in_].double().cpu()); cell.weight_hh.copy_(W[:, in_:].double().cpu())
+        cell.bias_ih.copy_(b.double().cpu()); cell.bias_hh.zero_()
+        cp = c_prev.cpu().double() if parent is None else c_prev.cpu().double()[parent.cpu().long()]
+        hr, cr = cell(A[:, :in_].double().cpu(), (A[:, in_:].double().cpu(), cp))
+    assert H.rel_err(c1, cr) < 1e-3 and H.rel_err(h1b.float(), hr) < 5e-3
