@@ -108,6 +108,38 @@ __global__ void embed_mean_kernel(const T* __restrict__ table, long long ldt, co
   }
 }
 
+// ------------------------------------------------------------------ LSTM step operands in one launch
+// Per row r: A[0][r, 0:E] = table[tok[r]] (next input embedding) and, for every layer l, A[l][r, in_l : in_l + H] =
+// hs[l][parent[r]] (recurrent h through the beam parent; rnn_models.py:107,135-137).  16-byte copies, 2-byte elements.
+constexpr int kMaxLstmLayers = 8;
+struct LstmPrepParams {
+  const uint16_t* table; long long ldt; const int* tok; int E; long long n_tok_rows;
+  const int* parent; int H, L, rows;
+  const uint16_t* hs[kMaxLstmLayers];       // [*, H] contiguous
+  uint16_t* A[kMaxLstmLayers]; long long lda[kMaxLstmLayers]; int in_off[kMaxLstmLayers];
+};
+__global__ void lstm_prepare_kernel(LstmPrepParams p) {
+  const int ce = p.E / 8, ch = p.H / 8;
+  const int per_row = ce + p.L * ch;
+  const long long total = (long long)p.rows * per_row;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / per_row);
+    int c = (int)(i - (long long)r * per_row);
+    if (c < ce) {
+      const long long t = p.tok[r];
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (t >= 0 && t < p.n_tok_rows) v = *reinterpret_cast<const uint4*>(p.table + t * p.ldt + c * 8);
+      *reinterpret_cast<uint4*>(p.A[0] + (long long)r * p.lda[0] + c * 8) = v;
+    } else {
+      c -= ce;
+      const int l = c / ch, cc = c - l * ch;
+      const long long pr = p.parent ? p.parent[r] : r;
+      *reinterpret_cast<uint4*>(p.A[l] + (long long)r * p.lda[l] + p.in_off[l] + cc * 8) =
+          *reinterpret_cast<const uint4*>(p.hs[l] + pr * p.H + cc * 8);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ LSTM cell (gate order i,f,g,o)
 // gates [R,4H] fp32 (bias already added); c_prev rows gathered through parent[] (beam reorder folded into
 // the read); h goes to up to two destinations (next layer's input slot and the
@@ -315,6 +347,25 @@ extern "C" int dh_cast(const void* src, void* dst, long long n, int src_dtype, i
     cast_kernel<float, float><<<g, kThreads, 0, s>>>((const float*)src, (float*)dst, n);
   else
     return dh_fail(DH_ERR_ARG, "dtype", __FILE__, __LINE__);
+  DH_LAUNCH_OK();
+  return DH_OK;
+}
+
+extern "C" int dh_lstm_prepare(const void* table, long long ldt, long long n_tok_rows, const int* tok, int E, const int* parent,
+                               const void* const* hs, void* const* A, const long long* lda, const int* in_off, int L, int H,
+                               int rows, cudaStream_t s) {
+  DH_ARG(table && tok && hs && A && lda && in_off && L >= 1 && L <= kMaxLstmLayers && rows >= 0);
+  DH_ARG(E % 8 == 0 && H % 8 == 0 && ldt % 8 == 0);
+  if (rows == 0) return DH_OK;
+  LstmPrepParams p{};
+  p.table = (const uint16_t*)table; p.ldt = ldt; p.tok = tok; p.E = E; p.n_tok_rows = n_tok_rows;
+  p.parent = parent; p.H = H; p.L = L; p.rows = rows;
+  for (int l = 0; l < L; ++l) {
+    DH_ARG(hs[l] && A[l] && lda[l] % 8 == 0 && in_off[l] % 8 == 0);
+    p.hs[l] = (const uint16_t*)hs[l]; p.A[l] = (uint16_t*)A[l]; p.lda[l] = lda[l]; p.in_off[l] = in_off[l];
+  }
+  const long long total = (long long)rows * (E / 8 + L * (H / 8));
+  lstm_prepare_kernel<<<grid_for(total), kThreads, 0, s>>>(p);
   DH_LAUNCH_OK();
   return DH_OK;
 }

@@ -23,7 +23,7 @@
 namespace {
 
 constexpr int BM = 128, BK = 64;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;            // warps 0-2 producer / MMA / TMEM, 4-7 epilogue, 8-11 second epilogue group
 constexpr int kStageLd = 36;             // floats per staged row (32 + 4: conflict-free for 16 B accesses)
 constexpr int kSmemBudget = 196608;      // bytes of A/B ring
 
@@ -201,7 +201,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);
+      mbar_init(tempty_bar(s), p.epi_mode ? 8 : 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 2) {
@@ -285,7 +285,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ======================================================================= epilogue
-    const int ew = warp - 4;                      // == warp % 4: TMEM lane quadrant this warp may read
+    const int ew = warp & 3;                      // TMEM lane quadrant this warp may read
+    const int eh = (warp - 4) >> 2;               // 0: warps 4-7, 1: warps 8-11 (other column half; fused epilogues only)
+    const int etid = (warp - 4) * 32 + lane;      // 0..255 over both epilogue groups
     if (p.epi_mode == 3) {
       // ---- LSTM cell epilogue (BN == 256): a tile holds the i, f, g, o pre-activations of 64 hidden units for 128 rows;
       // each thread owns one row: c = sig(f) c_prev[parent] + sig(i) tanh(g), h = sig(o) tanh(c) (nn.LSTM gate order).
@@ -298,16 +300,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(tfull_bar(as), (it >> 1) & 1, p.error, 4);
           tc_fence_after();
           const uint32_t tmem_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          for (int i = row_l; i < BN; i += 128) bias_s[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          for (int i = etid; i < BN; i += 256) bias_s[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
           const long long row = (long long)m0 + row_l;
           const bool row_ok = row < p.M;
           const int unit0 = (n0 >> 8) * 64;
           const long long prow = row_ok ? (p.parent ? (long long)__ldg(p.parent + row) : row) : 0;
           const float* cp = p.c_prev ? p.c_prev + prow * p.H + unit0 : nullptr;
 #pragma unroll 1
-          for (int u0 = 0; u0 < 64; u0 += 16) {
+          for (int u0 = eh * 32; u0 < eh * 32 + 32; u0 += 16) {
             uint32_t vi[16], vf[16], vg[16], vo[16];
             tc_ld16(tmem_row + (uint32_t)u0, vi);
             tc_ld16(tmem_row + (uint32_t)(64 + u0), vf);
@@ -380,14 +382,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_wait(tfull_bar(as), (it >> 1) & 1, p.error, 4);
         tc_fence_after();
         const uint32_t tmem_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
-        asm volatile("bar.sync 1, 128;" ::: "memory");          // readers of the previous bias slice are done
-        for (int i = row_l; i < BN; i += 128) bias_s[i] = (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");          // readers of the previous bias slice are done
+        for (int i = etid; i < BN; i += 256) bias_s[i] = (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         const long long row = (long long)m0 + row_l;
         const bool row_ok = row < p.M;
-        const float t0 = (p.epi_mode == 2 && row_ok) ? __ldg(p.thresh + row) : INFINITY;
+        // candidates are finite logits >= thresh[row]; clamping to -FLT_MAX folds the "> -inf" test into one compare
+        const float t0 = (p.epi_mode == 2 && row_ok) ? fmaxf(__ldg(p.thresh + row), -3.402823466e+38f) : INFINITY;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = eh * (BN / 64); c < (eh + 1) * (BN / 64); ++c) {
           const int col0 = n0 + c * 32;
           if (col0 >= p.N) break;                                 // warp-uniform
           uint32_t v[32];
@@ -403,15 +406,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             x[4 * g + 3] = __uint_as_float(v[4 * g + 3]) + b4.w;
           }
           const int nv = p.N - col0;                              // valid columns in this group (>= 1)
+          if (nv < 32) {                                          // last group of the row: mask the padding columns
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = j < nv ? x[j] : -INFINITY;
+          }
           float mx = -INFINITY;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, j < nv ? x[j] : -INFINITY);
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, x[j]);
           if (p.epi_mode == 1) {
             if (row_ok) p.gmax[row * p.ld_gmax + (col0 >> 5)] = mx;
-          } else if (mx >= t0 && mx > -INFINITY) {
+          } else if (mx >= t0) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              if (j < nv && x[j] >= t0 && x[j] > -INFINITY) {
+              if (x[j] >= t0) {
                 const int slot = atomicAdd(p.cand_count + row, 1);
                 if (slot < p.cand_cap) {
                   p.cand_idx[row * p.cand_cap + slot] = col0 + j;
@@ -425,6 +432,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(as));
       }
+    } else if (eh != 0) {
+      // second epilogue group: idle for plain stores
     } else if (p.tma_store) {
       // ---- slab epilogue: each thread owns one accumulator row; a round covers 128 B of every row (32 fp32 or
       // 64 half columns), written 128B-swizzled into one of two 16 KB slabs and stored by one TMA instruction.

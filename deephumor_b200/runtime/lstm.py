@@ -112,8 +112,13 @@ class LSTMDecoderRT:
         beam.init(ind, val, caption, eos_index, True)
         # ---- beam phase (rnn_models.py:105-137): fixed trip count, frozen-at-break on the device
         for i in range(p0 + 1, max_len):
-            ops.gather_rows(self.table, beam.last_tok, ws['A'][0][:R, :self.E])
-            self._recur(ws, R, beam.parent_state)
+            if self.dtype != torch.float32 and self.L <= 8:
+                ops.lstm_prepare(self.table, beam.last_tok, beam.parent_state, [ws['hs'][l] for l in range(self.L)],
+                                 [ws['A'][l][:R] for l in range(self.L)],
+                                 [self.E if l == 0 else self.H for l in range(self.L)], R)
+            else:
+                ops.gather_rows(self.table, beam.last_tok, ws['A'][0][:R, :self.E])
+                self._recur(ws, R, beam.parent_state)
             self._step(ws, R, cur, beam.parent_state, logits=not fused)
             cur = 1 - cur
             self._select(pl, R, B, i, beam.done, B, top_k, temperature, unk_index, noise_mode,

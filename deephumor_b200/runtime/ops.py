@@ -195,6 +195,17 @@ def lstm_layer_tc(A, Wp, bias_p, c_prev, parent, c_out, h_out0, h_out1):
              0 if h_out1 is None else _rows(h_out1), rows, H, K, stream())
 
 
+def lstm_prepare(table, tok, parent, hs, A, in_off, rows):
+    """One launch for every operand of an LSTM step: A[0][:, :E] = table[tok], A[l][:, in_off[l]:+H] = hs[l][parent]."""
+    import ctypes
+    L, H, E = len(hs), hs[0].shape[-1], table.shape[1]
+    assert all(h.is_contiguous() and h.dtype == table.dtype and h.element_size() == 2 for h in hs)
+    arr_p = ctypes.c_void_p * L
+    LIB.call('dh_lstm_prepare', ptr(table), _rows(table), table.shape[0], ptr(tok), E, ptr(parent),
+             arr_p(*[ptr(h) for h in hs]), arr_p(*[ptr(a) for a in A]), (ctypes.c_longlong * L)(*[_rows(a) for a in A]),
+             (ctypes.c_int * L)(*in_off), L, H, rows, stream())
+
+
 def pack_lstm_gates(t, H):
     """[4H, ...] in nn.LSTM gate order (i, f, g, o) -> rows grouped per 64 hidden units as [i | f | g | o] blocks."""
     rest = t.shape[1:]

@@ -24,7 +24,7 @@ extern "C" {
 typedef struct CUstream_st* cudaStream_t;
 #endif
 
-#define DH_VERSION 107
+#define DH_VERSION 108
 
 #define DH_OK 0
 #define DH_ERR_ARG (-1)
@@ -111,6 +111,12 @@ int dh_gather_rows(const void* src, long long lds, long long n_src_rows, const i
  * which folds the beam reorder of rnn_models.py:135-137 into the load. */
 int dh_lstm_cell(const float* gates, long long ldg, const float* c_prev, const int* parent, float* c_out, void* h_out0,
                  long long ldh0, void* h_out1, long long ldh1, int rows, int H, int dtype, cudaStream_t stream);
+/* All operands of one LSTM time step in one launch (2-byte elements): A[0][r, 0:E] = table[tok[r]] (rnn_models.py:107) and
+ * A[l][r, in_off[l] : +H] = hs[l][parent[r]] for l < L (the h regather of rnn_models.py:135-137).  hs / A / lda / in_off
+ * are HOST arrays of L entries (device pointers inside). */
+int dh_lstm_prepare(const void* table, long long ldt, long long n_tok_rows, const int* tok, int E, const int* parent,
+                    const void* const* hs, void* const* A, const long long* lda, const int* in_off, int L, int H, int rows,
+                    cudaStream_t stream);
 /* Tensor-core nn.LSTM layer step with the cell update fused into the contraction's epilogue (rnn_models.py:80,108):
  * gates = A[rows,K] Wp[4H,K]^T + bias_p with A = [x | h_prev], Wp = [W_ih | W_hh] whose rows are re-ordered per 64
  * hidden units as (i, f, g, o) blocks (bias_p = b_ih + b_hh likewise); c_prev is read through parent[] (nullable:
