@@ -41,6 +41,7 @@ struct TcParams {
   int res_chunks;                         // > 0: residual added on the tensor core as BN/64 extra K chunks (R x I)
   int* error;                             // device flag set before a watchdog trap
   // Vocab-projection epilogues that keep the logits out of HBM (dh_vocab_groupmax / dh_vocab_candidates):
+  int n_stride;                           // N blocks visited: 0, n_stride, 2 n_stride, ... (1 except for sampled group maxima)
   int epi_mode;                           // 0: store C; 1: maxima of 32-column groups; 2: compact logits >= thresh[row]
   float* gmax; long long ld_gmax;         // [M, ld_gmax] group maxima (mode 1)
   const float* thresh;                    // [M] lower bound of the row's top_k-th largest logit (mode 2)
@@ -99,6 +100,50 @@ __device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap*
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: the pair shares one UMMA of M = 256; both CTAs' loads signal the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w, int h,
+                                                     int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {   // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -145,20 +190,25 @@ __device__ __forceinline__ float tanh_fast(float x) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ int dh_cdiv_dev(int a, int b) { return (a + b - 1) / b; }
+
 // K-major, 128B-swizzled operand tile (rows of 64 bf16 = 128 B, 8-row atoms of 1024 B):
 // start address >> 4 | SBO = 1024 B (bits 32..45) | descriptor version 1 (bits 46..47) | SWIZZLE_128B (bits 61..63).
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
 }
 // kind::f16 instruction descriptor: D fp32, A/B bf16 (format 1) or f16 (format 0), both K-major, M = 128, N = bn.
-__device__ __forceinline__ uint32_t umma_idesc(int bn, int ab_dtype) {
+__device__ __forceinline__ uint32_t umma_idesc(int bn, int ab_dtype, int m = BM) {
   const uint32_t fmt = ab_dtype == DH_BF16 ? 1u : 0u;
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-template <int BN>
+// PAIR: two CTAs of a cluster (one TPC) run ONE tcgen05.mma.cta_group::2 of M = 256: each CTA stages its own 128 A rows and
+// HALF of the W tile (BN/2 rows) and owns the accumulator of its 128 rows -- a third less operand traffic per FLOP from L2,
+// which is what bounds these contractions (profiles/: ~12 TB/s chip-wide TMA ceiling).
+template <int BN, bool PAIR = false>
 struct Cfg {
-  static constexpr int kStageBytes = (BM + BN) * BK * 2;
+  static constexpr int kStageBytes = (BM + (PAIR ? BN / 2 : BN)) * BK * 2;
   static constexpr int kStages = kSmemBudget / kStageBytes;
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kStagingBytes = 2 * BM * 128;   // two 128-row x 128 B slabs (TMA store) / transpose scratch
@@ -166,12 +216,13 @@ struct Cfg {
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStagingBytes + kBiasBytes + 256;
 };
 
-template <int BN>
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
                const __grid_constant__ CUtensorMap map_i, const TcParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, PAIR>;
+  constexpr int CG = PAIR ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
@@ -201,69 +252,104 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), p.epi_mode ? 8 : 4);
+      mbar_init(tempty_bar(s), (p.epi_mode ? 8 : 4) * CG);   // the leader's barrier collects both CTAs' epilogue warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_word)),
-                 "r"((uint32_t)C::kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_word)),
+                   "r"((uint32_t)C::kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_word)),
+                   "r"((uint32_t)C::kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_word);
+  // tile = (M block of BM * CG rows, N block); a CTA pair walks the tiles together, CTA `rank` owning rows +rank * BM
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   const int tiles = p.m_blocks * p.n_blocks;
+  const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tstride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto tile_m0 = [&](int tile) { return (tile / p.n_blocks) * (BM * CG) + (int)cta_rank * BM; };
 
   if (warp == 0) {
     if (lane == 0) {
       // ===================================================================== TMA producer
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.n_blocks) * BM, n0 = (tile % p.n_blocks) * BN;
+      for (int tile = tile0; tile < tiles; tile += tstride) {
+        const int m0 = tile_m0(tile), n0 = (tile % p.n_blocks) * BN * p.n_stride;
+        // an M block past the end (odd block count, second CTA of the last pair) re-loads the last valid block: its
+        // accumulator is never stored, and every TMA coordinate stays inside the tensor
+        const int m0l = min(m0, (dh_cdiv_dev(p.M, BM) - 1) * BM);
         int img = 0, ph = 0, qw = 0;
         if (p.conv) {
-          img = m0 / p.HoWo;
-          const int rem = m0 - img * p.HoWo;
+          img = m0l / p.HoWo;
+          const int rem = m0l - img * p.HoWo;
           ph = rem / p.Wo;
           qw = rem - ph * p.Wo;
         }
+        const int nb0 = n0 + (int)cta_rank * (BN / CG);          // this CTA's slice of the W tile
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           mbar_wait(empty_bar(stage), phase ^ 1u, p.error, 1);
           const uint32_t sa = ring + stage * C::kStageBytes, sb = sa + BM * BK * 2;
-          mbar_expect_tx(full_bar(stage), C::kStageBytes);
-          if (p.conv) {
-            const int tap = kc / p.c_chunks, c0 = (kc - tap * p.c_chunks) * BK;
-            const int r = tap / p.kw, s = tap - r * p.kw;
-            tma_load_im2col(sa, &map_a, full_bar(stage), c0, qw * p.stride - p.pad, ph * p.stride - p.pad, img,
-                            (uint16_t)s, (uint16_t)r);
+          if (cta_rank == 0) mbar_expect_tx(full_bar(stage), C::kStageBytes * CG);
+          if (PAIR) {
+            const uint32_t fb = mapa_u32(full_bar(stage), 0);
+            if (p.conv) {
+              const int tap = kc / p.c_chunks, c0 = (kc - tap * p.c_chunks) * BK;
+              const int r = tap / p.kw, s = tap - r * p.kw;
+              tma_load_im2col_pair(sa, &map_a, fb, c0, qw * p.stride - p.pad, ph * p.stride - p.pad, img, (uint16_t)s,
+                                   (uint16_t)r);
+            } else {
+              tma_load_2d_pair(sa, &map_a, fb, kc * BK, m0l);
+            }
+            tma_load_2d_pair(sb, &map_b, fb, kc * BK, nb0);
           } else {
-            tma_load_2d(sa, &map_a, full_bar(stage), kc * BK, m0);
+            if (p.conv) {
+              const int tap = kc / p.c_chunks, c0 = (kc - tap * p.c_chunks) * BK;
+              const int r = tap / p.kw, s = tap - r * p.kw;
+              tma_load_im2col(sa, &map_a, full_bar(stage), c0, qw * p.stride - p.pad, ph * p.stride - p.pad, img,
+                              (uint16_t)s, (uint16_t)r);
+            } else {
+              tma_load_2d(sa, &map_a, full_bar(stage), kc * BK, m0l);
+            }
+            tma_load_2d(sb, &map_b, full_bar(stage), kc * BK, nb0);
           }
-          tma_load_2d(sb, &map_b, full_bar(stage), kc * BK, n0);
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
         // residual as extra K chunks: D += R[m0:m0+128, n0+64j : +64] x I[:, 64j : +64]^T  (exact in fp32 accumulate)
         for (int j = 0; j < p.res_chunks; ++j) {
           mbar_wait(empty_bar(stage), phase ^ 1u, p.error, 1);
           const uint32_t sa = ring + stage * C::kStageBytes, sb = sa + BM * BK * 2;
-          mbar_expect_tx(full_bar(stage), C::kStageBytes);
-          tma_load_2d(sa, &map_r, full_bar(stage), n0 + j * BK, m0);
-          tma_load_2d(sb, &map_i, full_bar(stage), j * BK, 0);
+          if (cta_rank == 0) mbar_expect_tx(full_bar(stage), C::kStageBytes * CG);
+          if (PAIR) {
+            const uint32_t fb = mapa_u32(full_bar(stage), 0);
+            tma_load_2d_pair(sa, &map_r, fb, n0 + j * BK, m0l);
+            tma_load_2d_pair(sb, &map_i, fb, j * BK, (int)cta_rank * (BN / CG));
+          } else {
+            tma_load_2d(sa, &map_r, full_bar(stage), n0 + j * BK, m0l);
+            tma_load_2d(sb, &map_i, full_bar(stage), j * BK, 0);
+          }
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================================================================== MMA issuer
-      const uint32_t idesc = umma_idesc(BN, p.ab_dtype);
+    if (lane == 0 && cta_rank == 0) {
+      // ===================================================================== MMA issuer (the pair's leader CTA only)
+      const uint32_t idesc = umma_idesc(BN, p.ab_dtype, BM * CG);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile0; tile < tiles; tile += tstride, ++it) {
         const int as = it & 1;
         mbar_wait(tempty_bar(as), ((it >> 1) & 1) ^ 1u, p.error, 2);
         tc_fence_after();
@@ -275,10 +361,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint32_t sa = ring + stage * C::kStageBytes, sb = sa + BM * BK * 2;
           const uint64_t da = umma_desc(sa), db = umma_desc(sb);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)   // +32 B per UMMA_K step inside the 128 B swizzle row
-            tc_mma(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
-          tc_commit(empty_bar(stage));         // frees the smem slot once these MMAs have read it
-          if (kc == chunks - 1) tc_commit(tfull_bar(as));
+          for (int k = 0; k < BK / 16; ++k) {  // +32 B per UMMA_K step inside the 128 B swizzle row
+            if (PAIR) tc_mma_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
+            else tc_mma(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
+          }
+          // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+          if (PAIR) tc_commit_pair(empty_bar(stage)); else tc_commit(empty_bar(stage));
+          if (kc == chunks - 1) { if (PAIR) tc_commit_pair(tfull_bar(as)); else tc_commit(tfull_bar(as)); }
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -294,8 +383,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (BN == 256) {
         const int row_l = ew * 32 + lane;
         int it = 0;
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-          const int m0 = (tile / p.n_blocks) * BM, n0 = (tile % p.n_blocks) * BN;
+        for (int tile = tile0; tile < tiles; tile += tstride, ++it) {
+          const int m0 = tile_m0(tile), n0 = (tile % p.n_blocks) * BN * p.n_stride;
           const int as = it & 1;
           mbar_wait(tfull_bar(as), (it >> 1) & 1, p.error, 4);
           tc_fence_after();
@@ -369,15 +458,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(as));
+          if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar(as), 0)); else mbar_arrive(tempty_bar(as)); }
         }
       }
     } else if (p.epi_mode) {
       // ---- selection epilogues: every thread owns one accumulator row; nothing of the [M,N] product is stored.
       const int row_l = ew * 32 + lane;
       int it = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-        const int m0 = (tile / p.n_blocks) * BM, n0 = (tile % p.n_blocks) * BN;
+      for (int tile = tile0; tile < tiles; tile += tstride, ++it) {
+        const int m0 = tile_m0(tile), n0 = (tile % p.n_blocks) * BN * p.n_stride;
         const int as = it & 1;
         mbar_wait(tfull_bar(as), (it >> 1) & 1, p.error, 4);
         tc_fence_after();
@@ -392,7 +481,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll 1
         for (int c = eh * (BN / 64); c < (eh + 1) * (BN / 64); ++c) {
           const int col0 = n0 + c * 32;
-          if (col0 >= p.N) break;                                 // warp-uniform
+          if (col0 >= p.N) {                                      // warp-uniform: group past the end of the row
+            if (p.epi_mode == 1 && row_ok) p.gmax[row * p.ld_gmax + (tile % p.n_blocks) * (BN / 32) + c] = -INFINITY;
+            continue;
+          }
           uint32_t v[32];
           tc_ld32(tmem_row + (uint32_t)(c * 32), v);
           float x[32];
@@ -414,7 +506,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) mx = fmaxf(mx, x[j]);
           if (p.epi_mode == 1) {
-            if (row_ok) p.gmax[row * p.ld_gmax + (col0 >> 5)] = mx;
+            if (row_ok) p.gmax[row * p.ld_gmax + (tile % p.n_blocks) * (BN / 32) + c] = mx;
           } else if (mx >= t0) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -430,7 +522,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(as));
+        if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar(as), 0)); else mbar_arrive(tempty_bar(as)); }
       }
     } else if (eh != 0) {
       // second epilogue group: idle for plain stores
@@ -445,8 +537,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const bool elected = (warp == 4 && lane == 0);
       uint32_t round_ctr = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-        const int m0 = (tile / p.n_blocks) * BM, n0 = (tile % p.n_blocks) * BN;
+      for (int tile = tile0; tile < tiles; tile += tstride, ++it) {
+        const int m0 = tile_m0(tile), n0 = (tile % p.n_blocks) * BN * p.n_stride;
         const int as = it & 1;
         mbar_wait(tfull_bar(as), (it >> 1) & 1, p.error, 4);
         tc_fence_after();
@@ -523,7 +615,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(as));
+        if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar(as), 0)); else mbar_arrive(tempty_bar(as)); }
       }
       if (elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else {
@@ -531,8 +623,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
     const bool res_vec = p.res && (p.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0);
     int it = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-      const int m0 = (tile / p.n_blocks) * BM, n0 = (tile % p.n_blocks) * BN;
+    for (int tile = tile0; tile < tiles; tile += tstride, ++it) {
+      const int m0 = tile_m0(tile), n0 = (tile % p.n_blocks) * BN * p.n_stride;
       const int as = it & 1;
       mbar_wait(tfull_bar(as), (it >> 1) & 1, p.error, 4);
       tc_fence_after();
@@ -624,16 +716,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar(as), 0)); else mbar_arrive(tempty_bar(as)); }
     }
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();   // pair: the peer's MMAs / remote arrives target this CTA until here
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::kTmemCols)
-                 : "memory");
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::kTmemCols)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::kTmemCols)
+                   : "memory");
   }
 }
 
@@ -697,21 +793,37 @@ int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long col
   return DH_OK;
 }
 
-template <int BN>
+template <int BN, bool PAIR>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mr, const CUtensorMap& mi,
            TcParams& p, cudaStream_t s) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, PAIR>;
   static bool attr = false;
   if (!attr) {
-    DH_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    DH_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr = true;
   }
-  p.n_blocks = dh_cdiv(p.N, BN);
-  p.m_blocks = dh_cdiv(p.M, BM);
+  if (p.n_stride < 1) p.n_stride = 1;
+  p.n_blocks = dh_cdiv(dh_cdiv(p.N, BN), p.n_stride);
+  p.m_blocks = dh_cdiv(p.M, PAIR ? 2 * BM : BM);
   const int tiles = p.m_blocks * p.n_blocks;
-  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
   if (p.res_chunks) p.res_chunks = BN / BK;
-  gemm_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, s>>>(ma, mb, mc, mr, mi, p);
+  if (PAIR) {
+    const int pairs = g_num_sms / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = C::kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    DH_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, PAIR>, ma, mb, mc, mr, mi, p));
+  } else {
+    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    gemm_tc_kernel<BN, PAIR><<<grid, kThreads, C::kSmemBytes, s>>>(ma, mb, mc, mr, mi, p);
+  }
   DH_LAUNCH_OK();
   return DH_OK;
 }
@@ -726,7 +838,13 @@ int pick_bn(int M, int N) {
 
 int dispatch(const CUtensorMap& ma, const void* W, long long ldw, TcParams& p, int bn, cudaStream_t s) {
   CUtensorMap mb, mc = ma, mr = ma, mi = ma;
-  int rc = make_map_2d(&mb, W, p.N, p.K, ldw, bn, p.ab_dtype);
+  // CTA pairs (cta_group::2) for the 128- and 256-wide tiles whenever there are at least two M blocks to pair up
+  static const bool pair_ok = !getenv("DH_TC_NO_PAIR");
+  // ... and the K loop is long enough (>= 16 chunks) to amortise the pair's cross-CTA barrier round trips: measured on
+  // the ResNet-50 / decoder shapes (profiles/), pairs win 6-30 % at K >= 1024 and lose 8-50 % on short-K, store-bound tiles
+  const bool pair = pair_ok && bn >= 128 && p.M > BM && p.k_chunks + (p.res ? bn / BK : 0) >= 16;
+  const int b_rows = pair ? bn / 2 : bn;                   // W rows one CTA stages per K chunk
+  int rc = make_map_2d(&mb, W, p.N, p.K, ldw, b_rows, p.ab_dtype);
   if (rc) return rc;
   p.error = g_error_flag;
   // TMA-store epilogue when the output rows are 16 B aligned; the residual then rides the tensor core (R x I) if it
@@ -745,14 +863,14 @@ int dispatch(const CUtensorMap& ma, const void* W, long long ldw, TcParams& p, i
     if (p.res) {
       rc = make_map_2d(&mr, p.res, p.M, p.N, p.ldr, BM, p.ab_dtype);
       if (rc) return rc;
-      rc = make_map_2d(&mi, g_identity[p.ab_dtype], 256, 256, 256, bn, p.ab_dtype);
+      rc = make_map_2d(&mi, g_identity[p.ab_dtype], 256, 256, 256, b_rows, p.ab_dtype);
       if (rc) return rc;
       p.res_chunks = 1;   // launch<> sets BN / 64
     }
   }
-  if (bn == 64) return launch<64>(ma, mb, mc, mr, mi, p, s);
-  if (bn == 128) return launch<128>(ma, mb, mc, mr, mi, p, s);
-  return launch<256>(ma, mb, mc, mr, mi, p, s);
+  if (bn == 64) return launch<64, false>(ma, mb, mc, mr, mi, p, s);
+  if (bn == 128) return pair ? launch<128, true>(ma, mb, mc, mr, mi, p, s) : launch<128, false>(ma, mb, mc, mr, mi, p, s);
+  return pair ? launch<256, true>(ma, mb, mc, mr, mi, p, s) : launch<256, false>(ma, mb, mc, mr, mi, p, s);
 }
 
 }  // namespace
@@ -786,9 +904,9 @@ extern "C" int dh_gemm_tc(const void* A, long long lda, const void* W, long long
 // Vocab projection with the logits kept on chip (models/rnn_models.py:81,109 and models/transformers.py:488,736 feeding
 // models/beam.py:32-37): pass 1 stores the maximum of every 32-column group of logits[M,N] = A W^T + bias, pass 2
 // recomputes the identical product and appends (column, logit) of every logit >= thresh[row] to the row's candidate list.
-static int vocab_pass(int mode, const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias,
-                      int M, int N, int K, float* gmax, long long ld_gmax, const float* thresh, int* cand_count,
-                      int* cand_idx, float* cand_val, int cand_cap, cudaStream_t stream) {
+static int vocab_pass(int mode, int tile_stride, const void* A, long long lda, const void* W, long long ldw, int ab_dtype,
+                      const float* bias, int M, int N, int K, float* gmax, long long ld_gmax, const float* thresh,
+                      int* cand_count, int* cand_idx, float* cand_val, int cand_cap, cudaStream_t stream) {
   DH_ARG(A && W && M >= 0 && N > 0 && K > 0);
   DH_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0);
   DH_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0);
@@ -802,6 +920,7 @@ static int vocab_pass(int mode, const void* A, long long lda, const void* W, lon
   p.ab_dtype = ab_dtype;
   p.bias = bias;
   p.epi_mode = mode;
+  p.n_stride = tile_stride;
   p.gmax = gmax; p.ld_gmax = ld_gmax;
   p.thresh = thresh; p.cand_count = cand_count; p.cand_idx = cand_idx; p.cand_val = cand_val; p.cand_cap = cand_cap;
   CUtensorMap ma;
@@ -841,16 +960,19 @@ extern "C" int dh_lstm_layer_tc(const void* A, long long lda, const void* Wp, lo
 }
 
 extern "C" int dh_vocab_groupmax(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias,
-                                 int M, int N, int K, float* gmax, long long ld_gmax, cudaStream_t stream) {
-  DH_ARG(gmax && ld_gmax >= dh_cdiv(N, 32));
-  return vocab_pass(1, A, lda, W, ldw, ab_dtype, bias, M, N, K, gmax, ld_gmax, nullptr, nullptr, nullptr, nullptr, 0, stream);
+                                 int M, int N, int K, int tile_stride, float* gmax, long long ld_gmax, cudaStream_t stream) {
+  DH_ARG(gmax && tile_stride >= 1);
+  const int bn = N <= 64 ? 64 : N <= 128 ? 128 : 256;
+  DH_ARG(ld_gmax >= (long long)dh_cdiv(dh_cdiv(N, bn), tile_stride) * (bn / 32));
+  return vocab_pass(1, tile_stride, A, lda, W, ldw, ab_dtype, bias, M, N, K, gmax, ld_gmax, nullptr, nullptr, nullptr, nullptr,
+                    0, stream);
 }
 
 extern "C" int dh_vocab_candidates(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias,
                                    int M, int N, int K, const float* thresh, int* cand_count, int* cand_idx, float* cand_val,
                                    int cand_cap, cudaStream_t stream) {
   DH_ARG(thresh && cand_count && cand_idx && cand_val && cand_cap > 0);
-  return vocab_pass(2, A, lda, W, ldw, ab_dtype, bias, M, N, K, nullptr, 0, thresh, cand_count, cand_idx, cand_val, cand_cap,
+  return vocab_pass(2, 1, A, lda, W, ldw, ab_dtype, bias, M, N, K, nullptr, 0, thresh, cand_count, cand_idx, cand_val, cand_cap,
                     stream);
 }
 

@@ -126,15 +126,23 @@ class LSTMDecoderRT:
         beam.final(temperature, noise_mode, 0, 0, max_len + 1, max(p0 + 1, max_len), pad_index, max_len, pl['ids'],
                    pl['lens'], dyn)
 
-    def generate(self, start_emb, caption, max_len, temperature, beam_size, top_k, eos_index, unk_index, noise_mode,
-                 seed, image_base, pad_index=0):
+    def generate(self, *args, **kw):
+        """Optimistic first try with a sampled pass 1 of the fused vocab projection; if a candidate list overflowed
+        (status bit 2) the whole generation is redone with the exhaustive pass 1, which cannot overflow."""
+        out = self._generate(*args, robust=False, **kw)
+        if out[3] and int(out[2].item()) & 2:
+            out = self._generate(*args, robust=True, **kw)
+        return out[:3]
+
+    def _generate(self, start_emb, caption, max_len, temperature, beam_size, top_k, eos_index, unk_index, noise_mode,
+                  seed, image_base, pad_index=0, robust=False):
         """start_emb fp32 [N,E]; caption int32 [N or 1, p] or None -> (ids int64 [N,max_len], lengths int64 [N], status).
 
         The decode loop is captured once per (batch, beam, lengths, sampling parameters) into a CUDA graph over
         static buffers and replayed; seed / image_base reach the kernels through a device word pair."""
         N, B, dev = start_emb.shape[0], beam_size, self.device
         p0 = 0 if caption is None else caption.shape[1]
-        key = (N, B, p0, max_len, float(temperature), top_k, eos_index, unk_index, noise_mode, pad_index)
+        key = (N, B, p0, max_len, float(temperature), top_k, eos_index, unk_index, noise_mode, pad_index, robust)
         pl = self._plans.get(key)
         if pl is None:
             if len(self._plans) >= 2:
@@ -142,7 +150,7 @@ class LSTMDecoderRT:
             R = N * B
             fused = ops.FUSED_VOCAB and ops.VocabSelect.supported(self.Wc, self.V, top_k)
             pl = dict(N=N, ws=self._alloc(max(R, N), logits=not fused),
-                      vsel=ops.VocabSelect(max(R, N), self.V, top_k, dev) if fused else None, beam=ops.Beam(N, B, max(max_len, p0 + 1), dev),
+                      vsel=ops.VocabSelect(max(R, N), self.V, top_k, dev, stride=1 if robust else None) if fused else None, beam=ops.Beam(N, B, max(max_len, p0 + 1), dev),
                       ind=torch.empty(R, B, dtype=torch.int32, device=dev),
                       val=torch.empty(R, B, dtype=torch.float32, device=dev),
                       dyn=torch.zeros(2, dtype=torch.int64, device=dev),
@@ -169,7 +177,8 @@ class LSTMDecoderRT:
                     self._decode(*args)
                 pl['graph'] = g
             pl['graph'].replay()
-        return pl['ids'].clone(), pl['lens'].clone(), pl['beam'].status.clone()
+        sampled = pl['vsel'] is not None and pl['vsel'].stride > 1
+        return pl['ids'].clone(), pl['lens'].clone(), pl['beam'].status.clone(), sampled
 
     def forward(self, image_emb, captions, lengths=None):
         """Teacher-forced logits [N, max(lengths), V] fp32 (rnn_models.py:28-46; packed-sequence semantics, Q24)."""

@@ -257,9 +257,19 @@ class VocabSelect:
     """Vocab projection fused with token selection for `rows` rows: two bit-identical tcgen05 passes over
     logits = A W^T + bias (group maxima -> threshold, then candidate compaction), logits never stored."""
 
-    def __init__(self, rows, V, top_k, device):
+    def __init__(self, rows, V, top_k, device, stride=None):
+        """stride: pass 1 visits every stride-th 256-column tile of the row (None: DH_VOCAB_STRIDE, default 1).
+        stride 1 can never overflow the candidate lists.  A sampled pass 1 is ~stride times cheaper but its looser
+        threshold lengthens the lists (216 instead of 51 candidates per row at stride 4, V = 36 541, top-k 50), which
+        costs more in pass 2 and the selection than pass 1 saves (measured, profiles/) -- so it is off by default; an
+        overflow is reported through DH_STATUS_TOO_MANY_TIES and the decoders then redo the generation with stride 1."""
         self.rows, self.V, self.top_k = rows, V, top_k
-        self.n_groups = (V + 31) // 32
+        bn = 64 if V <= 64 else 128 if V <= 128 else 256
+        n_blocks = (V + bn - 1) // bn
+        if stride is None:
+            stride = max(1, min(int(os.environ.get('DH_VOCAB_STRIDE', '1')), ((V + 31) // 32) // (4 * top_k)))
+        self.stride = stride
+        self.n_groups = (n_blocks + stride - 1) // stride * (bn // 32)
         self.cap = min((V + 31) // 32 * 32, 32 * top_k)
         f32, i32 = dict(dtype=torch.float32, device=device), dict(dtype=torch.int32, device=device)
         self.gmax = torch.empty(rows, self.n_groups, **f32)
@@ -279,10 +289,12 @@ class VocabSelect:
         rows, K = A.shape
         assert rows <= self.rows and W.shape == (self.V, K) and W.dtype == A.dtype
         args = (ptr(A), _rows(A), ptr(W), _rows(W), code(A), ptr(bias), rows, self.V, K)
-        with PROFILE.range('vocab_gemm', 2.0 * 2.0 * rows * self.V * K):
-            LIB.call('dh_vocab_groupmax', *args, ptr(self.gmax), self.n_groups, stream())
+        with PROFILE.range('vocab_pass1', 2.0 * rows * self.V * K / self.stride):
+            LIB.call('dh_vocab_groupmax', *args, self.stride, ptr(self.gmax), self.n_groups, stream())
+        with PROFILE.range('select_beam'):
             LIB.call('dh_vocab_threshold', ptr(self.gmax), self.n_groups, rows, self.n_groups, self.top_k,
                      ptr(self.thresh), ptr(self.count), stream())
+        with PROFILE.range('vocab_gemm', 2.0 * rows * self.V * K):          # one launch = one full [rows,V,K] product
             LIB.call('dh_vocab_candidates', *args, ptr(self.thresh), ptr(self.count), ptr(self.idx), ptr(self.val),
                      self.cap, stream())
         with PROFILE.range('select_beam'):

@@ -126,8 +126,16 @@ class XfmrDecoderRT:
             select(R, B, i, beam.done, beam_step=True)
         beam.final(temperature, noise_mode, 0, 0, max_len + 1, max_len, self.pad, max_len, pl['ids'], pl['lens'], dyn)
 
-    def generate(self, start_emb, spatial, caption, max_len, temperature, beam_size, top_k, eos_index, unk_index,
-                 noise_mode, seed, image_base):
+    def generate(self, *args, **kw):
+        """Optimistic first try with a sampled pass 1 of the fused vocab projection; if a candidate list overflowed
+        (status bit 2) the whole generation is redone with the exhaustive pass 1, which cannot overflow."""
+        out = self._generate(*args, robust=False, **kw)
+        if out[3] and int(out[2].item()) & 2:
+            out = self._generate(*args, robust=True, **kw)
+        return out[:3]
+
+    def _generate(self, start_emb, spatial, caption, max_len, temperature, beam_size, top_k, eos_index, unk_index,
+                  noise_mode, seed, image_base, robust=False):
         """start_emb fp32 [N,D]; spatial [N*49,D] (cross) or None; caption int32 [N or 1,p] or None.
         The decode is captured once per configuration into a CUDA graph over static buffers and replayed."""
         N, B, D, dev, dt = start_emb.shape[0], beam_size, self.D, self.device, self.dtype
@@ -137,14 +145,14 @@ class XfmrDecoderRT:
         need = max(S, 49) if self.cross else S                   # reference pads to max(T+1, 49) (Q15, Q19)
         if need > self.pos.shape[0]:
             raise IndexError('index out of range in self')       # what nn.Embedding raises in the reference (Q19)
-        key = (N, B, p0, max_len, float(temperature), top_k, eos_index, unk_index, noise_mode)
+        key = (N, B, p0, max_len, float(temperature), top_k, eos_index, unk_index, noise_mode, robust)
         pl = self._plans.get(key)
         if pl is None:
             self._plans.clear()
             rows_alloc = max(R, N)
             mk = lambda *shape, dtype=dt: torch.empty(*shape, dtype=dtype, device=dev)
             fused = ops.FUSED_VOCAB and ops.VocabSelect.supported(self.Wc, self.V, top_k)
-            pl = dict(N=N, vsel=ops.VocabSelect(rows_alloc, self.V, top_k, dev) if fused else None, x=mk(rows_alloc, D), qb=mk(rows_alloc, D), attn=mk(rows_alloc, D), tmp=mk(rows_alloc, D),
+            pl = dict(N=N, vsel=ops.VocabSelect(rows_alloc, self.V, top_k, dev, stride=1 if robust else None) if fused else None, x=mk(rows_alloc, D), qb=mk(rows_alloc, D), attn=mk(rows_alloc, D), tmp=mk(rows_alloc, D),
                       h1=mk(rows_alloc, self.pf), logits=None if fused else mk(rows_alloc, self.ldv, dtype=torch.float32),
                       Kc=[torch.zeros(R, S, D, dtype=dt, device=dev) for _ in range(self.L)],
                       Vc=[torch.zeros(R, S, D, dtype=dt, device=dev) for _ in range(self.L)],
@@ -175,7 +183,8 @@ class XfmrDecoderRT:
                     self._decode(*args)
                 pl['graph'] = g
             pl['graph'].replay()
-        return pl['ids'].clone(), pl['lens'].clone(), pl['beam'].status.clone()
+        sampled = pl['vsel'] is not None and pl['vsel'].stride > 1
+        return pl['ids'].clone(), pl['lens'].clone(), pl['beam'].status.clone(), sampled
 
     # ------------------------------------------------------------------ teacher-forced forward
     def hidden(self, start_emb, spatial, captions):

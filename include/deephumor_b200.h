@@ -24,7 +24,7 @@ extern "C" {
 typedef struct CUstream_st* cudaStream_t;
 #endif
 
-#define DH_VERSION 108
+#define DH_VERSION 109
 
 #define DH_OK 0
 #define DH_ERR_ARG (-1)
@@ -169,12 +169,16 @@ int dh_select_tokens(const float* logits, long long ld, int rows, int V, int bea
                      cudaStream_t stream);
 /* Vocab projection fused with the selection, logits never stored (rnn_models.py:81,109 / transformers.py:488,736 ->
  * beam.py:32-53).  logits[M,N] = A[M,K] W[N,K]^T + bias (tcgen05, A / W ab_dtype) are produced twice, bit-identically:
- *   dh_vocab_groupmax    gmax[m, g] = max of logits[m, 32g .. 32g+31]                       (pass 1)
+ *   dh_vocab_groupmax    gmax[m, g] = max of the g-th 32-column group of logits[m, :] among the N tiles 0, s, 2s, ...
+ *                        (s = tile_stride; tile = 256 columns; groups past N hold -inf)              (pass 1)
  *   dh_vocab_threshold   thresh[m] = top_k-th largest of gmax[m, :] (<= the top_k-th largest logit); cand_count[m] = 0
  *   dh_vocab_candidates  appends (column, logit) of every logit >= thresh[m] to row m's list     (pass 2)
- *   dh_select_candidates dh_select_tokens on those lists (cand_cap >= min(N, 32 * top_k) cannot overflow, ties aside). */
+ *   dh_select_candidates dh_select_tokens on those lists.
+ * With tile_stride == 1 a capacity cand_cap >= min(N, 32 * top_k) cannot overflow (ties aside).  tile_stride > 1 samples
+ * the row (any subset of logits gives a valid lower bound): pass 1 costs 1/s, the lists get a few times longer, and an
+ * overflow (DH_STATUS_TOO_MANY_TIES) tells the caller to redo the step with tile_stride == 1. */
 int dh_vocab_groupmax(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias, int M,
-                      int N, int K, float* gmax, long long ld_gmax, cudaStream_t stream);
+                      int N, int K, int tile_stride, float* gmax, long long ld_gmax, cudaStream_t stream);
 int dh_vocab_threshold(const float* gmax, long long ld_gmax, int rows, int n_groups, int top_k, float* thresh,
                        int* cand_count, cudaStream_t stream);
 int dh_vocab_candidates(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias, int M,

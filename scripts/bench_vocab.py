@@ -32,10 +32,11 @@ out16=torch.empty(M,ldc+(-ldc)%8,dtype=torch.bfloat16,device=dev)
 print('bf16 out', t(lambda: ops.gemm(A,W,out16[:,:N],bias=b)))
 # fused two-pass path (logits never stored)
 from deephumor_b200._lib import LIB, ptr, stream
-vs = ops.VocabSelect(M, N, 50, dev)
+vs = ops.VocabSelect(M, N, 50, dev, stride=int(os.environ.get('STRIDE', '0')) or None)
+print('pass-1 tile stride', vs.stride, 'groups', vs.n_groups)
 Ab = A
 args = (ptr(Ab), K, ptr(W), K, 1, ptr(b), M, N, K)
-print('pass1 groupmax', t(lambda: LIB.call('dh_vocab_groupmax', *args, ptr(vs.gmax), vs.n_groups, stream())))
+print('pass1 groupmax', t(lambda: LIB.call('dh_vocab_groupmax', *args, vs.stride, ptr(vs.gmax), vs.n_groups, stream())))
 print('threshold     ', t(lambda: LIB.call('dh_vocab_threshold', ptr(vs.gmax), vs.n_groups, M, vs.n_groups, 50, ptr(vs.thresh), ptr(vs.count), stream())))
 def p2():
     vs.count.zero_()

@@ -170,3 +170,32 @@ def test_full_size_generation_is_shard_invariant(kind, n_img, beam):
     pos = torch.arange(32, device=DEV).unsqueeze(0)
     assert bool((ids[pos.expand_as(ids) >= lens.unsqueeze(1)] == 0).all())
     assert len({tuple(r.tolist()) for r in ids.cpu()}) > n_img // 2      # captions depend on the image
+
+
+def test_sampled_pass1_overflow_falls_back_to_exhaustive_pass(monkeypatch):
+    """A classifier whose large logits all sit in vocabulary tiles the sampled pass 1 skips overflows the candidate
+    lists (status bit 2); generate() must then redo the step with the exhaustive pass 1 and return exactly what the
+    materialised-logits path returns."""
+    from deephumor_b200.runtime import ops
+    fx = H.load_fixture('canon', 'lstm')
+    monkeypatch.setenv('DH_VOCAB_STRIDE', '4')
+    m, sd, imgs, labs, caps, lens = build(fx, 'bf16')
+    with torch.no_grad():
+        b = m.decoder.classifier.bias
+        for t in (1, 2, 3, 5, 6, 7, 9, 10, 11):              # tiles of 256 columns that a stride-4 pass 1 never visits
+            b[256 * t:256 * (t + 1)] += 30.0
+    m.invalidate()
+    kw = dict(max_len=8, temperature=1.0, beam_size=5, top_k=50, noise='injected', seed=3)
+    res = []
+    for fused in (True, False):
+        ops.FUSED_VOCAB = fused
+        m.invalidate()
+        try:
+            with torch.no_grad():
+                res.append(m.generate(imgs.cuda(), **kw))
+        finally:
+            ops.FUSED_VOCAB = True
+    rt = m.decoder._rt()
+    (i0, l0), (i1, l1) = res
+    assert torch.equal(i0, i1) and torch.equal(l0, l1)
+    assert int(i0[:, 0].min()) >= 256 and int(i0[:, 0].max()) < 256 * 12       # the boosted columns win
