@@ -468,16 +468,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int tile = tile0; tile < tiles; tile += tstride, ++it) {
         const int m0 = tile_m0(tile), n0 = (tile % p.n_blocks) * BN * p.n_stride;
         const int as = it & 1;
+        const long long row = (long long)m0 + row_l;
+        const bool row_ok = row < p.M;
+        // issued before the wait on the accumulator so that its L2 round trip is hidden
+        const float thr = (p.epi_mode == 2 && row_ok) ? __ldg(p.thresh + row) : INFINITY;
         mbar_wait(tfull_bar(as), (it >> 1) & 1, p.error, 4);
         tc_fence_after();
         const uint32_t tmem_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
         asm volatile("bar.sync 1, 256;" ::: "memory");          // readers of the previous bias slice are done
         for (int i = etid; i < BN; i += 256) bias_s[i] = (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        const long long row = (long long)m0 + row_l;
-        const bool row_ok = row < p.M;
         // candidates are finite logits >= thresh[row]; clamping to -FLT_MAX folds the "> -inf" test into one compare
-        const float t0 = (p.epi_mode == 2 && row_ok) ? fmaxf(__ldg(p.thresh + row), -3.402823466e+38f) : INFINITY;
+        const float t0 = (p.epi_mode == 2 && row_ok) ? fmaxf(thr, -3.402823466e+38f) : INFINITY;
+        // Candidates of this thread's slice are parked in shared memory (the store staging area is idle in this mode) and
+        // appended with ONE atomic per row and tile: the slot's round trip to L2 is paid once, after the TMEM reads.
+        constexpr int kPend = 8;
+        uint2* pend = reinterpret_cast<uint2*>(staging) + etid * kPend;
+        int npend = 0;
+        auto flush = [&]() {
+          const int slot = atomicAdd(p.cand_count + row, npend);
+          for (int i = 0; i < npend; ++i) {
+            if (slot + i < p.cand_cap) {
+              p.cand_idx[row * p.cand_cap + slot + i] = (int)pend[i].x;
+              p.cand_val[row * p.cand_cap + slot + i] = __uint_as_float(pend[i].y);
+            }
+          }
+          npend = 0;
+        };
 #pragma unroll 1
         for (int c = eh * (BN / 64); c < (eh + 1) * (BN / 64); ++c) {
           const int col0 = n0 + c * 32;
@@ -511,18 +528,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               if (x[j] >= t0) {
-                const int slot = atomicAdd(p.cand_count + row, 1);
-                if (slot < p.cand_cap) {
-                  p.cand_idx[row * p.cand_cap + slot] = col0 + j;
-                  p.cand_val[row * p.cand_cap + slot] = x[j];
-                }
+                if (npend == kPend) flush();
+                pend[npend++] = make_uint2((uint32_t)(col0 + j), __float_as_uint(x[j]));
               }
             }
           }
         }
+        // the accumulator is drained: hand the TMEM buffer back to the MMA warp BEFORE paying the atomics' round trip
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar(as), 0)); else mbar_arrive(tempty_bar(as)); }
+        if (npend) flush();
       }
     } else if (eh != 0) {
       // second epilogue group: idle for plain stores

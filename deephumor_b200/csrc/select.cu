@@ -254,6 +254,9 @@ __global__ void __launch_bounds__(kSelThreads) select_tokens_kernel(SelParams p)
 // top_k) are then compacted per warp and ranked exactly.
 constexpr int kThrWarps = 8;
 constexpr int kThrCap = 256;
+// NPL > 0: the whole row (<= 32 * NPL group maxima) is loaded into registers with all loads in flight at once (one L2
+// round trip); NPL == 0: generic two-pass version for longer rows.
+template <int NPL>
 __global__ void __launch_bounds__(kThrWarps * 32) vocab_threshold_kernel(const float* __restrict__ gmax, long long ld, int rows,
                                                                         int n_groups, int top_k, float* __restrict__ thresh,
                                                                         int* __restrict__ cand_count) {
@@ -263,23 +266,41 @@ __global__ void __launch_bounds__(kThrWarps * 32) vocab_threshold_kernel(const f
   const int r = blockIdx.x * kThrWarps + w;
   if (r >= rows) return;
   const float* row = gmax + (long long)r * ld;
+  constexpr int NR = NPL > 0 ? NPL : 1;
+  float xr[NR];
+  if (NPL > 0) {
+#pragma unroll
+    for (int u = 0; u < NR; ++u) {
+      const int i = u * 32 + lane;
+      xr[u] = i < n_groups ? __ldg(row + i) : -INFINITY;
+    }
+  }
   float t0 = -INFINITY;
   if (top_k <= n_groups) {
     float t1 = -INFINITY;
     if (top_k <= 64) {
       float m1 = -INFINITY, m2 = -INFINITY;
-      for (int i0 = 0; i0 < n_groups; i0 += 256) {       // 8 independent loads in flight per lane
-        float x[8];
+      if (NPL > 0) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int i = i0 + u * 32 + lane;
-          x[u] = i < n_groups ? __ldg(row + i) : -INFINITY;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float hi = fmaxf(m1, x[u]);
-          m2 = fmaxf(m2, fminf(m1, x[u]));
+        for (int u = 0; u < NR; ++u) {
+          const float hi = fmaxf(m1, xr[u]);
+          m2 = fmaxf(m2, fminf(m1, xr[u]));
           m1 = hi;
+        }
+      } else {
+        for (int i0 = 0; i0 < n_groups; i0 += 256) {       // 8 independent loads in flight per lane
+          float x[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * 32 + lane;
+            x[u] = i < n_groups ? __ldg(row + i) : -INFINITY;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float hi = fmaxf(m1, x[u]);
+            m2 = fmaxf(m2, fminf(m1, x[u]));
+            m1 = hi;
+          }
         }
       }
       s_top[w][lane] = m1;
@@ -296,22 +317,22 @@ __global__ void __launch_bounds__(kThrWarps * 32) vocab_threshold_kernel(const f
       t1 = dh_warp_max(t1);            // exactly one slot has that rank; if it holds -inf (n_groups < 64) t1 stays -inf
     }
     int n = 0;
-    for (int i0 = 0; i0 < n_groups; i0 += 256) {
-      float x[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int i = i0 + u * 32 + lane;
-        x[u] = i < n_groups ? __ldg(row + i) : -INFINITY;
+    auto offer = [&](float x, bool in_range) {
+      const bool keep = in_range && x >= t1;
+      const unsigned mask = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const int pos = n + __popc(mask & ((1u << lane) - 1u));
+        if (pos < kThrCap) s_cand[w][pos] = x;
       }
+      n += __popc(mask);
+    };
+    if (NPL > 0) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const bool keep = (i0 + u * 32 + lane) < n_groups && x[u] >= t1;
-        const unsigned mask = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-          const int pos = n + __popc(mask & ((1u << lane) - 1u));
-          if (pos < kThrCap) s_cand[w][pos] = x[u];
-        }
-        n += __popc(mask);
+      for (int u = 0; u < NR; ++u) offer(xr[u], u * 32 + lane < n_groups);
+    } else {
+      for (int i0 = 0; i0 < n_groups; i0 += 32) {
+        const int i = i0 + lane;
+        offer(i < n_groups ? __ldg(row + i) : -INFINITY, i < n_groups);
       }
     }
     __syncwarp();
@@ -724,8 +745,11 @@ extern "C" int dh_vocab_threshold(const float* gmax, long long ld_gmax, int rows
                                   int* cand_count, cudaStream_t s) {
   DH_ARG(gmax && thresh && cand_count && rows >= 0 && n_groups > 0 && ld_gmax >= n_groups && top_k >= 1);
   if (rows == 0) return DH_OK;
-  vocab_threshold_kernel<<<dh_cdiv(rows, kThrWarps), kThrWarps * 32, 0, s>>>(gmax, ld_gmax, rows, n_groups, top_k, thresh,
-                                                                            cand_count);
+  const int grid = dh_cdiv(rows, kThrWarps);
+  if (n_groups <= 32 * 40)
+    vocab_threshold_kernel<40><<<grid, kThrWarps * 32, 0, s>>>(gmax, ld_gmax, rows, n_groups, top_k, thresh, cand_count);
+  else
+    vocab_threshold_kernel<0><<<grid, kThrWarps * 32, 0, s>>>(gmax, ld_gmax, rows, n_groups, top_k, thresh, cand_count);
   DH_LAUNCH_OK();
   return DH_OK;
 }

@@ -158,13 +158,26 @@ stem_pool_kernel(const float* __restrict__ images, const T* __restrict__ wp, con
     // ---- input band: rows 4*py0-5 .. 4*py0+9, fp32 NCHW -> T [row][5 + col][rgb]   (previous item's MMAs are all
     //      complete: its last accumulator group was drained before this point, so the band may be overwritten)
     const float* src = images + (long long)img * 3 * 224 * 224;
-    for (int i = tid; i < 3 * kBandRows * 56; i += kThreads) {
+    // all of a thread's loads are issued before the first conversion / store: one memory round trip per item, not ten
+    constexpr int kBandVec = 3 * kBandRows * 56, kBandIter = (kBandVec + kThreads - 1) / kThreads;
+    float4 bv[kBandIter];
+#pragma unroll
+    for (int u = 0; u < kBandIter; ++u) {
+      const int i = tid + u * kThreads;
       const int c4 = i % 56, rr = (i / 56) % kBandRows, c = i / (56 * kBandRows);
       const int gr = 4 * py0 - 5 + rr;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gr >= 0 && gr < 224) v = __ldg(reinterpret_cast<const float4*>(src + ((long long)c * 224 + gr) * 224) + c4);
-      T* d = band + rr * kPitch + (5 + 4 * c4) * 3 + c;
-      d[0] = dh_from_f<T>(v.x); d[3] = dh_from_f<T>(v.y); d[6] = dh_from_f<T>(v.z); d[9] = dh_from_f<T>(v.w);
+      bv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < kBandVec && gr >= 0 && gr < 224)
+        bv[u] = __ldg(reinterpret_cast<const float4*>(src + ((long long)c * 224 + gr) * 224) + c4);
+    }
+#pragma unroll
+    for (int u = 0; u < kBandIter; ++u) {
+      const int i = tid + u * kThreads;
+      if (i < kBandVec) {
+        const int c4 = i % 56, rr = (i / 56) % kBandRows, c = i / (56 * kBandRows);
+        T* d = band + rr * kPitch + (5 + 4 * c4) * 3 + c;
+        d[0] = dh_from_f<T>(bv[u].x); d[3] = dh_from_f<T>(bv[u].y); d[6] = dh_from_f<T>(bv[u].z); d[9] = dh_from_f<T>(bv[u].w);
+      }
     }
     __syncthreads();
 
