@@ -519,17 +519,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = j < nv ? x[j] : -INFINITY;
           }
-          float mx = -INFINITY;
+          float m8[4];                                            // maxima of the four 8-column quarters
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, x[j]);
+          for (int q = 0; q < 4; ++q) {
+            m8[q] = x[8 * q];
+#pragma unroll
+            for (int j = 1; j < 8; ++j) m8[q] = fmaxf(m8[q], x[8 * q + j]);
+          }
+          const float mx = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
           if (p.epi_mode == 1) {
             if (row_ok) p.gmax[row * p.ld_gmax + (tile % p.n_blocks) * (BN / 32) + c] = mx;
           } else if (mx >= t0) {
+            // rare (about top_k hits per row in all of V): only the quarters that hold a hit are scanned
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (x[j] >= t0) {
-                if (npend == kPend) flush();
-                pend[npend++] = make_uint2((uint32_t)(col0 + j), __float_as_uint(x[j]));
+            for (int q = 0; q < 4; ++q) {
+              if (m8[q] >= t0) {
+#pragma unroll
+                for (int j = 8 * q; j < 8 * q + 8; ++j) {
+                  if (x[j] >= t0) {
+                    if (npend == kPend) flush();
+                    pend[npend++] = make_uint2((uint32_t)(col0 + j), __float_as_uint(x[j]));
+                  }
+                }
               }
             }
           }

@@ -337,6 +337,8 @@ __global__ void __launch_bounds__(kThrWarps * 32) vocab_threshold_kernel(const f
     }
     __syncwarp();
     if (n <= kThrCap) {
+      // exact top_k-th largest of the n compacted maxima by rank counting (independent iterations; an MSB-first radix
+      // select was measured slower here: its 32 rounds are serially dependent and n is only ~60)
       for (int c = lane; c < n; c += 32) {
         const float v = s_cand[w][c];
         int gt = 0, ge = 0;
@@ -746,8 +748,8 @@ extern "C" int dh_vocab_threshold(const float* gmax, long long ld_gmax, int rows
   DH_ARG(gmax && thresh && cand_count && rows >= 0 && n_groups > 0 && ld_gmax >= n_groups && top_k >= 1);
   if (rows == 0) return DH_OK;
   const int grid = dh_cdiv(rows, kThrWarps);
-  if (n_groups <= 32 * 40)
-    vocab_threshold_kernel<40><<<grid, kThrWarps * 32, 0, s>>>(gmax, ld_gmax, rows, n_groups, top_k, thresh, cand_count);
+  if (n_groups <= 32 * 36)
+    vocab_threshold_kernel<36><<<grid, kThrWarps * 32, 0, s>>>(gmax, ld_gmax, rows, n_groups, top_k, thresh, cand_count);
   else
     vocab_threshold_kernel<0><<<grid, kThrWarps * 32, 0, s>>>(gmax, ld_gmax, rows, n_groups, top_k, thresh, cand_count);
   DH_LAUNCH_OK();
