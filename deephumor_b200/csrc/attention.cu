@@ -29,10 +29,37 @@ struct AttnParams {
   float scale;
 };
 
+// 16-byte vector of T -> VEC floats
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float* out) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+  }
+};
+template <> struct Vec16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* out) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      out[2 * i] = __uint_as_float(w[i] << 16);
+      out[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+};
+
+// One warp per (query row, head).  Scores: the warp is split into groups of LPK = hd / VEC lanes; a group reads one
+// key's head row with 16-byte loads (a whole 128-byte row per group for hd = 64 bf16, fully coalesced) and reduces
+// its dot product with shuffles, 32 / LPK keys per iteration.  Output: lanes over pairs of head dims, one 4/8-byte
+// load per key (coalesced).  The physical K/V row of every key (beam slot indirection) is resolved once per key.
 template <typename T>
 __global__ void __launch_bounds__(kWarps * 32) attn_kernel(AttnParams p) {
-  __shared__ float s_q[kWarps][128];
+  constexpr int VEC = Vec16<T>::N;
   __shared__ float s_p[kWarps][kMaxKeys];
+  __shared__ long long s_base[kWarps][kMaxKeys];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int hd = p.D / p.n_heads;
   const long long item = (long long)blockIdx.x * kWarps + w;
@@ -40,43 +67,62 @@ __global__ void __launch_bounds__(kWarps * 32) attn_kernel(AttnParams p) {
   const int r = (int)(item / p.n_heads), h = (int)(item % p.n_heads);
   const int img = r / p.rpi, b = r % p.rpi;
   const int nk = p.causal_full ? (b + 1) : p.n_keys;
-  const T* q = (const T*)p.q + (long long)r * p.ldq + h * hd;
-  for (int d = lane; d < hd; d += 32) s_q[w][d] = dh_to_f<T>(q[d]);
-  __syncwarp();
   const T* Kb = (const T*)p.K;
   const T* Vb = (const T*)p.V;
-  auto kv_row = [&](int t) -> long long {
-    int slot = p.slot_shared ? 0 : (p.src ? p.src[((long long)img * p.rpi + b) * p.S_alloc + t] : b);
-    return (((long long)img * p.slots + slot) * p.S_alloc + t) * p.D + h * hd;
-  };
+  for (int t = lane; t < nk; t += 32) {
+    const int slot = p.slot_shared ? 0 : (p.src ? p.src[((long long)img * p.rpi + b) * p.S_alloc + t] : b);
+    s_base[w][t] = (((long long)img * p.slots + slot) * p.S_alloc + t) * p.D + h * hd;
+  }
+  __syncwarp();
+  const int lpk = hd / VEC;                    // lanes per key (power of two <= 32, checked on the host)
+  const int kpi = 32 / lpk;                    // keys per iteration
+  const int gl = lane % lpk, gk = lane / lpk;
+  float qv[VEC];
+  Vec16<T>::load((const T*)p.q + (long long)r * p.ldq + h * hd + gl * VEC, qv);
   const int* seq_row = p.seq ? p.seq + (long long)(p.seq_per_image ? img : r) * p.seq_ld : nullptr;
   float mx = -INFINITY;
-  for (int t = lane; t < nk; t += 32) {
-    const T* kr = Kb + kv_row(t);
+  for (int t0 = 0; t0 < nk; t0 += kpi) {
+    const int t = t0 + gk;
     float acc = 0.f;
-    for (int d = 0; d < hd; ++d) acc = fmaf(s_q[w][d], dh_to_f<T>(kr[d]), acc);
-    float e = acc / p.scale;
-    bool masked = false;
-    if (seq_row && t >= 1) masked = (seq_row[t - 1] == p.pad);
-    if (p.enc_mask) masked = p.enc_mask[(long long)img * p.S_alloc + t] != 0;
-    if (masked) e = -1e8f;
-    s_p[w][t] = e;
-    mx = fmaxf(mx, e);
+    if (t < nk) {
+      float kv[VEC];
+      Vec16<T>::load(Kb + s_base[w][t] + gl * VEC, kv);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc = fmaf(qv[i], kv[i], acc);
+    }
+    for (int o = lpk >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (t < nk && gl == 0) {
+      float e = acc / p.scale;
+      bool masked = false;
+      if (seq_row && t >= 1) masked = (seq_row[t - 1] == p.pad);
+      if (p.enc_mask) masked = p.enc_mask[(long long)img * p.S_alloc + t] != 0;
+      if (masked) e = -1e8f;
+      s_p[w][t] = e;
+    }
   }
+  __syncwarp();
+  for (int t = lane; t < nk; t += 32) mx = fmaxf(mx, s_p[w][t]);
   mx = dh_warp_max(mx);
   float sum = 0.f;
   for (int t = lane; t < nk; t += 32) {
-    float e = expf(s_p[w][t] - mx);
+    const float e = expf(s_p[w][t] - mx);
     s_p[w][t] = e;
     sum += e;
   }
   sum = dh_warp_sum(sum);
   __syncwarp();
+  const float inv = 1.f / sum;
   T* o = (T*)p.out + (long long)r * p.ldo + h * hd;
-  for (int d = lane; d < hd; d += 32) {
-    float acc = 0.f;
-    for (int t = 0; t < nk; ++t) acc = fmaf(s_p[w][t] / sum, dh_to_f<T>(Vb[kv_row(t) + d]), acc);
-    o[d] = dh_from_f<T>(acc);
+  for (int d = 2 * lane; d < hd; d += 64) {     // hd is even (multiple of VEC)
+    float a0 = 0.f, a1 = 0.f;
+    for (int t = 0; t < nk; ++t) {
+      const float pt = s_p[w][t];
+      const T* vr = Vb + s_base[w][t] + d;
+      a0 = fmaf(pt, dh_to_f<T>(vr[0]), a0);
+      a1 = fmaf(pt, dh_to_f<T>(vr[1]), a1);
+    }
+    o[d] = dh_from_f<T>(a0 * inv);
+    o[d + 1] = dh_from_f<T>(a1 * inv);
   }
 }
 
@@ -99,6 +145,11 @@ extern "C" int dh_attention(const void* q, long long ldq, const void* K, const v
                             int seq_per_image, int pad, const unsigned char* enc_mask, float scale, int dtype,
                             cudaStream_t s) {
   DH_ARG(q && K && V && out && rows >= 0 && n_heads > 0 && D % n_heads == 0 && D / n_heads <= 128);
+  {
+    const int vec = dtype == DH_F32 ? 4 : 8, hd = D / n_heads, lpk = hd / vec;
+    DH_ARG(hd % vec == 0 && lpk >= 1 && lpk <= 32 && (lpk & (lpk - 1)) == 0 && ldq % vec == 0);   // 16-byte head rows
+    DH_ARG(((uintptr_t)q % 16) == 0 && ((uintptr_t)K % 16) == 0 && ((uintptr_t)V % 16) == 0);
+  }
   DH_ARG(rows_per_image > 0 && slots > 0 && S_alloc > 0);
   DH_ARG((causal_full ? rows_per_image : n_keys) <= kMaxKeys && (causal_full || (n_keys > 0 && n_keys <= S_alloc)));
   if (rows == 0) return DH_OK;
