@@ -126,6 +126,77 @@ __global__ void __launch_bounds__(kWarps * 32) attn_kernel(AttnParams p) {
   }
 }
 
+// Cross-attention over keys shared by all rows of an image (the 49 spatial tokens, transformers.py:100-121 via :366):
+// one CTA per (image, head), one warp per row of the image.  The head slice of K and V ([n_keys, hd] each) is staged
+// in shared memory once and reused by the image's rpi beam rows -- rpi times less L2 traffic than one warp per
+// (row, head) fetching it alone.
+template <typename T>
+__global__ void __launch_bounds__(32 * 16) attn_shared_kv_kernel(AttnParams p) {
+  constexpr int VEC = Vec16<T>::N;
+  extern __shared__ __align__(16) unsigned char smem_attn[];
+  const int hd = p.D / p.n_heads, nk = p.n_keys;
+  T* sK = reinterpret_cast<T*>(smem_attn);
+  T* sV = sK + (size_t)nk * hd;
+  float* s_p = reinterpret_cast<float*>(sV + (size_t)nk * hd);     // [rpi][nk]
+  const int img = blockIdx.x / p.n_heads, h = blockIdx.x % p.n_heads;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long kv0 = ((long long)img * p.slots * p.S_alloc) * p.D + h * hd;      // slot 0, key 0
+  const int cpr = hd / VEC;                                                        // 16-byte chunks per key row
+  for (int i = threadIdx.x; i < nk * cpr; i += blockDim.x) {
+    const int t = i / cpr, c = i - t * cpr;
+    *reinterpret_cast<uint4*>(sK + t * hd + c * VEC) = *reinterpret_cast<const uint4*>((const T*)p.K + kv0 + (long long)t * p.D + c * VEC);
+    *reinterpret_cast<uint4*>(sV + t * hd + c * VEC) = *reinterpret_cast<const uint4*>((const T*)p.V + kv0 + (long long)t * p.D + c * VEC);
+  }
+  __syncthreads();
+  const int r = img * p.rpi + w;
+  if (w >= p.rpi || r >= p.R) return;
+  float* sp = s_p + w * nk;
+  const int lpk = cpr, kpi = 32 / lpk;
+  const int gl = lane % lpk, gk = lane / lpk;
+  float qv[VEC];
+  Vec16<T>::load((const T*)p.q + (long long)r * p.ldq + h * hd + gl * VEC, qv);
+  for (int t0 = 0; t0 < nk; t0 += kpi) {
+    const int t = t0 + gk;
+    float acc = 0.f;
+    if (t < nk) {
+      float kv[VEC];
+      Vec16<T>::load(sK + t * hd + gl * VEC, kv);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc = fmaf(qv[i], kv[i], acc);
+    }
+    for (int o = lpk >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (t < nk && gl == 0) {
+      float e = acc / p.scale;
+      if (p.enc_mask && p.enc_mask[(long long)img * p.S_alloc + t] != 0) e = -1e8f;
+      sp[t] = e;
+    }
+  }
+  __syncwarp();
+  float mx = -INFINITY;
+  for (int t = lane; t < nk; t += 32) mx = fmaxf(mx, sp[t]);
+  mx = dh_warp_max(mx);
+  float sum = 0.f;
+  for (int t = lane; t < nk; t += 32) {
+    const float e = expf(sp[t] - mx);
+    sp[t] = e;
+    sum += e;
+  }
+  sum = dh_warp_sum(sum);
+  __syncwarp();
+  const float inv = 1.f / sum;
+  T* o = (T*)p.out + (long long)r * p.ldo + h * hd;
+  for (int d = 2 * lane; d < hd; d += 64) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int t = 0; t < nk; ++t) {
+      const float pt = sp[t];
+      a0 = fmaf(pt, dh_to_f<T>(sV[t * hd + d]), a0);
+      a1 = fmaf(pt, dh_to_f<T>(sV[t * hd + d + 1]), a1);
+    }
+    o[d] = dh_from_f<T>(a0 * inv);
+    o[d + 1] = dh_from_f<T>(a1 * inv);
+  }
+}
+
 // enc_mask[n, t] = any(spatial[n, t, :] == 0)   (transformers.py:480-481, Q16)
 template <typename T>
 __global__ void enc_mask_kernel(const T* __restrict__ x, unsigned char* __restrict__ mask, int rows, int D) {
@@ -155,6 +226,18 @@ extern "C" int dh_attention(const void* q, long long ldq, const void* K, const v
   if (rows == 0) return DH_OK;
   AttnParams p{q, ldq, K, V, out, ldo, rows, D, n_heads, rows_per_image, slots, S_alloc, src, slot_shared,
                n_keys, causal_full, seq, seq_ld, seq_per_image, pad, enc_mask, scale};
+  // keys shared by the rows of an image (cross-attention during generation): stage K/V once per (image, head)
+  const int esize = dtype == DH_F32 ? 4 : 2;
+  const size_t shared_smem = (size_t)2 * n_keys * (D / n_heads) * esize + (size_t)rows_per_image * n_keys * 4;
+  if (slot_shared && !causal_full && !seq && rows_per_image >= 2 && rows_per_image <= 16 && rows % rows_per_image == 0 &&
+      shared_smem <= 48 * 1024) {
+    const int g = (rows / rows_per_image) * n_heads;
+    if (dtype == DH_F32) attn_shared_kv_kernel<float><<<g, 32 * rows_per_image, shared_smem, s>>>(p);
+    else if (dtype == DH_BF16) attn_shared_kv_kernel<__nv_bfloat16><<<g, 32 * rows_per_image, shared_smem, s>>>(p);
+    else return dh_fail(DH_ERR_ARG, "dtype", __FILE__, __LINE__);
+    DH_LAUNCH_OK();
+    return DH_OK;
+  }
   int grid = dh_cdiv((long long)rows * n_heads, kWarps);
   if (dtype == DH_F32) attn_kernel<float><<<grid, kWarps * 32, 0, s>>>(p);
   else if (dtype == DH_BF16) attn_kernel<__nv_bfloat16><<<grid, kWarps * 32, 0, s>>>(p);
