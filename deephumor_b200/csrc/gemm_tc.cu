@@ -42,7 +42,9 @@ struct TcParams {
   int* error;                             // device flag set before a watchdog trap
   // Vocab-projection epilogues that keep the logits out of HBM (dh_vocab_groupmax / dh_vocab_candidates):
   int n_stride;                           // N blocks visited: 0, n_stride, 2 n_stride, ... (1 except for sampled group maxima)
-  int epi_mode;                           // 0: store C; 1: maxima of 32-column groups; 2: compact logits >= thresh[row]
+  int epi_mode;                           // 0: store C; 1: maxima of 32-column groups; 2: compact logits >= thresh[row];
+                                          // 3: LSTM cell; 4: per-group (max, sum exp) + target logit (log-softmax)
+  float* gsum; const long long* targets; float* tlogit;     // mode 4: [M, ld_gmax], [M] (int64), [M]
   float* gmax; long long ld_gmax;         // [M, ld_gmax] group maxima (mode 1)
   const float* thresh;                    // [M] lower bound of the row's top_k-th largest logit (mode 2)
   int* cand_count; int* cand_idx; float* cand_val; int cand_cap;   // [M], [M, cap], [M, cap]
@@ -472,6 +474,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const bool row_ok = row < p.M;
         // issued before the wait on the accumulator so that its L2 round trip is hidden
         const float thr = (p.epi_mode == 2 && row_ok) ? __ldg(p.thresh + row) : INFINITY;
+        const int tcol = (p.epi_mode == 4 && row_ok) ? (int)__ldg(p.targets + row) : -1;
         mbar_wait(tfull_bar(as), (it >> 1) & 1, p.error, 4);
         tc_fence_after();
         const uint32_t tmem_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
@@ -499,7 +502,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int c = eh * (BN / 64); c < (eh + 1) * (BN / 64); ++c) {
           const int col0 = n0 + c * 32;
           if (col0 >= p.N) {                                      // warp-uniform: group past the end of the row
-            if (p.epi_mode == 1 && row_ok) p.gmax[row * p.ld_gmax + (tile % p.n_blocks) * (BN / 32) + c] = -INFINITY;
+            if (p.epi_mode != 2 && row_ok) p.gmax[row * p.ld_gmax + (tile % p.n_blocks) * (BN / 32) + c] = -INFINITY;
+            if (p.epi_mode == 4 && row_ok) p.gsum[row * p.ld_gmax + (tile % p.n_blocks) * (BN / 32) + c] = 0.f;
             continue;
           }
           uint32_t v[32];
@@ -529,6 +533,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const float mx = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
           if (p.epi_mode == 1) {
             if (row_ok) p.gmax[row * p.ld_gmax + (tile % p.n_blocks) * (BN / 32) + c] = mx;
+          } else if (p.epi_mode == 4) {
+            // log-softmax pieces of this group (experiments/metrics.py:5): max, sum of exp(x - max), and the target's logit
+            float se = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) se += __expf(x[j] - mx);          // padding columns hold -inf -> 0
+            if (row_ok) {
+              const long long g = row * p.ld_gmax + (tile % p.n_blocks) * (BN / 32) + c;
+              p.gmax[g] = mx;
+              p.gsum[g] = se;
+              const int tj = tcol - col0;
+              if (tj >= 0 && tj < 32) {
+                float tl = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) tl = (j == tj) ? x[j] : tl;
+                p.tlogit[row] = tl;
+              }
+            }
           } else if (mx >= t0) {
             // rare (about top_k hits per row in all of V): only the quarters that hold a hit are scanned
 #pragma unroll
@@ -984,6 +1005,40 @@ extern "C" int dh_lstm_layer_tc(const void* A, long long lda, const void* Wp, lo
   rc = make_map_2d(&ma, A, rows, K, lda, BM, ab_dtype);
   if (rc) return rc;
   return dispatch(ma, Wp, ldw, p, 256, stream);
+}
+
+// log_softmax(A W^T + bias)[row, targets[row]] without storing the logits (experiments/metrics.py:5 on the classifier
+// output of rnn_models.py:44 / transformers.py:488,736): the contraction's epilogue keeps (max, sum exp) per 32-column
+// group and the target's logit; dh_vocab_logprob_reduce (select.cu) folds the groups of a row.
+int dh_vocab_logprob_reduce(const float* gmax, const float* gsum, long long ld, int rows, int n_groups, const float* tlogit,
+                            float* out, cudaStream_t s);
+extern "C" int dh_vocab_logprob(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias,
+                                int M, int N, int K, const long long* targets, float* gmax, float* gsum, long long ld_g,
+                                float* tlogit, float* out, cudaStream_t stream) {
+  DH_ARG(A && W && targets && gmax && gsum && tlogit && out && M >= 0 && N > 0 && K > 0);
+  DH_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0);
+  DH_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0);
+  DH_ARG(ab_dtype == DH_BF16 || ab_dtype == DH_F16);
+  const int bn = N <= 64 ? 64 : N <= 128 ? 128 : 256;
+  const int n_groups = dh_cdiv(N, bn) * (bn / 32);
+  DH_ARG(ld_g >= n_groups);
+  if (M == 0) return DH_OK;
+  int rc = tc_init();
+  if (rc) return rc;
+  TcParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.k_chunks = dh_cdiv(K, BK);
+  p.ab_dtype = ab_dtype;
+  p.bias = bias;
+  p.epi_mode = 4;
+  p.n_stride = 1;
+  p.gmax = gmax; p.gsum = gsum; p.ld_gmax = ld_g; p.targets = targets; p.tlogit = tlogit;
+  CUtensorMap ma;
+  rc = make_map_2d(&ma, A, M, K, lda, BM, ab_dtype);
+  if (rc) return rc;
+  rc = dispatch(ma, W, ldw, p, bn, stream);
+  if (rc) return rc;
+  return dh_vocab_logprob_reduce(gmax, gsum, ld_g, M, n_groups, tlogit, out, stream);
 }
 
 extern "C" int dh_vocab_groupmax(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias,

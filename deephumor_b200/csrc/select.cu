@@ -857,3 +857,34 @@ extern "C" int dh_select_beam_step(const int* cand_count, const int* cand_idx, c
   return launch_select_beam(p, cand_count, cand_idx, cand_val, cand_cap, n_img, 1, to_state(st), sp,
                             (size_t)beam * st->seq_ld * sizeof(int), s);
 }
+
+// out[row] = tlogit[row] - logsumexp(row) from the per-group (max, sum exp) pairs written by the contraction's epilogue.
+namespace {
+__global__ void __launch_bounds__(256) vocab_logprob_reduce_kernel(const float* __restrict__ gmax, const float* __restrict__ gsum,
+                                                                  long long ld, int rows, int n_groups,
+                                                                  const float* __restrict__ tlogit, float* __restrict__ out) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + w;
+  if (r >= rows) return;
+  const float* m = gmax + (long long)r * ld;
+  const float* sg = gsum + (long long)r * ld;
+  float mx = -INFINITY;
+  for (int i = lane; i < n_groups; i += 32) mx = fmaxf(mx, __ldg(m + i));
+  mx = dh_warp_max(mx);
+  float sum = 0.f;
+  for (int i = lane; i < n_groups; i += 32) {
+    const float mi = __ldg(m + i);
+    if (mi > -INFINITY) sum += __ldg(sg + i) * expf(mi - mx);
+  }
+  sum = dh_warp_sum(sum);
+  if (lane == 0) out[r] = tlogit[r] - mx - logf(sum);
+}
+}  // namespace
+
+int dh_vocab_logprob_reduce(const float* gmax, const float* gsum, long long ld, int rows, int n_groups, const float* tlogit,
+                            float* out, cudaStream_t s) {
+  if (rows == 0) return DH_OK;
+  vocab_logprob_reduce_kernel<<<dh_cdiv(rows, 8), 256, 0, s>>>(gmax, gsum, ld, rows, n_groups, tlogit, out);
+  DH_LAUNCH_OK();
+  return DH_OK;
+}

@@ -27,6 +27,18 @@ class _Captioner(RTModule):
         model.load_state_dict(ckpt['model'])
         return model
 
+    def perplexity(self, images, captions, lengths, labels=None, pad_index=0):
+        """`perplexity(self(images, captions[:, :-1], lengths[, labels])[:, :T], captions, lengths)` of the reference's
+        evaluation loop (experiments/trainer.py:66-81, experiments/metrics.py:4-9) with the log-softmax and target gather
+        fused into the classifier contraction: the [bs, T, V] logits (9.6 GB for config 3) are never materialised."""
+        enc = self.encoder(images, labels) if labels is not None else self.encoder(images)
+        lp = self._token_logprob(enc, captions[:, :-1], lengths, captions)
+        T = lp.shape[1]
+        tg = captions[:, :T].to(lp.device)
+        lp = lp / lengths.to(lp.device).unsqueeze(1)           # divide by lengths BEFORE masking (Q27)
+        lp = lp.masked_fill(tg == pad_index, 0.)
+        return (-lp.sum(dim=-1)).exp().mean()
+
     def _gen_kwargs(self, max_len, temperature, beam_size, top_k, eos_index, noise, seed, image_base):
         return dict(max_len=max_len, temperature=temperature, beam_size=beam_size, top_k=top_k, eos_index=eos_index,
                     noise=noise, seed=seed, image_base=image_base)
@@ -43,6 +55,9 @@ class CaptioningLSTM(_Captioner):
 
     def forward(self, images, captions, lengths=None):
         return self.decoder(self.encoder(images), captions, lengths)
+
+    def _token_logprob(self, enc, captions_in, lengths, targets):
+        return self.decoder.token_logprob(enc, captions_in, lengths, targets)
 
     def generate(self, image, caption=None, max_len=25, temperature=1.0, beam_size=10, top_k=50, eos_index=3,
                  *, noise=None, seed=None, image_base=0):
@@ -68,6 +83,9 @@ class CaptioningLSTMWithLabels(_Captioner):
 
     def forward(self, images, captions, lengths, labels):
         return self.decoder(self.encoder(images=images, labels=labels), captions, lengths)
+
+    def _token_logprob(self, enc, captions_in, lengths, targets):
+        return self.decoder.token_logprob(enc, captions_in, lengths, targets)
 
     def generate(self, image, label, caption=None, max_len=25, temperature=1.0, beam_size=10, top_k=50, eos_index=3,
                  *, noise=None, seed=None, image_base=0):
@@ -96,6 +114,9 @@ class CaptioningTransformerBase(_Captioner):
     def forward(self, images, captions, lengths=None):
         return self.decoder(captions, start_emb=self.encoder(images))
 
+    def _token_logprob(self, enc, captions_in, lengths, targets):
+        return self.decoder.token_logprob(captions_in, None, enc, targets)
+
     def generate(self, image, caption=None, max_len=25, temperature=1.0, beam_size=10, top_k=50, eos_index=3,
                  *, noise=None, seed=None, image_base=0):
         return self.decoder.generate(self.encoder(image), caption=caption,
@@ -121,6 +142,9 @@ class CaptioningTransformer(_Captioner):
     def forward(self, images, captions, lengths=None):
         image_emb, image_spatial_emb = self.encoder(images)
         return self.decoder(captions, enc_out=image_spatial_emb, start_emb=image_emb)
+
+    def _token_logprob(self, enc, captions_in, lengths, targets):
+        return self.decoder.token_logprob(captions_in, enc[1], enc[0], targets)
 
     def generate(self, image, caption=None, max_len=25, temperature=1.0, beam_size=10, top_k=50, eos_index=3,
                  *, noise=None, seed=None, image_base=0):

@@ -22,6 +22,10 @@ class LSTMDecoder(RTModule):
         dev = self._device()
         return self._rt().forward(image_emb.to(dev, torch.float32).contiguous(), captions.to(dev), lengths)
 
+    def token_logprob(self, image_emb, captions, lengths, targets):
+        dev = self._device()
+        return self._rt().token_logprob(image_emb.to(dev, torch.float32).contiguous(), captions.to(dev), lengths, targets)
+
     def generate(self, image_emb, caption=None, max_len=25, temperature=1.0, beam_size=10, top_k=50, eos_index=3,
                  *, noise=None, seed=None, image_base=0, unk_index=1):
         """image_emb [N,1,E] or [N,E] (reference: [1,1,E]); returns the reference's 1-D ids for N == 1, else

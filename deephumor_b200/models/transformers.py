@@ -78,6 +78,11 @@ class _DecoderBase(RTModule):
         assert enc_out.shape[1] == 49, 'cross-attention runtime expects the 7x7 = 49 spatial tokens'
         return enc_out.to(dev).reshape(n * 49, -1).to(rt.dtype).contiguous()
 
+    def token_logprob(self, x, enc_out, start_emb, targets):
+        dev = self._device()
+        sp = self._spatial(enc_out, dev) if self._cross else None
+        return self._rt().token_logprob(start_emb.to(dev, torch.float32).contiguous(), sp, x.to(dev), targets)
+
     def _generate(self, start_emb, enc_out, caption, max_len, temperature, beam_size, top_k, eos_index, noise, seed,
                   image_base, unk_index):
         assert beam_size <= top_k, '`beam_size` should be less than `top_k`'

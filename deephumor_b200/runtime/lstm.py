@@ -180,8 +180,9 @@ class LSTMDecoderRT:
         sampled = pl['vsel'] is not None and pl['vsel'].stride > 1
         return pl['ids'].clone(), pl['lens'].clone(), pl['beam'].status.clone(), sampled
 
-    def forward(self, image_emb, captions, lengths=None):
-        """Teacher-forced logits [N, max(lengths), V] fp32 (rnn_models.py:28-46; packed-sequence semantics, Q24)."""
+    def hidden(self, image_emb, captions, lengths=None):
+        """Teacher-forced top-layer outputs [N, max(lengths), H], zero at t >= length (rnn_models.py:28-44;
+        packed-sequence semantics, Q24)."""
         N, T = captions.shape
         dev, H = self.device, self.H
         S = T + 1
@@ -189,7 +190,7 @@ class LSTMDecoderRT:
             lengths = torch.full((N,), S, dtype=torch.int64, device=dev)
         lengths = lengths.to(dev)
         tmax = int(lengths.max())
-        ws = self._alloc(N)
+        ws = self._alloc(N, logits=False)
         tops = torch.zeros(N, tmax, H, dtype=self.dtype, device=dev)
         cap32 = captions.to(device=dev, dtype=torch.int32)
         cur = 0
@@ -207,7 +208,30 @@ class LSTMDecoderRT:
             cur = 1 - cur
         # pad_packed_sequence zero-fills outputs at t >= length before the classifier (rnn_models.py:41-44)
         keep = (torch.arange(tmax, device=dev).unsqueeze(0) < lengths.unsqueeze(1)).unsqueeze(-1)
-        tops = tops * keep.to(tops.dtype)
-        logits = torch.empty(N, tmax, self.V, dtype=torch.float32, device=dev)
-        ops.gemm(tops.view(N * tmax, H), self.Wc, logits.view(N * tmax, self.V), bias=self.bc)
+        return tops * keep.to(tops.dtype), tmax
+
+    def forward(self, image_emb, captions, lengths=None):
+        """Teacher-forced logits [N, max(lengths), V] fp32."""
+        N = captions.shape[0]
+        tops, tmax = self.hidden(image_emb, captions, lengths)
+        logits = torch.empty(N, tmax, self.V, dtype=torch.float32, device=self.device)
+        ops.gemm(tops.view(N * tmax, self.H), self.Wc, logits.view(N * tmax, self.V), bias=self.bc)
         return logits
+
+    def token_logprob(self, image_emb, captions, lengths, targets):
+        """log_softmax(classifier(lstm(...)))[n, t, targets[n, t]] for t < min(max(lengths), targets width) -> [N, T]
+        (experiments/metrics.py:5 fused into the classifier contraction in tensor-core mode)."""
+        N = captions.shape[0]
+        tops, tmax = self.hidden(image_emb, captions, lengths)
+        T = min(tmax, targets.shape[1])
+        tg = torch.zeros(N, tmax, dtype=torch.int64, device=self.device)
+        tg[:, :T] = targets[:, :T].to(self.device)
+        lp = torch.empty(N * tmax, dtype=torch.float32, device=self.device)
+        x = tops.view(N * tmax, self.H)
+        if x.dtype == torch.float32:
+            logits = torch.empty(N * tmax, self.V, dtype=torch.float32, device=self.device)
+            ops.gemm(x, self.Wc, logits, bias=self.bc)
+            ops.token_logprob(logits, tg.view(-1), lp)
+        else:
+            ops.vocab_logprob(x, self.Wc, self.bc, tg.view(-1), lp)
+        return lp.view(N, tmax)[:, :T]

@@ -349,6 +349,21 @@ class Beam:
                  image_base, final_step, len_if_running, pad, max_len, ptr(out_ids), ptr(out_len), ptr(dyn), stream())
 
 
+def vocab_logprob(A, W, bias, targets, out):
+    """out[m] = log_softmax(A W^T + bias)[m, targets[m]] on tensor cores, logits never stored (dh_vocab_logprob)."""
+    rows, K = A.shape
+    V = W.shape[0]
+    assert W.shape[1] == K and W.dtype == A.dtype and targets.dtype == torch.int64 and targets.is_contiguous()
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == rows
+    bn = 64 if V <= 64 else 128 if V <= 128 else 256
+    n_groups = (V + bn - 1) // bn * (bn // 32)
+    gmax = torch.empty(rows, n_groups, dtype=torch.float32, device=A.device)
+    gsum = torch.empty_like(gmax)
+    tl = torch.empty(rows, dtype=torch.float32, device=A.device)
+    LIB.call('dh_vocab_logprob', ptr(A), _rows(A), ptr(W), _rows(W), code(A), ptr(bias), rows, V, K, ptr(targets),
+             ptr(gmax), ptr(gsum), n_groups, ptr(tl), ptr(out), stream())
+
+
 def token_logprob(logits, targets, out):
     rows, V = logits.shape
     assert logits.dtype == torch.float32 and targets.dtype == torch.int64

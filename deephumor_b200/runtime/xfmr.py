@@ -219,6 +219,23 @@ class XfmrDecoderRT:
             self._ffn(lay, x, h1, tmp, rows)
         return x, S
 
+    def token_logprob(self, start_emb, spatial, captions, targets):
+        """log_softmax(decoder(captions))[n, t, targets[n, t]] for t < T = targets.shape[1] -> [N, T] fp32
+        (experiments/metrics.py:5 fused into the classifier contraction; logits [N,S,V] are never materialised)."""
+        N, T = targets.shape
+        x, S = self.hidden(start_emb, spatial, captions)
+        assert T <= S
+        tg = torch.full((N, S), self.pad, dtype=torch.int64, device=self.device)
+        tg[:, :T] = targets.to(self.device)
+        lp = torch.empty(N * S, dtype=torch.float32, device=self.device)
+        if x.dtype == torch.float32:
+            logits = torch.empty(N * S, self.V, dtype=torch.float32, device=self.device)
+            ops.gemm(x, self.Wc, logits, bias=self.bc)
+            ops.token_logprob(logits, tg.view(-1), lp)
+        else:
+            ops.vocab_logprob(x, self.Wc, self.bc, tg.view(-1), lp)
+        return lp.view(N, S)[:, :T]
+
     def forward(self, start_emb, spatial, captions):
         N = captions.shape[0]
         x, S = self.hidden(start_emb, spatial, captions)

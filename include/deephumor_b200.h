@@ -24,7 +24,7 @@ extern "C" {
 typedef struct CUstream_st* cudaStream_t;
 #endif
 
-#define DH_VERSION 109
+#define DH_VERSION 110
 
 #define DH_OK 0
 #define DH_ERR_ARG (-1)
@@ -202,6 +202,13 @@ int dh_beam_step(const dh_beam_state* st, const int* new_ind, const float* new_v
 int dh_beam_final(const dh_beam_state* st, int n_img, int beam, float temperature, int noise_mode,
                   unsigned long long seed, long long image_base, int final_step, int len_if_running, int pad, int max_len,
                   long long* out_ids, long long* out_len, const long long* dyn, cudaStream_t stream);
+/* out[m] = log_softmax(A[M,K] W[N,K]^T + bias)[m, targets[m]] with the logits kept on chip (experiments/metrics.py:5 on
+ * the classifier of rnn_models.py:44 / transformers.py:488,736): tcgen05 contraction whose epilogue keeps (max, sum exp)
+ * per 32-column group (gmax / gsum [M, ld_g], ld_g >= ceil(N/256)*8 for N > 128) and the target's logit (tlogit [M]),
+ * then a per-row fold.  A / W ab_dtype (DH_BF16 / DH_F16). */
+int dh_vocab_logprob(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias, int M,
+                     int N, int K, const long long* targets, float* gmax, float* gsum, long long ld_g, float* tlogit,
+                     float* out, cudaStream_t stream);
 /* log_softmax(logits)[target] per row (experiments/metrics.py:5). */
 int dh_token_logprob(const float* logits, long long ld, int rows, int V, const long long* targets, float* out,
                      cudaStream_t stream);

@@ -199,3 +199,21 @@ def test_sampled_pass1_overflow_falls_back_to_exhaustive_pass(monkeypatch):
     (i0, l0), (i1, l1) = res
     assert torch.equal(i0, i1) and torch.equal(l0, l1)
     assert int(i0[:, 0].min()) >= 256 and int(i0[:, 0].max()) < 256 * 12       # the boosted columns win
+
+
+@pytest.mark.parametrize('precision', ['bf16', 'fp32'])
+@pytest.mark.parametrize('tag', ['small', 'canon'])
+@pytest.mark.parametrize('kind', H.KINDS)
+def test_fused_perplexity_matches_materialised_logits(kind, tag, precision):
+    """model.perplexity (log-softmax + target gather in the classifier contraction's epilogue, logits never stored)
+    equals perplexity(model(...)) on the same device path, and the reference fixture within the mode's tolerance."""
+    fx = H.load_fixture(tag, kind)
+    m, sd, imgs, labs, caps, lens = build(fx, precision)
+    with torch.no_grad():
+        args = (imgs.cuda(), caps[:, :-1].cuda(), lens.cuda()) + ((labs.cuda(),) if kind == 'lstm_labels' else ())
+        logits = m(*args)
+        T = min(logits.shape[1], caps.shape[1])
+        pp0 = float(perplexity(logits[:, :T], caps[:, :T].cuda(), lens.cuda()))
+        pp1 = float(m.perplexity(imgs.cuda(), caps.cuda(), lens.cuda(), labs.cuda() if kind == 'lstm_labels' else None))
+    assert abs(pp1 - pp0) / pp0 < 2e-4
+    assert abs(pp1 - fx['perplexity']) / fx['perplexity'] < (1e-3 if precision == 'fp32' else 5e-2)
