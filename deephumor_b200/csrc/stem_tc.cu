@@ -93,11 +93,33 @@ template <> struct Pack2<__nv_bfloat16> {
   static __device__ __forceinline__ uint32_t f(float a, float b) { __nv_bfloat162 t = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&t); }
 };
 
-// images [n,3,224,224] fp32; wp [64][192] T (k = r*22 + s*3 + c, zero elsewhere); bias [64]; out [n,56,56,64] T.
-template <typename T>
+// Per-channel input normalisation of the uint8 path: (x / 255 - mean) / std, the exact fp32 operations of torchvision's
+// ToTensor + Normalize (deephumor_demo.ipynb cell 11), so a uint8 batch gives bit-identical features to the float one.
+struct PixelNorm { float mean[3], std[3]; };
+
+template <typename TIN> struct BandLoad;
+template <> struct BandLoad<float> {
+  using Vec = float4;
+  static __device__ __forceinline__ Vec zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  static __device__ __forceinline__ void unpack(const Vec& v, int, const PixelNorm&, float* o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+};
+template <> struct BandLoad<unsigned char> {
+  using Vec = uchar4;
+  static __device__ __forceinline__ Vec zero() { return make_uchar4(0, 0, 0, 0); }
+  static __device__ __forceinline__ void unpack(const Vec& v, int c, const PixelNorm& nm, float* o) {
+    o[0] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v.x, 255.f), nm.mean[c]), nm.std[c]);
+    o[1] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v.y, 255.f), nm.mean[c]), nm.std[c]);
+    o[2] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v.z, 255.f), nm.mean[c]), nm.std[c]);
+    o[3] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v.w, 255.f), nm.mean[c]), nm.std[c]);
+  }
+};
+
+// images [n,3,224,224] fp32 (or uint8 + PixelNorm); wp [64][192] T (k = r*22 + s*3 + c, zero elsewhere); bias [64];
+// out [n,56,56,64] T.
+template <typename T, typename TIN>
 __global__ void __launch_bounds__(kThreads, 1)
-stem_pool_kernel(const float* __restrict__ images, const T* __restrict__ wp, const float* __restrict__ bias,
-                 T* __restrict__ out, int n_img) {
+stem_pool_kernel(const TIN* __restrict__ images, const T* __restrict__ wp, const float* __restrict__ bias,
+                 T* __restrict__ out, int n_img, const PixelNorm nm) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -157,18 +179,20 @@ stem_pool_kernel(const float* __restrict__ images, const T* __restrict__ wp, con
     const int img = item / 28, py0 = (item - img * 28) * 2;
     // ---- input band: rows 4*py0-5 .. 4*py0+9, fp32 NCHW -> T [row][5 + col][rgb]   (previous item's MMAs are all
     //      complete: its last accumulator group was drained before this point, so the band may be overwritten)
-    const float* src = images + (long long)img * 3 * 224 * 224;
+    const TIN* src = images + (long long)img * 3 * 224 * 224;
+    using BV = typename BandLoad<TIN>::Vec;
     // all of a thread's loads are issued before the first conversion / store: one memory round trip per item, not ten
     constexpr int kBandVec = 3 * kBandRows * 56, kBandIter = (kBandVec + kThreads - 1) / kThreads;
-    float4 bv[kBandIter];
+    BV bv[kBandIter];
+    bool bz[kBandIter];                         // rows outside the image are zero AFTER normalisation (conv padding)
 #pragma unroll
     for (int u = 0; u < kBandIter; ++u) {
       const int i = tid + u * kThreads;
       const int c4 = i % 56, rr = (i / 56) % kBandRows, c = i / (56 * kBandRows);
       const int gr = 4 * py0 - 5 + rr;
-      bv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i < kBandVec && gr >= 0 && gr < 224)
-        bv[u] = __ldg(reinterpret_cast<const float4*>(src + ((long long)c * 224 + gr) * 224) + c4);
+      bv[u] = BandLoad<TIN>::zero();
+      bz[u] = !(i < kBandVec && gr >= 0 && gr < 224);
+      if (!bz[u]) bv[u] = __ldg(reinterpret_cast<const BV*>(src + ((long long)c * 224 + gr) * 224) + c4);
     }
 #pragma unroll
     for (int u = 0; u < kBandIter; ++u) {
@@ -176,7 +200,9 @@ stem_pool_kernel(const float* __restrict__ images, const T* __restrict__ wp, con
       if (i < kBandVec) {
         const int c4 = i % 56, rr = (i / 56) % kBandRows, c = i / (56 * kBandRows);
         T* d = band + rr * kPitch + (5 + 4 * c4) * 3 + c;
-        d[0] = dh_from_f<T>(bv[u].x); d[3] = dh_from_f<T>(bv[u].y); d[6] = dh_from_f<T>(bv[u].z); d[9] = dh_from_f<T>(bv[u].w);
+        float px[4] = {0.f, 0.f, 0.f, 0.f};
+        if (!bz[u]) BandLoad<TIN>::unpack(bv[u], c, nm, px);
+        d[0] = dh_from_f<T>(px[0]); d[3] = dh_from_f<T>(px[1]); d[6] = dh_from_f<T>(px[2]); d[9] = dh_from_f<T>(px[3]);
       }
     }
     __syncthreads();
@@ -290,6 +316,29 @@ int g_sms = 0;
 
 }  // namespace
 
+template <typename TIN>
+static int stem_launch(const TIN* images, const void* w_packed, const float* bias, void* out, int n, int dtype,
+                       const PixelNorm& nm, cudaStream_t stream) {
+  static bool attr = false;
+  if (!attr) {
+    int dev = 0;
+    DH_CUDA(cudaGetDevice(&dev));
+    DH_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+    DH_CUDA(cudaFuncSetAttribute(stem_pool_kernel<__half, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    DH_CUDA(cudaFuncSetAttribute(stem_pool_kernel<__nv_bfloat16, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr = true;
+  }
+  const int items = n * 28;
+  const int grid = items < g_sms ? items : g_sms;
+  if (dtype == DH_F16)
+    stem_pool_kernel<__half, TIN><<<grid, kThreads, kSmemBytes, stream>>>(images, (const __half*)w_packed, bias, (__half*)out, n, nm);
+  else
+    stem_pool_kernel<__nv_bfloat16, TIN><<<grid, kThreads, kSmemBytes, stream>>>(images, (const __nv_bfloat16*)w_packed, bias,
+                                                                                (__nv_bfloat16*)out, n, nm);
+  DH_LAUNCH_OK();
+  return DH_OK;
+}
+
 // images [n,3,224,224] fp32 NCHW; w_packed [64][192] (k = r*22 + s*3 + c, BN folded, zeros elsewhere) and out
 // [n,56,56,64] NHWC of dtype (DH_F16 / DH_BF16); bias fp32 [64].
 extern "C" int dh_stem_pool_tc(const float* images_nchw, const void* w_packed, const float* bias, void* out, int n, int H,
@@ -299,20 +348,20 @@ extern "C" int dh_stem_pool_tc(const float* images_nchw, const void* w_packed, c
   DH_ARG(dtype == DH_F16 || dtype == DH_BF16);
   DH_ARG(((uintptr_t)images_nchw % 16) == 0 && ((uintptr_t)w_packed % 16) == 0 && ((uintptr_t)out % 16) == 0);
   if (n == 0) return DH_OK;
-  if (!g_sms) {
-    int dev = 0;
-    DH_CUDA(cudaGetDevice(&dev));
-    DH_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
-    DH_CUDA(cudaFuncSetAttribute(stem_pool_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    DH_CUDA(cudaFuncSetAttribute(stem_pool_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-  }
-  const int items = n * 28;
-  const int grid = items < g_sms ? items : g_sms;
-  if (dtype == DH_F16)
-    stem_pool_kernel<__half><<<grid, kThreads, kSmemBytes, stream>>>(images_nchw, (const __half*)w_packed, bias, (__half*)out, n);
-  else
-    stem_pool_kernel<__nv_bfloat16><<<grid, kThreads, kSmemBytes, stream>>>(images_nchw, (const __nv_bfloat16*)w_packed, bias,
-                                                                            (__nv_bfloat16*)out, n);
-  DH_LAUNCH_OK();
-  return DH_OK;
+  return stem_launch<float>(images_nchw, w_packed, bias, out, n, dtype, PixelNorm{}, stream);
+}
+
+// Same from raw uint8 pixels [n,3,224,224] (NCHW, 0..255): (x / 255 - mean[c]) / std[c] is applied while the input band
+// is staged (torchvision ToTensor + Normalize, deephumor_demo.ipynb cell 11).
+extern "C" int dh_stem_pool_tc_u8(const unsigned char* images_nchw_u8, const float* mean3_host, const float* std3_host,
+                                  const void* w_packed, const float* bias, void* out, int n, int H, int W, int dtype,
+                                  cudaStream_t stream) {
+  DH_ARG(images_nchw_u8 && mean3_host && std3_host && w_packed && bias && out && n >= 0);
+  DH_ARG(H == 224 && W == 224);
+  DH_ARG(dtype == DH_F16 || dtype == DH_BF16);
+  DH_ARG(((uintptr_t)images_nchw_u8 % 4) == 0 && ((uintptr_t)w_packed % 16) == 0 && ((uintptr_t)out % 16) == 0);
+  if (n == 0) return DH_OK;
+  PixelNorm nm;
+  for (int c = 0; c < 3; ++c) { nm.mean[c] = mean3_host[c]; nm.std[c] = std3_host[c]; DH_ARG(std3_host[c] != 0.f); }
+  return stem_launch<unsigned char>(images_nchw_u8, w_packed, bias, out, n, dtype, nm, stream);
 }

@@ -11,11 +11,14 @@ from ._base import RTModule, prefixed
 
 
 def _stage(images, device):
-    """Device fp32 images; a pinned fp32 HOST batch is passed through as is: the encoder runtime streams it in
+    """Device fp32 (normalised) or uint8 (raw 0..255 pixels, normalised in the stem kernel with the ImageNet statistics
+    of the reference's preprocessing) images; a pinned HOST batch is passed through as is: the encoder runtime streams it in
     chunks so the host->device copy overlaps the trunk (an extension -- the reference takes device tensors only)."""
-    if images.device.type == 'cpu' and images.dtype == torch.float32 and images.is_contiguous() \
+    if images.device.type == 'cpu' and images.dtype in (torch.float32, torch.uint8) and images.is_contiguous() \
             and images.is_pinned() and images.shape[0] > 64:
         return images
+    if images.dtype == torch.uint8:          # raw pixels: ToTensor + Normalize happen inside the stem kernel
+        return images.to(device).contiguous()
     return images.to(device, torch.float32).contiguous()
 
 

@@ -105,9 +105,26 @@ class EncoderRT:
         ops.conv2d(x, pc.w, pc.bias, y, pc.stride, pc.pad, relu, residual)
         return y
 
+    # ImageNet statistics of the reference's preprocessing (deephumor_demo.ipynb cell 11: ToTensor + Normalize)
+    pixel_mean = (0.485, 0.456, 0.406)
+    pixel_std = (0.229, 0.224, 0.225)
+
+    def normalize(self, images_u8):
+        """uint8 [n,3,H,W] -> fp32 (x / 255 - mean) / std, the operation order of ToTensor + Normalize (check mode and
+        sizes the fused stem does not cover)."""
+        m = torch.tensor(self.pixel_mean, dtype=torch.float32, device=images_u8.device).view(1, 3, 1, 1)
+        sd = torch.tensor(self.pixel_std, dtype=torch.float32, device=images_u8.device).view(1, 3, 1, 1)
+        return ((images_u8.float() / 255.0) - m) / sd
+
     def trunk(self, images):
         """images [n,3,224,224] fp32 NCHW (device) -> features [n,7,7,2048] NHWC in the trunk storage dtype."""
         n, _, H, W = images.shape
+        if images.dtype == torch.uint8:
+            if self.tdtype != torch.float32 and H == 224 and W == 224 and ops.FUSED_STEM:
+                x = self._buf('pool', (n, 56, 56, 64))
+                ops.stem_pool_u8(images, self.pixel_mean, self.pixel_std, self.stem_wq, self.stem.bias, x)
+                return self._layers(x)
+            images = self.normalize(images)
         if self.tdtype != torch.float32 and H == 224 and W == 224 and ops.FUSED_STEM:
             x = self._buf('pool', (n, 56, 56, 64))
             ops.stem_pool(images, self.stem_wq, self.stem.bias, x)
@@ -154,7 +171,7 @@ class EncoderRT:
         while left > 0:
             sizes.append(min(self.chunk, left))
             left -= sizes[-1]
-        bufs = [self._buf(f'h2d{b}', (self.chunk,) + tuple(images.shape[1:]), torch.float32) for b in range(2)]
+        bufs = [self._buf(f'h2d{b}', (self.chunk,) + tuple(images.shape[1:]), images.dtype) for b in range(2)]
         cs.wait_stream(main)                           # earlier readers of the staging buffers are done
         i0 = 0
         for k, n in enumerate(sizes):

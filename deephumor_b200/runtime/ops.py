@@ -125,6 +125,17 @@ def stem_pool(images, w_packed, bias, out):
     LIB.call('dh_stem_pool_tc', ptr(images), ptr(w_packed), ptr(bias), ptr(out), n, H, W, code(out), stream())
 
 
+def stem_pool_u8(images, mean, std, w_packed, bias, out):
+    """uint8 images [n,3,224,224] (0..255) -> out [n,56,56,64]: ToTensor + Normalize(mean, std) fused into the stem."""
+    import ctypes
+    n, c, H, W = images.shape
+    assert c == 3 and images.is_contiguous() and images.dtype == torch.uint8 and out.is_contiguous()
+    assert w_packed.shape == (64, 192) and w_packed.dtype == out.dtype and w_packed.is_contiguous()
+    f3 = ctypes.c_float * 3
+    LIB.call('dh_stem_pool_tc_u8', ptr(images), f3(*[float(v) for v in mean]), f3(*[float(v) for v in std]),
+             ptr(w_packed), ptr(bias), ptr(out), n, H, W, code(out), stream())
+
+
 def maxpool3x3s2(x, y):
     n, H, W, C = x.shape
     LIB.call('dh_maxpool3x3s2', ptr(x), ptr(y), n, H, W, C, code(x), stream())

@@ -24,7 +24,7 @@ extern "C" {
 typedef struct CUstream_st* cudaStream_t;
 #endif
 
-#define DH_VERSION 110
+#define DH_VERSION 111
 
 #define DH_OK 0
 #define DH_ERR_ARG (-1)
@@ -101,6 +101,12 @@ int dh_im2col_nhwc(const void* x, void* A, int n, int H, int W, int C, int kh, i
  * w_packed [64][192] of dtype: element [o][r*22 + s*3 + c] = folded weight [o][c][r][s], zero elsewhere. */
 int dh_stem_pool_tc(const float* images_nchw, const void* w_packed, const float* bias, void* out, int n, int H, int W,
                     int dtype, cudaStream_t stream);
+/* The same from raw uint8 pixels [n,3,224,224] (NCHW, 0..255): (x / 255 - mean[c]) / std[c] -- torchvision's ToTensor +
+ * Normalize (deephumor_demo.ipynb cell 11) in the exact fp32 operation order -- is applied while the input band is staged,
+ * so the float image never exists in HBM.  mean3_host / std3_host are HOST arrays of 3 floats. */
+int dh_stem_pool_tc_u8(const unsigned char* images_nchw_u8, const float* mean3_host, const float* std3_host,
+                       const void* w_packed, const float* bias, void* out, int n, int H, int W, int dtype,
+                       cudaStream_t stream);
 /* watchdog code left by gemm_tc_kernel before it traps (0 = none). */
 int dh_tc_error_flag(int* out_host);
 

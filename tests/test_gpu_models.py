@@ -217,3 +217,24 @@ def test_fused_perplexity_matches_materialised_logits(kind, tag, precision):
         pp1 = float(m.perplexity(imgs.cuda(), caps.cuda(), lens.cuda(), labs.cuda() if kind == 'lstm_labels' else None))
     assert abs(pp1 - pp0) / pp0 < 2e-4
     assert abs(pp1 - fx['perplexity']) / fx['perplexity'] < (1e-3 if precision == 'fp32' else 5e-2)
+
+
+def test_uint8_images_generate_the_same_captions_as_preprocessed_floats():
+    """Raw uint8 pixels (device and pinned-host batches) through generate() == the float path fed with
+    ToTensor + Normalize output (preprocessing fused into the stem loader)."""
+    fx = H.load_fixture('small', 'xfmr')
+    m, sd, *_ = build(fx, 'bf16')
+    g = torch.Generator().manual_seed(11)
+    u8 = torch.randint(0, 256, (70, 3, 224, 224), generator=g, dtype=torch.uint8)
+    rt = m.encoder._rt()
+    flt = rt.normalize(u8)
+    kw = dict(max_len=8, temperature=1.0, beam_size=3, top_k=10, noise='injected', seed=2)
+    with torch.no_grad():
+        a = m.generate(flt.cuda(), **kw)
+        b = m.generate(u8.cuda(), **kw)
+        c = m.generate(u8.pin_memory(), **kw)
+        m.set_precision('fp32')
+        d = m.generate(flt[:4].cuda(), **kw)
+        e = m.generate(u8[:4].cuda(), **kw)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[0], c[0])
+    assert torch.equal(d[0], e[0])

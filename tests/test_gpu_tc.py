@@ -201,3 +201,22 @@ def test_lstm_layer_fused_cell_epilogue(rows, H_, in_, use_parent):
         cp = c_prev.cpu().double() if parent is None else c_prev.cpu().double()[parent.cpu().long()]
         hr, cr = cell(A[:, :in_].double().cpu(), (A[:, in_:].double().cpu(), cp))
     assert H.rel_err(c1, cr) < 1e-3 and H.rel_err(h1b.float(), hr) < 5e-3
+
+
+def test_fused_stem_from_uint8_pixels_is_bit_identical_to_the_float_path():
+    """uint8 input: ToTensor + Normalize fused into the stem's band loader give exactly the features of the float
+    path fed with torchvision-style preprocessed images (same fp32 operation order)."""
+    g = torch.Generator().manual_seed(5)
+    u8 = torch.randint(0, 256, (5, 3, 224, 224), generator=g, dtype=torch.uint8)
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    m = torch.tensor(mean).view(1, 3, 1, 1)
+    s = torch.tensor(std).view(1, 3, 1, 1)
+    flt = ((u8.float() / 255.0) - m) / s                  # ToTensor then Normalize
+    w, b = rnd(64, 3, 7, 7, seed=2, scale=0.1), rnd(64, seed=3)
+    wq = _pack_stem(w, torch.float16)
+    o_f = torch.empty(5, 56, 56, 64, dtype=torch.float16, device=DEV)
+    o_u = torch.empty_like(o_f)
+    ops.stem_pool(flt.to(DEV), wq, b.to(DEV), o_f)
+    ops.stem_pool_u8(u8.to(DEV), mean, std, wq, b.to(DEV), o_u)
+    torch.cuda.synchronize()
+    assert torch.equal(o_f, o_u)
