@@ -238,3 +238,36 @@ def test_uint8_images_generate_the_same_captions_as_preprocessed_floats():
         e = m.generate(u8[:4].cuda(), **kw)
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[0], c[0])
     assert torch.equal(d[0], e[0])
+
+
+@pytest.mark.parametrize('kind', ['lstm', 'xfmr'])
+def test_char_level_vocabulary_long_captions_match_oracle(kind):
+    """Char-level shapes of the 2020 checkpoints (V = 71, captions up to 100+ tokens): fp32
+    check mode tokens == the CPU oracle on the same weights / noise, tensor-core mode runs the same request, and
+    max_len beyond the position table raises IndexError like nn.Embedding in the reference (Q19)."""
+    from deephumor_b200.utils import synth, synth_weights
+    from oracle import noise as onoise
+    V, n_img, max_len = 71, 3, 100
+    hp = synth_weights.default_hp(kind, V, small=True)
+    if kind == 'xfmr':
+        hp['max_len'] = 128
+    sd = synth_weights.make_state_dict(kind, hp, seed=4)
+    m = CLS[kind](**hp)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval().set_precision('fp32')
+    imgs = synth.images(0, 0, n_img)
+    kw = dict(max_len=max_len, beam_size=4, top_k=20, temperature=1.1)
+    gaps = []
+    enc = omodel.encode(kind, sd, imgs, None)
+    oids, olen = omodel.generate_batch(kind, sd, hp, None, None, encoded=enc, gaps=gaps, noise=onoise.Noise('injected', 8), **kw)
+    with torch.no_grad():
+        ids, lens = m.generate(imgs.cuda(), noise='injected', seed=8, **kw)
+        for n in range(n_img):
+            if gaps[n] > H.NEAR_TIE:
+                assert ids[n].cpu().tolist() == oids[n].tolist() and int(lens[n]) == int(olen[n])
+        m.set_precision('bf16')
+        ids2, lens2 = m.generate(imgs.cuda(), noise='injected', seed=8, **kw)
+        assert ids2.shape == (n_img, max_len) and int(ids2.max()) < V
+        if kind == 'xfmr':
+            with pytest.raises(IndexError):
+                m.generate(imgs.cuda(), max_len=128, beam_size=2, top_k=5)
