@@ -218,7 +218,8 @@ struct Cfg {
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStagingBytes + kBiasBytes + 256;
 };
 
-template <int BN, bool PAIR>
+// EPI = TcParams::epi_mode as a compile-time constant: every epilogue is its own kernel (named in profiles, no dead code)
+template <int BN, bool PAIR, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
@@ -254,7 +255,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), (p.epi_mode ? 8 : 4) * CG);   // the leader's barrier collects both CTAs' epilogue warps
+      mbar_init(tempty_bar(s), (EPI ? 8 : 4) * CG);   // the leader's barrier collects both CTAs' epilogue warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 2) {
@@ -379,7 +380,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int ew = warp & 3;                      // TMEM lane quadrant this warp may read
     const int eh = (warp - 4) >> 2;               // 0: warps 4-7, 1: warps 8-11 (other column half; fused epilogues only)
     const int etid = (warp - 4) * 32 + lane;      // 0..255 over both epilogue groups
-    if (p.epi_mode == 3) {
+    if (EPI == 3) {
       // ---- LSTM cell epilogue (BN == 256): a tile holds the i, f, g, o pre-activations of 64 hidden units for 128 rows;
       // each thread owns one row: c = sig(f) c_prev[parent] + sig(i) tanh(g), h = sig(o) tanh(c) (nn.LSTM gate order).
       if (BN == 256) {
@@ -463,7 +464,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar(as), 0)); else mbar_arrive(tempty_bar(as)); }
         }
       }
-    } else if (p.epi_mode) {
+    } else if (EPI) {
       // ---- selection epilogues: every thread owns one accumulator row; nothing of the [M,N] product is stored.
       const int row_l = ew * 32 + lane;
       int it = 0;
@@ -473,8 +474,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const long long row = (long long)m0 + row_l;
         const bool row_ok = row < p.M;
         // issued before the wait on the accumulator so that its L2 round trip is hidden
-        const float thr = (p.epi_mode == 2 && row_ok) ? __ldg(p.thresh + row) : INFINITY;
-        const int tcol = (p.epi_mode == 4 && row_ok) ? (int)__ldg(p.targets + row) : -1;
+        const float thr = (EPI == 2 && row_ok) ? __ldg(p.thresh + row) : INFINITY;
+        const int tcol = (EPI == 4 && row_ok) ? (int)__ldg(p.targets + row) : -1;
         mbar_wait(tfull_bar(as), (it >> 1) & 1, p.error, 4);
         tc_fence_after();
         const uint32_t tmem_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
@@ -482,7 +483,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int i = etid; i < BN; i += 256) bias_s[i] = (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
         asm volatile("bar.sync 1, 256;" ::: "memory");
         // candidates are finite logits >= thresh[row]; clamping to -FLT_MAX folds the "> -inf" test into one compare
-        const float t0 = (p.epi_mode == 2 && row_ok) ? fmaxf(thr, -3.402823466e+38f) : INFINITY;
+        const float t0 = (EPI == 2 && row_ok) ? fmaxf(thr, -3.402823466e+38f) : INFINITY;
         // Candidates of this thread's slice are parked in shared memory (the store staging area is idle in this mode) and
         // appended with ONE atomic per row and tile: the slot's round trip to L2 is paid once, after the TMEM reads.
         constexpr int kPend = 8;
@@ -502,8 +503,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int c = eh * (BN / 64); c < (eh + 1) * (BN / 64); ++c) {
           const int col0 = n0 + c * 32;
           if (col0 >= p.N) {                                      // warp-uniform: group past the end of the row
-            if (p.epi_mode != 2 && row_ok) p.gmax[row * p.ld_gmax + (tile % p.n_blocks) * (BN / 32) + c] = -INFINITY;
-            if (p.epi_mode == 4 && row_ok) p.gsum[row * p.ld_gmax + (tile % p.n_blocks) * (BN / 32) + c] = 0.f;
+            if (EPI != 2 && row_ok) p.gmax[row * p.ld_gmax + (tile % p.n_blocks) * (BN / 32) + c] = -INFINITY;
+            if (EPI == 4 && row_ok) p.gsum[row * p.ld_gmax + (tile % p.n_blocks) * (BN / 32) + c] = 0.f;
             continue;
           }
           uint32_t v[32];
@@ -531,9 +532,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int j = 1; j < 8; ++j) m8[q] = fmaxf(m8[q], x[8 * q + j]);
           }
           const float mx = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
-          if (p.epi_mode == 1) {
+          if (EPI == 1) {
             if (row_ok) p.gmax[row * p.ld_gmax + (tile % p.n_blocks) * (BN / 32) + c] = mx;
-          } else if (p.epi_mode == 4) {
+          } else if (EPI == 4) {
             // log-softmax pieces of this group (experiments/metrics.py:5): max, sum of exp(x - max), and the target's logit
             float se = 0.f;
 #pragma unroll
@@ -841,13 +842,13 @@ int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long col
   return DH_OK;
 }
 
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, int EPI>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mr, const CUtensorMap& mi,
            TcParams& p, cudaStream_t s) {
   using C = Cfg<BN, PAIR>;
   static bool attr = false;
   if (!attr) {
-    DH_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    DH_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, PAIR, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr = true;
   }
   if (p.n_stride < 1) p.n_stride = 1;
@@ -867,13 +868,22 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, 
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    DH_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, PAIR>, ma, mb, mc, mr, mi, p));
+    DH_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, PAIR, EPI>, ma, mb, mc, mr, mi, p));
   } else {
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    gemm_tc_kernel<BN, PAIR><<<grid, kThreads, C::kSmemBytes, s>>>(ma, mb, mc, mr, mi, p);
+    gemm_tc_kernel<BN, PAIR, EPI><<<grid, kThreads, C::kSmemBytes, s>>>(ma, mb, mc, mr, mi, p);
   }
   DH_LAUNCH_OK();
   return DH_OK;
+}
+
+template <int EPI>
+int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mr, const CUtensorMap& mi,
+              TcParams& p, int bn, bool pair, cudaStream_t s) {
+  if (EPI == 3) return pair ? launch<256, true, 3>(ma, mb, mc, mr, mi, p, s) : launch<256, false, 3>(ma, mb, mc, mr, mi, p, s);
+  if (bn == 64) return launch<64, false, EPI>(ma, mb, mc, mr, mi, p, s);
+  if (bn == 128) return pair ? launch<128, true, EPI>(ma, mb, mc, mr, mi, p, s) : launch<128, false, EPI>(ma, mb, mc, mr, mi, p, s);
+  return pair ? launch<256, true, EPI>(ma, mb, mc, mr, mi, p, s) : launch<256, false, EPI>(ma, mb, mc, mr, mi, p, s);
 }
 
 int pick_bn(int M, int N) {
@@ -916,9 +926,13 @@ int dispatch(const CUtensorMap& ma, const void* W, long long ldw, TcParams& p, i
       p.res_chunks = 1;   // launch<> sets BN / 64
     }
   }
-  if (bn == 64) return launch<64, false>(ma, mb, mc, mr, mi, p, s);
-  if (bn == 128) return pair ? launch<128, true>(ma, mb, mc, mr, mi, p, s) : launch<128, false>(ma, mb, mc, mr, mi, p, s);
-  return pair ? launch<256, true>(ma, mb, mc, mr, mi, p, s) : launch<256, false>(ma, mb, mc, mr, mi, p, s);
+  switch (p.epi_mode) {
+    case 0: return launch_bn<0>(ma, mb, mc, mr, mi, p, bn, pair, s);
+    case 1: return launch_bn<1>(ma, mb, mc, mr, mi, p, bn, pair, s);
+    case 2: return launch_bn<2>(ma, mb, mc, mr, mi, p, bn, pair, s);
+    case 3: return launch_bn<3>(ma, mb, mc, mr, mi, p, bn, pair, s);
+    default: return launch_bn<4>(ma, mb, mc, mr, mi, p, bn, pair, s);
+  }
 }
 
 }  // namespace
