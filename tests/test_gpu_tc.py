@@ -103,7 +103,7 @@ def test_stem_im2col_gemm(dt):
 @pytest.mark.parametrize('mode', ['deterministic', 'injected'])
 @pytest.mark.parametrize('rows,V,K_,B,top_k,T', [(300, 36541, 512, 5, 50, 1.0), (7, 1000, 64, 3, 10, 0.8), (130, 4099, 128, 1, 1, 1.3),
                                                  (64, 2048, 256, 4, 64, 1.0), (5, 71, 64, 2, 2, 1.0), (5, 100, 64, 1, 1, 1.0),
-                                                 (40, 50001, 64, 3, 20, 1.0)])
+                                                 (40, 50001, 64, 3, 20, 1.0), (300, 4099, 1024, 5, 50, 1.0)])
 def test_fused_vocab_select_matches_materialised_logits(mode, rows, V, K_, B, top_k, T, stride):
     """Two-pass vocab projection (group maxima -> threshold -> candidate compaction, logits never stored) picks
     exactly what dh_select_tokens and the CPU oracle pick on the materialised logits of the same tcgen05 product."""
@@ -220,3 +220,21 @@ def test_fused_stem_from_uint8_pixels_is_bit_identical_to_the_float_path():
     ops.stem_pool_u8(u8.to(DEV), mean, std, wq, b.to(DEV), o_u)
     torch.cuda.synchronize()
     assert torch.equal(o_f, o_u)
+
+
+@pytest.mark.parametrize('rows,V,K_', [(300, 4099, 1024), (70, 36541, 512), (5, 71, 64), (129, 1000, 256)])
+def test_vocab_logprob_fused_epilogue(rows, V, K_):
+    """log_softmax(A W^T + b)[m, target[m]] from the contraction's (max, sum exp) epilogue (K = 1024 runs on CTA pairs)
+    against torch on the materialised logits of the same product."""
+    g = torch.Generator().manual_seed(rows + V)
+    A = (torch.randn(rows, K_, generator=g) * 0.5).to(torch.bfloat16).to(DEV)
+    W = (torch.randn(V, K_, generator=g) * 0.2).to(torch.bfloat16).to(DEV)
+    bias = torch.randn(V, generator=g).to(DEV)
+    tg = torch.randint(0, V, (rows,), generator=g).to(DEV)
+    tg[0], tg[-1] = 0, V - 1
+    out = torch.empty(rows, device=DEV)
+    ops.vocab_logprob(A, W, bias, tg, out)
+    logits = torch.empty(rows, (V + 3) // 4 * 4, device=DEV)
+    ops.gemm(A, W, logits[:, :V], bias=bias)
+    ref = torch.log_softmax(logits[:, :V].double(), dim=-1).gather(1, tg.view(-1, 1)).view(-1)
+    assert float((out.double() - ref).abs().max()) < 2e-4 * max(1.0, float(ref.abs().max()))
