@@ -585,16 +585,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t swz = (uint32_t)(row_l & 7);
       const bool elected = (warp == 4 && lane == 0);
       uint32_t round_ctr = 0;
-      int it = 0;
+      int it = 0, last_n0 = -1;
       for (int tile = tile0; tile < tiles; tile += tstride, ++it) {
         const int m0 = tile_m0(tile), n0 = (tile % p.n_blocks) * BN * p.n_stride;
         const int as = it & 1;
+        // bias slice of this tile -> smem, only when the N block changed, and before the wait on the accumulator so the
+        // global-load latency is off the per-tile critical path (all readers of the previous slice are past their last
+        // round barrier)
+        if (p.bias && n0 != last_n0) {
+          for (int i = row_l; i < BN; i += 128) bias_s[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+          last_n0 = n0;
+        }
         mbar_wait(tfull_bar(as), (it >> 1) & 1, p.error, 4);
         tc_fence_after();
         const uint32_t tmem_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
-        // bias slice of this tile -> smem (all readers of the previous slice are past their last round barrier)
-        if (p.bias)
-          for (int i = row_l; i < BN; i += 128) bias_s[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
 #pragma unroll 1
         for (int rd = 0; rd < BN / 32; ++rd) {
           const int col0 = n0 + rd * cpr;

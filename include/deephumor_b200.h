@@ -24,7 +24,7 @@ extern "C" {
 typedef struct CUstream_st* cudaStream_t;
 #endif
 
-#define DH_VERSION 111
+#define DH_VERSION 112
 
 #define DH_OK 0
 #define DH_ERR_ARG (-1)
@@ -89,6 +89,12 @@ int dh_gemm_tc(const void* A, long long lda, const void* W, long long ldw, int a
 int dh_conv2d_tc(const void* x, const void* w, const float* bias, const void* residual, void* y, int n, int H, int W,
                  int Cin, int Cout, int kh, int kw, int stride, int pad, int relu, int dtype, int tile_n,
                  cudaStream_t stream);
+/* 3x3 / stride 1 / pad 1 convolution (+ bias + ReLU) that loads each input pixel ONCE per tile (torchvision resnet.py:146-148,
+ * conv2 of the layer1 / layer2 bottlenecks): an 8 x 16 output rectangle per tile, its 10 x 18 halo fetched by one tiled TMA
+ * load per 64-channel chunk, the nine taps contracted as shifted UMMA-descriptor views of the same shared memory
+ * (csrc/conv3x3_tc.cu).  x / w / y as in dh_conv2d_tc; Cin % 64 == 0, Cout % 64 == 0. */
+int dh_conv3x3_halo_tc(const void* x, const void* w, const float* bias, void* y, int n, int H, int W, int Cin, int Cout,
+                       int relu, int dtype, cudaStream_t stream);
 /* Explicit gathers: the C_in = 3 stem straight from the NCHW fp32 image into A[n*Ho*Wo, k_padded] (bf16 / f16) with
  * k = (r*kw + s)*3 + c (encoders.py:56 -> resnet.py:197 conv1), and a generic NHWC gather A[m, (r*kw+s)*C + c]. */
 int dh_im2col_stem(const float* images_nchw, void* A, int n, int H, int W, int kh, int kw, int stride, int pad,

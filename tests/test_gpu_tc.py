@@ -83,6 +83,27 @@ def test_conv2d_tc_im2col_tma(n, H_, Cin, Cout, k, s, p, dt):
     assert torch.equal(y2.view_as(y), y)
 
 
+@pytest.mark.parametrize('dt', [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize('n,H_,Cin,Cout', [(2, 56, 64, 64), (3, 28, 128, 128), (1, 30, 64, 128), (5, 56, 128, 64), (2, 33, 192, 64)])
+def test_conv3x3_halo_kernel(n, H_, Cin, Cout, dt):
+    """Halo-tile 3x3 convolution (input read once, taps as shifted UMMA descriptor views) against torch and against
+    the im2col-TMA kernel; H not a multiple of the 8 x 16 tile exercises the clipped stores and the zero-filled halo."""
+    x, w, b = rnd(n, Cin, H_, H_, seed=1).to(dt), rnd(Cout, Cin, 3, 3, seed=2, scale=0.05).to(dt), rnd(Cout, seed=3)
+    ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), 1, 1)).float().permute(0, 2, 3, 1).contiguous()
+    xd = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    wd = w.permute(0, 2, 3, 1).contiguous().to(DEV)
+    y = torch.full(ref.shape, 7.0, dtype=dt, device=DEV)
+    from deephumor_b200._lib import LIB, ptr, stream
+    bd = b.to(DEV)
+    LIB.call('dh_conv3x3_halo_tc', ptr(xd), ptr(wd), ptr(bd), ptr(y), n, H_, H_, Cin, Cout, 1, ops.code(xd), stream())
+    y2 = torch.empty_like(y)
+    ops.conv2d(xd, wd, b.to(DEV), y2, 1, 1, True, tile_n=64)           # forces the im2col-TMA kernel
+    torch.cuda.synchronize()
+    tol = 4e-3 if dt == torch.bfloat16 else 5e-4
+    assert H.rel_err(y.float(), ref) < tol and H.rel_err(y2.float(), ref) < tol
+    assert H.rel_err(y.float(), y2.float()) < tol
+
+
 @pytest.mark.parametrize('dt', [torch.bfloat16, torch.float16])
 def test_stem_im2col_gemm(dt):
     n, H_ = 2, 64
