@@ -192,6 +192,8 @@ class EncoderRT:
         E = self.E
         start = torch.empty(N, E, dtype=torch.float32, device=self.device)
         sp = torch.empty(N * 49, E, dtype=self.dtype, device=self.device) if self.spatial else None
+        if N == 0:
+            return start, sp
         pooled = self._buf('pooled', (N, 2048), torch.float32)
         chunks = self._host_chunks(images) if not images.is_cuda else \
             ((i0, images[i0:i0 + self.chunk], None) for i0 in range(0, N, self.chunk))

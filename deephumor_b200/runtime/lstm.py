@@ -141,6 +141,9 @@ class LSTMDecoderRT:
         The decode loop is captured once per (batch, beam, lengths, sampling parameters) into a CUDA graph over
         static buffers and replayed; seed / image_base reach the kernels through a device word pair."""
         N, B, dev = start_emb.shape[0], beam_size, self.device
+        if N == 0:                                   # empty batch: nothing to launch
+            z = lambda *sh: torch.zeros(*sh, dtype=torch.int64, device=dev)
+            return z(0, max_len), z(0), torch.zeros(1, dtype=torch.int32, device=dev), False
         p0 = 0 if caption is None else caption.shape[1]
         key = (N, B, p0, max_len, float(temperature), top_k, eos_index, unk_index, noise_mode, pad_index, robust)
         pl = self._plans.get(key)

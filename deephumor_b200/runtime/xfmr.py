@@ -139,6 +139,9 @@ class XfmrDecoderRT:
         """start_emb fp32 [N,D]; spatial [N*49,D] (cross) or None; caption int32 [N or 1,p] or None.
         The decode is captured once per configuration into a CUDA graph over static buffers and replayed."""
         N, B, D, dev, dt = start_emb.shape[0], beam_size, self.D, self.device, self.dtype
+        if N == 0:                                   # empty batch: nothing to launch
+            z = lambda *sh: torch.zeros(*sh, dtype=torch.int64, device=dev)
+            return z(0, max_len), z(0), torch.zeros(1, dtype=torch.int32, device=dev), False
         R = N * B
         p0 = 0 if caption is None else caption.shape[1]
         S = max_len + 1                                          # cached positions 0..max_len

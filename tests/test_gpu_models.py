@@ -271,3 +271,21 @@ def test_char_level_vocabulary_long_captions_match_oracle(kind):
         if kind == 'xfmr':
             with pytest.raises(IndexError):
                 m.generate(imgs.cuda(), max_len=128, beam_size=2, top_k=5)
+
+
+def test_empty_and_chunk_crossing_batches():
+    """Edge sizes: an empty batch returns empty ids; a batch that crosses the 256-image trunk chunk (257) gives the same
+    captions for its first / last images as generating them alone with the matching image_base."""
+    from deephumor_b200.utils import synth
+    fx = H.load_fixture('small', 'lstm')
+    m, sd, *_ = build(fx, 'bf16')
+    kw = dict(max_len=6, temperature=1.0, beam_size=2, top_k=5, noise='injected', seed=4)
+    imgs = synth.images(0, 0, 257).cuda()
+    with torch.no_grad():
+        ids0, lens0 = m.generate(imgs[:0], **kw)
+        assert ids0.shape == (0, 6) and lens0.shape == (0,)
+        ids, lens = m.generate(imgs, **kw)
+        a = m.generate(imgs[:2], **kw)
+        b = m.generate(imgs[255:257], image_base=255, **kw)
+    assert ids.shape == (257, 6)
+    assert torch.equal(ids[:2], a[0]) and torch.equal(ids[255:], b[0]) and torch.equal(lens[255:], b[1])
