@@ -273,8 +273,12 @@ stem_pool_kernel(const TIN* __restrict__ images, const T* __restrict__ wp, const
         for (int kc = 0; kc < 3; ++kc) {
           const uint64_t da = umma_desc(a_buf[b] + (uint32_t)(kc * 128 * 128));
           const uint64_t db = umma_desc(w_buf + (uint32_t)(kc * 64 * 128));
+          // only K slots 0..159 hold data (154 real + zero padding): the last chunk needs 2 of its 4 K steps.  Every
+          // tcgen05.mma here is bound by re-reading its 128 x 16 A slice from shared memory (N = 64), so fewer
+          // instructions = proportionally less time.
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc_mma(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
+          for (int k = 0; k < (kc == 2 ? 2 : 4); ++k)
+            tc_mma(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
         }
         tc_commit(a_free(b));
         if (tap == 3) tc_commit(grp_done(0));
