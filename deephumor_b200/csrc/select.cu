@@ -252,15 +252,33 @@ __global__ void __launch_bounds__(kSelThreads) select_tokens_kernel(SelParams p)
 // One WARP per row, no block-level synchronisation: the two largest values of every lane's strided slice are 64
 // distinct group maxima whose top_k-th largest is a first bound t1 (top_k <= 64); group maxima >= t1 (a few more than
 // top_k) are then compacted per warp and ranked exactly.
-constexpr int kThrWarps = 8;
+constexpr int kThrWarps = 2;     // small CTAs: 2560 rows spread evenly over 148 SMs (8-warp CTAs left some SMs 3 CTAs, others 2)
 constexpr int kThrCap = 256;
+
+// m-th smallest (1-based, m <= 64) of the 64 order-preserving keys a warp holds two per lane, by m rounds of warp-wide
+// minimum extraction (redux.sync): O(8 m) instructions against O(64 * 64 / 32 * 5) for rank counting.  Keys of unused
+// slots must be 0xffffffff.
+__device__ __forceinline__ unsigned int warp_mth_smallest64(unsigned int a, unsigned int b, int m, int lane) {
+  unsigned int res = 0xffffffffu;
+  for (int i = 0; i < m; ++i) {
+    const unsigned int lo = a < b ? a : b;
+    res = __reduce_min_sync(0xffffffffu, lo);
+    const unsigned int has = __ballot_sync(0xffffffffu, lo == res);
+    if (lane == __ffs(has) - 1) {            // drop ONE instance (the lowest lane holding it)
+      if (a == res) a = 0xffffffffu; else b = 0xffffffffu;
+    }
+  }
+  return res;
+}
+__device__ __forceinline__ float key_to_float(unsigned int k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
 // NPL > 0: the whole row (<= 32 * NPL group maxima) is loaded into registers with all loads in flight at once (one L2
 // round trip); NPL == 0: generic two-pass version for longer rows.
 template <int NPL>
 __global__ void __launch_bounds__(kThrWarps * 32) vocab_threshold_kernel(const float* __restrict__ gmax, long long ld, int rows,
                                                                         int n_groups, int top_k, float* __restrict__ thresh,
                                                                         int* __restrict__ cand_count) {
-  __shared__ float s_top[kThrWarps][64];
   __shared__ float s_cand[kThrWarps][kThrCap];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * kThrWarps + w;
@@ -303,18 +321,8 @@ __global__ void __launch_bounds__(kThrWarps * 32) vocab_threshold_kernel(const f
           }
         }
       }
-      s_top[w][lane] = m1;
-      s_top[w][32 + lane] = m2;
-      __syncwarp();
-      int r1 = 0, r2 = 0;
-      for (int j = 0; j < 64; ++j) {
-        const float o = s_top[w][j];
-        r1 += (o > m1) || (o == m1 && j < lane);
-        r2 += (o > m2) || (o == m2 && j < 32 + lane);
-      }
-      if (r1 == top_k - 1) t1 = m1;
-      if (r2 == top_k - 1) t1 = m2;
-      t1 = dh_warp_max(t1);            // exactly one slot has that rank; if it holds -inf (n_groups < 64) t1 stays -inf
+      // top_k-th largest of the 64 per-lane top-2 values = (64 - top_k + 1)-th smallest
+      t1 = key_to_float(warp_mth_smallest64(order_key(m1), order_key(m2), 64 - top_k + 1, lane));
     }
     int n = 0;
     auto offer = [&](float x, bool in_range) {
@@ -336,9 +344,14 @@ __global__ void __launch_bounds__(kThrWarps * 32) vocab_threshold_kernel(const f
       }
     }
     __syncwarp();
-    if (n <= kThrCap) {
-      // exact top_k-th largest of the n compacted maxima by rank counting (independent iterations; an MSB-first radix
-      // select was measured slower here: its 32 rounds are serially dependent and n is only ~60)
+    if (n <= 64) {
+      // exact top_k-th largest of the n compacted maxima = (n - top_k + 1)-th smallest (n >= top_k: the compaction kept at
+      // least the top_k values that defined t1, or everything when t1 = -inf)
+      const unsigned int a = lane < n ? order_key(s_cand[w][lane]) : 0xffffffffu;
+      const unsigned int b = 32 + lane < n ? order_key(s_cand[w][32 + lane]) : 0xffffffffu;
+      t0 = key_to_float(warp_mth_smallest64(a, b, n - top_k + 1, lane));
+    } else if (n <= kThrCap) {
+      // rank counting (independent iterations) for the rare longer lists
       for (int c = lane; c < n; c += 32) {
         const float v = s_cand[w][c];
         int gt = 0, ge = 0;
