@@ -105,7 +105,7 @@ def build_model(kind, precision):
     cls = {'lstm': models.CaptioningLSTM, 'lstm_labels': models.CaptioningLSTMWithLabels,
            'xfmr_base': models.CaptioningTransformerBase, 'xfmr': models.CaptioningTransformer}[kind]
     hp = synth_weights.default_hp(kind, V)
-    if kind == 'lstm' and False:
+    if kind == 'lstm':            # BASELINE.json configs[0]: 1-layer LSTMDecoder, emb 256
         hp.update(emb_dim=256, num_layers=1)
     sd = synth_weights.make_state_dict(kind, hp, seed=0)
     m = cls(**hp)
