@@ -286,6 +286,9 @@ def run_ours(args):
         line['roofline']['note'] = ('kernel timed with CUDA events in an eager pass of the same steps right after the '
                                     'timed pass (which replays the decode loop as a CUDA graph)')
         line['stages_ms_per_step'] = {k: round(v[1] / args.steps, 3) for k, v in prof.items()}
+        # per-stage tensor-pipe fraction (algorithmic FLOPs of the stage / its CUDA-event time / measured sustained peak)
+        line['stages_tensor_frac'] = {k: round(v[2] / (v[1] / 1e3) / 1e12 / sustained, 3)
+                                      for k, v in prof.items() if v[2] > 0 and v[1] > 0}
     if not args.no_cpu_baseline and world == 1:          # reported at N = 1 only
         line['cpu_baseline'] = cpu_baseline(kind, hp, sd, beam, top_k, args.cpu_images)
     print(json.dumps(line))

@@ -7,6 +7,8 @@
 // Scores: lanes over keys, each lane reads one contiguous head row of K (16 B vector loads);
 // output: lanes over head dims, V rows read coalesced.  Masked keys get -1e8 (not -inf) as in the
 // reference (:111); keys beyond the causal horizon contribute exactly 0 there and are skipped here.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -197,6 +199,161 @@ __global__ void __launch_bounds__(32 * 16) attn_shared_kv_kernel(AttnParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ tensor-core path
+// Attention whose keys are shared by all query rows of an image -- cross-attention over the 49 spatial tokens (decode:
+// the image's beam rows; teacher-forced: its S positions) and teacher-forced causal self-attention -- as two small
+// matmuls per (image, head) on mma.sync m16n8k16 (bf16 in, fp32 accumulate): S = Q K^T, softmax on the accumulator
+// fragments, O = P V with P re-used from registers as the A operand.  head_dim 64, <= 64 keys, <= 64 query rows per image.
+// (tcgen05 needs M >= 64 rows per instruction; a 5-row x 49-key problem per head fits the warp-level MMA instead.)
+constexpr int kMmaPitch = 72;        // bf16 elements per staged row (64 + 8: conflict-free ldmatrix)
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t* r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t* r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+template <int NKT>      // NKT 8-key tiles (even): keys padded to 8 * NKT <= 64
+__global__ void __launch_bounds__(128) attn_mma_kernel(AttnParams p) {
+  constexpr int NKP = NKT * 8;
+  __shared__ __align__(16) __nv_bfloat16 sK[NKP * kMmaPitch];
+  __shared__ __align__(16) __nv_bfloat16 sV[NKP * kMmaPitch];
+  __shared__ __align__(16) __nv_bfloat16 sQ[64 * kMmaPitch];
+  const int img = blockIdx.x / p.n_heads, h = blockIdx.x % p.n_heads;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nk = p.causal_full ? p.rpi : p.n_keys;
+  const int q_rows = ((p.rpi + 15) / 16) * 16;                         // staged query rows (<= 64)
+  const __nv_bfloat16* Kg = (const __nv_bfloat16*)p.K + ((long long)img * p.slots * p.S_alloc) * p.D + h * 64;
+  const __nv_bfloat16* Vg = (const __nv_bfloat16*)p.V + ((long long)img * p.slots * p.S_alloc) * p.D + h * 64;
+  const __nv_bfloat16* Qg = (const __nv_bfloat16*)p.q + ((long long)img * p.rpi) * p.ldq + h * 64;
+  // staging by all 128 threads, loads first (all in flight), then the shared-memory stores
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  constexpr int kKV = NKP * 8 / 128;                       // 16-byte chunks per thread per array (NKP * 8 chunks)
+  uint4 rk[kKV], rv[kKV];
+#pragma unroll
+  for (int u = 0; u < kKV; ++u) {
+    const int i = threadIdx.x + u * 128, t = i >> 3, c = i & 7;
+    rk[u] = t < nk ? __ldg(reinterpret_cast<const uint4*>(Kg + (long long)t * p.D + c * 8)) : zero;
+    rv[u] = t < nk ? __ldg(reinterpret_cast<const uint4*>(Vg + (long long)t * p.D + c * 8)) : zero;
+  }
+  uint4 rq[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {                            // up to 64 query rows x 8 chunks
+    const int i = threadIdx.x + u * 128, r = i >> 3, c = i & 7;
+    rq[u] = (i < q_rows * 8 && r < p.rpi) ? __ldg(reinterpret_cast<const uint4*>(Qg + (long long)r * p.ldq + c * 8)) : zero;
+  }
+#pragma unroll
+  for (int u = 0; u < kKV; ++u) {
+    const int i = threadIdx.x + u * 128, t = i >> 3, c = i & 7;
+    *reinterpret_cast<uint4*>(sK + t * kMmaPitch + c * 8) = rk[u];
+    *reinterpret_cast<uint4*>(sV + t * kMmaPitch + c * 8) = rv[u];
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = threadIdx.x + u * 128, r = i >> 3, c = i & 7;
+    if (i < q_rows * 8) *reinterpret_cast<uint4*>(sQ + r * kMmaPitch + c * 8) = rq[u];
+  }
+  __syncthreads();
+  if (w * 16 >= q_rows) return;                            // staging-only warps
+  const uint32_t sK_u = (uint32_t)__cvta_generic_to_shared(sK), sV_u = (uint32_t)__cvta_generic_to_shared(sV);
+  const uint32_t sQ_u = (uint32_t)__cvta_generic_to_shared(sQ);
+  const int g = lane >> 2, t4 = lane & 3;
+  const int mat = lane >> 3, l8 = lane & 7;
+
+  // ---- S = Q K^T (16 query rows of this warp x NKP keys)
+  float sacc[NKT][4];
+#pragma unroll
+  for (int nt = 0; nt < NKT; ++nt) { sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f; }
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t a[4];
+    ldsm_x4(sQ_u + (uint32_t)(((w * 16 + (lane & 15)) * kMmaPitch + kk * 16 + (lane >> 4) * 8) * 2), a);
+#pragma unroll
+    for (int n2 = 0; n2 < NKT / 2; ++n2) {
+      uint32_t b[4];     // (keys 0-7, dims lo), (keys 0-7, dims hi), (keys 8-15, dims lo), (keys 8-15, dims hi)
+      ldsm_x4(sK_u + (uint32_t)(((n2 * 16 + (mat >> 1) * 8 + l8) * kMmaPitch + kk * 16 + (mat & 1) * 8) * 2), b);
+      mma_bf16(sacc[2 * n2], a, b[0], b[1]);
+      mma_bf16(sacc[2 * n2 + 1], a, b[2], b[3]);
+    }
+  }
+  // ---- scale, masks (excluded keys: beyond nk / the causal horizon; masked keys: -1e8 as in the reference), softmax
+  const int row0 = w * 16 + g, row1 = row0 + 8;
+  const int* seq_row = p.seq ? p.seq + (long long)img * p.seq_ld : nullptr;
+  const unsigned char* em = p.enc_mask ? p.enc_mask + (long long)img * p.S_alloc : nullptr;
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < NKT; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int col = nt * 8 + 2 * t4 + (e & 1);
+      const int row = e < 2 ? row0 : row1;
+      float v = sacc[nt][e] / p.scale;
+      if (col < nk) {
+        bool masked = false;
+        if (seq_row && col >= 1) masked = (seq_row[col - 1] == p.pad);
+        if (em) masked = em[col] != 0;
+        if (masked) v = -1e8f;
+      }
+      if (col >= nk || (p.causal_full && col > row)) v = -INFINITY;
+      sacc[nt][e] = v;
+      if (e < 2) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
+    }
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < NKT; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float pv = expf(sacc[nt][e] - (e < 2 ? mx0 : mx1));      // rows past rpi hold zeros: harmless, never stored
+      sacc[nt][e] = pv;
+      if (e < 2) sum0 += pv; else sum1 += pv;
+    }
+  }
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+  // ---- O = P V: the probability fragments are the A operand as they are (two 8-key tiles per 16-key step)
+  float oacc[8][4];
+#pragma unroll
+  for (int nd = 0; nd < 8; ++nd) { oacc[nd][0] = oacc[nd][1] = oacc[nd][2] = oacc[nd][3] = 0.f; }
+#pragma unroll
+  for (int kk = 0; kk < NKT / 2; ++kk) {
+    uint32_t a[4];
+    a[0] = pack_bf16(sacc[2 * kk][0], sacc[2 * kk][1]);
+    a[1] = pack_bf16(sacc[2 * kk][2], sacc[2 * kk][3]);
+    a[2] = pack_bf16(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1]);
+    a[3] = pack_bf16(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3]);
+#pragma unroll
+    for (int d2 = 0; d2 < 4; ++d2) {
+      uint32_t b[4];     // transposed loads: (keys lo, dims 0-7), (keys hi, dims 0-7), (keys lo, dims 8-15), (keys hi, dims 8-15)
+      ldsm_x4_trans(sV_u + (uint32_t)(((kk * 16 + (mat & 1) * 8 + l8) * kMmaPitch + d2 * 16 + (mat >> 1) * 8) * 2), b);
+      mma_bf16(oacc[2 * d2], a, b[0], b[1]);
+      mma_bf16(oacc[2 * d2 + 1], a, b[2], b[3]);
+    }
+  }
+  const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+  __nv_bfloat16* Og = (__nv_bfloat16*)p.out + ((long long)img * p.rpi) * p.ldo + h * 64;
+#pragma unroll
+  for (int nd = 0; nd < 8; ++nd) {
+    const int col = nd * 8 + 2 * t4;
+    if (row0 < p.rpi) *reinterpret_cast<uint32_t*>(Og + (long long)row0 * p.ldo + col) = pack_bf16(oacc[nd][0] * inv0, oacc[nd][1] * inv0);
+    if (row1 < p.rpi) *reinterpret_cast<uint32_t*>(Og + (long long)row1 * p.ldo + col) = pack_bf16(oacc[nd][2] * inv1, oacc[nd][3] * inv1);
+  }
+}
+
 // enc_mask[n, t] = any(spatial[n, t, :] == 0)   (transformers.py:480-481, Q16)
 template <typename T>
 __global__ void enc_mask_kernel(const T* __restrict__ x, unsigned char* __restrict__ mask, int rows, int D) {
@@ -226,6 +383,22 @@ extern "C" int dh_attention(const void* q, long long ldq, const void* K, const v
   if (rows == 0) return DH_OK;
   AttnParams p{q, ldq, K, V, out, ldo, rows, D, n_heads, rows_per_image, slots, S_alloc, src, slot_shared,
                n_keys, causal_full, seq, seq_ld, seq_per_image, pad, enc_mask, scale};
+  // keys shared by the rows of an image, bf16, head_dim 64, <= 64 keys and query rows per image: tensor-core path
+  {
+    const int nk = causal_full ? rows_per_image : n_keys;
+    static const bool mma_ok = !getenv("DH_NO_MMA_ATTN");
+    if (mma_ok && dtype == DH_BF16 && D / n_heads == 64 && slot_shared && nk <= 64 && rows_per_image <= 64 &&
+        rows % rows_per_image == 0 && (!seq || seq_per_image) && ldo % 2 == 0 && ((uintptr_t)out % 4) == 0) {
+      const int g = (rows / rows_per_image) * n_heads;
+      const int threads = 128;                 // 4 warps stage K / V / Q; ceil(rows_per_image / 16) of them compute
+      if (nk <= 16) attn_mma_kernel<2><<<g, threads, 0, s>>>(p);
+      else if (nk <= 32) attn_mma_kernel<4><<<g, threads, 0, s>>>(p);
+      else if (nk <= 48) attn_mma_kernel<6><<<g, threads, 0, s>>>(p);
+      else attn_mma_kernel<8><<<g, threads, 0, s>>>(p);
+      DH_LAUNCH_OK();
+      return DH_OK;
+    }
+  }
   // keys shared by the rows of an image (cross-attention during generation): stage K/V once per (image, head)
   const int esize = dtype == DH_F32 ? 4 : 2;
   const size_t shared_smem = (size_t)2 * n_keys * (D / n_heads) * esize + (size_t)rows_per_image * n_keys * 4;

@@ -54,8 +54,9 @@ class LSTMDecoderRT:
             A = ws['A'][l][:rows]
             nxt = ws['A'][l + 1][:rows, :H] if l + 1 < L else ws['top'][:rows]
             if self.fused_cell:
-                ops.lstm_layer_tc(A, self.Wpk[l], self.bpk[l], ws['c'][cur][l], parent, ws['c'][1 - cur][l][:rows], nxt,
-                                  ws['hs'][l][:rows])
+                with ops.PROFILE.range('lstm_layers', 2.0 * rows * 4 * H * A.shape[1]):
+                    ops.lstm_layer_tc(A, self.Wpk[l], self.bpk[l], ws['c'][cur][l], parent, ws['c'][1 - cur][l][:rows],
+                                      nxt, ws['hs'][l][:rows])
             else:
                 gates = ws['gates'][:rows]
                 ops.gemm(A, self.Wcat[l], gates, bias=self.bias[l])

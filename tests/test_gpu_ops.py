@@ -99,3 +99,39 @@ def test_select_tokens_matches_oracle(mode, V, B, K, T):
         assert torch.allclose(val[r].cpu(), ov[0], atol=1e-5)
     if K == 1:
         assert int(status.item()) & 1                    # row 1 is entirely filtered -> EMPTY_ROW flag
+
+
+@pytest.mark.parametrize('rpi,nk,causal,use_enc,use_pad', [(5, 49, False, True, False), (1, 49, False, True, False),
+                                                        (32, 0, True, False, True), (49, 49, False, True, False),
+                                                        (3, 7, False, False, False), (17, 0, True, False, True)])
+def test_attention_shared_keys_tensor_core_path(rpi, nk, causal, use_enc, use_pad):
+    """dh_attention with keys shared by an image's rows (bf16, head_dim 64): the mma.sync path against a float64 torch
+    restatement of MultiHeadAttentionLayer.forward's core (transformers.py:100-121) with the -1e8 masks."""
+    n_img, n_heads, D_ = 6, 8, 512
+    S = rpi if causal else nk
+    rows = n_img * rpi
+    g = torch.Generator().manual_seed(rpi * 100 + S)
+    q = (torch.randn(rows, D_, generator=g)).to(torch.bfloat16)
+    K = (torch.randn(n_img, S, D_, generator=g)).to(torch.bfloat16)
+    Vv = (torch.randn(n_img, S, D_, generator=g)).to(torch.bfloat16)
+    enc = (torch.rand(n_img, S, generator=g) < 0.2).to(torch.uint8) if use_enc else None
+    seq = torch.randint(0, 4, (n_img, S), generator=g).to(torch.int32) if use_pad else None     # 0 == pad
+    out = torch.empty(rows, D_, dtype=torch.bfloat16, device=DEV)
+    scale = 8.0
+    ops.attention(q.to(DEV), K.to(DEV), Vv.to(DEV), out, n_heads, rpi, 1, S, scale, slot_shared=True,
+                  n_keys=0 if causal else nk, causal_full=causal, seq=None if seq is None else seq.to(DEV),
+                  seq_per_image=True, pad=0, enc_mask=None if enc is None else enc.to(DEV))
+    qd = q.double().view(n_img, rpi, n_heads, 64).permute(0, 2, 1, 3)
+    kd = K.double().view(n_img, S, n_heads, 64).permute(0, 2, 1, 3)
+    vd = Vv.double().view(n_img, S, n_heads, 64).permute(0, 2, 1, 3)
+    e = qd @ kd.transpose(-1, -2) / scale                                  # [img, head, rpi, S]
+    if enc is not None:
+        e = e.masked_fill(enc.bool().view(n_img, 1, 1, S), -1e8)
+    if seq is not None:
+        padk = torch.zeros(n_img, S, dtype=torch.bool)
+        padk[:, 1:] = seq[:, :S - 1] == 0                                  # key t >= 1 masked iff token t-1 is pad
+        e = e.masked_fill(padk.view(n_img, 1, 1, S), -1e8)
+    if causal:
+        e = e.masked_fill(torch.triu(torch.ones(rpi, S, dtype=torch.bool), 1), float('-inf'))
+    ref = (torch.softmax(e, -1) @ vd).permute(0, 2, 1, 3).reshape(rows, D_)
+    assert H.rel_err(out.float(), ref.float()) < 1e-2
