@@ -358,6 +358,214 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   }
 }
 
+
+// ------------------------------------------------------------------------------------------- Cout == 64: transposed
+// With N = 64 output channels the M = 128 x N = 64 instruction is bound by re-reading its 128 x 16 A slice from shared
+// memory (~128 cycles per K = 16 step whatever N is).  Swapping the operands halves that: D^T[co, pixel] = W[co, k] X[pixel, k]^T
+// with the 64 channels as the UMMA M (A = the resident weight tile, 64 rows) and 256 pixels -- an 8 x 32 rectangle, the
+// same shifted halo views -- as N.  A tcgen05.mma of M = 64 puts accumulator row r in TMEM lane 32 * (r / 16) + r % 16
+// (probed: scripts/probes/umma_m64_layout.cu), so each of the four epilogue warps owns 16 channels; it transposes its
+// 16 x 256 slice through the swizzled slab back to NHWC for the TMA store.
+constexpr int kTHaloH = 34;                                   // 32 output rows + 2
+constexpr int kTHaloTx = kHaloW * kTHaloH * 128;              // 43 520 B
+constexpr int kTHaloBytes = 44032;                            // rounded to 1024
+constexpr int kTWStages = 9;                                  // one 8 KB slot per tap: resident when Cin == 64
+constexpr int kTSmemBytes = 1024 + 2 * kTHaloBytes + kTWStages * 8192 + 256 * 128 + 512;
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                      const __grid_constant__ CUtensorMap map_y, const HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t halo = base;                                        // 2 x kTHaloBytes
+  const uint32_t wring = base + 2 * kTHaloBytes;                     // 9 x 8 KB
+  const uint32_t slab = wring + kTWStages * 8192;                    // 256 pixels x 128 B
+  const uint32_t bars = slab + 256 * 128;
+  auto hfull = [&](int s) { return bars + 8u * s; };
+  auto hempty = [&](int s) { return bars + 8u * (2 + s); };
+  auto tfull = [&](int s) { return bars + 8u * (4 + s); };
+  auto tempty = [&](int s) { return bars + 8u * (6 + s); };
+  auto wfull = [&](int s) { return bars + 8u * (8 + s); };
+  auto wempty = [&](int s) { return bars + 8u * (8 + kTWStages + s); };
+  uint32_t* tmem_word = reinterpret_cast<uint32_t*>(gen + 2 * kTHaloBytes + kTWStages * 8192 + 256 * 128 + 8 * (8 + 2 * kTWStages));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(hfull(s), 1);
+      mbar_init(hempty(s), 1);
+      mbar_init(tfull(s), 1);
+      mbar_init(tempty(s), 4);
+    }
+    for (int s = 0; s < kTWStages; ++s) {
+      mbar_init(wfull(s), 1);
+      mbar_init(wempty(s), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  } else if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_word)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_word);
+
+  const int tiles = p.n * p.tiles_y * p.tiles_x;            // tiles_y counts 32-row tiles here; one N block (Cout == 64)
+  auto decode = [&](int tile, int& img, int& y0, int& x0) {
+    x0 = (tile % p.tiles_x) * 8;
+    const int sp = tile / p.tiles_x;
+    y0 = (sp % p.tiles_y) * 32;
+    img = sp / p.tiles_y;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================================================================== TMA producer
+      int hs = 0, ws = 0;
+      uint32_t hphase = 0, wphase = 0;
+      bool first = true;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        int img, y0, x0;
+        decode(tile, img, y0, x0);
+        for (int c = 0; c < p.c_chunks; ++c) {
+          mbar_wait(hempty(hs), hphase ^ 1u, p.error, 21);
+          mbar_expect_tx(hfull(hs), kTHaloTx);
+          tma_load_4d(halo + hs * kTHaloBytes, &map_x, hfull(hs), c * 64, x0 - 1, y0 - 1, img);
+          if (++hs == 2) { hs = 0; hphase ^= 1u; }
+          for (int t = 0; t < 9; ++t) {
+            if (p.w_resident) {
+              if (first) {
+                mbar_expect_tx(wfull(t), 8192);
+                tma_load_2d(wring + t * 8192, &map_w, wfull(t), t * p.Cin, 0);
+              }
+            } else {
+              mbar_wait(wempty(ws), wphase ^ 1u, p.error, 22);
+              mbar_expect_tx(wfull(ws), 8192);
+              tma_load_2d(wring + ws * 8192, &map_w, wfull(ws), t * p.Cin + c * 64, 0);
+              if (++ws == kTWStages) { ws = 0; wphase ^= 1u; }
+            }
+          }
+        }
+        first = false;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================================================================== MMA issuer: M = 64 channels, N = 256 pixels
+      const uint32_t fmt = p.dtype == DH_BF16 ? 1u : 0u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
+      int hs = 0, ws = 0, it = 0;
+      uint32_t hphase = 0, wphase = 0;
+      bool first = true;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        mbar_wait(tempty(as), ((it >> 1) & 1) ^ 1u, p.error, 23);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * 256);
+        for (int c = 0; c < p.c_chunks; ++c) {
+          mbar_wait(hfull(hs), hphase, p.error, 24);
+          tc_fence_after();
+          const uint32_t hb = halo + hs * kTHaloBytes;
+          for (int t = 0; t < 9; ++t) {
+            uint32_t wb;
+            if (p.w_resident) {
+              if (first) { mbar_wait(wfull(t), 0u, p.error, 25); tc_fence_after(); }
+              wb = wring + t * 8192;
+            } else {
+              mbar_wait(wfull(ws), wphase, p.error, 25);
+              tc_fence_after();
+              wb = wring + ws * 8192;
+            }
+            const int r = t / 3, s = t - r * 3;
+            const uint64_t da = umma_desc(wb, 1024);                                              // 64 channels x 64 K
+            const uint64_t db = umma_desc(hb + (uint32_t)((r * kHaloW + s) * 128), kHaloW * 128);   // 256 pixels, shifted view
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (c | t | k) ? 1u : 0u);
+            if (!p.w_resident) {
+              tc_commit(wempty(ws));
+              if (++ws == kTWStages) { ws = 0; wphase ^= 1u; }
+            }
+          }
+          tc_commit(hempty(hs));
+          if (++hs == 2) { hs = 0; hphase ^= 1u; }
+        }
+        tc_commit(tfull(as));
+        first = false;
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================================================================= epilogue: warp ew owns channels 16 ew .. 16 ew + 15
+    const int ew = warp - 4;
+    const int ch = ew * 16 + (lane & 15);
+    const bool active = lane < 16;
+    const float bias_v = (p.bias && active) ? __ldg(p.bias + ch) : 0.f;
+    const bool elected = (warp == 4 && lane == 0);
+    const uint32_t ch_chunk = (uint32_t)(ch >> 3), ch_off = (uint32_t)((ch & 7) * 2);
+    bool pending = false;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      int img, y0, x0;
+      decode(tile, img, y0, x0);
+      const int as = it & 1;
+      mbar_wait(tfull(as), (it >> 1) & 1, p.error, 26);
+      tc_fence_after();
+      if (elected && pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // slab free again
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const uint32_t tmem_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * 256);
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {                         // 32 pixels per TMEM load
+        uint32_t v[32];
+        tc_ld32(tmem_row + (uint32_t)(c * 32), v);
+        if (active) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(v[j]) + bias_v;
+            if (p.relu) x = fmaxf(x, 0.f);
+            const uint32_t pix = (uint32_t)(c * 32 + j);
+            const uint32_t addr = slab + pix * 128u + ((ch_chunk ^ (pix & 7u)) << 4) + ch_off;
+            if (p.dtype == DH_BF16) {
+              const __nv_bfloat16 hv = __float2bfloat16_rn(x);
+              asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const unsigned short*>(&hv)) : "memory");
+            } else {
+              const __half hv = __float2half_rn(x);
+              asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const unsigned short*>(&hv)) : "memory");
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(as));               // the accumulator is drained
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (elected) {
+        // slab rows are the tile's pixels in (y, x) order: two boxes {64 channels, 8, 16, 1}
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                         reinterpret_cast<uint64_t>(&map_y)),
+                     "r"(slab), "r"(0), "r"(x0), "r"(y0), "r"(img)
+                     : "memory");
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                         reinterpret_cast<uint64_t>(&map_y)),
+                     "r"(slab + 128u * 128u), "r"(0), "r"(x0), "r"(y0 + 16), "r"(img)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        pending = true;
+      }
+    }
+    if (elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -409,6 +617,22 @@ int launch_halo(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap&
   return DH_OK;
 }
 
+int launch_halo_t(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, HaloParams& p, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    DH_CUDA(cudaFuncSetAttribute(conv3x3_halo_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes));
+    attr = true;
+  }
+  p.n_blocks = 1;
+  p.tiles_y = dh_cdiv(p.H, 32);
+  p.w_resident = p.c_chunks == 1 ? 1 : 0;
+  const int tiles = p.n * p.tiles_y * p.tiles_x;
+  const int grid = tiles < g_sms ? tiles : g_sms;
+  conv3x3_halo_t_kernel<<<grid, kThreads, kTSmemBytes, s>>>(mx, mw, my, p);
+  DH_LAUNCH_OK();
+  return DH_OK;
+}
+
 }  // namespace
 
 // x [n,H,W,Cin] NHWC, w [Cout][3][3][Cin] (BN folded), y [n,H,W,Cout]; all dtype (DH_F16 / DH_BF16); Cin % 64 == 0,
@@ -427,7 +651,9 @@ extern "C" int dh_conv3x3_halo_tc(const void* x, const void* w, const float* bia
   p.tiles_x = dh_cdiv(W, 8); p.tiles_y = dh_cdiv(H, 16); p.c_chunks = Cin / 64;
   p.bias = bias; p.relu = relu; p.dtype = dtype; p.error = g_error;
   CUtensorMap mx, mw, my;
-  rc = map_nhwc(&mx, x, n, H, W, Cin, kHaloW, kHaloH, dtype);
+  static const bool transposed_ok = !getenv("DH_NO_HALO_T");
+  const bool transposed = transposed_ok && Cout == 64;          // channels as the UMMA M, 256 pixels as N
+  rc = map_nhwc(&mx, x, n, H, W, Cin, kHaloW, transposed ? kTHaloH : kHaloH, dtype);
   if (rc) return rc;
   rc = map_nhwc(&my, y, n, H, W, Cout, 8, 16, dtype);
   if (rc) return rc;
@@ -443,5 +669,6 @@ extern "C" int dh_conv3x3_halo_tc(const void* x, const void* w, const float* bia
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return dh_fail(DH_ERR_ARG, "cuTensorMapEncodeTiled rejected the weights", __FILE__, __LINE__);
   }
+  if (transposed) return launch_halo_t(mx, mw, my, p, stream);
   return bn == 128 ? launch_halo<128>(mx, mw, my, p, stream) : launch_halo<64>(mx, mw, my, p, stream);
 }
