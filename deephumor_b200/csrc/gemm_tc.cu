@@ -332,14 +332,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int j = 0; j < p.res_chunks; ++j) {
           mbar_wait(empty_bar(stage), phase ^ 1u, p.error, 1);
           const uint32_t sa = ring + stage * C::kStageBytes, sb = sa + BM * BK * 2;
-          if (cta_rank == 0) mbar_expect_tx(full_bar(stage), C::kStageBytes * CG);
           if (PAIR) {
+            if (cta_rank == 0) mbar_expect_tx(full_bar(stage), C::kStageBytes * CG);
             const uint32_t fb = mapa_u32(full_bar(stage), 0);
             tma_load_2d_pair(sa, &map_r, fb, n0 + j * BK, m0l);
             tma_load_2d_pair(sb, &map_i, fb, j * BK, (int)cta_rank * (BN / CG));
           } else {
+            // single CTA: the chunk's B operand is just the 64 x 64 identity (8 KB, not BN x 64 of mostly zeros); its MMAs
+            // write accumulator columns 64 j .. 64 j + 63 with N = 64
+            mbar_expect_tx(full_bar(stage), BM * BK * 2 + 64 * BK * 2);
             tma_load_2d(sa, &map_r, full_bar(stage), n0 + j * BK, m0l);
-            tma_load_2d(sb, &map_i, full_bar(stage), j * BK, 0);
+            tma_load_2d(sb, &map_i, full_bar(stage), 0, 0);
           }
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
@@ -349,6 +352,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0 && cta_rank == 0) {
       // ===================================================================== MMA issuer (the pair's leader CTA only)
       const uint32_t idesc = umma_idesc(BN, p.ab_dtype, BM * CG);
+      const uint32_t idesc64 = umma_idesc(64, p.ab_dtype, BM);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -363,10 +367,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tc_fence_after();
           const uint32_t sa = ring + stage * C::kStageBytes, sb = sa + BM * BK * 2;
           const uint64_t da = umma_desc(sa), db = umma_desc(sb);
+          if (!PAIR && kc >= p.k_chunks) {
+            // residual chunk j: D[:, 64 j .. 64 j + 63] += R[:, n0 + 64 j ..] x I64^T
+            const uint32_t td = tmem_d + (uint32_t)((kc - p.k_chunks) * 64);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {  // +32 B per UMMA_K step inside the 128 B swizzle row
-            if (PAIR) tc_mma_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
-            else tc_mma(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) tc_mma(td, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc64, 1u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {  // +32 B per UMMA_K step inside the 128 B swizzle row
+              if (PAIR) tc_mma_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
+              else tc_mma(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
+            }
           }
           // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
           if (PAIR) tc_commit_pair(empty_bar(stage)); else tc_commit(empty_bar(stage));
@@ -925,7 +936,7 @@ int dispatch(const CUtensorMap& ma, const void* W, long long ldw, TcParams& p, i
     if (p.res) {
       rc = make_map_2d(&mr, p.res, p.M, p.N, p.ldr, BM, p.ab_dtype);
       if (rc) return rc;
-      rc = make_map_2d(&mi, g_identity[p.ab_dtype], 256, 256, 256, b_rows, p.ab_dtype);
+      rc = make_map_2d(&mi, g_identity[p.ab_dtype], 256, 256, 256, pair ? b_rows : 64, p.ab_dtype);
       if (rc) return rc;
       p.res_chunks = 1;   // launch<> sets BN / 64
     }
