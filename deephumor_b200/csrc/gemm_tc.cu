@@ -26,6 +26,7 @@ constexpr int BM = 128, BK = 64;
 constexpr int kThreads = 384;            // warps 0-2 producer / MMA / TMEM, 4-7 epilogue, 8-11 second epilogue group
 constexpr int kStageLd = 36;             // floats per staged row (32 + 4: conflict-free for 16 B accesses)
 constexpr int kSmemBudget = 196608;      // bytes of A/B ring
+constexpr int kMaxLayers = 8;            // LSTM layers one dh_lstm_stack_tc launch can chain
 
 struct TcParams {
   int M, N, K;
@@ -51,6 +52,15 @@ struct TcParams {
   // LSTM cell epilogue (epi_mode 3, dh_lstm_layer_tc): the N axis is packed per 64 hidden units as [i | f | g | o]
   const float* c_prev; const int* parent; float* c_out;            // [*, H] fp32, parent[M] (nullable), [M, H] fp32
   void* h0; long long ldh0; void* h1; long long ldh1; int H;       // bf16 h to up to two destinations
+  // Multi-layer LSTM step in ONE launch (dh_lstm_stack_tc): tiles are ordered layer-major and walked in that order by every
+  // CTA; the tiles of layer l > 0 covering rows [m0, m0 + 128) load their x half only after ready[(l-1) * mb128 + m0 / 128]
+  // has reached n_blocks, i.e. every N tile of the layer below has stored h for those rows.  layers <= 1: plain single layer.
+  int layers, tiles_per_layer, mb128;
+  int a_layer_rows, w_layer_rows;                                  // row offset of layer l in the stacked A / Wp tensor maps
+  int kch_l[kMaxLayers], rot_l[kMaxLayers];                        // K chunks of layer l; chunk the K loop starts from
+  const float* bias_l[kMaxLayers]; const float* cprev_l[kMaxLayers]; float* cout_l[kMaxLayers];
+  void* h0_l[kMaxLayers]; long long ldh0_l[kMaxLayers]; void* h1_l[kMaxLayers]; long long ldh1_l[kMaxLayers];
+  int* ready;
 };
 
 // ------------------------------------------------------------------------------------------- PTX wrappers
@@ -130,8 +140,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Default semantics (release at CTA scope), as CUTLASS' ClusterBarrier::arrive: an explicit .release.cluster compiles to
+// MEMBAR.ALL.GPU and stalls the epilogue warp until all of its earlier global stores have drained (ncu: 25 % of the LSTM
+// epilogue); the TMEM hand-off itself is ordered by tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {   // arrives on `bar` in BOTH CTAs of the pair
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
@@ -193,6 +206,32 @@ __device__ __forceinline__ float tanh_fast(float x) {
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ int dh_cdiv_dev(int a, int b) { return (a + b - 1) / b; }
+
+// Cross-CTA hand-off of LSTM layer outputs inside one launch: the writer's epilogue stores h with ordinary (generic-proxy)
+// stores, fences, and bumps a counter with release semantics; the reader's TMA producer spins with acquire loads and then
+// orders its async-proxy (TMA) reads after them.
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void wait_ready(const int* flag, int target, int* error) {
+  if (ld_acquire_gpu(flag) >= target) { fence_proxy_async_all(); return; }
+  const long long t0 = clock64();
+  while (ld_acquire_gpu(flag) < target) {
+    __nanosleep(64);
+    if (clock64() - t0 > 4000000000ll) {
+      if (error) atomicExch(error, 5);
+      __threadfence_system();
+      __trap();
+    }
+  }
+  fence_proxy_async_all();
+}
 
 // K-major, 128B-swizzled operand tile (rows of 64 bf16 = 128 B, 8-row atoms of 1024 B):
 // start address >> 4 | SBO = 1024 B (bits 32..45) | descriptor version 1 (bits 46..47) | SWIZZLE_128B (bits 61..63).
@@ -277,7 +316,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_word);
   // tile = (M block of BM * CG rows, N block); a CTA pair walks the tiles together, CTA `rank` owning rows +rank * BM
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
-  const int tiles = p.m_blocks * p.n_blocks;
+  const int tiles = p.m_blocks * p.n_blocks * ((EPI == 3 && p.layers > 1) ? p.layers : 1);
   const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tstride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   auto tile_m0 = [&](int tile) { return (tile / p.n_blocks) * (BM * CG) + (int)cta_rank * BM; };
@@ -288,7 +327,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < tiles; tile += tstride) {
-        const int m0 = tile_m0(tile), n0 = (tile % p.n_blocks) * BN * p.n_stride;
+        int layer = 0, rt = tile;                                // EPI 3: layer-major tile order of a stacked LSTM step
+        if (EPI == 3 && p.layers > 1) { layer = tile / p.tiles_per_layer; rt = tile - layer * p.tiles_per_layer; }
+        const int m0 = tile_m0(rt), n0 = (rt % p.n_blocks) * BN * p.n_stride;
         // an M block past the end (odd block count, second CTA of the last pair) re-loads the last valid block: its
         // accumulator is never stored, and every TMA coordinate stays inside the tensor
         const int m0l = min(m0, (dh_cdiv_dev(p.M, BM) - 1) * BM);
@@ -299,8 +340,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           ph = rem / p.Wo;
           qw = rem - ph * p.Wo;
         }
-        const int nb0 = n0 + (int)cta_rank * (BN / CG);          // this CTA's slice of the W tile
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
+        const int a_row = m0l + ((EPI == 3 && p.layers > 1) ? layer * p.a_layer_rows : 0);
+        const int nb0 = n0 + (int)cta_rank * (BN / CG) +         // this CTA's slice of the W tile
+                        ((EPI == 3 && p.layers > 1) ? layer * p.w_layer_rows : 0);
+        const int kch = (EPI == 3 && p.layers > 1) ? p.kch_l[layer] : p.k_chunks;
+        const int rot = (EPI == 3 && p.layers > 1) ? p.rot_l[layer] : 0;
+        for (int j = 0; j < kch; ++j) {
+          // a stacked layer starts its K loop at the recurrent half (chunk rot), which is ready at launch, and reaches
+          // the x half -- written by the layer below during this launch -- last
+          int kc = j + rot;
+          if (kc >= kch) kc -= kch;
+          if (EPI == 3 && layer > 0 && kc == 0) wait_ready(p.ready + (layer - 1) * p.mb128 + (m0l >> 7), p.n_blocks, p.error);
           mbar_wait(empty_bar(stage), phase ^ 1u, p.error, 1);
           const uint32_t sa = ring + stage * C::kStageBytes, sb = sa + BM * BK * 2;
           if (cta_rank == 0) mbar_expect_tx(full_bar(stage), C::kStageBytes * CG);
@@ -312,7 +362,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               tma_load_im2col_pair(sa, &map_a, fb, c0, qw * p.stride - p.pad, ph * p.stride - p.pad, img, (uint16_t)s,
                                    (uint16_t)r);
             } else {
-              tma_load_2d_pair(sa, &map_a, fb, kc * BK, m0l);
+              tma_load_2d_pair(sa, &map_a, fb, kc * BK, a_row);
             }
             tma_load_2d_pair(sb, &map_b, fb, kc * BK, nb0);
           } else {
@@ -322,7 +372,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               tma_load_im2col(sa, &map_a, full_bar(stage), c0, qw * p.stride - p.pad, ph * p.stride - p.pad, img,
                               (uint16_t)s, (uint16_t)r);
             } else {
-              tma_load_2d(sa, &map_a, full_bar(stage), kc * BK, m0l);
+              tma_load_2d(sa, &map_a, full_bar(stage), kc * BK, a_row);
             }
             tma_load_2d(sb, &map_b, full_bar(stage), kc * BK, nb0);
           }
@@ -361,7 +411,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_wait(tempty_bar(as), ((it >> 1) & 1) ^ 1u, p.error, 2);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-        const int chunks = p.k_chunks + p.res_chunks;
+        const int chunks = ((EPI == 3 && p.layers > 1) ? p.kch_l[tile / p.tiles_per_layer] : p.k_chunks) + p.res_chunks;
         for (int kc = 0; kc < chunks; ++kc) {
           mbar_wait(full_bar(stage), phase, p.error, 3);
           tc_fence_after();
@@ -398,37 +448,60 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int row_l = ew * 32 + lane;
         int it = 0;
         for (int tile = tile0; tile < tiles; tile += tstride, ++it) {
-          const int m0 = tile_m0(tile), n0 = (tile % p.n_blocks) * BN * p.n_stride;
+          int layer = 0, rt = tile;
+          if (p.layers > 1) { layer = tile / p.tiles_per_layer; rt = tile - layer * p.tiles_per_layer; }
+          const int m0 = tile_m0(rt), n0 = (rt % p.n_blocks) * BN * p.n_stride;
+          const bool stack = p.layers > 1;
+          const float* bias = stack ? p.bias_l[layer] : p.bias;
+          const float* c_prev = stack ? p.cprev_l[layer] : p.c_prev;
+          float* c_out = stack ? p.cout_l[layer] : p.c_out;
+          void* h0 = stack ? p.h0_l[layer] : p.h0;
+          void* h1 = stack ? p.h1_l[layer] : p.h1;
+          const long long ldh0 = stack ? p.ldh0_l[layer] : p.ldh0, ldh1 = stack ? p.ldh1_l[layer] : p.ldh1;
           const int as = it & 1;
-          mbar_wait(tfull_bar(as), (it >> 1) & 1, p.error, 4);
-          tc_fence_after();
-          const uint32_t tmem_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          for (int i = etid; i < BN; i += 256) bias_s[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          // Everything that does not depend on the accumulator is issued BEFORE the wait on it: the bias slice (double
+          // buffered in the idle store-staging area: one barrier per tile, the readers of this buffer finished two tiles
+          // ago), the beam-parent index and the thread's 32 previous cell values.
+          float* bias_t = staging + (it & 1) * BN;
+          for (int i = etid; i < BN; i += 256) bias_t[i] = bias ? __ldg(bias + n0 + i) : 0.f;
           const long long row = (long long)m0 + row_l;
           const bool row_ok = row < p.M;
           const int unit0 = (n0 >> 8) * 64;
           const long long prow = row_ok ? (p.parent ? (long long)__ldg(p.parent + row) : row) : 0;
-          const float* cp = p.c_prev ? p.c_prev + prow * p.H + unit0 : nullptr;
-#pragma unroll 1
-          for (int u0 = eh * 32; u0 < eh * 32 + 32; u0 += 16) {
+          float4 cpv[8];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) cpv[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row_ok && c_prev) {
+            const float4* cp = reinterpret_cast<const float4*>(c_prev + prow * p.H + unit0 + eh * 32);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) cpv[g] = __ldg(cp + g);
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          mbar_wait(tfull_bar(as), (it >> 1) & 1, p.error, 4);
+          tc_fence_after();
+          const uint32_t tmem_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int u0 = eh * 32 + half * 16;
             uint32_t vi[16], vf[16], vg[16], vo[16];
             tc_ld16(tmem_row + (uint32_t)u0, vi);
             tc_ld16(tmem_row + (uint32_t)(64 + u0), vf);
             tc_ld16(tmem_row + (uint32_t)(128 + u0), vg);
             tc_ld16(tmem_row + (uint32_t)(192 + u0), vo);
+            tc_wait_ld();
+            if (half == 1) {
+              // the accumulator now lives in registers: hand the TMEM buffer back to the MMA warp before the cell math
+              // and the global stores (a release here would wait for those stores to drain)
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar(as), 0)); else mbar_arrive(tempty_bar(as)); }
+            }
             float cprev[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) cprev[j] = 0.f;
-            if (row_ok && cp) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const float4 c4 = __ldg(reinterpret_cast<const float4*>(cp + u0) + g);
-                cprev[4 * g] = c4.x; cprev[4 * g + 1] = c4.y; cprev[4 * g + 2] = c4.z; cprev[4 * g + 3] = c4.w;
-              }
+            for (int g = 0; g < 4; ++g) {
+              const float4 c4 = cpv[half * 4 + g];
+              cprev[4 * g] = c4.x; cprev[4 * g + 1] = c4.y; cprev[4 * g + 2] = c4.z; cprev[4 * g + 3] = c4.w;
             }
-            tc_wait_ld();
             float c2[16];
             uint32_t hw[8];
 #pragma unroll
@@ -436,10 +509,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               float h2[2];
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
-                const float gi = __uint_as_float(vi[j + e]) + bias_s[u0 + j + e];
-                const float gf = __uint_as_float(vf[j + e]) + bias_s[64 + u0 + j + e];
-                const float gg = __uint_as_float(vg[j + e]) + bias_s[128 + u0 + j + e];
-                const float go = __uint_as_float(vo[j + e]) + bias_s[192 + u0 + j + e];
+                const float gi = __uint_as_float(vi[j + e]) + bias_t[u0 + j + e];
+                const float gf = __uint_as_float(vf[j + e]) + bias_t[64 + u0 + j + e];
+                const float gg = __uint_as_float(vg[j + e]) + bias_t[128 + u0 + j + e];
+                const float go = __uint_as_float(vo[j + e]) + bias_t[192 + u0 + j + e];
                 // MUFU.TANH (rel. error 2^-11, far inside the bf16 rounding of h): sigmoid(x) = 0.5 + 0.5 tanh(x / 2)
                 const float si = fmaf(0.5f, tanh_fast(0.5f * gi), 0.5f), sf = fmaf(0.5f, tanh_fast(0.5f * gf), 0.5f);
                 const float so = fmaf(0.5f, tanh_fast(0.5f * go), 0.5f);
@@ -455,24 +528,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               }
             }
             if (row_ok) {
-              float4* co = reinterpret_cast<float4*>(p.c_out + row * p.H + unit0 + u0);
+              float4* co = reinterpret_cast<float4*>(c_out + row * p.H + unit0 + u0);
 #pragma unroll
               for (int g = 0; g < 4; ++g) co[g] = make_float4(c2[4 * g], c2[4 * g + 1], c2[4 * g + 2], c2[4 * g + 3]);
-              if (p.h0) {
-                uint4* d = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.h0) + row * p.ldh0 + unit0 + u0);
+              if (h0) {
+                uint4* d = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(h0) + row * ldh0 + unit0 + u0);
                 d[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                 d[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
               }
-              if (p.h1) {
-                uint4* d = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.h1) + row * p.ldh1 + unit0 + u0);
+              if (h1) {
+                uint4* d = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(h1) + row * ldh1 + unit0 + u0);
                 d[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                 d[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
               }
             }
           }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar(as), 0)); else mbar_arrive(tempty_bar(as)); }
+          if (stack && layer + 1 < p.layers) {
+            // publish this tile's h rows to the layer above: every thread's stores are fenced (and ordered against the
+            // consumer's async-proxy reads), then one release increment per tile
+            __threadfence();
+            fence_proxy_async_all();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (etid == 0 && m0 < p.M) {
+              __threadfence();
+              red_release_gpu(p.ready + layer * p.mb128 + (m0 >> 7), 1);
+            }
+          }
         }
       }
     } else if (EPI) {
@@ -869,7 +950,9 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, 
   if (p.n_stride < 1) p.n_stride = 1;
   p.n_blocks = dh_cdiv(dh_cdiv(p.N, BN), p.n_stride);
   p.m_blocks = dh_cdiv(p.M, PAIR ? 2 * BM : BM);
-  const int tiles = p.m_blocks * p.n_blocks;
+  p.tiles_per_layer = p.m_blocks * p.n_blocks;
+  p.mb128 = dh_cdiv(p.M, BM);
+  const int tiles = p.tiles_per_layer * ((EPI == 3 && p.layers > 1) ? p.layers : 1);
   if (p.res_chunks) p.res_chunks = BN / BK;
   if (PAIR) {
     const int pairs = g_num_sms / 2;
@@ -917,7 +1000,8 @@ int dispatch(const CUtensorMap& ma, const void* W, long long ldw, TcParams& p, i
   // the ResNet-50 / decoder shapes (profiles/), pairs win 6-30 % at K >= 1024 and lose 8-50 % on short-K, store-bound tiles
   const bool pair = pair_ok && bn >= 128 && p.M > BM && p.k_chunks + (p.res ? bn / BK : 0) >= 16;
   const int b_rows = pair ? bn / 2 : bn;                   // W rows one CTA stages per K chunk
-  int rc = make_map_2d(&mb, W, p.N, p.K, ldw, b_rows, p.ab_dtype);
+  const long long w_rows = (p.epi_mode == 3 && p.layers > 1) ? (long long)p.layers * p.w_layer_rows : p.N;
+  int rc = make_map_2d(&mb, W, w_rows, p.K, ldw, b_rows, p.ab_dtype);
   if (rc) return rc;
   p.error = g_error_flag;
   // TMA-store epilogue when the output rows are 16 B aligned; the residual then rides the tensor core (R x I) if it
@@ -1032,6 +1116,68 @@ extern "C" int dh_lstm_layer_tc(const void* A, long long lda, const void* Wp, lo
   p.h0 = h_out0; p.ldh0 = ldh0; p.h1 = h_out1; p.ldh1 = ldh1; p.H = H;
   CUtensorMap ma;
   rc = make_map_2d(&ma, A, rows, K, lda, BM, ab_dtype);
+  if (rc) return rc;
+  return dispatch(ma, Wp, ldw, p, 256, stream);
+}
+
+// All layers of an nn.LSTM time step in ONE persistent launch (rnn_models.py:80,108 with num_layers > 1): the tiles of the
+// layers are queued layer-major on the same CTAs, and a tile of layer l starts its K loop on the recurrent half of its
+// operand while the layer below is still running; it reaches the x half once the per-128-row counter says those rows of
+// h_{l-1} are stored.  Replaces `layers` dependent launches (each with its own tail wave) by one.
+extern "C" int dh_lstm_stack_tc(void* A, long long lda, long long a_layer_rows, const int* in_dims_host, const void* Wp,
+                                long long ldw, int ab_dtype, const float* bias_p, const float* c_prev, const int* parent,
+                                float* c_out, long long c_layer_stride, void* h_top, long long ld_top, void* hs,
+                                long long hs_layer_stride, int* ready, int rows, int H, int layers, int rotate_k,
+                                cudaStream_t stream) {
+  DH_ARG(A && in_dims_host && Wp && c_out && ready && rows >= 0 && H > 0 && H % 64 == 0);
+  DH_ARG(layers >= 1 && layers <= kMaxLayers && a_layer_rows >= rows);
+  DH_ARG(lda % 8 == 0 && ldw % 8 == 0 && c_layer_stride % 4 == 0 && hs_layer_stride % 8 == 0);
+  DH_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)Wp % 16) == 0 && ((uintptr_t)c_out % 16) == 0);
+  DH_ARG(!c_prev || ((uintptr_t)c_prev % 16) == 0);
+  DH_ARG(h_top && ((uintptr_t)h_top % 16) == 0 && ld_top % 8 == 0);
+  DH_ARG(!hs || ((uintptr_t)hs % 16) == 0);
+  DH_ARG(ab_dtype == DH_BF16 || ab_dtype == DH_F16);
+  DH_ARG((long long)layers * a_layer_rows < (1ll << 31));
+  if (rows == 0) return DH_OK;
+  int rc = tc_init();
+  if (rc) return rc;
+  TcParams p{};
+  int kmax = 0;
+  for (int l = 0; l < layers; ++l) {
+    const int in_l = in_dims_host[l], K_l = in_l + H;
+    DH_ARG(in_l > 0 && K_l % 8 == 0 && K_l <= lda && K_l <= ldw);
+    DH_ARG(l == 0 || in_l == H);                       // layer l > 0 consumes the H-wide h of the layer below
+    p.kch_l[l] = dh_cdiv(K_l, BK);
+    // start at the recurrent half when the x | h boundary falls on a chunk boundary
+    p.rot_l[l] = (rotate_k && l > 0 && in_l % BK == 0) ? in_l / BK : 0;
+    p.bias_l[l] = bias_p ? bias_p + (long long)l * 4 * H : nullptr;
+    p.cprev_l[l] = c_prev ? c_prev + l * c_layer_stride : nullptr;
+    p.cout_l[l] = c_out + l * c_layer_stride;
+    if (l + 1 < layers) {                              // x half of the next layer's operand
+      p.h0_l[l] = reinterpret_cast<uint16_t*>(A) + (long long)(l + 1) * a_layer_rows * lda;
+      p.ldh0_l[l] = lda;
+    } else {
+      p.h0_l[l] = h_top;
+      p.ldh0_l[l] = ld_top;
+    }
+    p.h1_l[l] = hs ? reinterpret_cast<uint16_t*>(hs) + l * hs_layer_stride : nullptr;
+    p.ldh1_l[l] = H;
+    kmax = K_l > kmax ? K_l : kmax;
+  }
+  p.M = rows; p.N = 4 * H; p.K = kmax;
+  p.k_chunks = dh_cdiv(kmax, BK);
+  p.ab_dtype = ab_dtype;
+  p.out_dtype = ab_dtype;
+  p.epi_mode = 3;
+  p.parent = parent; p.H = H;
+  p.layers = layers; p.a_layer_rows = (int)a_layer_rows; p.w_layer_rows = 4 * H;
+  p.ready = ready;
+  if (layers == 1) {                                   // plain single-layer launch
+    p.bias = p.bias_l[0]; p.c_prev = p.cprev_l[0]; p.c_out = p.cout_l[0];
+    p.h0 = p.h0_l[0]; p.ldh0 = p.ldh0_l[0]; p.h1 = p.h1_l[0]; p.ldh1 = p.ldh1_l[0];
+  }
+  CUtensorMap ma;
+  rc = make_map_2d(&ma, A, (long long)(layers - 1) * a_layer_rows + rows, kmax, lda, BM, ab_dtype);
   if (rc) return rc;
   return dispatch(ma, Wp, ldw, p, 256, stream);
 }

@@ -32,14 +32,26 @@ class LSTMDecoderRT:
         if self.fused_cell:
             self.Wpk = [ops.pack_lstm_gates(w, self.H) for w in self.Wcat]
             self.bpk = [ops.pack_lstm_gates(b, self.H) for b in self.bias]
+        # ... and, for num_layers > 1, one stacked copy so that a whole time step is a single persistent launch
+        self.in_dims = [self.E if l == 0 else self.H for l in range(self.L)]
+        self.Kmax = max(self.in_dims) + self.H
+        self.stacked = self.fused_cell and ops.LSTM_STACK and 1 < self.L <= 8 and self.Kmax % 8 == 0
+        if self.stacked:
+            self.Wpk_all = torch.zeros(self.L * 4 * self.H, self.Kmax, dtype=dtype, device=device)
+            for l, w in enumerate(self.Wpk):
+                self.Wpk_all[l * 4 * self.H:(l + 1) * 4 * self.H, :w.shape[1]] = w
+            self.bpk_all = torch.cat(self.bpk).contiguous()
         self.Wc, self.bc = to(sd[prefix + '.classifier.weight']), to(sd[prefix + '.classifier.bias'], torch.float32)
         self.ldv = (self.V + 3) // 4 * 4
         self._plans = {}
 
     def _alloc(self, rows, logits=True):
         d, dev, H, E, L = self.dtype, self.device, self.H, self.E, self.L
+        # layer l's operand [x | h_prev] lives in columns [0, in_l + H) of one stacked buffer (dh_lstm_stack_tc)
+        A_all = torch.zeros(L, rows, self.Kmax, dtype=d, device=dev)
         ws = dict(
-            A=[torch.zeros(rows, (E if l == 0 else H) + H, dtype=d, device=dev) for l in range(L)],
+            A_all=A_all, A=[A_all[l][:, :self.in_dims[l] + H] for l in range(L)],
+            ready=torch.zeros(1, dtype=torch.int32, device=dev), ready_next=0,
             gates=torch.empty(rows, 4 * H, dtype=torch.float32, device=dev),
             c=[torch.zeros(L, rows, H, dtype=torch.float32, device=dev) for _ in range(2)],
             hs=torch.zeros(L, rows, H, dtype=d, device=dev),
@@ -50,6 +62,19 @@ class LSTMDecoderRT:
     def _step(self, ws, rows, cur, parent, logits=True):
         """One LSTM time step over `rows` rows; A[l][:, in:] must already hold the (gathered) recurrent h."""
         L, H = self.L, self.H
+        if self.stacked:
+            # one zeroed counter region per launch (the decode zeroes the pool once, before its first step)
+            per = (L - 1) * ((rows + 127) // 128)
+            off = ws['ready_next']
+            assert off + per <= ws['ready'].numel(), 'ready-counter pool exhausted'
+            ws['ready_next'] = off + per
+            with ops.PROFILE.range('lstm_layers', sum(2.0 * rows * 4 * H * (i + H) for i in self.in_dims)):
+                ops.lstm_stack_tc(ws['A_all'], self.in_dims, self.Wpk_all, self.bpk_all, ws['c'][cur], parent,
+                                  ws['c'][1 - cur], ws['top'][:rows], ws['hs'], ws['ready'][off:off + per], rows)
+            if logits:
+                with ops.PROFILE.range('vocab_gemm', 2.0 * rows * self.V * H):
+                    ops.gemm(ws['top'][:rows], self.Wc, ws['logits'][:rows, :self.V], bias=self.bc)
+            return
         for l in range(L):
             A = ws['A'][l][:rows]
             nxt = ws['A'][l + 1][:rows, :H] if l + 1 < L else ws['top'][:rows]
@@ -98,6 +123,14 @@ class LSTMDecoderRT:
         beam.status.zero_()
         for c in ws['c']:
             c.zero_()
+        if self.stacked:
+            steps = p0 + 1 + max(0, max_len - p0 - 1)
+            need = steps * (self.L - 1) * ((max(R, N) + 127) // 128)
+            if ws['ready'].numel() < need:
+                assert not torch.cuda.is_current_stream_capturing()
+                ws['ready'] = torch.zeros(need, dtype=torch.int32, device=self.device)
+            ws['ready'].zero_()
+            ws['ready_next'] = 0
         # ---- prefix phase: 1 row per image (rnn_models.py:73-81)
         cur = 0
         ops.gather_rows(start_emb, None, ws['A'][0][:N, :self.E])

@@ -58,6 +58,8 @@ HALO_CONV = os.environ.get('DH_NO_HALO_CONV', '') == ''       # 3x3 stride-1 con
 HALO_COUT = 64
 FUSED_STEM = os.environ.get('DH_NO_FUSED_STEM', '') == ''     # conv1 + ReLU + maxpool in one tcgen05 kernel
 FUSED_LSTM = os.environ.get('DH_NO_FUSED_LSTM', '') == ''     # LSTM cell update in the gate GEMM's epilogue
+LSTM_STACK = os.environ.get('DH_NO_LSTM_STACK', '') == ''     # all LSTM layers of a step in one persistent launch
+LSTM_ROTATE = os.environ.get('DH_LSTM_ROTATE', '') != ''      # ... upper layers start on the recurrent half of K (measured: no gain)
 FUSED_VOCAB = os.environ.get('DH_NO_FUSED_VOCAB', '') == ''   # two-pass vocab projection, logits never stored
 
 
@@ -213,6 +215,32 @@ def lstm_layer_tc(A, Wp, bias_p, c_prev, parent, c_out, h_out0, h_out1):
     LIB.call('dh_lstm_layer_tc', ptr(A), _rows(A), ptr(Wp), _rows(Wp), code(A), ptr(bias_p), ptr(c_prev), ptr(parent),
              ptr(c_out), ptr(h_out0), 0 if h_out0 is None else _rows(h_out0), ptr(h_out1),
              0 if h_out1 is None else _rows(h_out1), rows, H, K, stream())
+
+
+def tc_error_flag():
+    """Watchdog code left by a tcgen05 kernel before it trapped (0 = none; dh_tc_error_flag)."""
+    import ctypes
+    out = ctypes.c_int(0)
+    LIB.call('dh_tc_error_flag', ctypes.byref(out))
+    return out.value
+
+
+def lstm_stack_tc(A_all, in_dims, Wp_all, bias_all, c_prev, parent, c_out, h_top, hs, ready, rows, rotate=None):
+    """Every layer of one LSTM time step in one persistent launch (dh_lstm_stack_tc): A_all [L, rows_alloc, Kmax] holds
+    layer l's [x | h_prev] in columns [0, in_l + H), Wp_all [L * 4H, Kmax] / bias_all [L * 4H] are gate-packed per layer
+    (zero past in_l + H), c_prev / c_out [L, rows_alloc, H] fp32, hs [L, rows_alloc, H]; `ready` is a zeroed int32 region
+    of (L - 1) * ceil(rows / 128) counters that the launch consumes."""
+    import ctypes
+    L, ra, Kmax = A_all.shape
+    H = Wp_all.shape[0] // (4 * L)
+    assert A_all.is_contiguous() and Wp_all.is_contiguous() and Wp_all.dtype == A_all.dtype and len(in_dims) == L
+    assert c_out.is_contiguous() and c_out.shape[0] == L and (c_prev is None or c_prev.shape == c_out.shape)
+    assert hs is None or (hs.is_contiguous() and hs.shape[0] == L and hs.dtype == A_all.dtype)
+    assert ready.dtype == torch.int32 and ready.numel() >= (L - 1) * ((rows + 127) // 128)
+    LIB.call('dh_lstm_stack_tc', ptr(A_all), Kmax, ra, (ctypes.c_int * L)(*in_dims), ptr(Wp_all), Wp_all.shape[1],
+             code(A_all), ptr(bias_all), ptr(c_prev), ptr(parent), ptr(c_out), c_out.stride(0), ptr(h_top), _rows(h_top),
+             ptr(hs), 0 if hs is None else hs.stride(0), ptr(ready), rows, H, L,
+             int(LSTM_ROTATE if rotate is None else rotate), stream())
 
 
 def lstm_prepare(table, tok, parent, hs, A, in_off, rows):

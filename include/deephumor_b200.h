@@ -24,7 +24,7 @@ extern "C" {
 typedef struct CUstream_st* cudaStream_t;
 #endif
 
-#define DH_VERSION 112
+#define DH_VERSION 113
 
 #define DH_OK 0
 #define DH_ERR_ARG (-1)
@@ -137,6 +137,19 @@ int dh_lstm_prepare(const void* table, long long ldt, long long n_tok_rows, cons
 int dh_lstm_layer_tc(const void* A, long long lda, const void* Wp, long long ldw, int ab_dtype, const float* bias_p,
                      const float* c_prev, const int* parent, float* c_out, void* h_out0, long long ldh0, void* h_out1,
                      long long ldh1, int rows, int H, int K, cudaStream_t stream);
+/* Every layer of one nn.LSTM time step in ONE persistent launch (rnn_models.py:23-24,80,108 with num_layers > 1).  Layer l
+ * computes what dh_lstm_layer_tc computes, on stacked operands: A [layers, a_layer_rows, lda] with layer l's [x | h_prev] in
+ * columns [0, in_l + H) (in_dims_host: HOST array; in_l == H for l > 0; columns past in_l + H must be zero in Wp), Wp
+ * [layers * 4H, ldw] and bias_p [layers * 4H] gate-packed per layer, c_prev / c_out [layers, *, H] fp32 with
+ * c_layer_stride elements between layers (c_prev rows read through parent[], shared by the layers), hs [layers, *, H]
+ * (nullable) receives every layer's h.  Layer l < layers-1 writes its h into the x half of A[l+1]; the top layer writes
+ * h_top [rows, ld_top].  Tiles are queued layer-major on the same CTAs; a tile of layer l > 0 starts on the recurrent half
+ * of its K loop (rotate_k != 0) and takes the x half once `ready` says the layer below has stored those 128 rows.
+ * ready: (layers - 1) * ceil(rows / 128) ints, ZERO on entry, left non-zero (one region per launch, or memset between). */
+int dh_lstm_stack_tc(void* A, long long lda, long long a_layer_rows, const int* in_dims_host, const void* Wp,
+                     long long ldw, int ab_dtype, const float* bias_p, const float* c_prev, const int* parent, float* c_out,
+                     long long c_layer_stride, void* h_top, long long ld_top, void* hs, long long hs_layer_stride,
+                     int* ready, int rows, int H, int layers, int rotate_k, cudaStream_t stream);
 /* out = LayerNorm(x + y), eps 1e-5 (transformers.py:360,368,375,627,634). y may be null. */
 int dh_add_layernorm(const void* x, long long ldx, const void* y, long long ldy, const float* gamma, const float* beta,
                      void* out, long long ldo, int rows, int D, int dtype, cudaStream_t stream);

@@ -28,3 +28,32 @@ gates = torch.empty(rows, 4 * H, device=dev)
 us2 = timeit(lambda: ops.gemm(A, W, gates, bias=b))
 print(f'plain gate GEMM (fp32 out): {us2:.1f} us')
 os.environ['X'] = '1'
+# ---- all layers of a time step in one persistent launch (dh_lstm_stack_tc) against L single-layer launches
+L = 3
+A_all = (torch.randn(L, rows, E + H, device=dev) * 0.3).to(torch.bfloat16)
+W_all = torch.cat([W] * L).contiguous()
+b_all = torch.cat([b] * L).contiguous()
+cc = [torch.randn(L, rows, H, device=dev) for _ in range(2)]
+hs = torch.empty(L, rows, H, dtype=torch.bfloat16, device=dev)
+top = torch.empty(rows, H, dtype=torch.bfloat16, device=dev)
+per = (L - 1) * ((rows + 127) // 128)
+pool = torch.zeros(64 * per, dtype=torch.int32, device=dev)
+state = {'i': 0}
+def stack(rot, layers=L):
+    i = state['i'] % 64
+    state['i'] += 1
+    if i == 0:
+        pool.zero_()
+    ops.lstm_stack_tc(A_all[:layers], [E] + [H] * (layers - 1), W_all[:layers * 4 * H], b_all[:layers * 4 * H], cc[0][:layers],
+                      parent, cc[1][:layers], top, hs[:layers], pool[i * per:(i + 1) * per], rows, rotate=rot)
+def three():
+    for l in range(L):
+        ops.lstm_layer_tc(A_all[l], W, b, cc[0][l], parent, cc[1][l], A_all[(l + 1) % L][:, :H], hs[l])
+print(f'{L} x lstm_layer_tc: {timeit(three):.1f} us')
+for rot in (0, 1):
+    state['i'] = 0
+    print(f'lstm_stack_tc L={L} rotate={rot}: {timeit(lambda: stack(rot)):.1f} us')
+state['i'] = 0
+print(f'lstm_stack_tc L=1: {timeit(lambda: stack(0, 1)):.1f} us')
+state['i'] = 0
+print(f'lstm_stack_tc L=2 rotate=1: {timeit(lambda: stack(1, 2)):.1f} us')

@@ -224,6 +224,61 @@ def test_lstm_layer_fused_cell_epilogue(rows, H_, in_, use_parent):
     assert H.rel_err(c1, cr) < 1e-3 and H.rel_err(h1b.float(), hr) < 5e-3
 
 
+@pytest.mark.parametrize('rows,H_,E_,L_,rotate', [(2560, 512, 512, 3, 1), (2560, 512, 512, 3, 0), (512, 512, 512, 3, 1),
+                                                 (300, 128, 64, 2, 1), (37, 64, 32, 4, 1), (1100, 256, 320, 2, 0)])
+def test_lstm_stack_one_launch_equals_layer_by_layer(rows, H_, E_, L_, rotate):
+    """dh_lstm_stack_tc (all layers of a time step in one persistent launch, cross-CTA ready counters) against L
+    dh_lstm_layer_tc launches on the same operands: bit-identical with the natural K order, within fp32 summation-order
+    noise when the upper layers start on the recurrent half.  Three consecutive steps exercise the counter regions."""
+    g = torch.Generator().manual_seed(rows + L_)
+    ra = rows + 5                                              # allocation taller than the live rows
+    in_dims = [E_] + [H_] * (L_ - 1)
+    Kmax = max(in_dims) + H_
+    Ws = [(torch.randn(4 * H_, i + H_, generator=g) * 0.1).to(torch.bfloat16).to(DEV) for i in in_dims]
+    bs = [torch.randn(4 * H_, generator=g).to(DEV) for _ in in_dims]
+    Wp_all = torch.zeros(L_ * 4 * H_, Kmax, dtype=torch.bfloat16, device=DEV)
+    for l, w in enumerate(Ws):
+        Wp_all[l * 4 * H_:(l + 1) * 4 * H_, :w.shape[1]] = ops.pack_lstm_gates(w, H_)
+    b_all = torch.cat([ops.pack_lstm_gates(b, H_) for b in bs]).contiguous()
+    A_all = torch.zeros(L_, ra, Kmax, dtype=torch.bfloat16, device=DEV)
+    A_ref = [torch.zeros(ra, i + H_, dtype=torch.bfloat16, device=DEV) for i in in_dims]
+    c = [torch.zeros(L_, ra, H_, device=DEV) for _ in range(2)]
+    c_ref = [torch.zeros(L_, ra, H_, device=DEV) for _ in range(2)]
+    hs, hs_ref = (torch.zeros(L_, ra, H_, dtype=torch.bfloat16, device=DEV) for _ in range(2))
+    top, top_ref = (torch.zeros(ra, H_, dtype=torch.bfloat16, device=DEV) for _ in range(2))
+    per = (L_ - 1) * ((rows + 127) // 128)
+    ready = torch.zeros(3 * per, dtype=torch.int32, device=DEV)
+    cur = 0
+    for t in range(3):
+        x = (torch.randn(rows, E_, generator=g) * 0.5).to(torch.bfloat16).to(DEV)
+        parent = torch.randint(0, rows, (rows,), generator=g).to(torch.int32).to(DEV) if t else None
+        A_all[0, :rows, :E_] = x
+        A_ref[0][:rows, :E_] = x
+        for l in range(L_):                                    # recurrent halves: h of the previous step through parent
+            src, src_ref = hs[l, :rows], hs_ref[l, :rows]
+            if parent is not None:
+                src, src_ref = src[parent.long()], src_ref[parent.long()]
+            A_all[l, :rows, in_dims[l]:in_dims[l] + H_] = src
+            A_ref[l][:rows, in_dims[l]:] = src_ref
+        ops.lstm_stack_tc(A_all, in_dims, Wp_all, b_all, c[cur], parent, c[1 - cur], top[:rows], hs,
+                          ready[t * per:(t + 1) * per], rows, rotate=rotate)
+        for l in range(L_):
+            nxt = A_ref[l + 1][:rows, :H_] if l + 1 < L_ else top_ref[:rows]
+            ops.lstm_layer_tc(A_ref[l][:rows], ops.pack_lstm_gates(Ws[l], H_), ops.pack_lstm_gates(bs[l], H_), c_ref[cur][l],
+                              parent, c_ref[1 - cur][l][:rows], nxt, hs_ref[l][:rows])
+        cur = 1 - cur
+        torch.cuda.synchronize()
+        if rotate:
+            assert H.rel_err(c[cur][:, :rows], c_ref[cur][:, :rows]) < 2e-3
+            assert H.rel_err(top[:rows].float(), top_ref[:rows].float()) < 8e-3
+            assert H.rel_err(hs[:, :rows].float(), hs_ref[:, :rows].float()) < 8e-3
+        else:
+            assert torch.equal(c[cur][:, :rows], c_ref[cur][:, :rows])
+            assert torch.equal(top[:rows], top_ref[:rows]) and torch.equal(hs[:, :rows], hs_ref[:, :rows])
+    assert int(ready.min()) == (4 * H_) // 256 and int(ready.max()) == (4 * H_) // 256
+    assert ops.tc_error_flag() == 0
+
+
 def test_fused_stem_from_uint8_pixels_is_bit_identical_to_the_float_path():
     """uint8 input: ToTensor + Normalize fused into the stem's band loader give exactly the features of the float
     path fed with torchvision-style preprocessed images (same fp32 operation order)."""
