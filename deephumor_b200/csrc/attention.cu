@@ -354,6 +354,217 @@ __global__ void __launch_bounds__(128) attn_mma_kernel(AttnParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ streaming path
+// Cross-attention during generation is a pure HBM stream: every decode step re-reads the 49 cached spatial K/V rows of every
+// image (2 x 49 x D bf16 = 100 KB per image and layer, far more than L2 holds for a batch), and does ~1 MFLOP per image on
+// them.  One persistent CTA per SM walks the images; a producer warp fetches an image's K and V rows with 1-D bulk copies
+// (cp.async.bulk, one per key row, completion on an mbarrier) into a ring of stages while eight consumer warps -- one per
+// head -- run the two small mma.sync products of the previous image.  Rows are staged with a pitch of D + 8 elements so
+// that ldmatrix is conflict-free; key rows past n_keys read a shared zero row.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init_(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000ll) __trap();      // a protocol bug must fail the launch, not hang the GPU
+  }
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ uint32_t movm_trans(uint32_t x) {     // 8x8 b16 transpose across the warp
+  uint32_t y;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+
+constexpr int kStreamWarps = 8;       // consumer warps (one head each)
+constexpr int kLoadWarps = 4;         // producer warps: a bulk copy is issued lane by lane (~60 cycles each), so the ~100
+                                      // copies of an image are spread over four warps to stay ahead of HBM
+
+template <int NKT>
+__global__ void __launch_bounds__((kStreamWarps + kLoadWarps) * 32, 1) attn_stream_kernel(AttnParams p, int n_img, int stages) {
+  extern __shared__ __align__(128) unsigned char smem_stream[];
+  const int nk = p.n_keys, D = p.D;
+  const uint32_t pitch = (uint32_t)(D + 8) * 2u;                 // bytes per staged key row
+  const uint32_t half_stage = (uint32_t)nk * pitch;              // K rows, then V rows
+  const uint32_t stage_bytes = 2u * half_stage;
+  const uint32_t s_base = smem_addr(smem_stream);
+  const uint32_t zero_row = s_base + (uint32_t)stages * stage_bytes;                   // pitch bytes of zeros
+  const uint32_t bars = zero_row + ((pitch + 15u) & ~15u);                             // full[stages], empty[stages]
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (uint32_t i = threadIdx.x * 4u; i < pitch; i += blockDim.x * 4u)
+    *reinterpret_cast<uint32_t*>(smem_stream + (size_t)stages * stage_bytes + i) = 0u;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init_(bars + 8u * s, 1);
+      mbar_init_(bars + 8u * (stages + s), kStreamWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long img_stride = (long long)p.slots * p.S_alloc * D;      // elements between images in K / V (slot 0 is used)
+  if (w >= kStreamWarps) {
+    // ===================================================================== producers: one bulk copy per key row
+    const int pw = w - kStreamWarps;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int img = blockIdx.x; img < n_img; img += gridDim.x) {
+      mbar_wait_(bars + 8u * (stages + stage), phase ^ 1u);
+      // the transaction count may run ahead of this expect_tx (other producer warps): the phase cannot complete before
+      // the single arrival it carries
+      if (pw == 0 && lane == 0) mbar_expect_tx_(bars + 8u * stage, 2u * (uint32_t)nk * (uint32_t)D * 2u);
+      const __nv_bfloat16* Kg = (const __nv_bfloat16*)p.K + img * img_stride;
+      const __nv_bfloat16* Vg = (const __nv_bfloat16*)p.V + img * img_stride;
+      const uint32_t dst = s_base + (uint32_t)stage * stage_bytes;
+      for (int t = pw + kLoadWarps * lane; t < nk; t += kLoadWarps * 32) {        // rows interleaved over the warps
+        bulk_load(dst + (uint32_t)t * pitch, Kg + (long long)t * D, (uint32_t)D * 2u, bars + 8u * stage);
+        bulk_load(dst + half_stage + (uint32_t)t * pitch, Vg + (long long)t * D, (uint32_t)D * 2u, bars + 8u * stage);
+      }
+      if (++stage == stages) { stage = 0; phase ^= 1u; }
+    }
+    return;
+  }
+  // ======================================================================= consumers: warp w owns heads w, w + 8, ...
+  // The products are taken TRANSPOSED, S^T = K Q^T and O^T = V^T P^T, so that the 16-wide M side of mma.m16n8k16 runs over
+  // keys / head dims (always full) and the 8-wide N side over the image's query rows (beam <= 8 in one pass): half the MMAs
+  // and half the softmax work of the row-major form, whose 16 query rows would be 2/3 padding at beam 5.
+  const int g = lane >> 2, t4 = lane & 3;
+  const int mat = lane >> 3, l8 = lane & 7;
+  constexpr int MT = NKT / 2;                                     // 16-key tiles
+  const int q_groups = (p.rpi + 7) / 8;
+  const float inv_scale = 1.f / p.scale;
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int img = blockIdx.x; img < n_img; img += gridDim.x) {
+    // the image's encoder-key mask as a 64-bit word (bit t: key t masked), fetched before the wait on the stage
+    unsigned long long emask = 0ull;
+    if (p.enc_mask) {
+      const unsigned char* em = p.enc_mask + (long long)img * p.S_alloc;
+      const unsigned lo = __ballot_sync(0xffffffffu, lane < nk && em[lane] != 0);
+      const unsigned hi = __ballot_sync(0xffffffffu, lane + 32 < nk && em[lane + 32] != 0);
+      emask = ((unsigned long long)hi << 32) | lo;
+    }
+    const uint32_t sK_u = s_base + (uint32_t)stage * stage_bytes, sV_u = sK_u + half_stage;
+    bool waited = false;
+    for (int h = w; h < p.n_heads; h += kStreamWarps) {
+      for (int qg = 0; qg < q_groups; ++qg) {
+        // ---- Q^T as the B operand (dims x 8 queries), straight from global memory; queries past rpi are zero
+        const int qrow = qg * 8 + g;
+        const __nv_bfloat16* Qg = (const __nv_bfloat16*)p.q + ((long long)img * p.rpi + qrow) * p.ldq + h * 64 + 2 * t4;
+        uint32_t qb[4][2];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          qb[kk][0] = qrow < p.rpi ? __ldg(reinterpret_cast<const unsigned int*>(Qg + kk * 16)) : 0u;
+          qb[kk][1] = qrow < p.rpi ? __ldg(reinterpret_cast<const unsigned int*>(Qg + kk * 16 + 8)) : 0u;
+        }
+        if (!waited) { mbar_wait_(bars + 8u * stage, phase); waited = true; }
+        // ---- S^T = K Q^T: sacc[mt] = {(key g, query 2 t4), (key g, query 2 t4 + 1), (key g + 8, ...), (key g + 8, ...)}
+        float sacc[MT][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) { sacc[mt][0] = sacc[mt][1] = sacc[mt][2] = sacc[mt][3] = 0.f; }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const int key = mt * 16 + (mat & 1) * 8 + l8;
+            uint32_t a[4];     // (keys 0-7, dims lo), (keys 8-15, dims lo), (keys 0-7, dims hi), (keys 8-15, dims hi)
+            ldsm_x4((key < nk ? sK_u + (uint32_t)key * pitch : zero_row) + (uint32_t)(h * 64 + kk * 16 + (mat >> 1) * 8) * 2u, a);
+            mma_bf16(sacc[mt], a, qb[kk][0], qb[kk][1]);
+          }
+        }
+        // ---- scale, any-zero encoder mask (-1e8 as in the reference, transformers.py:111), softmax over the keys: a
+        // query's scores sit in the lanes of equal t4 (8 values of g) x MT x 2 registers
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+          for (int hi = 0; hi < 2; ++hi) {
+            const int key = mt * 16 + hi * 8 + g;
+            const bool masked = (emask >> key) & 1ull, oob = key >= nk;
+            float v0 = sacc[mt][2 * hi] * inv_scale, v1 = sacc[mt][2 * hi + 1] * inv_scale;
+            v0 = oob ? -INFINITY : (masked ? -1e8f : v0);
+            v1 = oob ? -INFINITY : (masked ? -1e8f : v1);
+            sacc[mt][2 * hi] = v0; sacc[mt][2 * hi + 1] = v1;
+            mx0 = fmaxf(mx0, v0); mx1 = fmaxf(mx1, v1);
+          }
+        }
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
+          mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
+        }
+        float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+          for (int hi = 0; hi < 2; ++hi) {
+            const float p0 = __expf(sacc[mt][2 * hi] - mx0), p1 = __expf(sacc[mt][2 * hi + 1] - mx1);
+            sacc[mt][2 * hi] = p0; sacc[mt][2 * hi + 1] = p1;
+            sum0 += p0; sum1 += p1;
+          }
+        }
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          sum0 += __shfl_xor_sync(0xffffffffu, sum0, o);
+          sum1 += __shfl_xor_sync(0xffffffffu, sum1, o);
+        }
+        // ---- O^T = V^T P^T: the probabilities become the B operand (16 keys x 8 queries) after an 8x8 transpose of the
+        // accumulator fragments (movmatrix); V^T fragments come from transposing ldmatrix loads of V[key][dim]
+        float oacc[4][4];
+#pragma unroll
+        for (int md = 0; md < 4; ++md) { oacc[md][0] = oacc[md][1] = oacc[md][2] = oacc[md][3] = 0.f; }
+#pragma unroll
+        for (int kk = 0; kk < MT; ++kk) {
+          const uint32_t b0 = movm_trans(pack_bf16(sacc[kk][0], sacc[kk][1]));
+          const uint32_t b1 = movm_trans(pack_bf16(sacc[kk][2], sacc[kk][3]));
+          const int key = kk * 16 + (mat >> 1) * 8 + l8;
+          const uint32_t row_u = key < nk ? sV_u + (uint32_t)key * pitch : zero_row;
+#pragma unroll
+          for (int md = 0; md < 4; ++md) {
+            uint32_t a[4];     // (dims 0-7, keys lo), (dims 8-15, keys lo), (dims 0-7, keys hi), (dims 8-15, keys hi)
+            ldsm_x4_trans(row_u + (uint32_t)(h * 64 + md * 16 + (mat & 1) * 8) * 2u, a);
+            mma_bf16(oacc[md], a, b0, b1);
+          }
+        }
+        // ---- back to [query][dim] (movmatrix again) and out: lane (g, t4) stores query g, dims 16 md + 2 t4 (+ 8)
+        const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+        __nv_bfloat16* Og = (__nv_bfloat16*)p.out + ((long long)img * p.rpi + qrow) * p.ldo + h * 64 + 2 * t4;
+#pragma unroll
+        for (int md = 0; md < 4; ++md) {
+          const uint32_t lo = movm_trans(pack_bf16(oacc[md][0] * inv0, oacc[md][1] * inv1));
+          const uint32_t hi = movm_trans(pack_bf16(oacc[md][2] * inv0, oacc[md][3] * inv1));
+          if (qrow < p.rpi) {
+            *reinterpret_cast<uint32_t*>(Og + md * 16) = lo;
+            *reinterpret_cast<uint32_t*>(Og + md * 16 + 8) = hi;
+          }
+        }
+      }
+    }
+    if (!waited) mbar_wait_(bars + 8u * stage, phase);          // a warp without a head still follows the ring
+    __syncwarp();
+    if (lane == 0) mbar_arrive_(bars + 8u * (stages + stage));    // every ldmatrix of this warp on the stage has retired
+    if (++stage == stages) { stage = 0; phase ^= 1u; }
+  }
+}
+
 // enc_mask[n, t] = any(spatial[n, t, :] == 0)   (transformers.py:480-481, Q16)
 template <typename T>
 __global__ void enc_mask_kernel(const T* __restrict__ x, unsigned char* __restrict__ mask, int rows, int D) {
@@ -383,6 +594,47 @@ extern "C" int dh_attention(const void* q, long long ldq, const void* K, const v
   if (rows == 0) return DH_OK;
   AttnParams p{q, ldq, K, V, out, ldo, rows, D, n_heads, rows_per_image, slots, S_alloc, src, slot_shared,
                n_keys, causal_full, seq, seq_ld, seq_per_image, pad, enc_mask, scale};
+  // cross-attention over an image's cached K/V rows (generation and teacher-forced): persistent bulk-copy pipeline
+  {
+    static const bool stream_ok = !getenv("DH_NO_STREAM_ATTN");
+    static int n_sms = 0, smem_max = 0;
+    if (stream_ok && dtype == DH_BF16 && D / n_heads == 64 && D % 8 == 0 && slot_shared && !causal_full && !seq && !src &&
+        n_keys <= 64 && rows_per_image <= 64 && rows % rows_per_image == 0 && ldo % 2 == 0 && ((uintptr_t)out % 4) == 0 &&
+        ((uintptr_t)q % 4) == 0 && ldq % 2 == 0) {
+      if (!n_sms) {
+        int dev = 0;
+        DH_CUDA(cudaGetDevice(&dev));
+        DH_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        DH_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+      }
+      const int n_img = rows / rows_per_image;
+      const size_t pitch = (size_t)(D + 8) * 2, stage_bytes = 2 * (size_t)n_keys * pitch;
+      const size_t fixed = ((pitch + 15) & ~(size_t)15) + 16 * 8 + 128;
+      int stages = (int)(((size_t)smem_max - fixed) / stage_bytes);
+      if (stages > 4) stages = 4;
+      if (stages >= 2) {
+        const size_t smem = (size_t)stages * stage_bytes + fixed;
+        const int grid = n_img < n_sms ? n_img : n_sms;
+        const int threads = (kStreamWarps + kLoadWarps) * 32;
+#define DH_STREAM_LAUNCH(NKT)                                                                                          \
+  do {                                                                                                                 \
+    static bool attr = false;                                                                                          \
+    if (!attr) {                                                                                                       \
+      DH_CUDA(cudaFuncSetAttribute(attn_stream_kernel<NKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));   \
+      attr = true;                                                                                                     \
+    }                                                                                                                  \
+    attn_stream_kernel<NKT><<<grid, threads, smem, s>>>(p, n_img, stages);                                             \
+  } while (0)
+        if (n_keys <= 16) DH_STREAM_LAUNCH(2);
+        else if (n_keys <= 32) DH_STREAM_LAUNCH(4);
+        else if (n_keys <= 48) DH_STREAM_LAUNCH(6);
+        else DH_STREAM_LAUNCH(8);
+#undef DH_STREAM_LAUNCH
+        DH_LAUNCH_OK();
+        return DH_OK;
+      }
+    }
+  }
   // keys shared by the rows of an image, bf16, head_dim 64, <= 64 keys and query rows per image: tensor-core path
   {
     const int nk = causal_full ? rows_per_image : n_keys;

@@ -135,3 +135,32 @@ def test_attention_shared_keys_tensor_core_path(rpi, nk, causal, use_enc, use_pa
         e = e.masked_fill(torch.triu(torch.ones(rpi, S, dtype=torch.bool), 1), float('-inf'))
     ref = (torch.softmax(e, -1) @ vd).permute(0, 2, 1, 3).reshape(rows, D_)
     assert H.rel_err(out.float(), ref.float()) < 1e-2
+
+
+@pytest.mark.parametrize('n_img,rpi,nk,n_heads,S_alloc,slots', [(700, 5, 49, 8, 49, 1), (1000, 1, 49, 8, 49, 1),
+                                                               (333, 5, 20, 4, 24, 2), (150, 33, 49, 8, 49, 1)])
+def test_attention_streaming_cross_kv_ring(n_img, rpi, nk, n_heads, S_alloc, slots):
+    """Persistent bulk-copy cross-attention (attn_stream_kernel): more images than CTAs, so every CTA wraps its stage
+    ring several times; strided K/V allocations (S_alloc > n_keys, slots > 1: slot 0 is read); float64 torch reference of
+    transformers.py:100-121 with the any-zero encoder mask (-1e8)."""
+    D_ = n_heads * 64
+    rows = n_img * rpi
+    g = torch.Generator().manual_seed(n_img + rpi)
+    q = torch.randn(rows, D_, generator=g).to(torch.bfloat16)
+    K = torch.randn(n_img * slots, S_alloc, D_, generator=g).to(torch.bfloat16)
+    Vv = torch.randn(n_img * slots, S_alloc, D_, generator=g).to(torch.bfloat16)
+    enc = (torch.rand(n_img, S_alloc, generator=g) < 0.2).to(torch.uint8)
+    out = torch.empty(rows, D_, dtype=torch.bfloat16, device=DEV)
+    scale = 8.0
+    ops.attention(q.to(DEV), K.to(DEV), Vv.to(DEV), out, n_heads, rpi, slots, S_alloc, scale, slot_shared=True, n_keys=nk,
+                  enc_mask=enc.to(DEV))
+    torch.cuda.synchronize()
+    Ks = K.view(n_img, slots, S_alloc, D_)[:, 0, :nk]
+    Vs = Vv.view(n_img, slots, S_alloc, D_)[:, 0, :nk]
+    qd = q.double().view(n_img, rpi, n_heads, 64).permute(0, 2, 1, 3)
+    kd = Ks.double().reshape(n_img, nk, n_heads, 64).permute(0, 2, 1, 3)
+    vd = Vs.double().reshape(n_img, nk, n_heads, 64).permute(0, 2, 1, 3)
+    e = (qd @ kd.transpose(-1, -2) / scale).masked_fill(enc[:, :nk].bool().view(n_img, 1, 1, nk), -1e8)
+    ref = (torch.softmax(e, -1) @ vd).permute(0, 2, 1, 3).reshape(rows, D_)
+    assert H.rel_err(out.float(), ref.float()) < 1e-2
+
