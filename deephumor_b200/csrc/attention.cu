@@ -128,6 +128,171 @@ __global__ void __launch_bounds__(kWarps * 32) attn_kernel(AttnParams p) {
   }
 }
 
+// Incremental self-attention over the KV cache at D = 512 (8 heads of 64): one warp per query ROW, all heads at once.
+// A cached K / V row is 1 KB contiguous, so the warp reads it with two fully coalesced 512-byte loads (lane l holds dims
+// 8 l .. 8 l + 7 of heads l / 8 and 4 + l / 8); four keys are in flight per lane before the first is consumed, and the eight
+// partial dot products a lane then holds (4 keys x 2 heads) are reduced across its 8-lane head group with a halving
+// exchange (7 shuffles instead of 24).  The rows of a CTA are consecutive beams, mostly of one image, whose slot tables
+// share their common ancestors' rows: L1 serves the re-reads.
+constexpr int kRowWarps = 8;
+constexpr int kRowMaxKeys = 160;
+constexpr int kRowPitch = kRowMaxKeys + 1;      // scores [8 heads][keys], odd pitch: the head groups read distinct banks
+
+__device__ __forceinline__ void bf16x8_to_f32(const uint4 v, float* out) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    out[2 * i] = __uint_as_float(w[i] << 16);
+    out[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+__global__ void __launch_bounds__(kRowWarps * 32) attn_row_kernel(AttnParams p) {
+  __shared__ float s_p[kRowWarps][8 * kRowPitch];
+  __shared__ int s_off[kRowWarps][kRowMaxKeys];        // physical K / V row of key t; ~row when the key is masked
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * kRowWarps + w;
+  if (r >= p.R) return;
+  const int img = r / p.rpi, b = r % p.rpi;
+  const int nk = p.n_keys, D = 512;
+  const __nv_bfloat16* Kb = (const __nv_bfloat16*)p.K;
+  const __nv_bfloat16* Vb = (const __nv_bfloat16*)p.V;
+  float* sp = s_p[w];
+  int* soff = s_off[w];
+  const int* seq_row = p.seq ? p.seq + (long long)(p.seq_per_image ? img : r) * p.seq_ld : nullptr;
+  // physical row of every key (beam slot indirection); the sign bit carries the pad-key / encoder mask
+  for (int t = lane; t < nk; t += 32) {
+    const int slot = p.slot_shared ? 0 : (p.src ? p.src[((long long)img * p.rpi + b) * p.S_alloc + t] : b);
+    const int off = (int)(((long long)img * p.slots + slot) * p.S_alloc + t);      // < 2^31 rows (checked on the host)
+    bool masked = false;
+    if (seq_row && t >= 1) masked = (seq_row[t - 1] == p.pad);
+    if (p.enc_mask) masked = p.enc_mask[(long long)img * p.S_alloc + t] != 0;
+    soff[t] = masked ? ~off : off;
+  }
+  float qa[8], qb[8];
+  {
+    const __nv_bfloat16* qr = (const __nv_bfloat16*)p.q + (long long)r * p.ldq + lane * 8;
+    bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(qr)), qa);
+    bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(qr + 256)), qb);
+  }
+  __syncwarp();
+  const int grp = lane >> 3;                   // head group: heads grp and 4 + grp
+  // ---- scores: 4 keys per iteration
+  for (int t0 = 0; t0 < nk; t0 += 4) {
+    uint4 ka[4], kb[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int t = t0 + j;
+      if (t < nk) {
+        const int row = soff[t];
+        const long long off = (long long)(row < 0 ? ~row : row) * D;
+        ka[j] = __ldg(reinterpret_cast<const uint4*>(Kb + off + lane * 8));
+        kb[j] = __ldg(reinterpret_cast<const uint4*>(Kb + off + 256 + lane * 8));
+      } else {
+        ka[j] = kb[j] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    float v[8];                                // v[2 j] = key j, head grp;  v[2 j + 1] = key j, head 4 + grp
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float ka_f[8], kb_f[8];
+      bf16x8_to_f32(ka[j], ka_f);
+      bf16x8_to_f32(kb[j], kb_f);
+      float sa = 0.f, sb = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { sa = fmaf(qa[i], ka_f[i], sa); sb = fmaf(qb[i], kb_f[i], sb); }
+      v[2 * j] = sa; v[2 * j + 1] = sb;
+    }
+    // halving exchange over the 8 lanes of the head group: afterwards lane i of the group holds the total of v[i]
+    {
+      const bool up = lane & 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float send = up ? v[i] : v[4 + i], keep = up ? v[4 + i] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+    }
+    {
+      const bool up = lane & 2;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float send = up ? v[i] : v[2 + i], keep = up ? v[2 + i] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+    }
+    {
+      const bool up = lane & 1;
+      const float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+      v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+    const int idx = lane & 7, t = t0 + (idx >> 1), head = (idx & 1) * 4 + grp;
+    if (t < nk) sp[head * kRowPitch + t] = soff[t] < 0 ? -1e8f : v[0] / p.scale;
+  }
+  __syncwarp();
+  // ---- softmax per head: 4 lanes per head
+  {
+    const int head = lane >> 2, l4 = lane & 3;
+    float* ph = sp + head * kRowPitch;
+    float mx = -INFINITY;
+    for (int t = l4; t < nk; t += 4) mx = fmaxf(mx, ph[t]);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    float sum = 0.f;
+    for (int t = l4; t < nk; t += 4) {
+      const float e = expf(ph[t] - mx);
+      ph[t] = e;
+      sum += e;
+    }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    if (l4 == 0) ph[kRowMaxKeys] = 1.f / sum;           // the pad column of the row holds the normaliser
+  }
+  __syncwarp();
+  // ---- output: lane l accumulates dims 8 l .. 8 l + 7 of head grp and of head 4 + grp
+  float oa[8], ob[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) oa[i] = ob[i] = 0.f;
+  const float* pa = sp + grp * kRowPitch;
+  const float* pb = sp + (4 + grp) * kRowPitch;
+  for (int t0 = 0; t0 < nk; t0 += 4) {
+    uint4 va[4], vb[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int t = t0 + j;
+      if (t < nk) {
+        const int row = soff[t];
+        const long long off = (long long)(row < 0 ? ~row : row) * D;
+        va[j] = __ldg(reinterpret_cast<const uint4*>(Vb + off + lane * 8));
+        vb[j] = __ldg(reinterpret_cast<const uint4*>(Vb + off + 256 + lane * 8));
+      } else {
+        va[j] = vb[j] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int t = t0 + j;
+      const float wa = t < nk ? pa[t] : 0.f, wb = t < nk ? pb[t] : 0.f;
+      float fa[8], fb[8];
+      bf16x8_to_f32(va[j], fa);
+      bf16x8_to_f32(vb[j], fb);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { oa[i] = fmaf(wa, fa[i], oa[i]); ob[i] = fmaf(wb, fb[i], ob[i]); }
+    }
+  }
+  const float ia = pa[kRowMaxKeys], ib = pb[kRowMaxKeys];
+  uint32_t wa[4], wb[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 x = __floats2bfloat162_rn(oa[2 * i] * ia, oa[2 * i + 1] * ia);
+    __nv_bfloat162 y = __floats2bfloat162_rn(ob[2 * i] * ib, ob[2 * i + 1] * ib);
+    wa[i] = *reinterpret_cast<uint32_t*>(&x);
+    wb[i] = *reinterpret_cast<uint32_t*>(&y);
+  }
+  __nv_bfloat16* o = (__nv_bfloat16*)p.out + (long long)r * p.ldo + lane * 8;
+  *reinterpret_cast<uint4*>(o) = make_uint4(wa[0], wa[1], wa[2], wa[3]);
+  *reinterpret_cast<uint4*>(o + 256) = make_uint4(wb[0], wb[1], wb[2], wb[3]);
+}
+
 // Cross-attention over keys shared by all rows of an image (the 49 spatial tokens, transformers.py:100-121 via :366):
 // one CTA per (image, head), one warp per row of the image.  The head slice of K and V ([n_keys, hd] each) is staged
 // in shared memory once and reused by the image's rpi beam rows -- rpi times less L2 traffic than one warp per
@@ -662,6 +827,17 @@ extern "C" int dh_attention(const void* q, long long ldq, const void* K, const v
     else return dh_fail(DH_ERR_ARG, "dtype", __FILE__, __LINE__);
     DH_LAUNCH_OK();
     return DH_OK;
+  }
+  // incremental bf16 self-attention at D = 512 / 8 heads: one warp per row, whole 1 KB K / V rows per load
+  {
+    static const bool row_ok = !getenv("DH_NO_ROW_ATTN");
+    if (row_ok && dtype == DH_BF16 && D == 512 && n_heads == 8 && !causal_full && n_keys <= kRowMaxKeys && ldq % 8 == 0 &&
+        ldo % 8 == 0 && ((uintptr_t)out % 16) == 0 &&
+        (long long)(rows / rows_per_image + 1) * slots * S_alloc < (1ll << 31)) {
+      attn_row_kernel<<<dh_cdiv(rows, kRowWarps), kRowWarps * 32, 0, s>>>(p);
+      DH_LAUNCH_OK();
+      return DH_OK;
+    }
   }
   int grid = dh_cdiv((long long)rows * n_heads, kWarps);
   if (dtype == DH_F32) attn_kernel<float><<<grid, kWarps * 32, 0, s>>>(p);

@@ -30,3 +30,18 @@ for n_img, rpi in ((2048, 5), (4096, 1), (8192, 5)):
     us = timeit(run) / L
     mb = 2 * n_img * 49 * D * 2 / 1e6
     print(f'cross-attention n_img={n_img} rpi={rpi}: {us:.1f} us  ({mb:.0f} MB of K/V -> {mb / us * 1e3:.0f} GB/s)')
+# ---- incremental self-attention over the KV cache: rows = images x beams, keys through the slot table
+for n_img, B, nk in ((2048, 5, 17), (2048, 5, 33), (8192, 5, 17)):
+    rows, S = n_img * B, 33
+    q = torch.randn(rows, D, device=dev).to(torch.bfloat16)
+    Kc = torch.randn(n_img * B, S, D, device=dev).to(torch.bfloat16)
+    Vc = torch.randn(n_img * B, S, D, device=dev).to(torch.bfloat16)
+    # genealogy-like slot table: old positions point to few distinct slots, recent ones to the beam's own
+    src = torch.zeros(n_img, B, S, dtype=torch.int32, device=dev)
+    for t in range(S):
+        src[:, :, t] = torch.arange(B, device=dev).view(1, B) if t >= nk - 3 else torch.randint(0, 2, (n_img, 1), device=dev).int()
+    seq = torch.randint(1, 100, (rows, S), dtype=torch.int32, device=dev)
+    out = torch.empty(rows, D, dtype=torch.bfloat16, device=dev)
+    us = timeit(lambda: ops.attention(q, Kc, Vc, out, H, B, B, S, 8.0, src=src, n_keys=nk, seq=seq, seq_per_image=False, pad=0))
+    mb = 2 * rows * nk * D * 2 / 1e6
+    print(f'self-attention rows={rows} keys={nk}: {us:.1f} us  ({mb:.0f} MB of K/V row reads -> {mb / us * 1e3:.0f} GB/s)')

@@ -164,3 +164,39 @@ def test_attention_streaming_cross_kv_ring(n_img, rpi, nk, n_heads, S_alloc, slo
     ref = (torch.softmax(e, -1) @ vd).permute(0, 2, 1, 3).reshape(rows, D_)
     assert H.rel_err(out.float(), ref.float()) < 1e-2
 
+
+@pytest.mark.parametrize('n_img,B,nk,S_alloc,use_src', [(37, 5, 18, 33, True), (64, 1, 7, 33, False), (9, 10, 33, 40, True),
+                                                       (3, 5, 1, 33, True), (5, 4, 130, 160, True)])
+def test_attention_incremental_self_row_kernel(n_img, B, nk, S_alloc, use_src):
+    """Incremental bf16 self-attention over the KV cache (attn_row_kernel: one warp per row, all 8 heads, keys through
+    the per-(beam, position) slot table) against a float64 torch restatement of transformers.py:100-121 with the pad-key
+    mask (-1e8) of transformers.py:473-477."""
+    D_, n_heads = 512, 8
+    rows = n_img * B
+    g = torch.Generator().manual_seed(n_img * 7 + nk)
+    q = torch.randn(rows, D_, generator=g).to(torch.bfloat16)
+    K = torch.randn(n_img * B, S_alloc, D_, generator=g).to(torch.bfloat16)
+    Vv = torch.randn(n_img * B, S_alloc, D_, generator=g).to(torch.bfloat16)
+    src = torch.randint(0, B, (n_img, B, S_alloc), generator=g).to(torch.int32) if use_src else None
+    seq = torch.randint(0, 3, (rows, S_alloc), generator=g).to(torch.int32)                 # 0 == pad
+    out = torch.empty(rows, D_, dtype=torch.bfloat16, device=DEV)
+    scale = 8.0
+    ops.attention(q.to(DEV), K.to(DEV), Vv.to(DEV), out, n_heads, B, B, S_alloc, scale,
+                  src=None if src is None else src.to(DEV), slot_shared=(B == 1), n_keys=nk, seq=seq.to(DEV),
+                  seq_per_image=False, pad=0)
+    torch.cuda.synchronize()
+    Kp, Vp = K.view(n_img, B, S_alloc, D_), Vv.view(n_img, B, S_alloc, D_)
+    t = torch.arange(nk)
+    ref = torch.empty(rows, D_, dtype=torch.float64)
+    for r in range(rows):
+        i, b = divmod(r, B)
+        slot = src[i, b, :nk].long() if src is not None else torch.full((nk,), 0 if B == 1 else b)
+        kr = Kp[i, slot, t].double().view(nk, n_heads, 64).permute(1, 0, 2)              # [head, key, 64]
+        vr = Vp[i, slot, t].double().view(nk, n_heads, 64).permute(1, 0, 2)
+        e = (q[r].double().view(n_heads, 1, 64) @ kr.transpose(-1, -2)).squeeze(1) / scale  # [head, key]
+        padk = torch.zeros(nk, dtype=torch.bool)
+        padk[1:] = seq[r, :nk - 1] == 0
+        e = e.masked_fill(padk.view(1, nk), -1e8)
+        ref[r] = (torch.softmax(e, -1).unsqueeze(1) @ vr).reshape(D_)
+    assert H.rel_err(out.float(), ref.float()) < 1e-2
+
