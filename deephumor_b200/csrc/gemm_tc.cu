@@ -996,9 +996,12 @@ int dispatch(const CUtensorMap& ma, const void* W, long long ldw, TcParams& p, i
   CUtensorMap mb, mc = ma, mr = ma, mi = ma;
   // CTA pairs (cta_group::2) for the 128- and 256-wide tiles whenever there are at least two M blocks to pair up
   static const bool pair_ok = !getenv("DH_TC_NO_PAIR");
-  // ... and the K loop is long enough (>= 16 chunks) to amortise the pair's cross-CTA barrier round trips: measured on
-  // the ResNet-50 / decoder shapes (profiles/), pairs win 6-30 % at K >= 1024 and lose 8-50 % on short-K, store-bound tiles
-  const bool pair = pair_ok && bn >= 128 && p.M > BM && p.k_chunks + (p.res ? bn / BK : 0) >= 16;
+  // ... and the K loop is long enough (>= 8 chunks incl. residual chunks) to amortise the pair's cross-CTA barrier round
+  // trips.  Measured per ResNet-50 / decoder shape (profiles/r01_bench_conv_pairmin.txt): pairs win 6-30 % at K >= 1024,
+  // 4-9 % at K = 512 (l3.c1, l3.c3, l3.ds, l4.c3, the vocab projection) now that the remote accumulator hand-off carries no
+  // GPU-scope membar, and lose on the 1-2 chunk store-bound tiles of layer1 (l1.c3 +8 % at a threshold of 4).
+  static const int pair_min_chunks = getenv("DH_TC_PAIR_MIN_CHUNKS") ? atoi(getenv("DH_TC_PAIR_MIN_CHUNKS")) : 8;
+  const bool pair = pair_ok && bn >= 128 && p.M > BM && p.k_chunks + (p.res ? bn / BK : 0) >= pair_min_chunks;
   const int b_rows = pair ? bn / 2 : bn;                   // W rows one CTA stages per K chunk
   const long long w_rows = (p.epi_mode == 3 && p.layers > 1) ? (long long)p.layers * p.w_layer_rows : p.N;
   int rc = make_map_2d(&mb, W, w_rows, p.K, ldw, b_rows, p.ab_dtype);
