@@ -459,22 +459,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           void* h1 = stack ? p.h1_l[layer] : p.h1;
           const long long ldh0 = stack ? p.ldh0_l[layer] : p.ldh0, ldh1 = stack ? p.ldh1_l[layer] : p.ldh1;
           const int as = it & 1;
-          // Everything that does not depend on the accumulator is issued BEFORE the wait on it: the bias slice (double
-          // buffered in the idle store-staging area: one barrier per tile, the readers of this buffer finished two tiles
-          // ago), the beam-parent index and the thread's 32 previous cell values.
-          float* bias_t = staging + (it & 1) * BN;
-          for (int i = etid; i < BN; i += 256) bias_t[i] = bias ? __ldg(bias + n0 + i) : 0.f;
+          // Everything that does not depend on the accumulator is issued BEFORE the wait on it: the bias slice, the
+          // beam-parent index and the previous cell values.  Global traffic is COALESCED through a 4 KB per-warp staging
+          // area: a thread owns an accumulator row (TMEM lane), so row-wise loads / stores would touch 32 lines per
+          // instruction (ncu: the epilogue, not the tensor pipe, bounded the kernel); here lane l moves 16 B of row
+          // i * 8 + l / 4, so an instruction covers 8 rows x 64 contiguous bytes, and the row owner exchanges its 64 B
+          // with the staging area (XOR-swizzled: both access patterns are bank-conflict free).
+          asm volatile("bar.sync 1, 256;" ::: "memory");          // readers of the previous bias slice are done
+          for (int i = etid; i < BN; i += 256) bias_s[i] = bias ? __ldg(bias + n0 + i) : 0.f;
           const long long row = (long long)m0 + row_l;
           const bool row_ok = row < p.M;
-          const int unit0 = (n0 >> 8) * 64;
+          const int unit0 = (n0 >> 8) * 64 + eh * 32;             // first of this thread's 32 hidden units
           const long long prow = row_ok ? (p.parent ? (long long)__ldg(p.parent + row) : row) : 0;
+          const int cr = lane >> 2, cc = lane & 3;                // cooperative role: row i * 8 + cr, 16-byte chunk cc
+          const uint32_t wst = base + C::kStages * C::kStageBytes + (uint32_t)(warp - 4) * 4096u;
+          const uint32_t cbuf = wst, hbuf = wst + 2048u;          // [32 rows][64 B] each
+          auto swz = [](int r, int j) { return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); };
           float4 cpv[8];
 #pragma unroll
-          for (int g = 0; g < 8; ++g) cpv[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row_ok && c_prev) {
-            const float4* cp = reinterpret_cast<const float4*>(c_prev + prow * p.H + unit0 + eh * 32);
-#pragma unroll
-            for (int g = 0; g < 8; ++g) cpv[g] = __ldg(cp + g);
+          for (int g = 0; g < 8; ++g) {
+            const int rr = (g & 3) * 8 + cr;
+            const long long pr = __shfl_sync(0xffffffffu, prow, rr);
+            const bool ok = (long long)m0 + ew * 32 + rr < p.M;
+            cpv[g] = (ok && c_prev) ? __ldg(reinterpret_cast<const float4*>(c_prev + pr * p.H + unit0 + (g >> 2) * 16 + cc * 4))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");
           mbar_wait(tfull_bar(as), (it >> 1) & 1, p.error, 4);
@@ -488,19 +496,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tc_ld16(tmem_row + (uint32_t)(64 + u0), vf);
             tc_ld16(tmem_row + (uint32_t)(128 + u0), vg);
             tc_ld16(tmem_row + (uint32_t)(192 + u0), vo);
+            __syncwarp();                                         // the previous half's read-out of cbuf is complete
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 c4 = cpv[half * 4 + i];
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cbuf + swz(i * 8 + cr, cc)), "f"(c4.x), "f"(c4.y),
+                           "f"(c4.z), "f"(c4.w) : "memory");
+            }
+            __syncwarp();
+            float cprev[16];
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(cprev[4 * g]), "=f"(cprev[4 * g + 1]), "=f"(cprev[4 * g + 2]), "=f"(cprev[4 * g + 3])
+                           : "r"(cbuf + swz(lane, g)) : "memory");
             tc_wait_ld();
             if (half == 1) {
               // the accumulator now lives in registers: hand the TMEM buffer back to the MMA warp before the cell math
-              // and the global stores (a release here would wait for those stores to drain)
+              // and the global stores
               tc_fence_before();
               __syncwarp();
               if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar(as), 0)); else mbar_arrive(tempty_bar(as)); }
-            }
-            float cprev[16];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const float4 c4 = cpv[half * 4 + g];
-              cprev[4 * g] = c4.x; cprev[4 * g + 1] = c4.y; cprev[4 * g + 2] = c4.z; cprev[4 * g + 3] = c4.w;
             }
             float c2[16];
             uint32_t hw[8];
@@ -509,10 +525,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               float h2[2];
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
-                const float gi = __uint_as_float(vi[j + e]) + bias_t[u0 + j + e];
-                const float gf = __uint_as_float(vf[j + e]) + bias_t[64 + u0 + j + e];
-                const float gg = __uint_as_float(vg[j + e]) + bias_t[128 + u0 + j + e];
-                const float go = __uint_as_float(vo[j + e]) + bias_t[192 + u0 + j + e];
+                const float gi = __uint_as_float(vi[j + e]) + bias_s[u0 + j + e];
+                const float gf = __uint_as_float(vf[j + e]) + bias_s[64 + u0 + j + e];
+                const float gg = __uint_as_float(vg[j + e]) + bias_s[128 + u0 + j + e];
+                const float go = __uint_as_float(vo[j + e]) + bias_s[192 + u0 + j + e];
                 // MUFU.TANH (rel. error 2^-11, far inside the bf16 rounding of h): sigmoid(x) = 0.5 + 0.5 tanh(x / 2)
                 const float si = fmaf(0.5f, tanh_fast(0.5f * gi), 0.5f), sf = fmaf(0.5f, tanh_fast(0.5f * gf), 0.5f);
                 const float so = fmaf(0.5f, tanh_fast(0.5f * go), 0.5f);
@@ -527,20 +543,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 hw[j >> 1] = *reinterpret_cast<uint32_t*>(&t);
               }
             }
-            if (row_ok) {
-              float4* co = reinterpret_cast<float4*>(c_out + row * p.H + unit0 + u0);
+            // the owner's new cell values replace the old ones in its own row of cbuf; its 16 h values (32 B) go to hbuf
 #pragma unroll
-              for (int g = 0; g < 4; ++g) co[g] = make_float4(c2[4 * g], c2[4 * g + 1], c2[4 * g + 2], c2[4 * g + 3]);
-              if (h0) {
-                uint4* d = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(h0) + row * ldh0 + unit0 + u0);
-                d[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                d[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-              }
-              if (h1) {
-                uint4* d = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(h1) + row * ldh1 + unit0 + u0);
-                d[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                d[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-              }
+            for (int g = 0; g < 4; ++g)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cbuf + swz(lane, g)), "f"(c2[4 * g]),
+                           "f"(c2[4 * g + 1]), "f"(c2[4 * g + 2]), "f"(c2[4 * g + 3]) : "memory");
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hbuf + swz(lane, half * 2 + g)), "r"(hw[4 * g]),
+                           "r"(hw[4 * g + 1]), "r"(hw[4 * g + 2]), "r"(hw[4 * g + 3]) : "memory");
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = i * 8 + cr;
+              const long long grow = (long long)m0 + ew * 32 + rr;
+              float4 v;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                           : "r"(cbuf + swz(rr, cc)) : "memory");
+              if (grow < p.M) *reinterpret_cast<float4*>(c_out + grow * p.H + unit0 + half * 16 + cc * 4) = v;
+            }
+          }
+          // h of both halves: 64 B per row, again 8 rows per store instruction, to up to two destinations
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = i * 8 + cr;
+            const long long grow = (long long)m0 + ew * 32 + rr;
+            uint4 v;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                         : "r"(hbuf + swz(rr, cc)) : "memory");
+            if (grow < p.M) {
+              if (h0) *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(h0) + grow * ldh0 + unit0 + cc * 8) = v;
+              if (h1) *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(h1) + grow * ldh1 + unit0 + cc * 8) = v;
             }
           }
           if (stack && layer + 1 < p.layers) {
