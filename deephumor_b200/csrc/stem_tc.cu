@@ -6,10 +6,12 @@
 //
 //   work item   = one image x two pooled rows (112 pooled pixels = the 128 TMEM lanes of one accumulator, 16 idle)
 //   input band  = the 15 input rows those pixels depend on, fp32 -> half, pixel-interleaved [row][col][rgb] in smem
-//   tap (dy,dx) = the conv output at (2py-1+dy, 2px-1+dx) of EVERY lane's pooled pixel: one 128 x 64 x 192 UMMA
-//                 (tcgen05.mma kind::f16, fp32 accumulators in TMEM) whose A tile the 256 threads gather from the band
-//                 with 4-byte loads and write 128B-swizzled (K layout: 7 kernel rows x 22 slots = 21 (s,c) values + one
-//                 junk value that meets a zero weight; padded to 192 with zeros)
+//   tap (dy,dx) = the conv output at (2py-1+dy, 2px-1+dx) of EVERY lane's pooled pixel: one 128 x 64 x 160 UMMA
+//                 (tcgen05.mma kind::f16, fp32 accumulators in TMEM) whose A operand lives in TENSOR MEMORY: the 256
+//                 threads gather their pixel's patch from the band with 4-byte loads and tcgen05.st it into their own
+//                 TMEM lane (K layout: 7 kernel rows x 22 slots = 21 (s,c) values + one junk value that meets a zero
+//                 weight; padded to 160 with zeros).  With A in shared memory every N = 64 MMA was bound by re-reading
+//                 its 128 x 16 A slice (128 cycles instead of 32) and the tile cost an extra smem write pass.
 //   pooling     = max over the 9 taps' accumulators of a lane, in registers (+bias, ReLU after the max: both monotone);
 //                 taps that fall into the pool's padding are skipped per lane.
 //
@@ -25,10 +27,11 @@ constexpr int kThreads = 256;
 constexpr int kPitch = 696;                 // halves per band row: (5 + 224 + 2 pad pixels) * 3 channels + junk, even
 constexpr int kBandRows = 15;
 constexpr int kKp = 192;                    // padded K: 7 * 22 = 154 real slots
-constexpr int kABytes = 3 * 128 * 128;      // A tile: 3 K-chunks of [128 rows x 128 B]
 constexpr int kWBytes = 3 * 64 * 128;       // W tile: 3 K-chunks of [64 rows x 128 B]
 constexpr int kBandBytes = kBandRows * kPitch * 2;
-constexpr int kSmemBytes = 1024 + 2 * kABytes + kWBytes + ((kBandBytes + 127) / 128) * 128 + 256 + 128;
+constexpr int kSmemBytes = 1024 + kWBytes + ((kBandBytes + 127) / 128) * 128 + 256 + 128;
+constexpr int kACols = 80;                  // A operand in TMEM: 160 halves = 80 32-bit columns per lane
+constexpr uint32_t kTmemCols = 256;         // 2 accumulator slots x 64 + A (80), power of two: two CTAs share an SM's 512
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -64,6 +67,37 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A from tensor memory (lane = row, 32-bit column j = K elements 2 j, 2 j + 1), B from shared memory
+__device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tc_st4(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
+               : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -117,34 +151,32 @@ template <> struct BandLoad<unsigned char> {
 // images [n,3,224,224] fp32 (or uint8 + PixelNorm); wp [64][192] T (k = r*22 + s*3 + c, zero elsewhere); bias [64];
 // out [n,56,56,64] T.
 template <typename T, typename TIN>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 stem_pool_kernel(const TIN* __restrict__ images, const T* __restrict__ wp, const float* __restrict__ bias,
                  T* __restrict__ out, int n_img, const PixelNorm nm) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t a_buf[2] = {base, base + (uint32_t)kABytes};
-  const uint32_t w_buf = base + 2u * kABytes;
-  T* band = reinterpret_cast<T*>(gbase + 2 * kABytes + kWBytes);
+  const uint32_t w_buf = base;
+  T* band = reinterpret_cast<T*>(gbase + kWBytes);
   constexpr int kBandPad = ((kBandBytes + 127) / 128) * 128;
-  float* bias_s = reinterpret_cast<float*>(gbase + 2 * kABytes + kWBytes + kBandPad);
-  const uint32_t bars = base + 2u * kABytes + kWBytes + kBandPad + 256u;     // a_free[2], grp_done[3]
-  uint32_t* tmem_word = reinterpret_cast<uint32_t*>(gbase + 2 * kABytes + kWBytes + kBandPad + 256 + 64);
-  auto a_free = [&](int b) { return bars + 8u * b; };
-  auto grp_done = [&](int g) { return bars + 8u * (2 + g); };
+  float* bias_s = reinterpret_cast<float*>(gbase + kWBytes + kBandPad);
+  const uint32_t bars = base + kWBytes + kBandPad + 256u;     // mma_done[2]: the MMAs of the taps of each parity
+  uint32_t* tmem_word = reinterpret_cast<uint32_t*>(gbase + kWBytes + kBandPad + 256 + 64);
+  auto mma_done = [&](uint32_t b) { return bars + 8u * b; };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // ---- one-time setup: barriers, TMEM, zeroed A tiles / band (pad columns, K padding and idle rows stay zero), weights
+  // ---- one-time setup: barriers, TMEM, zeroed band (pad columns stay zero), weights
   if (tid == 0) {
-    for (int i = 0; i < 5; ++i) mbar_init(bars + 8u * i, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(bars + 8u * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_word)), "r"(512u)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_word)), "r"(kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = tid; i < (2 * kABytes + kWBytes + kBandPad) / 16; i += kThreads)
+  for (int i = tid; i < (kWBytes + kBandPad) / 16; i += kThreads)
     *reinterpret_cast<uint4*>(gbase + i * 16) = make_uint4(0u, 0u, 0u, 0u);
   if (tid < 64) bias_s[tid] = bias[tid];
   __syncthreads();
@@ -158,14 +190,18 @@ stem_pool_kernel(const TIN* __restrict__ images, const T* __restrict__ wp, const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_word);
+  const uint32_t tmem_a = tmem_base + 128u;                 // columns 128 .. 207: the A operand
   // kind::f16 instruction descriptor: D fp32, A/B half (0) or bf16 (1), K-major, N = 64, M = 128
   const uint32_t fmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
   const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
-  // builder role: row m of the A tile, half 0 = kernel rows 0..3 (chunks 0..10), half 1 = rows 4..6 (chunks 11..19)
+  // builder role: row m of the A operand = TMEM lane m (warps w and w + 4 share lane quadrant w % 4); half 0 writes the
+  // columns of kernel rows 0..3 (words 0..43), half 1 those of rows 4..6 (words 44..76) and the zero padding (77..79)
   const int m = tid & 127, half = tid >> 7;
-  const int m_py = m / 56, m_px = m - m_py * 56;
   const bool m_ok = m < 112;
+  const int mc = m_ok ? m : 0;                 // idle lanes gather lane 0's patch: finite values, rows never read back
+  const int m_py = mc / 56, m_px = mc - m_py * 56;
+  const uint32_t a_lane = tmem_a + ((uint32_t)((warp & 3) * 32) << 16);
   // epilogue role: TMEM lane quadrant q, channel half ch0
   const int q = warp & 3, ch0 = (warp >> 2) * 32;
   const int e_m = q * 32 + lane;
@@ -173,12 +209,11 @@ stem_pool_kernel(const TIN* __restrict__ images, const T* __restrict__ wp, const
   const bool e_ok = e_m < 112;
 
   const int items = n_img * 28;
-  uint32_t uses[2] = {0u, 0u};      // completed-use counters of the two A buffers (uniform across the CTA)
-  uint32_t it = 0;
-  for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+  uint32_t n_tap = 0;                           // taps issued so far by this CTA (uniform): slot / barrier parity bookkeeping
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
     const int img = item / 28, py0 = (item - img * 28) * 2;
-    // ---- input band: rows 4*py0-5 .. 4*py0+9, fp32 NCHW -> T [row][5 + col][rgb]   (previous item's MMAs are all
-    //      complete: its last accumulator group was drained before this point, so the band may be overwritten)
+    // ---- input band: rows 4*py0-5 .. 4*py0+9, fp32 NCHW -> T [row][5 + col][rgb]   (the previous item's last gather
+    //      is behind the __syncthreads that closed it, so the band may be overwritten)
     const TIN* src = images + (long long)img * 3 * 224 * 224;
     using BV = typename BandLoad<TIN>::Vec;
     // all of a thread's loads are issued before the first conversion / store: one memory round trip per item, not ten
@@ -210,9 +245,12 @@ stem_pool_kernel(const TIN* __restrict__ images, const T* __restrict__ wp, const
     float acc[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) acc[j] = -INFINITY;
-    auto drain = [&](int slot, int dy, int dx) {
+    // max-pool the accumulator of tap (dy, dx), issued as this CTA's tap number n, into the thread's 32 channels
+    auto drain = [&](uint32_t n, int dy, int dx) {
+      mbar_wait(mma_done(n & 1u), (n >> 1) & 1u);
+      tc_fence_after();
       uint32_t v[32];
-      tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 64 + ch0), v);
+      tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (n & 1u) * 64u + (uint32_t)ch0, v);
       const bool valid = !((dy == 0 && py0 + e_py == 0) || (dx == 0 && e_px == 0));   // pool padding (-inf) is skipped
       if (valid) {
 #pragma unroll
@@ -221,81 +259,79 @@ stem_pool_kernel(const TIN* __restrict__ images, const T* __restrict__ wp, const
     };
 
 #pragma unroll 1
-    for (int tap = 0; tap < 9; ++tap) {
+    for (int tap = 0; tap < 9; ++tap, ++n_tap) {
       const int dy = tap / 3, dx = tap - dy * 3;
-      const int b = tap & 1;
-      if (uses[b] > 0) mbar_wait(a_free(b), (uses[b] - 1) & 1u);     // MMAs of the previous use have read the buffer
-      if (tap == 8) {
-        // accumulator slots 0..3 (taps 0..3) are reused by tap 8: drain them first
-        mbar_wait(grp_done(0), it & 1u);
-        tc_fence_after();
+      // gather this thread's part of its pixel's patch (LSU work that overlaps the previous tap's MMAs)
+      const uint32_t* rowp = reinterpret_cast<const uint32_t*>(band + (4 * m_py + 2 * dy) * kPitch + 12 * m_px + 6 * dx);
+      // 8-byte loads: adjacent lanes are 24 B apart, so the 16 lanes of a half-warp cover 32 distinct banks with LDS.64
+      // (4-byte loads are 2-way conflicted); the patch row starts on an even word for dx = 0, 2 and on an odd one for dx = 1
+      uint32_t w[44];
+      auto gather_row = [&](const uint32_t* rp, uint32_t* d, bool odd) {
+        if (!odd) {
 #pragma unroll
-        for (int s = 0; s < 4; ++s) drain(s, s / 3, s % 3);
-        tc_fence_before();
-      }
-      if (m_ok) {
-        const uint32_t* rowp = reinterpret_cast<const uint32_t*>(band + (4 * m_py + 2 * dy) * kPitch + 12 * m_px + 6 * dx);
-        const uint32_t arow = a_buf[b] + (uint32_t)(m * 128);
-        const uint32_t sw = (uint32_t)(m & 7);
-        if (half == 0) {
-          uint32_t w[44];
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int j = 0; j < 11; ++j) w[r * 11 + j] = rowp[r * (kPitch / 2) + j];
-#pragma unroll
-          for (int c = 0; c < 11; ++c)
-            sts128(arow + (uint32_t)((c >> 3) * 128 * 128) + ((((uint32_t)c & 7u) ^ sw) << 4), w[4 * c], w[4 * c + 1],
-                   w[4 * c + 2], w[4 * c + 3]);
+          for (int q2 = 0; q2 < 5; ++q2) {
+            const uint2 v = *reinterpret_cast<const uint2*>(rp + 2 * q2);
+            d[2 * q2] = v.x; d[2 * q2 + 1] = v.y;
+          }
+          d[10] = rp[10];
         } else {
-          uint32_t w[36];
+          d[0] = rp[0];
 #pragma unroll
-          for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int j = 0; j < 11; ++j) w[r * 11 + j] = rowp[(4 + r) * (kPitch / 2) + j];
-          w[33] = 0u; w[34] = 0u; w[35] = 0u;
-#pragma unroll
-          for (int c = 0; c < 9; ++c) {
-            const int cc = 11 + c;
-            sts128(arow + (uint32_t)((cc >> 3) * 128 * 128) + ((((uint32_t)cc & 7u) ^ sw) << 4), w[4 * c], w[4 * c + 1],
-                   w[4 * c + 2], w[4 * c + 3]);
+          for (int q2 = 0; q2 < 5; ++q2) {
+            const uint2 v = *reinterpret_cast<const uint2*>(rp + 1 + 2 * q2);
+            d[1 + 2 * q2] = v.x; d[2 + 2 * q2] = v.y;
           }
         }
+      };
+      if (half == 0) {
+        if (dx & 1) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) gather_row(rowp + r * (kPitch / 2), w + r * 11, true);
+        } else {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) gather_row(rowp + r * (kPitch / 2), w + r * 11, false);
+        }
+      } else {
+        if (dx & 1) {
+#pragma unroll
+          for (int r = 0; r < 3; ++r) gather_row(rowp + (4 + r) * (kPitch / 2), w + r * 11, true);
+        } else {
+#pragma unroll
+          for (int r = 0; r < 3; ++r) gather_row(rowp + (4 + r) * (kPitch / 2), w + r * 11, false);
+        }
+#pragma unroll
+        for (int j = 33; j < 44; ++j) w[j] = 0u;
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      // the previous tap's MMAs have read the A operand (and its accumulator is complete)
+      if (n_tap > 0) { mbar_wait(mma_done((n_tap - 1u) & 1u), ((n_tap - 1u) >> 1) & 1u); tc_fence_after(); }
+      if (half == 0) {                          // warp-uniform: warps 0..3
+        tc_st32(a_lane, w);
+        tc_st8(a_lane + 32u, w + 32);
+        tc_st4(a_lane + 40u, w + 40);
+      } else {
+        tc_st32(a_lane + 44u, w);
+        tc_st4(a_lane + 76u, w + 32);
+      }
+      tc_wait_st();
       tc_fence_before();
       __syncthreads();
       if (tid == 0) {
         tc_fence_after();
-        const uint32_t slot = tap == 8 ? 0u : (uint32_t)tap;
-        const uint32_t tmem_d = tmem_base + slot * 64u;
+        const uint32_t tmem_d = tmem_base + (n_tap & 1u) * 64u;
+        // K slots 0..159 (154 real + zero padding) = 10 K steps of 16; B chunk kc holds K slots 64 kc .. 64 kc + 63
 #pragma unroll
-        for (int kc = 0; kc < 3; ++kc) {
-          const uint64_t da = umma_desc(a_buf[b] + (uint32_t)(kc * 128 * 128));
-          const uint64_t db = umma_desc(w_buf + (uint32_t)(kc * 64 * 128));
-          // only K slots 0..159 hold data (154 real + zero padding): the last chunk needs 2 of its 4 K steps.  Every
-          // tcgen05.mma here is bound by re-reading its 128 x 16 A slice from shared memory (N = 64), so fewer
-          // instructions = proportionally less time.
-#pragma unroll
-          for (int k = 0; k < (kc == 2 ? 2 : 4); ++k)
-            tc_mma(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
+        for (int ks = 0; ks < 10; ++ks) {
+          const uint64_t db = umma_desc(w_buf + (uint32_t)((ks >> 2) * 64 * 128)) + (uint64_t)(2 * (ks & 3));
+          tc_mma_ts(tmem_d, tmem_a + (uint32_t)(ks * 8), db, idesc, ks ? 1u : 0u);
         }
-        tc_commit(a_free(b));
-        if (tap == 3) tc_commit(grp_done(0));
-        if (tap == 7) tc_commit(grp_done(1));
-        if (tap == 8) tc_commit(grp_done(2));
+        tc_commit(mma_done(n_tap & 1u));
       }
-      ++uses[b];
+      // pool the previous tap while this one runs on the tensor core
+      if (tap > 0) { drain(n_tap - 1u, (tap - 1) / 3, (tap - 1) % 3); tc_fence_before(); }
     }
-    // ---- drain taps 4..7 and 8, then bias + ReLU + store (32 channels = 64 B per thread)
-    mbar_wait(grp_done(1), it & 1u);
-    tc_fence_after();
-#pragma unroll
-    for (int s = 4; s < 8; ++s) drain(s, s / 3, s % 3);
-    mbar_wait(grp_done(2), it & 1u);
-    tc_fence_after();
-    drain(0, 2, 2);
+    drain(n_tap - 1u, 2, 2);
     tc_fence_before();
+    // ---- bias + ReLU + store (32 channels = 64 B per thread)
     if (e_ok) {
       uint32_t o[16];
 #pragma unroll
@@ -312,7 +348,7 @@ stem_pool_kernel(const TIN* __restrict__ images, const T* __restrict__ wp, const
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -333,7 +369,7 @@ static int stem_launch(const TIN* images, const void* w_packed, const float* bia
     attr = true;
   }
   const int items = n * 28;
-  const int grid = items < g_sms ? items : g_sms;
+  const int grid = items < 2 * g_sms ? items : 2 * g_sms;       // two CTAs per SM (256 TMEM columns and ~47 KB each)
   if (dtype == DH_F16)
     stem_pool_kernel<__half, TIN><<<grid, kThreads, kSmemBytes, stream>>>(images, (const __half*)w_packed, bias, (__half*)out, n, nm);
   else
