@@ -304,6 +304,17 @@ def cpu_baseline(kind, hp, sd, beam, top_k, n_img):
     torch.set_num_threads(cores)
     imgs = synth.images(0, 0, n_img)
     labs = synth.labels(0, 0, n_img, V) if kind == 'lstm_labels' else None
+    if beam == 0:
+        # teacher-forced workload (config 3): the reference's forward + experiments/metrics.perplexity on a batch
+        caps, lens = synth.captions(0, 0, n_img, V, width=MAX_LEN, min_len=8)
+        with torch.no_grad():
+            run = lambda n: omodel.perplexity(omodel.forward(kind, sd, hp, imgs[:n], caps[:n, :-1]), caps[:n], lens[:n])
+            run(1)                                                                                       # warm-up
+            t0 = time.time()
+            run(n_img)
+            dt = time.time() - t0
+        return {'value': round(n_img / dt, 3), 'unit': 'sequences/s', 'cores': cores, 'kind': 'port',
+                'sample': f'{n_img} sequences of the same workload in one batch, torch CPU fp32, {cores} threads, {dt:.1f} s'}
     kw = dict(max_len=MAX_LEN, beam_size=beam, top_k=top_k, temperature=1.0, noise=onoise.Noise('injected', 1234),
               faithful_cost=True)
     with torch.no_grad():

@@ -39,7 +39,7 @@ class PackedConv:
 class EncoderRT:
     """prefix = 'encoder' (ImageEncoder) or 'encoder.image_encoder' (inside ImageLabelEncoder)."""
 
-    def __init__(self, sd, prefix, dtype, device, spatial=False, label_prefix=None, fuse_prefix=None, chunk=256):
+    def __init__(self, sd, prefix, dtype, device, spatial=False, label_prefix=None, fuse_prefix=None, chunk=512):
         self.dtype, self.device, self.spatial, self.chunk = dtype, device, spatial, chunk
         # Tensor-core mode stores the trunk (weights + activations) in fp16, not bf16: same tcgen05 kind::f16 rate,
         # 3 more significand bits.  bf16 storage leaves ~0.7 % error on the 7x7 feature map, which the mean-centring
@@ -154,8 +154,8 @@ class EncoderRT:
     def _host_chunks(self, images):
         """Pinned HOST images -> device chunks, copied on a side stream into two staging buffers so the H2D transfer
         of chunk k+1 overlaps the trunk of chunk k (yields (first index, device chunk, event to record when consumed)).
-        The schedule starts small (64, then 192 images) so the trunk starts after 0.7 ms of copying, then uses the
-        full trunk chunk, which runs the convolutions at their best rate."""
+        The schedule starts small (64, then 192, then 256 images) so the trunk starts after 0.7 ms of copying, then uses
+        the full trunk chunk, which runs the convolutions at their best rate."""
         N = images.shape[0]
         main = torch.cuda.current_stream()
         if not hasattr(self, '_copy_stream'):
@@ -163,9 +163,11 @@ class EncoderRT:
             self._copied = [torch.cuda.Event(), torch.cuda.Event()]
             self._consumed = [torch.cuda.Event(), torch.cuda.Event()]
         cs = self._copy_stream
+        # ramp 64 / 192 / 256, then full trunk chunks (512 images run the layer3/4 convolutions ~6 % faster per image than
+        # 256: fewer partial waves; profiles/r01_bench_conv_n512.txt)
         sizes, left = [], N
-        for want in (64, 192):
-            if left > self.chunk:
+        for want in (64, 192, 256):
+            if (left >= 2 * want) if want < 256 else (left > self.chunk):
                 sizes.append(want)
                 left -= want
         while left > 0:

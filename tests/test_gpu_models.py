@@ -274,13 +274,14 @@ def test_char_level_vocabulary_long_captions_match_oracle(kind):
 
 
 def test_empty_and_chunk_crossing_batches():
-    """Edge sizes: an empty batch returns empty ids; a batch that crosses the 256-image trunk chunk (257) gives the same
-    captions for its first / last images as generating them alone with the matching image_base."""
+    """Edge sizes: an empty batch returns empty ids; a batch that crosses the trunk chunk (257 images, chunk set to 256)
+    gives the same captions for its first / last images as generating them alone with the matching image_base."""
     from deephumor_b200.utils import synth
     fx = H.load_fixture('small', 'lstm')
     m, sd, *_ = build(fx, 'bf16')
     kw = dict(max_len=6, temperature=1.0, beam_size=2, top_k=5, noise='injected', seed=4)
     imgs = synth.images(0, 0, 257).cuda()
+    m.encoder._rt().chunk = 256
     with torch.no_grad():
         ids0, lens0 = m.generate(imgs[:0], **kw)
         assert ids0.shape == (0, 6) and lens0.shape == (0,)
