@@ -79,6 +79,37 @@ __global__ void avgpool_kernel(const T* __restrict__ x, TO* __restrict__ out, in
   }
 }
 
+// 2-byte activations: 8 channels per thread with 16-byte loads, 7 rows in flight; per channel the same ascending-row
+// summation as the scalar kernel (bit-identical results).
+template <typename T, typename TO>
+__global__ void __launch_bounds__(256) avgpool_vec_kernel(const T* __restrict__ x, TO* __restrict__ out, int N, int HW, int C,
+                                                          long long ldo) {
+  const int C8 = C >> 3;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)N * C8) return;
+  const int c = (int)(i % C8) * 8, n = (int)(i / C8);
+  const T* p = x + (long long)n * HW * C + c;
+  float s[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = 0.f;
+  for (int j0 = 0; j0 < HW; j0 += 7) {
+    uint4 v[7];
+#pragma unroll
+    for (int u = 0; u < 7; ++u)
+      v[u] = j0 + u < HW ? __ldg(reinterpret_cast<const uint4*>(p + (long long)(j0 + u) * C)) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int u = 0; u < 7; ++u) {
+      if (j0 + u < HW) {
+        const T* e8 = reinterpret_cast<const T*>(&v[u]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s[e] += dh_to_f<T>(e8[e]);
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) out[(long long)n * ldo + c + e] = dh_from_f<TO>(s[e] / (float)HW);
+}
+
 // ------------------------------------------------------------------ row gathers
 // dst[r, 0:width] = src[idx ? idx[r] : r, 0:width]   (optionally scaled and with a second addend row)
 template <typename TS, typename TD, typename TI>
@@ -194,6 +225,55 @@ __global__ void add_layernorm_kernel(const T* __restrict__ x, long long ldx, con
   }
 }
 
+// 2-byte types with D = 256 * NCH: every element is read ONCE (16-byte loads, 8 elements per lane and 256-column chunk),
+// mean / centred variance / normalisation run on registers, 16-byte stores.  One warp per row.
+template <typename T, int NCH>
+__global__ void __launch_bounds__(256) add_layernorm_vec_kernel(const T* __restrict__ x, long long ldx, const T* __restrict__ y,
+                                                                long long ldy, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, T* __restrict__ out,
+                                                                long long ldo, int R, float eps) {
+  constexpr int D = 256 * NCH;
+  const int lane = threadIdx.x & 31;
+  const int r = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+  if (r >= R) return;
+  float v[NCH * 8];
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    const int c = k * 256 + lane * 8;
+    const uint4 a = *reinterpret_cast<const uint4*>(x + (long long)r * ldx + c);
+    const T* ap = reinterpret_cast<const T*>(&a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[k * 8 + i] = dh_to_f<T>(ap[i]);
+    if (y) {
+      const uint4 b = *reinterpret_cast<const uint4*>(y + (long long)r * ldy + c);
+      const T* bp = reinterpret_cast<const T*>(&b);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[k * 8 + i] += dh_to_f<T>(bp[i]);
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NCH * 8; ++i) s += v[i];
+  const float mean = dh_warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NCH * 8; ++i) { v[i] -= mean; q += v[i] * v[i]; }
+  const float rstd = rsqrtf(dh_warp_sum(q) / (float)D + eps);
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    const int c = k * 256 + lane * 8;
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(beta + c), b1 = *reinterpret_cast<const float4*>(beta + c + 4);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    uint4 o;
+    T* op = reinterpret_cast<T*>(&o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) op[i] = dh_from_f<T>(v[k * 8 + i] * rstd * gg[i] + bb[i]);
+    *reinterpret_cast<uint4*>(out + (long long)r * ldo + c) = o;
+  }
+}
+
 // ------------------------------------------------------------------ transformer input embedding
 // x[r] = (pos==0 ? start[r / rows_per_start] : tok_table[tokens[r]]) / scale + pos_table[pos]
 // (transformers.py:455-470; the image slot is scaled too, Q18).  tokens may be null when pos_of_row==0 everywhere.
@@ -253,6 +333,13 @@ extern "C" int dh_avgpool(const void* x, void* out, long long ldo, int n, int HW
   DH_ARG(x && out && n >= 0 && HW > 0);
   if (n == 0) return DH_OK;
   long long total = (long long)n * C;
+  if (dtype != DH_F32 && out_dtype == DH_F32 && C % 8 == 0 && ((uintptr_t)x % 16) == 0) {
+    const int gv = dh_cdiv(total / 8, 256);
+    if (dtype == DH_BF16) avgpool_vec_kernel<__nv_bfloat16, float><<<gv, 256, 0, s>>>((const __nv_bfloat16*)x, (float*)out, n, HW, C, ldo);
+    else avgpool_vec_kernel<__half, float><<<gv, 256, 0, s>>>((const __half*)x, (float*)out, n, HW, C, ldo);
+    DH_LAUNCH_OK();
+    return DH_OK;
+  }
   if (out_dtype == DH_F32)
     DH_DISPATCH(dtype, (avgpool_kernel<T, float><<<grid_for(total), kThreads, 0, s>>>((const T*)x, (float*)out, n, HW, C, ldo)));
   else
@@ -310,6 +397,18 @@ extern "C" int dh_add_layernorm(const void* x, long long ldx, const void* y, lon
                                 const float* beta, void* out, long long ldo, int rows, int D, int dtype, cudaStream_t s) {
   DH_ARG(x && gamma && beta && out && rows >= 0 && D > 0);
   if (rows == 0) return DH_OK;
+  // 2-byte activations with 256 / 512 / 1024 columns and 16-byte aligned rows: single-read vectorised kernel
+  if (dtype != DH_F32 && (D == 256 || D == 512 || D == 1024) && ldx % 8 == 0 && ldo % 8 == 0 && (!y || ldy % 8 == 0) &&
+      ((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 16) == 0 && (!y || ((uintptr_t)y % 16) == 0) &&
+      ((uintptr_t)gamma % 16) == 0 && ((uintptr_t)beta % 16) == 0) {
+    const int gv = dh_cdiv(rows, 8);
+#define DH_LN_VEC(T, NCH) add_layernorm_vec_kernel<T, NCH><<<gv, 256, 0, s>>>((const T*)x, ldx, (const T*)y, ldy, gamma, beta, (T*)out, ldo, rows, 1e-5f)
+    if (dtype == DH_BF16) { if (D == 256) DH_LN_VEC(__nv_bfloat16, 1); else if (D == 512) DH_LN_VEC(__nv_bfloat16, 2); else DH_LN_VEC(__nv_bfloat16, 4); }
+    else { if (D == 256) DH_LN_VEC(__half, 1); else if (D == 512) DH_LN_VEC(__half, 2); else DH_LN_VEC(__half, 4); }
+#undef DH_LN_VEC
+    DH_LAUNCH_OK();
+    return DH_OK;
+  }
   int g = grid_for((long long)rows * 32);
   DH_DISPATCH(dtype, (add_layernorm_kernel<T><<<g, kThreads, 0, s>>>((const T*)x, ldx, (const T*)y, ldy, gamma, beta, (T*)out, ldo,
                                                                   rows, D, 1e-5f)));

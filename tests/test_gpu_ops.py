@@ -60,6 +60,32 @@ def test_layout_pool_kernels():
     assert H.rel_err(p, x.mean(dim=(2, 3))) < 1e-6
 
 
+@pytest.mark.parametrize('rows,D_,dt,use_y', [(1000, 512, torch.bfloat16, True), (37, 256, torch.float16, True),
+                                             (4097, 1024, torch.bfloat16, False)])
+def test_add_layernorm_vectorised_two_byte(rows, D_, dt, use_y):
+    """Single-read 16-byte add + LayerNorm kernel for 2-byte activations (transformers.py:360,368,375,627,634) on strided
+    rows, against torch's layer_norm on the same rounded inputs."""
+    x = rnd(rows, D_ + 8, seed=1).to(dt).to(DEV)[:, :D_]
+    y = rnd(rows, D_, seed=2).to(dt).to(DEV) if use_y else None
+    g, b = rnd(D_, seed=3).to(DEV), rnd(D_, seed=4).to(DEV)
+    out = torch.empty(rows, D_ + 8, dtype=dt, device=DEV)[:, :D_]
+    ops.add_layernorm(x, y, g, b, out)
+    ref = F.layer_norm(x.float() + (y.float() if use_y else 0.), (D_,), g, b, 1e-5)
+    assert H.rel_err(out.float(), ref) < (4e-3 if dt == torch.bfloat16 else 6e-4)
+
+
+def test_avgpool_vectorised_matches_scalar_order():
+    """avgpool over 49 positions of fp16 NHWC features (encoders.py:60): 16-byte loads, per channel the ascending-row
+    fp32 summation of the scalar kernel."""
+    x = rnd(5, 49, 2048, seed=11).to(torch.float16).to(DEV)
+    out = torch.empty(5, 2048, device=DEV)
+    ops.avgpool(x, out)
+    ref = torch.zeros(5, 2048, device=DEV)
+    for j in range(49):
+        ref += x[:, j].float()
+    assert torch.equal(out, ref / torch.full_like(ref, 49.0))     # tensor / tensor: IEEE division (scalar division multiplies by 1/49)
+
+
 def test_layernorm_lstm_cell_embed():
     x, y, g, b = rnd(37, 96, seed=1), rnd(37, 96, seed=2), rnd(96, seed=3), rnd(96, seed=4)
     out = torch.empty(37, 96, device=DEV)
