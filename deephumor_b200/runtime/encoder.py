@@ -36,6 +36,10 @@ class PackedConv:
         self.stride, self.pad, self.cout, self.kh = stride, pad, w.shape[0], w.shape[1]
 
 
+import os as _os
+H2D_RAMP = tuple(int(v) for v in _os.environ.get('DH_H2D_RAMP', '64,192,256').split(','))
+
+
 class EncoderRT:
     """prefix = 'encoder' (ImageEncoder) or 'encoder.image_encoder' (inside ImageLabelEncoder)."""
 
@@ -163,10 +167,12 @@ class EncoderRT:
             self._copied = [torch.cuda.Event(), torch.cuda.Event()]
             self._consumed = [torch.cuda.Event(), torch.cuda.Event()]
         cs = self._copy_stream
-        # ramp 64 / 192 / 256, then full trunk chunks (512 images run the layer3/4 convolutions ~6 % faster per image than
-        # 256: fewer partial waves; profiles/r01_bench_conv_n512.txt)
+        # ramp, then full trunk chunks (512 images run the layer3/4 convolutions ~6 % faster per image than 256: fewer
+        # partial waves; profiles/r01_bench_conv_n512.txt).  Copies are sequential and faster than the trunk, so the GPU
+        # only starves when a chunk grows faster than the trunk of the previous one takes: a ramp step is taken while
+        # at least twice its size is left.
         sizes, left = [], N
-        for want in (64, 192, 256):
+        for want in H2D_RAMP:
             if (left >= 2 * want) if want < 256 else (left > self.chunk):
                 sizes.append(want)
                 left -= want
