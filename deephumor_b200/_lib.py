@@ -25,6 +25,14 @@ class BeamState(ctypes.Structure):
                 ('S_alloc', ctypes.c_int)]
 
 
+class LstmOperands(ctypes.Structure):
+    """struct dh_lstm_operands (include/deephumor_b200.h)."""
+    _fields_ = [('table', ctypes.c_void_p), ('ldt', ctypes.c_longlong), ('n_tok_rows', ctypes.c_longlong),
+                ('E', ctypes.c_int), ('H', ctypes.c_int), ('L', ctypes.c_int),
+                ('hs', ctypes.c_void_p * 8), ('A', ctypes.c_void_p * 8), ('lda', ctypes.c_longlong * 8),
+                ('in_off', ctypes.c_int * 8)]
+
+
 def parse_header(path=HEADER):
     """Returns {name: (restype, [argtypes], [argnames])} for every function the header declares."""
     text = open(path).read()

@@ -648,10 +648,16 @@ __global__ void __launch_bounds__(32) beam_step_kernel(BeamState st, StepParams 
 
 // One CTA per image, one warp per logits row of the image: warp_select on every row's candidate list, then (do_beam)
 // warp 0 runs the beam step of the image on the picks -- selection and beam bookkeeping of one decode step in ONE launch.
+// Operand gathers of the next LSTM time step for the image's rows (dh_lstm_operands; L == 0: none)
+struct LstmNext {
+  const uint16_t* table; long long ldt, n_tok_rows; int E, H, L;
+  const uint16_t* hs[8]; uint16_t* A[8]; long long lda[8]; int in_off[8];
+};
+
 __global__ void __launch_bounds__(32 * kMaxBeam) select_beam_kernel(SelParams p, const int* __restrict__ cand_count,
                                                                    const int* __restrict__ cand_idx,
                                                                    const float* __restrict__ cand_val, int cap, int do_beam,
-                                                                   BeamState st, StepParams sp) {
+                                                                   BeamState st, StepParams sp, LstmNext nx) {
   extern __shared__ int dyn_smem[];
   const int img = blockIdx.x, warp = threadIdx.x >> 5;
   if (p.done && p.done[img]) return;
@@ -670,6 +676,27 @@ __global__ void __launch_bounds__(32 * kMaxBeam) select_beam_kernel(SelParams p,
   __syncthreads();                                   // the picks of all rows (global memory) are visible to warp 0
   if (warp == 0)
     beam_step_body(st, sp, img, reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(dyn_smem) + (size_t)p.rpi * kWarpSelBytes));
+  if (nx.L == 0) return;
+  // ---- next LSTM step's operands for this image's rows: 16-byte copies by the whole CTA
+  __syncthreads();                                   // last_tok / parent_state of the image (written by warp 0) are visible
+  const int ce = nx.E / 8, ch = nx.H / 8, per_row = ce + nx.L * ch;
+  for (int i = threadIdx.x; i < p.rpi * per_row; i += blockDim.x) {
+    const int b = i / per_row;
+    int c = i - b * per_row;
+    const long long row = (long long)img * p.rpi + b;
+    if (c < ce) {
+      const long long t = st.last_tok[row];
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (t >= 0 && t < nx.n_tok_rows) v = *reinterpret_cast<const uint4*>(nx.table + t * nx.ldt + c * 8);
+      *reinterpret_cast<uint4*>(nx.A[0] + row * nx.lda[0] + c * 8) = v;
+    } else {
+      c -= ce;
+      const int l = c / ch, cc = c - l * ch;
+      const long long pr = st.parent_state[row];
+      *reinterpret_cast<uint4*>(nx.A[l] + row * nx.lda[l] + nx.in_off[l] + cc * 8) =
+          *reinterpret_cast<const uint4*>(nx.hs[l] + pr * nx.H + cc * 8);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(32) beam_final_kernel(BeamState st, int n_img, int B, float T, int noise_mode,
@@ -827,7 +854,7 @@ extern "C" int dh_token_logprob(const float* logits, long long ld, int rows, int
 
 static int launch_select_beam(const SelParams& p, const int* cand_count, const int* cand_idx, const float* cand_val, int cap,
                               int n_img, int do_beam, const BeamState& st, const StepParams& sp, size_t seq_bytes,
-                              cudaStream_t s) {
+                              cudaStream_t s, const LstmNext& nx = LstmNext{}) {
   static bool attr_set = false;
   if (!attr_set) {
     DH_CUDA(cudaFuncSetAttribute(select_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -835,7 +862,7 @@ static int launch_select_beam(const SelParams& p, const int* cand_count, const i
     attr_set = true;
   }
   const size_t smem = (size_t)p.rpi * kWarpSelBytes + (do_beam ? seq_bytes : 0);
-  select_beam_kernel<<<n_img, 32 * p.rpi, smem, s>>>(p, cand_count, cand_idx, cand_val, cap, do_beam, st, sp);
+  select_beam_kernel<<<n_img, 32 * p.rpi, smem, s>>>(p, cand_count, cand_idx, cand_val, cap, do_beam, st, sp, nx);
   DH_LAUNCH_OK();
   return DH_OK;
 }
@@ -854,21 +881,52 @@ extern "C" int dh_select_candidates(const int* cand_count, const int* cand_idx, 
   return launch_select_beam(p, cand_count, cand_idx, cand_val, cand_cap, rows / rows_per_image, 0, BeamState{}, StepParams{}, 0, s);
 }
 
-extern "C" int dh_select_beam_step(const int* cand_count, const int* cand_idx, const float* cand_val, int cand_cap,
-                                   const dh_beam_state* st, int* ind, float* val, int* status, int n_img, int beam, int top_k,
-                                   float temperature, int unk, int step, int max_len, int eos, int lstm_semantics,
-                                   int noise_mode, unsigned long long seed, long long image_base, const long long* dyn,
-                                   cudaStream_t s) {
+static int select_beam_step(const int* cand_count, const int* cand_idx, const float* cand_val, int cand_cap,
+                            const dh_beam_state* st, int* ind, float* val, int* status, int n_img, int beam, int top_k,
+                            float temperature, int unk, int step, int max_len, int eos, int lstm_semantics, int noise_mode,
+                            unsigned long long seed, long long image_base, const long long* dyn, const dh_lstm_operands* next,
+                            cudaStream_t s) {
   DH_ARG(cand_count && cand_idx && cand_val && cand_cap > 0 && ind && val && status);
   DH_ARG(check_state(st, n_img, beam) && top_k >= 1 && beam <= top_k && temperature > 0.f && step >= 1);
   DH_ARG(st->seq_ld >= max_len && (size_t)beam * st->seq_ld * sizeof(int) <= 40 * 1024);
   DH_ARG(noise_mode == DH_NOISE_DETERMINISTIC || noise_mode == DH_NOISE_INJECTED);
+  LstmNext nx{};
+  if (next) {
+    DH_ARG(next->table && next->L >= 1 && next->L <= 8 && next->E % 8 == 0 && next->H % 8 == 0 && next->ldt % 8 == 0);
+    nx.table = (const uint16_t*)next->table; nx.ldt = next->ldt; nx.n_tok_rows = next->n_tok_rows;
+    nx.E = next->E; nx.H = next->H; nx.L = next->L;
+    for (int l = 0; l < next->L; ++l) {
+      DH_ARG(next->hs[l] && next->A[l] && next->lda[l] % 8 == 0 && next->in_off[l] % 8 == 0);
+      DH_ARG(((uintptr_t)next->hs[l] % 16) == 0 && ((uintptr_t)next->A[l] % 16) == 0);
+      nx.hs[l] = (const uint16_t*)next->hs[l]; nx.A[l] = (uint16_t*)next->A[l]; nx.lda[l] = next->lda[l];
+      nx.in_off[l] = next->in_off[l];
+    }
+  }
   if (n_img == 0) return DH_OK;
   SelParams p{nullptr, 0, n_img * beam, 0, beam, top_k, unk, beam, temperature, noise_mode, seed, image_base, step,
               st->done, ind, val, status, dyn};
   StepParams sp{ind, val, n_img, beam, step, max_len, eos, lstm_semantics, temperature, noise_mode, seed, image_base, dyn};
   return launch_select_beam(p, cand_count, cand_idx, cand_val, cand_cap, n_img, 1, to_state(st), sp,
-                            (size_t)beam * st->seq_ld * sizeof(int), s);
+                            (size_t)beam * st->seq_ld * sizeof(int), s, nx);
+}
+
+extern "C" int dh_select_beam_step(const int* cand_count, const int* cand_idx, const float* cand_val, int cand_cap,
+                                   const dh_beam_state* st, int* ind, float* val, int* status, int n_img, int beam, int top_k,
+                                   float temperature, int unk, int step, int max_len, int eos, int lstm_semantics,
+                                   int noise_mode, unsigned long long seed, long long image_base, const long long* dyn,
+                                   cudaStream_t s) {
+  return select_beam_step(cand_count, cand_idx, cand_val, cand_cap, st, ind, val, status, n_img, beam, top_k, temperature, unk,
+                          step, max_len, eos, lstm_semantics, noise_mode, seed, image_base, dyn, nullptr, s);
+}
+
+extern "C" int dh_select_beam_step_lstm(const int* cand_count, const int* cand_idx, const float* cand_val, int cand_cap,
+                                        const dh_beam_state* st, int* ind, float* val, int* status, int n_img, int beam,
+                                        int top_k, float temperature, int unk, int step, int max_len, int eos,
+                                        int lstm_semantics, int noise_mode, unsigned long long seed, long long image_base,
+                                        const long long* dyn, const dh_lstm_operands* next, cudaStream_t s) {
+  DH_ARG(next);
+  return select_beam_step(cand_count, cand_idx, cand_val, cand_cap, st, ind, val, status, n_img, beam, top_k, temperature, unk,
+                          step, max_len, eos, lstm_semantics, noise_mode, seed, image_base, dyn, next, s);
 }
 
 // out[row] = tlogit[row] - logsumexp(row) from the per-group (max, sum exp) pairs written by the contraction's epilogue.

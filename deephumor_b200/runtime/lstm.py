@@ -90,14 +90,15 @@ class LSTMDecoderRT:
             with ops.PROFILE.range('vocab_gemm', 2.0 * rows * self.V * H):
                 ops.gemm(ws['top'][:rows], self.Wc, ws['logits'][:rows, :self.V], bias=self.bc)
 
-    def _select(self, pl, rows, rpi, step, done, B, top_k, temperature, unk_index, noise_mode, beam_step=None):
+    def _select(self, pl, rows, rpi, step, done, B, top_k, temperature, unk_index, noise_mode, beam_step=None,
+                lstm_next=None):
         """classifier + BeamSearchHelper selection for `rows` rows (rnn_models.py:81,87-92,109-113): fused two-pass
         vocab projection (logits never stored) in tensor-core mode, materialised fp32 logits in check mode."""
         ws, beam = pl['ws'], pl['beam']
         if pl['vsel'] is not None:
             pl['vsel'].run(ws['top'][:rows], self.Wc, self.bc, B, temperature, unk_index, rpi, noise_mode, step, done,
                            pl['ind'], pl['val'], beam.status, pl['dyn'],
-                           beam_step=None if beam_step is None else (beam,) + beam_step)
+                           beam_step=None if beam_step is None else (beam,) + beam_step, lstm_next=lstm_next)
         else:
             with ops.PROFILE.range('select_beam'):
                 ops.select_tokens(ws['logits'][:rows, :self.V], self.V, B, top_k, temperature, unk_index, rpi, noise_mode,
@@ -145,18 +146,30 @@ class LSTMDecoderRT:
         self._select(pl, N, 1, p0, None, B, top_k, temperature, unk_index, noise_mode)
         beam.init(ind, val, caption, eos_index, True)
         # ---- beam phase (rnn_models.py:105-137): fixed trip count, frozen-at-break on the device
+        # the gathers of a step's operands (next token embedding, recurrent h through the beam parent) ride in the previous
+        # step's select + beam launch when the selection is fused (dh_select_beam_step_lstm); the first step takes them
+        # from a launch of their own
+        two_byte = self.dtype != torch.float32 and self.L <= 8
+        nxt_ops = None
+        if fused and two_byte and ops.FUSED_PREPARE:
+            nxt_ops = pl.get('lstm_next')
+            if nxt_ops is None:
+                nxt_ops = pl['lstm_next'] = ops.lstm_operands(self.table, [ws['hs'][l] for l in range(self.L)],
+                                                              [ws['A'][l][:R] for l in range(self.L)],
+                                                              [self.E if l == 0 else self.H for l in range(self.L)])
         for i in range(p0 + 1, max_len):
-            if self.dtype != torch.float32 and self.L <= 8:
-                ops.lstm_prepare(self.table, beam.last_tok, beam.parent_state, [ws['hs'][l] for l in range(self.L)],
-                                 [ws['A'][l][:R] for l in range(self.L)],
-                                 [self.E if l == 0 else self.H for l in range(self.L)], R)
+            if two_byte:
+                if nxt_ops is None or i == p0 + 1:
+                    ops.lstm_prepare(self.table, beam.last_tok, beam.parent_state, [ws['hs'][l] for l in range(self.L)],
+                                     [ws['A'][l][:R] for l in range(self.L)],
+                                     [self.E if l == 0 else self.H for l in range(self.L)], R)
             else:
                 ops.gather_rows(self.table, beam.last_tok, ws['A'][0][:R, :self.E])
                 self._recur(ws, R, beam.parent_state)
             self._step(ws, R, cur, beam.parent_state, logits=not fused)
             cur = 1 - cur
             self._select(pl, R, B, i, beam.done, B, top_k, temperature, unk_index, noise_mode,
-                         beam_step=(max_len, eos_index, True))
+                         beam_step=(max_len, eos_index, True), lstm_next=nxt_ops if i + 1 < max_len else None)
         beam.final(temperature, noise_mode, 0, 0, max_len + 1, max(p0 + 1, max_len), pad_index, max_len, pl['ids'],
                    pl['lens'], dyn)
 

@@ -7,7 +7,7 @@ import os
 
 import torch
 
-from .._lib import LIB, BeamState, ptr, stream
+from .._lib import LIB, BeamState, LstmOperands, ptr, stream
 
 F32, BF16, F16 = 0, 1, 2
 NOISE = {'deterministic': 0, 'injected': 1}
@@ -60,6 +60,7 @@ FUSED_STEM = os.environ.get('DH_NO_FUSED_STEM', '') == ''     # conv1 + ReLU + m
 FUSED_LSTM = os.environ.get('DH_NO_FUSED_LSTM', '') == ''     # LSTM cell update in the gate GEMM's epilogue
 LSTM_STACK = os.environ.get('DH_NO_LSTM_STACK', '') == ''     # all LSTM layers of a step in one persistent launch
 LSTM_ROTATE = os.environ.get('DH_LSTM_ROTATE', '') != ''      # ... upper layers start on the recurrent half of K (measured: no gain)
+FUSED_PREPARE = os.environ.get('DH_NO_FUSED_PREPARE', '') == ''   # next LSTM step's gathers in the select + beam launch
 FUSED_VOCAB = os.environ.get('DH_NO_FUSED_VOCAB', '') == ''   # two-pass vocab projection, logits never stored
 
 
@@ -243,6 +244,17 @@ def lstm_stack_tc(A_all, in_dims, Wp_all, bias_all, c_prev, parent, c_out, h_top
              int(LSTM_ROTATE if rotate is None else rotate), stream())
 
 
+def lstm_operands(table, hs, A, in_off):
+    """struct dh_lstm_operands for dh_select_beam_step_lstm: the gathers of lstm_prepare, described once per plan."""
+    L, H, E = len(hs), hs[0].shape[-1], table.shape[1]
+    assert L <= 8 and all(h.is_contiguous() and h.dtype == table.dtype and h.element_size() == 2 for h in hs)
+    o = LstmOperands()
+    o.table, o.ldt, o.n_tok_rows, o.E, o.H, o.L = ptr(table), _rows(table), table.shape[0], E, H, L
+    for l in range(L):
+        o.hs[l], o.A[l], o.lda[l], o.in_off[l] = ptr(hs[l]), ptr(A[l]), _rows(A[l]), in_off[l]
+    return o
+
+
 def lstm_prepare(table, tok, parent, hs, A, in_off, rows):
     """One launch for every operand of an LSTM step: A[0][:, :E] = table[tok], A[l][:, in_off[l]:+H] = hs[l][parent]."""
     import ctypes
@@ -331,8 +343,9 @@ class VocabSelect:
         return A.dtype in (torch.bfloat16, torch.float16) and top_k <= (V + 31) // 32
 
     def run(self, A, W, bias, beam, temperature, unk, rows_per_image, noise_mode, step, done, ind, val, status, dyn,
-            seed=0, image_base=0, beam_step=None):
-        """beam_step = (Beam, max_len, eos, lstm_semantics): also run that image's beam step in the same launch."""
+            seed=0, image_base=0, beam_step=None, lstm_next=None):
+        """beam_step = (Beam, max_len, eos, lstm_semantics): also run that image's beam step in the same launch;
+        lstm_next (ops.lstm_operands): ... and gather the next LSTM step's operands for the image's rows."""
         import ctypes
         rows, K = A.shape
         assert rows <= self.rows and W.shape == (self.V, K) and W.dtype == A.dtype
@@ -353,10 +366,13 @@ class VocabSelect:
             else:
                 bm, max_len, eos, lstm_sem = beam_step
                 assert rows == bm.n_img * bm.beam and rows_per_image == bm.beam == beam
-                LIB.call('dh_select_beam_step', ptr(self.count), ptr(self.idx), ptr(self.val), self.cap,
-                         ctypes.byref(bm.c), ptr(ind), ptr(val), ptr(status), bm.n_img, beam, self.top_k,
-                         float(temperature), unk, step, max_len, eos, int(lstm_sem), noise_mode, seed, image_base,
-                         ptr(dyn), stream())
+                common = (ptr(self.count), ptr(self.idx), ptr(self.val), self.cap, ctypes.byref(bm.c), ptr(ind), ptr(val),
+                          ptr(status), bm.n_img, beam, self.top_k, float(temperature), unk, step, max_len, eos,
+                          int(lstm_sem), noise_mode, seed, image_base, ptr(dyn))
+                if lstm_next is None:
+                    LIB.call('dh_select_beam_step', *common, stream())
+                else:
+                    LIB.call('dh_select_beam_step_lstm', *common, ctypes.byref(lstm_next), stream())
 
 
 class Beam:

@@ -24,7 +24,7 @@ extern "C" {
 typedef struct CUstream_st* cudaStream_t;
 #endif
 
-#define DH_VERSION 113
+#define DH_VERSION 114
 
 #define DH_OK 0
 #define DH_ERR_ARG (-1)
@@ -219,6 +219,21 @@ int dh_select_beam_step(const int* cand_count, const int* cand_idx, const float*
                         const dh_beam_state* st, int* ind, float* val, int* status, int n_img, int beam, int top_k,
                         float temperature, int unk, int step, int max_len, int eos, int lstm_semantics, int noise_mode,
                         unsigned long long seed, long long image_base, const long long* dyn, cudaStream_t stream);
+/* The same launch, followed -- per image, once its beam step has chosen tokens and parents -- by the operand gathers of the
+ * NEXT LSTM time step (what dh_lstm_prepare does in a launch of its own; rnn_models.py:107,135-137): A[0][r, 0:E] =
+ * table[last_tok[r]] and A[l][r, in_off[l] : +H] = hs[l][parent_state[r]] for the image's beam rows.  Images that are done
+ * keep their operands. */
+typedef struct dh_lstm_operands {
+  const void* table; long long ldt; long long n_tok_rows;   /* embedding table [n_tok_rows, ldt] (2-byte elements) */
+  int E, H, L;                                               /* E, H multiples of 8; L <= 8 */
+  const void* hs[8];                                         /* [*, H] contiguous per layer */
+  void* A[8]; long long lda[8]; int in_off[8];               /* operand buffers, leading dimensions, column of the h half */
+} dh_lstm_operands;
+int dh_select_beam_step_lstm(const int* cand_count, const int* cand_idx, const float* cand_val, int cand_cap,
+                             const dh_beam_state* st, int* ind, float* val, int* status, int n_img, int beam, int top_k,
+                             float temperature, int unk, int step, int max_len, int eos, int lstm_semantics, int noise_mode,
+                             unsigned long long seed, long long image_base, const long long* dyn,
+                             const dh_lstm_operands* next, cudaStream_t stream);
 int dh_beam_init(const dh_beam_state* st, const int* ind0, const float* val0, const int* prefix, long long prefix_ld,
                  int prefix_rows, int prefix_len, int n_img, int beam, int eos, int lstm_semantics, cudaStream_t stream);
 int dh_beam_step(const dh_beam_state* st, const int* new_ind, const float* new_val, int n_img, int beam, int step,
