@@ -394,13 +394,21 @@ __device__ void warp_select(const SelParams& p, int r, int img, int nc_total, co
   const float* vv = staged ? w.a_val : gv;
   // ---- exact k-th largest among the candidates: #{> v} < top_k <= #{>= v}; -inf if fewer than top_k candidates
   float kth = -INFINITY;
-  for (int c = lane; c < nc; c += 32) {
-    const float v = vv[c];
-    int gt = 0, ge = 0;
-    for (int j = 0; j < nc; ++j) { const float o = vv[j]; gt += o > v; ge += o >= v; }
-    if (gt < p.top_k && p.top_k <= ge) kth = v;
+  if (nc <= 64 && nc >= p.top_k && nc - p.top_k < 16) {
+    // the usual case (the fused projection hands over ~top_k + 1 candidates): the top_k-th largest of nc values is the
+    // (nc - top_k + 1)-th smallest -- one or two rounds of warp-wide minimum extraction instead of O(nc^2 / 32) rank counts
+    const unsigned int a = lane < nc ? order_key(vv[lane]) : 0xffffffffu;
+    const unsigned int b = 32 + lane < nc ? order_key(vv[32 + lane]) : 0xffffffffu;
+    kth = key_to_float(warp_mth_smallest64(a, b, nc - p.top_k + 1, lane));
+  } else {
+    for (int c = lane; c < nc; c += 32) {
+      const float v = vv[c];
+      int gt = 0, ge = 0;
+      for (int j = 0; j < nc; ++j) { const float o = vv[j]; gt += o > v; ge += o >= v; }
+      if (gt < p.top_k && p.top_k <= ge) kth = v;
+    }
+    kth = dh_warp_max(kth);
   }
-  kth = dh_warp_max(kth);
   // ---- survivors: value >= k-th largest (ties kept) and id != <unk>
   int ns = 0;
   for (int c0 = 0; c0 < nc; c0 += 32) {
