@@ -33,6 +33,7 @@ struct TcParams {
   int m_blocks, n_blocks, k_chunks;
   int conv;                               // 0: A via tiled TMA {K, M}; 1: A via im2col TMA {C, W, H, N}
   int HoWo, Wo, c_chunks, kw, stride, pad;
+  int k1_chunks, stride2;                 // > 0: K chunks >= k1_chunks come from a SECOND 1x1 source (map_r) of stride2
   const float* bias;
   const void* res; long long ldr; int res_dtype;
   void* out; long long ldc; int out_dtype;
@@ -286,6 +287,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tma_prefetch_desc(&map_b);
     if (p.tma_store) tma_prefetch_desc(&map_c);
     if (p.res_chunks) { tma_prefetch_desc(&map_r); tma_prefetch_desc(&map_i); }
+    if (p.k1_chunks) tma_prefetch_desc(&map_r);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -356,7 +358,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (cta_rank == 0) mbar_expect_tx(full_bar(stage), C::kStageBytes * CG);
           if (PAIR) {
             const uint32_t fb = mapa_u32(full_bar(stage), 0);
-            if (p.conv) {
+            if (p.conv && p.k1_chunks && kc >= p.k1_chunks) {
+              // second source of a dual 1x1 convolution (the bottleneck's downsample branch, torchvision resnet.py:157-158)
+              tma_load_im2col_pair(sa, &map_r, fb, (kc - p.k1_chunks) * BK, qw * p.stride2, ph * p.stride2, img, 0, 0);
+            } else if (p.conv) {
               const int tap = kc / p.c_chunks, c0 = (kc - tap * p.c_chunks) * BK;
               const int r = tap / p.kw, s = tap - r * p.kw;
               tma_load_im2col_pair(sa, &map_a, fb, c0, qw * p.stride - p.pad, ph * p.stride - p.pad, img, (uint16_t)s,
@@ -366,7 +371,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             tma_load_2d_pair(sb, &map_b, fb, kc * BK, nb0);
           } else {
-            if (p.conv) {
+            if (p.conv && p.k1_chunks && kc >= p.k1_chunks) {
+              tma_load_im2col(sa, &map_r, full_bar(stage), (kc - p.k1_chunks) * BK, qw * p.stride2, ph * p.stride2, img, 0, 0);
+            } else if (p.conv) {
               const int tap = kc / p.c_chunks, c0 = (kc - tap * p.c_chunks) * BK;
               const int r = tap / p.kw, s = tap - r * p.kw;
               tma_load_im2col(sa, &map_a, full_bar(stage), c0, qw * p.stride - p.pad, ph * p.stride - p.pad, img,
@@ -1025,8 +1032,9 @@ int pick_bn(int M, int N) {
   return (t256 >= 2ll * (g_num_sms ? g_num_sms : 148) || N % 256 == 0 && t256 >= (g_num_sms ? g_num_sms : 148)) ? 256 : 128;
 }
 
-int dispatch(const CUtensorMap& ma, const void* W, long long ldw, TcParams& p, int bn, cudaStream_t s) {
-  CUtensorMap mb, mc = ma, mr = ma, mi = ma;
+int dispatch(const CUtensorMap& ma, const void* W, long long ldw, TcParams& p, int bn, cudaStream_t s,
+             const CUtensorMap* second_a = nullptr) {
+  CUtensorMap mb, mc = ma, mr = second_a ? *second_a : ma, mi = ma;
   // CTA pairs (cta_group::2) for the 128- and 256-wide tiles whenever there are at least two M blocks to pair up
   static const bool pair_ok = !getenv("DH_TC_NO_PAIR");
   // ... and the K loop is long enough (>= 8 chunks incl. residual chunks) to amortise the pair's cross-CTA barrier round
@@ -1269,6 +1277,22 @@ extern "C" int dh_vocab_candidates(const void* A, long long lda, const void* W, 
                     stream);
 }
 
+// im2col-mode tensor map over an NHWC activation tensor: box = {64 channels, 128 output pixels}
+static int make_map_im2col(CUtensorMap* map, const void* x, int n, int H, int W, int Cin, int kh, int kw, int stride, int pad,
+                           int dtype) {
+  cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+  int lower[2] = {-pad, -pad};
+  int upper[2] = {pad - (kw - 1), pad - (kh - 1)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = g_encode_im2col(map, dtype == DH_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                               const_cast<void*>(x), dims, strides, lower, upper,
+                               (cuuint32_t)BK, (cuuint32_t)BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return dh_fail(DH_ERR_ARG, "cuTensorMapEncodeIm2col rejected the activation tensor", __FILE__, __LINE__);
+  return DH_OK;
+}
+
 // x [n,H,W,Cin] NHWC (Cin % 64 == 0), w [Cout][kh][kw][Cin] (BN folded), y [n,Ho,Wo,Cout]; all bf16 or all f16.
 extern "C" int dh_conv2d_tc(const void* x, const void* w, const float* bias, const void* residual, void* y, int n, int H,
                             int W, int Cin, int Cout, int kh, int kw, int stride, int pad, int relu, int dtype, int tile_n,
@@ -1291,17 +1315,43 @@ extern "C" int dh_conv2d_tc(const void* x, const void* w, const float* bias, con
   p.bias = bias; p.res = residual; p.ldr = Cout; p.res_dtype = dtype;
   p.out = y; p.ldc = Cout; p.out_dtype = dtype; p.relu = relu;
   CUtensorMap ma;
-  cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
-  cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
-  int lower[2] = {-pad, -pad};
-  int upper[2] = {pad - (kw - 1), pad - (kh - 1)};
-  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-  CUresult r = g_encode_im2col(&ma, dtype == DH_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
-                               const_cast<void*>(x), dims, strides, lower, upper,
-                               (cuuint32_t)BK, (cuuint32_t)BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return dh_fail(DH_ERR_ARG, "cuTensorMapEncodeIm2col rejected the activation tensor", __FILE__, __LINE__);
+  rc = make_map_im2col(&ma, x, n, H, W, Cin, kh, kw, stride, pad, dtype);
+  if (rc) return rc;
   return dispatch(ma, w, p.K, p, tile_n ? tile_n : pick_bn(p.M, Cout), stream);
+}
+
+// The first bottleneck of a ResNet stage ends in relu(bn3(conv3(y2)) + bn_d(conv_d(x))) (torchvision resnet.py:154-161 with
+// the downsample branch :157-158): two 1x1 convolutions onto the same output grid.  Here they are ONE contraction over
+// K = C1 + C2 -- chunks [0, C1/64) from y2 (stride 1), the rest from the block input x (stride2) through a second im2col
+// map, weights [W3 | Wd] concatenated along K, bias = b3 + bd -- so the downsample output is neither written nor re-read
+// (1.6 GB of HBM traffic per 512 images in layer1) and no residual chunks ride the tensor core.
+extern "C" int dh_conv1x1_dual_tc(const void* x1, const void* x2, const void* w_cat, const float* bias, void* y, int n, int Ho,
+                                  int Wo, int C1, int H2, int W2, int C2, int stride2, int Cout, int relu, int dtype,
+                                  int tile_n, cudaStream_t stream) {
+  DH_ARG(dtype == DH_BF16 || dtype == DH_F16);
+  DH_ARG(x1 && x2 && w_cat && y && n >= 0 && C1 > 0 && C1 % 64 == 0 && C2 > 0 && C2 % 64 == 0 && Cout > 0 && Cout % 4 == 0);
+  DH_ARG(stride2 >= 1 && (H2 - 1) / stride2 + 1 == Ho && (W2 - 1) / stride2 + 1 == Wo && Ho > 0 && Wo > 0);
+  DH_ARG(((uintptr_t)x1 % 16) == 0 && ((uintptr_t)x2 % 16) == 0 && ((uintptr_t)w_cat % 16) == 0);
+  DH_ARG(tile_n == 0 || tile_n == 64 || tile_n == 128 || tile_n == 256);
+  if (n == 0) return DH_OK;
+  int rc = tc_init();
+  if (rc) return rc;
+  const long long M = (long long)n * Ho * Wo;
+  DH_ARG(M < (1ll << 31));
+  TcParams p{};
+  p.M = (int)M; p.N = Cout; p.K = C1 + C2;
+  p.k_chunks = p.K / BK;
+  p.conv = 1; p.HoWo = Ho * Wo; p.Wo = Wo; p.c_chunks = C1 / BK; p.kw = 1; p.stride = 1; p.pad = 0;
+  p.k1_chunks = C1 / BK; p.stride2 = stride2;
+  p.ab_dtype = dtype;
+  p.bias = bias;
+  p.out = y; p.ldc = Cout; p.out_dtype = dtype; p.relu = relu;
+  CUtensorMap ma, ma2;
+  rc = make_map_im2col(&ma, x1, n, Ho, Wo, C1, 1, 1, 1, 0, dtype);
+  if (rc) return rc;
+  rc = make_map_im2col(&ma2, x2, n, H2, W2, C2, 1, 1, stride2, 0, dtype);
+  if (rc) return rc;
+  return dispatch(ma, w_cat, p.K, p, tile_n ? tile_n : pick_bn(p.M, Cout), stream, &ma2);
 }
 
 // Non-zero after a watchdog trap inside gemm_tc_kernel: 1 producer, 2 MMA/accumulator, 3 MMA/operands, 4 epilogue.

@@ -74,6 +74,13 @@ class EncoderRT:
                     c1=mk(q + '.conv1', q + '.bn1', 1, 0), c2=mk(q + '.conv2', q + '.bn2', stride, 1),
                     c3=mk(q + '.conv3', q + '.bn3', 1, 0),
                     down=mk(q + '.downsample.0', q + '.downsample.1', stride, 0) if b == 0 else None))
+        if tdtype != torch.float32:
+            # first block of every stage: conv3 and the downsample branch as ONE contraction over [y2 | x] (dh_conv1x1_dual_tc)
+            for blk in self.blocks:
+                if blk['down'] is not None:
+                    c3, dn = blk['c3'], blk['down']
+                    blk['dual_w'] = torch.cat([c3.w.reshape(c3.cout, -1), dn.w.reshape(dn.cout, -1)], dim=1).contiguous()
+                    blk['dual_b'] = (c3.bias + dn.bias).contiguous()
         W = sd[prefix + '.linear.weight'].float()
         b = sd[prefix + '.linear.bias'].float()
         g, be = sd[prefix + '.bn.weight'].float(), sd[prefix + '.bn.bias'].float()
@@ -151,6 +158,12 @@ class EncoderRT:
         for i, blk in enumerate(self.blocks):
             y1 = self._conv(f'b{i}c1', x, blk['c1'], True)
             y2 = self._conv(f'b{i}c2', y1, blk['c2'], True)
+            if 'dual_w' in blk and ops.DUAL_CONV:
+                n, Ho, Wo, _ = y2.shape
+                out = self._buf(f'b{i}c3', (n, Ho, Wo, blk['c3'].cout))
+                ops.conv1x1_dual(y2, x, blk['dual_w'], blk['dual_b'], out, blk['down'].stride, True)
+                x = out
+                continue
             idn = self._conv(f'b{i}ds', x, blk['down'], False) if blk['down'] is not None else x
             x = self._conv(f'b{i}c3', y2, blk['c3'], True, residual=idn)
         return x

@@ -61,6 +61,7 @@ FUSED_LSTM = os.environ.get('DH_NO_FUSED_LSTM', '') == ''     # LSTM cell update
 LSTM_STACK = os.environ.get('DH_NO_LSTM_STACK', '') == ''     # all LSTM layers of a step in one persistent launch
 LSTM_ROTATE = os.environ.get('DH_LSTM_ROTATE', '') != ''      # ... upper layers start on the recurrent half of K (measured: no gain)
 FUSED_PREPARE = os.environ.get('DH_NO_FUSED_PREPARE', '') == ''   # next LSTM step's gathers in the select + beam launch
+DUAL_CONV = os.environ.get('DH_NO_DUAL_CONV', '') == ''       # conv3 + downsample of a stage's first block as one contraction
 FUSED_VOCAB = os.environ.get('DH_NO_FUSED_VOCAB', '') == ''   # two-pass vocab projection, logits never stored
 
 
@@ -114,6 +115,18 @@ def conv2d(x, w, bias, y, stride, pad, relu, residual=None, tile_n=0):
         assert x.dtype == w.dtype == y.dtype and (residual is None or residual.dtype == x.dtype)
         LIB.call('dh_conv2d_tc', ptr(x), ptr(w), ptr(bias), ptr(residual), ptr(y), n, H, W, Cin, Cout, kh, kw,
                  stride, pad, int(relu), code(x), tile_n, stream())
+
+
+def conv1x1_dual(x1, x2, w_cat, bias, y, stride2, relu, tile_n=0):
+    """y = act(x1 * W1 + x2[::stride2, ::stride2] * W2 + bias) with w_cat = [W1 | W2] ([Cout, C1 + C2]): conv3 and the
+    downsample branch of a stage's first bottleneck in one contraction (dh_conv1x1_dual_tc)."""
+    n, Ho, Wo, C1 = x1.shape
+    _, H2, W2, C2 = x2.shape
+    Cout = w_cat.shape[0]
+    assert x1.is_contiguous() and x2.is_contiguous() and y.is_contiguous() and w_cat.is_contiguous()
+    assert w_cat.shape[1] == C1 + C2 and x1.dtype == x2.dtype == w_cat.dtype == y.dtype and y.shape == (n, Ho, Wo, Cout)
+    LIB.call('dh_conv1x1_dual_tc', ptr(x1), ptr(x2), ptr(w_cat), ptr(bias), ptr(y), n, Ho, Wo, C1, H2, W2, C2, stride2, Cout,
+             int(relu), code(x1), tile_n, stream())
 
 
 def im2col_stem(images, A, kh, kw, stride, pad):

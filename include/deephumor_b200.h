@@ -24,7 +24,7 @@ extern "C" {
 typedef struct CUstream_st* cudaStream_t;
 #endif
 
-#define DH_VERSION 114
+#define DH_VERSION 115
 
 #define DH_OK 0
 #define DH_ERR_ARG (-1)
@@ -89,6 +89,13 @@ int dh_gemm_tc(const void* A, long long lda, const void* W, long long ldw, int a
 int dh_conv2d_tc(const void* x, const void* w, const float* bias, const void* residual, void* y, int n, int H, int W,
                  int Cin, int Cout, int kh, int kw, int stride, int pad, int relu, int dtype, int tile_n,
                  cudaStream_t stream);
+/* relu(conv3(y2) + downsample(x)) of a ResNet stage's first bottleneck (torchvision resnet.py:154-161) as ONE contraction
+ * over K = C1 + C2: x1 = y2 [n,Ho,Wo,C1] (1x1, stride 1), x2 = the block input [n,H2,W2,C2] (1x1, stride2, so that
+ * (H2 - 1) / stride2 + 1 == Ho), w_cat [Cout][C1 + C2] = [W3 | Wd] (BN folded), bias = b3 + bd.  The downsample output
+ * is neither written nor re-read.  C1, C2 % 64 == 0. */
+int dh_conv1x1_dual_tc(const void* x1, const void* x2, const void* w_cat, const float* bias, void* y, int n, int Ho, int Wo,
+                       int C1, int H2, int W2, int C2, int stride2, int Cout, int relu, int dtype, int tile_n,
+                       cudaStream_t stream);
 /* 3x3 / stride 1 / pad 1 convolution (+ bias + ReLU) that loads each input pixel ONCE per tile (torchvision resnet.py:146-148,
  * conv2 of the layer1 / layer2 bottlenecks): an 8 x 16 output rectangle per tile, its 10 x 18 halo fetched by one tiled TMA
  * load per 64-channel chunk, the nine taps contracted as shifted UMMA-descriptor views of the same shared memory

@@ -83,6 +83,26 @@ def test_conv2d_tc_im2col_tma(n, H_, Cin, Cout, k, s, p, dt):
     assert torch.equal(y2.view_as(y), y)
 
 
+@pytest.mark.parametrize('n,Ho,C1,C2,Cout,s2', [(3, 56, 64, 64, 256, 1), (5, 28, 128, 256, 512, 2), (9, 14, 256, 512, 1024, 2),
+                                              (40, 7, 512, 1024, 2048, 2), (2, 5, 64, 128, 64, 2)])
+def test_conv1x1_dual_conv3_plus_downsample(n, Ho, C1, C2, Cout, s2):
+    """relu(conv3(y2) + downsample(x)) of a stage's first bottleneck as one contraction over [y2 | x] (dh_conv1x1_dual_tc:
+    second im2col source with its own stride) against a float64 reference (torchvision resnet.py:154-161)."""
+    dt = torch.float16
+    H2 = Ho * s2 - (s2 - 1) if s2 > 1 and Ho == 5 else Ho * s2          # an odd input size too: (H2 - 1) // s2 + 1 == Ho
+    y2 = rnd(n, C1, Ho, Ho, seed=1).to(dt)
+    x = rnd(n, C2, H2, H2, seed=2).to(dt)
+    w3, wd = rnd(Cout, C1, 1, 1, seed=3, scale=0.05).to(dt), rnd(Cout, C2, 1, 1, seed=4, scale=0.05).to(dt)
+    b3, bd = rnd(Cout, seed=5), rnd(Cout, seed=6)
+    ref = F.relu(F.conv2d(y2.double(), w3.double(), b3.double()) + F.conv2d(x.double(), wd.double(), bd.double(), s2))
+    ref = ref.float().permute(0, 2, 3, 1).contiguous()
+    w_cat = torch.cat([w3.view(Cout, C1), wd.view(Cout, C2)], 1).contiguous().to(DEV)
+    out = torch.empty(n, Ho, Ho, Cout, dtype=dt, device=DEV)
+    ops.conv1x1_dual(y2.permute(0, 2, 3, 1).contiguous().to(DEV), x.permute(0, 2, 3, 1).contiguous().to(DEV), w_cat,
+                     (b3 + bd).to(DEV), out, s2, True)
+    assert H.rel_err(out.float(), ref) < 5e-4
+
+
 @pytest.mark.parametrize('dt', [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize('n,H_,Cin,Cout', [(2, 56, 64, 64), (3, 28, 128, 128), (1, 30, 64, 128), (5, 56, 128, 64), (2, 33, 192, 64)])
 def test_conv3x3_halo_kernel(n, H_, Cin, Cout, dt):
