@@ -90,3 +90,30 @@ def test_vocab_save_load(tmp_path):
     p = str(tmp_path / 'v.txt')
     v.save(p)
     assert Vocab.load(p).tokens == v.tokens
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """The host structs passed by pointer through the C ABI (dh_beam_state, dh_lstm_operands) are mirrored by hand in
+    deephumor_b200/_lib.py: compile the header with gcc and compare sizes and field offsets."""
+    import ctypes
+    import shutil
+    import subprocess
+    from deephumor_b200 import _lib
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('gcc not available')
+    structs = {'dh_beam_state': _lib.BeamState, 'dh_lstm_operands': _lib.LstmOperands}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{_lib.HEADER}"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'layout'
+    subprocess.run([gcc, '-o', str(exe), str(src)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f'{cname}.{fname}']) == getattr(cls, fname).offset, (cname, fname)
