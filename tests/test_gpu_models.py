@@ -290,3 +290,26 @@ def test_empty_and_chunk_crossing_batches():
         b = m.generate(imgs[255:257], image_base=255, **kw)
     assert ids.shape == (257, 6)
     assert torch.equal(ids[:2], a[0]) and torch.equal(ids[255:], b[0]) and torch.equal(lens[255:], b[1])
+
+
+def test_trunk_pass_size_does_not_change_the_features():
+    """Device-resident batches of >= 2048 images run the trunk in 1024-image passes, smaller ones / host batches in 512
+    (runtime/encoder.py): every output element is one fixed-order K loop whatever the pass size, so the embeddings of the
+    same 2048 images must be bit-identical between 1024-image passes and 256-image passes."""
+    from deephumor_b200.runtime import encoder as enc_rt, ops
+    fx = H.load_fixture('small', 'lstm')
+    m, *_ = build(fx, 'bf16')
+    imgs = torch.empty(2048, 3, 224, 224, device='cuda')
+    ops.synth_images(imgs, 0, 0)
+    rt = m.encoder._rt()
+    with torch.no_grad():
+        assert enc_rt.TRUNK_CHUNK_DEVICE == 1024
+        e_big = m.encoder(imgs).clone()
+        saved = (rt.chunk, enc_rt.TRUNK_CHUNK_DEVICE)
+        try:
+            rt.chunk, enc_rt.TRUNK_CHUNK_DEVICE = 256, 256
+            e_small = m.encoder(imgs).clone()
+        finally:
+            rt.chunk, enc_rt.TRUNK_CHUNK_DEVICE = saved
+    assert torch.isfinite(e_big).all() and torch.equal(e_big, e_small)
+
