@@ -44,6 +44,23 @@ TRUNK_CHUNK_DEVICE = int(_os.environ.get('DH_TRUNK_CHUNK_DEVICE', '1024'))
 H2D_RAMP = tuple(int(v) for v in _os.environ.get('DH_H2D_RAMP', '64,192,256').split(','))
 
 
+def h2d_schedule(n_images, chunk, ramp=None):
+    """Sizes of the host->device copies / trunk passes of a pinned host batch: a ramp (64, 192, 256 by default), then full
+    trunk chunks (512 images run the layer3/4 convolutions ~6 % faster per image than 256: fewer partial waves;
+    profiles/r01_bench_conv_n512.txt).  Copies are sequential and faster than the trunk, so the GPU only starves when a
+    chunk grows faster than the trunk of the previous one takes: a ramp step below 256 is taken while at least twice its
+    size is left, the 256 step only when more than a full chunk is left."""
+    sizes, left = [], n_images
+    for want in (H2D_RAMP if ramp is None else ramp):
+        if want <= chunk and ((left >= 2 * want) if want < 256 else (left > chunk)):
+            sizes.append(want)
+            left -= want
+    while left > 0:
+        sizes.append(min(chunk, left))
+        left -= sizes[-1]
+    return sizes
+
+
 class EncoderRT:
     """prefix = 'encoder' (ImageEncoder) or 'encoder.image_encoder' (inside ImageLabelEncoder)."""
 
@@ -185,18 +202,7 @@ class EncoderRT:
             self._copied = [torch.cuda.Event(), torch.cuda.Event()]
             self._consumed = [torch.cuda.Event(), torch.cuda.Event()]
         cs = self._copy_stream
-        # ramp, then full trunk chunks (512 images run the layer3/4 convolutions ~6 % faster per image than 256: fewer
-        # partial waves; profiles/r01_bench_conv_n512.txt).  Copies are sequential and faster than the trunk, so the GPU
-        # only starves when a chunk grows faster than the trunk of the previous one takes: a ramp step is taken while
-        # at least twice its size is left.
-        sizes, left = [], N
-        for want in H2D_RAMP:
-            if (left >= 2 * want) if want < 256 else (left > self.chunk):
-                sizes.append(want)
-                left -= want
-        while left > 0:
-            sizes.append(min(self.chunk, left))
-            left -= sizes[-1]
+        sizes = h2d_schedule(N, self.chunk)
         bufs = [self._buf(f'h2d{b}', (self.chunk,) + tuple(images.shape[1:]), images.dtype) for b in range(2)]
         cs.wait_stream(main)                           # earlier readers of the staging buffers are done
         i0 = 0

@@ -117,3 +117,17 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
         assert int(got[cname]) == ctypes.sizeof(cls), cname
         for fname, _ in cls._fields_:
             assert int(got[f'{cname}.{fname}']) == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_host_batch_copy_schedule():
+    """runtime/encoder.h2d_schedule: every image is copied exactly once, no pass exceeds the trunk chunk, the ramp is only
+    taken when enough images are left, and the default schedule of the benchmark batch is 64 / 192 / 256."""
+    from deephumor_b200.runtime.encoder import h2d_schedule
+    assert h2d_schedule(512, 512, (64, 192, 256)) == [64, 192, 256]
+    assert h2d_schedule(65, 512, (64, 192, 256)) == [65]
+    assert h2d_schedule(4096, 512, (64, 192, 256))[:5] == [64, 192, 256, 512, 512]
+    for n in (0, 1, 63, 64, 127, 128, 300, 511, 512, 513, 1000, 4096, 8191):
+        for chunk in (100, 256, 512, 1024):
+            sizes = h2d_schedule(n, chunk, (64, 192, 256))
+            assert sum(sizes) == n and all(0 < s <= chunk for s in sizes)      # a pass never exceeds the staging buffer
+
