@@ -273,7 +273,7 @@ def run_ours(args):
     sustained = pk.get('bf16_tflops_sustained', pk.get('bf16_tflops'))
     line['step_tflops'] = round(flops_step / (ms / args.steps / 1e3) / 1e12, 2)
     if prof and prof.get('vocab_gemm'):
-        n, tot_ms, flops = prof['vocab_gemm']
+        n, tot_ms, flops, _ = prof['vocab_gemm']
         ach = flops / (tot_ms / 1e3) / 1e12
         tensor_path = args.precision == 'bf16'
         line['roofline'] = {'kernel': 'gemm_tc_kernel, candidate-compaction epilogue (vocab projection [rows,512]x[512,36541], '

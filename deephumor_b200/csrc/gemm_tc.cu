@@ -62,6 +62,14 @@ struct TcParams {
   const float* bias_l[kMaxLayers]; const float* cprev_l[kMaxLayers]; float* cout_l[kMaxLayers];
   void* h0_l[kMaxLayers]; long long ldh0_l[kMaxLayers]; void* h1_l[kMaxLayers]; long long ldh1_l[kMaxLayers];
   int* ready;
+  // Three row-major destinations for one contraction (dh_gemm_tc_split3: fused Q | K | V projection): N tile n0 goes to
+  // destination n0 / split_n through map_c / map_r / map_i, at column n0 % split_n.  0: single destination.
+  int split_n;
+  // Sampled vocab selection (dh_vocab_*_fix): n_offset = first N block visited by a strided pass 1; cond_mode 1 = run only
+  // if some row's candidate count lies outside [cond_min, cond_max] (the sampled threshold missed), 2 = run only if
+  // *cond_flag != 0; redo (nullable) = rows whose candidates this launch may emit.
+  int n_offset, cond_mode, cond_min, cond_max;
+  const int* cond_count; int* cond_flag; const unsigned char* redo;
 };
 
 // ------------------------------------------------------------------------------------------- PTX wrappers
@@ -282,12 +290,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                                     C::kBiasBytes + 8 * (2 * C::kStages + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p.cond_mode) {
+    // fix-up launches of the sampled vocab selection: nothing to do unless a row's sampled threshold missed.  Every CTA
+    // (both CTAs of a pair) evaluates the same predicate on the same data, before any barrier / TMEM set-up.
+    int bad = 0;
+    if (p.cond_mode == 1) {
+      for (int i = threadIdx.x; i < p.M; i += kThreads) {
+        const int c = __ldg(p.cond_count + i);
+        bad |= (c < p.cond_min) | (c > p.cond_max);
+      }
+      if (blockIdx.x == 0 && threadIdx.x == 0 && p.cond_flag) *p.cond_flag = 0;      // set again by dh_vocab_threshold_fix
+    } else {
+      bad = *reinterpret_cast<const volatile int*>(p.cond_flag) != 0;
+    }
+    if (!__syncthreads_or(bad)) return;
+  }
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     if (p.tma_store) tma_prefetch_desc(&map_c);
     if (p.res_chunks) { tma_prefetch_desc(&map_r); tma_prefetch_desc(&map_i); }
     if (p.k1_chunks) tma_prefetch_desc(&map_r);
+    if (p.split_n) { tma_prefetch_desc(&map_r); tma_prefetch_desc(&map_i); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -331,7 +355,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int tile = tile0; tile < tiles; tile += tstride) {
         int layer = 0, rt = tile;                                // EPI 3: layer-major tile order of a stacked LSTM step
         if (EPI == 3 && p.layers > 1) { layer = tile / p.tiles_per_layer; rt = tile - layer * p.tiles_per_layer; }
-        const int m0 = tile_m0(rt), n0 = (rt % p.n_blocks) * BN * p.n_stride;
+        const int m0 = tile_m0(rt), n0 = ((rt % p.n_blocks) * p.n_stride + p.n_offset) * BN;
         // an M block past the end (odd block count, second CTA of the last pair) re-loads the last valid block: its
         // accumulator is never stored, and every TMA coordinate stays inside the tensor
         const int m0l = min(m0, (dh_cdiv_dev(p.M, BM) - 1) * BM);
@@ -457,7 +481,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int tile = tile0; tile < tiles; tile += tstride, ++it) {
           int layer = 0, rt = tile;
           if (p.layers > 1) { layer = tile / p.tiles_per_layer; rt = tile - layer * p.tiles_per_layer; }
-          const int m0 = tile_m0(rt), n0 = (rt % p.n_blocks) * BN * p.n_stride;
+          const int m0 = tile_m0(rt), n0 = ((rt % p.n_blocks) * p.n_stride + p.n_offset) * BN;
           const bool stack = p.layers > 1;
           const float* bias = stack ? p.bias_l[layer] : p.bias;
           const float* c_prev = stack ? p.cprev_l[layer] : p.c_prev;
@@ -600,13 +624,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // ---- selection epilogues: every thread owns one accumulator row; nothing of the [M,N] product is stored.
       const int row_l = ew * 32 + lane;
       int it = 0;
+      // Candidates of this thread's slice are parked in shared memory (the store staging area is idle in this mode) and
+      // appended with ONE atomic per row and tile.  The atomic's round trip to L2 is taken OFF the per-tile critical path:
+      // it is issued when a tile's scan ends and its result (the list slot) is consumed one tile later, after the next
+      // accumulator has been drained -- with unrelated rows nearly every warp appends something for every tile, and waiting
+      // for the slot right away doubled the kernel's time (ncu: 155 us, tensor pipe 34 % active).  Two parking buffers.
+      constexpr int kPend = 8;
+      uint2* pend_base = reinterpret_cast<uint2*>(staging) + etid * kPend;
+      int def_n = 0, def_slot = 0;
+      long long def_row = 0;
+      const uint2* def_buf = pend_base;
+      auto write_out = [&](long long row, int slot, int n, const uint2* buf) {
+        for (int i = 0; i < n; ++i) {
+          if (slot + i < p.cand_cap) {
+            p.cand_idx[row * p.cand_cap + slot + i] = (int)buf[i].x;
+            p.cand_val[row * p.cand_cap + slot + i] = __uint_as_float(buf[i].y);
+          }
+        }
+      };
       for (int tile = tile0; tile < tiles; tile += tstride, ++it) {
-        const int m0 = tile_m0(tile), n0 = (tile % p.n_blocks) * BN * p.n_stride;
+        const int m0 = tile_m0(tile), n0 = ((tile % p.n_blocks) * p.n_stride + p.n_offset) * BN;
         const int as = it & 1;
         const long long row = (long long)m0 + row_l;
         const bool row_ok = row < p.M;
         // issued before the wait on the accumulator so that its L2 round trip is hidden
-        const float thr = (EPI == 2 && row_ok) ? __ldg(p.thresh + row) : INFINITY;
+        const bool emit = EPI == 2 && row_ok && (!p.redo || __ldg(p.redo + row));
+        const float thr = emit ? __ldg(p.thresh + row) : INFINITY;
         const int tcol = (EPI == 4 && row_ok) ? (int)__ldg(p.targets + row) : -1;
         mbar_wait(tfull_bar(as), (it >> 1) & 1, p.error, 4);
         tc_fence_after();
@@ -615,20 +658,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int i = etid; i < BN; i += 256) bias_s[i] = (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
         asm volatile("bar.sync 1, 256;" ::: "memory");
         // candidates are finite logits >= thresh[row]; clamping to -FLT_MAX folds the "> -inf" test into one compare
-        const float t0 = (EPI == 2 && row_ok) ? fmaxf(thr, -3.402823466e+38f) : INFINITY;
-        // Candidates of this thread's slice are parked in shared memory (the store staging area is idle in this mode) and
-        // appended with ONE atomic per row and tile: the slot's round trip to L2 is paid once, after the TMEM reads.
-        constexpr int kPend = 8;
-        uint2* pend = reinterpret_cast<uint2*>(staging) + etid * kPend;
+        const float t0 = emit ? fmaxf(thr, -3.402823466e+38f) : INFINITY;
+        uint2* pend = pend_base + (it & 1) * (256 * kPend);
         int npend = 0;
-        auto flush = [&]() {
+        auto flush = [&]() {                                      // parking buffer full (rare): append synchronously
           const int slot = atomicAdd(p.cand_count + row, npend);
-          for (int i = 0; i < npend; ++i) {
-            if (slot + i < p.cand_cap) {
-              p.cand_idx[row * p.cand_cap + slot + i] = (int)pend[i].x;
-              p.cand_val[row * p.cand_cap + slot + i] = __uint_as_float(pend[i].y);
-            }
-          }
+          write_out(row, slot, npend, pend);
           npend = 0;
         };
 #pragma unroll 1
@@ -684,7 +719,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               }
             }
           } else if (mx >= t0) {
-            // rare (about top_k hits per row in all of V): only the quarters that hold a hit are scanned
+            // a few hits per row in all of V: only the quarters that hold one are scanned
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               if (m8[q] >= t0) {
@@ -699,12 +734,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           }
         }
-        // the accumulator is drained: hand the TMEM buffer back to the MMA warp BEFORE paying the atomics' round trip
+        // the accumulator is drained: hand the TMEM buffer back to the MMA warp BEFORE any list traffic
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar(as), 0)); else mbar_arrive(tempty_bar(as)); }
-        if (npend) flush();
+        if (EPI == 2) {
+          if (def_n) write_out(def_row, def_slot, def_n, def_buf);         // the previous tile's slot has long arrived
+          def_n = npend; def_row = row; def_buf = pend;
+          if (npend) def_slot = atomicAdd(p.cand_count + row, npend);      // consumed one tile later
+        }
       }
+      if (EPI == 2 && def_n) write_out(def_row, def_slot, def_n, def_buf);
     } else if (eh != 0) {
       // second epilogue group: idle for plain stores
     } else if (p.tma_store) {
@@ -719,7 +759,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t round_ctr = 0;
       int it = 0, last_n0 = -1;
       for (int tile = tile0; tile < tiles; tile += tstride, ++it) {
-        const int m0 = tile_m0(tile), n0 = (tile % p.n_blocks) * BN * p.n_stride;
+        const int m0 = tile_m0(tile), n0 = ((tile % p.n_blocks) * p.n_stride + p.n_offset) * BN;
         const int as = it & 1;
         // bias slice of this tile -> smem, only when the N block changed, and before the wait on the accumulator so the
         // global-load latency is off the per-tile critical path (all readers of the previous slice are past their last
@@ -790,9 +830,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           asm volatile("bar.sync 1, 128;" ::: "memory");
           if (elected) {
+            // split destinations (fused Q | K | V projection): the N tile lies entirely inside one of them
+            const CUtensorMap* mc = &map_c;
+            int ccol = col0;
+            if (p.split_n) {
+              const int w = n0 / p.split_n;
+              mc = w == 0 ? &map_c : w == 1 ? &map_r : &map_i;
+              ccol = col0 - w * p.split_n;
+            }
             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                             reinterpret_cast<uint64_t>(&map_c)),
-                         "r"(slab), "r"(col0), "r"(m0)
+                             reinterpret_cast<uint64_t>(mc)),
+                         "r"(slab), "r"(ccol), "r"(m0)
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
@@ -809,7 +857,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const bool res_vec = p.res && (p.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0);
     int it = 0;
     for (int tile = tile0; tile < tiles; tile += tstride, ++it) {
-      const int m0 = tile_m0(tile), n0 = (tile % p.n_blocks) * BN * p.n_stride;
+      const int m0 = tile_m0(tile), n0 = ((tile % p.n_blocks) * p.n_stride + p.n_offset) * BN;
       const int as = it & 1;
       mbar_wait(tfull_bar(as), (it >> 1) & 1, p.error, 4);
       tc_fence_after();
@@ -988,7 +1036,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, 
     attr = true;
   }
   if (p.n_stride < 1) p.n_stride = 1;
-  p.n_blocks = dh_cdiv(dh_cdiv(p.N, BN), p.n_stride);
+  p.n_blocks = dh_cdiv(dh_cdiv(p.N, BN) - p.n_offset, p.n_stride);
   p.m_blocks = dh_cdiv(p.M, PAIR ? 2 * BM : BM);
   p.tiles_per_layer = p.m_blocks * p.n_blocks;
   p.mb128 = dh_cdiv(p.M, BM);
@@ -1033,8 +1081,8 @@ int pick_bn(int M, int N) {
 }
 
 int dispatch(const CUtensorMap& ma, const void* W, long long ldw, TcParams& p, int bn, cudaStream_t s,
-             const CUtensorMap* second_a = nullptr) {
-  CUtensorMap mb, mc = ma, mr = second_a ? *second_a : ma, mi = ma;
+             const CUtensorMap* second_a = nullptr, const CUtensorMap* third = nullptr) {
+  CUtensorMap mb, mc = ma, mr = second_a ? *second_a : ma, mi = third ? *third : ma;
   // CTA pairs (cta_group::2) for the 128- and 256-wide tiles whenever there are at least two M blocks to pair up
   static const bool pair_ok = !getenv("DH_TC_NO_PAIR");
   // ... and the K loop is long enough (>= 8 chunks incl. residual chunks) to amortise the pair's cross-CTA barrier round
@@ -1058,7 +1106,7 @@ int dispatch(const CUtensorMap& ma, const void* W, long long ldw, TcParams& p, i
   if (p.epi_mode) {
     // selection epilogues store nothing of C
   } else if (out_ok && res_ok) {
-    rc = make_map_2d(&mc, p.out, p.M, p.N, p.ldc, BM, p.out_dtype);
+    rc = make_map_2d(&mc, p.out, p.M, p.split_n ? p.split_n : p.N, p.ldc, BM, p.out_dtype);
     if (rc) return rc;
     p.tma_store = 1;
     if (p.res) {
@@ -1069,6 +1117,7 @@ int dispatch(const CUtensorMap& ma, const void* W, long long ldw, TcParams& p, i
       p.res_chunks = 1;   // launch<> sets BN / 64
     }
   }
+  if (p.split_n && !p.tma_store) return dh_fail(DH_ERR_ARG, "split destinations need the TMA-store epilogue", __FILE__, __LINE__);
   switch (p.epi_mode) {
     case 0: return launch_bn<0>(ma, mb, mc, mr, mi, p, bn, pair, s);
     case 1: return launch_bn<1>(ma, mb, mc, mr, mi, p, bn, pair, s);
@@ -1106,12 +1155,58 @@ extern "C" int dh_gemm_tc(const void* A, long long lda, const void* W, long long
   return dispatch(ma, W, ldw, p, tile_n ? tile_n : pick_bn(M, N), stream);
 }
 
+// One contraction, three destinations: [C0 | C1 | C2][M, 3 * split_n] = A[M,K] * W[3 * split_n, K]^T + bias, block j of
+// split_n columns stored to Cj (own leading dimension).  The transformer decode step projects Q, K and V of the new position
+// from the same activation row (models/transformers.py:97-99): W = [fc_q | fc_k | fc_v] stacked along N, C0 = the query
+// buffer, C1 / C2 = this position's slots of the K / V caches (row stride = slots * positions * D), so the activations are
+// read once and the K / V rows land in the cache without a copy.
+extern "C" int dh_gemm_tc_split3(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias,
+                                 void* C0, long long ldc0, void* C1, long long ldc1, void* C2, long long ldc2, int out_dtype,
+                                 int split_n, int M, int K, cudaStream_t stream) {
+  DH_ARG(A && W && C0 && C1 && C2 && M >= 0 && K > 0 && split_n > 0 && split_n % 128 == 0);
+  DH_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0);
+  DH_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0);
+  DH_ARG(ab_dtype == DH_BF16 || ab_dtype == DH_F16);
+  DH_ARG(out_dtype == DH_BF16 || out_dtype == DH_F16);
+  DH_ARG(((uintptr_t)C0 % 16) == 0 && ((uintptr_t)C1 % 16) == 0 && ((uintptr_t)C2 % 16) == 0);
+  DH_ARG(ldc0 % 8 == 0 && ldc1 % 8 == 0 && ldc2 % 8 == 0);
+  if (M == 0) return DH_OK;
+  int rc = tc_init();
+  if (rc) return rc;
+  TcParams p{};
+  p.M = M; p.N = 3 * split_n; p.K = K;
+  p.k_chunks = dh_cdiv(K, BK);
+  p.ab_dtype = ab_dtype;
+  p.bias = bias;
+  p.out = C0; p.ldc = ldc0; p.out_dtype = out_dtype;
+  p.split_n = split_n;
+  CUtensorMap ma, m1, m2;
+  rc = make_map_2d(&ma, A, M, K, lda, BM, ab_dtype);
+  if (rc) return rc;
+  rc = make_map_2d(&m1, C1, M, split_n, ldc1, BM, out_dtype);
+  if (rc) return rc;
+  rc = make_map_2d(&m2, C2, M, split_n, ldc2, BM, out_dtype);
+  if (rc) return rc;
+  int bn = pick_bn(M, p.N);
+  if (split_n % bn) bn = 128;
+  return dispatch(ma, W, ldw, p, bn, stream, &m1, &m2);
+}
+
 // Vocab projection with the logits kept on chip (models/rnn_models.py:81,109 and models/transformers.py:488,736 feeding
 // models/beam.py:32-37): pass 1 stores the maximum of every 32-column group of logits[M,N] = A W^T + bias, pass 2
 // recomputes the identical product and appends (column, logit) of every logit >= thresh[row] to the row's candidate list.
+struct VocabFix {          // optional behaviour of a vocab pass (see TcParams::cond_mode)
+  int tile_offset = 0;
+  int cond_mode = 0, cond_min = 0, cond_max = 0;
+  const int* cond_count = nullptr;
+  int* cond_flag = nullptr;
+  const unsigned char* redo = nullptr;
+};
+
 static int vocab_pass(int mode, int tile_stride, const void* A, long long lda, const void* W, long long ldw, int ab_dtype,
                       const float* bias, int M, int N, int K, float* gmax, long long ld_gmax, const float* thresh,
-                      int* cand_count, int* cand_idx, float* cand_val, int cand_cap, cudaStream_t stream) {
+                      int* cand_count, int* cand_idx, float* cand_val, int cand_cap, cudaStream_t stream,
+                      const VocabFix& fx = VocabFix()) {
   DH_ARG(A && W && M >= 0 && N > 0 && K > 0);
   DH_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0);
   DH_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0);
@@ -1126,6 +1221,9 @@ static int vocab_pass(int mode, int tile_stride, const void* A, long long lda, c
   p.bias = bias;
   p.epi_mode = mode;
   p.n_stride = tile_stride;
+  p.n_offset = fx.tile_offset;
+  p.cond_mode = fx.cond_mode; p.cond_min = fx.cond_min; p.cond_max = fx.cond_max;
+  p.cond_count = fx.cond_count; p.cond_flag = fx.cond_flag; p.redo = fx.redo;
   p.gmax = gmax; p.ld_gmax = ld_gmax;
   p.thresh = thresh; p.cand_count = cand_count; p.cand_idx = cand_idx; p.cand_val = cand_val; p.cand_cap = cand_cap;
   CUtensorMap ma;
@@ -1260,13 +1358,21 @@ extern "C" int dh_vocab_logprob(const void* A, long long lda, const void* W, lon
   return dh_vocab_logprob_reduce(gmax, gsum, ld_g, M, n_groups, tlogit, out, stream);
 }
 
-extern "C" int dh_vocab_groupmax(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias,
-                                 int M, int N, int K, int tile_stride, float* gmax, long long ld_gmax, cudaStream_t stream) {
-  DH_ARG(gmax && tile_stride >= 1);
+static int vocab_groups(int N, int tile_stride, int tile_offset) {
   const int bn = N <= 64 ? 64 : N <= 128 ? 128 : 256;
-  DH_ARG(ld_gmax >= (long long)dh_cdiv(dh_cdiv(N, bn), tile_stride) * (bn / 32));
+  return dh_cdiv(dh_cdiv(N, bn) - tile_offset, tile_stride) * (bn / 32);
+}
+
+extern "C" int dh_vocab_groupmax(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias,
+                                 int M, int N, int K, int tile_stride, int tile_offset, float* gmax, long long ld_gmax,
+                                 cudaStream_t stream) {
+  DH_ARG(gmax && tile_stride >= 1 && tile_offset >= 0 && tile_offset < tile_stride);
+  DH_ARG(tile_offset < dh_cdiv(N, N <= 64 ? 64 : N <= 128 ? 128 : 256));
+  DH_ARG(ld_gmax >= vocab_groups(N, tile_stride, tile_offset));
+  VocabFix fx;
+  fx.tile_offset = tile_offset;
   return vocab_pass(1, tile_stride, A, lda, W, ldw, ab_dtype, bias, M, N, K, gmax, ld_gmax, nullptr, nullptr, nullptr, nullptr,
-                    0, stream);
+                    0, stream, fx);
 }
 
 extern "C" int dh_vocab_candidates(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias,
@@ -1275,6 +1381,30 @@ extern "C" int dh_vocab_candidates(const void* A, long long lda, const void* W, 
   DH_ARG(thresh && cand_count && cand_idx && cand_val && cand_cap > 0);
   return vocab_pass(2, 1, A, lda, W, ldw, ab_dtype, bias, M, N, K, nullptr, 0, thresh, cand_count, cand_idx, cand_val, cand_cap,
                     stream);
+}
+
+// Fix-up launches behind a SAMPLED pass 1 (see include/deephumor_b200.h): both contractions return at once -- before any
+// barrier or tensor-memory set-up -- unless some row's candidate count left [count_min, count_max] / *any_flag is set.
+extern "C" int dh_vocab_groupmax_fix(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias,
+                                     int M, int N, int K, float* gmax, long long ld_gmax, const int* cand_count, int count_min,
+                                     int count_max, int* any_flag, cudaStream_t stream) {
+  DH_ARG(gmax && cand_count && any_flag && count_min >= 0 && count_max >= count_min);
+  DH_ARG(ld_gmax >= vocab_groups(N, 1, 0));
+  VocabFix fx;
+  fx.cond_mode = 1; fx.cond_min = count_min; fx.cond_max = count_max; fx.cond_count = cand_count; fx.cond_flag = any_flag;
+  return vocab_pass(1, 1, A, lda, W, ldw, ab_dtype, bias, M, N, K, gmax, ld_gmax, nullptr, nullptr, nullptr, nullptr, 0, stream,
+                    fx);
+}
+
+extern "C" int dh_vocab_candidates_fix(const void* A, long long lda, const void* W, long long ldw, int ab_dtype,
+                                       const float* bias, int M, int N, int K, const float* thresh, int* cand_count,
+                                       int* cand_idx, float* cand_val, int cand_cap, const unsigned char* redo, int* any_flag,
+                                       cudaStream_t stream) {
+  DH_ARG(thresh && cand_count && cand_idx && cand_val && cand_cap > 0 && redo && any_flag);
+  VocabFix fx;
+  fx.cond_mode = 2; fx.cond_flag = any_flag; fx.redo = redo;
+  return vocab_pass(2, 1, A, lda, W, ldw, ab_dtype, bias, M, N, K, nullptr, 0, thresh, cand_count, cand_idx, cand_val, cand_cap,
+                    stream, fx);
 }
 
 // im2col-mode tensor map over an NHWC activation tensor: box = {64 channels, 128 output pixels}

@@ -275,14 +275,27 @@ __device__ __forceinline__ float key_to_float(unsigned int k) {
 }
 // NPL > 0: the whole row (<= 32 * NPL group maxima) is loaded into registers with all loads in flight at once (one L2
 // round trip); NPL == 0: generic two-pass version for longer rows.
+struct ThrFix {              // fix-up form (dh_vocab_threshold_fix): only rows whose candidate count left [cmin, cmax]
+  int on, cmin, cmax;
+  unsigned char* redo;       // [rows] 1 = this row's threshold was replaced (its list must be rebuilt), else 0
+  int* any_flag;             // set to 1 if any row was replaced
+};
+
 template <int NPL>
 __global__ void __launch_bounds__(kThrWarps * 32) vocab_threshold_kernel(const float* __restrict__ gmax, long long ld, int rows,
                                                                         int n_groups, int top_k, float* __restrict__ thresh,
-                                                                        int* __restrict__ cand_count) {
+                                                                        int* __restrict__ cand_count, ThrFix fx) {
   __shared__ float s_cand[kThrWarps][kThrCap];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * kThrWarps + w;
   if (r >= rows) return;
+  if (fx.on) {
+    const int c = cand_count[r];
+    const bool bad = c < fx.cmin || c > fx.cmax;
+    if (lane == 0) fx.redo[r] = (unsigned char)bad;
+    if (!bad) return;
+    if (lane == 0) atomicOr(fx.any_flag, 1);
+  }
   const float* row = gmax + (long long)r * ld;
   constexpr int NR = NPL > 0 ? NPL : 1;
   float xr[NR];
@@ -395,11 +408,27 @@ __device__ void warp_select(const SelParams& p, int r, int img, int nc_total, co
   // ---- exact k-th largest among the candidates: #{> v} < top_k <= #{>= v}; -inf if fewer than top_k candidates
   float kth = -INFINITY;
   if (nc <= 64 && nc >= p.top_k && nc - p.top_k < 16) {
-    // the usual case (the fused projection hands over ~top_k + 1 candidates): the top_k-th largest of nc values is the
-    // (nc - top_k + 1)-th smallest -- one or two rounds of warp-wide minimum extraction instead of O(nc^2 / 32) rank counts
+    // an exhaustive pass 1 hands over ~top_k + 1 candidates: the top_k-th largest of nc values is the (nc - top_k + 1)-th
+    // smallest -- one or two rounds of warp-wide minimum extraction instead of O(nc^2 / 32) rank counts
     const unsigned int a = lane < nc ? order_key(vv[lane]) : 0xffffffffu;
     const unsigned int b = 32 + lane < nc ? order_key(vv[32 + lane]) : 0xffffffffu;
     kth = key_to_float(warp_mth_smallest64(a, b, nc - p.top_k + 1, lane));
+  } else if (staged && nc >= p.top_k) {
+    // a sampled pass 1 hands over a few times top_k candidates: bit-wise radix select on the order-preserving keys, eight per
+    // lane in registers -- 32 rounds of (8 compares + one warp-wide add), independent of the list length
+    unsigned int key[kWarpCap / 32];
+#pragma unroll
+    for (int u = 0; u < kWarpCap / 32; ++u) key[u] = u * 32 + lane < nc ? order_key(vv[u * 32 + lane]) : 0u;
+    unsigned int ans = 0u;
+    for (int b = 31; b >= 0; --b) {
+      const unsigned int trial = ans | (1u << b);
+      int cnt = 0;
+#pragma unroll
+      for (int u = 0; u < kWarpCap / 32; ++u) cnt += key[u] >= trial;
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if (cnt >= p.top_k) ans = trial;
+    }
+    kth = key_to_float(ans);
   } else {
     for (int c = lane; c < nc; c += 32) {
       const float v = vv[c];
@@ -791,17 +820,34 @@ extern "C" int dh_select_tokens(const float* logits, long long ld, int rows, int
   return DH_OK;
 }
 
+static int launch_threshold(const float* gmax, long long ld_gmax, int rows, int n_groups, int top_k, float* thresh,
+                            int* cand_count, const ThrFix& fx, cudaStream_t s) {
+  const int grid = dh_cdiv(rows, kThrWarps);
+  if (n_groups <= 32 * 5)
+    vocab_threshold_kernel<5><<<grid, kThrWarps * 32, 0, s>>>(gmax, ld_gmax, rows, n_groups, top_k, thresh, cand_count, fx);
+  else if (n_groups <= 32 * 36)
+    vocab_threshold_kernel<36><<<grid, kThrWarps * 32, 0, s>>>(gmax, ld_gmax, rows, n_groups, top_k, thresh, cand_count, fx);
+  else
+    vocab_threshold_kernel<0><<<grid, kThrWarps * 32, 0, s>>>(gmax, ld_gmax, rows, n_groups, top_k, thresh, cand_count, fx);
+  DH_LAUNCH_OK();
+  return DH_OK;
+}
+
 extern "C" int dh_vocab_threshold(const float* gmax, long long ld_gmax, int rows, int n_groups, int top_k, float* thresh,
                                   int* cand_count, cudaStream_t s) {
   DH_ARG(gmax && thresh && cand_count && rows >= 0 && n_groups > 0 && ld_gmax >= n_groups && top_k >= 1);
   if (rows == 0) return DH_OK;
-  const int grid = dh_cdiv(rows, kThrWarps);
-  if (n_groups <= 32 * 36)
-    vocab_threshold_kernel<36><<<grid, kThrWarps * 32, 0, s>>>(gmax, ld_gmax, rows, n_groups, top_k, thresh, cand_count);
-  else
-    vocab_threshold_kernel<0><<<grid, kThrWarps * 32, 0, s>>>(gmax, ld_gmax, rows, n_groups, top_k, thresh, cand_count);
-  DH_LAUNCH_OK();
-  return DH_OK;
+  return launch_threshold(gmax, ld_gmax, rows, n_groups, top_k, thresh, cand_count, ThrFix{}, s);
+}
+
+extern "C" int dh_vocab_threshold_fix(const float* gmax, long long ld_gmax, int rows, int n_groups, int top_k, float* thresh,
+                                      int* cand_count, int count_min, int count_max, unsigned char* redo, int* any_flag,
+                                      cudaStream_t s) {
+  DH_ARG(gmax && thresh && cand_count && rows >= 0 && n_groups > 0 && ld_gmax >= n_groups && top_k >= 1);
+  DH_ARG(redo && any_flag && count_min >= 0 && count_max >= count_min);
+  if (rows == 0) return DH_OK;
+  return launch_threshold(gmax, ld_gmax, rows, n_groups, top_k, thresh, cand_count, ThrFix{1, count_min, count_max, redo, any_flag},
+                          s);
 }
 
 static int check_state(const dh_beam_state* st, int n_img, int beam) {

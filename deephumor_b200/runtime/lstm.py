@@ -145,6 +145,7 @@ class LSTMDecoderRT:
             cur = 1 - cur
         self._select(pl, N, 1, p0, None, B, top_k, temperature, unk_index, noise_mode)
         beam.init(ind, val, caption, eos_index, True)
+        ops.trace_beam(p0, beam)
         # ---- beam phase (rnn_models.py:105-137): fixed trip count, frozen-at-break on the device
         # the gathers of a step's operands (next token embedding, recurrent h through the beam parent) ride in the previous
         # step's select + beam launch when the selection is fused (dh_select_beam_step_lstm); the first step takes them
@@ -170,6 +171,7 @@ class LSTMDecoderRT:
             cur = 1 - cur
             self._select(pl, R, B, i, beam.done, B, top_k, temperature, unk_index, noise_mode,
                          beam_step=(max_len, eos_index, True), lstm_next=nxt_ops if i + 1 < max_len else None)
+            ops.trace_beam(i, beam)
         beam.final(temperature, noise_mode, 0, 0, max_len + 1, max(p0 + 1, max_len), pad_index, max_len, pl['ids'],
                    pl['lens'], dyn)
 
@@ -216,7 +218,7 @@ class LSTMDecoderRT:
         pl['dyn_host'][0], pl['dyn_host'][1] = seed, image_base
         pl['dyn'].copy_(pl['dyn_host'], non_blocking=True)
         args = (pl, p0, max_len, temperature, B, top_k, eos_index, unk_index, noise_mode, pad_index)
-        if ops.PROFILE.on or not ops.USE_GRAPHS:
+        if ops.PROFILE.on or not ops.USE_GRAPHS or ops.TRACE is not None:
             self._decode(*args)
         else:
             if pl['graph'] is None:

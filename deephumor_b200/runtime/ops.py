@@ -23,8 +23,8 @@ class _Profile:
         self.on, self.ev = True, []
 
     class _Range:
-        def __init__(self, prof, tag, flops):
-            self.prof, self.tag, self.flops = prof, tag, flops
+        def __init__(self, prof, tag, flops, nbytes):
+            self.prof, self.tag, self.flops, self.nbytes = prof, tag, flops, nbytes
 
         def __enter__(self):
             if self.prof.on:
@@ -35,24 +35,31 @@ class _Profile:
         def __exit__(self, *a):
             if self.prof.on:
                 self.e1.record()
-                self.prof.ev.append((self.tag, self.e0, self.e1, self.flops))
+                self.prof.ev.append((self.tag, self.e0, self.e1, self.flops, self.nbytes))
 
-    def range(self, tag, flops=0.0):
-        return self._Range(self, tag, flops)
+    def range(self, tag, flops=0.0, nbytes=0.0):
+        """flops: algorithmic FLOPs of a tensor-bound stage; nbytes: algorithmic HBM bytes of a bandwidth-bound one."""
+        return self._Range(self, tag, flops, nbytes)
 
     def stop(self):
-        """-> {tag: (count, total_ms, total_flops)}"""
+        """-> {tag: (count, total_ms, total_flops, total_bytes)}"""
         self.on = False
         torch.cuda.synchronize()
         out = {}
-        for tag, e0, e1, fl in self.ev:
-            n, ms, f = out.get(tag, (0, 0.0, 0.0))
-            out[tag] = (n + 1, ms + e0.elapsed_time(e1), f + fl)
+        for tag, e0, e1, fl, nb in self.ev:
+            n, ms, f, b = out.get(tag, (0, 0.0, 0.0, 0.0))
+            out[tag] = (n + 1, ms + e0.elapsed_time(e1), f + fl, b + nb)
         self.ev = []
         return out
 
 
 PROFILE = _Profile()
+TRACE = None    # tests: a list that receives (step, seq, val, ended, done) clones of the beam state after every decode step
+
+
+def trace_beam(step, beam):
+    if TRACE is not None:
+        TRACE.append((step, beam.seq.clone(), beam.val.clone(), beam.ended.clone(), beam.done.clone()))
 USE_GRAPHS = os.environ.get('DH_NO_GRAPH', '') == ''   # capture decode loops into CUDA graphs
 HALO_CONV = os.environ.get('DH_NO_HALO_CONV', '') == ''       # 3x3 stride-1 convs of layer1 via the halo-tile kernel
 HALO_COUT = 64
@@ -200,6 +207,19 @@ def gemm(A, W, out, bias=None, residual=None, relu=False, tile_n=0):
                  ptr(out), _rows(out), code(out), M, N, K, int(relu), tile_n, stream())
 
 
+def gemm_split3(A, W, bias, outs):
+    """[outs[0] | outs[1] | outs[2]] = A @ W^T + bias with W [3n, K]: one tcgen05 contraction, three row-major destinations
+    (dh_gemm_tc_split3; the fused Q | K | V projection of a transformer decode step)."""
+    M, K = A.shape
+    n = W.shape[0] // 3
+    assert W.shape == (3 * n, K) and W.dtype == A.dtype and len(outs) == 3
+    assert all(o.shape == (M, n) and o.dtype == outs[0].dtype and o.stride(1) == 1 for o in outs)
+    if M == 0:
+        return
+    LIB.call('dh_gemm_tc_split3', ptr(A), _rows(A), ptr(W), _rows(W), code(A), ptr(bias), ptr(outs[0]), _rows(outs[0]),
+             ptr(outs[1]), _rows(outs[1]), ptr(outs[2]), _rows(outs[2]), code(outs[0]), n, M, K, stream())
+
+
 def gather_rows(src, idx, dst, width=None):
     """dst[r, :width] = src[idx[r] (or r), :width] with dtype conversion."""
     rows = dst.shape[0]
@@ -326,34 +346,64 @@ def select_tokens(logits, V, beam, top_k, temperature, unk, rows_per_image, nois
              stream())
 
 
+def sampled_rank(top_k, frac, eps=1e-7):
+    """Rank j for a SAMPLED pass 1 that sees a fraction `frac` of the vocabulary: the j-th largest sampled value lies above
+    the top_k-th largest logit only if at least j of the row's top_k - 1 largest logits fell into the sample, which -- for a
+    sample unrelated to the logits -- has probability P(Bin(top_k - 1, frac) >= j).  Returns the smallest j that pushes it
+    below eps (the rare miss is repaired on the device by the *_fix launches, so eps only bounds their cost)."""
+    import math
+    n = top_k - 1
+    for j in range(1, top_k + 1):
+        tail = sum(math.comb(n, i) * frac ** i * (1.0 - frac) ** (n - i) for i in range(j, n + 1))
+        if tail < eps:
+            return j
+    return top_k
+
+
 class VocabSelect:
-    """Vocab projection fused with token selection for `rows` rows: two bit-identical tcgen05 passes over
-    logits = A W^T + bias (group maxima -> threshold, then candidate compaction), logits never stored."""
+    """Vocab projection fused with token selection for `rows` rows, logits never stored (dh_vocab_* in the header).
+
+    The selection kernels are exact for any per-row threshold that leaves between top_k and `cap` candidates in the row's
+    list.  Default: a SAMPLED pass 1 over every stride-th 256-column tile (1/stride of a full contraction) whose rank is
+    chosen so that the threshold is low enough except with probability < 1e-7 per row, one full contraction that compacts
+    the candidates (a few times top_k per row), and three fix-up launches that return at once unless a row's list came out
+    short or overflowed -- then they redo that step's threshold exhaustively, inside the same CUDA graph.  stride 1 = the
+    exhaustive two-pass form (two full contractions, ~top_k + 1 candidates per row)."""
 
     def __init__(self, rows, V, top_k, device, stride=None):
-        """stride: pass 1 visits every stride-th 256-column tile of the row (None: DH_VOCAB_STRIDE, default 1).
-        stride 1 can never overflow the candidate lists.  A sampled pass 1 is ~stride times cheaper but its looser
-        threshold lengthens the lists (216 instead of 51 candidates per row at stride 4, V = 36 541, top-k 50), which
-        costs more in pass 2 and the selection than pass 1 saves (measured, profiles/) -- so it is off by default; an
-        overflow is reported through DH_STATUS_TOO_MANY_TIES and the decoders then redo the generation with stride 1."""
         self.rows, self.V, self.top_k = rows, V, top_k
-        bn = 64 if V <= 64 else 128 if V <= 128 else 256
-        n_blocks = (V + bn - 1) // bn
+        bn = self.bn = 64 if V <= 64 else 128 if V <= 128 else 256
+        self.n_blocks = n_blocks = (V + bn - 1) // bn
         if stride is None:
-            stride = max(1, min(int(os.environ.get('DH_VOCAB_STRIDE', '1')), ((V + 31) // 32) // (4 * top_k)))
-        self.stride = stride
-        self.n_groups = (n_blocks + stride - 1) // stride * (bn // 32)
+            stride = int(os.environ.get('DH_VOCAB_STRIDE', '8'))
+        # a sampled pass needs enough sampled groups for the rank statistics and room below the candidate capacity
+        while stride > 1 and (n_blocks // stride) * (bn // 32) < 4 * top_k:
+            stride //= 2
+        self.stride = max(1, stride)
+        self.n_groups_full = n_blocks * (bn // 32)
         self.cap = min((V + 31) // 32 * 32, 32 * top_k)
+        if self.stride > 1:
+            frac = ((n_blocks + self.stride - 1) // self.stride) / n_blocks      # largest sampled fraction over the offsets
+            self.rank = min(sampled_rank(top_k, frac), 64)
+        else:
+            self.rank = top_k
         f32, i32 = dict(dtype=torch.float32, device=device), dict(dtype=torch.int32, device=device)
-        self.gmax = torch.empty(rows, self.n_groups, **f32)
+        self.gmax = torch.empty(rows, self.n_groups_full, **f32)
         self.thresh = torch.empty(rows, **f32)
         self.count = torch.zeros(rows, **i32)
         self.idx = torch.empty(rows, self.cap, **i32)
         self.val = torch.empty(rows, self.cap, **f32)
+        self.redo = torch.zeros(rows, dtype=torch.uint8, device=device) if self.stride > 1 else None
+        self.flag = torch.zeros(1, **i32) if self.stride > 1 else None
+
+    def groups(self, offset):
+        return (self.n_blocks - offset + self.stride - 1) // self.stride * (self.bn // 32)
 
     @staticmethod
     def supported(A, V, top_k):
-        return A.dtype in (torch.bfloat16, torch.float16) and top_k <= (V + 31) // 32
+        # the threshold kernel ranks at most 64 values exactly and the warp-level selection stages 256 candidates: larger
+        # top_k takes the materialised-logits path (dh_select_tokens), which has no such limits
+        return A.dtype in (torch.bfloat16, torch.float16) and top_k <= 64 and top_k <= (V + 31) // 32
 
     def run(self, A, W, bias, beam, temperature, unk, rows_per_image, noise_mode, step, done, ind, val, status, dyn,
             seed=0, image_base=0, beam_step=None, lstm_next=None):
@@ -363,14 +413,24 @@ class VocabSelect:
         rows, K = A.shape
         assert rows <= self.rows and W.shape == (self.V, K) and W.dtype == A.dtype
         args = (ptr(A), _rows(A), ptr(W), _rows(W), code(A), ptr(bias), rows, self.V, K)
-        with PROFILE.range('vocab_pass1', 2.0 * rows * self.V * K / self.stride):
-            LIB.call('dh_vocab_groupmax', *args, self.stride, ptr(self.gmax), self.n_groups, stream())
-        with PROFILE.range('select_beam'):
-            LIB.call('dh_vocab_threshold', ptr(self.gmax), self.n_groups, rows, self.n_groups, self.top_k,
+        offset = step % self.stride                       # the sampled tiles rotate from step to step
+        ng = self.groups(offset)
+        lists = (ptr(self.thresh), ptr(self.count), ptr(self.idx), ptr(self.val), self.cap)
+        with PROFILE.range('vocab_pass1', 2.0 * rows * min(self.V, ng * 32) * K):
+            LIB.call('dh_vocab_groupmax', *args, self.stride, offset, ptr(self.gmax), self.n_groups_full, stream())
+        with PROFILE.range('vocab_threshold', nbytes=4.0 * rows * ng):
+            LIB.call('dh_vocab_threshold', ptr(self.gmax), self.n_groups_full, rows, ng, self.rank,
                      ptr(self.thresh), ptr(self.count), stream())
         with PROFILE.range('vocab_gemm', 2.0 * rows * self.V * K):          # one launch = one full [rows,V,K] product
-            LIB.call('dh_vocab_candidates', *args, ptr(self.thresh), ptr(self.count), ptr(self.idx), ptr(self.val),
-                     self.cap, stream())
+            LIB.call('dh_vocab_candidates', *args, *lists, stream())
+        if self.stride > 1:
+            lo, hi = min(self.top_k, self.V), self.cap
+            with PROFILE.range('vocab_fixup'):
+                LIB.call('dh_vocab_groupmax_fix', *args, ptr(self.gmax), self.n_groups_full, ptr(self.count), lo, hi,
+                         ptr(self.flag), stream())
+                LIB.call('dh_vocab_threshold_fix', ptr(self.gmax), self.n_groups_full, rows, self.n_groups_full, self.top_k,
+                         ptr(self.thresh), ptr(self.count), lo, hi, ptr(self.redo), ptr(self.flag), stream())
+                LIB.call('dh_vocab_candidates_fix', *args, *lists, ptr(self.redo), ptr(self.flag), stream())
         with PROFILE.range('select_beam'):
             if beam_step is None:
                 LIB.call('dh_select_candidates', ptr(self.count), ptr(self.idx), ptr(self.val), self.cap, rows, beam,

@@ -35,6 +35,10 @@ class XfmrDecoderRT:
             for n in ('fc_1', 'fc_2'):
                 lay[f'pf.{n}.w'], lay[f'pf.{n}.b'] = to(sd[f'{q}.pf.{n}.weight']), to(sd[f'{q}.pf.{n}.bias'], f32)
             lay['pf_ln.g'], lay['pf_ln.b'] = to(sd[f'{q}.pf_ln.weight'], f32), to(sd[f'{q}.pf_ln.bias'], f32)
+            if dtype != torch.float32 and self.D % 128 == 0:
+                # tensor-core mode: Q | K | V of the new position in ONE contraction (dh_gemm_tc_split3)
+                lay['self_attn.qkv.w'] = torch.cat([lay[f'self_attn.fc_{n}.w'] for n in 'qkv']).contiguous()
+                lay['self_attn.qkv.b'] = torch.cat([lay[f'self_attn.fc_{n}.b'] for n in 'qkv']).contiguous()
             self.layers.append(lay)
         self.pf = self.layers[0]['pf.fc_1.w'].shape[0]
         self.Wc, self.bc = to(sd[prefix + '.classifier.weight']), to(sd[prefix + '.classifier.bias'], f32)
@@ -57,13 +61,19 @@ class XfmrDecoderRT:
 
     def _post_attn(self, lay, att, x, attn, tmp, rows):
         """x <- LN(x + fc_o(attn))."""
-        ops.gemm(attn[:rows], lay[f'{att}.fc_o.w'], tmp[:rows], bias=lay[f'{att}.fc_o.b'], residual=x[:rows])
-        ops.add_layernorm(tmp[:rows], None, lay[f'{att}_ln.g'], lay[f'{att}_ln.b'], x[:rows])
+        D, es = self.D, x.element_size()
+        with ops.PROFILE.range('xfmr_proj', 2.0 * rows * D * D):
+            ops.gemm(attn[:rows], lay[f'{att}.fc_o.w'], tmp[:rows], bias=lay[f'{att}.fc_o.b'], residual=x[:rows])
+        with ops.PROFILE.range('xfmr_layernorm', nbytes=2.0 * rows * D * es):
+            ops.add_layernorm(tmp[:rows], None, lay[f'{att}_ln.g'], lay[f'{att}_ln.b'], x[:rows])
 
     def _ffn(self, lay, x, h1, tmp, rows):
-        ops.gemm(x[:rows], lay['pf.fc_1.w'], h1[:rows], bias=lay['pf.fc_1.b'], relu=True)
-        ops.gemm(h1[:rows], lay['pf.fc_2.w'], tmp[:rows], bias=lay['pf.fc_2.b'], residual=x[:rows])
-        ops.add_layernorm(tmp[:rows], None, lay['pf_ln.g'], lay['pf_ln.b'], x[:rows])
+        D, es = self.D, x.element_size()
+        with ops.PROFILE.range('xfmr_ffn', 4.0 * rows * D * self.pf):
+            ops.gemm(x[:rows], lay['pf.fc_1.w'], h1[:rows], bias=lay['pf.fc_1.b'], relu=True)
+            ops.gemm(h1[:rows], lay['pf.fc_2.w'], tmp[:rows], bias=lay['pf.fc_2.b'], residual=x[:rows])
+        with ops.PROFILE.range('xfmr_layernorm', nbytes=2.0 * rows * D * es):
+            ops.add_layernorm(tmp[:rows], None, lay['pf_ln.g'], lay['pf_ln.b'], x[:rows])
 
     # ------------------------------------------------------------------ generation
     def _decode(self, pl, p0, max_len, temperature, B, top_k, eos_index, unk_index, noise_mode):
@@ -74,7 +84,8 @@ class XfmrDecoderRT:
         x, qb, attn, tmp, h1, logits = pl['x'], pl['qb'], pl['attn'], pl['tmp'], pl['h1'], pl['logits']
         Kc, Vc, beam, ind, val, dyn = pl['Kc'], pl['Vc'], pl['beam'], pl['ind'], pl['val'], pl['dyn']
         beam.status.zero_()
-        xkv, emask = self._cross_kv(spatial, N) if self.cross else (None, None)
+        with ops.PROFILE.range('xfmr_cross_kv', 4.0 * N * 49 * D * D * self.L if self.cross else 0.0):
+            xkv, emask = self._cross_kv(spatial, N) if self.cross else (None, None)
 
         vsel = pl['vsel']
 
@@ -100,17 +111,28 @@ class XfmrDecoderRT:
             for l, lay in enumerate(self.layers):
                 kdst = Kc[l].view(R * S, D)[pos::S * slot_stride][:rows]
                 vdst = Vc[l].view(R * S, D)[pos::S * slot_stride][:rows]
-                ops.gemm(x[:rows], lay['self_attn.fc_q.w'], qb[:rows], bias=lay['self_attn.fc_q.b'])
-                ops.gemm(x[:rows], lay['self_attn.fc_k.w'], kdst, bias=lay['self_attn.fc_k.b'])
-                ops.gemm(x[:rows], lay['self_attn.fc_v.w'], vdst, bias=lay['self_attn.fc_v.b'])
-                ops.attention(qb[:rows], Kc[l], Vc[l], attn[:rows], self.n_heads, rpi, B, S, lay['self_attn.scale'],
-                              src=src, slot_shared=(rpi == 1), n_keys=pos + 1, seq=seq, seq_per_image=False,
-                              pad=self.pad)
+                es = x.element_size()
+                with ops.PROFILE.range('xfmr_proj', 6.0 * rows * D * D):
+                    if 'self_attn.qkv.w' in lay:
+                        # one contraction; the K / V rows of this position land straight in their cache slots
+                        ops.gemm_split3(x[:rows], lay['self_attn.qkv.w'], lay['self_attn.qkv.b'], (qb[:rows], kdst, vdst))
+                    else:
+                        ops.gemm(x[:rows], lay['self_attn.fc_q.w'], qb[:rows], bias=lay['self_attn.fc_q.b'])
+                        ops.gemm(x[:rows], lay['self_attn.fc_k.w'], kdst, bias=lay['self_attn.fc_k.b'])
+                        ops.gemm(x[:rows], lay['self_attn.fc_v.w'], vdst, bias=lay['self_attn.fc_v.b'])
+                # self-attention over the cache: every row reads its pos + 1 cached K and V rows once (1 KB each at D = 512)
+                with ops.PROFILE.range('xfmr_self_attn', nbytes=2.0 * rows * (pos + 1) * D * es + 2.0 * rows * D * es):
+                    ops.attention(qb[:rows], Kc[l], Vc[l], attn[:rows], self.n_heads, rpi, B, S, lay['self_attn.scale'],
+                                  src=src, slot_shared=(rpi == 1), n_keys=pos + 1, seq=seq, seq_per_image=False,
+                                  pad=self.pad)
                 self._post_attn(lay, 'self_attn', x, attn, tmp, rows)
                 if self.cross:
-                    ops.gemm(x[:rows], lay['enc_attn.fc_q.w'], qb[:rows], bias=lay['enc_attn.fc_q.b'])
-                    ops.attention(qb[:rows], xkv[l][0], xkv[l][1], attn[:rows], self.n_heads, rpi, 1, 49,
-                                  lay['enc_attn.scale'], slot_shared=True, n_keys=49, enc_mask=emask)
+                    with ops.PROFILE.range('xfmr_proj', 2.0 * rows * D * D):
+                        ops.gemm(x[:rows], lay['enc_attn.fc_q.w'], qb[:rows], bias=lay['enc_attn.fc_q.b'])
+                    # cross-attention: an image's 49 K and V rows are read once per step for all of its beam rows
+                    with ops.PROFILE.range('xfmr_cross_attn', nbytes=2.0 * (rows // rpi) * 49 * D * es + 2.0 * rows * D * es):
+                        ops.attention(qb[:rows], xkv[l][0], xkv[l][1], attn[:rows], self.n_heads, rpi, 1, 49,
+                                      lay['enc_attn.scale'], slot_shared=True, n_keys=49, enc_mask=emask)
                     self._post_attn(lay, 'enc_attn', x, attn, tmp, rows)
                 self._ffn(lay, x, h1, tmp, rows)
 
@@ -120,10 +142,12 @@ class XfmrDecoderRT:
             step(N, 1, t, tok, caption, None)
         select(N, 1, p0, None)
         beam.init(ind, val, caption, eos_index, False)
+        ops.trace_beam(p0, beam)
         # ---- beam phase: i = p0+1 .. max_len inclusive (Q10); fixed trip count, frozen-at-break on the device
         for i in range(p0 + 1, max_len + 1):
             step(R, B, i, beam.last_tok, beam.seq, beam.src)
             select(R, B, i, beam.done, beam_step=True)
+            ops.trace_beam(i, beam)
         beam.final(temperature, noise_mode, 0, 0, max_len + 1, max_len, self.pad, max_len, pl['ids'], pl['lens'], dyn)
 
     def generate(self, *args, **kw):
@@ -175,7 +199,7 @@ class XfmrDecoderRT:
         pl['dyn_host'][0], pl['dyn_host'][1] = seed, image_base
         pl['dyn'].copy_(pl['dyn_host'], non_blocking=True)
         args = (pl, p0, max_len, temperature, B, top_k, eos_index, unk_index, noise_mode)
-        if ops.PROFILE.on or not ops.USE_GRAPHS:
+        if ops.PROFILE.on or not ops.USE_GRAPHS or ops.TRACE is not None:
             self._decode(*args)
         else:
             if pl['graph'] is None:

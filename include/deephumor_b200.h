@@ -24,7 +24,7 @@ extern "C" {
 typedef struct CUstream_st* cudaStream_t;
 #endif
 
-#define DH_VERSION 115
+#define DH_VERSION 201
 
 #define DH_OK 0
 #define DH_ERR_ARG (-1)
@@ -83,6 +83,14 @@ int dh_gemm_f32(const float* A, long long lda, const float* W, long long ldw, co
 int dh_gemm_tc(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias,
                const void* residual, long long ldr, int res_dtype, void* C, long long ldc, int out_dtype, int M, int N,
                int K, int relu, int tile_n, cudaStream_t stream);
+/* One contraction, three destinations: block j (of split_n columns) of A[M,K] W[3*split_n,K]^T + bias goes to Cj with its own
+ * leading dimension.  The transformer decode step projects Q, K and V of the new position from the same activation
+ * (transformers.py:97-99): W = [fc_q | fc_k | fc_v] stacked along N, C0 = the query buffer, C1 / C2 = this position's rows of
+ * the K / V caches, so the K / V rows land in the cache without a copy.  split_n % 128 == 0; Cj of out_dtype (DH_BF16 /
+ * DH_F16), 16 B aligned rows. */
+int dh_gemm_tc_split3(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias, void* C0,
+                      long long ldc0, void* C1, long long ldc1, void* C2, long long ldc2, int out_dtype, int split_n, int M,
+                      int K, cudaStream_t stream);
 /* Implicit-GEMM convolution (torchvision resnet.py:143-163 conv+BN+ReLU(+identity)): x NHWC, Cin % 64 == 0,
  * w [Cout][kh][kw][Cin] with BN folded, residual / y NHWC, all of dtype (DH_BF16 or DH_F16).  The A operand is
  * fetched by im2col-mode TMA. */
@@ -201,21 +209,39 @@ int dh_select_tokens(const float* logits, long long ld, int rows, int V, int bea
                      cudaStream_t stream);
 /* Vocab projection fused with the selection, logits never stored (rnn_models.py:81,109 / transformers.py:488,736 ->
  * beam.py:32-53).  logits[M,N] = A[M,K] W[N,K]^T + bias (tcgen05, A / W ab_dtype) are produced twice, bit-identically:
- *   dh_vocab_groupmax    gmax[m, g] = max of the g-th 32-column group of logits[m, :] among the N tiles 0, s, 2s, ...
- *                        (s = tile_stride; tile = 256 columns; groups past N hold -inf)              (pass 1)
- *   dh_vocab_threshold   thresh[m] = top_k-th largest of gmax[m, :] (<= the top_k-th largest logit); cand_count[m] = 0
- *   dh_vocab_candidates  appends (column, logit) of every logit >= thresh[m] to row m's list     (pass 2)
+ *   dh_vocab_groupmax    gmax[m, g] = max of the g-th 32-column group of logits[m, :] among the N tiles o, o + s, o + 2s, ...
+ *                        (s = tile_stride, o = tile_offset; tile = 256 columns; groups past N hold -inf)   (pass 1)
+ *   dh_vocab_threshold   thresh[m] = top_k-th largest of gmax[m, :]; cand_count[m] = 0
+ *   dh_vocab_candidates  appends (column, logit) of every finite logit >= thresh[m] to row m's list     (pass 2)
  *   dh_select_candidates dh_select_tokens on those lists.
- * With tile_stride == 1 a capacity cand_cap >= min(N, 32 * top_k) cannot overflow (ties aside).  tile_stride > 1 samples
- * the row (any subset of logits gives a valid lower bound): pass 1 costs 1/s, the lists get a few times longer, and an
- * overflow (DH_STATUS_TOO_MANY_TIES) tells the caller to redo the step with tile_stride == 1. */
+ * The selection is exact for ANY threshold that leaves at least top_k (and at most cand_cap) candidates in the list, because
+ * dh_select_candidates recomputes the exact top_k-th largest value from the list.  Two ways to get such a threshold:
+ *   exhaustive  tile_stride 1, rank top_k: the top_k-th largest group maximum is a lower bound of the top_k-th largest logit
+ *               and at most 32 * top_k logits reach it, so cand_cap >= min(N, 32 * top_k) cannot overflow (ties aside).  Costs a
+ *               second full contraction.
+ *   sampled     tile_stride s > 1 and a rank j < top_k chosen so that the j-th largest SAMPLED group maximum lies below the
+ *               top_k-th largest logit except with negligible probability (the host picks j from the binomial tail).  Pass 1
+ *               costs 1/s.  The three *_fix entries then repair, inside the same stream / CUDA graph, the rare step in which
+ *               a row's list came out shorter than top_k or longer than cand_cap: each returns immediately unless such a row
+ *               exists.  dh_vocab_groupmax_fix = exhaustive pass 1 (and *any_flag = 0); dh_vocab_threshold_fix = exact
+ *               threshold, cand_count = 0, redo = 1 for the failing rows (redo = 0 for the others), *any_flag = 1;
+ *               dh_vocab_candidates_fix = pass 2 for the rows with redo != 0, only if *any_flag != 0. */
 int dh_vocab_groupmax(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias, int M,
-                      int N, int K, int tile_stride, float* gmax, long long ld_gmax, cudaStream_t stream);
+                      int N, int K, int tile_stride, int tile_offset, float* gmax, long long ld_gmax, cudaStream_t stream);
 int dh_vocab_threshold(const float* gmax, long long ld_gmax, int rows, int n_groups, int top_k, float* thresh,
                        int* cand_count, cudaStream_t stream);
 int dh_vocab_candidates(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias, int M,
                         int N, int K, const float* thresh, int* cand_count, int* cand_idx, float* cand_val, int cand_cap,
                         cudaStream_t stream);
+int dh_vocab_groupmax_fix(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias, int M,
+                          int N, int K, float* gmax, long long ld_gmax, const int* cand_count, int count_min, int count_max,
+                          int* any_flag, cudaStream_t stream);
+int dh_vocab_threshold_fix(const float* gmax, long long ld_gmax, int rows, int n_groups, int top_k, float* thresh,
+                           int* cand_count, int count_min, int count_max, unsigned char* redo, int* any_flag,
+                           cudaStream_t stream);
+int dh_vocab_candidates_fix(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias, int M,
+                            int N, int K, const float* thresh, int* cand_count, int* cand_idx, float* cand_val, int cand_cap,
+                            const unsigned char* redo, int* any_flag, cudaStream_t stream);
 int dh_select_candidates(const int* cand_count, const int* cand_idx, const float* cand_val, int cand_cap, int rows,
                          int beam, int top_k, float temperature, int unk, int rows_per_image, int noise_mode,
                          unsigned long long seed, long long image_base, int step, const unsigned char* done, int* ind,

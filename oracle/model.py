@@ -211,23 +211,77 @@ def perplexity(logits, targets, lengths, pad_index=0):
 
 # ------------------------------------------------------------------------------ selection algebra
 class Trace:
-    """Collects the smallest relative decision margin of a generation (near-tie policy, Appendix D.5)."""
+    """Collects decision margins of a generation (near-tie policy, Appendix D.5) and, optionally, the beam state
+    after every step.
 
-    def __init__(self):
+    min_gap   smallest RELATIVE margin between consecutive race scores among the first k+1 (fp32 check-mode policy).
+    abs_gap   smallest ABSOLUTE margin in logit units: |log s_i - log s_j| * T between consecutive race scores
+              among the first k+1 (what a logit perturbation has to exceed to reorder a draw), and the gap between the
+              k-th and (k+1)-th largest logit of a top-k filter whenever the boundary token could reach the draw.
+    step_abs  {step: smallest abs_gap among that step's decisions}; states {step: (seq, val, ended)} when keep_states.
+    """
+
+    def __init__(self, keep_states=False):
         self.min_gap = float('inf')
+        self.abs_gap = float('inf')
         self.steps = 0
         self.error = None
+        self.step = None
+        self.step_abs = {}
+        self.states = {} if keep_states else None
 
-    def see(self, score_sorted, k):
+    def at(self, step):
+        self.step = step
+
+    def _abs(self, g):
+        self.abs_gap = min(self.abs_gap, g)
+        if self.step is not None:
+            self.step_abs[self.step] = min(self.step_abs.get(self.step, float('inf')), g)
+
+    def see(self, score_sorted, k, temperature=1.0):
         s = score_sorted[..., :k + 1].double()
         if s.shape[-1] < 2:
             return
         hi, lo = s[..., :-1], s[..., 1:]
         denom = hi.abs().clamp_min(1e-30)
         gap = ((hi - lo) / denom)
-        gap = gap[hi > 0] if (hi > 0).any() else gap
+        live = hi > 0
+        gap = gap[live] if live.any() else gap
         if gap.numel():
             self.min_gap = min(self.min_gap, float(gap.min()))
+        if live.any():
+            lg = (hi[live].log() - lo[live].clamp_min(1e-300).log()) * temperature
+            self._abs(float(lg.min()))
+
+    def see_filter(self, logits, top_k, unk, B, temperature, q):
+        """Margin of the top-k filter (beam.py:32-37): a flip at the k-th / (k+1)-th logit only changes the outcome if
+        the boundary token can be drawn, i.e. its race score is within the first B+1 of the row."""
+        if logits.shape[-1] <= top_k:
+            return
+        top = torch.topk(logits, top_k + 1, dim=-1)
+        for r in range(logits.shape[0]):
+            x = logits[r].double()
+            fl = x.clone()
+            fl[x < top.values[r, top_k - 1].double()] = NEG_INF
+            fl[unk] = NEG_INF
+            sc = torch.softmax(fl / temperature, -1)
+            z = torch.exp((x - x.max()) / temperature)
+            zs = float(z[fl > NEG_INF].sum())
+            qq = torch.ones_like(x) if q is None else q[r].double()
+            race = sc / qq
+            cut = float(torch.topk(race, min(B + 1, race.numel())).values[-1])
+            for j in (top.indices[r, top_k - 1], top.indices[r, top_k]):
+                j = int(j)
+                if j == unk:
+                    continue
+                hyp = float(z[j] / zs / qq[j])                      # its race score if it is (or were) inside the filter
+                if hyp >= cut:
+                    self._abs(float(top.values[r, top_k - 1] - top.values[r, top_k]))
+                    break
+
+    def state(self, step, seq, val, ended):
+        if self.states is not None:
+            self.states[step] = (seq.clone(), val.clone(), ended.clone())
 
 
 def filter_top_k(logits, top_k, unk):
@@ -247,12 +301,14 @@ def draw(values, k, temperature, q, trace=None):
     score = p if q is None else p / q
     srt = torch.sort(score, dim=-1, descending=True, stable=True)
     if trace is not None:
-        trace.see(srt.values, k)
+        trace.see(srt.values, k, temperature)
     return srt.indices[..., :k]
 
 
 def select_tokens(logits, B, T, top_k, unk, q, trace):
     """filter -> draw B per row -> log_softmax over the B picked raw logits (Q4).  logits [R,V]."""
+    if trace is not None:
+        trace.see_filter(logits, top_k, unk, B, T, q)
     fl = filter_top_k(logits, top_k, unk)
     ind = draw(fl, B, T, q, trace)
     val = torch.gather(fl, 1, ind).log_softmax(-1)
@@ -293,6 +349,8 @@ def generate_lstm(sd, hp, image_emb, caption=None, max_len=25, temperature=1.0, 
     logits = F.linear(out, W, bW)
     h, c = h.repeat(1, B, 1), c.repeat(1, B, 1)                              # :84
     p0 = 0 if caption is None else caption.shape[1]
+    if trace is not None:
+        trace.at(p0)
     ind, val = select_tokens(logits, B, temperature, top_k, unk_index,
                              noise.q(image_index, p0, CALL_TOKEN, 1, V), trace)
     last, val = ind[0].clone(), val[0].clone()
@@ -300,7 +358,11 @@ def generate_lstm(sd, hp, image_emb, caption=None, max_len=25, temperature=1.0, 
     if caption is not None:
         seq = torch.cat([caption.repeat(B, 1), seq], dim=1)
     ended = last == eos_index                                                # :103 (Q9)
+    if trace is not None:
+        trace.state(p0, seq, val, ended)
     for i in range(seq.shape[1], max_len):                                   # :105 (Q11)
+        if trace is not None:
+            trace.at(i)
         out, h, c = lstm_step(sd, 'decoder.lstm', L, sd['decoder.embedding.weight'][last], h, c)
         logits = F.linear(out, W, bW)
         ind, nv = select_tokens(logits, B, temperature, top_k, unk_index,
@@ -314,10 +376,13 @@ def generate_lstm(sd, hp, image_emb, caption=None, max_len=25, temperature=1.0, 
         ended = cend[f]
         if trace is not None:
             trace.steps = i
+            trace.state(i, seq, val, ended)
         if bool(ended.all()):                                                # :131
             break
         sp = f // B                                                          # :135-137 misaligned parent (Q8)
         h, c = h[:, sp], c[:, sp]
+    if trace is not None:
+        trace.at(max_len + 1)
     pick = draw(val.unsqueeze(0), 1, temperature, noise.q(image_index, max_len + 1, CALL_FINAL, 1, B), trace)[0, 0]
     return seq[pick]                                                         # :140-143 (Q13)
 
@@ -347,6 +412,8 @@ def generate_xfmr(sd, hp, cross, start_emb, enc_out=None, caption=None, max_len=
         p0 = caption.shape[1]
         seq[:, :p0] = caption
     logits = logits_at(seq, start_emb, enc_out, p0)
+    if trace is not None:
+        trace.at(p0)
     ind, val = select_tokens(logits, B, temperature, top_k, unk_index,
                              noise.q(image_index, p0, CALL_TOKEN, 1, V), trace)
     val = val[0].clone()
@@ -355,8 +422,12 @@ def generate_xfmr(sd, hp, cross, start_emb, enc_out=None, caption=None, max_len=
     start_b = start_emb.repeat(B, 1)
     enc_b = enc_out.repeat(B, 1, 1) if cross else None
     ended = torch.zeros(B, dtype=torch.bool)                                 # NOT initialised from tokens (Q9)
+    if trace is not None:
+        trace.state(p0, seq, val, ended)
     i = p0 + 1
     for i in range(p0 + 1, max_len + 1):                                     # inclusive upper bound (Q10)
+        if trace is not None:
+            trace.at(i)
         logits = logits_at(seq, start_b, enc_b, i)
         ind, nv = select_tokens(logits, B, temperature, top_k, unk_index,
                                 noise.q(image_index, i, CALL_TOKEN, B, V), trace)
@@ -369,8 +440,11 @@ def generate_xfmr(sd, hp, cross, start_emb, enc_out=None, caption=None, max_len=
         val, seq, ended = cval[f], cseq[f], cend[f]
         if trace is not None:
             trace.steps = i
+            trace.state(i, seq, val, ended)
         if bool(ended.all()):
             break
+    if trace is not None:
+        trace.at(max_len + 1)
     pick = draw(val.unsqueeze(0), 1, temperature, noise.q(image_index, max_len + 1, CALL_FINAL, 1, B), trace)[0, 0]
     return seq[pick, :i]
 
@@ -386,9 +460,10 @@ def generate(kind, sd, hp, image, label=None, caption=None, image_index=0, encod
 
 
 def generate_batch(kind, sd, hp, images, labels=None, first_index=0, pad_index=0, max_len=25, encoded=None,
-                   gaps=None, **kw):
+                   gaps=None, traces=None, **kw):
     """Batched oracle = python loop over images (Appendix D.4): ids [N,max_len] padded + lengths [N].
-    encoded = (start [N,E], enc [N,49,E] | None) from ``encode``; gaps = list receiving per-image min margins."""
+    encoded = (start [N,E], enc [N,49,E] | None) from ``encode``; gaps = list receiving per-image min relative margins;
+    traces = list receiving each image's Trace (per-step beam states and absolute margins)."""
     N = images.shape[0] if images is not None else encoded[0].shape[0]
     ids = torch.full((N, max_len), pad_index, dtype=torch.int64)
     lens = torch.zeros(N, dtype=torch.int64)
@@ -397,11 +472,13 @@ def generate_batch(kind, sd, hp, images, labels=None, first_index=0, pad_index=0
         enc_n = None
         if encoded is not None:
             enc_n = (encoded[0][n:n + 1], None if encoded[1] is None else encoded[1][n:n + 1])
-        tr = Trace() if gaps is not None else None
+        tr = Trace(keep_states=traces is not None) if (gaps is not None or traces is not None) else None
         s = generate(kind, sd, hp, None if images is None else images[n:n + 1], lab, image_index=first_index + n,
                      max_len=max_len, encoded=enc_n, trace=tr, **kw)
         if gaps is not None:
             gaps.append(tr.min_gap)
+        if traces is not None:
+            traces.append(tr)
         s = s.reshape(-1)
         ids[n, :len(s)] = s
         lens[n] = len(s)

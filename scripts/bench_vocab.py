@@ -4,7 +4,9 @@ import torch
 from deephumor_b200.runtime import ops
 dev='cuda'
 M,N,K=2560,36541,512
-A=torch.randn(M,K,device=dev).to(torch.bfloat16); W=(torch.randn(N,K,device=dev)*0.5).to(torch.bfloat16)
+A=torch.randn(M,K,device=dev).to(torch.bfloat16)
+if os.environ.get('CORR'):   # strongly correlated rows (what random-init LSTM states look like)
+    A=(torch.randn(1,K,device=dev)+0.2*torch.randn(M,K,device=dev)).to(torch.bfloat16); W=(torch.randn(N,K,device=dev)*0.5).to(torch.bfloat16)
 b=torch.randn(N,device=dev)
 ldc=(N+3)//4*4
 out=torch.empty(M,ldc,device=dev)
@@ -33,11 +35,11 @@ print('bf16 out', t(lambda: ops.gemm(A,W,out16[:,:N],bias=b)))
 # fused two-pass path (logits never stored)
 from deephumor_b200._lib import LIB, ptr, stream
 vs = ops.VocabSelect(M, N, 50, dev, stride=int(os.environ.get('STRIDE', '0')) or None)
-print('pass-1 tile stride', vs.stride, 'groups', vs.n_groups)
+print('pass-1 tile stride', vs.stride, 'rank', vs.rank, 'groups', vs.groups(0))
 Ab = A
 args = (ptr(Ab), K, ptr(W), K, 1, ptr(b), M, N, K)
-print('pass1 groupmax', t(lambda: LIB.call('dh_vocab_groupmax', *args, vs.stride, ptr(vs.gmax), vs.n_groups, stream())))
-print('threshold     ', t(lambda: LIB.call('dh_vocab_threshold', ptr(vs.gmax), vs.n_groups, M, vs.n_groups, 50, ptr(vs.thresh), ptr(vs.count), stream())))
+print('pass1 groupmax', t(lambda: LIB.call('dh_vocab_groupmax', *args, vs.stride, 0, ptr(vs.gmax), vs.n_groups_full, stream())))
+print('threshold     ', t(lambda: LIB.call('dh_vocab_threshold', ptr(vs.gmax), vs.n_groups_full, M, vs.groups(0), vs.rank, ptr(vs.thresh), ptr(vs.count), stream())))
 def p2():
     vs.count.zero_()
     LIB.call('dh_vocab_candidates', *args, ptr(vs.thresh), ptr(vs.count), ptr(vs.idx), ptr(vs.val), vs.cap, stream())
@@ -45,3 +47,15 @@ print('pass2 candidates (+zero)', t(p2))
 print('select_candidates', t(lambda: LIB.call('dh_select_candidates', ptr(vs.count), ptr(vs.idx), ptr(vs.val), vs.cap, M, 5, 50, 1.0, 1, 5, 1, 1, 0, 3, None, ptr(ind), ptr(val), ptr(status), None, stream())))
 print('fused total', t(lambda: vs.run(A, W, b, 5, 1.0, 1, 5, 1, 3, None, ind, val, status, None, seed=1)))
 print('candidates per row: mean %.1f max %d' % (float(vs.count.float().mean()), int(vs.count.max())))
+
+if vs.stride > 1:
+    lo, hi = 50, vs.cap
+    def fix():
+        LIB.call('dh_vocab_groupmax_fix', *args, ptr(vs.gmax), vs.n_groups_full, ptr(vs.count), lo, hi, ptr(vs.flag), stream())
+        LIB.call('dh_vocab_threshold_fix', ptr(vs.gmax), vs.n_groups_full, M, vs.n_groups_full, 50, ptr(vs.thresh), ptr(vs.count), lo, hi, ptr(vs.redo), ptr(vs.flag), stream())
+        LIB.call('dh_vocab_candidates_fix', *args, ptr(vs.thresh), ptr(vs.count), ptr(vs.idx), ptr(vs.val), vs.cap, ptr(vs.redo), ptr(vs.flag), stream())
+    print('fix-up x3 (nothing to fix)', t(fix))
+    print('rows below top_k:', int((vs.count < 50).sum()), 'min count', int(vs.count.min()), 'redo', int(vs.redo.sum()))
+    vs.count[:7] = 3      # force the repair path for 7 rows
+    fix(); torch.cuda.synchronize()
+    print('after forced repair: redo', int(vs.redo.sum()), 'counts', vs.count[:8].tolist(), 'flag', int(vs.flag))

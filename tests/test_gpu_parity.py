@@ -1,0 +1,121 @@
+"""Token-level parity of the CUDA path with reference-derived results at BASELINE sizes.
+
+ * tensor-core (bf16) mode -- the benchmarked path: fused vocab selection + beam step launch, in-launch operand gathers,
+   stacked LSTM, fused Q|K|V projection -- is compared with the CPU oracle STEP BY STEP: the whole beam state (sequences,
+   ended flags, cumulative scores) of every image must equal the oracle's after every decode step, up to the first step
+   whose oracle decision margin is below the stated bf16 bound (tests/helpers.py: BOUND_BF16); final captions must equal the
+   unmodified reference's (tests/golden, oracle/make_golden.py) for every image whose smallest margin exceeds the bound.
+ * fp32 check mode at BASELINE configs[1] (512 images) and a configs[4]-shaped batch (256 images, CaptioningTransformer):
+   captions of a 64-image sample equal the CPU oracle's bit for bit (near-ties below NEAR_TIE reported, bounded).
+ * BASELINE configs[0] exactly (cfg1 fixture from the unmodified reference): 1-layer LSTM, emb 256, greedy.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from deephumor_b200 import models
+from deephumor_b200.runtime import ops
+from deephumor_b200.utils import synth, synth_weights
+from oracle import model as omodel, noise as onoise
+from tests import helpers as H
+
+CLS = {'lstm': models.CaptioningLSTM, 'lstm_labels': models.CaptioningLSTMWithLabels,
+       'xfmr_base': models.CaptioningTransformerBase, 'xfmr': models.CaptioningTransformer}
+
+
+def build(kind, hp, sd, precision):
+    m = CLS[kind](**hp)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda().eval().set_precision(precision)
+
+
+def generate(m, kind, imgs, labs, **kw):
+    with torch.no_grad():
+        a = (imgs.cuda(), labs.cuda()) if kind == 'lstm_labels' else (imgs.cuda(),)
+        return m.generate(*a, **kw)
+
+
+def traced_generate(m, kind, imgs, labs, **kw):
+    ops.TRACE = []
+    try:
+        out = generate(m, kind, imgs, labs, **kw)
+        torch.cuda.synchronize()
+        return out, ops.TRACE
+    finally:
+        ops.TRACE = None
+
+
+@pytest.mark.parametrize('precision', ['bf16', 'fp32'])
+@pytest.mark.parametrize('variant', [1, 2])        # canon fixture: injected noise, beam 5 / top-k 50 and beam 1 / top-k 50
+@pytest.mark.parametrize('kind', H.KINDS)
+def test_beam_states_follow_the_oracle_step_by_step(kind, variant, precision):
+    fx = H.load_fixture('canon', kind)
+    g = fx['gen'][variant]
+    sd, imgs, labs, caps, lens = H.fixture_inputs(fx)
+    n = 32 if kind.startswith('lstm') else 16                  # the cache-less oracle transformer costs ~1 s per caption
+    oids, olens, traces = H.oracle_traces(fx, g, sd, imgs, labs, caps, n)
+    assert torch.equal(oids, g['ids'][:n]) and torch.equal(olens, g['lengths'][:n])       # oracle == unmodified reference
+    m = build(kind, fx['hp'], sd, precision)
+    kw = dict(max_len=fx['max_len'], temperature=g['temperature'], beam_size=g['beam_size'], top_k=g['top_k'],
+              noise=g['mode'], seed=g['noise_seed'])
+    (ids, ln), trace_dev = traced_generate(m, kind, imgs[:n], None if labs is None else labs[:n], **kw)
+    bound, vtol = (H.BOUND_BF16, 0.25) if precision == 'bf16' else (H.BOUND_FP32, 2e-3)
+    checked, total, whole = H.compare_beam_states(trace_dev, traces, g['beam_size'], bound, vtol)
+    print(f'{kind} {precision} B={g["beam_size"]}: {checked}/{total} steps checked against the oracle, {whole}/{n} images end to end')
+    # the comparison must not be vacuous
+    assert checked >= (0.9 if precision == 'fp32' else 0.25) * total
+    # images whose every decision clears the bound must reproduce the reference's caption exactly
+    full = [i for i, t in enumerate(traces) if t.abs_gap >= bound]
+    for i in full:
+        assert ids[i].cpu().tolist() == g['ids'][i].tolist() and int(ln[i]) == int(g['lengths'][i]), f'image {i}'
+    if precision == 'fp32':
+        assert len(full) >= n // 2
+
+
+@pytest.mark.parametrize('precision', ['bf16', 'fp32'])
+def test_cfg1_exact_config_matches_reference_fixture(precision):
+    """BASELINE.json configs[0]: CaptioningLSTM (1-layer, emb 256) greedy generate (beam 1, top-k 1), 8 images, max_len 32."""
+    fx = H.load_fixture('cfg1', 'lstm')
+    sd, imgs, labs, caps, lens = H.fixture_inputs(fx)
+    m = build('lstm', fx['hp'], sd, precision)
+    for g in fx['gen']:
+        ids, ln = generate(m, 'lstm', imgs, None, max_len=32, temperature=1.0, beam_size=1, top_k=1, noise=g['mode'],
+                           seed=g['noise_seed'])
+        # greedy has no sampling margins: the decision margin is the top-1 / top-2 logit gap
+        same = [ids[n].cpu().tolist() == g['ids'][n].tolist() and int(ln[n]) == int(g['lengths'][n]) for n in range(8)]
+        if precision == 'fp32':
+            assert all(same), same
+        else:
+            assert sum(same) >= 6, same          # bf16: an arg-max over 36 541 logits may flip on a near-tie
+
+
+@pytest.mark.parametrize('kind,n_img,sample', [('lstm_labels', 512, 64), ('xfmr', 256, 64)])
+def test_baseline_size_batches_match_the_oracle_in_fp32_mode(kind, n_img, sample):
+    """configs[1] (512 images, CaptioningLSTMWithLabels) and a configs[4]-shaped batch (256 images, CaptioningTransformer),
+    beam 5 / top-k 50 / 32 tokens / V = 36 541, injected noise, fp32 check mode: the captions of `sample` images spread over
+    the batch equal the CPU oracle's (per-image loop like the reference), bit for bit; near-ties are bounded."""
+    V, base = 36541, 5000
+    hp = synth_weights.default_hp(kind, V)
+    sd = synth_weights.make_state_dict(kind, hp, seed=0)
+    m = build(kind, hp, sd, 'fp32')
+    images = torch.empty(n_img, 3, 224, 224, device='cuda')
+    ops.synth_images(images, 0, base)
+    labs = synth.labels(0, base, n_img, V) if kind == 'lstm_labels' else None
+    kw = dict(max_len=32, temperature=1.0, beam_size=5, top_k=50)
+    ids, lens = generate(m, kind, images, labs, noise='injected', seed=77, image_base=base, **kw)
+    pick = list(range(0, n_img, n_img // sample))[:sample]
+    sel = images[pick].cpu()
+    assert torch.equal(sel, torch.stack([synth.images(0, base + i, 1)[0] for i in pick[:2]] + [sel[j] for j in range(2, len(pick))]))
+    bad, near = [], []
+    with torch.no_grad():
+        for j, i in enumerate(pick):
+            lab = None if labs is None else labs[i:i + 1]
+            gaps = []
+            oid, oln = omodel.generate_batch(kind, sd, hp, sel[j:j + 1], lab, first_index=base + i, gaps=gaps,
+                                             noise=onoise.Noise('injected', 77), **kw)
+            same = ids[i].cpu().tolist() == oid[0].tolist() and int(lens[i]) == int(oln[0])
+            if not same:
+                (near if gaps[0] < H.NEAR_TIE else bad).append(i)
+    assert not bad, f'{kind}: caption mismatch with the oracle on images {bad} (near-tie excused: {near})'
+    assert len(near) <= sample // 8, near
