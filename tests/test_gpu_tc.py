@@ -140,7 +140,7 @@ def test_stem_im2col_gemm(dt):
     assert H.rel_err(y.float(), ref) < (4e-3 if dt == torch.bfloat16 else 5e-4)
 
 
-@pytest.mark.parametrize('stride', [1, 4])
+@pytest.mark.parametrize('stride', [1, 4, 8])
 @pytest.mark.parametrize('mode', ['deterministic', 'injected'])
 @pytest.mark.parametrize('rows,V,K_,B,top_k,T', [(300, 36541, 512, 5, 50, 1.0), (7, 1000, 64, 3, 10, 0.8), (130, 4099, 128, 1, 1, 1.3),
                                                  (64, 2048, 256, 4, 64, 1.0), (5, 71, 64, 2, 2, 1.0), (5, 100, 64, 1, 1, 1.0),
@@ -164,7 +164,6 @@ def test_fused_vocab_select_matches_materialised_logits(mode, rows, V, K_, B, to
     ind0, val0, st0 = mk()
     ops.select_tokens(logits[:, :V], V, B, top_k, T, 1, rpi, ops.NOISE[mode], 11, 5, 3, None, ind0, val0, st0)
     assert ops.VocabSelect.supported(A, V, top_k)
-    stride = max(1, min(stride, ((V + 31) // 32) // (4 * top_k)))      # keep >= 4 top_k sampled groups
     vs = ops.VocabSelect(rows, V, top_k, DEV, stride=stride)
     ind1, val1, st1 = mk()
     vs.run(A, W, bias, B, T, 1, rpi, ops.NOISE[mode], 3, None, ind1, val1, st1, None, seed=11, image_base=5)
@@ -181,6 +180,48 @@ def test_fused_vocab_select_matches_materialised_logits(mode, rows, V, K_, B, to
         oi, ov = omodel.select_tokens(lc[r:r + 1], B, T, top_k, 1, q, None)
         assert ind1[r].cpu().tolist() == oi[0].tolist()
         assert torch.allclose(val1[r].cpu(), ov[0], atol=1e-5)
+
+
+@pytest.mark.parametrize('stride', [4, 8])
+def test_sampled_threshold_miss_is_repaired_in_stream(stride):
+    """A row whose largest logits ALL sit in the tiles the sampled pass 1 visits gets a threshold above its top_k-th largest
+    logit (fewer than top_k candidates); the fix-up launches must detect it from the candidate counts and redo that row
+    exhaustively, in stream order, so the picks equal the materialised-logits path; untouched rows keep their lists."""
+    rows, V, K_, B, top_k, step = 200, 36541, 512, 5, 50, 5
+    g = torch.Generator().manual_seed(3)
+    A = (torch.randn(rows, K_, generator=g) * 0.5).to(torch.bfloat16).to(DEV)
+    W = (torch.randn(V, K_, generator=g) * 0.2).to(torch.bfloat16).to(DEV)
+    bias = torch.randn(V, generator=g)
+    vs = ops.VocabSelect(rows, V, top_k, DEV, stride=stride)
+    assert vs.stride == stride and vs.rank < top_k
+    off = step % stride
+    cols = [(off + stride * t) * 256 + 32 * gidx + 5 for t in range(7) for gidx in range(8)][:49]     # distinct sampled groups
+    bias[cols] += 40.0                                      # the 49 largest logits of EVERY row; the 50th is an ordinary one
+    bias = bias.to(DEV)
+    logits = torch.empty(rows, (V + 3) // 4 * 4, device=DEV)
+    ops.gemm(A, W, logits[:, :V], bias=bias)
+    mk = lambda: (torch.empty(rows, B, dtype=torch.int32, device=DEV), torch.empty(rows, B, device=DEV),
+                  torch.zeros(1, dtype=torch.int32, device=DEV))
+    ind0, val0, st0 = mk()
+    ops.select_tokens(logits[:, :V], V, B, top_k, 1.0, 1, B, ops.NOISE['injected'], 11, 5, step, None, ind0, val0, st0)
+    ind1, val1, st1 = mk()
+    vs.run(A, W, bias, B, 1.0, 1, B, ops.NOISE['injected'], step, None, ind1, val1, st1, None, seed=11, image_base=5)
+    torch.cuda.synchronize()
+    assert int(vs.redo.sum()) == rows and int(vs.flag) == 1                     # every row missed and was repaired
+    assert int(vs.count.min()) >= top_k and int(vs.count.max()) <= vs.cap
+    assert int(st1.item()) == 0 and torch.equal(ind0, ind1) and torch.equal(val0, val1)
+    # next step: ordinary rows -> nothing to repair, the flag is cleared again
+    bias2 = torch.randn(V, generator=g).to(DEV)
+    vs.run(A, W, bias2, B, 1.0, 1, B, ops.NOISE['injected'], step + 1, None, ind1, val1, st1, None, seed=11, image_base=5)
+    torch.cuda.synchronize()
+    assert int(vs.redo.sum()) == 0 and int(vs.flag) == 0 and int(vs.count.min()) >= top_k
+
+
+def test_top_k_above_64_takes_the_materialised_path():
+    """the fused selection ranks at most 64 group maxima exactly; larger top_k must not be routed to it."""
+    A = torch.zeros(4, 64, dtype=torch.bfloat16, device=DEV)
+    assert ops.VocabSelect.supported(A, 36541, 64) and not ops.VocabSelect.supported(A, 36541, 100)
+    assert not ops.VocabSelect.supported(A, 1000, 50)       # fewer than top_k 32-column groups
 
 
 def _pack_stem(w, dt):
