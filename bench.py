@@ -1,21 +1,30 @@
 """Headline benchmark: captions/sec, beam 5, 32 tokens (BASELINE.json), one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg5|cfg4|cfg1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg5|cfg2|cfg4|cfg3|cfg1]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
 A "step" = one pass of the caption path over one batch of synthetic images: ResNet-50 encoder (+ label encoder)
--> decoder -> stochastic beam search (beam 5, top-k 50, max_len 32) -> token ids.  Default workload at every N is
-BASELINE.json configs[1]: CaptioningLSTMWithLabels (emb 512 / hidden 512 / 3 layers, V = 36 541), 512 images per
-GPU (weak scaling: images are sharded by global index, no collective in the loop, ONE all-gather of ids at the end
-of each step).  `value` = images all ranks processed / max-over-ranks device time, inputs resident in HBM; `e2e`
-= same through model.generate() with pinned HOST images copied in and ids copied out every step.
+-> decoder -> stochastic beam search (beam 5, top-k 50, max_len 32) -> token ids -> ONE all-gather of the ids.
+
+Default workload at every N is BASELINE.json configs[4] (`cfg5`, the north star's multi-GPU configuration):
+CaptioningTransformer (7x7 spatial features, cross-attention), 65 536 images per step STRONG-scaled over the N GPUs
+(65 536 / N images per rank, generated in sub-batches of 8 192 -- the per-GPU batch at N = 8), sharded by global
+image index, no collective in the loop.  The JSON line also carries a `cfg2` object: BASELINE.json configs[1]
+(CaptioningLSTMWithLabels, 512 images per GPU, weak-scaled) with its own value / e2e / stages.
+
+`value`  = images all ranks processed / max-over-ranks device time, fp32 NCHW images resident in HBM (the reference
+           API's input type).
+`e2e`    = the same metric through model.generate() with HOST buffers: uint8 pixels in pinned host memory (what a
+           loader holds before ToTensor + Normalize, which run fused in the stem kernel), streamed host->device inside
+           the call, ids / lengths copied back to the host every step.
 
 --impl reference times the CPU restatement of the reference (oracle/, kind "port": /root/reference is pure
 Python + torch and does not exist on the GPU box) on a bounded sample of the same workload, all host threads.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -29,24 +38,26 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 V = 36541
-WORKLOADS = {
-    # name: (kind, per-GPU batch, beam, top_k, description)
-    'cfg2': ('lstm_labels', 512, 5, 50, 'CaptioningLSTMWithLabels beam5 top_k50 max_len32, 512 images/GPU, V=36541'),
-    'cfg5': ('xfmr', 8192, 5, 50, 'CaptioningTransformer beam5 top_k50 max_len32, 8192 images/GPU, V=36541'),
-    'cfg4': ('xfmr', 4096, 1, 50, 'CaptioningTransformer top_k50 sampling max_len32, 4096 images/GPU, V=36541'),
-    'cfg1': ('lstm', 8, 1, 1, 'CaptioningLSTM greedy max_len32, 8 images/GPU, V=36541'),
-    # teacher-forced perplexity eval (value = sequences/s): encoder + decoder over 32 positions + fused log-softmax
-    'cfg3': ('xfmr_base', 2048, 0, 0, 'CaptioningTransformerBase teacher-forced perplexity, 2048 x 32 tokens/GPU, V=36541'),
-}
 MAX_LEN = 32
+SUB_BATCH = 8192
+WORKLOADS = {
+    # name: (kind, images, scaling, beam, top_k, description)   images = total (strong) or per GPU (weak)
+    'cfg5': ('xfmr', 65536, 'strong', 5, 50,
+             'CaptioningTransformer beam5 top_k50 max_len32, 65536 images sharded over the GPUs, V=36541'),
+    'cfg2': ('lstm_labels', 512, 'weak', 5, 50, 'CaptioningLSTMWithLabels beam5 top_k50 max_len32, 512 images/GPU, V=36541'),
+    'cfg4': ('xfmr', 4096, 'weak', 1, 50, 'CaptioningTransformer top_k50 sampling max_len32, 4096 images/GPU, V=36541'),
+    'cfg1': ('lstm', 8, 'weak', 1, 1, 'CaptioningLSTM greedy max_len32, 8 images/GPU, V=36541'),
+    # teacher-forced perplexity eval (value = sequences/s): encoder + decoder over 32 positions + fused log-softmax
+    'cfg3': ('xfmr_base', 2048, 'weak', 0, 0,
+             'CaptioningTransformerBase teacher-forced perplexity, 2048 x 32 tokens/GPU, V=36541'),
+}
 METRIC = 'captions/sec (beam 5, 32 tok)'
 
 
 def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
-        d = json.load(open(p))
-        return d, 'measured'
+        return json.load(open(p)), 'measured'
     return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
 
 
@@ -64,7 +75,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix='.csv')
             os.close(fd)
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-lms', '25', '-i', str(self.index)],
+                                          '-lms', '50', '-i', str(self.index)],
                                          stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -99,15 +110,19 @@ class ClockSampler:
         return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': max(mx), 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def build_model(kind, precision):
-    from deephumor_b200 import models
+def model_hp(kind):
     from deephumor_b200.utils import synth_weights
-    cls = {'lstm': models.CaptioningLSTM, 'lstm_labels': models.CaptioningLSTMWithLabels,
-           'xfmr_base': models.CaptioningTransformerBase, 'xfmr': models.CaptioningTransformer}[kind]
     hp = synth_weights.default_hp(kind, V)
     if kind == 'lstm':            # BASELINE.json configs[0]: 1-layer LSTMDecoder, emb 256
         hp.update(emb_dim=256, num_layers=1)
-    sd = synth_weights.make_state_dict(kind, hp, seed=0)
+    return hp, synth_weights.make_state_dict(kind, hp, seed=0)
+
+
+def build_model(kind, precision):
+    from deephumor_b200 import models
+    cls = {'lstm': models.CaptioningLSTM, 'lstm_labels': models.CaptioningLSTMWithLabels,
+           'xfmr_base': models.CaptioningTransformerBase, 'xfmr': models.CaptioningTransformer}[kind]
+    hp, sd = model_hp(kind)
     m = cls(**hp)
     m.load_state_dict(sd, strict=True)
     return m.cuda().eval().set_precision(precision), hp, sd
@@ -127,12 +142,295 @@ def algorithmic_flops(kind, beam, n_img):
     return n_img * (enc + extra + steps * row_step)
 
 
-def traffic_bytes(args, rows):
+def config_of(name, world, batch=0):
+    """The `config` object of the JSON line: identical for the CUDA arm and the reference arm of the same workload."""
+    kind, images, scaling, beam, top_k, desc = WORKLOADS[name]
+    total = batch * world if batch else (images if scaling == 'strong' else images * world)
+    return {'workload': f'{name}: {desc}', 'images_per_step': total, 'images_per_gpu': total // world,
+            'sub_batch': min(SUB_BATCH, total // world), 'max_len': MAX_LEN, 'beam_size': beam, 'top_k': top_k,
+            'noise': 'injected', 'scaling': scaling,
+            'parallelism': f'dp{world} (images sharded by global index; one all-gather of ids per step)',
+            'l2': 'inputs larger than L2 (>= 300 MB of images per GPU per step)',
+            'precision': 'ours: trunk fp16 storage / fp32 accumulate (tcgen05 kind::f16), decoders bf16 / fp32 accumulate, '
+                         'global embedding head fp32; reference arm: fp32 on the host CPU',
+            'input': 'ours: `value` from fp32 NCHW images resident in HBM, `e2e` from uint8 NCHW pixels in pinned host memory'}
+
+
+def u8_of(images):
+    """uint8 pixels derived from the synthetic fp32 images (same global-index keyed content)."""
+    return (images * 58.0 + 116.0).clamp_(0, 255).to(torch.uint8)
+
+
+class Workload:
+    """One rank's share of a workload: model, device-resident fp32 images, pinned-host uint8 pixels, step functions."""
+
+    def __init__(self, name, rank, world, dev, precision, batch=0):
+        from deephumor_b200.runtime import ops
+        from deephumor_b200.utils import synth
+        self.name, self.rank, self.world, self.dev = name, rank, world, dev
+        self.kind, images, self.scaling, self.beam, self.top_k, self.desc = WORKLOADS[name]
+        self.total = batch * world if batch else (images if self.scaling == 'strong' else images * world)
+        assert self.total % world == 0
+        self.n_local = self.total // world
+        self.first = rank * self.n_local
+        self.sub = min(SUB_BATCH, self.n_local)
+        assert self.n_local % self.sub == 0
+        self.model, self.hp, self.sd = build_model(self.kind, precision)
+        self.images = torch.empty(self.n_local, 3, 224, 224, device=dev)
+        self.host_u8 = torch.empty(self.n_local, 3, 224, 224, dtype=torch.uint8, pin_memory=True)
+        for i0 in range(0, self.n_local, 1024):
+            i1 = min(i0 + 1024, self.n_local)
+            ops.synth_images(self.images[i0:i1], 0, self.first + i0)
+            self.host_u8[i0:i1].copy_(u8_of(self.images[i0:i1].clone()))
+        self.labels = synth.labels(0, self.first, self.n_local, V).to(dev) if self.kind == 'lstm_labels' else None
+        self.host_labels = self.labels.cpu().pin_memory() if self.labels is not None else None
+        self.captions = self.cap_lens = None
+        if name == 'cfg3':
+            c, l = synth.captions(0, self.first, self.n_local, V, width=MAX_LEN, min_len=8)
+            self.captions, self.cap_lens = c.to(dev), l.to(dev)
+        self.gen_kw = dict(max_len=MAX_LEN, temperature=1.0, beam_size=self.beam, top_k=self.top_k, noise='injected',
+                           seed=1234)
+
+    def _generate(self, img, lab, i0):
+        with torch.no_grad():
+            kw = dict(self.gen_kw, image_base=self.first + i0)
+            out = self.model.generate(img, lab, **kw) if lab is not None else self.model.generate(img, **kw)
+        if isinstance(out, tuple):
+            return out
+        ids = torch.zeros(1, MAX_LEN, dtype=torch.int64, device=self.dev)
+        ids[0, :out.numel()] = out
+        return ids, torch.tensor([out.numel()], device=self.dev)
+
+    def _gather(self, outs):
+        # the path's only collective (SURVEY.md 8(e)): one all-gather of ids (+ lengths) per step; identity at N = 1
+        from deephumor_b200.runtime import shard
+        ids = outs[0][0] if len(outs) == 1 else torch.cat([o[0] for o in outs])
+        lens = outs[0][1] if len(outs) == 1 else torch.cat([o[1] for o in outs])
+        return shard.gather_captions(ids, lens, total=self.total)
+
+    def step(self):
+        """Device-resident fp32 images -> gathered ids (on the device)."""
+        if self.captions is not None:                    # config 3: one scalar leaves the device
+            with torch.no_grad():
+                return self.model.perplexity(self.images, self.captions, self.cap_lens)
+        outs = []
+        for i0 in range(0, self.n_local, self.sub):
+            lab = self.labels[i0:i0 + self.sub] if self.labels is not None else None
+            outs.append(self._generate(self.images[i0:i0 + self.sub], lab, i0))
+        return self._gather(outs)
+
+    def step_e2e(self):
+        """Pinned-host uint8 pixels -> ids / lengths on the HOST: generate() streams the pixels to the device in chunks
+        (copy of chunk k + 1 overlapping the trunk of chunk k), preprocessing fused into the stem kernel."""
+        if self.captions is not None:
+            with torch.no_grad():
+                return self.model.perplexity(self.host_u8, self.captions, self.cap_lens).cpu()
+        outs = []
+        for i0 in range(0, self.n_local, self.sub):
+            lab = self.host_labels[i0:i0 + self.sub].to(self.dev, non_blocking=True) if self.host_labels is not None else None
+            outs.append(self._generate(self.host_u8[i0:i0 + self.sub], lab, i0))
+        ids, lens = self._gather(outs)
+        return ids.cpu(), lens.cpu()
+
+    def h2d_bytes(self):
+        return int(self.host_u8.numel() + (self.host_labels.numel() * 8 if self.host_labels is not None else 0))
+
+    def d2h_bytes(self):
+        return int(self.total * MAX_LEN * 8 + self.total * 8) if self.captions is None else 4
+
+
+def timed(fn, steps, dist, dev, profile=False):
+    """`steps` calls of fn bracketed by barrier + synchronize, CUDA events on the launching stream, max over ranks."""
+    from deephumor_b200 import _lib
+    from deephumor_b200.runtime import ops
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = _lib.LIB.launches
+    if profile:
+        ops.PROFILE.start()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    prof = ops.PROFILE.stop() if profile else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    return float(ms.item()), _lib.LIB.launches - l0, prof
+
+
+def measure(wl, steps, warmup, dist, dev, rank, local, min_seconds=2.0):
+    """Warm-up, the timed device-resident pass (with clock sampling), one eagerly launched profiling step (CUDA-event
+    ranges per stage; the timed pass replays the decode loop as a CUDA graph, where events cannot be recorded), and the
+    end-to-end pass from pinned host pixels.  A workload whose K steps take less than `min_seconds` runs more steps (the
+    line reports the count it timed)."""
+    for _ in range(max(warmup, 3)):
+        wl.step()
+    ms1, _, _ = timed(wl.step, 1, dist, dev)
+    k = max(steps, int(math.ceil(min_seconds * 1e3 / max(ms1, 1e-3))))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, _, _ = timed(wl.step, k, dist, dev)
+    clocks = sampler.stop() if rank == 0 else None
+    _, launches_step, prof = timed(wl.step, 1, dist, dev, profile=True)
+    wl.step_e2e()
+    ms_e2e, _, _ = timed(wl.step_e2e, k, dist, dev)
+    return dict(ms=ms, k=k, ms_e2e=ms_e2e, ke=k, clocks=clocks, prof=prof, launches_step=launches_step)
+
+
+def stage_report(prof, pk):
+    """Per-stage time of ONE step, tensor-pipe fraction of the tensor-bound stages (algorithmic FLOPs / CUDA-event time /
+    measured sustained bf16 peak) and HBM GB/s of the bandwidth-bound ones (algorithmic bytes / time; fraction of the
+    measured copy bandwidth -- above 1 means the stage is served by L1/L2 reuse, e.g. beams sharing cached K/V rows)."""
+    sustained = pk.get('bf16_tflops_sustained', pk.get('bf16_tflops'))
+    hbm = pk.get('hbm_gbs', 6650.0)
+    ms = {k: round(v[1], 3) for k, v in prof.items()}
+    tf = {k: round(v[2] / (v[1] / 1e3) / 1e12 / sustained, 3) for k, v in prof.items() if v[2] > 0 and v[1] > 0}
+    gb = {k: {'gbs': round(v[3] / (v[1] / 1e3) / 1e9, 1), 'frac': round(v[3] / (v[1] / 1e3) / 1e9 / hbm, 3)}
+          for k, v in prof.items() if v[3] > 0 and v[1] > 0}
+    return ms, tf, gb
+
+
+def roofline_of(res, pk, pk_src, precision, traffic):
+    """Roofline of the dominant single-shape kernel: the vocab-projection contraction with the candidate-compaction
+    epilogue (one launch = one full [rows, 36541, 512] product); achieved = algorithmic FLOPs / CUDA-event time."""
+    prof = res['prof']
+    if not prof or not prof.get('vocab_gemm'):
+        return None
+    sustained = pk.get('bf16_tflops_sustained', pk.get('bf16_tflops'))
+    n, tot_ms, flops, _ = prof['vocab_gemm']
+    ach = flops / (tot_ms / 1e3) / 1e12
+    return {'kernel': 'gemm_tc_kernel<256,pair,2>: vocab projection [rows,512]x[512,36541] with the candidate-compaction '
+                      'epilogue (logits never stored)' if precision == 'bf16' else 'igemm_f32_kernel (fp32 check mode FFMA)',
+            'bound': 'tensor', 'achieved': round(ach, 2), 'peak': sustained, 'unit': 'TFLOP/s',
+            'frac': round(ach / sustained, 4), 'traffic': traffic,
+            'peak_source': f'{pk_src}, bf16 sustained (kernel timed inside a seconds-long region)', 'launches': n,
+            'avg_ms': round(tot_ms / n, 4), 'share_of_step': round(tot_ms / (res['ms'] / res['k']), 4),
+            'note': 'kernel timed with CUDA events in an eagerly launched step right after the timed pass (which replays the '
+                    'decode loop as a CUDA graph); rows are the workload\'s real decoder states -- see roofline_decorrelated'}
+
+
+def roofline_decorrelated(wl, pk, rows):
+    """The same kernel on UNRELATED rows (per-row random activations): random-init decoder states of different images are
+    nearly collinear (cosine ~0.96), which is the best case for the candidate scan; trained weights are not."""
+    from deephumor_b200._lib import LIB, ptr, stream
+    from deephumor_b200.runtime import ops
+    dec = wl.model.decoder._rt()
+    dev = wl.dev
+    K = dec.Wc.shape[1]
+    g = torch.Generator(device=dev).manual_seed(7)
+    A = (torch.randn(rows, K, device=dev, generator=g) * 0.5).to(dec.Wc.dtype)
+    vs = ops.VocabSelect(rows, V, wl.top_k or 50, dev)
+    args = (ptr(A), K, ptr(dec.Wc), K, ops.code(A), ptr(dec.bc), rows, V, K)
+    LIB.call('dh_vocab_groupmax', *args, vs.stride, 0, ptr(vs.gmax), vs.n_groups_full, stream())
+    LIB.call('dh_vocab_threshold', ptr(vs.gmax), vs.n_groups_full, rows, vs.groups(0), vs.rank, ptr(vs.thresh), ptr(vs.count),
+             stream())
+    flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    ts = []
+    for _ in range(12):
+        vs.count.zero_()
+        flush.zero_()                                                 # L2 flush between timed launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        LIB.call('dh_vocab_candidates', *args, ptr(vs.thresh), ptr(vs.count), ptr(vs.idx), ptr(vs.val), vs.cap, stream())
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts = sorted(ts[2:])
+    ms = ts[len(ts) // 2]
+    peak = pk.get('bf16_tflops', 1590.0)
+    ach = 2.0 * rows * V * K / (ms / 1e3) / 1e12
+    return {'kernel': 'same kernel, per-row random activations (unrelated rows), timed alone with an L2 flush between launches',
+            'rows': rows, 'avg_ms': round(ms, 4), 'achieved': round(ach, 2), 'peak': peak, 'unit': 'TFLOP/s',
+            'frac': round(ach / peak, 4), 'peak_source': 'bf16 burst (kernel timed alone)',
+            'candidates_per_row': round(float(vs.count.float().mean()), 1)}
+
+
+def gpu_eager_baseline(dev):
+    """The existing Blackwell library path on the same box: torchvision ResNet-50 through
+    cuDNN (channels_last; bf16 and TF32) and torch.matmul (cuBLASLt) for the vocab projection.  Reported, not the target."""
+    out = {}
+
+    def run(fn, reps):
+        with torch.no_grad():
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    try:
+        import torchvision
+        net = torchvision.models.resnet50(weights=None)
+        trunk = torch.nn.Sequential(*list(net.children())[:-2]).to(dev).eval()
+        x = torch.randn(512, 3, 224, 224, device=dev)
+        t16 = trunk.to(torch.bfloat16).to(memory_format=torch.channels_last)
+        x16 = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        ms = run(lambda: t16(x16), 5)
+        out['resnet50_trunk_bf16_channels_last'] = {'images_per_s': round(512 / ms * 1e3, 1), 'ms_per_512': round(ms, 3)}
+        torch.backends.cudnn.allow_tf32 = True
+        torch.backends.cuda.matmul.allow_tf32 = True
+        t32 = trunk.float().to(memory_format=torch.channels_last)
+        x32 = x.contiguous(memory_format=torch.channels_last)
+        ms = run(lambda: t32(x32), 5)
+        out['resnet50_trunk_tf32_channels_last'] = {'images_per_s': round(512 / ms * 1e3, 1), 'ms_per_512': round(ms, 3)}
+        del trunk, t16, t32, x, x16, x32
+    except Exception as e:                               # the bar is informative only
+        out['resnet50_trunk'] = f'unavailable: {type(e).__name__}: {e}'[:160]
+    try:
+        a = torch.randn(2560, 512, device=dev).to(torch.bfloat16)
+        w = torch.randn(V, 512, device=dev).to(torch.bfloat16)
+        c = torch.empty(2560, V, device=dev, dtype=torch.bfloat16)
+        ms = run(lambda: torch.matmul(a, w.t(), out=c), 20)
+        out['matmul_2560x512x36541_bf16'] = {'ms': round(ms, 4), 'tflops': round(2 * 2560 * 512 * V / ms / 1e9, 1),
+                                             'note': 'stores bf16 logits (187 MB); ours never stores them'}
+    except Exception as e:
+        out['matmul'] = f'unavailable: {type(e).__name__}: {e}'[:160]
+    torch.cuda.empty_cache()
+    return out
+
+
+def traffic_bytes(precision, rows):
     """DRAM bytes per launch of the roofline kernel from the committed `ncu --set full` capture (same shape only)."""
     p = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
-    if args.precision != 'bf16' or rows != 2560 or not os.path.exists(p):
+    if precision != 'bf16' or not os.path.exists(p):
         return None
-    return json.load(open(p)).get('dram_bytes_per_launch')
+    d = json.load(open(p))
+    by_rows = d.get('dram_bytes_per_launch_by_rows', {})
+    return by_rows.get(str(rows), d.get('dram_bytes_per_launch') if rows == 2560 else None)
+
+
+def summarize(wl, res, pk, pk_src, precision, world, batch=0):
+    teacher = wl.captions is not None
+    unit = 'sequences/s' if teacher else 'captions/s'
+    value = wl.total * res['k'] / (res['ms'] / 1e3)
+    e2e = wl.total * res['ke'] / (res['ms_e2e'] / 1e3)
+    out = {
+        'value': round(value, 2), 'unit': unit, 'steps': res['k'], 'ms_per_step': round(res['ms'] / res['k'], 3),
+        'scaling': wl.scaling, 'config': config_of(wl.name, world, batch),
+        'decode_tokens_per_s': round(value * MAX_LEN, 1),
+        'e2e': {'value': round(e2e, 2), 'unit': unit, 'ms_per_step': round(res['ms_e2e'] / res['ke'], 3), 'steps': res['ke'],
+                'h2d_bytes_per_step': wl.h2d_bytes() * world, 'd2h_bytes_per_step': wl.d2h_bytes(),
+                'input': 'uint8 pixels from pinned host memory, ToTensor + Normalize fused into the stem kernel'},
+        'gpu_launches': int(res['launches_step'] * res['k']), 'gpu_launches_per_step': int(res['launches_step']),
+        'clocks': res['clocks'], 'timed_region_s': round(res['ms'] / 1e3, 2),
+        'step_tflops': round(algorithmic_flops(wl.kind, wl.beam, wl.total) / (res['ms'] / res['k'] / 1e3) / 1e12, 2),
+    }
+    rl = roofline_of(res, pk, pk_src, precision, traffic_bytes(precision, wl.sub * max(wl.beam, 1)))
+    if rl:
+        out['roofline'] = rl
+    if res['prof']:
+        out['stages_ms_per_step'], out['stages_tensor_frac'], out['stages_hbm'] = stage_report(res['prof'], pk)
+    return out
 
 
 def run_ours(args):
@@ -144,154 +442,55 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    from deephumor_b200 import _lib
-    from deephumor_b200.runtime import ops, shard
-    from deephumor_b200.utils import synth
-    kind, batch, beam, top_k, desc = WORKLOADS[args.workload]
-    if args.batch:
-        batch = args.batch
-    model, hp, sd = build_model(kind, args.precision)
+    from deephumor_b200.runtime import ops
     dev = torch.device('cuda', local)
-    first = rank * batch
-    images = torch.empty(batch, 3, 224, 224, device=dev)
-    ops.synth_images(images, 0, first)
-    labels = synth.labels(0, first, batch, V).to(dev) if kind == 'lstm_labels' else None
-    host_images = torch.empty(batch, 3, 224, 224, pin_memory=True)
-    host_images.copy_(images)
-    host_labels = labels.cpu().pin_memory() if labels is not None else None
-    gen_kw = dict(max_len=MAX_LEN, temperature=1.0, beam_size=beam, top_k=top_k, noise='injected', seed=1234,
-                  image_base=first)
-
-    captions = cap_lens = None
-    if args.workload == 'cfg3':
-        captions, cap_lens = synth.captions(0, first, batch, V, width=MAX_LEN, min_len=8)
-        captions, cap_lens = captions.to(dev), cap_lens.to(dev)
-
-    def step(img, lab):
-        if captions is not None:                     # config 3: one scalar leaves the device
-            with torch.no_grad():
-                pp = model.perplexity(img, captions, cap_lens)
-            return pp.view(1, 1), pp.view(1)
-        with torch.no_grad():
-            out = model.generate(img, lab, **gen_kw) if lab is not None else model.generate(img, **gen_kw)
-        ids, lens = out if isinstance(out, tuple) else (out.view(1, -1), torch.tensor([out.numel()], device=dev))
-        # the path's only collective: one all-gather of ids (+lengths) per step; identity at N=1
-        return shard.gather_captions(ids, lens, total=batch * world)
-
-    def step_e2e():
-        # the user-facing call with HOST buffers: generate() streams the pinned images to the device in chunks
-        # (copy of chunk k+1 overlapping the trunk of chunk k) and the ids / lengths are read back
-        lab = host_labels.to(dev, non_blocking=True) if host_labels is not None else None
-        ids, lens = step(host_images, lab)
-        return ids.cpu(), (lens.cpu() if lens is not None else None)
-
-    def timed(fn, steps, profile=False):
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = _lib.LIB.launches
-        if profile:
-            ops.PROFILE.start()
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        prof = ops.PROFILE.stop() if profile else None
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-            dist.barrier()
-        return float(ms.item()), _lib.LIB.launches - l0, prof
+    wl = Workload(args.workload, rank, world, dev, args.precision, args.batch)
 
     if args.profile_mode:       # under `ncu --profile-from-start off`: warm-up, then ONE eagerly launched step
-        step(images, labels)
-        step(images, labels)
+        wl.step()
+        wl.step()
         torch.cuda.synchronize()
         ops.USE_GRAPHS = False
         torch.cuda.profiler.start()
-        step(images, labels)
+        wl.step()
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
-    for _ in range(max(args.warmup, 3)):
-        step(images, labels)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ms, launches, _ = timed(lambda: step(images, labels), args.steps)
-    clocks = sampler.stop() if rank == 0 else None
-    # per-stage / per-kernel CUDA-event ranges: a second pass over the same steps, launched eagerly because the
-    # timed pass replays the decode loop as one CUDA graph (events cannot be recorded inside a replay)
-    _, launches_eager, prof = timed(lambda: step(images, labels), args.steps, profile=True)
-    launches = max(launches, launches_eager)
-    step_e2e()
-    ms_e2e, _, _ = timed(step_e2e, args.steps)
-    # extension: raw uint8 pixels from the host, ToTensor + Normalize fused into the stem kernel
-    ms_e2e_u8 = None
-    if args.precision == 'bf16' and captions is None:
-        host_u8 = torch.randint(0, 256, (batch, 3, 224, 224), dtype=torch.uint8).pin_memory()
 
-        def step_e2e_u8():
-            lab = host_labels.to(dev, non_blocking=True) if host_labels is not None else None
-            ids, lens = step(host_u8, lab)
-            return ids.cpu(), lens.cpu()
-        step_e2e_u8()
-        ms_e2e_u8, _, _ = timed(step_e2e_u8, args.steps)
-
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
-    total = batch * world
-    value = total * args.steps / (ms / 1e3)
-    e2e = total * args.steps / (ms_e2e / 1e3)
     pk, pk_src = peaks()
-    line = {
-        'metric': METRIC if captions is None else 'sequences/sec (teacher-forced perplexity, 32 tok)',
-        'value': round(value, 2), 'unit': 'captions/s' if captions is None else 'sequences/s', 'n_gpus': world, 'steps': args.steps,
-        'warmup': max(args.warmup, 3), 'ms_per_step': round(ms / args.steps, 3), 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': args.precision if args.precision != 'fp32' else 'f32',
-        'data': 'synthetic (hash-generated 224x224 images by global index, random-init weights seed 0)',
-        'config': {'workload': f'{args.workload}: {desc}', 'images_per_gpu': batch, 'global_batch': total,
-                   'max_len': MAX_LEN, 'beam_size': beam, 'top_k': top_k, 'noise': 'injected',
-                   'l2': 'inputs larger than L2 (308 MB fp32 images per GPU per step)',
-                   'parallelism': f'dp{world} (images sharded by global index; one all-gather of ids per step)'},
-        'decode_tokens_per_s': round(value * MAX_LEN, 1),
-        'e2e': {'value': round(e2e, 2), 'unit': 'captions/s', 'ms_per_step': round(ms_e2e / args.steps, 3),
-                'h2d_bytes_per_step': int(host_images.numel() * 4 + (host_labels.numel() * 8 if host_labels is not None else 0)),
-                'd2h_bytes_per_step': int(batch * MAX_LEN * 8 + batch * 8)},
-        'gpu_launches': int(launches), 'clocks': clocks,
-    }
-    if ms_e2e_u8 is not None:
-        line['e2e_uint8'] = {'value': round(total * args.steps / (ms_e2e_u8 / 1e3), 2), 'unit': 'captions/s',
-                             'ms_per_step': round(ms_e2e_u8 / args.steps, 3), 'h2d_bytes_per_step': int(batch * 3 * 224 * 224),
-                             'note': 'host uint8 pixels, preprocessing fused into the stem kernel (not the headline e2e)'}
-    # ---- roofline of the dominant kernel (the vocab-projection contraction)
-    flops_step = algorithmic_flops(kind, beam, batch)
-    sustained = pk.get('bf16_tflops_sustained', pk.get('bf16_tflops'))
-    line['step_tflops'] = round(flops_step / (ms / args.steps / 1e3) / 1e12, 2)
-    if prof and prof.get('vocab_gemm'):
-        n, tot_ms, flops, _ = prof['vocab_gemm']
-        ach = flops / (tot_ms / 1e3) / 1e12
-        tensor_path = args.precision == 'bf16'
-        line['roofline'] = {'kernel': 'gemm_tc_kernel, candidate-compaction epilogue (vocab projection [rows,512]x[512,36541], '
-                                      'pass 2 of the fused selection; logits never stored)' if tensor_path
-                            else 'igemm_f32_kernel (fp32 check mode FFMA)',
-                            'bound': 'tensor', 'achieved': round(ach, 2), 'peak': sustained, 'unit': 'TFLOP/s',
-                            'frac': round(ach / sustained, 4), 'traffic': traffic_bytes(args, batch * beam), 'peak_source': f'{pk_src}, sustained bf16',
-                            'launches': n, 'avg_ms': round(tot_ms / n, 4),
-                            'share_of_step': round(tot_ms / args.steps / (ms / args.steps), 4)}
-        line['roofline']['note'] = ('kernel timed with CUDA events in an eager pass of the same steps right after the '
-                                    'timed pass (which replays the decode loop as a CUDA graph)')
-        line['stages_ms_per_step'] = {k: round(v[1] / args.steps, 3) for k, v in prof.items()}
-        # per-stage tensor-pipe fraction (algorithmic FLOPs of the stage / its CUDA-event time / measured sustained peak)
-        line['stages_tensor_frac'] = {k: round(v[2] / (v[1] / 1e3) / 1e12 / sustained, 3)
-                                      for k, v in prof.items() if v[2] > 0 and v[1] > 0}
-    if not args.no_cpu_baseline and world == 1:          # reported at N = 1 only
-        line['cpu_baseline'] = cpu_baseline(kind, hp, sd, beam, top_k, args.cpu_images)
-    print(json.dumps(line))
+    res = measure(wl, args.steps, args.warmup, dist, dev, rank, local)
+    line = None
+    if rank == 0:
+        s = summarize(wl, res, pk, pk_src, args.precision, world, args.batch)
+        line = {'metric': METRIC if wl.captions is None else 'sequences/sec (teacher-forced perplexity, 32 tok)',
+                'value': s.pop('value'), 'unit': s.pop('unit'), 'n_gpus': world, 'steps': s.pop('steps'),
+                'steps_requested': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': s.pop('ms_per_step'),
+                'higher_is_better': True, 'scaling': s.pop('scaling'), 'vs_baseline': None,
+                'dtype': args.precision if args.precision != 'fp32' else 'f32',
+                'data': 'synthetic (hash-generated 224x224 images by global index, random-init weights seed 0)'}
+        line.update(s)
+        if args.precision == 'bf16' and wl.captions is None and not args.quick:
+            line['roofline_decorrelated'] = roofline_decorrelated(wl, pk, min(wl.sub * wl.beam, 40960))
+    # second workload on the same line: BASELINE.json configs[1] (weak-scaled 512 images per GPU)
+    if args.workload == 'cfg5' and not args.quick and not args.batch:
+        del wl
+        torch.cuda.empty_cache()
+        wl2 = Workload('cfg2', rank, world, dev, args.precision)
+        r2 = measure(wl2, args.steps, args.warmup, dist, dev, rank, local)
+        if rank == 0:
+            line['cfg2'] = summarize(wl2, r2, pk, pk_src, args.precision, world)
+            if args.precision == 'bf16':
+                line['cfg2']['roofline_decorrelated'] = roofline_decorrelated(wl2, pk, 2560)
+        del wl2
+        torch.cuda.empty_cache()
+    if rank == 0:
+        if world == 1 and not args.quick:
+            line['gpu_eager_baseline'] = gpu_eager_baseline(dev)
+        if not args.no_cpu_baseline and world == 1:          # reported at N = 1 only
+            kind, _, _, beam, top_k, _ = WORKLOADS[args.workload]
+            hp, sd = model_hp(kind)
+            line['cpu_baseline'] = cpu_baseline(kind, hp, sd, beam, top_k, args.cpu_images)
+        print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 
@@ -304,6 +503,8 @@ def cpu_baseline(kind, hp, sd, beam, top_k, n_img):
     torch.set_num_threads(cores)
     imgs = synth.images(0, 0, n_img)
     labs = synth.labels(0, 0, n_img, V) if kind == 'lstm_labels' else None
+    what = ('CPU restatement of the reference (oracle/; the unmodified reference is pure Python + torch and is absent on this '
+            f'box), torch CPU fp32, {cores} threads')
     if beam == 0:
         # teacher-forced workload (config 3): the reference's forward + experiments/metrics.perplexity on a batch
         caps, lens = synth.captions(0, 0, n_img, V, width=MAX_LEN, min_len=8)
@@ -314,7 +515,7 @@ def cpu_baseline(kind, hp, sd, beam, top_k, n_img):
             run(n_img)
             dt = time.time() - t0
         return {'value': round(n_img / dt, 3), 'unit': 'sequences/s', 'cores': cores, 'kind': 'port',
-                'sample': f'{n_img} sequences of the same workload in one batch, torch CPU fp32, {cores} threads, {dt:.1f} s'}
+                'sample': f'{n_img} sequences of the same workload in one batch, {what}, {dt:.1f} s'}
     kw = dict(max_len=MAX_LEN, beam_size=beam, top_k=top_k, temperature=1.0, noise=onoise.Noise('injected', 1234),
               faithful_cost=True)
     with torch.no_grad():
@@ -323,19 +524,18 @@ def cpu_baseline(kind, hp, sd, beam, top_k, n_img):
         omodel.generate_batch(kind, sd, hp, imgs, labs, **kw)
         dt = time.time() - t0
     return {'value': round(n_img / dt, 3), 'unit': 'captions/s', 'cores': cores, 'kind': 'port',
-            'sample': f'{n_img} images of the same workload, one at a time (the reference generate() is batch-1), '
-                      f'torch CPU fp32, {cores} threads, {dt:.1f} s'}
+            'sample': f'{n_img} images of the same workload, one at a time (the reference generate() is batch-1), {what}, '
+                      f'{dt:.1f} s'}
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
-    from deephumor_b200.utils import synth_weights
-    kind, batch, beam, top_k, desc = WORKLOADS[args.workload]
-    hp = synth_weights.default_hp(kind, V)
-    sd = synth_weights.make_state_dict(kind, hp, seed=0)
-    n = min(args.cpu_images, 32)          # ~5 s of host work per step keeps K + W steps within a few minutes
+    kind, images, scaling, beam, top_k, desc = WORKLOADS[args.workload]
+    hp, sd = model_hp(kind)
+    # a step = a bounded sample of the workload: a few seconds of host work keeps W + K steps within a few minutes
+    n = min(args.cpu_images, 6 if kind.startswith('xfmr') else 24)
     vals = []
     for i in range(args.warmup + args.steps):
         cb = cpu_baseline(kind, hp, sd, beam, top_k, n)
@@ -347,24 +547,24 @@ def run_reference(args):
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': round(value, 3), 'unit': 'captions/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(n / value * 1e3, 1), 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'{args.workload}: {desc}', 'sample_images_per_step': n, 'max_len': MAX_LEN,
-                   'beam_size': beam, 'top_k': top_k},
-        'cpu_baseline': cb,
+        'scaling': scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': config_of(args.workload, world, args.batch), 'sample_images_per_step': n, 'cpu_baseline': cb,
         'e2e': {'value': round(value, 3), 'unit': 'captions/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default='cfg5', choices=sorted(WORKLOADS))
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--batch', type=int, default=0, help='override images per GPU')
-    ap.add_argument('--cpu-images', type=int, default=64, help='bounded CPU sample size (about 10 s of host work)')
+    ap.add_argument('--cpu-images', type=int, default=16, help='bounded CPU sample size (about 10 s of host work)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--quick', action='store_true',
+                    help='headline workload only: no cfg2 object, eager-library bar or decorrelated roofline')
     ap.add_argument('--profile-mode', action='store_true', help='1 warm-up + 1 step only (for ncu launch lists)')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -376,8 +376,8 @@ class VocabSelect:
         self.n_blocks = n_blocks = (V + bn - 1) // bn
         if stride is None:
             stride = int(os.environ.get('DH_VOCAB_STRIDE', '8'))
-        # a sampled pass needs enough sampled groups for the rank statistics and room below the candidate capacity
-        while stride > 1 and (n_blocks // stride) * (bn // 32) < 4 * top_k:
+        # a sampled pass needs enough sampled groups for the rank statistics (rank <= 64, a few times fewer than the groups)
+        while stride > 1 and (n_blocks // stride) * (bn // 32) < max(64, 2 * top_k):
             stride //= 2
         self.stride = max(1, stride)
         self.n_groups_full = n_blocks * (bn // 32)

@@ -4,9 +4,11 @@ import torch
 from deephumor_b200.runtime import ops
 dev='cuda'
 M,N,K=2560,36541,512
+W=(torch.randn(N,K,device=dev)*0.5).to(torch.bfloat16)
+W=(torch.randn(N,K,device=dev)*0.5).to(torch.bfloat16)
 A=torch.randn(M,K,device=dev).to(torch.bfloat16)
 if os.environ.get('CORR'):   # strongly correlated rows (what random-init LSTM states look like)
-    A=(torch.randn(1,K,device=dev)+0.2*torch.randn(M,K,device=dev)).to(torch.bfloat16); W=(torch.randn(N,K,device=dev)*0.5).to(torch.bfloat16)
+    A=(torch.randn(1,K,device=dev)+0.2*torch.randn(M,K,device=dev)).to(torch.bfloat16)
 b=torch.randn(N,device=dev)
 ldc=(N+3)//4*4
 out=torch.empty(M,ldc,device=dev)

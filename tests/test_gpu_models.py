@@ -205,6 +205,8 @@ def test_fused_perplexity_matches_materialised_logits(kind, tag, precision):
     equals perplexity(model(...)) on the same device path, and the reference fixture within the mode's tolerance."""
     fx = H.load_fixture(tag, kind)
     m, sd, imgs, labs, caps, lens = build(fx, precision)
+    nf = H.n_fwd(fx)
+    imgs, caps, lens, labs = imgs[:nf], caps[:nf], lens[:nf], (None if labs is None else labs[:nf])
     with torch.no_grad():
         args = (imgs.cuda(), caps[:, :-1].cuda(), lens.cuda()) + ((labs.cuda(),) if kind == 'lstm_labels' else ())
         logits = m(*args)
