@@ -49,6 +49,9 @@ class RTModule(nn.Module):
         return r
 
     def _device(self):
+        if self.training:
+            raise RuntimeError('deephumor_b200 modules implement the eval-mode path only (folded BatchNorm statistics, no dropout, '
+                               'no autograd): call .eval() first; training through them is not supported')
         dev = next(self.parameters()).device
         if dev.type != 'cuda':
             raise RuntimeError('deephumor_b200 models run on a CUDA (sm_100a) device only: call .cuda() first '

@@ -59,6 +59,9 @@ class _DecoderBase(RTModule):
     def __init__(self, num_tokens, hid_dim=512, n_layers=6, n_heads=8, pf_dim=2048, dropout=0., pad_index=None,
                  max_len=128):
         super().__init__()
+        if pad_index is None:
+            # the reference documents pad_index=None as "no masking"; its captioners always pass 0 (caption_models.py:211-212)
+            raise NotImplementedError('pad_index=None (no key masking) is not supported: pass the pad token id (0)')
         self.pad_index = pad_index
         self.tok_embedding = nn.Embedding(num_tokens, hid_dim)
         self.pos_embedding = nn.Embedding(max_len, hid_dim)
@@ -86,6 +89,8 @@ class _DecoderBase(RTModule):
     def _generate(self, start_emb, enc_out, caption, max_len, temperature, beam_size, top_k, eos_index, noise, seed,
                   image_base, unk_index):
         assert beam_size <= top_k, '`beam_size` should be less than `top_k`'
+        if max_len + 1 > 160:
+            raise ValueError(f'max_len={max_len}: the KV cache / slot tables hold at most 160 positions per beam (max_len <= 159)')
         dev = self._device()
         start = start_emb.to(dev, torch.float32).contiguous()
         sp = self._spatial(enc_out, dev) if self._cross else None

@@ -124,17 +124,23 @@ class EncoderRT:
 
     # ---------------------------------------------------------------- trunk
     def _buf(self, name, shape, dtype=None):
-        key = (name, tuple(shape), dtype or self.tdtype)
-        t = self._ws.get(key)
-        if t is None:
-            t = torch.empty(shape, dtype=dtype or self.tdtype, device=self.device)
-            self._ws[key] = t
-        return t
+        """Workspace `name` viewed as `shape`: ONE allocation per name, grown to the largest size requested so far, so that
+        varying batch / chunk sizes (copy ramp, tail chunks, a server's changing N) do not accumulate a set of buffers each."""
+        dtype = dtype or self.tdtype
+        numel = 1
+        for d in shape:
+            numel *= int(d)
+        t = self._ws.get(name)
+        if t is None or t.dtype != dtype or t.numel() < numel:
+            t = torch.empty(max(numel, 1), dtype=dtype, device=self.device)
+            self._ws[name] = t
+        return t[:numel].view(*shape)
 
     def _conv(self, name, x, pc, relu, residual=None):
         n, H, W, _ = x.shape
         Ho = (H + 2 * pc.pad - pc.kh) // pc.stride + 1
-        y = self._buf(name, (n, Ho, Ho, pc.cout))
+        Wo = (W + 2 * pc.pad - pc.kh) // pc.stride + 1          # square kernels; H and W may differ
+        y = self._buf(name, (n, Ho, Wo, pc.cout))
         ops.conv2d(x, pc.w, pc.bias, y, pc.stride, pc.pad, relu, residual)
         return y
 
@@ -163,16 +169,16 @@ class EncoderRT:
             ops.stem_pool(images, self.stem_wq, self.stem.bias, x)
             return self._layers(x)
         if self.tdtype != torch.float32:
-            Ho = (H + 6 - 7) // 2 + 1
-            A = self._buf('stemA', (n * Ho * Ho, 192))
+            Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+            A = self._buf('stemA', (n * Ho * Wo, 192))
             ops.im2col_stem(images, A, 7, 7, 2, 3)
-            x = self._buf('stem', (n, Ho, Ho, 64))
-            ops.gemm(A, self.stem_w, x.view(n * Ho * Ho, 64), bias=self.stem.bias, relu=True)
+            x = self._buf('stem', (n, Ho, Wo, 64))
+            ops.gemm(A, self.stem_w, x.view(n * Ho * Wo, 64), bias=self.stem.bias, relu=True)
         else:
             x = self._buf('in', (n, H, W, 4))
             ops.nchw_to_nhwc4(images, x, halo=0)
             x = self._conv('stem', x, self.stem, True)
-        y = self._buf('pool', (n, x.shape[1] // 2, x.shape[2] // 2, 64))
+        y = self._buf('pool', (n, (x.shape[1] - 1) // 2 + 1, (x.shape[2] - 1) // 2 + 1, 64))
         ops.maxpool3x3s2(x, y)
         return self._layers(y)
 
@@ -203,7 +209,7 @@ class EncoderRT:
             self._consumed = [torch.cuda.Event(), torch.cuda.Event()]
         cs = self._copy_stream
         sizes = h2d_schedule(N, self.chunk)
-        bufs = [self._buf(f'h2d{b}', (self.chunk,) + tuple(images.shape[1:]), images.dtype) for b in range(2)]
+        bufs = [self._buf(f'h2d{b}.{images.dtype}', (self.chunk,) + tuple(images.shape[1:]), images.dtype) for b in range(2)]
         cs.wait_stream(main)                           # earlier readers of the staging buffers are done
         i0 = 0
         for k, n in enumerate(sizes):
@@ -238,6 +244,9 @@ class EncoderRT:
                 consumed.record()                      # the staging buffer may be overwritten by the next-but-one copy
             hw = feat.shape[1] * feat.shape[2]
             ops.avgpool(feat.view(n, hw, 2048), pooled[i0:i0 + n])
+            if self.spatial and hw != 49:
+                raise ValueError(f'spatial features need 224 x 224 images (7 x 7 = 49 tokens for the cross-attention decoder); '
+                                 f'got a {feat.shape[1]} x {feat.shape[2]} feature map')
             if self.spatial:
                 ops.gemm(feat.view(n * hw, 2048), self.Wsp, sp[i0 * 49:(i0 + n) * 49], bias=self.bsp)
         # global heads once for the whole batch (fp32 FFMA, 64x64 tiles)

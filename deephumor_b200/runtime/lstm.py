@@ -43,7 +43,7 @@ class LSTMDecoderRT:
             self.bpk_all = torch.cat(self.bpk).contiguous()
         self.Wc, self.bc = to(sd[prefix + '.classifier.weight']), to(sd[prefix + '.classifier.bias'], torch.float32)
         self.ldv = (self.V + 3) // 4 * 4
-        self._plans = {}
+        self._plans = ops.PlanCache()
 
     def _alloc(self, rows, logits=True):
         d, dev, H, E, L = self.dtype, self.device, self.H, self.E, self.L
@@ -97,16 +97,16 @@ class LSTMDecoderRT:
         ws, beam = pl['ws'], pl['beam']
         if pl['vsel'] is not None:
             pl['vsel'].run(ws['top'][:rows], self.Wc, self.bc, B, temperature, unk_index, rpi, noise_mode, step, done,
-                           pl['ind'], pl['val'], beam.status, pl['dyn'],
+                           pl['ind'], pl['val'], beam.status, pl['dynw'].dev,
                            beam_step=None if beam_step is None else (beam,) + beam_step, lstm_next=lstm_next)
         else:
             with ops.PROFILE.range('select_beam'):
                 ops.select_tokens(ws['logits'][:rows, :self.V], self.V, B, top_k, temperature, unk_index, rpi, noise_mode,
-                                  0, 0, step, done, pl['ind'], pl['val'], beam.status, pl['dyn'])
+                                  0, 0, step, done, pl['ind'], pl['val'], beam.status, pl['dynw'].dev)
                 if beam_step is not None:
                     max_len, eos_index, lstm_sem = beam_step
                     beam.step(pl['ind'], pl['val'], step, max_len, eos_index, lstm_sem, temperature, noise_mode, 0, 0,
-                              pl['dyn'])
+                              pl['dynw'].dev)
 
     def _recur(self, ws, rows, parent):
         """A[l][:, in:] <- hs[l][parent] for every layer (recurrent operand of the next step)."""
@@ -117,7 +117,7 @@ class LSTMDecoderRT:
     def _decode(self, pl, p0, max_len, temperature, B, top_k, eos_index, unk_index, noise_mode, pad_index):
         """Launches the whole decode (prefix phase, first selection, beam loop, final pick) on static buffers of plan
         `pl`; fixed trip count and no host synchronisation, so it can be captured in a CUDA graph."""
-        ws, beam, ind, val, dyn, N = pl['ws'], pl['beam'], pl['ind'], pl['val'], pl['dyn'], pl['N']
+        ws, beam, ind, val, dyn, N = pl['ws'], pl['beam'], pl['ind'], pl['val'], pl['dynw'].dev, pl['N']
         start_emb, caption = pl['start'], pl['caption']
         R = N * B
         fused = pl['vsel'] is not None
@@ -197,26 +197,22 @@ class LSTMDecoderRT:
         key = (N, B, p0, max_len, float(temperature), top_k, eos_index, unk_index, noise_mode, pad_index, robust)
         pl = self._plans.get(key)
         if pl is None:
-            if len(self._plans) >= 2:
-                self._plans.clear()
             R = N * B
             fused = ops.FUSED_VOCAB and ops.VocabSelect.supported(self.Wc, self.V, top_k)
             pl = dict(N=N, ws=self._alloc(max(R, N), logits=not fused),
                       vsel=ops.VocabSelect(max(R, N), self.V, top_k, dev, stride=1 if robust else None) if fused else None, beam=ops.Beam(N, B, max(max_len, p0 + 1), dev),
                       ind=torch.empty(R, B, dtype=torch.int32, device=dev),
                       val=torch.empty(R, B, dtype=torch.float32, device=dev),
-                      dyn=torch.zeros(2, dtype=torch.int64, device=dev),
-                      dyn_host=torch.zeros(2, dtype=torch.int64).pin_memory(),
+                      dynw=ops.DynWords(dev),
                       start=torch.empty(N, self.E, dtype=torch.float32, device=dev),
                       caption=None if caption is None else torch.empty(N, p0, dtype=torch.int32, device=dev),
                       ids=torch.empty(N, max_len, dtype=torch.int64, device=dev),
                       lens=torch.empty(N, dtype=torch.int64, device=dev), graph=None)
-            self._plans[key] = pl
+            self._plans.put(key, pl)
         pl['start'].copy_(start_emb)
         if caption is not None:
             pl['caption'].copy_(caption.expand(N, p0))
-        pl['dyn_host'][0], pl['dyn_host'][1] = seed, image_base
-        pl['dyn'].copy_(pl['dyn_host'], non_blocking=True)
+        pl['dynw'].set(seed, image_base)
         args = (pl, p0, max_len, temperature, B, top_k, eos_index, unk_index, noise_mode, pad_index)
         if ops.PROFILE.on or not ops.USE_GRAPHS or ops.TRACE is not None:
             self._decode(*args)

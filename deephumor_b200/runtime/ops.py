@@ -72,6 +72,55 @@ DUAL_CONV = os.environ.get('DH_NO_DUAL_CONV', '') == ''       # conv3 + downsamp
 FUSED_VOCAB = os.environ.get('DH_NO_FUSED_VOCAB', '') == ''   # two-pass vocab projection, logits never stored
 
 
+class DynWords:
+    """{seed, image_base} device words read by a captured decode graph.  The host values go through a small ring of pinned
+    buffers, each guarded by an event, so a second generate() issued before the first copy has executed cannot overwrite
+    the words the first one is about to read."""
+
+    def __init__(self, device, slots=4):
+        self.dev = torch.zeros(2, dtype=torch.int64, device=device)
+        self.host = [torch.zeros(2, dtype=torch.int64).pin_memory() for _ in range(slots)]
+        self.events = [None] * slots
+        self.next = 0
+
+    def set(self, seed, image_base):
+        i = self.next
+        self.next = (i + 1) % len(self.host)
+        if self.events[i] is not None:
+            self.events[i].synchronize()
+        self.host[i][0], self.host[i][1] = seed, image_base
+        self.dev.copy_(self.host[i], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[i] = ev
+
+
+class PlanCache:
+    """Small LRU of decode plans (static buffers + captured CUDA graph per configuration): alternating between a few
+    shapes must not re-capture a graph on every call, and a long-running server must not keep every shape it ever saw."""
+
+    def __init__(self, capacity=4):
+        from collections import OrderedDict
+        self.capacity, self.items = capacity, OrderedDict()
+
+    def get(self, key):
+        pl = self.items.get(key)
+        if pl is not None:
+            self.items.move_to_end(key)
+        return pl
+
+    def put(self, key, plan):
+        self.items[key] = plan
+        while len(self.items) > self.capacity:
+            self.items.popitem(last=False)
+
+    def clear(self):
+        self.items.clear()
+
+    def __len__(self):
+        return len(self.items)
+
+
 def code(t):
     if t.dtype == torch.float32:
         return F32
@@ -108,6 +157,7 @@ def conv2d(x, w, bias, y, stride, pad, relu, residual=None, tile_n=0):
     n, H, W, Cin = x.shape
     Cout, kh, kw, _ = w.shape
     assert x.is_contiguous() and w.is_contiguous() and y.is_contiguous() and w.shape[3] == Cin
+    assert tuple(y.shape) == (n, (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1, Cout), 'conv2d output shape'
     if x.dtype == torch.float32:
         LIB.call('dh_conv2d_f32', ptr(x), ptr(w), ptr(bias), ptr(residual), ptr(y), n, H, W, Cin, Cout, kh, kw,
                  stride, pad, int(relu), stream())
@@ -140,6 +190,7 @@ def im2col_stem(images, A, kh, kw, stride, pad):
     """images [n,3,H,W] fp32 NCHW -> A [n*Ho*Wo, Kp] bf16, k = (r*kw+s)*3 + c, zero padded."""
     n, c, H, W = images.shape
     assert c == 3 and images.is_contiguous() and images.dtype == torch.float32 and A.is_contiguous()
+    assert A.shape[0] == n * ((H + 2 * pad - kh) // stride + 1) * ((W + 2 * pad - kw) // stride + 1), 'im2col rows'
     LIB.call('dh_im2col_stem', ptr(images), ptr(A), n, H, W, kh, kw, stride, pad, A.shape[1], code(A), stream())
 
 
@@ -170,6 +221,7 @@ def stem_pool_u8(images, mean, std, w_packed, bias, out):
 
 def maxpool3x3s2(x, y):
     n, H, W, C = x.shape
+    assert tuple(y.shape) == (n, (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1, C) and x.is_contiguous() and y.is_contiguous()
     LIB.call('dh_maxpool3x3s2', ptr(x), ptr(y), n, H, W, C, code(x), stream())
 
 

@@ -43,7 +43,7 @@ class XfmrDecoderRT:
         self.pf = self.layers[0]['pf.fc_1.w'].shape[0]
         self.Wc, self.bc = to(sd[prefix + '.classifier.weight']), to(sd[prefix + '.classifier.bias'], f32)
         self.ldv = (self.V + 3) // 4 * 4
-        self._plans = {}
+        self._plans = ops.PlanCache()
 
     # ------------------------------------------------------------------ shared layer pieces
     def _cross_kv(self, spatial, n_img):
@@ -82,7 +82,7 @@ class XfmrDecoderRT:
         R, S = N * B, max_len + 1
         start_emb, spatial, caption = pl['start'], pl['spatial'], pl['caption']
         x, qb, attn, tmp, h1, logits = pl['x'], pl['qb'], pl['attn'], pl['tmp'], pl['h1'], pl['logits']
-        Kc, Vc, beam, ind, val, dyn = pl['Kc'], pl['Vc'], pl['beam'], pl['ind'], pl['val'], pl['dyn']
+        Kc, Vc, beam, ind, val, dyn = pl['Kc'], pl['Vc'], pl['beam'], pl['ind'], pl['val'], pl['dynw'].dev
         beam.status.zero_()
         with ops.PROFILE.range('xfmr_cross_kv', 4.0 * N * 49 * D * D * self.L if self.cross else 0.0):
             xkv, emask = self._cross_kv(spatial, N) if self.cross else (None, None)
@@ -175,7 +175,6 @@ class XfmrDecoderRT:
         key = (N, B, p0, max_len, float(temperature), top_k, eos_index, unk_index, noise_mode, robust)
         pl = self._plans.get(key)
         if pl is None:
-            self._plans.clear()
             rows_alloc = max(R, N)
             mk = lambda *shape, dtype=dt: torch.empty(*shape, dtype=dtype, device=dev)
             fused = ops.FUSED_VOCAB and ops.VocabSelect.supported(self.Wc, self.V, top_k)
@@ -185,19 +184,17 @@ class XfmrDecoderRT:
                       Vc=[torch.zeros(R, S, D, dtype=dt, device=dev) for _ in range(self.L)],
                       beam=ops.Beam(N, B, max_len, dev, kv_slots=S),
                       ind=mk(R, B, dtype=torch.int32), val=mk(R, B, dtype=torch.float32),
-                      dyn=torch.zeros(2, dtype=torch.int64, device=dev),
-                      dyn_host=torch.zeros(2, dtype=torch.int64).pin_memory(),
+                      dynw=ops.DynWords(dev),
                       start=mk(N, D, dtype=torch.float32), spatial=mk(N * 49, D) if self.cross else None,
                       caption=None if caption is None else mk(N, p0, dtype=torch.int32),
                       ids=mk(N, max_len, dtype=torch.int64), lens=mk(N, dtype=torch.int64), graph=None)
-            self._plans[key] = pl
+            self._plans.put(key, pl)
         pl['start'].copy_(start_emb)
         if self.cross:
             pl['spatial'].copy_(spatial)
         if caption is not None:
             pl['caption'].copy_(caption.expand(N, p0))
-        pl['dyn_host'][0], pl['dyn_host'][1] = seed, image_base
-        pl['dyn'].copy_(pl['dyn_host'], non_blocking=True)
+        pl['dynw'].set(seed, image_base)
         args = (pl, p0, max_len, temperature, B, top_k, eos_index, unk_index, noise_mode)
         if ops.PROFILE.on or not ops.USE_GRAPHS or ops.TRACE is not None:
             self._decode(*args)

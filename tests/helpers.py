@@ -14,8 +14,10 @@ NEAR_TIE = 3e-5      # decisions whose oracle margin is below this are reported,
 # oracle margin, in logit units, is within the path's numeric error.  The north-star budget is 1e-2 relative on logits; the
 # canonical classifiers produce logits with RMS ~2, i.e. up to ~2e-2 absolute per logit, and a margin is a difference of two
 # of them, accumulated over the steps of a cumulative beam score.  Decisions with an oracle margin above this bound must agree.
-BOUND_BF16 = 0.10
-BOUND_FP32 = 1e-4
+# The bound is derived from the measured error of the mode: BOUND_FACTOR x the largest absolute error of the mode's
+# teacher-forced logits against the reference fixture (a margin is a difference of two logits / cumulative scores).
+BOUND_FACTOR = 4.0
+BOUND_FP32 = 2e-3
 
 
 def rel_err(a, b):
@@ -69,28 +71,27 @@ def oracle_traces(fx, g, sd, imgs, labs, caps, n=None):
     return ids, lens, traces
 
 
-def compare_beam_states(trace_dev, traces, beam, bound, val_tol):
-    """Step-by-step parity of the device beam state with the oracle's: for every image, every step up to (not including)
-    the first one whose oracle margin is below `bound` must show identical beam sequences / ended flags and scores within
-    val_tol.  Returns (steps checked, steps available, images whose whole decode was checked)."""
-    checked = total = whole = 0
+def compare_beam_states(trace_dev, traces, beam, val_tol):
+    """Step-by-step comparison of the device beam state with the oracle's.  For every image the states (beam sequences,
+    ended flags, cumulative scores within val_tol) are compared after every decode step until the first step at which they
+    differ.  Returns one record per image: (first differing step or None, oracle margin of that step's decisions in logit
+    units, steps matched, steps available).  Past a divergence the two decodes follow different beams, so nothing later is
+    comparable; a divergence is legitimate only at a step whose oracle margin is within the mode's numeric error."""
     by_step = {st: (seq.cpu(), val.cpu(), ended.cpu()) for st, seq, val, ended, _ in trace_dev}
+    out = []
     for n, tr in enumerate(traces):
         steps = sorted(tr.states)
-        total += len(steps)
-        ok_all = True
+        first, matched = None, 0
         for st in steps:
-            if tr.step_abs.get(st, float('inf')) < bound:
-                ok_all = False
-                break
             oseq, oval, oend = tr.states[st]
             seq, val, ended = by_step[st]
             cols = oseq.shape[1]
-            mine = seq[n * beam:(n + 1) * beam, :cols].long()
-            assert torch.equal(mine, oseq), f'image {n} step {st}: beam sequences differ\n{mine}\n{oseq}'
-            assert torch.equal(ended[n * beam:(n + 1) * beam].bool(), oend), f'image {n} step {st}: ended flags differ'
-            assert torch.allclose(val[n * beam:(n + 1) * beam], oval, atol=val_tol, rtol=0), \
-                f'image {n} step {st}: beam scores differ {val[n * beam:(n + 1) * beam]} vs {oval}'
-            checked += 1
-        whole += ok_all
-    return checked, total, whole
+            same = (torch.equal(seq[n * beam:(n + 1) * beam, :cols].long(), oseq)
+                    and torch.equal(ended[n * beam:(n + 1) * beam].bool(), oend)
+                    and torch.allclose(val[n * beam:(n + 1) * beam], oval, atol=val_tol, rtol=0))
+            if not same:
+                first = st
+                break
+            matched += 1
+        out.append((first, tr.step_abs.get(first, float('inf')) if first is not None else None, matched, len(steps)))
+    return out

@@ -59,29 +59,51 @@ def traced_generate(m, kind, imgs, labs, **kw):
         ops.TRACE = None
 
 
+def logit_error(m, fx, kind, imgs, labs, caps, lens):
+    """Largest absolute error of the mode's teacher-forced logits against the reference fixture (first n_fwd images)."""
+    nf = H.n_fwd(fx)
+    with torch.no_grad():
+        args = (imgs[:nf].cuda(), caps[:nf, :-1].cuda(), lens[:nf].cuda()) + ((labs[:nf].cuda(),) if kind == 'lstm_labels' else ())
+        logits = m(*args)
+    ref = fx['logits']
+    return float((logits[..., :ref.shape[-1]].float().cpu() - ref).abs().max())
+
+
 @pytest.mark.parametrize('precision', ['bf16', 'fp32'])
 @pytest.mark.parametrize('variant', [1, 2])        # canon fixture: injected noise, beam 5 / top-k 50 and beam 1 / top-k 50
 @pytest.mark.parametrize('kind', H.KINDS)
 def test_beam_states_follow_the_oracle_step_by_step(kind, variant, precision):
+    """The device decode (fused vocab selection + beam step launch, in-launch operand gathers, stacked LSTM / fused Q|K|V)
+    must reproduce the oracle's beam state after EVERY step; the first step at which an image's state differs must be a
+    near-tie of the oracle (margin within BOUND_FACTOR x the mode's measured logit error), and whole captions must equal
+    the unmodified reference's for every image that never hits such a near-tie."""
     n = 32 if kind.startswith('lstm') else 16                  # the cache-less oracle transformer costs ~1 s per caption
     fx, sd, imgs, labs, oids, olens, traces = oracle_run(kind, variant, n)
     g = fx['gen'][variant]
     assert torch.equal(oids, g['ids'][:n]) and torch.equal(olens, g['lengths'][:n])       # oracle == unmodified reference
     m = build(kind, fx['hp'], sd, precision)
+    caps, lens = H.fixture_inputs(fx)[3:]
+    err = logit_error(m, fx, kind, imgs, labs, caps, lens)
+    bound = max(H.BOUND_FACTOR * err, 1e-4) if precision == 'bf16' else H.BOUND_FP32
     kw = dict(max_len=fx['max_len'], temperature=g['temperature'], beam_size=g['beam_size'], top_k=g['top_k'],
               noise=g['mode'], seed=g['noise_seed'])
     (ids, ln), trace_dev = traced_generate(m, kind, imgs[:n], None if labs is None else labs[:n], **kw)
-    bound, vtol = (H.BOUND_BF16, 0.25) if precision == 'bf16' else (H.BOUND_FP32, 2e-3)
-    checked, total, whole = H.compare_beam_states(trace_dev, traces, g['beam_size'], bound, vtol)
-    print(f'{kind} {precision} B={g["beam_size"]}: {checked}/{total} steps checked against the oracle, {whole}/{n} images end to end')
-    # the comparison must not be vacuous
-    assert checked >= (0.9 if precision == 'fp32' else 0.25) * total
-    # images whose every decision clears the bound must reproduce the reference's caption exactly
-    full = [i for i, t in enumerate(traces) if t.abs_gap >= bound]
-    for i in full:
+    rec = H.compare_beam_states(trace_dev, traces, g['beam_size'], val_tol=4 * bound)
+    matched, total = sum(r[2] for r in rec), sum(r[3] for r in rec)
+    whole = [i for i, r in enumerate(rec) if r[0] is None]
+    div = [(i, r[0], r[1]) for i, r in enumerate(rec) if r[0] is not None]
+    print(f'{kind} {precision} B={g["beam_size"]}: max |dlogit| {err:.2e} -> bound {bound:.2e}; {matched}/{total} steps equal '
+          f'the oracle, {len(whole)}/{n} captions end to end; divergences (image, step, margin): '
+          + ', '.join(f'({i},{st},{mg:.1e})' for i, st, mg in div))
+    unexplained = [(i, st, mg) for i, st, mg in div if mg > bound]
+    assert not unexplained, f'beam state differs from the oracle at decisions with margin > {bound:.2e}: {unexplained}'
+    for i in whole:                                            # no near-tie on the way: the reference's caption, exactly
         assert ids[i].cpu().tolist() == g['ids'][i].tolist() and int(ln[i]) == int(g['lengths'][i]), f'image {i}'
+    # the comparison must not be vacuous
     if precision == 'fp32':
-        assert len(full) >= n // 2
+        assert len(whole) >= n - max(2, n // 8) and matched >= 0.9 * total
+    else:
+        assert matched >= 0.15 * total
 
 
 @pytest.mark.parametrize('precision', ['bf16', 'fp32'])

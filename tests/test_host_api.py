@@ -85,6 +85,60 @@ def test_vocab_tokenizers_and_text_helpers():
     assert split_caption('hello , world <sep> bye <emp>', 3) == ['hello, world', 'bye', '']
 
 
+def test_batched_text_helpers_equal_the_per_item_reference_forms():
+    """batched ids -> text / text -> ids over (ids [N, max_len], lengths [N]) == the reference's
+    one-string-at-a-time helpers (experiments/inference.py:11-58) item by item; when /root/reference is present the
+    reference's own functions are the comparison."""
+    from deephumor_b200.experiments import seqs_to_texts, split_captions, texts_to_seqs
+    wt = WordPunctTokenizer()
+    words = [f'w{i}' for i in range(200)] + ['hello', ',', 'world', '!', '<sep>']
+    v = Vocab(words)
+    g = torch.Generator().manual_seed(0)
+    N, L = 300, 32
+    ids = torch.randint(0, len(v), (N, L), generator=g)
+    ids[::3, 7] = 3                                   # <eos> in the middle
+    ids[::5, 0] = 3                                   # <eos> first: empty text
+    lengths = torch.randint(1, L + 1, (N,), generator=g)
+    texts = seqs_to_texts(ids, lengths, v)
+    ref_fn = seq_to_text
+    try:
+        from oracle import refshim
+        if refshim.available():
+            refshim.import_reference()
+            from deephumor.experiments.inference import seq_to_text as ref_fn      # the unmodified reference
+    except Exception:
+        pass
+    for n in range(N):
+        assert texts[n] == ref_fn(ids[n, :int(lengths[n])], v)
+    strings = ['Hello , world !', 'w1 w2 <sep> w3 unknownword', '', 'w5']
+    seqs, lens = texts_to_seqs(strings, v, wt)
+    for n, t in enumerate(strings):
+        one = text_to_seq(t, v, wt) if t else torch.zeros(1, 0, dtype=torch.int64)
+        assert seqs[n, :int(lens[n])].tolist() == one[0].tolist() and int(lens[n]) == one.shape[1]
+        assert bool((seqs[n, int(lens[n]):] == 0).all())
+    assert split_captions(['a , b <sep> c', 'd'], 2) == [split_caption('a , b <sep> c', 2), split_caption('d', 2)]
+
+
+def test_plan_cache_is_an_lru():
+    from deephumor_b200.runtime.ops import PlanCache
+    c = PlanCache(capacity=2)
+    c.put('a', 1); c.put('b', 2)
+    assert c.get('a') == 1                               # 'a' becomes the most recent
+    c.put('c', 3)                                        # evicts 'b', not 'a'
+    assert c.get('b') is None and c.get('a') == 1 and c.get('c') == 3 and len(c) == 2
+
+
+def test_api_guards_raise_instead_of_silently_differing():
+    """training mode and pad_index=None are not implemented by the runtime -- they must raise, not diverge."""
+    from deephumor_b200.models import TransformerDecoder
+    with pytest.raises(NotImplementedError):
+        TransformerDecoder(num_tokens=50, hid_dim=64, n_layers=1, n_heads=4, pf_dim=64, pad_index=None)
+    m = TransformerDecoder(num_tokens=50, hid_dim=64, n_layers=1, n_heads=4, pf_dim=64, pad_index=0)
+    m.train()
+    with pytest.raises(RuntimeError):
+        m._device()
+
+
 def test_vocab_save_load(tmp_path):
     v = Vocab(['b', 'a'])
     p = str(tmp_path / 'v.txt')
