@@ -297,7 +297,7 @@ def stage_report(prof, pk):
 
 
 def roofline_of(res, pk, pk_src, precision, traffic):
-    """Roofline of the dominant single-shape kernel: the vocab-projection contraction with the candidate-compaction
+    """Roofline of the dominant single-shape kernel: the vocab-projection contraction with the sparse-materialisation
     epilogue (one launch = one full [rows, 36541, 512] product); achieved = algorithmic FLOPs / CUDA-event time."""
     prof = res['prof']
     if not prof or not prof.get('vocab_gemm'):
@@ -305,8 +305,8 @@ def roofline_of(res, pk, pk_src, precision, traffic):
     sustained = pk.get('bf16_tflops_sustained', pk.get('bf16_tflops'))
     n, tot_ms, flops, _ = prof['vocab_gemm']
     ach = flops / (tot_ms / 1e3) / 1e12
-    return {'kernel': 'gemm_tc_kernel<256,pair,2>: vocab projection [rows,512]x[512,36541] with the candidate-compaction '
-                      'epilogue (logits never stored)' if precision == 'bf16' else 'igemm_f32_kernel (fp32 check mode FFMA)',
+    return {'kernel': 'gemm_tc_kernel<256,pair,2>: vocab projection [rows,512]x[512,36541] with the sparse-materialisation '
+                      'epilogue (only the 32-column groups that hold a candidate are stored)' if precision == 'bf16' else 'igemm_f32_kernel (fp32 check mode FFMA)',
             'bound': 'tensor', 'achieved': round(ach, 2), 'peak': sustained, 'unit': 'TFLOP/s',
             'frac': round(ach / sustained, 4), 'traffic': traffic,
             'peak_source': f'{pk_src}, bf16 sustained (kernel timed inside a seconds-long region)', 'launches': n,
@@ -337,7 +337,8 @@ def roofline_decorrelated(wl, pk, rows):
         flush.zero_()                                                 # L2 flush between timed launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        LIB.call('dh_vocab_candidates', *args, ptr(vs.thresh), ptr(vs.count), ptr(vs.idx), ptr(vs.val), vs.cap, stream())
+        LIB.call('dh_vocab_candidates', *args, ptr(vs.thresh), ptr(vs.count), ptr(vs.sp_logits), vs.sp_ld, ptr(vs.hitmap),
+                 vs.hit_ld, stream())
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
@@ -348,7 +349,7 @@ def roofline_decorrelated(wl, pk, rows):
     return {'kernel': 'same kernel, per-row random activations (unrelated rows), timed alone with an L2 flush between launches',
             'rows': rows, 'avg_ms': round(ms, 4), 'achieved': round(ach, 2), 'peak': peak, 'unit': 'TFLOP/s',
             'frac': round(ach / peak, 4), 'peak_source': 'bf16 burst (kernel timed alone)',
-            'candidates_per_row': round(float(vs.count.float().mean()), 1)}
+            'stored_groups_per_row': round(float(vs.count.float().mean()), 1)}
 
 
 def gpu_eager_baseline(dev):

@@ -25,6 +25,12 @@ class BeamState(ctypes.Structure):
                 ('S_alloc', ctypes.c_int)]
 
 
+class VocabSparse(ctypes.Structure):
+    """struct dh_vocab_sparse (include/deephumor_b200.h)."""
+    _fields_ = [('thresh', ctypes.c_void_p), ('hitmap', ctypes.c_void_p), ('hit_ld', ctypes.c_longlong),
+                ('logits', ctypes.c_void_p), ('ld', ctypes.c_longlong), ('n_cols', ctypes.c_int)]
+
+
 class LstmOperands(ctypes.Structure):
     """struct dh_lstm_operands (include/deephumor_b200.h)."""
     _fields_ = [('table', ctypes.c_void_p), ('ldt', ctypes.c_longlong), ('n_tok_rows', ctypes.c_longlong),

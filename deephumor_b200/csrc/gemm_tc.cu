@@ -49,7 +49,11 @@ struct TcParams {
   float* gsum; const long long* targets; float* tlogit;     // mode 4: [M, ld_gmax], [M] (int64), [M]
   float* gmax; long long ld_gmax;         // [M, ld_gmax] group maxima (mode 1)
   const float* thresh;                    // [M] lower bound of the row's top_k-th largest logit (mode 2)
-  int* cand_count; int* cand_idx; float* cand_val; int cand_cap;   // [M], [M, cap], [M, cap]
+  // mode 2 (sparse materialisation): every 32-column group whose maximum reaches thresh[row] is stored as is (128 B) into
+  // the dense-pitch buffer sp_logits [M, sp_ld]; hitmap [M, hit_ld] gets one byte per (row, N tile, column half) with one
+  // bit per stored group -- written exactly once, no atomics, no data-dependent control flow beyond the predicated stores;
+  // cand_count[row] accumulates the number of stored groups (fire-and-forget reduction).
+  float* sp_logits; long long sp_ld; unsigned char* hitmap; long long hit_ld; int* cand_count;
   // LSTM cell epilogue (epi_mode 3, dh_lstm_layer_tc): the N axis is packed per 64 hidden units as [i | f | g | o]
   const float* c_prev; const int* parent; float* c_out;            // [*, H] fp32, parent[M] (nullable), [M, H] fp32
   void* h0; long long ldh0; void* h1; long long ldh1; int H;       // bf16 h to up to two destinations
@@ -624,24 +628,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // ---- selection epilogues: every thread owns one accumulator row; nothing of the [M,N] product is stored.
       const int row_l = ew * 32 + lane;
       int it = 0;
-      // Candidates of this thread's slice are parked in shared memory (the store staging area is idle in this mode) and
-      // appended with ONE atomic per row and tile.  The atomic's round trip to L2 is taken OFF the per-tile critical path:
-      // it is issued when a tile's scan ends and its result (the list slot) is consumed one tile later, after the next
-      // accumulator has been drained -- with unrelated rows nearly every warp appends something for every tile, and waiting
-      // for the slot right away doubled the kernel's time (ncu: 155 us, tensor pipe 34 % active).  Two parking buffers.
-      constexpr int kPend = 8;
-      uint2* pend_base = reinterpret_cast<uint2*>(staging) + etid * kPend;
-      int def_n = 0, def_slot = 0;
-      long long def_row = 0;
-      const uint2* def_buf = pend_base;
-      auto write_out = [&](long long row, int slot, int n, const uint2* buf) {
-        for (int i = 0; i < n; ++i) {
-          if (slot + i < p.cand_cap) {
-            p.cand_idx[row * p.cand_cap + slot + i] = (int)buf[i].x;
-            p.cand_val[row * p.cand_cap + slot + i] = __uint_as_float(buf[i].y);
-          }
-        }
-      };
       for (int tile = tile0; tile < tiles; tile += tstride, ++it) {
         const int m0 = tile_m0(tile), n0 = ((tile % p.n_blocks) * p.n_stride + p.n_offset) * BN;
         const int as = it & 1;
@@ -659,13 +645,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("bar.sync 1, 256;" ::: "memory");
         // candidates are finite logits >= thresh[row]; clamping to -FLT_MAX folds the "> -inf" test into one compare
         const float t0 = emit ? fmaxf(thr, -3.402823466e+38f) : INFINITY;
-        uint2* pend = pend_base + (it & 1) * (256 * kPend);
-        int npend = 0;
-        auto flush = [&]() {                                      // parking buffer full (rare): append synchronously
-          const int slot = atomicAdd(p.cand_count + row, npend);
-          write_out(row, slot, npend, pend);
-          npend = 0;
-        };
+        unsigned int bits = 0u;                                   // groups of this (row, tile, half) that hold a candidate
 #pragma unroll 1
         for (int c = eh * (BN / 64); c < (eh + 1) * (BN / 64); ++c) {
           const int col0 = n0 + c * 32;
@@ -719,32 +699,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               }
             }
           } else if (mx >= t0) {
-            // a few hits per row in all of V: only the quarters that hold one are scanned
+            // the group holds at least one logit >= thresh[row]: store its 32 logits (one full 128 B line of the row) and
+            // leave the element-wise work to the selection kernel -- the epilogue's instruction count no longer depends on
+            // where the candidates sit (per-lane divergent element scans made unrelated rows 2x slower than collinear ones)
+            bits |= 1u << (c - eh * (BN / 64));
+            float4* dst = reinterpret_cast<float4*>(p.sp_logits + row * p.sp_ld + col0);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (m8[q] >= t0) {
-#pragma unroll
-                for (int j = 8 * q; j < 8 * q + 8; ++j) {
-                  if (x[j] >= t0) {
-                    if (npend == kPend) flush();
-                    pend[npend++] = make_uint2((uint32_t)(col0 + j), __float_as_uint(x[j]));
-                  }
-                }
-              }
-            }
+            for (int g = 0; g < 8; ++g) dst[g] = make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]);
           }
         }
         // the accumulator is drained: hand the TMEM buffer back to the MMA warp BEFORE any list traffic
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar(as), 0)); else mbar_arrive(tempty_bar(as)); }
-        if (EPI == 2) {
-          if (def_n) write_out(def_row, def_slot, def_n, def_buf);         // the previous tile's slot has long arrived
-          def_n = npend; def_row = row; def_buf = pend;
-          if (npend) def_slot = atomicAdd(p.cand_count + row, npend);      // consumed one tile later
+        if (EPI == 2 && emit) {
+          p.hitmap[row * p.hit_ld + (long long)(((tile % p.n_blocks) * p.n_stride + p.n_offset) * 2 + eh)] = (unsigned char)bits;
+          if (bits) atomicAdd(p.cand_count + row, __popc(bits));           // result unused: compiles to a fire-and-forget RED
         }
       }
-      if (EPI == 2 && def_n) write_out(def_row, def_slot, def_n, def_buf);
     } else if (eh != 0) {
       // second epilogue group: idle for plain stores
     } else if (p.tma_store) {
@@ -1205,8 +1177,8 @@ struct VocabFix {          // optional behaviour of a vocab pass (see TcParams::
 
 static int vocab_pass(int mode, int tile_stride, const void* A, long long lda, const void* W, long long ldw, int ab_dtype,
                       const float* bias, int M, int N, int K, float* gmax, long long ld_gmax, const float* thresh,
-                      int* cand_count, int* cand_idx, float* cand_val, int cand_cap, cudaStream_t stream,
-                      const VocabFix& fx = VocabFix()) {
+                      int* cand_count, float* sp_logits, long long sp_ld, unsigned char* hitmap, long long hit_ld,
+                      cudaStream_t stream, const VocabFix& fx = VocabFix()) {
   DH_ARG(A && W && M >= 0 && N > 0 && K > 0);
   DH_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0);
   DH_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0);
@@ -1225,7 +1197,8 @@ static int vocab_pass(int mode, int tile_stride, const void* A, long long lda, c
   p.cond_mode = fx.cond_mode; p.cond_min = fx.cond_min; p.cond_max = fx.cond_max;
   p.cond_count = fx.cond_count; p.cond_flag = fx.cond_flag; p.redo = fx.redo;
   p.gmax = gmax; p.ld_gmax = ld_gmax;
-  p.thresh = thresh; p.cand_count = cand_count; p.cand_idx = cand_idx; p.cand_val = cand_val; p.cand_cap = cand_cap;
+  p.thresh = thresh; p.cand_count = cand_count;
+  p.sp_logits = sp_logits; p.sp_ld = sp_ld; p.hitmap = hitmap; p.hit_ld = hit_ld;
   CUtensorMap ma;
   rc = make_map_2d(&ma, A, M, K, lda, BM, ab_dtype);
   if (rc) return rc;
@@ -1371,16 +1344,22 @@ extern "C" int dh_vocab_groupmax(const void* A, long long lda, const void* W, lo
   DH_ARG(ld_gmax >= vocab_groups(N, tile_stride, tile_offset));
   VocabFix fx;
   fx.tile_offset = tile_offset;
-  return vocab_pass(1, tile_stride, A, lda, W, ldw, ab_dtype, bias, M, N, K, gmax, ld_gmax, nullptr, nullptr, nullptr, nullptr,
+  return vocab_pass(1, tile_stride, A, lda, W, ldw, ab_dtype, bias, M, N, K, gmax, ld_gmax, nullptr, nullptr, nullptr, 0, nullptr,
                     0, stream, fx);
 }
 
+static int sparse_args_ok(int N, const float* sp_logits, long long sp_ld, const unsigned char* hitmap, long long hit_ld) {
+  const int bn = N <= 64 ? 64 : N <= 128 ? 128 : 256;
+  const int nb = dh_cdiv(N, bn);
+  return sp_logits && hitmap && sp_ld >= (long long)nb * bn && sp_ld % 4 == 0 && ((uintptr_t)sp_logits % 16) == 0 && hit_ld >= 2 * nb;
+}
+
 extern "C" int dh_vocab_candidates(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias,
-                                   int M, int N, int K, const float* thresh, int* cand_count, int* cand_idx, float* cand_val,
-                                   int cand_cap, cudaStream_t stream) {
-  DH_ARG(thresh && cand_count && cand_idx && cand_val && cand_cap > 0);
-  return vocab_pass(2, 1, A, lda, W, ldw, ab_dtype, bias, M, N, K, nullptr, 0, thresh, cand_count, cand_idx, cand_val, cand_cap,
-                    stream);
+                                   int M, int N, int K, const float* thresh, int* cand_count, float* sp_logits, long long sp_ld,
+                                   unsigned char* hitmap, long long hit_ld, cudaStream_t stream) {
+  DH_ARG(thresh && cand_count && sparse_args_ok(N, sp_logits, sp_ld, hitmap, hit_ld));
+  return vocab_pass(2, 1, A, lda, W, ldw, ab_dtype, bias, M, N, K, nullptr, 0, thresh, cand_count, sp_logits, sp_ld, hitmap,
+                    hit_ld, stream);
 }
 
 // Fix-up launches behind a SAMPLED pass 1 (see include/deephumor_b200.h): both contractions return at once -- before any
@@ -1392,19 +1371,19 @@ extern "C" int dh_vocab_groupmax_fix(const void* A, long long lda, const void* W
   DH_ARG(ld_gmax >= vocab_groups(N, 1, 0));
   VocabFix fx;
   fx.cond_mode = 1; fx.cond_min = count_min; fx.cond_max = count_max; fx.cond_count = cand_count; fx.cond_flag = any_flag;
-  return vocab_pass(1, 1, A, lda, W, ldw, ab_dtype, bias, M, N, K, gmax, ld_gmax, nullptr, nullptr, nullptr, nullptr, 0, stream,
-                    fx);
+  return vocab_pass(1, 1, A, lda, W, ldw, ab_dtype, bias, M, N, K, gmax, ld_gmax, nullptr, nullptr, nullptr, 0, nullptr, 0,
+                    stream, fx);
 }
 
 extern "C" int dh_vocab_candidates_fix(const void* A, long long lda, const void* W, long long ldw, int ab_dtype,
                                        const float* bias, int M, int N, int K, const float* thresh, int* cand_count,
-                                       int* cand_idx, float* cand_val, int cand_cap, const unsigned char* redo, int* any_flag,
-                                       cudaStream_t stream) {
-  DH_ARG(thresh && cand_count && cand_idx && cand_val && cand_cap > 0 && redo && any_flag);
+                                       float* sp_logits, long long sp_ld, unsigned char* hitmap, long long hit_ld,
+                                       const unsigned char* redo, int* any_flag, cudaStream_t stream) {
+  DH_ARG(thresh && cand_count && sparse_args_ok(N, sp_logits, sp_ld, hitmap, hit_ld) && redo && any_flag);
   VocabFix fx;
   fx.cond_mode = 2; fx.cond_flag = any_flag; fx.redo = redo;
-  return vocab_pass(2, 1, A, lda, W, ldw, ab_dtype, bias, M, N, K, nullptr, 0, thresh, cand_count, cand_idx, cand_val, cand_cap,
-                    stream, fx);
+  return vocab_pass(2, 1, A, lda, W, ldw, ab_dtype, bias, M, N, K, nullptr, 0, thresh, cand_count, sp_logits, sp_ld, hitmap,
+                    hit_ld, stream, fx);
 }
 
 // im2col-mode tensor map over an NHWC activation tensor: box = {64 channels, 128 output pixels}

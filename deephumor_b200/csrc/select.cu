@@ -379,64 +379,124 @@ __global__ void __launch_bounds__(kThrWarps * 32) vocab_threshold_kernel(const f
   if (lane == 0) { thresh[r] = t0; cand_count[r] = 0; }
 }
 
-// Warp-level selection from a row's candidate list (written by dh_vocab_candidates in atomic-slot order): exact top_k-th
-// largest (ties kept, Q3), survivors compacted and sorted by column so every floating-point reduction is run-to-run
-// deterministic, softmax(l/T), Exp(1)-race draw of B ids, log_softmax scores over the picks (models/beam.py:32-53,79).
-constexpr int kWarpCap = 256;
-struct WarpSel {
-  int* a_idx; float* a_val;     // [kWarpCap] staged raw candidates, later the survivors sorted by column
-  int* t_idx; float* t_val;     // [kWarpCap] unsorted survivors
-  float* score;                 // [kWarpCap]
-  int* pick_idx; float* pick_logit;   // [kMaxBeam]
+// Warp-level selection from a row's SPARSELY MATERIALISED logits (written by dh_vocab_candidates): the hit map names the
+// 32-column groups that hold at least one logit >= thresh[row]; their 128-byte lines are gathered (one lane per group, eight
+// 16-byte loads in flight per lane), filtered against the threshold, and the exact top_k-th largest value (ties kept, Q3) is
+// taken from that candidate list.  Survivors are sorted by column so every floating-point reduction is run-to-run
+// deterministic; then softmax(l/T), the Exp(1)-race draw of B ids and the log_softmax scores over the picks
+// (models/beam.py:32-53,79).
+constexpr int kCandCap = 512;    // candidates (logits >= thresh) a warp can rank
+constexpr int kSurvMax = 160;    // survivors (logits >= the exact top_k-th largest): top_k <= 64 plus ties
+struct VocabSparse {
+  const float* thresh;           // [rows]
+  const unsigned char* hitmap;   // [rows, hit_ld]: one byte per (N tile, column half), one bit per stored 32-column group
+  long long hit_ld;
+  const float* logits;           // [rows, ld]: only the groups named by the hit map hold data
+  long long ld;
+  int n_bytes, groups_per_byte;
 };
-constexpr int kWarpSelBytes = 5 * kWarpCap * 4 + 2 * kMaxBeam * 4;
+struct WarpSel {
+  int* c_idx; float* c_val;     // [kCandCap] candidates, later the survivors sorted by column
+  int* t_idx; float* t_val;     // [kSurvMax] unsorted survivors   } the group list of the gather phase aliases these
+  float* score;                 // [kSurvMax]                       } three arrays (3 * kSurvMax ints)
+  int* pick_idx; float* pick_logit;   // [kMaxBeam]
+  int* counter;                 // candidate count of the gather phase
+};
+constexpr int kWarpSelBytes = 2 * kCandCap * 4 + 3 * kSurvMax * 4 + 2 * kMaxBeam * 4 + 16;
 
-__device__ void warp_select(const SelParams& p, int r, int img, int nc_total, const int* __restrict__ gi,
-                            const float* __restrict__ gv, int cap, WarpSel w) {
-  const int lane = threadIdx.x & 31;
-  int nc = nc_total;
-  if (nc > cap) {
-    if (lane == 0) atomicOr(p.status, DH_STATUS_TOO_MANY_TIES);
-    nc = cap;
+template <int KPL>   // keys per lane
+__device__ __forceinline__ float warp_kth_largest(const float* vv, int nc, int k, int lane) {
+  // bit-wise radix select on the order-preserving keys held in registers: 32 rounds of (KPL compares + one warp-wide add)
+  unsigned int key[KPL];
+#pragma unroll
+  for (int u = 0; u < KPL; ++u) key[u] = u * 32 + lane < nc ? order_key(vv[u * 32 + lane]) : 0u;
+  unsigned int ans = 0u;
+  for (int b = 31; b >= 0; --b) {
+    const unsigned int trial = ans | (1u << b);
+    int cnt = 0;
+#pragma unroll
+    for (int u = 0; u < KPL; ++u) cnt += key[u] >= trial;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (cnt >= k) ans = trial;
   }
-  const bool staged = nc <= kWarpCap;
-  if (staged)
-    for (int c = lane; c < nc; c += 32) { w.a_idx[c] = gi[c]; w.a_val[c] = gv[c]; }
+  return key_to_float(ans);
+}
+
+__device__ void warp_select(const SelParams& p, int r, int img, const VocabSparse& vs, WarpSel w) {
+  const int lane = threadIdx.x & 31;
+  const float thr = __ldg(vs.thresh + r);
+  const float t0 = fmaxf(thr, -3.402823466e+38f);          // candidates are finite
+  // ---- phase A: list of stored groups, in column order
+  int* glist = w.t_idx;
+  constexpr int kGroupCap = 3 * kSurvMax;
+  const unsigned char* hm = vs.hitmap + (long long)r * vs.hit_ld;
+  int ng = 0;
+  for (int b0 = 0; b0 < vs.n_bytes; b0 += 32) {
+    const int bi = b0 + lane;
+    unsigned int byte = bi < vs.n_bytes ? (unsigned int)__ldg(hm + bi) : 0u;
+    const int mine = __popc(byte);
+    int off = mine;                                          // exclusive prefix over the lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, off, o); if (lane >= o) off += t; }
+    const int tot = __shfl_sync(0xffffffffu, off, 31);
+    int pos = ng + off - mine;
+    while (byte) {
+      const int bit = __ffs(byte) - 1;
+      byte &= byte - 1u;
+      if (pos < kGroupCap) glist[pos] = bi * vs.groups_per_byte + bit;
+      ++pos;
+    }
+    ng += tot;
+  }
+  if (ng > kGroupCap) {
+    if (lane == 0) atomicOr(p.status, DH_STATUS_TOO_MANY_TIES);
+    ng = kGroupCap;
+  }
+  if (lane == 0) *w.counter = 0;
   __syncwarp();
-  const int* ii = staged ? w.a_idx : gi;
-  const float* vv = staged ? w.a_val : gv;
+  // ---- phase B: one lane per group: its 32 logits as eight independent 16-byte loads, hits appended through a shared-memory
+  // counter (the list order is irrelevant: the threshold is order-free and the survivors are sorted by column below)
+  const float* lrow = vs.logits + (long long)r * vs.ld;
+  for (int i = lane; i < ng; i += 32) {
+    const int col0 = glist[i] * 32;
+    float4 v[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) v[g] = __ldg(reinterpret_cast<const float4*>(lrow + col0) + g);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float x4[4] = {v[g].x, v[g].y, v[g].z, v[g].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (x4[e] >= t0) {
+          const int slot = atomicAdd(w.counter, 1);
+          if (slot < kCandCap) { w.c_idx[slot] = col0 + 4 * g + e; w.c_val[slot] = x4[e]; }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  int nc = *w.counter;
+  __syncwarp();
+  if (nc > kCandCap) {
+    if (lane == 0) atomicOr(p.status, DH_STATUS_TOO_MANY_TIES);
+    nc = kCandCap;
+  }
+  const int* ii = w.c_idx;
+  const float* vv = w.c_val;
   // ---- exact k-th largest among the candidates: #{> v} < top_k <= #{>= v}; -inf if fewer than top_k candidates
   float kth = -INFINITY;
-  if (nc <= 64 && nc >= p.top_k && nc - p.top_k < 16) {
-    // an exhaustive pass 1 hands over ~top_k + 1 candidates: the top_k-th largest of nc values is the (nc - top_k + 1)-th
-    // smallest -- one or two rounds of warp-wide minimum extraction instead of O(nc^2 / 32) rank counts
-    const unsigned int a = lane < nc ? order_key(vv[lane]) : 0xffffffffu;
-    const unsigned int b = 32 + lane < nc ? order_key(vv[32 + lane]) : 0xffffffffu;
-    kth = key_to_float(warp_mth_smallest64(a, b, nc - p.top_k + 1, lane));
-  } else if (staged && nc >= p.top_k) {
-    // a sampled pass 1 hands over a few times top_k candidates: bit-wise radix select on the order-preserving keys, eight per
-    // lane in registers -- 32 rounds of (8 compares + one warp-wide add), independent of the list length
-    unsigned int key[kWarpCap / 32];
-#pragma unroll
-    for (int u = 0; u < kWarpCap / 32; ++u) key[u] = u * 32 + lane < nc ? order_key(vv[u * 32 + lane]) : 0u;
-    unsigned int ans = 0u;
-    for (int b = 31; b >= 0; --b) {
-      const unsigned int trial = ans | (1u << b);
-      int cnt = 0;
-#pragma unroll
-      for (int u = 0; u < kWarpCap / 32; ++u) cnt += key[u] >= trial;
-      cnt = __reduce_add_sync(0xffffffffu, cnt);
-      if (cnt >= p.top_k) ans = trial;
+  if (nc >= p.top_k) {
+    if (nc <= 64 && nc - p.top_k < 16) {
+      // an exhaustive pass 1 hands over ~top_k + 1 candidates: the top_k-th largest of nc values is the (nc - top_k + 1)-th
+      // smallest -- one or two rounds of warp-wide minimum extraction
+      const unsigned int a = lane < nc ? order_key(vv[lane]) : 0xffffffffu;
+      const unsigned int b = 32 + lane < nc ? order_key(vv[32 + lane]) : 0xffffffffu;
+      kth = key_to_float(warp_mth_smallest64(a, b, nc - p.top_k + 1, lane));
+    } else if (nc <= 256) {
+      kth = warp_kth_largest<8>(vv, nc, p.top_k, lane);      // a sampled pass 1 hands over a few times top_k candidates
+    } else {
+      kth = warp_kth_largest<kCandCap / 32>(vv, nc, p.top_k, lane);
     }
-    kth = key_to_float(ans);
-  } else {
-    for (int c = lane; c < nc; c += 32) {
-      const float v = vv[c];
-      int gt = 0, ge = 0;
-      for (int j = 0; j < nc; ++j) { const float o = vv[j]; gt += o > v; ge += o >= v; }
-      if (gt < p.top_k && p.top_k <= ge) kth = v;
-    }
-    kth = dh_warp_max(kth);
   }
   // ---- survivors: value >= k-th largest (ties kept) and id != <unk>
   int ns = 0;
@@ -446,13 +506,13 @@ __device__ void warp_select(const SelParams& p, int r, int img, int nc_total, co
     const unsigned mask = __ballot_sync(0xffffffffu, keep);
     if (keep) {
       const int pos = ns + __popc(mask & ((1u << lane) - 1u));
-      if (pos < kWarpCap) { w.t_idx[pos] = ii[c]; w.t_val[pos] = vv[c]; }
+      if (pos < kSurvMax) { w.t_idx[pos] = ii[c]; w.t_val[pos] = vv[c]; }
     }
     ns += __popc(mask);
   }
-  if (ns > kWarpCap) {
+  if (ns > kSurvMax) {
     if (lane == 0) atomicOr(p.status, DH_STATUS_TOO_MANY_TIES);
-    ns = kWarpCap;
+    ns = kSurvMax;
   }
   __syncwarp();
   if (ns == 0) {   // whole row filtered: torch.multinomial raises (Q3)
@@ -460,21 +520,23 @@ __device__ void warp_select(const SelParams& p, int r, int img, int nc_total, co
     if (lane < p.B) { p.ind[(long long)r * p.B + lane] = 0; p.val[(long long)r * p.B + lane] = 0.f; }
     return;
   }
+  int* a_idx = w.c_idx;                            // the candidate arrays are free again: sorted survivors
+  float* a_val = w.c_val;
   for (int c = lane; c < ns; c += 32) {          // sort by column (ids are distinct)
     const int id = w.t_idx[c];
     int pos = 0;
     for (int j = 0; j < ns; ++j) pos += w.t_idx[j] < id;
-    w.a_idx[pos] = id;
-    w.a_val[pos] = w.t_val[c];
+    a_idx[pos] = id;
+    a_val[pos] = w.t_val[c];
   }
   __syncwarp();
   // ---- softmax(l / T) over survivors (everything else has p == 0 exactly), noise, B rounds of arg-max
   float m2 = -INFINITY;
-  for (int s = lane; s < ns; s += 32) m2 = fmaxf(m2, w.a_val[s] / p.T);
+  for (int s = lane; s < ns; s += 32) m2 = fmaxf(m2, a_val[s] / p.T);
   m2 = dh_warp_max(m2);
   float sum = 0.f;
   for (int s = lane; s < ns; s += 32) {
-    const float e = expf(w.a_val[s] / p.T - m2);
+    const float e = expf(a_val[s] / p.T - m2);
     w.score[s] = e;
     sum += e;
   }
@@ -485,7 +547,7 @@ __device__ void warp_select(const SelParams& p, int r, int img, int nc_total, co
                                                  DH_CALL_TOKEN, (unsigned long long)(r % p.rpi));
   for (int s = lane; s < ns; s += 32) {
     float pr = w.score[s] / sum;
-    if (p.noise_mode == DH_NOISE_INJECTED) pr = pr / dh_exp_noise(rk, (unsigned long long)w.a_idx[s]);
+    if (p.noise_mode == DH_NOISE_INJECTED) pr = pr / dh_exp_noise(rk, (unsigned long long)a_idx[s]);
     w.score[s] = pr;
   }
   __syncwarp();
@@ -493,7 +555,7 @@ __device__ void warp_select(const SelParams& p, int r, int img, int nc_total, co
   for (int j = 0; j < npick; ++j) {
     float best = -1.f; int bi = 0x7fffffff, bs = -1;
     for (int s = lane; s < ns; s += 32) {
-      const float sc = w.score[s]; const int id = w.a_idx[s];
+      const float sc = w.score[s]; const int id = a_idx[s];
       if (sc > best || (sc == best && sc >= 0.f && id < bi)) { best = sc; bi = id; bs = s; }
     }
 #pragma unroll
@@ -505,7 +567,7 @@ __device__ void warp_select(const SelParams& p, int r, int img, int nc_total, co
     }
     if (lane == 0) {
       w.pick_idx[j] = bi;
-      w.pick_logit[j] = w.a_val[bs];
+      w.pick_logit[j] = a_val[bs];
       w.score[bs] = -2.f;   // taken
     }
     __syncwarp();
@@ -691,24 +753,23 @@ struct LstmNext {
   const uint16_t* hs[8]; uint16_t* A[8]; long long lda[8]; int in_off[8];
 };
 
-__global__ void __launch_bounds__(32 * kMaxBeam) select_beam_kernel(SelParams p, const int* __restrict__ cand_count,
-                                                                   const int* __restrict__ cand_idx,
-                                                                   const float* __restrict__ cand_val, int cap, int do_beam,
+__global__ void __launch_bounds__(32 * kMaxBeam) select_beam_kernel(SelParams p, VocabSparse vs, int do_beam,
                                                                    BeamState st, StepParams sp, LstmNext nx) {
   extern __shared__ int dyn_smem[];
   const int img = blockIdx.x, warp = threadIdx.x >> 5;
   if (p.done && p.done[img]) return;
   unsigned char* base = reinterpret_cast<unsigned char*>(dyn_smem) + (size_t)warp * kWarpSelBytes;
   WarpSel w;
-  w.a_idx = reinterpret_cast<int*>(base);
-  w.a_val = reinterpret_cast<float*>(base + kWarpCap * 4);
-  w.t_idx = reinterpret_cast<int*>(base + 2 * kWarpCap * 4);
-  w.t_val = reinterpret_cast<float*>(base + 3 * kWarpCap * 4);
-  w.score = reinterpret_cast<float*>(base + 4 * kWarpCap * 4);
-  w.pick_idx = reinterpret_cast<int*>(base + 5 * kWarpCap * 4);
-  w.pick_logit = reinterpret_cast<float*>(base + 5 * kWarpCap * 4 + kMaxBeam * 4);
+  w.c_idx = reinterpret_cast<int*>(base);
+  w.c_val = reinterpret_cast<float*>(base + kCandCap * 4);
+  w.t_idx = reinterpret_cast<int*>(base + 2 * kCandCap * 4);
+  w.t_val = reinterpret_cast<float*>(base + 2 * kCandCap * 4 + kSurvMax * 4);
+  w.score = reinterpret_cast<float*>(base + 2 * kCandCap * 4 + 2 * kSurvMax * 4);
+  w.pick_idx = reinterpret_cast<int*>(base + 2 * kCandCap * 4 + 3 * kSurvMax * 4);
+  w.pick_logit = reinterpret_cast<float*>(base + 2 * kCandCap * 4 + 3 * kSurvMax * 4 + kMaxBeam * 4);
+  w.counter = reinterpret_cast<int*>(base + 2 * kCandCap * 4 + 3 * kSurvMax * 4 + 2 * kMaxBeam * 4);
   const int r = img * p.rpi + warp;
-  warp_select(p, r, img, cand_count[r], cand_idx + (long long)r * cap, cand_val + (long long)r * cap, cap, w);
+  warp_select(p, r, img, vs, w);
   if (!do_beam) return;
   __syncthreads();                                   // the picks of all rows (global memory) are visible to warp 0
   if (warp == 0)
@@ -906,9 +967,17 @@ extern "C" int dh_token_logprob(const float* logits, long long ld, int rows, int
   return DH_OK;
 }
 
-static int launch_select_beam(const SelParams& p, const int* cand_count, const int* cand_idx, const float* cand_val, int cap,
-                              int n_img, int do_beam, const BeamState& st, const StepParams& sp, size_t seq_bytes,
-                              cudaStream_t s, const LstmNext& nx = LstmNext{}) {
+static int to_sparse(const dh_vocab_sparse* v, VocabSparse* out) {
+  if (!v || !v->thresh || !v->hitmap || !v->logits || v->n_cols <= 0) return 0;
+  const int bn = v->n_cols <= 64 ? 64 : v->n_cols <= 128 ? 128 : 256;
+  const int nb = dh_cdiv(v->n_cols, bn);
+  if (v->hit_ld < 2 * nb || v->ld < (long long)nb * bn || v->ld % 4 != 0 || ((uintptr_t)v->logits % 16) != 0) return 0;
+  *out = VocabSparse{v->thresh, v->hitmap, v->hit_ld, v->logits, v->ld, 2 * nb, bn / 64};
+  return 1;
+}
+
+static int launch_select_beam(const SelParams& p, const VocabSparse& vs, int n_img, int do_beam, const BeamState& st,
+                              const StepParams& sp, size_t seq_bytes, cudaStream_t s, const LstmNext& nx = LstmNext{}) {
   static bool attr_set = false;
   if (!attr_set) {
     DH_CUDA(cudaFuncSetAttribute(select_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -916,31 +985,32 @@ static int launch_select_beam(const SelParams& p, const int* cand_count, const i
     attr_set = true;
   }
   const size_t smem = (size_t)p.rpi * kWarpSelBytes + (do_beam ? seq_bytes : 0);
-  select_beam_kernel<<<n_img, 32 * p.rpi, smem, s>>>(p, cand_count, cand_idx, cand_val, cap, do_beam, st, sp, nx);
+  select_beam_kernel<<<n_img, 32 * p.rpi, smem, s>>>(p, vs, do_beam, st, sp, nx);
   DH_LAUNCH_OK();
   return DH_OK;
 }
 
-extern "C" int dh_select_candidates(const int* cand_count, const int* cand_idx, const float* cand_val, int cand_cap, int rows,
-                                    int beam, int top_k, float temperature, int unk, int rows_per_image, int noise_mode,
-                                    unsigned long long seed, long long image_base, int step, const unsigned char* done,
-                                    int* ind, float* val, int* status, const long long* dyn, cudaStream_t s) {
-  DH_ARG(cand_count && cand_idx && cand_val && cand_cap > 0 && ind && val && status && rows >= 0);
+extern "C" int dh_select_candidates(const dh_vocab_sparse* cand, int rows, int beam, int top_k, float temperature, int unk,
+                                    int rows_per_image, int noise_mode, unsigned long long seed, long long image_base, int step,
+                                    const unsigned char* done, int* ind, float* val, int* status, const long long* dyn,
+                                    cudaStream_t s) {
+  VocabSparse vs{};
+  DH_ARG(to_sparse(cand, &vs) && ind && val && status && rows >= 0);
   DH_ARG(beam >= 1 && beam <= kMaxBeam && top_k >= 1 && beam <= top_k && temperature > 0.f);
   DH_ARG(rows_per_image >= 1 && rows_per_image <= kMaxBeam && rows % rows_per_image == 0);
   DH_ARG(noise_mode == DH_NOISE_DETERMINISTIC || noise_mode == DH_NOISE_INJECTED);
   if (rows == 0) return DH_OK;
   SelParams p{nullptr, 0, rows, 0, beam, top_k, unk, rows_per_image, temperature, noise_mode, seed, image_base, step,
               done, ind, val, status, dyn};
-  return launch_select_beam(p, cand_count, cand_idx, cand_val, cand_cap, rows / rows_per_image, 0, BeamState{}, StepParams{}, 0, s);
+  return launch_select_beam(p, vs, rows / rows_per_image, 0, BeamState{}, StepParams{}, 0, s);
 }
 
-static int select_beam_step(const int* cand_count, const int* cand_idx, const float* cand_val, int cand_cap,
-                            const dh_beam_state* st, int* ind, float* val, int* status, int n_img, int beam, int top_k,
-                            float temperature, int unk, int step, int max_len, int eos, int lstm_semantics, int noise_mode,
-                            unsigned long long seed, long long image_base, const long long* dyn, const dh_lstm_operands* next,
-                            cudaStream_t s) {
-  DH_ARG(cand_count && cand_idx && cand_val && cand_cap > 0 && ind && val && status);
+static int select_beam_step(const dh_vocab_sparse* cand, const dh_beam_state* st, int* ind, float* val, int* status, int n_img,
+                            int beam, int top_k, float temperature, int unk, int step, int max_len, int eos, int lstm_semantics,
+                            int noise_mode, unsigned long long seed, long long image_base, const long long* dyn,
+                            const dh_lstm_operands* next, cudaStream_t s) {
+  VocabSparse vs{};
+  DH_ARG(to_sparse(cand, &vs) && ind && val && status);
   DH_ARG(check_state(st, n_img, beam) && top_k >= 1 && beam <= top_k && temperature > 0.f && step >= 1);
   DH_ARG(st->seq_ld >= max_len && (size_t)beam * st->seq_ld * sizeof(int) <= 40 * 1024);
   DH_ARG(noise_mode == DH_NOISE_DETERMINISTIC || noise_mode == DH_NOISE_INJECTED);
@@ -960,27 +1030,24 @@ static int select_beam_step(const int* cand_count, const int* cand_idx, const fl
   SelParams p{nullptr, 0, n_img * beam, 0, beam, top_k, unk, beam, temperature, noise_mode, seed, image_base, step,
               st->done, ind, val, status, dyn};
   StepParams sp{ind, val, n_img, beam, step, max_len, eos, lstm_semantics, temperature, noise_mode, seed, image_base, dyn};
-  return launch_select_beam(p, cand_count, cand_idx, cand_val, cand_cap, n_img, 1, to_state(st), sp,
-                            (size_t)beam * st->seq_ld * sizeof(int), s, nx);
+  return launch_select_beam(p, vs, n_img, 1, to_state(st), sp, (size_t)beam * st->seq_ld * sizeof(int), s, nx);
 }
 
-extern "C" int dh_select_beam_step(const int* cand_count, const int* cand_idx, const float* cand_val, int cand_cap,
-                                   const dh_beam_state* st, int* ind, float* val, int* status, int n_img, int beam, int top_k,
-                                   float temperature, int unk, int step, int max_len, int eos, int lstm_semantics,
-                                   int noise_mode, unsigned long long seed, long long image_base, const long long* dyn,
-                                   cudaStream_t s) {
-  return select_beam_step(cand_count, cand_idx, cand_val, cand_cap, st, ind, val, status, n_img, beam, top_k, temperature, unk,
-                          step, max_len, eos, lstm_semantics, noise_mode, seed, image_base, dyn, nullptr, s);
+extern "C" int dh_select_beam_step(const dh_vocab_sparse* cand, const dh_beam_state* st, int* ind, float* val, int* status,
+                                   int n_img, int beam, int top_k, float temperature, int unk, int step, int max_len, int eos,
+                                   int lstm_semantics, int noise_mode, unsigned long long seed, long long image_base,
+                                   const long long* dyn, cudaStream_t s) {
+  return select_beam_step(cand, st, ind, val, status, n_img, beam, top_k, temperature, unk, step, max_len, eos, lstm_semantics,
+                          noise_mode, seed, image_base, dyn, nullptr, s);
 }
 
-extern "C" int dh_select_beam_step_lstm(const int* cand_count, const int* cand_idx, const float* cand_val, int cand_cap,
-                                        const dh_beam_state* st, int* ind, float* val, int* status, int n_img, int beam,
-                                        int top_k, float temperature, int unk, int step, int max_len, int eos,
+extern "C" int dh_select_beam_step_lstm(const dh_vocab_sparse* cand, const dh_beam_state* st, int* ind, float* val, int* status,
+                                        int n_img, int beam, int top_k, float temperature, int unk, int step, int max_len, int eos,
                                         int lstm_semantics, int noise_mode, unsigned long long seed, long long image_base,
                                         const long long* dyn, const dh_lstm_operands* next, cudaStream_t s) {
   DH_ARG(next);
-  return select_beam_step(cand_count, cand_idx, cand_val, cand_cap, st, ind, val, status, n_img, beam, top_k, temperature, unk,
-                          step, max_len, eos, lstm_semantics, noise_mode, seed, image_base, dyn, next, s);
+  return select_beam_step(cand, st, ind, val, status, n_img, beam, top_k, temperature, unk, step, max_len, eos, lstm_semantics,
+                          noise_mode, seed, image_base, dyn, next, s);
 }
 
 // out[row] = tlogit[row] - logsumexp(row) from the per-group (max, sum exp) pairs written by the contraction's epilogue.

@@ -7,7 +7,7 @@ import os
 
 import torch
 
-from .._lib import LIB, BeamState, LstmOperands, ptr, stream
+from .._lib import LIB, BeamState, LstmOperands, VocabSparse, ptr, stream
 
 F32, BF16, F16 = 0, 1, 2
 NOISE = {'deterministic': 0, 'injected': 1}
@@ -413,14 +413,17 @@ def sampled_rank(top_k, frac, eps=1e-7):
 
 
 class VocabSelect:
-    """Vocab projection fused with token selection for `rows` rows, logits never stored (dh_vocab_* in the header).
+    """Vocab projection fused with token selection for `rows` rows, dense logits never stored (dh_vocab_* in the header).
 
-    The selection kernels are exact for any per-row threshold that leaves between top_k and `cap` candidates in the row's
-    list.  Default: a SAMPLED pass 1 over every stride-th 256-column tile (1/stride of a full contraction) whose rank is
-    chosen so that the threshold is low enough except with probability < 1e-7 per row, one full contraction that compacts
-    the candidates (a few times top_k per row), and three fix-up launches that return at once unless a row's list came out
-    short or overflowed -- then they redo that step's threshold exhaustively, inside the same CUDA graph.  stride 1 = the
-    exhaustive two-pass form (two full contractions, ~top_k + 1 candidates per row)."""
+    Pass 2 stores only the 32-column groups that hold a logit >= the row's threshold (sparse materialisation: a hit map plus
+    their 128-byte lines in a dense-pitch buffer) and the selection kernels rank exactly what they find there, so they are
+    exact for any per-row threshold that leaves at least top_k candidates.  Default: a SAMPLED pass 1 over every stride-th
+    256-column tile (1/stride of a full contraction) whose rank is chosen so that the threshold is low enough except with
+    probability < 1e-7 per row, one full contraction for pass 2, and three fix-up launches that return at once unless a row
+    stored too few / too many groups -- then they redo that step's threshold exhaustively, inside the same CUDA graph.
+    stride 1 = the exhaustive two-pass form (two full contractions, ~top_k + 1 candidates per row)."""
+
+    GROUP_CAP = 400          # stored groups per row the selection kernel accepts (its list holds 480); more -> fix-up
 
     def __init__(self, rows, V, top_k, device, stride=None):
         self.rows, self.V, self.top_k = rows, V, top_k
@@ -433,7 +436,6 @@ class VocabSelect:
             stride //= 2
         self.stride = max(1, stride)
         self.n_groups_full = n_blocks * (bn // 32)
-        self.cap = min((V + 31) // 32 * 32, 32 * top_k)
         if self.stride > 1:
             frac = ((n_blocks + self.stride - 1) // self.stride) / n_blocks      # largest sampled fraction over the offsets
             self.rank = min(sampled_rank(top_k, frac), 64)
@@ -443,19 +445,38 @@ class VocabSelect:
         self.gmax = torch.empty(rows, self.n_groups_full, **f32)
         self.thresh = torch.empty(rows, **f32)
         self.count = torch.zeros(rows, **i32)
-        self.idx = torch.empty(rows, self.cap, **i32)
-        self.val = torch.empty(rows, self.cap, **f32)
+        self.sp_ld = n_blocks * bn
+        self.sp_logits = torch.empty(rows, self.sp_ld, **f32)               # only the stored groups are ever written / read
+        self.hit_ld = 2 * n_blocks
+        self.hitmap = torch.zeros(rows, self.hit_ld, dtype=torch.uint8, device=device)
         self.redo = torch.zeros(rows, dtype=torch.uint8, device=device) if self.stride > 1 else None
         self.flag = torch.zeros(1, **i32) if self.stride > 1 else None
+        self.c = VocabSparse(ptr(self.thresh), ptr(self.hitmap), self.hit_ld, ptr(self.sp_logits), self.sp_ld, V)
 
     def groups(self, offset):
         return (self.n_blocks - offset + self.stride - 1) // self.stride * (self.bn // 32)
 
     @staticmethod
     def supported(A, V, top_k):
-        # the threshold kernel ranks at most 64 values exactly and the warp-level selection stages 256 candidates: larger
+        # the threshold kernel ranks at most 64 values exactly and the warp-level selection keeps 160 survivors: larger
         # top_k takes the materialised-logits path (dh_select_tokens), which has no such limits
         return A.dtype in (torch.bfloat16, torch.float16) and top_k <= 64 and top_k <= (V + 31) // 32
+
+    def candidates(self, rows):
+        """Number of logits >= thresh per row (host-side diagnostic; walks the hit map)."""
+        hm = self.hitmap[:rows].cpu()
+        th = self.thresh[:rows].cpu()
+        lg = self.sp_logits[:rows].cpu().view(rows, -1, 32)
+        cpb = self.bn // 64
+        out = torch.zeros(rows, dtype=torch.int64)
+        for r in range(rows):
+            nz = torch.nonzero(hm[r]).flatten()
+            for bi in nz.tolist():
+                byte = int(hm[r, bi])
+                for bit in range(cpb):
+                    if byte >> bit & 1:
+                        out[r] += int((lg[r, bi * cpb + bit] >= th[r]).sum())
+        return out
 
     def run(self, A, W, bias, beam, temperature, unk, rows_per_image, noise_mode, step, done, ind, val, status, dyn,
             seed=0, image_base=0, beam_step=None, lstm_next=None):
@@ -467,7 +488,7 @@ class VocabSelect:
         args = (ptr(A), _rows(A), ptr(W), _rows(W), code(A), ptr(bias), rows, self.V, K)
         offset = step % self.stride                       # the sampled tiles rotate from step to step
         ng = self.groups(offset)
-        lists = (ptr(self.thresh), ptr(self.count), ptr(self.idx), ptr(self.val), self.cap)
+        lists = (ptr(self.thresh), ptr(self.count), ptr(self.sp_logits), self.sp_ld, ptr(self.hitmap), self.hit_ld)
         with PROFILE.range('vocab_pass1', 2.0 * rows * min(self.V, ng * 32) * K):
             LIB.call('dh_vocab_groupmax', *args, self.stride, offset, ptr(self.gmax), self.n_groups_full, stream())
         with PROFILE.range('vocab_threshold', nbytes=4.0 * rows * ng):
@@ -476,7 +497,8 @@ class VocabSelect:
         with PROFILE.range('vocab_gemm', 2.0 * rows * self.V * K):          # one launch = one full [rows,V,K] product
             LIB.call('dh_vocab_candidates', *args, *lists, stream())
         if self.stride > 1:
-            lo, hi = min(self.top_k, self.V), self.cap
+            # stored groups per row: at least top_k of them guarantee top_k candidates; the selection kernel lists <= 480
+            lo, hi = min(self.top_k, self.n_groups_full), self.GROUP_CAP
             with PROFILE.range('vocab_fixup'):
                 LIB.call('dh_vocab_groupmax_fix', *args, ptr(self.gmax), self.n_groups_full, ptr(self.count), lo, hi,
                          ptr(self.flag), stream())
@@ -485,13 +507,13 @@ class VocabSelect:
                 LIB.call('dh_vocab_candidates_fix', *args, *lists, ptr(self.redo), ptr(self.flag), stream())
         with PROFILE.range('select_beam'):
             if beam_step is None:
-                LIB.call('dh_select_candidates', ptr(self.count), ptr(self.idx), ptr(self.val), self.cap, rows, beam,
+                LIB.call('dh_select_candidates', ctypes.byref(self.c), rows, beam,
                          self.top_k, float(temperature), unk, rows_per_image, noise_mode, seed, image_base, step,
                          ptr(done), ptr(ind), ptr(val), ptr(status), ptr(dyn), stream())
             else:
                 bm, max_len, eos, lstm_sem = beam_step
                 assert rows == bm.n_img * bm.beam and rows_per_image == bm.beam == beam
-                common = (ptr(self.count), ptr(self.idx), ptr(self.val), self.cap, ctypes.byref(bm.c), ptr(ind), ptr(val),
+                common = (ctypes.byref(self.c), ctypes.byref(bm.c), ptr(ind), ptr(val),
                           ptr(status), bm.n_img, beam, self.top_k, float(temperature), unk, step, max_len, eos,
                           int(lstm_sem), noise_mode, seed, image_base, ptr(dyn))
                 if lstm_next is None:

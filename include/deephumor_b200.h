@@ -24,7 +24,7 @@ extern "C" {
 typedef struct CUstream_st* cudaStream_t;
 #endif
 
-#define DH_VERSION 201
+#define DH_VERSION 202
 
 #define DH_OK 0
 #define DH_ERR_ARG (-1)
@@ -207,32 +207,43 @@ int dh_select_tokens(const float* logits, long long ld, int rows, int V, int bea
                      int rows_per_image, int noise_mode, unsigned long long seed, long long image_base, int step,
                      const unsigned char* done, int* ind, float* val, int* status, const long long* dyn,
                      cudaStream_t stream);
-/* Vocab projection fused with the selection, logits never stored (rnn_models.py:81,109 / transformers.py:488,736 ->
- * beam.py:32-53).  logits[M,N] = A[M,K] W[N,K]^T + bias (tcgen05, A / W ab_dtype) are produced twice, bit-identically:
+/* Vocab projection fused with the selection, dense logits never stored (rnn_models.py:81,109 / transformers.py:488,736 ->
+ * beam.py:32-53).  logits[M,N] = A[M,K] W[N,K]^T + bias (tcgen05, A / W ab_dtype):
  *   dh_vocab_groupmax    gmax[m, g] = max of the g-th 32-column group of logits[m, :] among the N tiles o, o + s, o + 2s, ...
  *                        (s = tile_stride, o = tile_offset; tile = 256 columns; groups past N hold -inf)   (pass 1)
  *   dh_vocab_threshold   thresh[m] = top_k-th largest of gmax[m, :]; cand_count[m] = 0
- *   dh_vocab_candidates  appends (column, logit) of every finite logit >= thresh[m] to row m's list     (pass 2)
- *   dh_select_candidates dh_select_tokens on those lists.
- * The selection is exact for ANY threshold that leaves at least top_k (and at most cand_cap) candidates in the list, because
- * dh_select_candidates recomputes the exact top_k-th largest value from the list.  Two ways to get such a threshold:
+ *   dh_vocab_candidates  SPARSE MATERIALISATION (pass 2): every 32-column group of row m whose maximum is >= thresh[m] is
+ *                        stored as is (one 128-byte line) at sp_logits[m, 32 g ..]; hitmap[m, 2 t + h] holds one bit per
+ *                        stored group of N tile t, column half h (written for every (m, t, h), no atomics);
+ *                        cand_count[m] += number of stored groups.  The epilogue does the same work wherever the candidates
+ *                        sit, and a few per cent of the logits reach memory.
+ *   dh_select_candidates gathers the stored groups, keeps the logits >= thresh[m], and runs dh_select_tokens on them.
+ * The selection is exact for ANY threshold that leaves at least top_k candidates (and at most 480 stored groups / 512
+ * candidates per row), because dh_select_candidates recomputes the exact top_k-th largest value.  Two ways to get one:
  *   exhaustive  tile_stride 1, rank top_k: the top_k-th largest group maximum is a lower bound of the top_k-th largest logit
- *               and at most 32 * top_k logits reach it, so cand_cap >= min(N, 32 * top_k) cannot overflow (ties aside).  Costs a
- *               second full contraction.
+ *               and at most top_k groups reach it.  Costs a second full contraction.
  *   sampled     tile_stride s > 1 and a rank j < top_k chosen so that the j-th largest SAMPLED group maximum lies below the
  *               top_k-th largest logit except with negligible probability (the host picks j from the binomial tail).  Pass 1
  *               costs 1/s.  The three *_fix entries then repair, inside the same stream / CUDA graph, the rare step in which
- *               a row's list came out shorter than top_k or longer than cand_cap: each returns immediately unless such a row
+ *               a row stored fewer than count_min or more than count_max groups: each returns immediately unless such a row
  *               exists.  dh_vocab_groupmax_fix = exhaustive pass 1 (and *any_flag = 0); dh_vocab_threshold_fix = exact
  *               threshold, cand_count = 0, redo = 1 for the failing rows (redo = 0 for the others), *any_flag = 1;
  *               dh_vocab_candidates_fix = pass 2 for the rows with redo != 0, only if *any_flag != 0. */
+typedef struct dh_vocab_sparse {
+  const float* thresh;            /* [rows] */
+  const unsigned char* hitmap;    /* [rows, hit_ld], hit_ld >= 2 * ceil(n_cols / 256) */
+  long long hit_ld;
+  const float* logits;            /* [rows, ld], ld >= ceil(n_cols / 256) * 256, ld % 4 == 0, 16-byte aligned */
+  long long ld;
+  int n_cols;                     /* N (vocabulary size) */
+} dh_vocab_sparse;
 int dh_vocab_groupmax(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias, int M,
                       int N, int K, int tile_stride, int tile_offset, float* gmax, long long ld_gmax, cudaStream_t stream);
 int dh_vocab_threshold(const float* gmax, long long ld_gmax, int rows, int n_groups, int top_k, float* thresh,
                        int* cand_count, cudaStream_t stream);
 int dh_vocab_candidates(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias, int M,
-                        int N, int K, const float* thresh, int* cand_count, int* cand_idx, float* cand_val, int cand_cap,
-                        cudaStream_t stream);
+                        int N, int K, const float* thresh, int* cand_count, float* sp_logits, long long sp_ld,
+                        unsigned char* hitmap, long long hit_ld, cudaStream_t stream);
 int dh_vocab_groupmax_fix(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias, int M,
                           int N, int K, float* gmax, long long ld_gmax, const int* cand_count, int count_min, int count_max,
                           int* any_flag, cudaStream_t stream);
@@ -240,18 +251,17 @@ int dh_vocab_threshold_fix(const float* gmax, long long ld_gmax, int rows, int n
                            int* cand_count, int count_min, int count_max, unsigned char* redo, int* any_flag,
                            cudaStream_t stream);
 int dh_vocab_candidates_fix(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias, int M,
-                            int N, int K, const float* thresh, int* cand_count, int* cand_idx, float* cand_val, int cand_cap,
-                            const unsigned char* redo, int* any_flag, cudaStream_t stream);
-int dh_select_candidates(const int* cand_count, const int* cand_idx, const float* cand_val, int cand_cap, int rows,
-                         int beam, int top_k, float temperature, int unk, int rows_per_image, int noise_mode,
-                         unsigned long long seed, long long image_base, int step, const unsigned char* done, int* ind,
-                         float* val, int* status, const long long* dyn, cudaStream_t stream);
+                            int N, int K, const float* thresh, int* cand_count, float* sp_logits, long long sp_ld,
+                            unsigned char* hitmap, long long hit_ld, const unsigned char* redo, int* any_flag,
+                            cudaStream_t stream);
+int dh_select_candidates(const dh_vocab_sparse* cand, int rows, int beam, int top_k, float temperature, int unk,
+                         int rows_per_image, int noise_mode, unsigned long long seed, long long image_base, int step,
+                         const unsigned char* done, int* ind, float* val, int* status, const long long* dyn, cudaStream_t stream);
 /* dh_select_candidates for the beam rows of every image followed by dh_beam_step of that image, in one launch
  * (one CTA per image, one warp per row).  ind / val [n_img*beam, beam] receive the picks as in dh_select_tokens. */
-int dh_select_beam_step(const int* cand_count, const int* cand_idx, const float* cand_val, int cand_cap,
-                        const dh_beam_state* st, int* ind, float* val, int* status, int n_img, int beam, int top_k,
-                        float temperature, int unk, int step, int max_len, int eos, int lstm_semantics, int noise_mode,
-                        unsigned long long seed, long long image_base, const long long* dyn, cudaStream_t stream);
+int dh_select_beam_step(const dh_vocab_sparse* cand, const dh_beam_state* st, int* ind, float* val, int* status, int n_img,
+                        int beam, int top_k, float temperature, int unk, int step, int max_len, int eos, int lstm_semantics,
+                        int noise_mode, unsigned long long seed, long long image_base, const long long* dyn, cudaStream_t stream);
 /* The same launch, followed -- per image, once its beam step has chosen tokens and parents -- by the operand gathers of the
  * NEXT LSTM time step (what dh_lstm_prepare does in a launch of its own; rnn_models.py:107,135-137): A[0][r, 0:E] =
  * table[last_tok[r]] and A[l][r, in_off[l] : +H] = hs[l][parent_state[r]] for the image's beam rows.  Images that are done
@@ -262,10 +272,9 @@ typedef struct dh_lstm_operands {
   const void* hs[8];                                         /* [*, H] contiguous per layer */
   void* A[8]; long long lda[8]; int in_off[8];               /* operand buffers, leading dimensions, column of the h half */
 } dh_lstm_operands;
-int dh_select_beam_step_lstm(const int* cand_count, const int* cand_idx, const float* cand_val, int cand_cap,
-                             const dh_beam_state* st, int* ind, float* val, int* status, int n_img, int beam, int top_k,
-                             float temperature, int unk, int step, int max_len, int eos, int lstm_semantics, int noise_mode,
-                             unsigned long long seed, long long image_base, const long long* dyn,
+int dh_select_beam_step_lstm(const dh_vocab_sparse* cand, const dh_beam_state* st, int* ind, float* val, int* status, int n_img,
+                             int beam, int top_k, float temperature, int unk, int step, int max_len, int eos, int lstm_semantics,
+                             int noise_mode, unsigned long long seed, long long image_base, const long long* dyn,
                              const dh_lstm_operands* next, cudaStream_t stream);
 int dh_beam_init(const dh_beam_state* st, const int* ind0, const float* val0, const int* prefix, long long prefix_ld,
                  int prefix_rows, int prefix_len, int n_img, int beam, int eos, int lstm_semantics, cudaStream_t stream);

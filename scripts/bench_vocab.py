@@ -42,22 +42,20 @@ Ab = A
 args = (ptr(Ab), K, ptr(W), K, 1, ptr(b), M, N, K)
 print('pass1 groupmax', t(lambda: LIB.call('dh_vocab_groupmax', *args, vs.stride, 0, ptr(vs.gmax), vs.n_groups_full, stream())))
 print('threshold     ', t(lambda: LIB.call('dh_vocab_threshold', ptr(vs.gmax), vs.n_groups_full, M, vs.groups(0), vs.rank, ptr(vs.thresh), ptr(vs.count), stream())))
+lists = (ptr(vs.thresh), ptr(vs.count), ptr(vs.sp_logits), vs.sp_ld, ptr(vs.hitmap), vs.hit_ld)
 def p2():
     vs.count.zero_()
-    LIB.call('dh_vocab_candidates', *args, ptr(vs.thresh), ptr(vs.count), ptr(vs.idx), ptr(vs.val), vs.cap, stream())
+    LIB.call('dh_vocab_candidates', *args, *lists, stream())
 print('pass2 candidates (+zero)', t(p2))
-print('select_candidates', t(lambda: LIB.call('dh_select_candidates', ptr(vs.count), ptr(vs.idx), ptr(vs.val), vs.cap, M, 5, 50, 1.0, 1, 5, 1, 1, 0, 3, None, ptr(ind), ptr(val), ptr(status), None, stream())))
+import ctypes
+print('select_candidates', t(lambda: LIB.call('dh_select_candidates', ctypes.byref(vs.c), M, 5, 50, 1.0, 1, 5, 1, 1, 0, 3, None, ptr(ind), ptr(val), ptr(status), None, stream())))
 print('fused total', t(lambda: vs.run(A, W, b, 5, 1.0, 1, 5, 1, 3, None, ind, val, status, None, seed=1)))
-print('candidates per row: mean %.1f max %d' % (float(vs.count.float().mean()), int(vs.count.max())))
-
+print('stored groups per row: mean %.1f max %d' % (float(vs.count.float().mean()), int(vs.count.max())), ' status', int(status))
 if vs.stride > 1:
-    lo, hi = 50, vs.cap
+    lo, hi = 50, vs.GROUP_CAP
     def fix():
         LIB.call('dh_vocab_groupmax_fix', *args, ptr(vs.gmax), vs.n_groups_full, ptr(vs.count), lo, hi, ptr(vs.flag), stream())
         LIB.call('dh_vocab_threshold_fix', ptr(vs.gmax), vs.n_groups_full, M, vs.n_groups_full, 50, ptr(vs.thresh), ptr(vs.count), lo, hi, ptr(vs.redo), ptr(vs.flag), stream())
-        LIB.call('dh_vocab_candidates_fix', *args, ptr(vs.thresh), ptr(vs.count), ptr(vs.idx), ptr(vs.val), vs.cap, ptr(vs.redo), ptr(vs.flag), stream())
+        LIB.call('dh_vocab_candidates_fix', *args, *lists, ptr(vs.redo), ptr(vs.flag), stream())
     print('fix-up x3 (nothing to fix)', t(fix))
     print('rows below top_k:', int((vs.count < 50).sum()), 'min count', int(vs.count.min()), 'redo', int(vs.redo.sum()))
-    vs.count[:7] = 3      # force the repair path for 7 rows
-    fix(); torch.cuda.synchronize()
-    print('after forced repair: redo', int(vs.redo.sum()), 'counts', vs.count[:8].tolist(), 'flag', int(vs.flag))
