@@ -74,6 +74,11 @@ struct TcParams {
   // *cond_flag != 0; redo (nullable) = rows whose candidates this launch may emit.
   int n_offset, cond_mode, cond_min, cond_max;
   const int* cond_count; int* cond_flag; const unsigned char* redo;
+  // Image-aligned M tiles + fused global average pool (dh_gemm_tc_pool: the last bottleneck's conv3, encoders.py:60-61):
+  // a tile covers bm_rows = floor(128 / pool_hw) * pool_hw rows, i.e. whole images, so the slab epilogue can reduce the
+  // pool_hw rows of each image per column and store their mean (fp32) without a second pass over the feature map.
+  int bm_rows;                            // rows of A / C per CTA tile (128 unless pooling)
+  int pool_hw; float* pool_out; long long ld_pool;
 };
 
 // ------------------------------------------------------------------------------------------- PTX wrappers
@@ -349,7 +354,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int tiles = p.m_blocks * p.n_blocks * ((EPI == 3 && p.layers > 1) ? p.layers : 1);
   const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tstride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  auto tile_m0 = [&](int tile) { return (tile / p.n_blocks) * (BM * CG) + (int)cta_rank * BM; };
+  auto tile_m0 = [&](int tile) { return (tile / p.n_blocks) * (p.bm_rows * CG) + (int)cta_rank * p.bm_rows; };
 
   if (warp == 0) {
     if (lane == 0) {
@@ -362,7 +367,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int m0 = tile_m0(rt), n0 = ((rt % p.n_blocks) * p.n_stride + p.n_offset) * BN;
         // an M block past the end (odd block count, second CTA of the last pair) re-loads the last valid block: its
         // accumulator is never stored, and every TMA coordinate stays inside the tensor
-        const int m0l = min(m0, (dh_cdiv_dev(p.M, BM) - 1) * BM);
+        const int m0l = min(m0, (dh_cdiv_dev(p.M, p.bm_rows) - 1) * p.bm_rows);
+        const uint32_t stage_tx = (uint32_t)(p.bm_rows + BN / CG) * (BK * 2);   // bytes one CTA's loads of a stage deliver
         int img = 0, ph = 0, qw = 0;
         if (p.conv) {
           img = m0l / p.HoWo;
@@ -383,7 +389,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (EPI == 3 && layer > 0 && kc == 0) wait_ready(p.ready + (layer - 1) * p.mb128 + (m0l >> 7), p.n_blocks, p.error);
           mbar_wait(empty_bar(stage), phase ^ 1u, p.error, 1);
           const uint32_t sa = ring + stage * C::kStageBytes, sb = sa + BM * BK * 2;
-          if (cta_rank == 0) mbar_expect_tx(full_bar(stage), C::kStageBytes * CG);
+          if (cta_rank == 0) mbar_expect_tx(full_bar(stage), stage_tx * CG);
           if (PAIR) {
             const uint32_t fb = mapa_u32(full_bar(stage), 0);
             if (p.conv && p.k1_chunks && kc >= p.k1_chunks) {
@@ -418,14 +424,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(empty_bar(stage), phase ^ 1u, p.error, 1);
           const uint32_t sa = ring + stage * C::kStageBytes, sb = sa + BM * BK * 2;
           if (PAIR) {
-            if (cta_rank == 0) mbar_expect_tx(full_bar(stage), C::kStageBytes * CG);
+            if (cta_rank == 0) mbar_expect_tx(full_bar(stage), stage_tx * CG);
             const uint32_t fb = mapa_u32(full_bar(stage), 0);
             tma_load_2d_pair(sa, &map_r, fb, n0 + j * BK, m0l);
             tma_load_2d_pair(sb, &map_i, fb, j * BK, (int)cta_rank * (BN / CG));
           } else {
             // single CTA: the chunk's B operand is just the 64 x 64 identity (8 KB, not BN x 64 of mostly zeros); its MMAs
             // write accumulator columns 64 j .. 64 j + 63 with N = 64
-            mbar_expect_tx(full_bar(stage), BM * BK * 2 + 64 * BK * 2);
+            mbar_expect_tx(full_bar(stage), p.bm_rows * BK * 2 + 64 * BK * 2);
             tma_load_2d(sa, &map_r, full_bar(stage), n0 + j * BK, m0l);
             tma_load_2d(sb, &map_i, full_bar(stage), 0, 0);
           }
@@ -816,6 +822,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
+          if (p.pool_out) {
+            // fused global average pool: the slab holds this round's 64 columns of the tile's whole images exactly as they
+            // are stored (already rounded to the output type); one thread per (image, column) adds the image's rows in
+            // ascending order -- the summation of dh_avgpool, bit for bit -- while the TMA store drains the same slab
+            const int hw = p.pool_hw, gimg = p.bm_rows / hw;
+            for (int q = row_l; q < gimg * 64; q += 128) {
+              const int i = q >> 6, c = q & 63;
+              const long long img = (long long)(m0 / hw) + i;
+              if ((img + 1) * hw <= p.M && col0 + c < p.N) {
+                float s = 0.f;
+                for (int r = i * hw; r < (i + 1) * hw; ++r) {
+                  uint16_t raw;
+                  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(raw)
+                               : "r"(slab + (uint32_t)r * 128u + ((((uint32_t)c >> 3) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)c & 7u) * 2u));
+                  s += p.out_dtype == DH_BF16 ? __bfloat162float(__ushort_as_bfloat16(raw)) : __half2float(__ushort_as_half(raw));
+                }
+                p.pool_out[img * p.ld_pool + col0 + c] = s / (float)hw;
+              }
+            }
+          }
           ++round_ctr;
         }
         tc_fence_before();
@@ -1009,7 +1035,8 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, 
   }
   if (p.n_stride < 1) p.n_stride = 1;
   p.n_blocks = dh_cdiv(dh_cdiv(p.N, BN) - p.n_offset, p.n_stride);
-  p.m_blocks = dh_cdiv(p.M, PAIR ? 2 * BM : BM);
+  if (p.bm_rows <= 0) p.bm_rows = BM;
+  p.m_blocks = dh_cdiv(p.M, PAIR ? 2 * p.bm_rows : p.bm_rows);
   p.tiles_per_layer = p.m_blocks * p.n_blocks;
   p.mb128 = dh_cdiv(p.M, BM);
   const int tiles = p.tiles_per_layer * ((EPI == 3 && p.layers > 1) ? p.layers : 1);
@@ -1062,7 +1089,8 @@ int dispatch(const CUtensorMap& ma, const void* W, long long ldw, TcParams& p, i
   // 4-9 % at K = 512 (l3.c1, l3.c3, l3.ds, l4.c3, the vocab projection) now that the remote accumulator hand-off carries no
   // GPU-scope membar, and lose on the 1-2 chunk store-bound tiles of layer1 (l1.c3 +8 % at a threshold of 4).
   static const int pair_min_chunks = getenv("DH_TC_PAIR_MIN_CHUNKS") ? atoi(getenv("DH_TC_PAIR_MIN_CHUNKS")) : 8;
-  const bool pair = pair_ok && bn >= 128 && p.M > BM && p.k_chunks + (p.res ? bn / BK : 0) >= pair_min_chunks;
+  const int bm_rows = p.bm_rows > 0 ? p.bm_rows : BM;
+  const bool pair = pair_ok && bn >= 128 && p.M > bm_rows && p.k_chunks + (p.res ? bn / BK : 0) >= pair_min_chunks;
   const int b_rows = pair ? bn / 2 : bn;                   // W rows one CTA stages per K chunk
   const long long w_rows = (p.epi_mode == 3 && p.layers > 1) ? (long long)p.layers * p.w_layer_rows : p.N;
   int rc = make_map_2d(&mb, W, w_rows, p.K, ldw, b_rows, p.ab_dtype);
@@ -1078,11 +1106,11 @@ int dispatch(const CUtensorMap& ma, const void* W, long long ldw, TcParams& p, i
   if (p.epi_mode) {
     // selection epilogues store nothing of C
   } else if (out_ok && res_ok) {
-    rc = make_map_2d(&mc, p.out, p.M, p.split_n ? p.split_n : p.N, p.ldc, BM, p.out_dtype);
+    rc = make_map_2d(&mc, p.out, p.M, p.split_n ? p.split_n : p.N, p.ldc, bm_rows, p.out_dtype);
     if (rc) return rc;
     p.tma_store = 1;
     if (p.res) {
-      rc = make_map_2d(&mr, p.res, p.M, p.N, p.ldr, BM, p.ab_dtype);
+      rc = make_map_2d(&mr, p.res, p.M, p.N, p.ldr, bm_rows, p.ab_dtype);
       if (rc) return rc;
       rc = make_map_2d(&mi, g_identity[p.ab_dtype], 256, 256, 256, pair ? b_rows : 64, p.ab_dtype);
       if (rc) return rc;
@@ -1125,6 +1153,37 @@ extern "C" int dh_gemm_tc(const void* A, long long lda, const void* W, long long
   rc = make_map_2d(&ma, A, M, K, lda, BM, ab_dtype);
   if (rc) return rc;
   return dispatch(ma, W, ldw, p, tile_n ? tile_n : pick_bn(M, N), stream);
+}
+
+// C = act(A W^T + bias + residual) AND pool[i, :] = mean of rows [i * pool_hw, (i + 1) * pool_hw) of C (fp32): the last
+// bottleneck's conv3 + bn3 + residual + ReLU with the AdaptiveAvgPool2d of encoders.py:39,60 in its epilogue (a 1x1 / stride 1
+// convolution over NHWC is this plain contraction over the pixel rows).  M tiles hold whole images (pool_hw <= 128,
+// M % pool_hw == 0); the pooled means equal dh_avgpool on the stored C bit for bit.
+extern "C" int dh_gemm_tc_pool(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias,
+                               const void* residual, long long ldr, void* C, long long ldc, int M, int N, int K, int relu,
+                               int pool_hw, float* pool, long long ld_pool, cudaStream_t stream) {
+  DH_ARG(A && W && C && pool && M >= 0 && N > 0 && K > 0);
+  DH_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0 && (!residual || ldr % 8 == 0));
+  DH_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0 && ((uintptr_t)C % 16) == 0 && ((uintptr_t)residual % 16) == 0);
+  DH_ARG(ab_dtype == DH_BF16 || ab_dtype == DH_F16);
+  DH_ARG(pool_hw >= 1 && pool_hw <= BM && M % pool_hw == 0 && ld_pool >= N);
+  if (M == 0) return DH_OK;
+  int rc = tc_init();
+  if (rc) return rc;
+  TcParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.k_chunks = dh_cdiv(K, BK);
+  p.ab_dtype = ab_dtype;
+  p.bias = bias; p.res = residual; p.ldr = ldr; p.res_dtype = ab_dtype;
+  p.out = C; p.ldc = ldc; p.out_dtype = ab_dtype; p.relu = relu;
+  p.bm_rows = BM / pool_hw * pool_hw;
+  p.pool_hw = pool_hw; p.pool_out = pool; p.ld_pool = ld_pool;
+  CUtensorMap ma;
+  rc = make_map_2d(&ma, A, M, K, lda, p.bm_rows, ab_dtype);
+  if (rc) return rc;
+  rc = dispatch(ma, W, ldw, p, N % 256 == 0 ? 256 : N % 128 == 0 ? 128 : 64, stream);
+  if (rc) return rc;
+  return p.tma_store ? DH_OK : dh_fail(DH_ERR_ARG, "pooled epilogue needs the TMA-store path", __FILE__, __LINE__);
 }
 
 // One contraction, three destinations: [C0 | C1 | C2][M, 3 * split_n] = A[M,K] * W[3 * split_n, K]^T + bias, block j of

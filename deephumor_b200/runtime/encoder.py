@@ -155,19 +155,20 @@ class EncoderRT:
         sd = torch.tensor(self.pixel_std, dtype=torch.float32, device=images_u8.device).view(1, 3, 1, 1)
         return ((images_u8.float() / 255.0) - m) / sd
 
-    def trunk(self, images):
-        """images [n,3,224,224] fp32 NCHW (device) -> features [n,7,7,2048] NHWC in the trunk storage dtype."""
+    def trunk(self, images, pooled=None):
+        """images [n,3,224,224] fp32 NCHW (device) -> features [n,7,7,2048] NHWC in the trunk storage dtype.
+        pooled (fp32 [n,2048], optional) receives the global average pool; returns (features, pooled_written)."""
         n, _, H, W = images.shape
         if images.dtype == torch.uint8:
             if self.tdtype != torch.float32 and H == 224 and W == 224 and ops.FUSED_STEM:
                 x = self._buf('pool', (n, 56, 56, 64))
                 ops.stem_pool_u8(images, self.pixel_mean, self.pixel_std, self.stem_wq, self.stem.bias, x)
-                return self._layers(x)
+                return self._layers(x, pooled)
             images = self.normalize(images)
         if self.tdtype != torch.float32 and H == 224 and W == 224 and ops.FUSED_STEM:
             x = self._buf('pool', (n, 56, 56, 64))
             ops.stem_pool(images, self.stem_wq, self.stem.bias, x)
-            return self._layers(x)
+            return self._layers(x, pooled)
         if self.tdtype != torch.float32:
             Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
             A = self._buf('stemA', (n * Ho * Wo, 192))
@@ -180,9 +181,10 @@ class EncoderRT:
             x = self._conv('stem', x, self.stem, True)
         y = self._buf('pool', (n, (x.shape[1] - 1) // 2 + 1, (x.shape[2] - 1) // 2 + 1, 64))
         ops.maxpool3x3s2(x, y)
-        return self._layers(y)
+        return self._layers(y, pooled)
 
-    def _layers(self, x):
+    def _layers(self, x, pooled=None):
+        last = len(self.blocks) - 1
         for i, blk in enumerate(self.blocks):
             y1 = self._conv(f'b{i}c1', x, blk['c1'], True)
             y2 = self._conv(f'b{i}c2', y1, blk['c2'], True)
@@ -193,8 +195,18 @@ class EncoderRT:
                 x = out
                 continue
             idn = self._conv(f'b{i}ds', x, blk['down'], False) if blk['down'] is not None else x
+            n, Ho, Wo, C2 = y2.shape
+            if (i == last and pooled is not None and ops.FUSED_POOL and self.tdtype != torch.float32 and Ho * Wo <= 128
+                    and blk['down'] is None):
+                # conv3 + bn3 + identity + ReLU of the last bottleneck with AdaptiveAvgPool2d((1,1)) in its epilogue
+                # (encoders.py:39,60): M tiles of whole images, the map is never re-read for the pooled vector
+                c3 = blk['c3']
+                out = self._buf(f'b{i}c3', (n, Ho, Wo, c3.cout))
+                ops.gemm_pool(y2.view(n * Ho * Wo, C2), c3.w.view(c3.cout, C2), out.view(n * Ho * Wo, c3.cout), pooled,
+                              Ho * Wo, bias=c3.bias, residual=idn.view(n * Ho * Wo, c3.cout), relu=True)
+                return out, True
             x = self._conv(f'b{i}c3', y2, blk['c3'], True, residual=idn)
-        return x
+        return x, False
 
     def _host_chunks(self, images):
         """Pinned HOST images -> device chunks, copied on a side stream into two staging buffers so the H2D transfer
@@ -239,11 +251,12 @@ class EncoderRT:
         for i0, img, consumed in chunks:
             n = img.shape[0]
             with ops.PROFILE.range('encoder_trunk', 8.174e9 * n):
-                feat = self.trunk(img.contiguous())
+                feat, has_pool = self.trunk(img.contiguous(), pooled[i0:i0 + n])
             if consumed is not None:
                 consumed.record()                      # the staging buffer may be overwritten by the next-but-one copy
             hw = feat.shape[1] * feat.shape[2]
-            ops.avgpool(feat.view(n, hw, 2048), pooled[i0:i0 + n])
+            if not has_pool:
+                ops.avgpool(feat.view(n, hw, 2048), pooled[i0:i0 + n])
             if self.spatial and hw != 49:
                 raise ValueError(f'spatial features need 224 x 224 images (7 x 7 = 49 tokens for the cross-attention decoder); '
                                  f'got a {feat.shape[1]} x {feat.shape[2]} feature map')

@@ -69,6 +69,7 @@ LSTM_STACK = os.environ.get('DH_NO_LSTM_STACK', '') == ''     # all LSTM layers 
 LSTM_ROTATE = os.environ.get('DH_LSTM_ROTATE', '') != ''      # ... upper layers start on the recurrent half of K (measured: no gain)
 FUSED_PREPARE = os.environ.get('DH_NO_FUSED_PREPARE', '') == ''   # next LSTM step's gathers in the select + beam launch
 DUAL_CONV = os.environ.get('DH_NO_DUAL_CONV', '') == ''       # conv3 + downsample of a stage's first block as one contraction
+FUSED_POOL = os.environ.get('DH_NO_FUSED_POOL', '') == ''       # global average pool in the last conv3's epilogue
 FUSED_VOCAB = os.environ.get('DH_NO_FUSED_VOCAB', '') == ''   # two-pass vocab projection, logits never stored
 
 
@@ -257,6 +258,21 @@ def gemm(A, W, out, bias=None, residual=None, relu=False, tile_n=0):
         LIB.call('dh_gemm_tc', ptr(A), _rows(A), ptr(W), _rows(W), code(A), ptr(bias), ptr(residual),
                  0 if residual is None else _rows(residual), 0 if residual is None else code(residual),
                  ptr(out), _rows(out), code(out), M, N, K, int(relu), tile_n, stream())
+
+
+def gemm_pool(A, W, out, pool, pool_hw, bias=None, residual=None, relu=False):
+    """out = act(A @ W^T + bias + residual) and pool[i] = mean of out's rows [i * pool_hw, (i + 1) * pool_hw) (fp32), one
+    launch (dh_gemm_tc_pool: conv3 of the last bottleneck with the global average pool in its epilogue)."""
+    M, K = A.shape
+    N = W.shape[0]
+    assert W.shape == (N, K) and out.shape == (M, N) and A.dtype == W.dtype == out.dtype and M % pool_hw == 0
+    assert pool.dtype == torch.float32 and pool.shape == (M // pool_hw, N) and pool.stride(1) == 1
+    assert residual is None or (residual.dtype == A.dtype and residual.shape == (M, N))
+    if M == 0:
+        return
+    LIB.call('dh_gemm_tc_pool', ptr(A), _rows(A), ptr(W), _rows(W), code(A), ptr(bias), ptr(residual),
+             0 if residual is None else _rows(residual), ptr(out), _rows(out), M, N, K, int(relu), pool_hw, ptr(pool),
+             _rows(pool), stream())
 
 
 def gemm_split3(A, W, bias, outs):

@@ -83,6 +83,13 @@ int dh_gemm_f32(const float* A, long long lda, const float* W, long long ldw, co
 int dh_gemm_tc(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias,
                const void* residual, long long ldr, int res_dtype, void* C, long long ldc, int out_dtype, int M, int N,
                int K, int relu, int tile_n, cudaStream_t stream);
+/* dh_gemm_tc plus a fused global average pool: pool[i, :] (fp32) = mean of rows [i * pool_hw, (i + 1) * pool_hw) of the
+ * stored C.  The last bottleneck's conv3 + bn3 + identity + ReLU (torchvision resnet.py:154-161) with the
+ * AdaptiveAvgPool2d((1,1)) of encoders.py:39,60 in its epilogue -- the 7x7x2048 map is written once (for the spatial
+ * tokens) and never re-read for the pooled vector.  M % pool_hw == 0, pool_hw <= 128, C / residual of ab_dtype. */
+int dh_gemm_tc_pool(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias,
+                    const void* residual, long long ldr, void* C, long long ldc, int M, int N, int K, int relu,
+                    int pool_hw, float* pool, long long ld_pool, cudaStream_t stream);
 /* One contraction, three destinations: block j (of split_n columns) of A[M,K] W[3*split_n,K]^T + bias goes to Cj with its own
  * leading dimension.  The transformer decode step projects Q, K and V of the new position from the same activation
  * (transformers.py:97-99): W = [fc_q | fc_k | fc_v] stacked along N, C0 = the query buffer, C1 / C2 = this position's rows of

@@ -253,16 +253,25 @@ class Trace:
             lg = (hi[live].log() - lo[live].clamp_min(1e-300).log()) * temperature
             self._abs(float(lg.min()))
 
+    FILTER_WINDOW = 64
+
     def see_filter(self, logits, top_k, unk, B, temperature, q):
-        """Margin of the top-k filter (beam.py:32-37): a flip at the k-th / (k+1)-th logit only changes the outcome if
-        the boundary token can be drawn, i.e. its race score is within the first B+1 of the row."""
-        if logits.shape[-1] <= top_k:
+        """Margin of the top-k filter (beam.py:32-37).  Membership of token j flips when a perturbation of the logits
+        carries it across the filter boundary: a member at rank r < k leaves once the (k+1)-th largest logit overtakes it
+        (distance x_j - x_(k+1)); an outsider enters once it overtakes the k-th largest (distance x_(k) - x_j).  With
+        near-tied logits MANY tokens around rank k are that close, not only the two boundary ones, so every token within
+        FILTER_WINDOW ranks of the boundary is examined.  A flip only changes the outcome if the token can be drawn, i.e.
+        its (hypothetical) race score reaches the first B+1 of the row."""
+        V = logits.shape[-1]
+        if V <= top_k:
             return
-        top = torch.topk(logits, top_k + 1, dim=-1)
+        w = min(V, top_k + self.FILTER_WINDOW)
+        top = torch.topk(logits, w, dim=-1)
         for r in range(logits.shape[0]):
             x = logits[r].double()
+            kth, k1th = top.values[r, top_k - 1].double(), top.values[r, top_k].double()
             fl = x.clone()
-            fl[x < top.values[r, top_k - 1].double()] = NEG_INF
+            fl[x < kth] = NEG_INF
             fl[unk] = NEG_INF
             sc = torch.softmax(fl / temperature, -1)
             z = torch.exp((x - x.max()) / temperature)
@@ -270,14 +279,14 @@ class Trace:
             qq = torch.ones_like(x) if q is None else q[r].double()
             race = sc / qq
             cut = float(torch.topk(race, min(B + 1, race.numel())).values[-1])
-            for j in (top.indices[r, top_k - 1], top.indices[r, top_k]):
-                j = int(j)
-                if j == unk:
-                    continue
-                hyp = float(z[j] / zs / qq[j])                      # its race score if it is (or were) inside the filter
-                if hyp >= cut:
-                    self._abs(float(top.values[r, top_k - 1] - top.values[r, top_k]))
-                    break
+            idx = top.indices[r, max(0, top_k - self.FILTER_WINDOW):]
+            xs = x[idx]
+            inside = xs >= kth
+            dist = torch.where(inside, xs - k1th, kth - xs)
+            hyp = z[idx] / zs / qq[idx]                             # race score if the token is (or were) inside the filter
+            reach = (hyp >= cut) & (idx != unk)
+            if bool(reach.any()):
+                self._abs(float(dist[reach].min()))
 
     def state(self, step, seq, val, ended):
         if self.states is not None:

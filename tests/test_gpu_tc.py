@@ -375,3 +375,49 @@ def test_vocab_logprob_fused_epilogue(rows, V, K_):
     ops.gemm(A, W, logits[:, :V], bias=bias)
     ref = torch.log_softmax(logits[:, :V].double(), dim=-1).gather(1, tg.view(-1, 1)).view(-1)
     assert float((out.double() - ref).abs().max()) < 2e-4 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize('dt', [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize('n,hw,N,K', [(5, 49, 2048, 512), (1, 49, 2048, 512), (4, 49, 256, 64), (7, 49, 320, 192), (3, 64, 512, 128),
+                                      (3, 100, 256, 64), (6, 16, 128, 64), (300, 49, 2048, 512), (2, 128, 256, 64)])
+def test_gemm_pool_equals_gemm_then_avgpool(n, hw, N, K, dt):
+    """dh_gemm_tc_pool (conv3 of the last bottleneck with the global average pool in its epilogue, encoders.py:60) against
+    the two-launch form on the same operands: the stored map and the pooled means are identical bit for bit, and both
+    match a float64 restatement."""
+    M = n * hw
+    A, W, b, r = rnd(M, K, seed=1).to(dt).to(DEV), rnd(N, K, seed=2, scale=0.1).to(dt).to(DEV), rnd(N, seed=3).to(DEV), rnd(M, N, seed=4).to(dt).to(DEV)
+    out = torch.zeros(M, N, dtype=dt, device=DEV)
+    pool = torch.full((n, N), 7.0, device=DEV)
+    ops.gemm_pool(A, W, out, pool, hw, bias=b, residual=r, relu=True)
+    out2 = torch.zeros(M, N, dtype=dt, device=DEV)
+    pool2 = torch.zeros(n, N, device=DEV)
+    ops.gemm(A, W, out2, bias=b, residual=r, relu=True)
+    ops.avgpool(out2.view(n, hw, N), pool2)
+    assert torch.equal(out, out2)
+    assert torch.equal(pool, pool2)
+    ref = F.relu(A.double() @ W.double().T + b.double() + r.double())
+    assert H.rel_err(out.float(), ref.float()) < 4e-3
+    assert H.rel_err(pool, ref.view(n, hw, N).mean(1).float()) < 2e-3
+
+
+def test_encoder_fused_pool_equals_separate_avgpool():
+    """EncoderRT with the pooled epilogue on and off: identical embeddings (the trunk's last launch is the only difference)."""
+    from deephumor_b200 import models
+    from deephumor_b200.utils import synth, synth_weights
+    hp = synth_weights.default_hp('xfmr', 1000, small=True)
+    sd = synth_weights.make_state_dict('xfmr', hp, seed=1)
+    m = models.CaptioningTransformer(**hp)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    m.set_precision('bf16')
+    imgs = synth.images(0, 0, 5).cuda()
+    outs = []
+    for flag in (True, False):
+        ops.FUSED_POOL = flag
+        try:
+            with torch.no_grad():
+                outs.append([t.clone() for t in m.encoder(imgs)])
+        finally:
+            ops.FUSED_POOL = True
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
