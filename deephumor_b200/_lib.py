@@ -39,6 +39,65 @@ class LstmOperands(ctypes.Structure):
                 ('in_off', ctypes.c_int * 8)]
 
 
+class Resnet50Weights(ctypes.Structure):
+    """struct dh_resnet50_weights (include/deephumor_b200.h)."""
+    _fields_ = [('stem_w', ctypes.c_void_p), ('stem_b', ctypes.c_void_p),
+                ('conv_w', (ctypes.c_void_p * 3) * 16), ('conv_b', (ctypes.c_void_p * 3) * 16),
+                ('dual_w', ctypes.c_void_p * 4), ('dual_b', ctypes.c_void_p * 4),
+                ('mean', ctypes.c_float * 3), ('std', ctypes.c_float * 3), ('dtype', ctypes.c_int)]
+
+
+class XfmrLayer(ctypes.Structure):
+    """struct dh_xfmr_layer (include/deephumor_b200.h)."""
+    _fields_ = [('qkv_w', ctypes.c_void_p), ('qkv_b', ctypes.c_void_p),
+                ('so_w', ctypes.c_void_p), ('so_b', ctypes.c_void_p), ('sln_g', ctypes.c_void_p), ('sln_b', ctypes.c_void_p),
+                ('s_scale', ctypes.c_float),
+                ('cq_w', ctypes.c_void_p), ('cq_b', ctypes.c_void_p),
+                ('co_w', ctypes.c_void_p), ('co_b', ctypes.c_void_p), ('cln_g', ctypes.c_void_p), ('cln_b', ctypes.c_void_p),
+                ('c_scale', ctypes.c_float),
+                ('f1_w', ctypes.c_void_p), ('f1_b', ctypes.c_void_p), ('f2_w', ctypes.c_void_p), ('f2_b', ctypes.c_void_p),
+                ('fln_g', ctypes.c_void_p), ('fln_b', ctypes.c_void_p)]
+
+
+XFMR_MAX_LAYERS = 8
+
+
+class XfmrWeights(ctypes.Structure):
+    """struct dh_xfmr_weights (include/deephumor_b200.h)."""
+    _fields_ = [('n_layers', ctypes.c_int), ('D', ctypes.c_int), ('n_heads', ctypes.c_int), ('pf', ctypes.c_int),
+                ('cross', ctypes.c_int), ('dtype', ctypes.c_int), ('pad', ctypes.c_int), ('scale', ctypes.c_float),
+                ('tok', ctypes.c_void_p), ('pos', ctypes.c_void_p), ('ld_tok', ctypes.c_longlong),
+                ('layer', XfmrLayer * XFMR_MAX_LAYERS)]
+
+
+class XfmrBuffers(ctypes.Structure):
+    """struct dh_xfmr_buffers (include/deephumor_b200.h)."""
+    _fields_ = [('x', ctypes.c_void_p), ('qb', ctypes.c_void_p), ('attn', ctypes.c_void_p), ('tmp', ctypes.c_void_p),
+                ('h1', ctypes.c_void_p),
+                ('Kc', ctypes.c_void_p * XFMR_MAX_LAYERS), ('Vc', ctypes.c_void_p * XFMR_MAX_LAYERS),
+                ('xK', ctypes.c_void_p * XFMR_MAX_LAYERS), ('xV', ctypes.c_void_p * XFMR_MAX_LAYERS),
+                ('enc_mask', ctypes.c_void_p), ('start', ctypes.c_void_p), ('ld_start', ctypes.c_longlong),
+                ('seq', ctypes.c_void_p), ('seq_ld', ctypes.c_longlong), ('src', ctypes.c_void_p),
+                ('slots', ctypes.c_int), ('S', ctypes.c_int)]
+
+
+class Ctx:
+    """Opaque dh_ctx* (path-level entries): created lazily, destroyed with the Python object."""
+
+    def __init__(self):
+        self.handle = ctypes.c_void_p()
+        LIB.load()
+        LIB.call('dh_ctx_create', ctypes.byref(self.handle), launches=0)
+        self.keep = []                    # tensors whose device pointers the context holds
+
+    def __del__(self):
+        try:
+            if self.handle:
+                LIB.load().dh_ctx_destroy(self.handle)
+        except Exception:
+            pass
+
+
 def parse_header(path=HEADER):
     """Returns {name: (restype, [argtypes], [argnames])} for every function the header declares."""
     text = open(path).read()
@@ -95,10 +154,11 @@ class _Lib:
     def _header_version(self):
         return int(re.search(r'#define DH_VERSION (\d+)', open(HEADER).read()).group(1))
 
-    def call(self, name, *args):
+    def call(self, name, *args, launches=1):
+        """launches: kernels the entry launches (path-level entries launch many; pure host entries none)."""
         dll = self.load()
         rc = getattr(dll, name)(*args)
-        self.launches += 1
+        self.launches += launches
         if rc != 0:
             msg = dll.dh_last_error().decode(errors='replace')
             kind = 'argument error' if rc < 0 else f'CUDA error {rc}'

@@ -45,7 +45,8 @@ struct TcParams {
   // Vocab-projection epilogues that keep the logits out of HBM (dh_vocab_groupmax / dh_vocab_candidates):
   int n_stride;                           // N blocks visited: 0, n_stride, 2 n_stride, ... (1 except for sampled group maxima)
   int epi_mode;                           // 0: store C; 1: maxima of 32-column groups; 2: compact logits >= thresh[row];
-                                          // 3: LSTM cell; 4: per-group (max, sum exp) + target logit (log-softmax)
+                                          // 3: LSTM cell; 4: per-group (max, sum exp) + target logit (log-softmax);
+                                          // 5: LayerNorm over the full row (both N halves on one CTA)
   float* gsum; const long long* targets; float* tlogit;     // mode 4: [M, ld_gmax], [M] (int64), [M]
   float* gmax; long long ld_gmax;         // [M, ld_gmax] group maxima (mode 1)
   const float* thresh;                    // [M] lower bound of the row's top_k-th largest logit (mode 2)
@@ -79,6 +80,9 @@ struct TcParams {
   // pool_hw rows of each image per column and store their mean (fp32) without a second pass over the feature map.
   int bm_rows;                            // rows of A / C per CTA tile (128 unless pooling)
   int pool_hw; float* pool_out; long long ld_pool;
+  // LayerNorm epilogue (epi_mode 5, dh_gemm_tc_ln): N == 2 * BN, a CTA computes BOTH N halves of its row block into the two
+  // accumulator buffers, its two epilogue groups exchange row sums, and out = LN(A W^T + bias + residual) * gamma + beta
+  const float* ln_gamma; const float* ln_beta; float ln_eps;
 };
 
 // ------------------------------------------------------------------------------------------- PTX wrappers
@@ -207,6 +211,31 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tc_ld32_nw(uint32_t taddr, uint32_t* v) {   // no wait: pair with tc_wait_ld()
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+// Packed fp32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100a): two IEEE fp32 operations per issued instruction
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ f32x2 pk2u(uint32_t a, uint32_t b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ void un2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -265,14 +294,19 @@ __device__ __forceinline__ uint32_t umma_idesc(int bn, int ab_dtype, int m = BM)
 // PAIR: two CTAs of a cluster (one TPC) run ONE tcgen05.mma.cta_group::2 of M = 256: each CTA stages its own 128 A rows and
 // HALF of the W tile (BN/2 rows) and owns the accumulator of its 128 rows -- a third less operand traffic per FLOP from L2,
 // which is what bounds these contractions (profiles/: ~12 TB/s chip-wide TMA ceiling).
-template <int BN, bool PAIR = false>
+template <int BN, bool PAIR = false, int EPI = 0>
 struct Cfg {
   static constexpr int kStageBytes = (BM + (PAIR ? BN / 2 : BN)) * BK * 2;
-  static constexpr int kStages = kSmemBudget / kStageBytes;
+  // LayerNorm mode gives up ring stages for its parameter block (5 x 32 KB stages as a pair, 3 x 48 KB alone)
+  static constexpr int kStages = EPI == 5 ? (PAIR ? 5 : 3) : kSmemBudget / kStageBytes;
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kStagingBytes = 2 * BM * 128;   // two 128-row x 128 B slabs (TMA store) / transpose scratch
   static constexpr int kBiasBytes = 1024;              // bias slice of the current tile (BN <= 256 floats)
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStagingBytes + kBiasBytes + 256;
+  // LayerNorm mode: bias | gamma | beta of the whole 2 BN-wide row (fp32) + double-buffered per-row (mean, M2) partials of
+  // the two column halves
+  static constexpr int kLnBytes = EPI == 5 ? 3 * 2 * BN * 4 + 2 * 2 * BM * 2 * 4 : 0;
+  static constexpr int kLnOff = kStages * kStageBytes + kStagingBytes + kBiasBytes + 256;
+  static constexpr int kSmemBytes = 1024 + kLnOff + kLnBytes;
 };
 
 // EPI = TcParams::epi_mode as a compile-time constant: every epilogue is its own kernel (named in profiles, no dead code)
@@ -281,7 +315,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
                const __grid_constant__ CUtensorMap map_i, const TcParams p) {
-  using C = Cfg<BN, PAIR>;
+  using C = Cfg<BN, PAIR, EPI>;
   constexpr int CG = PAIR ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -329,7 +363,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), (EPI ? 8 : 4) * CG);   // the leader's barrier collects both CTAs' epilogue warps
+      mbar_init(tempty_bar(s), ((EPI && EPI != 5) ? 8 : 4) * CG);   // LayerNorm mode: one group drains each buffer   // the leader's barrier collects both CTAs' epilogue warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 2) {
@@ -354,6 +388,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int tiles = p.m_blocks * p.n_blocks * ((EPI == 3 && p.layers > 1) ? p.layers : 1);
   const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tstride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  // virtual tile sequence of this CTA (pair): tile_of(0), tile_of(1), ... until >= tiles.  LayerNorm mode walks ROW BLOCKS with
+  // the stride and visits both N halves of a block back to back (accumulator buffer = half)
+  auto tile_of = [&](int it) { return EPI == 5 ? 2 * (tile0 + (it >> 1) * tstride) + (it & 1) : tile0 + it * tstride; };
   auto tile_m0 = [&](int tile) { return (tile / p.n_blocks) * (p.bm_rows * CG) + (int)cta_rank * p.bm_rows; };
 
   if (warp == 0) {
@@ -361,7 +398,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // ===================================================================== TMA producer
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = tile0; tile < tiles; tile += tstride) {
+      for (int it = 0, tile; (tile = tile_of(it)) < tiles; ++it) {
         int layer = 0, rt = tile;                                // EPI 3: layer-major tile order of a stacked LSTM step
         if (EPI == 3 && p.layers > 1) { layer = tile / p.tiles_per_layer; rt = tile - layer * p.tiles_per_layer; }
         const int m0 = tile_m0(rt), n0 = ((rt % p.n_blocks) * p.n_stride + p.n_offset) * BN;
@@ -446,8 +483,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t idesc64 = umma_idesc(64, p.ab_dtype, BM);
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int tile = tile0; tile < tiles; tile += tstride, ++it) {
+      for (int it = 0, tile; (tile = tile_of(it)) < tiles; ++it) {
         const int as = it & 1;
         mbar_wait(tempty_bar(as), ((it >> 1) & 1) ^ 1u, p.error, 2);
         tc_fence_after();
@@ -487,8 +523,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // each thread owns one row: c = sig(f) c_prev[parent] + sig(i) tanh(g), h = sig(o) tanh(c) (nn.LSTM gate order).
       if (BN == 256) {
         const int row_l = ew * 32 + lane;
-        int it = 0;
-        for (int tile = tile0; tile < tiles; tile += tstride, ++it) {
+        for (int it = 0, tile; (tile = tile_of(it)) < tiles; ++it) {
           int layer = 0, rt = tile;
           if (p.layers > 1) { layer = tile / p.tiles_per_layer; rt = tile - layer * p.tiles_per_layer; }
           const int m0 = tile_m0(rt), n0 = ((rt % p.n_blocks) * p.n_stride + p.n_offset) * BN;
@@ -630,11 +665,122 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
       }
+    } else if (EPI == 5) {
+      // ---- LayerNorm epilogue (transformers.py:355-356,365-366,374-375: x = LN(x + sublayer(x))): accumulator buffer `eh`
+      // holds columns [eh * BN, (eh + 1) * BN) of the row block (bias still to add; the residual already rode the tensor
+      // core).  A thread owns one row of its half and makes TWO passes over tensor memory, 64 columns per wait, in packed
+      // fp32 pairs (FADD2 / FFMA2): (1) sum and squared deviations about a pivot (the half's first element), turned into the
+      // half's (mean, M2) and merged with the other half's by the pairwise-variance formula -- as accurate as a two-pass
+      // variance; (2) normalise, scale, shift, round, slab, TMA store.  bias / gamma / beta sit in shared memory.
+      const int row_l = ew * 32 + lane;
+      float* lnp = reinterpret_cast<float*>(gen_base + C::kLnOff);          // [3][2 BN]: bias | gamma | beta
+      float* part = lnp + 3 * 2 * BN;                                       // [2 buffers][2 halves][BM][2]
+      const uint32_t slab = base + C::kStages * C::kStageBytes + (uint32_t)eh * (BM * 128);
+      const uint32_t srow = slab + (uint32_t)row_l * 128u;
+      const uint32_t swz = (uint32_t)(row_l & 7);
+      const bool elected = (ew == 0 && lane == 0);
+      const int bar_half = 2 + eh;                                // named barrier of this half's 128 threads
+      const int nh = eh * BN;                                     // first column of this half
+      for (int i = etid; i < 2 * BN; i += 256) {
+        lnp[i] = p.bias ? __ldg(p.bias + i) : 0.f;
+        lnp[2 * BN + i] = __ldg(p.ln_gamma + i);
+        lnp[4 * BN + i] = __ldg(p.ln_beta + i);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float2* bias2 = reinterpret_cast<const float2*>(lnp + nh);
+      const float2* gam2 = reinterpret_cast<const float2*>(lnp + 2 * BN + nh);
+      const float2* bet2 = reinterpret_cast<const float2*>(lnp + 4 * BN + nh);
+      for (int i = 0, tile; (tile = tile_of(2 * i + eh)) < tiles; ++i) {
+        const int m0 = tile_m0(tile);
+        mbar_wait(tfull_bar(eh), i & 1, p.error, 4);
+        tc_fence_after();
+        const uint32_t tmem_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(eh * BN);
+        f32x2 s_a = pk2(0.f, 0.f), s_b = s_a, q_a = s_a, q_b = s_a, negp = s_a;
+        float pivot = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c) {
+          uint32_t v[64];
+          tc_ld32_nw(tmem_row + (uint32_t)(c * 64), v);
+          tc_ld32_nw(tmem_row + (uint32_t)(c * 64 + 32), v + 32);
+          tc_wait_ld();
+          if (c == 0) {
+            pivot = __uint_as_float(v[0]) + bias2[0].x;
+            negp = pk2(-pivot, -pivot);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float2 b0 = bias2[c * 32 + j], b1 = bias2[c * 32 + j + 1];
+            const f32x2 d0 = add2(add2(pk2u(v[2 * j], v[2 * j + 1]), pk2(b0.x, b0.y)), negp);
+            const f32x2 d1 = add2(add2(pk2u(v[2 * j + 2], v[2 * j + 3]), pk2(b1.x, b1.y)), negp);
+            s_a = add2(s_a, d0); q_a = fma2(d0, d0, q_a);
+            s_b = add2(s_b, d1); q_b = fma2(d1, d1, q_b);
+          }
+        }
+        float s0, s1, q0, q1;
+        un2(add2(s_a, s_b), s0, s1);
+        un2(add2(q_a, q_b), q0, q1);
+        const float sh = s0 + s1, qh = q0 + q1;
+        float* pp = part + (size_t)(i & 1) * (2 * BM * 2);
+        pp[(eh * BM + row_l) * 2] = pivot + sh * (1.f / (float)BN);                 // mean of this half
+        pp[(eh * BM + row_l) * 2 + 1] = qh - sh * sh * (1.f / (float)BN);           // sum of squared deviations about it
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float m_0 = pp[row_l * 2], M_0 = pp[row_l * 2 + 1], m_1 = pp[(BM + row_l) * 2], M_1 = pp[(BM + row_l) * 2 + 1];
+        const float mean = 0.5f * (m_0 + m_1);
+        const float var = (M_0 + M_1 + (m_0 - m_1) * (m_0 - m_1) * (0.5f * (float)BN)) * (1.f / (float)(2 * BN));
+        const float rstd = rsqrtf(fmaxf(var, 0.f) + p.ln_eps);
+        const f32x2 rr = pk2(rstd, rstd), negm = pk2(-mean, -mean);
+#pragma unroll 1
+        for (int rd = 0; rd < BN / 64; ++rd) {
+          // one slab per half: the previous round's TMA store must have read it before it is rewritten
+          if (elected) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          uint32_t v[64];
+          tc_ld32_nw(tmem_row + (uint32_t)(rd * 64), v);
+          tc_ld32_nw(tmem_row + (uint32_t)(rd * 64 + 32), v + 32);
+          tc_wait_ld();
+          if (rd == BN / 64 - 1) {
+            // the accumulator half now lives in registers: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar(eh), 0)); else mbar_arrive(tempty_bar(eh)); }
+          }
+          uint32_t w[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float2 b0 = bias2[rd * 32 + j], g0 = gam2[rd * 32 + j], e0 = bet2[rd * 32 + j];
+            const f32x2 a = mul2(rr, pk2(g0.x, g0.y));
+            const f32x2 k = fma2(add2(pk2(b0.x, b0.y), negm), a, pk2(e0.x, e0.y));
+            float y0, y1;
+            un2(fma2(pk2u(v[2 * j], v[2 * j + 1]), a, k), y0, y1);
+            if (p.out_dtype == DH_BF16) {
+              __nv_bfloat162 t = __floats2bfloat162_rn(y0, y1);
+              w[j] = *reinterpret_cast<uint32_t*>(&t);
+            } else {
+              __half2 t = __floats2half2_rn(y0, y1);
+              w[j] = *reinterpret_cast<uint32_t*>(&t);
+            }
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_half) : "memory");      // the slab is free (elected waited above)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (((uint32_t)j ^ swz) << 4)),
+                         "r"(w[4 * j]), "r"(w[4 * j + 1]), "r"(w[4 * j + 2]), "r"(w[4 * j + 3])
+                         : "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_half) : "memory");
+          if (elected) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(&map_c)),
+                         "r"(slab), "r"(nh + rd * 64), "r"(m0)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      }
+      if (elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else if (EPI) {
       // ---- selection epilogues: every thread owns one accumulator row; nothing of the [M,N] product is stored.
       const int row_l = ew * 32 + lane;
-      int it = 0;
-      for (int tile = tile0; tile < tiles; tile += tstride, ++it) {
+      for (int it = 0, tile; (tile = tile_of(it)) < tiles; ++it) {
         const int m0 = tile_m0(tile), n0 = ((tile % p.n_blocks) * p.n_stride + p.n_offset) * BN;
         const int as = it & 1;
         const long long row = (long long)m0 + row_l;
@@ -735,8 +881,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t swz = (uint32_t)(row_l & 7);
       const bool elected = (warp == 4 && lane == 0);
       uint32_t round_ctr = 0;
-      int it = 0, last_n0 = -1;
-      for (int tile = tile0; tile < tiles; tile += tstride, ++it) {
+      int last_n0 = -1;
+      for (int it = 0, tile; (tile = tile_of(it)) < tiles; ++it) {
         const int m0 = tile_m0(tile), n0 = ((tile % p.n_blocks) * p.n_stride + p.n_offset) * BN;
         const int as = it & 1;
         // bias slice of this tile -> smem, only when the N block changed, and before the wait on the accumulator so the
@@ -853,8 +999,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     float* st = staging + ew * 32 * kStageLd;
     const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
     const bool res_vec = p.res && (p.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0);
-    int it = 0;
-    for (int tile = tile0; tile < tiles; tile += tstride, ++it) {
+    for (int it = 0, tile; (tile = tile_of(it)) < tiles; ++it) {
       const int m0 = tile_m0(tile), n0 = ((tile % p.n_blocks) * p.n_stride + p.n_offset) * BN;
       const int as = it & 1;
       mbar_wait(tfull_bar(as), (it >> 1) & 1, p.error, 4);
@@ -1027,7 +1172,7 @@ int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long col
 template <int BN, bool PAIR, int EPI>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mr, const CUtensorMap& mi,
            TcParams& p, cudaStream_t s) {
-  using C = Cfg<BN, PAIR>;
+  using C = Cfg<BN, PAIR, EPI>;
   static bool attr = false;
   if (!attr) {
     DH_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, PAIR, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
@@ -1039,7 +1184,8 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, 
   p.m_blocks = dh_cdiv(p.M, PAIR ? 2 * p.bm_rows : p.bm_rows);
   p.tiles_per_layer = p.m_blocks * p.n_blocks;
   p.mb128 = dh_cdiv(p.M, BM);
-  const int tiles = p.tiles_per_layer * ((EPI == 3 && p.layers > 1) ? p.layers : 1);
+  // LayerNorm mode schedules ROW BLOCKS (each CTA / pair runs both N halves of a block)
+  const int tiles = EPI == 5 ? p.m_blocks : p.tiles_per_layer * ((EPI == 3 && p.layers > 1) ? p.layers : 1);
   if (p.res_chunks) p.res_chunks = BN / BK;
   if (PAIR) {
     const int pairs = g_num_sms / 2;
@@ -1103,7 +1249,7 @@ int dispatch(const CUtensorMap& ma, const void* W, long long ldw, TcParams& p, i
   const bool res_ok = !p.res || (p.res_dtype == p.ab_dtype && (uintptr_t)p.res % 16 == 0 && (p.ldr * 2) % 16 == 0);
   p.tma_store = 0;
   p.res_chunks = 0;
-  if (p.epi_mode) {
+  if (p.epi_mode && p.epi_mode != 5) {
     // selection epilogues store nothing of C
   } else if (out_ok && res_ok) {
     rc = make_map_2d(&mc, p.out, p.M, p.split_n ? p.split_n : p.N, p.ldc, bm_rows, p.out_dtype);
@@ -1123,6 +1269,9 @@ int dispatch(const CUtensorMap& ma, const void* W, long long ldw, TcParams& p, i
     case 1: return launch_bn<1>(ma, mb, mc, mr, mi, p, bn, pair, s);
     case 2: return launch_bn<2>(ma, mb, mc, mr, mi, p, bn, pair, s);
     case 3: return launch_bn<3>(ma, mb, mc, mr, mi, p, bn, pair, s);
+    case 5:
+      if (!p.tma_store) return dh_fail(DH_ERR_ARG, "LayerNorm epilogue needs 16-byte aligned output / residual rows", __FILE__, __LINE__);
+      return pair ? launch<256, true, 5>(ma, mb, mc, mr, mi, p, s) : launch<256, false, 5>(ma, mb, mc, mr, mi, p, s);
     default: return launch_bn<4>(ma, mb, mc, mr, mi, p, bn, pair, s);
   }
 }
@@ -1184,6 +1333,35 @@ extern "C" int dh_gemm_tc_pool(const void* A, long long lda, const void* W, long
   rc = dispatch(ma, W, ldw, p, N % 256 == 0 ? 256 : N % 128 == 0 ? 128 : 64, stream);
   if (rc) return rc;
   return p.tma_store ? DH_OK : dh_fail(DH_ERR_ARG, "pooled epilogue needs the TMA-store path", __FILE__, __LINE__);
+}
+
+// out = LayerNorm(A W^T + bias + residual) * gamma + beta over rows of N == 512 columns: the post-LN sublayer tail of a decoder
+// layer (models/transformers.py:355-356,365-366,374-375 -- fc_o / fc_2, dropout (eval: identity), residual add, nn.LayerNorm)
+// in ONE launch: a CTA (pair) holds the whole row block in its two accumulator buffers, so the pre-norm sums are never stored.
+// out may alias residual (each row block is read through TMA before its own stores are issued and no other CTA touches it).
+extern "C" int dh_gemm_tc_ln(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias,
+                             const void* residual, long long ldr, const float* gamma, const float* beta, float eps, void* out,
+                             long long ldc, int M, int N, int K, cudaStream_t stream) {
+  DH_ARG(A && W && out && gamma && beta && M >= 0 && K > 0 && N == 512 && eps > 0.f);
+  DH_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0 && (!residual || ldr % 8 == 0));
+  DH_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)residual % 16) == 0);
+  DH_ARG(((uintptr_t)bias % 16) == 0 && ((uintptr_t)gamma % 16) == 0 && ((uintptr_t)beta % 16) == 0);
+  DH_ARG(ab_dtype == DH_BF16 || ab_dtype == DH_F16);
+  if (M == 0) return DH_OK;
+  int rc = tc_init();
+  if (rc) return rc;
+  TcParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.k_chunks = dh_cdiv(K, BK);
+  p.ab_dtype = ab_dtype;
+  p.bias = bias; p.res = residual; p.ldr = ldr; p.res_dtype = ab_dtype;
+  p.out = out; p.ldc = ldc; p.out_dtype = ab_dtype;
+  p.epi_mode = 5;
+  p.ln_gamma = gamma; p.ln_beta = beta; p.ln_eps = eps;
+  CUtensorMap ma;
+  rc = make_map_2d(&ma, A, M, K, lda, BM, ab_dtype);
+  if (rc) return rc;
+  return dispatch(ma, W, ldw, p, 256, stream);
 }
 
 // One contraction, three destinations: [C0 | C1 | C2][M, 3 * split_n] = A[M,K] * W[3 * split_n, K]^T + bias, block j of

@@ -382,8 +382,8 @@ __global__ void __launch_bounds__(kThrWarps * 32) vocab_threshold_kernel(const f
 // Warp-level selection from a row's SPARSELY MATERIALISED logits (written by dh_vocab_candidates): the hit map names the
 // 32-column groups that hold at least one logit >= thresh[row]; their 128-byte lines are gathered (one lane per group, eight
 // 16-byte loads in flight per lane), filtered against the threshold, and the exact top_k-th largest value (ties kept, Q3) is
-// taken from that candidate list.  Survivors are sorted by column so every floating-point reduction is run-to-run
-// deterministic; then softmax(l/T), the Exp(1)-race draw of B ids and the log_softmax scores over the picks
+// taken from that candidate list.  Candidates and survivors stay in column order, so every floating-point reduction is
+// run-to-run deterministic; then softmax(l/T), the Exp(1)-race draw of B ids and the log_softmax scores over the picks
 // (models/beam.py:32-53,79).
 constexpr int kCandCap = 512;    // candidates (logits >= thresh) a warp can rank
 constexpr int kSurvMax = 160;    // survivors (logits >= the exact top_k-th largest): top_k <= 64 plus ties
@@ -431,19 +431,22 @@ __device__ void warp_select(const SelParams& p, int r, int img, const VocabSpars
   constexpr int kGroupCap = 3 * kSurvMax;
   const unsigned char* hm = vs.hitmap + (long long)r * vs.hit_ld;
   int ng = 0;
-  for (int b0 = 0; b0 < vs.n_bytes; b0 += 32) {
-    const int bi = b0 + lane;
-    unsigned int byte = bi < vs.n_bytes ? (unsigned int)__ldg(hm + bi) : 0u;
-    const int mine = __popc(byte);
-    int off = mine;                                          // exclusive prefix over the lanes
+  for (int b0 = 0; b0 < vs.n_bytes; b0 += 128) {             // four map bytes per lane and round, all loads in flight
+    const int bi = b0 + 4 * lane;
+    unsigned int word = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (bi + k < vs.n_bytes) word |= (unsigned int)__ldg(hm + bi + k) << (8 * k);
+    const int mine = __popc(word);
+    int off = mine;                                          // inclusive prefix over the lanes
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, off, o); if (lane >= o) off += t; }
     const int tot = __shfl_sync(0xffffffffu, off, 31);
     int pos = ng + off - mine;
-    while (byte) {
-      const int bit = __ffs(byte) - 1;
-      byte &= byte - 1u;
-      if (pos < kGroupCap) glist[pos] = bi * vs.groups_per_byte + bit;
+    while (word) {
+      const int bit = __ffs(word) - 1;
+      word &= word - 1u;
+      if (pos < kGroupCap) glist[pos] = (bi + (bit >> 3)) * vs.groups_per_byte + (bit & 7);
       ++pos;
     }
     ng += tot;
@@ -452,30 +455,44 @@ __device__ void warp_select(const SelParams& p, int r, int img, const VocabSpars
     if (lane == 0) atomicOr(p.status, DH_STATUS_TOO_MANY_TIES);
     ng = kGroupCap;
   }
-  if (lane == 0) *w.counter = 0;
   __syncwarp();
-  // ---- phase B: one lane per group: its 32 logits as eight independent 16-byte loads, hits appended through a shared-memory
-  // counter (the list order is irrelevant: the threshold is order-free and the survivors are sorted by column below)
+  // ---- phase B: one lane per group (eight independent 16-byte loads in flight): the 32 logits of a group are compared
+  // with the threshold into a bit mask without branching, the masks' population counts are prefix-summed over the warp and
+  // every lane appends the COLUMNS of its (few) hits at its own offset -- no atomics, and the list comes out in column
+  // order.  The hit values are fetched afterwards, one independent load per candidate (the lines are in L1 / L2).
   const float* lrow = vs.logits + (long long)r * vs.ld;
-  for (int i = lane; i < ng; i += 32) {
-    const int col0 = glist[i] * 32;
-    float4 v[8];
+  int nc = 0;
+  for (int i0 = 0; i0 < ng; i0 += 32) {
+    const int i = i0 + lane;
+    unsigned int mask = 0u;
+    int col0 = 0;
+    if (i < ng) {
+      col0 = glist[i] * 32;
+      float4 v[8];
 #pragma unroll
-    for (int g = 0; g < 8; ++g) v[g] = __ldg(reinterpret_cast<const float4*>(lrow + col0) + g);
+      for (int g = 0; g < 8; ++g) v[g] = __ldg(reinterpret_cast<const float4*>(lrow + col0) + g);
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const float x4[4] = {v[g].x, v[g].y, v[g].z, v[g].w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (x4[e] >= t0) {
-          const int slot = atomicAdd(w.counter, 1);
-          if (slot < kCandCap) { w.c_idx[slot] = col0 + 4 * g + e; w.c_val[slot] = x4[e]; }
-        }
+      for (int g = 0; g < 8; ++g) {
+        mask |= (v[g].x >= t0 ? 1u : 0u) << (4 * g) | (v[g].y >= t0 ? 1u : 0u) << (4 * g + 1) |
+                (v[g].z >= t0 ? 1u : 0u) << (4 * g + 2) | (v[g].w >= t0 ? 1u : 0u) << (4 * g + 3);
       }
     }
+    const int mine = __popc(mask);
+    int off = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, off, o); if (lane >= o) off += t; }
+    const int tot = __shfl_sync(0xffffffffu, off, 31);
+    int pos = nc + off - mine;
+    while (mask) {
+      const int bit = __ffs(mask) - 1;
+      mask &= mask - 1u;
+      if (pos < kCandCap) w.c_idx[pos] = col0 + bit;
+      ++pos;
+    }
+    nc += tot;
   }
   __syncwarp();
-  int nc = *w.counter;
+  for (int c = lane; c < min(nc, kCandCap); c += 32) w.c_val[c] = __ldg(lrow + w.c_idx[c]);
   __syncwarp();
   if (nc > kCandCap) {
     if (lane == 0) atomicOr(p.status, DH_STATUS_TOO_MANY_TIES);
@@ -522,12 +539,11 @@ __device__ void warp_select(const SelParams& p, int r, int img, const VocabSpars
   }
   int* a_idx = w.c_idx;                            // the candidate arrays are free again: sorted survivors
   float* a_val = w.c_val;
-  for (int c = lane; c < ns; c += 32) {          // sort by column (ids are distinct)
-    const int id = w.t_idx[c];
-    int pos = 0;
-    for (int j = 0; j < ns; ++j) pos += w.t_idx[j] < id;
-    a_idx[pos] = id;
-    a_val[pos] = w.t_val[c];
+  // the gather phase lists the candidates in column order and the compaction keeps it: the survivors are already sorted by
+  // column, which is what makes every floating-point reduction below run-to-run deterministic
+  for (int c = lane; c < ns; c += 32) {
+    a_idx[c] = w.t_idx[c];
+    a_val[c] = w.t_val[c];
   }
   __syncwarp();
   // ---- softmax(l / T) over survivors (everything else has p == 0 exactly), noise, B rounds of arg-max
@@ -753,7 +769,7 @@ struct LstmNext {
   const uint16_t* hs[8]; uint16_t* A[8]; long long lda[8]; int in_off[8];
 };
 
-__global__ void __launch_bounds__(32 * kMaxBeam) select_beam_kernel(SelParams p, VocabSparse vs, int do_beam,
+__global__ void __launch_bounds__(32 * kMaxBeam, 2) select_beam_kernel(SelParams p, VocabSparse vs, int do_beam,
                                                                    BeamState st, StepParams sp, LstmNext nx) {
   extern __shared__ int dyn_smem[];
   const int img = blockIdx.x, warp = threadIdx.x >> 5;
@@ -777,23 +793,42 @@ __global__ void __launch_bounds__(32 * kMaxBeam) select_beam_kernel(SelParams p,
   if (nx.L == 0) return;
   // ---- next LSTM step's operands for this image's rows: 16-byte copies by the whole CTA
   __syncthreads();                                   // last_tok / parent_state of the image (written by warp 0) are visible
+  // (row token / parent are fetched once into shared memory; then four independent 16-byte copies are in flight per thread)
+  __shared__ int s_tok[kMaxBeam], s_par[kMaxBeam];
+  if (threadIdx.x < p.rpi) {
+    s_tok[threadIdx.x] = st.last_tok[(long long)img * p.rpi + threadIdx.x];
+    s_par[threadIdx.x] = st.parent_state[(long long)img * p.rpi + threadIdx.x];
+  }
+  __syncthreads();
   const int ce = nx.E / 8, ch = nx.H / 8, per_row = ce + nx.L * ch;
-  for (int i = threadIdx.x; i < p.rpi * per_row; i += blockDim.x) {
-    const int b = i / per_row;
-    int c = i - b * per_row;
-    const long long row = (long long)img * p.rpi + b;
-    if (c < ce) {
-      const long long t = st.last_tok[row];
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (t >= 0 && t < nx.n_tok_rows) v = *reinterpret_cast<const uint4*>(nx.table + t * nx.ldt + c * 8);
-      *reinterpret_cast<uint4*>(nx.A[0] + row * nx.lda[0] + c * 8) = v;
-    } else {
-      c -= ce;
-      const int l = c / ch, cc = c - l * ch;
-      const long long pr = st.parent_state[row];
-      *reinterpret_cast<uint4*>(nx.A[l] + row * nx.lda[l] + nx.in_off[l] + cc * 8) =
-          *reinterpret_cast<const uint4*>(nx.hs[l] + pr * nx.H + cc * 8);
+  const int total = p.rpi * per_row;
+  for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
+    uint4 v[4];
+    uint4* dst[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      dst[u] = nullptr;
+      v[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (i < total) {
+        const int b = i / per_row;
+        int c = i - b * per_row;
+        const long long row = (long long)img * p.rpi + b;
+        if (c < ce) {
+          const long long t = s_tok[b];
+          dst[u] = reinterpret_cast<uint4*>(nx.A[0] + row * nx.lda[0] + c * 8);
+          if (t >= 0 && t < nx.n_tok_rows) v[u] = __ldg(reinterpret_cast<const uint4*>(nx.table + t * nx.ldt + c * 8));
+        } else {
+          c -= ce;
+          const int l = c / ch, cc = c - l * ch;
+          dst[u] = reinterpret_cast<uint4*>(nx.A[l] + row * nx.lda[l] + nx.in_off[l] + cc * 8);
+          v[u] = *reinterpret_cast<const uint4*>(nx.hs[l] + (long long)s_par[b] * nx.H + cc * 8);
+        }
+      }
     }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (dst[u]) *dst[u] = v[u];
   }
 }
 

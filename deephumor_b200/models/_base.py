@@ -65,6 +65,17 @@ class RTModule(nn.Module):
             cache[k] = build(PRECISIONS[self.precision], self._device())
         return cache[k]
 
+    @staticmethod
+    def preprocess(images, size=224):
+        """The reference's image transform up to ToTensor (deephumor_demo.ipynb cell 11: `Resize((224, 224))` on PIL
+        images; data/datasets.py:48-53,94-98) on the device, bit-exact with Pillow: a list of PIL images or uint8 [H,W,3]
+        RGB arrays of any sizes -> uint8 [n,3,size,size] (NCHW) on the current CUDA device.  Pass the result to
+        `generate` / `forward` / `perplexity`: ToTensor + Normalize are fused into the stem kernel."""
+        import numpy as np
+        from ..runtime import ops
+        arrs = [np.asarray(im.convert('RGB')) if hasattr(im, 'convert') else im for im in images]
+        return ops.resize_images(arrs, size)
+
     def set_precision(self, precision):
         assert precision in PRECISIONS
         self.precision = precision

@@ -159,6 +159,14 @@ class EncoderRT:
         """images [n,3,224,224] fp32 NCHW (device) -> features [n,7,7,2048] NHWC in the trunk storage dtype.
         pooled (fp32 [n,2048], optional) receives the global average pool; returns (features, pooled_written)."""
         n, _, H, W = images.shape
+        if (ops.PATH_ENTRIES and self.tdtype != torch.float32 and H == 224 and W == 224 and ops.FUSED_STEM and ops.DUAL_CONV
+                and ops.HALO_CONV and ops.FUSED_POOL and images.dtype in (torch.uint8, torch.float32)):
+            # the whole trunk (+ pooled epilogue) behind one path-level C entry: dh_resnet50_forward
+            if getattr(self, '_ctx', None) is None:
+                self._ctx = ops.resnet50_ctx(self)
+            feat = self._buf('feat', (n, 7, 7, 2048))
+            ops.resnet50_forward(self._ctx, images, feat, pooled, lambda nb: self._buf('trunk_ws', (nb,), torch.uint8))
+            return feat, pooled is not None
         if images.dtype == torch.uint8:
             if self.tdtype != torch.float32 and H == 224 and W == 224 and ops.FUSED_STEM:
                 x = self._buf('pool', (n, 56, 56, 64))

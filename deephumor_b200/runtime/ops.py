@@ -7,7 +7,8 @@ import os
 
 import torch
 
-from .._lib import LIB, BeamState, LstmOperands, VocabSparse, ptr, stream
+from .._lib import (LIB, BeamState, Ctx, LstmOperands, Resnet50Weights, VocabSparse, XfmrBuffers, XfmrLayer, XfmrWeights,
+                    ptr, stream)
 
 F32, BF16, F16 = 0, 1, 2
 NOISE = {'deterministic': 0, 'injected': 1}
@@ -69,6 +70,8 @@ LSTM_STACK = os.environ.get('DH_NO_LSTM_STACK', '') == ''     # all LSTM layers 
 LSTM_ROTATE = os.environ.get('DH_LSTM_ROTATE', '') != ''      # ... upper layers start on the recurrent half of K (measured: no gain)
 FUSED_PREPARE = os.environ.get('DH_NO_FUSED_PREPARE', '') == ''   # next LSTM step's gathers in the select + beam launch
 DUAL_CONV = os.environ.get('DH_NO_DUAL_CONV', '') == ''       # conv3 + downsample of a stage's first block as one contraction
+PATH_ENTRIES = os.environ.get('DH_NO_PATH_ENTRIES', '') == ''   # trunk / decoder step through the path-level C entries
+FUSED_LN = os.environ.get('DH_NO_FUSED_LN', '') == ''           # LayerNorm + residual in the fc_o / fc_2 contraction's epilogue
 FUSED_POOL = os.environ.get('DH_NO_FUSED_POOL', '') == ''       # global average pool in the last conv3's epilogue
 FUSED_VOCAB = os.environ.get('DH_NO_FUSED_VOCAB', '') == ''   # two-pass vocab projection, logits never stored
 
@@ -273,6 +276,25 @@ def gemm_pool(A, W, out, pool, pool_hw, bias=None, residual=None, relu=False):
     LIB.call('dh_gemm_tc_pool', ptr(A), _rows(A), ptr(W), _rows(W), code(A), ptr(bias), ptr(residual),
              0 if residual is None else _rows(residual), ptr(out), _rows(out), M, N, K, int(relu), pool_hw, ptr(pool),
              _rows(pool), stream())
+
+
+def gemm_ln_supported(x, N):
+    return FUSED_LN and x.dtype in (torch.bfloat16, torch.float16) and N == 512
+
+
+def gemm_ln(A, W, bias, residual, gamma, beta, out, eps=1e-5):
+    """out = LayerNorm(A @ W^T + bias + residual) * gamma + beta for N == 512 in one launch (dh_gemm_tc_ln); out may be the
+    residual buffer itself."""
+    M, K = A.shape
+    N = W.shape[0]
+    assert W.shape == (N, K) and out.shape == (M, N) and A.dtype == W.dtype == out.dtype and N == 512
+    assert residual is None or (residual.dtype == A.dtype and residual.shape == (M, N))
+    assert gamma.dtype == beta.dtype == torch.float32 and gamma.numel() == beta.numel() == N
+    if M == 0:
+        return
+    LIB.call('dh_gemm_tc_ln', ptr(A), _rows(A), ptr(W), _rows(W), code(A), ptr(bias), ptr(residual),
+             0 if residual is None else _rows(residual), ptr(gamma), ptr(beta), float(eps), ptr(out), _rows(out), M, N, K,
+             stream())
 
 
 def gemm_split3(A, W, bias, outs):
@@ -595,3 +617,123 @@ def token_logprob(logits, targets, out):
     rows, V = logits.shape
     assert logits.dtype == torch.float32 and targets.dtype == torch.int64
     LIB.call('dh_token_logprob', ptr(logits), _rows(logits), rows, V, ptr(targets), ptr(out), stream())
+
+
+def resize_images(images, out_size=224):
+    """torchvision `Resize((out_size, out_size))` of PIL RGB images on the device (dh_resize_bilinear_u8, bit-exact with
+    Pillow): images = list of uint8 HWC arrays / tensors of different sizes -> uint8 [n,3,out_size,out_size] NCHW on the
+    current device (the input format of the fused uint8 stem).  One pinned staging copy, three launches."""
+    import ctypes
+    import numpy as np
+    n = len(images)
+    dev = torch.device('cuda', torch.cuda.current_device())
+    out = torch.empty(n, 3, out_size, out_size, dtype=torch.uint8, device=dev)
+    if n == 0:
+        return out
+    ts = [torch.as_tensor(np.ascontiguousarray(im)) if not torch.is_tensor(im) else im.contiguous() for im in images]
+    for t in ts:
+        if t.dtype != torch.uint8 or t.dim() != 3 or t.shape[2] != 3:
+            raise ValueError('resize_images expects uint8 images of shape [H, W, 3] (RGB, as PIL.Image.convert("RGB") gives)')
+    hs, ws = [int(t.shape[0]) for t in ts], [int(t.shape[1]) for t in ts]
+    offs, total = [], 0
+    for h, w in zip(hs, ws):
+        offs.append(total)
+        total += (h * w * 3 + 255) // 256 * 256
+    if all(t.is_cuda for t in ts):
+        packed = torch.empty(total, dtype=torch.uint8, device=dev)
+        for t, o in zip(ts, offs):
+            packed[o:o + t.numel()].copy_(t.reshape(-1))
+    else:
+        host = torch.empty(total, dtype=torch.uint8, pin_memory=True)
+        for t, o in zip(ts, offs):
+            host[o:o + t.numel()].copy_(t.reshape(-1))
+        packed = host.to(dev, non_blocking=True)
+    ia = (ctypes.c_int * n)
+    nbytes = ctypes.c_longlong(0)
+    LIB.call('dh_resize_workspace_bytes', n, ia(*hs), ia(*ws), out_size, ctypes.byref(nbytes))
+    ws_buf = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    LIB.call('dh_resize_bilinear_u8', ptr(packed), (ctypes.c_longlong * n)(*offs), ia(*hs), ia(*ws), n, out_size, ptr(out),
+             ptr(ws_buf), nbytes.value, stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ path-level entries
+DH_STAGE_RESNET50 = 1
+
+
+def resnet50_ctx(enc):
+    """dh_ctx holding the packed trunk of an EncoderRT (dh_ctx_set_resnet50)."""
+    import ctypes
+    ctx = Ctx()
+    w = Resnet50Weights()
+    w.stem_w, w.stem_b = ptr(enc.stem_wq), ptr(enc.stem.bias)
+    stage = 0
+    for i, blk in enumerate(enc.blocks):
+        for j, name in enumerate(('c1', 'c2', 'c3')):
+            w.conv_w[i][j], w.conv_b[i][j] = ptr(blk[name].w), ptr(blk[name].bias)
+        if 'dual_w' in blk:
+            w.dual_w[stage], w.dual_b[stage] = ptr(blk['dual_w']), ptr(blk['dual_b'])
+            stage += 1
+    for c in range(3):
+        w.mean[c], w.std[c] = enc.pixel_mean[c], enc.pixel_std[c]
+    w.dtype = code(enc.stem_wq)
+    LIB.call('dh_ctx_set_resnet50', ctx.handle, ctypes.byref(w), launches=0)
+    return ctx
+
+
+def resnet50_forward(ctx, images, feat, pooled, workspace_of):
+    """images fp32 / uint8 [n,3,224,224] -> feat [n,7,7,2048] (+ pooled fp32 [n,2048]) through dh_resnet50_forward;
+    workspace_of(nbytes) returns a uint8 device buffer of at least that size."""
+    import ctypes
+    n, _, H, W = images.shape
+    assert images.is_contiguous() and feat.is_contiguous() and (pooled is None or (pooled.is_contiguous() and pooled.dtype == torch.float32))
+    nbytes = ctypes.c_longlong(0)
+    LIB.call('dh_workspace_bytes', ctx.handle, DH_STAGE_RESNET50, n, H, W, ctypes.byref(nbytes), launches=0)
+    ws = workspace_of(nbytes.value)
+    LIB.call('dh_resnet50_forward', ctx.handle, ptr(images), int(images.dtype == torch.uint8), n, H, W, ptr(feat), ptr(pooled),
+             ptr(ws), nbytes.value, stream(), launches=49)
+
+
+def xfmr_ctx(rt):
+    """dh_ctx holding the packed decoder stack of an XfmrDecoderRT (dh_ctx_set_xfmr)."""
+    import ctypes
+    ctx = Ctx()
+    w = XfmrWeights()
+    w.n_layers, w.D, w.n_heads, w.pf, w.cross, w.dtype, w.pad = rt.L, rt.D, rt.n_heads, rt.pf, int(rt.cross), code(rt.tok), rt.pad
+    w.scale = rt.scale
+    w.tok, w.pos, w.ld_tok = ptr(rt.tok), ptr(rt.pos), _rows(rt.tok)
+    for l, lay in enumerate(rt.layers):
+        y = w.layer[l]
+        y.qkv_w, y.qkv_b = ptr(lay['self_attn.qkv.w']), ptr(lay['self_attn.qkv.b'])
+        y.so_w, y.so_b = ptr(lay['self_attn.fc_o.w']), ptr(lay['self_attn.fc_o.b'])
+        y.sln_g, y.sln_b, y.s_scale = ptr(lay['self_attn_ln.g']), ptr(lay['self_attn_ln.b']), lay['self_attn.scale']
+        if rt.cross:
+            y.cq_w, y.cq_b = ptr(lay['enc_attn.fc_q.w']), ptr(lay['enc_attn.fc_q.b'])
+            y.co_w, y.co_b = ptr(lay['enc_attn.fc_o.w']), ptr(lay['enc_attn.fc_o.b'])
+            y.cln_g, y.cln_b, y.c_scale = ptr(lay['enc_attn_ln.g']), ptr(lay['enc_attn_ln.b']), lay['enc_attn.scale']
+        y.f1_w, y.f1_b, y.f2_w, y.f2_b = ptr(lay['pf.fc_1.w']), ptr(lay['pf.fc_1.b']), ptr(lay['pf.fc_2.w']), ptr(lay['pf.fc_2.b'])
+        y.fln_g, y.fln_b = ptr(lay['pf_ln.g']), ptr(lay['pf_ln.b'])
+    LIB.call('dh_ctx_set_xfmr', ctx.handle, ctypes.byref(w), launches=0)
+    return ctx
+
+
+def xfmr_buffers(x, qb, attn, tmp, h1, Kc, Vc, xkv, enc_mask, start, slots, S):
+    b = XfmrBuffers()
+    b.x, b.qb, b.attn, b.tmp, b.h1 = ptr(x), ptr(qb), ptr(attn), ptr(tmp), ptr(h1)
+    for l in range(len(Kc)):
+        b.Kc[l], b.Vc[l] = ptr(Kc[l]), ptr(Vc[l])
+        if xkv is not None:
+            b.xK[l], b.xV[l] = ptr(xkv[l][0]), ptr(xkv[l][1])
+    b.enc_mask = ptr(enc_mask)
+    b.start, b.ld_start = ptr(start), _rows(start)
+    b.slots, b.S = slots, S
+    return b
+
+
+def xfmr_step(ctx, bufs, rows, rpi, pos, tokens, seq, src, n_layers, cross):
+    """One decoder-stack step through dh_xfmr_step (embed + per layer 5 / 8 launches)."""
+    import ctypes
+    bufs.seq, bufs.seq_ld = ptr(seq), (0 if seq is None else _rows(seq))
+    bufs.src = ptr(src)
+    LIB.call('dh_xfmr_step', ctx.handle, ctypes.byref(bufs), rows, rpi, pos, ptr(tokens), stream(),
+             launches=1 + n_layers * (8 if cross else 5))

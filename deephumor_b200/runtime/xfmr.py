@@ -62,6 +62,12 @@ class XfmrDecoderRT:
     def _post_attn(self, lay, att, x, attn, tmp, rows):
         """x <- LN(x + fc_o(attn))."""
         D, es = self.D, x.element_size()
+        if ops.gemm_ln_supported(x, D):
+            # fc_o + residual + LayerNorm in one launch, in place on x (dh_gemm_tc_ln)
+            with ops.PROFILE.range('xfmr_proj_ln', 2.0 * rows * D * D):
+                ops.gemm_ln(attn[:rows], lay[f'{att}.fc_o.w'], lay[f'{att}.fc_o.b'], x[:rows], lay[f'{att}_ln.g'],
+                            lay[f'{att}_ln.b'], x[:rows])
+            return
         with ops.PROFILE.range('xfmr_proj', 2.0 * rows * D * D):
             ops.gemm(attn[:rows], lay[f'{att}.fc_o.w'], tmp[:rows], bias=lay[f'{att}.fc_o.b'], residual=x[:rows])
         with ops.PROFILE.range('xfmr_layernorm', nbytes=2.0 * rows * D * es):
@@ -69,6 +75,11 @@ class XfmrDecoderRT:
 
     def _ffn(self, lay, x, h1, tmp, rows):
         D, es = self.D, x.element_size()
+        if ops.gemm_ln_supported(x, D):
+            with ops.PROFILE.range('xfmr_ffn', 4.0 * rows * D * self.pf):
+                ops.gemm(x[:rows], lay['pf.fc_1.w'], h1[:rows], bias=lay['pf.fc_1.b'], relu=True)
+                ops.gemm_ln(h1[:rows], lay['pf.fc_2.w'], lay['pf.fc_2.b'], x[:rows], lay['pf_ln.g'], lay['pf_ln.b'], x[:rows])
+            return
         with ops.PROFILE.range('xfmr_ffn', 4.0 * rows * D * self.pf):
             ops.gemm(x[:rows], lay['pf.fc_1.w'], h1[:rows], bias=lay['pf.fc_1.b'], relu=True)
             ops.gemm(h1[:rows], lay['pf.fc_2.w'], tmp[:rows], bias=lay['pf.fc_2.b'], residual=x[:rows])
@@ -104,8 +115,18 @@ class XfmrDecoderRT:
                     if beam_step:
                         beam.step(ind, val, step_i, max_len, eos_index, False, temperature, noise_mode, 0, 0, dyn)
 
+        use_path = (ops.PATH_ENTRIES and not ops.PROFILE.on and all('self_attn.qkv.w' in lay for lay in self.layers)
+                    and self.L <= 8 and ops.FUSED_LN)
+        if use_path:
+            if getattr(self, '_ctx', None) is None:
+                self._ctx = ops.xfmr_ctx(self)
+            bufs = ops.xfmr_buffers(x, qb, attn, tmp, h1, Kc, Vc, xkv, emask, start_emb, B, S)
+
         def step(rows, rpi, pos, tokens, seq, src):
             """One new position `pos` for `rows` rows (rpi rows per image)."""
+            if use_path:                                           # the whole stack behind one path-level C entry
+                ops.xfmr_step(self._ctx, bufs, rows, rpi, pos, tokens, seq, src, self.L, self.cross)
+                return
             ops.xfmr_embed(self.tok, self.pos, start_emb, rpi, tokens, None, pos, self.scale, x[:rows])
             slot_stride = (B if rpi == 1 else 1)                 # prefix phase writes slot 0 of each image
             for l, lay in enumerate(self.layers):

@@ -90,6 +90,13 @@ int dh_gemm_tc(const void* A, long long lda, const void* W, long long ldw, int a
 int dh_gemm_tc_pool(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias,
                     const void* residual, long long ldr, void* C, long long ldc, int M, int N, int K, int relu,
                     int pool_hw, float* pool, long long ld_pool, cudaStream_t stream);
+/* out = LayerNorm(A W^T + bias + residual) * gamma + beta, rows of N == 512 columns, in one launch: the post-LN tail of every
+ * decoder sublayer (transformers.py:355-356,365-366,374-375: fc_o / fc_2 -> dropout (eval) -> residual add -> nn.LayerNorm).
+ * A CTA (pair) keeps the whole 128-row x 512-column block in tensor memory, so the pre-norm sums never reach HBM.
+ * residual / out of ab_dtype; out may alias residual; bias / gamma / beta fp32, 16-byte aligned. */
+int dh_gemm_tc_ln(const void* A, long long lda, const void* W, long long ldw, int ab_dtype, const float* bias,
+                  const void* residual, long long ldr, const float* gamma, const float* beta, float eps, void* out,
+                  long long ldc, int M, int N, int K, cudaStream_t stream);
 /* One contraction, three destinations: block j (of split_n columns) of A[M,K] W[3*split_n,K]^T + bias goes to Cj with its own
  * leading dimension.  The transformer decode step projects Q, K and V of the new position from the same activation
  * (transformers.py:97-99): W = [fc_q | fc_k | fc_v] stacked along N, C0 = the query buffer, C1 / C2 = this position's rows of
@@ -135,6 +142,15 @@ int dh_stem_pool_tc(const float* images_nchw, const void* w_packed, const float*
 int dh_stem_pool_tc_u8(const unsigned char* images_nchw_u8, const float* mean3_host, const float* std3_host,
                        const void* w_packed, const float* bias, void* out, int n, int H, int W, int dtype,
                        cudaStream_t stream);
+/* torchvision `Resize((out_size, out_size))` on PIL RGB images (deephumor_demo.ipynb cell 11; data/datasets.py:48-53,94-98),
+ * i.e. Pillow's two-pass antialiased BILINEAR resampling (22-bit fixed-point taps, uint8 intermediate), bit-exact.
+ * n images of different sizes, HWC uint8, packed in one device buffer at byte offsets_host[i] (heights / widths / offsets
+ * are HOST arrays); out uint8 [n,3,out_size,out_size] NCHW = the input of dh_stem_pool_tc_u8.  The caller provides the
+ * workspace (256-byte aligned) of dh_resize_workspace_bytes; in / out ratios up to 79 per axis, out_size <= 256. */
+int dh_resize_workspace_bytes(int n, const int* heights_host, const int* widths_host, int out_size, long long* bytes_out);
+int dh_resize_bilinear_u8(const unsigned char* packed_hwc, const long long* offsets_host, const int* heights_host,
+                          const int* widths_host, int n, int out_size, unsigned char* out_nchw, void* workspace,
+                          long long workspace_bytes, cudaStream_t stream);
 /* watchdog code left by gemm_tc_kernel before it traps (0 = none). */
 int dh_tc_error_flag(int* out_host);
 
@@ -301,6 +317,68 @@ int dh_vocab_logprob(const void* A, long long lda, const void* W, long long ldw,
 /* log_softmax(logits)[target] per row (experiments/metrics.py:5). */
 int dh_token_logprob(const float* logits, long long ld, int rows, int V, const long long* targets, float* out,
                      cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------ path-level entries
+ * A whole stage of the caption path behind ONE call (csrc/path.cu), for consumers that are not the Python runtime.  A
+ * dh_ctx is a HOST table of device pointers to the packed weights (packing as documented per entry above; the Python
+ * packer is deephumor_b200/runtime/encoder.py / xfmr.py); it owns no device memory.  Workspaces are the caller's. */
+typedef struct dh_ctx dh_ctx;
+
+#define DH_STAGE_RESNET50 1
+
+typedef struct dh_resnet50_weights {
+  const void* stem_w;          /* [64][192] fused-stem packing, K slot r*22 + s*3 + c (dh_stem_pool_tc) */
+  const float* stem_b;
+  const void* conv_w[16][3];   /* bottleneck b (3 + 4 + 6 + 3 in stage order): conv1 / conv2 / conv3, BN folded, */
+  const float* conv_b[16][3];  /*   [Cout][kh][kw][Cin] in `dtype`; biases fp32 */
+  const void* dual_w[4];       /* first bottleneck of each stage: [W_conv3 | W_downsample] along K (dh_conv1x1_dual_tc) */
+  const float* dual_b[4];      /*   b_conv3 + b_downsample */
+  float mean[3], std[3];       /* Normalize() statistics for uint8 input */
+  int dtype;                   /* DH_F16 or DH_BF16: storage type of weights and activations */
+} dh_resnet50_weights;
+
+#define DH_XFMR_MAX_LAYERS 8
+typedef struct dh_xfmr_layer {
+  const void* qkv_w; const float* qkv_b;                    /* [3D, D] = [fc_q | fc_k | fc_v] of self_attn, [3D] */
+  const void* so_w; const float* so_b; const float* sln_g; const float* sln_b; float s_scale;
+  const void* cq_w; const float* cq_b;                      /* enc_attn (cross == 1): fc_q; K / V are projected per image */
+  const void* co_w; const float* co_b; const float* cln_g; const float* cln_b; float c_scale;
+  const void* f1_w; const float* f1_b; const void* f2_w; const float* f2_b; const float* fln_g; const float* fln_b;
+} dh_xfmr_layer;
+typedef struct dh_xfmr_weights {
+  int n_layers, D, n_heads, pf, cross, dtype, pad;
+  float scale;                                              /* decoder.scale = sqrt(hid_dim) */
+  const void* tok; const void* pos; long long ld_tok;       /* embedding tables, `dtype` */
+  dh_xfmr_layer layer[DH_XFMR_MAX_LAYERS];
+} dh_xfmr_weights;
+typedef struct dh_xfmr_buffers {
+  void* x; void* qb; void* attn; void* tmp; void* h1;       /* [rows, D] x 4 (tmp only when D != 512), [rows, pf] */
+  void* Kc[DH_XFMR_MAX_LAYERS]; void* Vc[DH_XFMR_MAX_LAYERS];   /* KV cache per layer [rows_total, S, D] */
+  const void* xK[DH_XFMR_MAX_LAYERS]; const void* xV[DH_XFMR_MAX_LAYERS];   /* cross K / V per layer [n_img * 49, D] */
+  const unsigned char* enc_mask;                            /* [n_img * 49] (dh_enc_mask) */
+  const float* start; long long ld_start;                   /* image embedding [n_img, D] fp32 (position 0) */
+  const int* seq; long long seq_ld;                         /* beam sequences (pad-key mask) */
+  const int* src;                                           /* KV slot table [rows, S] (null in the prefix phase) */
+  int slots, S;                                             /* cache slots per image (= beam), cached positions */
+} dh_xfmr_buffers;
+
+int dh_ctx_create(dh_ctx** out);
+int dh_ctx_destroy(dh_ctx* ctx);
+int dh_ctx_set_resnet50(dh_ctx* ctx, const dh_resnet50_weights* w);
+int dh_ctx_set_xfmr(dh_ctx* ctx, const dh_xfmr_weights* w);
+/* bytes of the caller-provided, 256-byte aligned workspace of a stage for n images of H x W */
+int dh_workspace_bytes(const dh_ctx* ctx, int stage, int n, int H, int W, long long* bytes_out);
+/* ResNet-50 trunk of ImageEncoder (encoders.py:34-39,56; torchvision resnet.py:143-163,197-204) + the global average pool
+ * (encoders.py:39,60): images fp32 (or uint8 when images_u8) [n,3,224,224] NCHW -> feat [n,7,7,2048] NHWC (weights' dtype)
+ * and pooled [n,2048] fp32 (nullable).  50 launches.  DH_ERR_UNSUPPORTED for other image sizes (use the per-op entries). */
+int dh_resnet50_forward(const dh_ctx* ctx, const void* images_nchw, int images_u8, int n, int H, int W, void* feat,
+                        float* pooled, void* workspace, long long workspace_bytes, cudaStream_t stream);
+/* One new position for `rows` rows through the whole decoder stack against the KV cache (transformers.py:343-377 per layer,
+ * :455-486 around it; SelfAttentionDecoderLayer :612-636 when cross == 0): embed, then per layer fused Q|K|V (K / V rows land
+ * in cache slot `pos`), self-attention through the beam slot table, fc_o + residual + LayerNorm, [cross-attention over the
+ * image's 49 tokens], FFN + residual + LayerNorm.  The hidden state of the new position is left in buffers->x. */
+int dh_xfmr_step(const dh_ctx* ctx, const dh_xfmr_buffers* buffers, int rows, int rows_per_image, int pos, const int* tokens,
+                 cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -421,3 +421,33 @@ def test_encoder_fused_pool_equals_separate_avgpool():
             ops.FUSED_POOL = True
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize('dt', [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize('M,K', [(128, 512), (1, 512), (130, 64), (2560, 2048), (40960, 512), (777, 1024), (300, 128)])
+def test_gemm_layernorm_epilogue(M, K, dt):
+    """dh_gemm_tc_ln (fc_o / fc_2 + residual + nn.LayerNorm of a decoder sublayer, transformers.py:355-356,374-375) against a
+    float64 restatement on the same rounded operands, out of place and in place on the residual; and against the two-launch
+    form (dh_gemm_tc + dh_add_layernorm), which rounds the pre-norm sum to 2 bytes first."""
+    N = 512
+    A, W = rnd(M, K, seed=1).to(dt).to(DEV), rnd(N, K, seed=2, scale=0.1).to(dt).to(DEV)
+    b, r = rnd(N, seed=3).to(DEV), rnd(M, N, seed=4).to(dt).to(DEV)
+    g, be = (1.0 + 0.2 * rnd(N, seed=5)).to(DEV), rnd(N, seed=6, scale=0.3).to(DEV)
+    ref = F.layer_norm(A.double() @ W.double().T + b.double() + r.double(), (N,), g.double(), be.double(), 1e-5).float()
+    out = torch.zeros(M, N, dtype=dt, device=DEV)
+    ops.gemm_ln(A, W, b, r, g, be, out)
+    tol = 4e-3 if dt == torch.bfloat16 else 6e-4                  # one rounding of the output
+    assert H.rel_err(out.float(), ref) < tol
+    x = r.clone()
+    ops.gemm_ln(A, W, b, x, g, be, x)                             # in place on the residual (how the decoder runs it)
+    assert torch.equal(x, out)
+    tmp = torch.zeros(M, N, dtype=dt, device=DEV)
+    two = torch.zeros(M, N, dtype=dt, device=DEV)
+    ops.gemm(A, W, tmp, bias=b, residual=r)
+    ops.add_layernorm(tmp, None, g, be, two)
+    assert H.rel_err(two.float(), ref) >= H.rel_err(out.float(), ref) * 0.5      # the fused form is no less accurate
+    assert H.rel_err(out.float(), two.float()) < 3 * tol
+    out2 = torch.zeros(M, N, dtype=dt, device=DEV)
+    ops.gemm_ln(A, W, None, None, g, be, out2)                    # no bias / residual
+    ref2 = F.layer_norm(A.double() @ W.double().T, (N,), g.double(), be.double(), 1e-5).float()
+    assert H.rel_err(out2.float(), ref2) < tol

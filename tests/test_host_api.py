@@ -155,7 +155,9 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
     gcc = shutil.which('gcc')
     if gcc is None:
         pytest.skip('gcc not available')
-    structs = {'dh_beam_state': _lib.BeamState, 'dh_lstm_operands': _lib.LstmOperands, 'dh_vocab_sparse': _lib.VocabSparse}
+    structs = {'dh_beam_state': _lib.BeamState, 'dh_lstm_operands': _lib.LstmOperands, 'dh_vocab_sparse': _lib.VocabSparse,
+               'dh_resnet50_weights': _lib.Resnet50Weights, 'dh_xfmr_layer': _lib.XfmrLayer, 'dh_xfmr_weights': _lib.XfmrWeights,
+               'dh_xfmr_buffers': _lib.XfmrBuffers}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{_lib.HEADER}"', 'int main(void) {']
     for cname, cls in structs.items():
         lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
