@@ -293,6 +293,38 @@ __global__ void xfmr_embed_kernel(const T* __restrict__ tok_table, const T* __re
   }
 }
 
+// 2-byte tables: eight columns per thread with 16-byte loads / stores, same arithmetic per element as the scalar kernel
+template <typename T>
+__global__ void __launch_bounds__(256) xfmr_embed_vec_kernel(const T* __restrict__ tok_table, const T* __restrict__ pos_table,
+                                                             long long ldt, const float* __restrict__ start, long long lds,
+                                                             int rows_per_start, const int* __restrict__ tokens,
+                                                             const int* __restrict__ positions, int pos_const, float scale,
+                                                             T* __restrict__ out, long long ldo, int R, int D) {
+  const int d8 = D >> 3;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)R * d8) return;
+  const int r = (int)(i / d8), c = (int)(i - (long long)r * d8) * 8;
+  const int pos = positions ? positions[r] : pos_const;
+  float e[8];
+  if (pos == 0) {
+    const float4* sp = reinterpret_cast<const float4*>(start + (long long)(r / rows_per_start) * lds + c);
+    const float4 a = __ldg(sp), b = __ldg(sp + 1);
+    e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b.x; e[5] = b.y; e[6] = b.z; e[7] = b.w;
+  } else {
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(tok_table + (long long)tokens[r] * ldt + c));
+    const T* t8 = reinterpret_cast<const T*>(&t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) e[j] = dh_to_f<T>(t8[j]);
+  }
+  const uint4 pv = __ldg(reinterpret_cast<const uint4*>(pos_table + (long long)pos * ldt + c));
+  const T* p8 = reinterpret_cast<const T*>(&pv);
+  uint4 o;
+  T* o8 = reinterpret_cast<T*>(&o);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o8[j] = dh_from_f<T>(e[j] / scale + dh_to_f<T>(p8[j]));
+  *reinterpret_cast<uint4*>(out + (long long)r * ldo + c) = o;
+}
+
 template <typename TS, typename TD>
 __global__ void cast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -423,6 +455,19 @@ extern "C" int dh_xfmr_embed(const void* tok_table, const void* pos_table, long 
   DH_ARG(tokens || (!positions && pos_const == 0));
   if (rows == 0) return DH_OK;
   long long total = (long long)rows * D;
+  if (dtype != DH_F32 && D % 8 == 0 && ldt % 8 == 0 && ldo % 8 == 0 && lds % 4 == 0 && ((uintptr_t)tok_table % 16) == 0 &&
+      ((uintptr_t)pos_table % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)start % 16) == 0) {
+    const int g = dh_cdiv(total / 8, 256);
+    if (dtype == DH_BF16)
+      xfmr_embed_vec_kernel<__nv_bfloat16><<<g, 256, 0, s>>>((const __nv_bfloat16*)tok_table, (const __nv_bfloat16*)pos_table, ldt,
+                                                             start, lds, rows_per_start, tokens, positions, pos_const, scale,
+                                                             (__nv_bfloat16*)out, ldo, rows, D);
+    else
+      xfmr_embed_vec_kernel<__half><<<g, 256, 0, s>>>((const __half*)tok_table, (const __half*)pos_table, ldt, start, lds,
+                                                      rows_per_start, tokens, positions, pos_const, scale, (__half*)out, ldo, rows, D);
+    DH_LAUNCH_OK();
+    return DH_OK;
+  }
   DH_DISPATCH(dtype, (xfmr_embed_kernel<T><<<grid_for(total), kThreads, 0, s>>>((const T*)tok_table, (const T*)pos_table, ldt, start,
                                                                               lds, rows_per_start, tokens, positions, pos_const,
                                                                               scale, (T*)out, ldo, rows, D)));

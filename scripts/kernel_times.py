@@ -32,3 +32,20 @@ print(f'# {name}: {wl.n_local} images, step {step_ms:.3f} ms (CUDA events, unpro
 print(f'{"kernel":100s} {"count":>6s} {"total ms":>10s} {"avg us":>9s} {"max us":>9s} {"share":>6s}')
 for k, (n, tot, mx) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f'{k[:100]:100s} {n:6d} {tot / 1e3:10.3f} {tot / n:9.2f} {mx:9.2f} {tot / total:6.3f}')
+
+# ---- idle time between consecutive kernels (where the step is not covered by kernel time)
+evs = sorted([(ev.time_range.start, ev.time_range.end, ev.name) for ev in prof.events()
+              if ev.device_type == torch.autograd.DeviceType.CUDA], key=lambda e: e[0])
+gaps, by_prev = [], {}
+for (s0, e0, n0), (s1, e1, n1) in zip(evs, evs[1:]):
+    g = s1 - e0
+    if g > 0:
+        gaps.append((g, n0, n1))
+        c, t = by_prev.get(n0[:60], (0, 0.0))
+        by_prev[n0[:60]] = (c + 1, t + g)
+print(f'\n# idle time between kernels: {sum(g[0] for g in gaps) / 1e3:.3f} ms in {len(gaps)} gaps; by preceding kernel:')
+for k, (c, t) in sorted(by_prev.items(), key=lambda kv: -kv[1][1])[:12]:
+    print(f'  {t / 1e3:8.3f} ms in {c:5d} gaps after {k}')
+print('# largest gaps:')
+for g, n0, n1 in sorted(gaps, key=lambda g: -g[0])[:12]:
+    print(f'  {g:9.1f} us  {n0[:50]}  ->  {n1[:50]}')

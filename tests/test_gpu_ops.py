@@ -229,3 +229,22 @@ def test_attention_incremental_self_row_kernel(n_img, B, nk, S_alloc, use_src):
         ref[r] = (torch.softmax(e, -1).unsqueeze(1) @ vr).reshape(D_)
     assert H.rel_err(out.float(), ref.float()) < 1e-2
 
+
+
+@pytest.mark.parametrize('dt', [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize('rows,D,rps,pos', [(10, 512, 5, 0), (10, 512, 5, 7), (37, 64, 1, 3), (2560, 512, 5, 31), (6, 40, 2, 0)])
+def test_xfmr_embed_vectorised_equals_formula(rows, D, rps, pos, dt):
+    """(start | tok_embedding[token]) / scale + pos_embedding[pos] (transformers.py:455-470): the 16-byte vectorised kernel of
+    the 2-byte tables and the scalar kernel give exactly the rounded fp32 expression."""
+    g = torch.Generator().manual_seed(rows + D + pos)
+    V = 97
+    tok = torch.randn(V, D, generator=g).to(dt).cuda()
+    pe = torch.randn(40, D, generator=g).to(dt).cuda()
+    start = torch.randn((rows + rps - 1) // rps, D, generator=g).cuda()
+    tokens = torch.randint(0, V, (rows,), generator=g, dtype=torch.int32).cuda()
+    out = torch.empty(rows, D, dtype=dt, device='cuda')
+    scale = 22.627416997969522
+    ops.xfmr_embed(tok, pe, start, rps, tokens, None, pos, scale, out)
+    e = start.repeat_interleave(rps, 0)[:rows] if pos == 0 else tok[tokens.long()].float()
+    ref = (e / torch.tensor(scale, dtype=torch.float32).cuda() + pe[pos].float()).to(dt)
+    assert torch.equal(out, ref)
