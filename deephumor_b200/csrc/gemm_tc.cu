@@ -294,43 +294,55 @@ __device__ __forceinline__ uint32_t umma_idesc(int bn, int ab_dtype, int m = BM)
 // PAIR: two CTAs of a cluster (one TPC) run ONE tcgen05.mma.cta_group::2 of M = 256: each CTA stages its own 128 A rows and
 // HALF of the W tile (BN/2 rows) and owns the accumulator of its 128 rows -- a third less operand traffic per FLOP from L2,
 // which is what bounds these contractions (profiles/: ~12 TB/s chip-wide TMA ceiling).
-template <int BN, bool PAIR = false, int EPI = 0>
+// ARES ("A resident"): the CTA keeps the whole K extent (<= 8 chunks = 128 KB) of its 128 A rows in shared memory and walks a
+// CONTIGUOUS run of N tiles of that row block, so only the W tiles stream through the ring.  A contraction with K = 512 and
+// 256 x 256 pair tiles moves 512 KB from L2 per 67 MFLOP when A and W both stream -- 17 TB/s at the tensor peak, above what L2
+// delivers (~11.5 TB/s measured: profiles/r02_ncu_vocab_pass2_40960.csv shows 74 % tensor-active) -- and half of that with A
+// resident.
+template <int BN, bool PAIR = false, int EPI = 0, bool ARES = false>
 struct Cfg {
-  static constexpr int kStageBytes = (BM + (PAIR ? BN / 2 : BN)) * BK * 2;
+  static constexpr int kMaxResChunks = 8;
+  static constexpr int kAresBytes = ARES ? kMaxResChunks * BM * BK * 2 : 0;
+  static constexpr int kStageBytes = ((ARES ? 0 : BM) + (PAIR ? BN / 2 : BN)) * BK * 2;
   // LayerNorm mode gives up ring stages for its parameter block (5 x 32 KB stages as a pair, 3 x 48 KB alone)
-  static constexpr int kStages = EPI == 5 ? (PAIR ? 5 : 3) : kSmemBudget / kStageBytes;
+  static constexpr int kStages = EPI == 5 ? (PAIR ? 5 : 3) : ARES ? (PAIR ? 5 : 3) : kSmemBudget / kStageBytes;
+  static constexpr int kRingBytes = kAresBytes + kStages * kStageBytes;     // resident A block + ring
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kStagingBytes = 2 * BM * 128;   // two 128-row x 128 B slabs (TMA store) / transpose scratch
-  static constexpr int kBiasBytes = 1024;              // bias slice of the current tile (BN <= 256 floats)
+  // two 128-row x 128 B slabs (TMA store) / per-warp transpose scratch; the selection epilogues (1, 2, 4) stage nothing
+  static constexpr int kStagingBytes = (EPI == 1 || EPI == 2 || EPI == 4) ? 0 : 2 * BM * 128;
+  // bias slice of the current tile (BN <= 256 floats); double-buffered in the selection epilogues
+  static constexpr int kBiasBytes = (EPI == 1 || EPI == 2 || EPI == 4) ? 2048 : 1024;
   // LayerNorm mode: bias | gamma | beta of the whole 2 BN-wide row (fp32) + double-buffered per-row (mean, M2) partials of
   // the two column halves
   static constexpr int kLnBytes = EPI == 5 ? 3 * 2 * BN * 4 + 2 * 2 * BM * 2 * 4 : 0;
-  static constexpr int kLnOff = kStages * kStageBytes + kStagingBytes + kBiasBytes + 256;
+  static constexpr int kLnOff = kRingBytes + kStagingBytes + kBiasBytes + 256;
   static constexpr int kSmemBytes = 1024 + kLnOff + kLnBytes;
 };
 
 // EPI = TcParams::epi_mode as a compile-time constant: every epilogue is its own kernel (named in profiles, no dead code)
-template <int BN, bool PAIR, int EPI>
+template <int BN, bool PAIR, int EPI, bool ARES = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
                const __grid_constant__ CUtensorMap map_i, const TcParams p) {
-  using C = Cfg<BN, PAIR, EPI>;
+  using C = Cfg<BN, PAIR, EPI, ARES>;
   constexpr int CG = PAIR ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t ring = base;
-  float* staging = reinterpret_cast<float*>(gen_base + C::kStages * C::kStageBytes);
-  float* bias_s = reinterpret_cast<float*>(gen_base + C::kStages * C::kStageBytes + C::kStagingBytes);
-  const uint32_t bars = base + C::kStages * C::kStageBytes + C::kStagingBytes + C::kBiasBytes;
+  const uint32_t ares = base;                       // resident A block (ARES): chunk kc at ares + kc * 16 KB
+  const uint32_t ring = base + C::kAresBytes;
+  float* staging = reinterpret_cast<float*>(gen_base + C::kRingBytes);
+  float* bias_s = reinterpret_cast<float*>(gen_base + C::kRingBytes + C::kStagingBytes);
+  const uint32_t bars = base + C::kRingBytes + C::kStagingBytes + C::kBiasBytes;
   // barrier slots (8 B each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]; then the TMEM base word
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (C::kStages + s); };
   auto tfull_bar = [&](int s) { return bars + 8u * (2 * C::kStages + s); };
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * C::kStages + 2 + s); };
-  uint32_t* tmem_word = reinterpret_cast<uint32_t*>(gen_base + C::kStages * C::kStageBytes + C::kStagingBytes +
-                                                    C::kBiasBytes + 8 * (2 * C::kStages + 4));
+  const uint32_t afull_bar = bars + 8u * (2 * C::kStages + 4), afree_bar = bars + 8u * (2 * C::kStages + 5);   // ARES only
+  uint32_t* tmem_word = reinterpret_cast<uint32_t*>(gen_base + C::kRingBytes + C::kStagingBytes +
+                                                    C::kBiasBytes + 8 * (2 * C::kStages + 6));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p.cond_mode) {
@@ -365,6 +377,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), ((EPI && EPI != 5) ? 8 : 4) * CG);   // LayerNorm mode: one group drains each buffer   // the leader's barrier collects both CTAs' epilogue warps
     }
+    if (ARES) { mbar_init(afull_bar, 1); mbar_init(afree_bar, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 2) {
     if (PAIR) {
@@ -390,7 +403,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int tstride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   // virtual tile sequence of this CTA (pair): tile_of(0), tile_of(1), ... until >= tiles.  LayerNorm mode walks ROW BLOCKS with
   // the stride and visits both N halves of a block back to back (accumulator buffer = half)
-  auto tile_of = [&](int it) { return EPI == 5 ? 2 * (tile0 + (it >> 1) * tstride) + (it & 1) : tile0 + it * tstride; };
+  // ARES: CTA (pair) c owns the contiguous run [c * per, (c + 1) * per) of the m-major tile order, i.e. consecutive N tiles of
+  // (mostly) one row block
+  const int ares_per = ARES ? dh_cdiv_dev(tiles, tstride) : 0;
+  const int ares_end = ARES ? min(tiles, (tile0 + 1) * ares_per) : 0;
+  auto tile_of = [&](int it) {
+    if (ARES) { const int t = tile0 * ares_per + it; return t < ares_end ? t : tiles; }
+    return EPI == 5 ? 2 * (tile0 + (it >> 1) * tstride) + (it & 1) : tile0 + it * tstride;
+  };
   auto tile_m0 = [&](int tile) { return (tile / p.n_blocks) * (p.bm_rows * CG) + (int)cta_rank * p.bm_rows; };
 
   if (warp == 0) {
@@ -398,6 +418,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // ===================================================================== TMA producer
       int stage = 0;
       uint32_t phase = 0;
+      int ares_mb = -1, ares_loads = 0;
       for (int it = 0, tile; (tile = tile_of(it)) < tiles; ++it) {
         int layer = 0, rt = tile;                                // EPI 3: layer-major tile order of a stacked LSTM step
         if (EPI == 3 && p.layers > 1) { layer = tile / p.tiles_per_layer; rt = tile - layer * p.tiles_per_layer; }
@@ -418,6 +439,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         ((EPI == 3 && p.layers > 1) ? layer * p.w_layer_rows : 0);
         const int kch = (EPI == 3 && p.layers > 1) ? p.kch_l[layer] : p.k_chunks;
         const int rot = (EPI == 3 && p.layers > 1) ? p.rot_l[layer] : 0;
+        if (ARES) {
+          // resident A: (re)load the row block's K extent when the run crosses into a new row block -- after the MMAs that
+          // read the previous one have retired -- then stream only W tiles through the ring
+          const int mb = rt / p.n_blocks;
+          if (mb != ares_mb) {
+            if (ares_mb >= 0) mbar_wait(afree_bar, (uint32_t)((ares_loads - 1) & 1), p.error, 1);
+            if (cta_rank == 0) mbar_expect_tx(afull_bar, (uint32_t)(kch * p.bm_rows * BK * 2) * CG);
+            const uint32_t ab = PAIR ? mapa_u32(afull_bar, 0) : afull_bar;
+            for (int kc = 0; kc < kch; ++kc) {
+              if (PAIR) tma_load_2d_pair(ares + kc * (BM * BK * 2), &map_a, ab, kc * BK, a_row);
+              else tma_load_2d(ares + kc * (BM * BK * 2), &map_a, ab, kc * BK, a_row);
+            }
+            ares_mb = mb;
+            ++ares_loads;
+          }
+          for (int kc = 0; kc < kch; ++kc) {
+            mbar_wait(empty_bar(stage), phase ^ 1u, p.error, 1);
+            const uint32_t sb = ring + stage * C::kStageBytes;
+            if (cta_rank == 0) mbar_expect_tx(full_bar(stage), (uint32_t)C::kStageBytes * CG);
+            if (PAIR) tma_load_2d_pair(sb, &map_b, mapa_u32(full_bar(stage), 0), kc * BK, nb0);
+            else tma_load_2d(sb, &map_b, full_bar(stage), kc * BK, nb0);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+          }
+          continue;
+        }
         for (int j = 0; j < kch; ++j) {
           // a stacked layer starts its K loop at the recurrent half (chunk rot), which is ready at launch, and reaches
           // the x half -- written by the layer below during this launch -- last
@@ -483,16 +529,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t idesc64 = umma_idesc(64, p.ab_dtype, BM);
       int stage = 0;
       uint32_t phase = 0;
+      int ares_mb = -1, ares_cnt = 0;
       for (int it = 0, tile; (tile = tile_of(it)) < tiles; ++it) {
         const int as = it & 1;
         mbar_wait(tempty_bar(as), ((it >> 1) & 1) ^ 1u, p.error, 2);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
         const int chunks = ((EPI == 3 && p.layers > 1) ? p.kch_l[tile / p.tiles_per_layer] : p.k_chunks) + p.res_chunks;
+        if (ARES && tile / p.n_blocks != ares_mb) {              // a new row block: its resident A must have landed
+          mbar_wait(afull_bar, (uint32_t)(ares_cnt & 1), p.error, 3);
+          tc_fence_after();
+          ares_mb = tile / p.n_blocks;
+          ++ares_cnt;
+        }
         for (int kc = 0; kc < chunks; ++kc) {
           mbar_wait(full_bar(stage), phase, p.error, 3);
           tc_fence_after();
-          const uint32_t sa = ring + stage * C::kStageBytes, sb = sa + BM * BK * 2;
+          const uint32_t sa = ARES ? ares + kc * (BM * BK * 2) : ring + stage * C::kStageBytes;
+          const uint32_t sb = ARES ? ring + stage * C::kStageBytes : sa + BM * BK * 2;
           const uint64_t da = umma_desc(sa), db = umma_desc(sb);
           if (!PAIR && kc >= p.k_chunks) {
             // residual chunk j: D[:, 64 j .. 64 j + 63] += R[:, n0 + 64 j ..] x I64^T
@@ -510,6 +564,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (PAIR) tc_commit_pair(empty_bar(stage)); else tc_commit(empty_bar(stage));
           if (kc == chunks - 1) { if (PAIR) tc_commit_pair(tfull_bar(as)); else tc_commit(tfull_bar(as)); }
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+        }
+        if (ARES) {
+          // last tile of this row block in the run: once its MMAs retire the producer may overwrite the resident A
+          const int nt = tile_of(it + 1);
+          if (nt >= tiles || nt / p.n_blocks != ares_mb) { if (PAIR) tc_commit_pair(afree_bar); else tc_commit(afree_bar); }
         }
       }
     }
@@ -548,7 +607,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int unit0 = (n0 >> 8) * 64 + eh * 32;             // first of this thread's 32 hidden units
           const long long prow = row_ok ? (p.parent ? (long long)__ldg(p.parent + row) : row) : 0;
           const int cr = lane >> 2, cc = lane & 3;                // cooperative role: row i * 8 + cr, 16-byte chunk cc
-          const uint32_t wst = base + C::kStages * C::kStageBytes + (uint32_t)(warp - 4) * 4096u;
+          const uint32_t wst = base + C::kRingBytes + (uint32_t)(warp - 4) * 4096u;
           const uint32_t cbuf = wst, hbuf = wst + 2048u;          // [32 rows][64 B] each
           auto swz = [](int r, int j) { return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); };
           float4 cpv[8];
@@ -675,7 +734,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int row_l = ew * 32 + lane;
       float* lnp = reinterpret_cast<float*>(gen_base + C::kLnOff);          // [3][2 BN]: bias | gamma | beta
       float* part = lnp + 3 * 2 * BN;                                       // [2 buffers][2 halves][BM][2]
-      const uint32_t slab = base + C::kStages * C::kStageBytes + (uint32_t)eh * (BM * 128);
+      const uint32_t slab = base + C::kRingBytes + (uint32_t)eh * (BM * 128);
       const uint32_t srow = slab + (uint32_t)row_l * 128u;
       const uint32_t swz = (uint32_t)(row_l & 7);
       const bool elected = (ew == 0 && lane == 0);
@@ -779,85 +838,124 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else if (EPI) {
       // ---- selection epilogues: every thread owns one accumulator row; nothing of the [M,N] product is stored.
+      // The epilogue, not the tensor pipe, paced these kernels (ncu: 74 % tensor-active at K = 512, no time spent waiting for
+      // the accumulator), so everything that is not the scan itself is taken off the per-tile path: the bias slice of the NEXT
+      // tile is fetched into a register while this tile is scanned and published through a double-buffered shared-memory
+      // slice (one barrier per tile), the row's threshold / target are re-read only when the row block changes, and tensor
+      // memory is read 64 columns per wait.
       const int row_l = ew * 32 + lane;
+      float* bias_buf[2] = {bias_s, bias_s + BN};
+      auto tile_n0 = [&](int tile) { return ((tile % p.n_blocks) * p.n_stride + p.n_offset) * BN; };
+      {
+        const int t0i = tile_of(0);
+        if (t0i < tiles && etid < BN) {
+          const int n0 = tile_n0(t0i);
+          bias_buf[0][etid] = (p.bias && n0 + etid < p.N) ? __ldg(p.bias + n0 + etid) : 0.f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      int cur_m0 = -1;
+      bool row_ok = false, emit = false;
+      long long row = 0;
+      float t0 = INFINITY;
+      int tcol = -1;
       for (int it = 0, tile; (tile = tile_of(it)) < tiles; ++it) {
-        const int m0 = tile_m0(tile), n0 = ((tile % p.n_blocks) * p.n_stride + p.n_offset) * BN;
+        const int m0 = tile_m0(tile), n0 = tile_n0(tile);
         const int as = it & 1;
-        const long long row = (long long)m0 + row_l;
-        const bool row_ok = row < p.M;
-        // issued before the wait on the accumulator so that its L2 round trip is hidden
-        const bool emit = EPI == 2 && row_ok && (!p.redo || __ldg(p.redo + row));
-        const float thr = emit ? __ldg(p.thresh + row) : INFINITY;
-        const int tcol = (EPI == 4 && row_ok) ? (int)__ldg(p.targets + row) : -1;
+        const float* bias_cur = bias_buf[it & 1];
+        float bias_next = 0.f;
+        {
+          const int nt = tile_of(it + 1);
+          if (nt < tiles && etid < BN) {
+            const int nn0 = tile_n0(nt);
+            bias_next = (p.bias && nn0 + etid < p.N) ? __ldg(p.bias + nn0 + etid) : 0.f;
+          }
+        }
+        if (m0 != cur_m0) {
+          // per-row operands: issued before the wait on the accumulator so that their L2 round trip is hidden
+          cur_m0 = m0;
+          row = (long long)m0 + row_l;
+          row_ok = row < p.M;
+          emit = EPI == 2 && row_ok && (!p.redo || __ldg(p.redo + row));
+          // candidates are finite logits >= thresh[row]; clamping to -FLT_MAX folds the "> -inf" test into one compare
+          t0 = emit ? fmaxf(__ldg(p.thresh + row), -3.402823466e+38f) : INFINITY;
+          tcol = (EPI == 4 && row_ok) ? (int)__ldg(p.targets + row) : -1;
+        }
         mbar_wait(tfull_bar(as), (it >> 1) & 1, p.error, 4);
         tc_fence_after();
         const uint32_t tmem_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
-        asm volatile("bar.sync 1, 256;" ::: "memory");          // readers of the previous bias slice are done
-        for (int i = etid; i < BN; i += 256) bias_s[i] = (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        // candidates are finite logits >= thresh[row]; clamping to -FLT_MAX folds the "> -inf" test into one compare
-        const float t0 = emit ? fmaxf(thr, -3.402823466e+38f) : INFINITY;
         unsigned int bits = 0u;                                   // groups of this (row, tile, half) that hold a candidate
+        constexpr int kGroups = BN / 64;                          // 32-column groups per thread
 #pragma unroll 1
-        for (int c = eh * (BN / 64); c < (eh + 1) * (BN / 64); ++c) {
-          const int col0 = n0 + c * 32;
-          if (col0 >= p.N) {                                      // warp-uniform: group past the end of the row
-            if (EPI != 2 && row_ok) p.gmax[row * p.ld_gmax + (tile % p.n_blocks) * (BN / 32) + c] = -INFINITY;
-            if (EPI == 4 && row_ok) p.gsum[row * p.ld_gmax + (tile % p.n_blocks) * (BN / 32) + c] = 0.f;
-            continue;
-          }
-          uint32_t v[32];
-          tc_ld32(tmem_row + (uint32_t)(c * 32), v);
-          float x[32];
-          const float4* bs = reinterpret_cast<const float4*>(bias_s + c * 32);
+        for (int c2 = 0; c2 < kGroups; c2 += 2) {
+          uint32_t vv[2][32];
+          const int cbase = eh * kGroups + c2;
+          const bool two = c2 + 1 < kGroups;
+          tc_ld32_nw(tmem_row + (uint32_t)(cbase * 32), vv[0]);
+          if (two) tc_ld32_nw(tmem_row + (uint32_t)((cbase + 1) * 32), vv[1]);
+          tc_wait_ld();
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 b4 = bs[g];
-            x[4 * g] = __uint_as_float(v[4 * g]) + b4.x;
-            x[4 * g + 1] = __uint_as_float(v[4 * g + 1]) + b4.y;
-            x[4 * g + 2] = __uint_as_float(v[4 * g + 2]) + b4.z;
-            x[4 * g + 3] = __uint_as_float(v[4 * g + 3]) + b4.w;
-          }
-          const int nv = p.N - col0;                              // valid columns in this group (>= 1)
-          if (nv < 32) {                                          // last group of the row: mask the padding columns
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = j < nv ? x[j] : -INFINITY;
-          }
-          float m8[4];                                            // maxima of the four 8-column quarters
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            m8[q] = x[8 * q];
-#pragma unroll
-            for (int j = 1; j < 8; ++j) m8[q] = fmaxf(m8[q], x[8 * q + j]);
-          }
-          const float mx = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
-          if (EPI == 1) {
-            if (row_ok) p.gmax[row * p.ld_gmax + (tile % p.n_blocks) * (BN / 32) + c] = mx;
-          } else if (EPI == 4) {
-            // log-softmax pieces of this group (experiments/metrics.py:5): max, sum of exp(x - max), and the target's logit
-            float se = 0.f;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) se += __expf(x[j] - mx);          // padding columns hold -inf -> 0
-            if (row_ok) {
-              const long long g = row * p.ld_gmax + (tile % p.n_blocks) * (BN / 32) + c;
-              p.gmax[g] = mx;
-              p.gsum[g] = se;
-              const int tj = tcol - col0;
-              if (tj >= 0 && tj < 32) {
-                float tl = 0.f;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) tl = (j == tj) ? x[j] : tl;
-                p.tlogit[row] = tl;
-              }
+          for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) break;
+            const int c = cbase + u;
+            const int col0 = n0 + c * 32;
+            if (col0 >= p.N) {                                      // warp-uniform: group past the end of the row
+              if (EPI != 2 && row_ok) p.gmax[row * p.ld_gmax + (tile % p.n_blocks) * (BN / 32) + c] = -INFINITY;
+              if (EPI == 4 && row_ok) p.gsum[row * p.ld_gmax + (tile % p.n_blocks) * (BN / 32) + c] = 0.f;
+              continue;
             }
-          } else if (mx >= t0) {
-            // the group holds at least one logit >= thresh[row]: store its 32 logits (one full 128 B line of the row) and
-            // leave the element-wise work to the selection kernel -- the epilogue's instruction count no longer depends on
-            // where the candidates sit (per-lane divergent element scans made unrelated rows 2x slower than collinear ones)
-            bits |= 1u << (c - eh * (BN / 64));
-            float4* dst = reinterpret_cast<float4*>(p.sp_logits + row * p.sp_ld + col0);
+            const uint32_t* v = vv[u];
+            float x[32];
+            const float4* bs = reinterpret_cast<const float4*>(bias_cur + c * 32);
 #pragma unroll
-            for (int g = 0; g < 8; ++g) dst[g] = make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]);
+            for (int g = 0; g < 8; ++g) {
+              const float4 b4 = bs[g];
+              x[4 * g] = __uint_as_float(v[4 * g]) + b4.x;
+              x[4 * g + 1] = __uint_as_float(v[4 * g + 1]) + b4.y;
+              x[4 * g + 2] = __uint_as_float(v[4 * g + 2]) + b4.z;
+              x[4 * g + 3] = __uint_as_float(v[4 * g + 3]) + b4.w;
+            }
+            const int nv = p.N - col0;                              // valid columns in this group (>= 1)
+            if (nv < 32) {                                          // last group of the row: mask the padding columns
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = j < nv ? x[j] : -INFINITY;
+            }
+            float m8[4];                                            // maxima of the four 8-column quarters
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              m8[q] = x[8 * q];
+#pragma unroll
+              for (int j = 1; j < 8; ++j) m8[q] = fmaxf(m8[q], x[8 * q + j]);
+            }
+            const float mx = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+            if (EPI == 1) {
+              if (row_ok) p.gmax[row * p.ld_gmax + (tile % p.n_blocks) * (BN / 32) + c] = mx;
+            } else if (EPI == 4) {
+              // log-softmax pieces of this group (experiments/metrics.py:5): max, sum of exp(x - max), and the target's logit
+              float se = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) se += __expf(x[j] - mx);          // padding columns hold -inf -> 0
+              if (row_ok) {
+                const long long g = row * p.ld_gmax + (tile % p.n_blocks) * (BN / 32) + c;
+                p.gmax[g] = mx;
+                p.gsum[g] = se;
+                const int tj = tcol - col0;
+                if (tj >= 0 && tj < 32) {
+                  float tl = 0.f;
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) tl = (j == tj) ? x[j] : tl;
+                  p.tlogit[row] = tl;
+                }
+              }
+            } else if (mx >= t0) {
+              // the group holds at least one logit >= thresh[row]: store its 32 logits (one full 128 B line of the row) and
+              // leave the element-wise work to the selection kernel -- the epilogue's instruction count does not depend on
+              // where the candidates sit (per-lane divergent element scans made unrelated rows 2x slower than collinear ones)
+              bits |= 1u << (c - eh * kGroups);
+              float4* dst = reinterpret_cast<float4*>(p.sp_logits + row * p.sp_ld + col0);
+#pragma unroll
+              for (int g = 0; g < 8; ++g) dst[g] = make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]);
+            }
           }
         }
         // the accumulator is drained: hand the TMEM buffer back to the MMA warp BEFORE any list traffic
@@ -868,13 +966,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           p.hitmap[row * p.hit_ld + (long long)(((tile % p.n_blocks) * p.n_stride + p.n_offset) * 2 + eh)] = (unsigned char)bits;
           if (bits) atomicAdd(p.cand_count + row, __popc(bits));           // result unused: compiles to a fire-and-forget RED
         }
+        // publish the next tile's bias slice; the barrier also keeps this tile's slice alive until every reader is done
+        if (etid < BN) bias_buf[(it + 1) & 1][etid] = bias_next;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
     } else if (eh != 0) {
       // second epilogue group: idle for plain stores
     } else if (p.tma_store) {
       // ---- slab epilogue: each thread owns one accumulator row; a round covers 128 B of every row (32 fp32 or
       // 64 half columns), written 128B-swizzled into one of two 16 KB slabs and stored by one TMA instruction.
-      const uint32_t slabs = base + C::kStages * C::kStageBytes;
+      const uint32_t slabs = base + C::kRingBytes;
       const bool out32 = p.out_dtype == DH_F32;
       const int cpr = out32 ? 32 : 64;
       const int row_l = ew * 32 + lane;
@@ -1169,13 +1270,13 @@ int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long col
   return DH_OK;
 }
 
-template <int BN, bool PAIR, int EPI>
+template <int BN, bool PAIR, int EPI, bool ARES = false>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mr, const CUtensorMap& mi,
            TcParams& p, cudaStream_t s) {
-  using C = Cfg<BN, PAIR, EPI>;
+  using C = Cfg<BN, PAIR, EPI, ARES>;
   static bool attr = false;
   if (!attr) {
-    DH_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, PAIR, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    DH_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, PAIR, EPI, ARES>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr = true;
   }
   if (p.n_stride < 1) p.n_stride = 1;
@@ -1199,10 +1300,10 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, 
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    DH_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, PAIR, EPI>, ma, mb, mc, mr, mi, p));
+    DH_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, PAIR, EPI, ARES>, ma, mb, mc, mr, mi, p));
   } else {
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    gemm_tc_kernel<BN, PAIR, EPI><<<grid, kThreads, C::kSmemBytes, s>>>(ma, mb, mc, mr, mi, p);
+    gemm_tc_kernel<BN, PAIR, EPI, ARES><<<grid, kThreads, C::kSmemBytes, s>>>(ma, mb, mc, mr, mi, p);
   }
   DH_LAUNCH_OK();
   return DH_OK;
@@ -1211,6 +1312,11 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, 
 template <int EPI>
 int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mr, const CUtensorMap& mi,
               TcParams& p, int bn, bool pair, cudaStream_t s) {
+  // full vocab-projection pass (143 N tiles per row block, K <= 512): A resident in shared memory, W streamed.  Measured at
+  // 40 960 rows: 1109 vs 1159 us; the strided pass 1 (18 tiles per row block) re-loads A too often to gain and stays streamed.
+  static const bool ares_ok = !getenv("DH_TC_NO_ARES");
+  if (EPI == 2 && ares_ok && bn == 256 && pair && p.k_chunks <= 8 && !p.conv && !p.res_chunks && p.n_stride == 1)
+    return launch<256, true, EPI == 2 ? 2 : 1, true>(ma, mb, mc, mr, mi, p, s);
   if (EPI == 3) return pair ? launch<256, true, 3>(ma, mb, mc, mr, mi, p, s) : launch<256, false, 3>(ma, mb, mc, mr, mi, p, s);
   if (bn == 64) return launch<64, false, EPI>(ma, mb, mc, mr, mi, p, s);
   if (bn == 128) return pair ? launch<128, true, EPI>(ma, mb, mc, mr, mi, p, s) : launch<128, false, EPI>(ma, mb, mc, mr, mi, p, s);
