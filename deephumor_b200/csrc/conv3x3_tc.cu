@@ -566,6 +566,263 @@ conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   }
 }
 
+
+// ------------------------------------------------------------------------------------------- conv2 -> conv3 in one kernel
+// The tail of a layer1 identity bottleneck (torchvision resnet.py:150-161): relu(bn2(conv2 3x3 (64 -> 64))) feeding
+// relu(bn3(conv3 1x1 (64 -> 256)) + identity).  Both run at the HBM roofline one layer at a time, and conv3 is POINTWISE on
+// conv2's output, so the 8 x 32 pixel tile that conv2 leaves in the swizzled slab (256 pixel rows x 64 channels, K-major) is
+// exactly the A operand of conv3: it never goes to HBM (-410 MB per block and 512 images).  Per tile:
+//   MMA warp    conv2 as in conv3x3_halo_t_kernel (weights = M, 256 pixels = N, nine shifted halo views) into TMEM columns
+//               [0, 256); conv3 for each 128-pixel half as 4 tcgen05.mma of 128 x 256 x 16 (A = the slab half, B = the resident
+//               64 x 256 weight tile) into columns [256, 512).  The issue order is software-pipelined -- conv3(half 0),
+//               conv2 of the NEXT tile, conv3(half 1) -- so the tensor core works while the epilogue drains.
+//   epilogue    (1) conv2 accumulator -> bias, ReLU, 16-bit, transposed into the slab; (2) per half: conv3 accumulator + bias
+//               + identity (read straight from the block input, 128 contiguous bytes per pixel and round) -> ReLU -> slab ->
+//               4-D TMA store of 64-channel boxes.
+constexpr int kFW3Bytes = 256 * 128;                              // conv3 weights [256 cout][64] K-major
+constexpr int kFSmemBytes = 1024 + kTHaloBytes + 9 * 8192 + kFW3Bytes + 256 * 128 + 2 * 128 * 128 + 1024 + 512;
+
+struct FusedTailParams {
+  int n, H, W, tiles_x, tiles_y;
+  const float* bias2; const float* bias3;
+  const void* residual;                                         // block input [n, H, W, 256]
+  int dtype;
+  int* error;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_c3_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w2,
+                        const __grid_constant__ CUtensorMap map_w3, const __grid_constant__ CUtensorMap map_out,
+                        const FusedTailParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t halo = base;                                        // 10 x 34 pixels x 128 B
+  const uint32_t w2s = base + kTHaloBytes;                           // 9 taps x 8 KB
+  const uint32_t w3s = w2s + 9 * 8192;                               // 256 x 128 B
+  const uint32_t y2s = w3s + kFW3Bytes;                              // conv2 output: 256 pixels x 128 B = conv3's A operand
+  const uint32_t outs = y2s + 256 * 128;                             // two 128-pixel x 128 B store slabs
+  float* bias3_s = reinterpret_cast<float*>(gen + kTHaloBytes + 9 * 8192 + kFW3Bytes + 256 * 128 + 2 * 128 * 128);
+  const uint32_t bars = outs + 2 * 128 * 128 + 1024;
+  const uint32_t hfull = bars, hempty = bars + 8, wfull = bars + 16, t2full = bars + 24, t2empty = bars + 32,
+                 y2full = bars + 40, y2free = bars + 48, t3full = bars + 56, t3empty = bars + 64;
+  uint32_t* tmem_word = reinterpret_cast<uint32_t*>(gen + kTHaloBytes + 9 * 8192 + kFW3Bytes + 256 * 128 + 2 * 128 * 128 + 1024 + 128);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 1 && lane == 0) {
+    mbar_init(hfull, 1); mbar_init(hempty, 1); mbar_init(wfull, 1);
+    mbar_init(t2full, 1); mbar_init(t2empty, 4);
+    mbar_init(y2full, 1); mbar_init(y2free, 1);
+    mbar_init(t3full, 1); mbar_init(t3empty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  } else if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_word)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 256; i += kThreads) bias3_s[i] = p.bias3 ? __ldg(p.bias3 + i) : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_word);
+
+  const int tiles = p.n * p.tiles_y * p.tiles_x;
+  const int n_my = tiles > (int)blockIdx.x ? (tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  auto decode = [&](int it, int& img, int& y0, int& x0) {
+    const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+    x0 = (tile % p.tiles_x) * 8;
+    const int sp = tile / p.tiles_x;
+    y0 = (sp % p.tiles_y) * 32;
+    img = sp / p.tiles_y;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================================================================== TMA producer: weights once, one halo per tile
+      mbar_expect_tx(wfull, 9 * 8192 + kFW3Bytes);
+      for (int t = 0; t < 9; ++t) tma_load_2d(w2s + t * 8192, &map_w2, wfull, t * 64, 0);
+      tma_load_2d(w3s, &map_w3, wfull, 0, 0);
+      for (int it = 0; it < n_my; ++it) {
+        int img, y0, x0;
+        decode(it, img, y0, x0);
+        mbar_wait(hempty, (uint32_t)((it & 1) ^ 1), p.error, 31);
+        mbar_expect_tx(hfull, kTHaloTx);
+        tma_load_4d(halo, &map_x, hfull, 0, x0 - 1, y0 - 1, img);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_my > 0) {
+      // ===================================================================== MMA issuer
+      const uint32_t fmt = p.dtype == DH_BF16 ? 1u : 0u;
+      const uint32_t idesc2 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
+      const uint32_t idesc3 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      mbar_wait(wfull, 0u, p.error, 32);
+      tc_fence_after();
+      auto conv2 = [&](int it) {
+        mbar_wait(hfull, (uint32_t)(it & 1), p.error, 33);
+        mbar_wait(t2empty, (uint32_t)((it & 1) ^ 1), p.error, 34);
+        tc_fence_after();
+        for (int t = 0; t < 9; ++t) {
+          const int r = t / 3, s = t - r * 3;
+          const uint64_t da = umma_desc(w2s + t * 8192, 1024);                                    // 64 channels x 64 K
+          const uint64_t db = umma_desc(halo + (uint32_t)((r * kHaloW + s) * 128), kHaloW * 128);   // 256 pixels, shifted view
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (t | k) ? 1u : 0u);
+        }
+        tc_commit(hempty);
+        tc_commit(t2full);
+      };
+      auto conv3 = [&](int it, int h) {
+        const int q = 2 * it + h;
+        if (h == 0) mbar_wait(y2full, (uint32_t)(it & 1), p.error, 35);
+        mbar_wait(t3empty, (uint32_t)((q & 1) ^ 1), p.error, 36);
+        tc_fence_after();
+        const uint64_t da = umma_desc(y2s + (uint32_t)h * (128 * 128), 1024);                     // 128 pixels x 64 K
+        const uint64_t db = umma_desc(w3s, 1024);                                                 // 256 channels x 64 K
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc_mma(tmem_base + 256u, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc3, k ? 1u : 0u);
+        tc_commit(t3full);
+        if (h == 1) tc_commit(y2free);                            // the slab may be rewritten once these MMAs have read it
+      };
+      conv2(0);
+      for (int it = 0; it < n_my; ++it) {
+        conv3(it, 0);
+        if (it + 1 < n_my) conv2(it + 1);
+        conv3(it, 1);
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================================================================= epilogue
+    const int ew = warp - 4;
+    const int ch = ew * 16 + (lane & 15);                       // conv2 accumulator row (M = 64 layout) of this lane
+    const bool active = lane < 16;
+    const float bias2_v = (p.bias2 && active) ? __ldg(p.bias2 + ch) : 0.f;
+    const bool elected = (warp == 4 && lane == 0);
+    const uint32_t ch_chunk = (uint32_t)(ch >> 3), ch_off = (uint32_t)((ch & 7) * 2);
+    const int row_l = ew * 32 + lane;                           // conv3 accumulator row = pixel of the half
+    const uint32_t swz = (uint32_t)(row_l & 7);
+    uint32_t round_ctr = 0;
+    for (int it = 0; it < n_my; ++it) {
+      int img, y0, x0;
+      decode(it, img, y0, x0);
+      // ---- (1) conv2 accumulator -> slab (conv3's A operand)
+      mbar_wait(t2full, (uint32_t)(it & 1), p.error, 37);
+      mbar_wait(y2free, (uint32_t)((it & 1) ^ 1), p.error, 38);  // conv3 of the previous tile has read the slab
+      tc_fence_after();
+      {
+        const uint32_t tmem_row = tmem_base + ((uint32_t)(ew * 32) << 16);
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {                           // 32 pixels per TMEM load
+          uint32_t v[32];
+          tc_ld32(tmem_row + (uint32_t)(c * 32), v);
+          if (active) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float x = fmaxf(__uint_as_float(v[j]) + bias2_v, 0.f);
+              const uint32_t pix = (uint32_t)(c * 32 + j);
+              const uint32_t addr = y2s + pix * 128u + ((ch_chunk ^ (pix & 7u)) << 4) + ch_off;
+              if (p.dtype == DH_BF16) {
+                const __nv_bfloat16 hv = __float2bfloat16_rn(x);
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const unsigned short*>(&hv)) : "memory");
+              } else {
+                const __half hv = __float2half_rn(x);
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const unsigned short*>(&hv)) : "memory");
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t2empty);                      // conv2's accumulator is drained
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (elected) mbar_arrive(y2full);
+      // ---- (2) conv3 accumulator of each 128-pixel half + bias + identity -> ReLU -> store
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int q = 2 * it + h;
+        const int pix = h * 128 + row_l, gy = y0 + (pix >> 3), gx = x0 + (pix & 7);
+        const bool inb = gy < p.H && gx < p.W;
+        const uint4* res = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.residual) +
+                                                           (((long long)img * p.H + gy) * p.W + gx) * 256);
+        mbar_wait(t3full, (uint32_t)(q & 1), p.error, 39);
+        tc_fence_after();
+        const uint32_t tmem_row = tmem_base + ((uint32_t)(ew * 32) << 16) + 256u;
+#pragma unroll 1
+        for (int rd = 0; rd < 4; ++rd) {
+          uint4 rv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rv[j] = inb ? __ldg(res + rd * 8 + j) : make_uint4(0u, 0u, 0u, 0u);
+          const uint32_t slab = outs + (round_ctr & 1u) * (128 * 128);
+          if (elected && round_ctr >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          uint32_t v[64];
+          tc_ld32(tmem_row + (uint32_t)(rd * 64), v);
+          tc_ld32(tmem_row + (uint32_t)(rd * 64 + 32), v + 32);
+          if (rd == 3) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t3empty);                // conv3's accumulator now lives in registers
+          }
+          const float4* b4 = reinterpret_cast<const float4*>(bias3_s + rd * 64);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {                         // 8 channels per 16-byte slab chunk
+            const float4 ba = b4[2 * j], bb = b4[2 * j + 1];
+            const uint32_t rr[4] = {rv[j].x, rv[j].y, rv[j].z, rv[j].w};
+            float r8[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (p.dtype == DH_BF16) {
+                const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&rr[e]);
+                r8[2 * e] = __low2float(t); r8[2 * e + 1] = __high2float(t);
+              } else {
+                const __half2 t = *reinterpret_cast<const __half2*>(&rr[e]);
+                r8[2 * e] = __low2float(t); r8[2 * e + 1] = __high2float(t);
+              }
+            }
+            const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a0 = fmaxf(__uint_as_float(v[8 * j + 2 * e]) + bv[2 * e] + r8[2 * e], 0.f);
+              const float a1 = fmaxf(__uint_as_float(v[8 * j + 2 * e + 1]) + bv[2 * e + 1] + r8[2 * e + 1], 0.f);
+              if (p.dtype == DH_BF16) {
+                __nv_bfloat162 t = __floats2bfloat162_rn(a0, a1);
+                w[e] = *reinterpret_cast<uint32_t*>(&t);
+              } else {
+                __half2 t = __floats2half2_rn(a0, a1);
+                w[e] = *reinterpret_cast<uint32_t*>(&t);
+              }
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slab + (uint32_t)row_l * 128u + (((uint32_t)j ^ swz) << 4)),
+                         "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (elected) {
+            // slab rows are the half's pixels in (y, x) order: one box {64 channels, 8, 16, 1}; pixels outside the image
+            // are clipped by TMA
+            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(&map_out)),
+                         "r"(slab), "r"(rd * 64), "r"(x0), "r"(y0 + h * 16), "r"(img)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          ++round_ctr;
+        }
+      }
+    }
+    if (elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -671,4 +928,54 @@ extern "C" int dh_conv3x3_halo_tc(const void* x, const void* w, const float* bia
   }
   if (transposed) return launch_halo_t(mx, mw, my, p, stream);
   return bn == 128 ? launch_halo<128>(mx, mw, my, p, stream) : launch_halo<64>(mx, mw, my, p, stream);
+}
+
+// Tail of a layer1-shaped identity bottleneck in ONE launch (torchvision resnet.py:150-161): y = relu(bn3(conv3(relu(bn2(
+// conv2(y1))))) + x) with conv2 3x3 / stride 1 / pad 1 (64 -> 64) and conv3 1x1 (64 -> 256); y1 [n,H,W,64], x and y
+// [n,H,W,256] NHWC, w2 [64][3][3][64], w3 [256][64] (BN folded), all `dtype`.  conv2's output never reaches HBM.
+extern "C" int dh_bottleneck_tail_tc(const void* y1, const void* w2, const float* bias2, const void* w3, const float* bias3,
+                                     const void* x, void* y, int n, int H, int W, int dtype, cudaStream_t stream) {
+  DH_ARG(y1 && w2 && w3 && x && y && n >= 0 && H > 0 && W > 0);
+  DH_ARG(dtype == DH_BF16 || dtype == DH_F16);
+  DH_ARG(((uintptr_t)y1 % 16) == 0 && ((uintptr_t)w2 % 16) == 0 && ((uintptr_t)w3 % 16) == 0 && ((uintptr_t)x % 16) == 0 &&
+         ((uintptr_t)y % 16) == 0);
+  if (n == 0) return DH_OK;
+  int rc = halo_init();
+  if (rc) return rc;
+  FusedTailParams p{};
+  p.n = n; p.H = H; p.W = W; p.tiles_x = dh_cdiv(W, 8); p.tiles_y = dh_cdiv(H, 32);
+  p.bias2 = bias2; p.bias3 = bias3; p.residual = x; p.dtype = dtype; p.error = g_error;
+  CUtensorMap mx, mw2, mw3, mo;
+  rc = map_nhwc(&mx, y1, n, H, W, 64, kHaloW, kTHaloH, dtype);
+  if (rc) return rc;
+  rc = map_nhwc(&mo, y, n, H, W, 256, 8, 16, dtype);
+  if (rc) return rc;
+  const CUtensorMapDataType ty = dtype == DH_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  cuuint32_t estr[2] = {1, 1};
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)9 * 64, 64};
+    cuuint64_t strides[1] = {(cuuint64_t)9 * 64 * 2};
+    cuuint32_t box[2] = {64, 64};
+    if (g_encode(&mw2, ty, 2, const_cast<void*>(w2), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return dh_fail(DH_ERR_ARG, "cuTensorMapEncodeTiled rejected the conv2 weights", __FILE__, __LINE__);
+  }
+  {
+    cuuint64_t dims[2] = {64, 256};
+    cuuint64_t strides[1] = {64 * 2};
+    cuuint32_t box[2] = {64, 256};
+    if (g_encode(&mw3, ty, 2, const_cast<void*>(w3), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return dh_fail(DH_ERR_ARG, "cuTensorMapEncodeTiled rejected the conv3 weights", __FILE__, __LINE__);
+  }
+  static bool attr = false;
+  if (!attr) {
+    DH_CUDA(cudaFuncSetAttribute(conv3x3_c3_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmemBytes));
+    attr = true;
+  }
+  const int tiles = n * p.tiles_y * p.tiles_x;
+  const int grid = tiles < g_sms ? tiles : g_sms;
+  conv3x3_c3_fused_kernel<<<grid, kThreads, kFSmemBytes, stream>>>(mx, mw2, mw3, mo, p);
+  DH_LAUNCH_OK();
+  return DH_OK;
 }

@@ -9,6 +9,8 @@
 //   dh_xfmr_step          one new position through the whole decoder stack with the KV cache (models/transformers.py:343-377
 //                         per layer, :455-486 around it): embed -> per layer [Q|K|V, self-attention, fc_o + LN, (Q, cross-
 //                         attention, fc_o + LN), fc_1, fc_2 + LN].
+#include <stdlib.h>
+
 #include <new>
 
 #include "common.cuh"
@@ -104,33 +106,65 @@ extern "C" int dh_resnet50_forward(const dh_ctx* ctx, const void* images_nchw, i
   else
     rc = dh_stem_pool_tc((const float*)images_nchw, w.stem_w, w.stem_b, xb[0], n, H, W, dt, stream);
   if (rc) return rc;
+  // One bottleneck (torchvision resnet.py:143-163) for `cnt` images: x -> out, through the conv1 / conv2 scratch buffers
+  auto bottleneck = [&](int s, int b, int blk, const void* x, void* out, int cnt, int hw, int cin, float* pool) -> int {
+    const int mid = 64 << s, cout = 4 * mid;
+    const int stride = (b == 0 && s > 0) ? 2 : 1;
+    const int ho = (hw + 2 - 3) / stride + 1;
+    // conv1 1x1 + bn1 + relu (resnet.py:146-148)
+    int r = dh_conv2d_tc(x, w.conv_w[blk][0], w.conv_b[blk][0], nullptr, y1, cnt, hw, hw, cin, mid, 1, 1, 1, 0, 1, dt, 0, stream);
+    if (r) return r;
+    // layer1 identity blocks: conv2 -> conv3 + identity in one launch, conv2's output stays on chip (dh_bottleneck_tail_tc)
+    static const bool fused_tail = !getenv("DH_NO_FUSED_TAIL");
+    if (fused_tail && b > 0 && mid == 64 && stride == 1 && cin == 256 && !pool)
+      return dh_bottleneck_tail_tc(y1, w.conv_w[blk][1], w.conv_b[blk][1], w.conv_w[blk][2], w.conv_b[blk][2], x, out, cnt, hw, hw, dt,
+                                   stream);
+    // conv2 3x3 (stride on conv2: ResNet v1.5, resnet.py:109-110) + bn2 + relu (:150-152)
+    if (stride == 1 && hw >= 28 && mid == 64)
+      r = dh_conv3x3_halo_tc(y1, w.conv_w[blk][1], w.conv_b[blk][1], y2, cnt, hw, hw, mid, mid, 1, dt, stream);
+    else
+      r = dh_conv2d_tc(y1, w.conv_w[blk][1], w.conv_b[blk][1], nullptr, y2, cnt, hw, hw, mid, mid, 3, 3, stride, 1, 1, dt, 0, stream);
+    if (r) return r;
+    // conv3 1x1 + bn3 (+ downsample branch of a stage's first block, :157-158) + identity + relu (:154-161)
+    if (b == 0)
+      return dh_conv1x1_dual_tc(y2, x, w.dual_w[s], w.dual_b[s], out, cnt, ho, ho, mid, hw, hw, cin, stride, cout, 1, dt, 0, stream);
+    if (pool)
+      return dh_gemm_tc_pool(y2, mid, w.conv_w[blk][2], mid, dt, w.conv_b[blk][2], x, cout, out, cout, cnt * ho * ho, cout, mid, 1,
+                             ho * ho, pool, cout, stream);
+    return dh_conv2d_tc(y2, w.conv_w[blk][2], w.conv_b[blk][2], x, out, cnt, ho, ho, mid, cout, 1, 1, 1, 0, 1, dt, 0, stream);
+  };
   int cur = 0, hw = 56, cin = 64, blk = 0;
-  for (int s = 0; s < 4; ++s) {
+  // layer1 works on 56 x 56 maps of 64 - 256 channels (1.6 MB per image and tensor) and every one of its ten convolutions
+  // runs at the HBM roofline when the batch goes through one layer at a time.  Taking `l2_chunk` images through the WHOLE
+  // stage before the next ones keeps the block-to-block activations inside the 126 MB L2 (write-back): only the stage's
+  // input and output cross HBM.  The two block-output scratch maps of a chunk live in the unused three quarters of xb[cur]
+  // (the stem output has 64 of the 256 channels the buffer is sized for).
+  static const int l2_chunk = getenv("DH_TRUNK_L2_CHUNK") ? atoi(getenv("DH_TRUNK_L2_CHUNK")) : 0;
+  if (l2_chunk > 0 && n > l2_chunk && 2ll * l2_chunk * 256 <= (long long)n * 192) {
+    const long long px = 56ll * 56;
+    unsigned char* in0 = (unsigned char*)xb[0];
+    unsigned char* scratch = in0 + al((long long)n * px * 64 * 2);
+    for (int i0 = 0; i0 < n; i0 += l2_chunk) {
+      const int cnt = n - i0 < l2_chunk ? n - i0 : l2_chunk;
+      void* sa = scratch;
+      void* sb = scratch + al((long long)l2_chunk * px * 256 * 2);
+      const void* x = in0 + (long long)i0 * px * 64 * 2;
+      void* outp = (unsigned char*)xb[1] + (long long)i0 * px * 256 * 2;
+      rc = bottleneck(0, 0, 0, x, sa, cnt, 56, 64, nullptr);
+      if (!rc) rc = bottleneck(0, 1, 1, sa, sb, cnt, 56, 256, nullptr);
+      if (!rc) rc = bottleneck(0, 2, 2, sb, outp, cnt, 56, 256, nullptr);
+      if (rc) return rc;
+    }
+    cur = 1; cin = 256; blk = 3;
+  }
+  for (int s = (blk ? 1 : 0); s < 4; ++s) {
     const int mid = 64 << s, cout = 4 * mid;
     for (int b = 0; b < kBlocks[s]; ++b, ++blk) {
       const int stride = (b == 0 && s > 0) ? 2 : 1;
       const int ho = (hw + 2 - 3) / stride + 1;
-      const void* x = xb[cur];
       const bool last = (s == 3 && b == kBlocks[3] - 1);
       void* out = last ? feat : xb[cur ^ 1];
-      // conv1 1x1 + bn1 + relu (resnet.py:146-148)
-      rc = dh_conv2d_tc(x, w.conv_w[blk][0], w.conv_b[blk][0], nullptr, y1, n, hw, hw, cin, mid, 1, 1, 1, 0, 1, dt, 0, stream);
-      if (rc) return rc;
-      // conv2 3x3 (stride on conv2: ResNet v1.5, resnet.py:109-110) + bn2 + relu (:150-152)
-      if (stride == 1 && hw >= 28 && mid == 64)
-        rc = dh_conv3x3_halo_tc(y1, w.conv_w[blk][1], w.conv_b[blk][1], y2, n, hw, hw, mid, mid, 1, dt, stream);
-      else
-        rc = dh_conv2d_tc(y1, w.conv_w[blk][1], w.conv_b[blk][1], nullptr, y2, n, hw, hw, mid, mid, 3, 3, stride, 1, 1, dt, 0, stream);
-      if (rc) return rc;
-      // conv3 1x1 + bn3 (+ downsample branch of a stage's first block, :157-158) + identity + relu (:154-161)
-      if (b == 0) {
-        rc = dh_conv1x1_dual_tc(y2, x, w.dual_w[s], w.dual_b[s], out, n, ho, ho, mid, hw, hw, cin, stride, cout, 1, dt, 0, stream);
-      } else if (last && pooled && ho * ho <= 128) {
-        rc = dh_gemm_tc_pool(y2, mid, w.conv_w[blk][2], mid, dt, w.conv_b[blk][2], x, cout, out, cout, n * ho * ho, cout, mid, 1,
-                             ho * ho, pooled, cout, stream);
-      } else {
-        rc = dh_conv2d_tc(y2, w.conv_w[blk][2], w.conv_b[blk][2], x, out, n, ho, ho, mid, cout, 1, 1, 1, 0, 1, dt, 0, stream);
-      }
+      rc = bottleneck(s, b, blk, xb[cur], out, n, hw, cin, (last && pooled && ho * ho <= 128) ? pooled : nullptr);
       if (rc) return rc;
       cur ^= 1;
       hw = ho;

@@ -59,9 +59,11 @@ class LSTMDecoderRT:
             logits=torch.empty(rows, self.ldv, dtype=torch.float32, device=dev) if logits else None)
         return ws
 
-    def _step(self, ws, rows, cur, parent, logits=True):
-        """One LSTM time step over `rows` rows; A[l][:, in:] must already hold the (gathered) recurrent h."""
+    def _step(self, ws, rows, cur, parent, logits=True, top_out=None):
+        """One LSTM time step over `rows` rows; A[l][:, in:] must already hold the (gathered) recurrent h.  The top layer's
+        h goes to top_out ([rows, H], any row stride) or ws['top']."""
         L, H = self.L, self.H
+        top = ws['top'][:rows] if top_out is None else top_out
         if self.stacked:
             # one zeroed counter region per launch (the decode zeroes the pool once, before its first step)
             per = (L - 1) * ((rows + 127) // 128)
@@ -70,14 +72,14 @@ class LSTMDecoderRT:
             ws['ready_next'] = off + per
             with ops.PROFILE.range('lstm_layers', sum(2.0 * rows * 4 * H * (i + H) for i in self.in_dims)):
                 ops.lstm_stack_tc(ws['A_all'], self.in_dims, self.Wpk_all, self.bpk_all, ws['c'][cur], parent,
-                                  ws['c'][1 - cur], ws['top'][:rows], ws['hs'], ws['ready'][off:off + per], rows)
+                                  ws['c'][1 - cur], top, ws['hs'], ws['ready'][off:off + per], rows)
             if logits:
                 with ops.PROFILE.range('vocab_gemm', 2.0 * rows * self.V * H):
-                    ops.gemm(ws['top'][:rows], self.Wc, ws['logits'][:rows, :self.V], bias=self.bc)
+                    ops.gemm(top, self.Wc, ws['logits'][:rows, :self.V], bias=self.bc)
             return
         for l in range(L):
             A = ws['A'][l][:rows]
-            nxt = ws['A'][l + 1][:rows, :H] if l + 1 < L else ws['top'][:rows]
+            nxt = ws['A'][l + 1][:rows, :H] if l + 1 < L else top
             if self.fused_cell:
                 with ops.PROFILE.range('lstm_layers', 2.0 * rows * 4 * H * A.shape[1]):
                     ops.lstm_layer_tc(A, self.Wpk[l], self.bpk[l], ws['c'][cur][l], parent, ws['c'][1 - cur][l][:rows],
@@ -88,7 +90,7 @@ class LSTMDecoderRT:
                 ops.lstm_cell(gates, ws['c'][cur][l], parent, ws['c'][1 - cur][l][:rows], nxt, ws['hs'][l][:rows])
         if logits:
             with ops.PROFILE.range('vocab_gemm', 2.0 * rows * self.V * H):
-                ops.gemm(ws['top'][:rows], self.Wc, ws['logits'][:rows, :self.V], bias=self.bc)
+                ops.gemm(top, self.Wc, ws['logits'][:rows, :self.V], bias=self.bc)
 
     def _select(self, pl, rows, rpi, step, done, B, top_k, temperature, unk_index, noise_mode, beam_step=None,
                 lstm_next=None):
@@ -241,6 +243,9 @@ class LSTMDecoderRT:
         ws = self._alloc(N, logits=False)
         tops = torch.zeros(N, tmax, H, dtype=self.dtype, device=dev)
         cap32 = captions.to(device=dev, dtype=torch.int32)
+        if self.stacked:                                 # one zeroed ready-counter region per time step's launch
+            ws['ready'] = torch.zeros(tmax * (self.L - 1) * ((N + 127) // 128), dtype=torch.int32, device=dev)
+            ws['ready_next'] = 0
         cur = 0
         for t in range(tmax):
             if t == 0:
@@ -248,11 +253,9 @@ class LSTMDecoderRT:
             else:
                 ops.gather_rows(self.table, cap32[:, t - 1].contiguous(), ws['A'][0][:N, :self.E])
                 self._recur(ws, N, None)
-            L = self.L
-            for l in range(L):
-                ops.gemm(ws['A'][l][:N], self.Wcat[l], ws['gates'][:N], bias=self.bias[l])
-                nxt = ws['A'][l + 1][:N, :H] if l + 1 < L else tops[:, t]
-                ops.lstm_cell(ws['gates'][:N], ws['c'][cur][l], None, ws['c'][1 - cur][l][:N], nxt, ws['hs'][l][:N])
+            # the same step as generate(): in tensor-core mode every layer of the step is one persistent launch with the cell
+            # update in the gate contraction's epilogue (dh_lstm_stack_tc), the top layer writing straight into tops[:, t]
+            self._step(ws, N, cur, None, logits=False, top_out=tops[:, t])
             cur = 1 - cur
         # pad_packed_sequence zero-fills outputs at t >= length before the classifier (rnn_models.py:41-44)
         keep = (torch.arange(tmax, device=dev).unsqueeze(0) < lengths.unsqueeze(1)).unsqueeze(-1)

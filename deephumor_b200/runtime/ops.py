@@ -190,6 +190,16 @@ def conv1x1_dual(x1, x2, w_cat, bias, y, stride2, relu, tile_n=0):
              int(relu), code(x1), tile_n, stream())
 
 
+def bottleneck_tail(y1, w2, b2, w3, b3, x, y):
+    """y = relu(conv3(relu(conv2(y1) + b2)) + b3 + x): conv2 3x3 (64 -> 64) and conv3 1x1 (64 -> 256) of a layer1 identity
+    bottleneck in one launch (dh_bottleneck_tail_tc)."""
+    n, H, W, C = y1.shape
+    assert C == 64 and w2.shape == (64, 3, 3, 64) and w3.shape[0] == 256 and w3.numel() == 256 * 64
+    assert x.shape == (n, H, W, 256) and y.shape == (n, H, W, 256)
+    assert all(t.is_contiguous() and t.dtype == y1.dtype for t in (y1, w2, w3, x, y))
+    LIB.call('dh_bottleneck_tail_tc', ptr(y1), ptr(w2), ptr(b2), ptr(w3), ptr(b3), ptr(x), ptr(y), n, H, W, code(y1), stream())
+
+
 def im2col_stem(images, A, kh, kw, stride, pad):
     """images [n,3,H,W] fp32 NCHW -> A [n*Ho*Wo, Kp] bf16, k = (r*kw+s)*3 + c, zero padded."""
     n, c, H, W = images.shape

@@ -124,6 +124,11 @@ int dh_conv1x1_dual_tc(const void* x1, const void* x2, const void* w_cat, const 
  * (csrc/conv3x3_tc.cu).  x / w / y as in dh_conv2d_tc; Cin % 64 == 0, Cout % 64 == 0. */
 int dh_conv3x3_halo_tc(const void* x, const void* w, const float* bias, void* y, int n, int H, int W, int Cin, int Cout,
                        int relu, int dtype, cudaStream_t stream);
+/* Tail of a layer1-shaped identity bottleneck in ONE launch (torchvision resnet.py:150-161): y = relu(bn3(conv3(relu(bn2(conv2(
+ * y1))))) + x), conv2 3x3 / 1 / 1 (64 -> 64), conv3 1x1 (64 -> 256); y1 [n,H,W,64], x / y [n,H,W,256] NHWC, w2 [64][3][3][64],
+ * w3 [256][64] (BN folded).  conv2's output tile stays in shared memory as conv3's operand (never written to HBM). */
+int dh_bottleneck_tail_tc(const void* y1, const void* w2, const float* bias2, const void* w3, const float* bias3, const void* x,
+                          void* y, int n, int H, int W, int dtype, cudaStream_t stream);
 /* Explicit gathers: the C_in = 3 stem straight from the NCHW fp32 image into A[n*Ho*Wo, k_padded] (bf16 / f16) with
  * k = (r*kw + s)*3 + c (encoders.py:56 -> resnet.py:197 conv1), and a generic NHWC gather A[m, (r*kw+s)*C + c]. */
 int dh_im2col_stem(const float* images_nchw, void* A, int n, int H, int W, int kh, int kw, int stride, int pad,

@@ -451,3 +451,30 @@ def test_gemm_layernorm_epilogue(M, K, dt):
     ops.gemm_ln(A, W, None, None, g, be, out2)                    # no bias / residual
     ref2 = F.layer_norm(A.double() @ W.double().T, (N,), g.double(), be.double(), 1e-5).float()
     assert H.rel_err(out2.float(), ref2) < tol
+
+
+@pytest.mark.parametrize('dt', [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize('n,H_,W_', [(2, 56, 56), (1, 32, 8), (3, 40, 24), (1, 56, 60), (5, 64, 16)])
+def test_bottleneck_tail_fused_conv2_conv3(n, H_, W_, dt):
+    """dh_bottleneck_tail_tc (conv2 3x3 + bn2 + relu -> conv3 1x1 + bn3 + identity + relu of a layer1 bottleneck, torchvision
+    resnet.py:150-161, in one launch) against a float64 restatement on the same rounded operands (conv2's output rounded to
+    the storage type, as the two-launch form stores it) and against the two launches themselves."""
+    y1 = rnd(n, 64, H_, W_, seed=1).to(dt)
+    w2, b2 = rnd(64, 64, 3, 3, seed=2, scale=0.06).to(dt), rnd(64, seed=3, scale=0.2)
+    w3, b3 = rnd(256, 64, 1, 1, seed=4, scale=0.15).to(dt), rnd(256, seed=5, scale=0.2)
+    x = rnd(n, 256, H_, W_, seed=6).to(dt)
+    y2 = F.relu(F.conv2d(y1.double(), w2.double(), b2.double(), 1, 1)).to(dt)
+    ref = F.relu(F.conv2d(y2.double(), w3.double(), b3.double()) + x.double()).float().permute(0, 2, 3, 1).contiguous()
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().to(DEV)
+    y1d, xd = nhwc(y1), nhwc(x)
+    w2d, w3d = w2.permute(0, 2, 3, 1).contiguous().to(DEV), w3.permute(0, 2, 3, 1).contiguous().to(DEV)
+    out = torch.zeros(n, H_, W_, 256, dtype=dt, device=DEV)
+    ops.bottleneck_tail(y1d, w2d, b2.to(DEV), w3d, b3.to(DEV), xd, out)
+    tol = 4e-3 if dt == torch.bfloat16 else 6e-4
+    assert H.rel_err(out.float(), ref) < tol
+    y2d = torch.zeros(n, H_, W_, 64, dtype=dt, device=DEV)
+    two = torch.zeros_like(out)
+    ops.conv2d(y1d, w2d, b2.to(DEV), y2d, 1, 1, True)
+    ops.conv2d(y2d, w3d, b3.to(DEV), two, 1, 0, True, residual=xd)
+    assert H.rel_err(out.float(), two.float()) < tol
+    assert float((out.float() - two.float()).abs().max()) <= 2 * float(ref.abs().max()) * (2 ** -8 if dt == torch.bfloat16 else 2 ** -11)
