@@ -104,6 +104,12 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// Packed fp32 pairs (FADD2 on sm_100a): two IEEE fp32 additions per issued instruction
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ f32x2 pk2u(uint32_t a, uint32_t b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ void un2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 // K-major, 128B-swizzled operand: start >> 4 | stride between 8-row groups (SBO) | descriptor version 1 | SWIZZLE_128B.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo_bytes) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(sbo_bytes >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
@@ -580,7 +586,8 @@ conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
 //               + identity (read straight from the block input, 128 contiguous bytes per pixel and round) -> ReLU -> slab ->
 //               4-D TMA store of 64-channel boxes.
 constexpr int kFW3Bytes = 256 * 128;                              // conv3 weights [256 cout][64] K-major
-constexpr int kFSmemBytes = 1024 + kTHaloBytes + 9 * 8192 + kFW3Bytes + 256 * 128 + 2 * 128 * 128 + 1024 + 512;
+constexpr int kFHaloBytes = 2 * kHaloBytes;                        // two 10 x 18 halos: rows 0-15 and 16-31 of the 8 x 32 tile
+constexpr int kFSmemBytes = 1024 + kFHaloBytes + 9 * 8192 + kFW3Bytes + 256 * 128 + 2 * 128 * 128 + 1024 + 512;
 
 struct FusedTailParams {
   int n, H, W, tiles_x, tiles_y;
@@ -590,37 +597,41 @@ struct FusedTailParams {
   int* error;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+constexpr int kFThreads = 384;                                   // producer / MMA / TMEM warps + eight epilogue warps
+__global__ void __launch_bounds__(kFThreads, 1)
 conv3x3_c3_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w2,
                         const __grid_constant__ CUtensorMap map_w3, const __grid_constant__ CUtensorMap map_out,
                         const FusedTailParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t halo = base;                                        // 10 x 34 pixels x 128 B
-  const uint32_t w2s = base + kTHaloBytes;                           // 9 taps x 8 KB
+  const uint32_t halo = base;                                        // 2 x (10 x 18 pixels x 128 B): one per 16-row half
+  const uint32_t w2s = base + kFHaloBytes;                           // 9 taps x 8 KB
   const uint32_t w3s = w2s + 9 * 8192;                               // 256 x 128 B
   const uint32_t y2s = w3s + kFW3Bytes;                              // conv2 output: 256 pixels x 128 B = conv3's A operand
   const uint32_t outs = y2s + 256 * 128;                             // two 128-pixel x 128 B store slabs
-  float* bias3_s = reinterpret_cast<float*>(gen + kTHaloBytes + 9 * 8192 + kFW3Bytes + 256 * 128 + 2 * 128 * 128);
+  float* bias3_s = reinterpret_cast<float*>(gen + kFHaloBytes + 9 * 8192 + kFW3Bytes + 256 * 128 + 2 * 128 * 128);
   const uint32_t bars = outs + 2 * 128 * 128 + 1024;
-  const uint32_t hfull = bars, hempty = bars + 8, wfull = bars + 16, t2full = bars + 24, t2empty = bars + 32,
-                 y2full = bars + 40, y2free = bars + 48, t3full = bars + 56, t3empty = bars + 64;
-  uint32_t* tmem_word = reinterpret_cast<uint32_t*>(gen + kTHaloBytes + 9 * 8192 + kFW3Bytes + 256 * 128 + 2 * 128 * 128 + 1024 + 128);
+  const uint32_t wfull = bars + 16, t2full = bars + 24, t2empty = bars + 32, y2full = bars + 40, y2free = bars + 48,
+                 t3full = bars + 56, t3empty = bars + 64;
+  auto hfull = [&](int s) { return bars + 72u + 8u * s; };
+  auto hempty = [&](int s) { return bars + 88u + 8u * s; };
+  uint32_t* tmem_word = reinterpret_cast<uint32_t*>(gen + kFHaloBytes + 9 * 8192 + kFW3Bytes + 256 * 128 + 2 * 128 * 128 + 1024 + 128);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 1 && lane == 0) {
-    mbar_init(hfull, 1); mbar_init(hempty, 1); mbar_init(wfull, 1);
-    mbar_init(t2full, 1); mbar_init(t2empty, 4);
+    for (int s = 0; s < 2; ++s) { mbar_init(hfull(s), 1); mbar_init(hempty(s), 1); }
+    mbar_init(wfull, 1);
+    mbar_init(t2full, 1); mbar_init(t2empty, 8);
     mbar_init(y2full, 1); mbar_init(y2free, 1);
-    mbar_init(t3full, 1); mbar_init(t3empty, 4);
+    mbar_init(t3full, 1); mbar_init(t3empty, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_word)), "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < 256; i += kThreads) bias3_s[i] = p.bias3 ? __ldg(p.bias3 + i) : 0.f;
+  for (int i = threadIdx.x; i < 256; i += kFThreads) bias3_s[i] = p.bias3 ? __ldg(p.bias3 + i) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -645,31 +656,39 @@ conv3x3_c3_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       for (int it = 0; it < n_my; ++it) {
         int img, y0, x0;
         decode(it, img, y0, x0);
-        mbar_wait(hempty, (uint32_t)((it & 1) ^ 1), p.error, 31);
-        mbar_expect_tx(hfull, kTHaloTx);
-        tma_load_4d(halo, &map_x, hfull, 0, x0 - 1, y0 - 1, img);
+        // the tile's two 16-row halves have a halo buffer each: the next tile's upper half loads while this tile's lower
+        // half is still being multiplied
+        for (int sub = 0; sub < 2; ++sub) {
+          mbar_wait(hempty(sub), (uint32_t)((it & 1) ^ 1), p.error, 31);
+          mbar_expect_tx(hfull(sub), kHaloTx);
+          tma_load_4d(halo + sub * kHaloBytes, &map_x, hfull(sub), 0, x0 - 1, y0 + 16 * sub - 1, img);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && n_my > 0) {
       // ===================================================================== MMA issuer
       const uint32_t fmt = p.dtype == DH_BF16 ? 1u : 0u;
-      const uint32_t idesc2 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
+      const uint32_t idesc2 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
       const uint32_t idesc3 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       mbar_wait(wfull, 0u, p.error, 32);
       tc_fence_after();
       auto conv2 = [&](int it) {
-        mbar_wait(hfull, (uint32_t)(it & 1), p.error, 33);
         mbar_wait(t2empty, (uint32_t)((it & 1) ^ 1), p.error, 34);
-        tc_fence_after();
-        for (int t = 0; t < 9; ++t) {
-          const int r = t / 3, s = t - r * 3;
-          const uint64_t da = umma_desc(w2s + t * 8192, 1024);                                    // 64 channels x 64 K
-          const uint64_t db = umma_desc(halo + (uint32_t)((r * kHaloW + s) * 128), kHaloW * 128);   // 256 pixels, shifted view
+        for (int sub = 0; sub < 2; ++sub) {                       // 128 pixels (16 rows) per halo buffer
+          mbar_wait(hfull(sub), (uint32_t)(it & 1), p.error, 33);
+          tc_fence_after();
+          const uint32_t hb = halo + sub * kHaloBytes;
+          for (int t = 0; t < 9; ++t) {
+            const int r = t / 3, s = t - r * 3;
+            const uint64_t da = umma_desc(w2s + t * 8192, 1024);                                  // 64 channels x 64 K
+            const uint64_t db = umma_desc(hb + (uint32_t)((r * kHaloW + s) * 128), kHaloW * 128);   // 128 pixels, shifted view
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc_mma(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (t | k) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              tc_mma(tmem_base + (uint32_t)(sub * 128), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (t | k) ? 1u : 0u);
+          }
+          tc_commit(hempty(sub));
         }
-        tc_commit(hempty);
         tc_commit(t2full);
       };
       auto conv3 = [&](int it, int h) {
@@ -692,8 +711,11 @@ conv3x3_c3_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       }
     }
   } else if (warp >= 4) {
-    // ======================================================================= epilogue
-    const int ew = warp - 4;
+    // ======================================================================= epilogue: EIGHT warps.  A warp may only read the
+    // TMEM lane quadrant warp % 4, so warps 4-7 and 8-11 cover the same rows and split the COLUMNS: with one thread per
+    // accumulator row and four warps the epilogue (512 outputs per thread and tile: unpack identity, two adds, max, pack),
+    // not HBM, paced the kernel (ncu: 30 k cycles per tile, 22 % tensor-active).
+    const int ew = warp & 3, eg = (warp - 4) >> 2;
     const int ch = ew * 16 + (lane & 15);                       // conv2 accumulator row (M = 64 layout) of this lane
     const bool active = lane < 16;
     const float bias2_v = (p.bias2 && active) ? __ldg(p.bias2 + ch) : 0.f;
@@ -705,14 +727,30 @@ conv3x3_c3_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     for (int it = 0; it < n_my; ++it) {
       int img, y0, x0;
       decode(it, img, y0, x0);
-      // ---- (1) conv2 accumulator -> slab (conv3's A operand)
+      // identity rows of this thread's two pixels (one per half): this group's 32 channels of every 64-channel round are 64
+      // contiguous bytes.  They are needed a few thousand cycles from now: pull the lines into L2 first, and fetch each round's
+      // chunk one round ahead into registers
+      const uint4* res_h[2];
+      bool inb_h[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int pix = h * 128 + row_l, gy = y0 + (pix >> 3), gx = x0 + (pix & 7);
+        inb_h[h] = gy < p.H && gx < p.W;
+        res_h[h] = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.residual) +
+                                                  (((long long)img * p.H + gy) * p.W + gx) * 256) + eg * 4;
+        if (inb_h[h]) {
+#pragma unroll
+          for (int l = 0; l < 2; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(res_h[h] + (2 * l + eg) * 8 - eg * 4));
+        }
+      }
+      // ---- (1) conv2 accumulator -> slab (conv3's A operand); group eg takes pixels [128 eg, 128 eg + 128)
       mbar_wait(t2full, (uint32_t)(it & 1), p.error, 37);
       mbar_wait(y2free, (uint32_t)((it & 1) ^ 1), p.error, 38);  // conv3 of the previous tile has read the slab
       tc_fence_after();
       {
         const uint32_t tmem_row = tmem_base + ((uint32_t)(ew * 32) << 16);
 #pragma unroll 1
-        for (int c = 0; c < 8; ++c) {                           // 32 pixels per TMEM load
+        for (int c = eg * 4; c < eg * 4 + 4; ++c) {             // 32 pixels per TMEM load
           uint32_t v[32];
           tc_ld32(tmem_row + (uint32_t)(c * 32), v);
           if (active) {
@@ -736,70 +774,77 @@ conv3x3_c3_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       __syncwarp();
       if (lane == 0) mbar_arrive(t2empty);                      // conv2's accumulator is drained
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (elected) mbar_arrive(y2full);
-      // ---- (2) conv3 accumulator of each 128-pixel half + bias + identity -> ReLU -> store
+      // ---- (2) conv3 accumulator of each 128-pixel half + bias + identity -> ReLU -> store; group eg takes channels
+      // [64 rd + 32 eg, 64 rd + 32 eg + 32) of round rd
+      uint4 rnext[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rnext[j] = inb_h[0] ? __ldg(res_h[0] + j) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
         const int q = 2 * it + h;
-        const int pix = h * 128 + row_l, gy = y0 + (pix >> 3), gx = x0 + (pix & 7);
-        const bool inb = gy < p.H && gx < p.W;
-        const uint4* res = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.residual) +
-                                                           (((long long)img * p.H + gy) * p.W + gx) * 256);
         mbar_wait(t3full, (uint32_t)(q & 1), p.error, 39);
         tc_fence_after();
-        const uint32_t tmem_row = tmem_base + ((uint32_t)(ew * 32) << 16) + 256u;
+        const uint32_t tmem_row = tmem_base + ((uint32_t)(ew * 32) << 16) + 256u + (uint32_t)(eg * 32);
 #pragma unroll 1
         for (int rd = 0; rd < 4; ++rd) {
-          uint4 rv[8];
+          uint4 rv[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) rv[j] = inb ? __ldg(res + rd * 8 + j) : make_uint4(0u, 0u, 0u, 0u);
+          for (int j = 0; j < 4; ++j) rv[j] = rnext[j];
+          {
+            // next round's identity chunk (the other half's first chunk after this half's last)
+            const bool more = !(h == 1 && rd == 3);
+            const uint4* np = rd == 3 ? res_h[1] : res_h[h] + (rd + 1) * 8;
+            const bool nin = rd == 3 ? inb_h[1] : inb_h[h];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rnext[j] = (more && nin) ? __ldg(np + j) : make_uint4(0u, 0u, 0u, 0u);
+          }
           const uint32_t slab = outs + (round_ctr & 1u) * (128 * 128);
           if (elected && round_ctr >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          uint32_t v[64];
+          uint32_t v[32];
           tc_ld32(tmem_row + (uint32_t)(rd * 64), v);
-          tc_ld32(tmem_row + (uint32_t)(rd * 64 + 32), v + 32);
           if (rd == 3) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(t3empty);                // conv3's accumulator now lives in registers
           }
-          const float4* b4 = reinterpret_cast<const float4*>(bias3_s + rd * 64);
+          const float2* b2p = reinterpret_cast<const float2*>(bias3_s + rd * 64 + eg * 32);
+          uint32_t w[16];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {                         // 8 channels per 16-byte slab chunk
-            const float4 ba = b4[2 * j], bb = b4[2 * j + 1];
+          for (int j = 0; j < 4; ++j) {                         // 8 channels per 16-byte chunk
             const uint32_t rr[4] = {rv[j].x, rv[j].y, rv[j].z, rv[j].w};
-            float r8[8];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
+              float r0, r1;
               if (p.dtype == DH_BF16) {
                 const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&rr[e]);
-                r8[2 * e] = __low2float(t); r8[2 * e + 1] = __high2float(t);
+                r0 = __low2float(t); r1 = __high2float(t);
               } else {
                 const __half2 t = *reinterpret_cast<const __half2*>(&rr[e]);
-                r8[2 * e] = __low2float(t); r8[2 * e + 1] = __high2float(t);
+                r0 = __low2float(t); r1 = __high2float(t);
               }
-            }
-            const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-            uint32_t w[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float a0 = fmaxf(__uint_as_float(v[8 * j + 2 * e]) + bv[2 * e] + r8[2 * e], 0.f);
-              const float a1 = fmaxf(__uint_as_float(v[8 * j + 2 * e + 1]) + bv[2 * e + 1] + r8[2 * e + 1], 0.f);
+              const float2 bb = b2p[4 * j + e];
+              // packed fp32 pair: (acc + bias) + identity, two IEEE additions per issued instruction
+              float a0, a1;
+              un2(add2(add2(pk2u(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]), pk2(bb.x, bb.y)), pk2(r0, r1)), a0, a1);
+              a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f);
               if (p.dtype == DH_BF16) {
                 __nv_bfloat162 t = __floats2bfloat162_rn(a0, a1);
-                w[e] = *reinterpret_cast<uint32_t*>(&t);
+                w[4 * j + e] = *reinterpret_cast<uint32_t*>(&t);
               } else {
                 __half2 t = __floats2half2_rn(a0, a1);
-                w[e] = *reinterpret_cast<uint32_t*>(&t);
+                w[4 * j + e] = *reinterpret_cast<uint32_t*>(&t);
               }
             }
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slab + (uint32_t)row_l * 128u + (((uint32_t)j ^ swz) << 4)),
-                         "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
           }
+          asm volatile("bar.sync 1, 256;" ::: "memory");          // the slab is free (the elected thread waited above)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slab + (uint32_t)row_l * 128u + (((uint32_t)(eg * 4 + j) ^ swz) << 4)),
+                         "r"(w[4 * j]), "r"(w[4 * j + 1]), "r"(w[4 * j + 2]), "r"(w[4 * j + 3]) : "memory");
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
           if (elected) {
             // slab rows are the half's pixels in (y, x) order: one box {64 channels, 8, 16, 1}; pixels outside the image
             // are clipped by TMA
@@ -946,7 +991,7 @@ extern "C" int dh_bottleneck_tail_tc(const void* y1, const void* w2, const float
   p.n = n; p.H = H; p.W = W; p.tiles_x = dh_cdiv(W, 8); p.tiles_y = dh_cdiv(H, 32);
   p.bias2 = bias2; p.bias3 = bias3; p.residual = x; p.dtype = dtype; p.error = g_error;
   CUtensorMap mx, mw2, mw3, mo;
-  rc = map_nhwc(&mx, y1, n, H, W, 64, kHaloW, kTHaloH, dtype);
+  rc = map_nhwc(&mx, y1, n, H, W, 64, kHaloW, kHaloH, dtype);
   if (rc) return rc;
   rc = map_nhwc(&mo, y, n, H, W, 256, 8, 16, dtype);
   if (rc) return rc;
@@ -975,7 +1020,7 @@ extern "C" int dh_bottleneck_tail_tc(const void* y1, const void* w2, const float
   }
   const int tiles = n * p.tiles_y * p.tiles_x;
   const int grid = tiles < g_sms ? tiles : g_sms;
-  conv3x3_c3_fused_kernel<<<grid, kThreads, kFSmemBytes, stream>>>(mx, mw2, mw3, mo, p);
+  conv3x3_c3_fused_kernel<<<grid, kFThreads, kFSmemBytes, stream>>>(mx, mw2, mw3, mo, p);
   DH_LAUNCH_OK();
   return DH_OK;
 }

@@ -114,8 +114,11 @@ extern "C" int dh_resnet50_forward(const dh_ctx* ctx, const void* images_nchw, i
     // conv1 1x1 + bn1 + relu (resnet.py:146-148)
     int r = dh_conv2d_tc(x, w.conv_w[blk][0], w.conv_b[blk][0], nullptr, y1, cnt, hw, hw, cin, mid, 1, 1, 1, 0, 1, dt, 0, stream);
     if (r) return r;
-    // layer1 identity blocks: conv2 -> conv3 + identity in one launch, conv2's output stays on chip (dh_bottleneck_tail_tc)
-    static const bool fused_tail = !getenv("DH_NO_FUSED_TAIL");
+    // layer1 identity blocks: conv2 -> conv3 + identity in one launch, conv2's output stays on chip (dh_bottleneck_tail_tc).
+    // Opt-in: correct (tests/test_gpu_tc.py) but not faster yet -- 590 us against 171 + 295 us for the two launches at 512
+    // images (profiles/r02_bench_bottleneck_tail.txt): with the identity added in the epilogue instead of on the tensor core,
+    // eight epilogue warps still spend 25 k cycles per 256-pixel tile against 12.7 k of HBM time.
+    static const bool fused_tail = getenv("DH_FUSED_TAIL") != nullptr;
     if (fused_tail && b > 0 && mid == 64 && stride == 1 && cin == 256 && !pool)
       return dh_bottleneck_tail_tc(y1, w.conv_w[blk][1], w.conv_b[blk][1], w.conv_w[blk][2], w.conv_b[blk][2], x, out, cnt, hw, hw, dt,
                                    stream);
