@@ -321,3 +321,29 @@ def test_trunk_pass_size_does_not_change_the_features():
             rt.chunk, enc_rt.TRUNK_CHUNK_DEVICE = saved
     assert torch.isfinite(e_big).all() and torch.equal(e_big, e_small)
 
+
+
+@pytest.mark.parametrize('kind', ['xfmr', 'xfmr_base'])
+def test_path_level_entries_equal_the_per_op_launch_sequence(kind):
+    """dh_resnet50_forward / dh_xfmr_step (csrc/path.cu: the trunk and one decoder-stack step behind one C call each) against
+    the same launch sequence issued op by op from Python: identical embeddings and identical captions."""
+    from deephumor_b200.runtime import ops
+    fx = H.load_fixture('canon', kind)
+    m, sd, imgs, labs, caps, lens = build(fx, 'bf16')
+    g = fx['gen'][1]
+    kw = dict(max_len=fx['max_len'], temperature=g['temperature'], beam_size=g['beam_size'], top_k=g['top_k'],
+              noise=g['mode'], seed=g['noise_seed'])
+    outs = []
+    for flag in (True, False):
+        ops.PATH_ENTRIES = flag
+        m.invalidate()
+        try:
+            with torch.no_grad():
+                enc = m.encoder(imgs[:8].cuda())
+                ids, ln = m.generate(imgs[:8].cuda(), **kw)
+            outs.append(([t.clone() for t in (enc if isinstance(enc, tuple) else (enc,))], ids.clone(), ln.clone()))
+        finally:
+            ops.PATH_ENTRIES = True
+    for a, b in zip(outs[0][0], outs[1][0]):
+        assert torch.equal(a, b)
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
