@@ -278,9 +278,37 @@ def measure(wl, steps, warmup, dist, dev, rank, local, min_seconds=2.0):
     ms, _, _ = timed(wl.step, k, dist, dev)
     clocks = sampler.stop() if rank == 0 else None
     _, launches_step, prof = timed(wl.step, 1, dist, dev, profile=True)
+    insitu = kernels_insitu(wl) if rank == 0 else None
     wl.step_e2e()
     ms_e2e, _, _ = timed(wl.step_e2e, k, dist, dev)
-    return dict(ms=ms, k=k, ms_e2e=ms_e2e, ke=k, clocks=clocks, prof=prof, launches_step=launches_step)
+    return dict(ms=ms, k=k, ms_e2e=ms_e2e, ke=k, clocks=clocks, prof=prof, launches_step=launches_step, insitu=insitu)
+
+
+def kernels_insitu(wl, top=10):
+    """Per-kernel device time INSIDE one step of the timed configuration (CUDA-graph replay included): CUPTI activity
+    records through torch.profiler.  The eager CUDA-event stage ranges carry a few microseconds of launch gap per launch;
+    these do not.  -> {'step_kernel_ms', 'kernels': [{'name', 'count', 'ms', 'share'}]} or None if the profiler is missing."""
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            wl.step()
+            torch.cuda.synchronize()
+        agg = {}
+        for ev in prof.events():
+            if ev.device_type == torch.autograd.DeviceType.CUDA:
+                t = ev.device_time if hasattr(ev, 'device_time') else ev.cuda_time
+                n, tot = agg.get(ev.name, (0, 0.0))
+                agg[ev.name] = (n + 1, tot + t)
+        total = sum(v[1] for v in agg.values())
+        if total <= 0:
+            return None
+        short = lambda k: k.replace('(anonymous namespace)::', '').replace('void ', '').split('(')[0][:64]
+        rows = sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]
+        return {'step_kernel_ms': round(total / 1e3, 3),
+                'kernels': [{'name': short(k), 'count': n, 'ms': round(t / 1e3, 3), 'share': round(t / total, 3)}
+                            for k, (n, t) in rows]}
+    except Exception as e:                               # measurement aid only
+        return {'unavailable': str(e)[:120]}
 
 
 def stage_report(prof, pk):
@@ -431,6 +459,8 @@ def summarize(wl, res, pk, pk_src, precision, world, batch=0):
         out['roofline'] = rl
     if res['prof']:
         out['stages_ms_per_step'], out['stages_tensor_frac'], out['stages_hbm'] = stage_report(res['prof'], pk)
+    if res.get('insitu'):
+        out['kernels_insitu'] = res['insitu']
     return out
 
 
