@@ -12,8 +12,9 @@
 //                 TMEM lane (K layout: 7 kernel rows x 22 slots = 21 (s,c) values + one junk value that meets a zero
 //                 weight; padded to 160 with zeros).  With A in shared memory every N = 64 MMA was bound by re-reading
 //                 its 128 x 16 A slice (128 cycles instead of 32) and the tile cost an extra smem write pass.
-//   pooling     = max over the 9 taps' accumulators of a lane, in registers (+bias, ReLU after the max: both monotone);
-//                 taps that fall into the pool's padding are skipped per lane.
+//   pooling     = max over the taps' accumulators of a lane, in registers (+bias, ReLU after the max: both monotone);
+//                 taps that fall into the pool's padding are skipped per lane.  Only the six taps dx = 1, 2 are computed:
+//                 tap (dy, 0) of a pooled pixel is tap (dy, 2) of its left neighbour = the neighbouring lane's accumulator.
 //
 // Computing each conv pixel once per pooling window costs 2.25x the conv FLOPs (0.53 GFLOP/image on a >1 PFLOP/s pipe)
 // and removes every intermediate from HBM: the kernel reads 602 KB and writes 401 KB per image.
@@ -29,7 +30,7 @@ constexpr int kBandRows = 15;
 constexpr int kKp = 192;                    // padded K: 7 * 22 = 154 real slots
 constexpr int kWBytes = 3 * 64 * 128;       // W tile: 3 K-chunks of [64 rows x 128 B]
 constexpr int kBandBytes = kBandRows * kPitch * 2;
-constexpr int kSmemBytes = 1024 + kWBytes + ((kBandBytes + 127) / 128) * 128 + 256 + 128;
+constexpr int kSmemBytes = 1024 + kWBytes + ((kBandBytes + 127) / 128) * 128 + 256 + 128 + 8 * 32 * 4;
 constexpr int kACols = 80;                  // A operand in TMEM: 160 halves = 80 32-bit columns per lane
 constexpr uint32_t kTmemCols = 256;         // 2 accumulator slots x 64 + A (80), power of two: two CTAs share an SM's 512
 
@@ -163,6 +164,7 @@ stem_pool_kernel(const TIN* __restrict__ images, const T* __restrict__ wp, const
   float* bias_s = reinterpret_cast<float*>(gbase + kWBytes + kBandPad);
   const uint32_t bars = base + kWBytes + kBandPad + 256u;     // mma_done[2]: the MMAs of the taps of each parity
   uint32_t* tmem_word = reinterpret_cast<uint32_t*>(gbase + kWBytes + kBandPad + 256 + 64);
+  float* xch = reinterpret_cast<float*>(gbase + kWBytes + kBandPad + 256 + 128);   // [8 warps][32]: last lane's accumulator
   auto mma_done = [&](uint32_t b) { return bars + 8u * b; };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -246,21 +248,38 @@ stem_pool_kernel(const TIN* __restrict__ images, const T* __restrict__ wp, const
 #pragma unroll
     for (int j = 0; j < 32; ++j) acc[j] = -INFINITY;
     // max-pool the accumulator of tap (dy, dx), issued as this CTA's tap number n, into the thread's 32 channels
+    // Only the taps dx = 1, 2 are computed: tap (dy, 0) of pooled pixel px is conv column 2 px - 1 = tap (dy, 2) of pooled
+    // pixel px - 1, i.e. the accumulator of the NEIGHBOURING lane (one shuffle per channel; the first lane of a warp takes it
+    // from the last lane of the warp below through shared memory).  Six taps instead of nine, the same values.
     auto drain = [&](uint32_t n, int dy, int dx) {
       mbar_wait(mma_done(n & 1u), (n >> 1) & 1u);
       tc_fence_after();
       uint32_t v[32];
       tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (n & 1u) * 64u + (uint32_t)ch0, v);
-      const bool valid = !((dy == 0 && py0 + e_py == 0) || (dx == 0 && e_px == 0));   // pool padding (-inf) is skipped
+      const bool valid = !(dy == 0 && py0 + e_py == 0);         // pool padding (-inf) is skipped
       if (valid) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], __uint_as_float(v[j]));
       }
+      if (dx == 2) {
+        if (lane == 31) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) xch[warp * 32 + j] = __uint_as_float(v[j]);
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        const bool shift_ok = valid && e_ok && e_px >= 1;       // px = 0: tap dx = 0 lies in the pool's padding
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float u = __shfl_up_sync(0xffffffffu, __uint_as_float(v[j]), 1);
+          if (lane == 0 && q > 0) u = xch[(warp - 1) * 32 + j];
+          if (shift_ok) acc[j] = fmaxf(acc[j], u);
+        }
+      }
     };
 
 #pragma unroll 1
-    for (int tap = 0; tap < 9; ++tap, ++n_tap) {
-      const int dy = tap / 3, dx = tap - dy * 3;
+    for (int tap = 0; tap < 6; ++tap, ++n_tap) {
+      const int dy = tap >> 1, dx = 1 + (tap & 1);
       // gather this thread's part of its pixel's patch (LSU work that overlaps the previous tap's MMAs)
       const uint32_t* rowp = reinterpret_cast<const uint32_t*>(band + (4 * m_py + 2 * dy) * kPitch + 12 * m_px + 6 * dx);
       // 8-byte loads: adjacent lanes are 24 B apart, so the 16 lanes of a half-warp cover 32 distinct banks with LDS.64
@@ -327,7 +346,7 @@ stem_pool_kernel(const TIN* __restrict__ images, const T* __restrict__ wp, const
         tc_commit(mma_done(n_tap & 1u));
       }
       // pool the previous tap while this one runs on the tensor core
-      if (tap > 0) { drain(n_tap - 1u, (tap - 1) / 3, (tap - 1) % 3); tc_fence_before(); }
+      if (tap > 0) { drain(n_tap - 1u, (tap - 1) >> 1, 1 + ((tap - 1) & 1)); tc_fence_before(); }
     }
     drain(n_tap - 1u, 2, 2);
     tc_fence_before();
