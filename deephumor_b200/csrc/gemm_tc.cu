@@ -15,6 +15,15 @@
 //
 // Tiles are scheduled statically (tile = blockIdx.x + i * gridDim.x, n fastest so CTAs running together
 // share the A rows through L2); grid = min(tiles, #SMs).  M / N / K tails rely on TMA zero fill.
+//
+// Variants selected at compile time (template <BN, PAIR, EPI, ARES>), each its own kernel in profiles:
+//   PAIR   two CTAs of a cluster run one tcgen05.mma.cta_group::2 of M = 256, each staging half of the W tile
+//   EPI 0  bias / ReLU / residual (R x I chunks on the tensor core) -> swizzled slab -> TMA store; optional fused global
+//          average pool over image-aligned M tiles (dh_gemm_tc_pool); three destinations (dh_gemm_tc_split3)
+//   EPI 1  maxima of 32-column groups (sampled pass 1 of the vocab projection)        EPI 2  sparse materialisation (pass 2)
+//   EPI 3  LSTM cell update, all layers of a time step chained in one launch          EPI 4  log-softmax pieces (perplexity)
+//   EPI 5  LayerNorm over the full 512-wide row: both N halves of a row block on one CTA (pair), packed-fp32 epilogue
+//   ARES   the A row block stays resident in shared memory, the CTA walks a contiguous run of N tiles (pass 2)
 #include <cuda.h>
 #include <stdlib.h>
 
