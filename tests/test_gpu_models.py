@@ -347,3 +347,29 @@ def test_path_level_entries_equal_the_per_op_launch_sequence(kind):
     for a, b in zip(outs[0][0], outs[1][0]):
         assert torch.equal(a, b)
     assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+
+
+def test_headline_config_is_run_to_run_deterministic_and_shard_invariant():
+    """BASELINE configs[4] at a tenth of a GPU's share (CaptioningTransformer, 2 048 images = 10 240 beam rows, beam 5, top-k 50,
+    32 tokens, V = 36 541, tensor-core mode, host uint8 pixels through the fused stem): two runs give identical ids (every
+    reduction on the path is ordered), and generating the batch as 4 shards with image_base offsets gives the same ids --
+    what makes the strong-scaled 1 / 2 / 4 / 8-GPU runs of bench.py produce one and the same result."""
+    from deephumor_b200.runtime import ops
+    from deephumor_b200.utils import synth_weights
+    V, n_img = 36541, 2048
+    hp = synth_weights.default_hp('xfmr', V)
+    sd = synth_weights.make_state_dict('xfmr', hp, seed=0)
+    m = CLS['xfmr'](**hp)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval().set_precision('bf16')
+    images = torch.empty(n_img, 3, 224, 224, device=DEV)
+    ops.synth_images(images, 0, 7000)
+    u8 = (images * 58.0 + 116.0).clamp_(0, 255).to(torch.uint8)
+    kw = dict(max_len=32, temperature=1.0, beam_size=5, top_k=50, noise='injected', seed=3)
+    with torch.no_grad():
+        a, la = m.generate(u8, image_base=7000, **kw)
+        b, lb = m.generate(u8, image_base=7000, **kw)
+        assert torch.equal(a, b) and torch.equal(la, lb)
+        parts = [m.generate(u8[i:i + 512], image_base=7000 + i, **kw) for i in range(0, n_img, 512)]
+    assert torch.equal(a, torch.cat([p[0] for p in parts])) and torch.equal(la, torch.cat([p[1] for p in parts]))
+    assert int(a.max()) < V and int(la.min()) >= 1
