@@ -721,13 +721,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           }
           if (stack && layer + 1 < p.layers) {
-            // publish this tile's h rows to the layer above: every thread's stores are fenced (and ordered against the
-            // consumer's async-proxy reads), then one release increment per tile
-            __threadfence();
-            fence_proxy_async_all();
+            // publish this tile's h rows to the layer above: the CTA barrier orders every epilogue thread's stores before
+            // thread 0, whose GPU-scope fence + release increment is cumulative over them (the pattern of a cooperative grid
+            // sync); a fence per thread made all 256 threads wait for their stores to drain (MEMBAR.GPU: 4 % of the kernel's
+            // samples).  The consumer orders its async-proxy (TMA) reads after its acquire (wait_ready).
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (etid == 0 && m0 < p.M) {
               __threadfence();
+              fence_proxy_async_all();
               red_release_gpu(p.ready + layer * p.mb128 + (m0 >> 7), 1);
             }
           }
