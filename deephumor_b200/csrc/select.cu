@@ -656,17 +656,18 @@ struct StepParams {
   float T; int noise_mode; unsigned long long seed; long long image_base; const long long* dyn;
 };
 
-// One warp per image; s_seq is B * seq_ld ints of shared memory.
+// One warp per image; s_seq is B * seq_ld (+ B * S_alloc for the KV slot table) ints of DYNAMIC shared memory: a static
+// [16][160] slot-table array cost 10 KB per CTA and one resident CTA per SM in the selection launch.
 __device__ void beam_step_body(const BeamState& st, const StepParams& p, int img, int* s_seq) {
   __shared__ float s_score[kMaxBeam * kMaxBeam];
   __shared__ float s_cval[kMaxBeam * kMaxBeam];
   __shared__ int s_ctok[kMaxBeam * kMaxBeam];
   __shared__ unsigned char s_cend[kMaxBeam * kMaxBeam], s_cpar[kMaxBeam * kMaxBeam];
   __shared__ int s_f[kMaxBeam];
-  __shared__ int s_src[kMaxBeam][kMaxSlots];
   const int lane = threadIdx.x & 31, B = p.B;
   if (st.done[img]) return;
   const long long base = (long long)img * B;
+  int* s_src = s_seq + (long long)B * st.seq_ld;              // [B][S_alloc]
   // --- candidate layout (beam.py:83-102): ended row -> 1 copy, live row -> B copies
   int e = 0, copies = 0;
   float v = 0.f;
@@ -690,7 +691,7 @@ __device__ void beam_step_body(const BeamState& st, const StepParams& p, int img
   // stage old sequences (and slot table) before they are overwritten
   for (long long i = lane; i < (long long)B * st.seq_ld; i += 32) s_seq[i] = st.seq[base * st.seq_ld + i];
   if (st.src)
-    for (int i = lane; i < B * st.S_alloc; i += 32) s_src[i / st.S_alloc][i % st.S_alloc] = st.src[base * st.S_alloc + i];
+    for (int i = lane; i < B * st.S_alloc; i += 32) s_src[i] = st.src[base * st.S_alloc + i];
   __syncwarp();
   // --- pruning draw: sample B of N from softmax(cand_val / T) (Q7)
   float mx = -INFINITY;
@@ -747,7 +748,7 @@ __device__ void beam_step_body(const BeamState& st, const StepParams& p, int img
     }
     if (st.src) {
       int* sr = st.src + (base + j) * st.S_alloc;
-      for (int t = lane; t < st.S_alloc; t += 32) sr[t] = (t <= p.step) ? s_src[par][t] : j;
+      for (int t = lane; t < st.S_alloc; t += 32) sr[t] = (t <= p.step) ? s_src[par * st.S_alloc + t] : j;
     }
   }
   if (lane == 0 && all_ended) {
@@ -946,6 +947,10 @@ extern "C" int dh_vocab_threshold_fix(const float* gmax, long long ld_gmax, int 
                           s);
 }
 
+static size_t beam_smem_bytes(const dh_beam_state* st, int beam) {      // staged sequences + KV slot table of one image
+  return (size_t)beam * (size_t)(st->seq_ld + (st->src ? st->S_alloc : 0)) * sizeof(int);
+}
+
 static int check_state(const dh_beam_state* st, int n_img, int beam) {
   if (!st || !st->seq || !st->val || !st->ended || !st->done || !st->final_len || !st->last_tok || !st->parent_state) return 0;
   if (n_img < 0 || beam < 1 || beam > kMaxBeam || st->seq_ld < 1) return 0;
@@ -974,10 +979,10 @@ extern "C" int dh_beam_step(const dh_beam_state* st, const int* new_ind, const f
                             int step, int max_len, int eos, int lstm_semantics, float temperature, int noise_mode,
                             unsigned long long seed, long long image_base, const long long* dyn, cudaStream_t s) {
   DH_ARG(check_state(st, n_img, beam) && new_ind && new_val && temperature > 0.f && step >= 1);
-  DH_ARG(st->seq_ld >= max_len && (size_t)beam * st->seq_ld * sizeof(int) <= 40 * 1024);
+  DH_ARG(st->seq_ld >= max_len && beam_smem_bytes(st, beam) <= 40 * 1024);
   if (n_img == 0) return DH_OK;
   StepParams p{new_ind, new_val, n_img, beam, step, max_len, eos, lstm_semantics, temperature, noise_mode, seed, image_base, dyn};
-  beam_step_kernel<<<n_img, 32, (size_t)beam * st->seq_ld * sizeof(int), s>>>(to_state(st), p);
+  beam_step_kernel<<<n_img, 32, beam_smem_bytes(st, beam), s>>>(to_state(st), p);
   DH_LAUNCH_OK();
   return DH_OK;
 }
@@ -1047,7 +1052,7 @@ static int select_beam_step(const dh_vocab_sparse* cand, const dh_beam_state* st
   VocabSparse vs{};
   DH_ARG(to_sparse(cand, &vs) && ind && val && status);
   DH_ARG(check_state(st, n_img, beam) && top_k >= 1 && beam <= top_k && temperature > 0.f && step >= 1);
-  DH_ARG(st->seq_ld >= max_len && (size_t)beam * st->seq_ld * sizeof(int) <= 40 * 1024);
+  DH_ARG(st->seq_ld >= max_len && beam_smem_bytes(st, beam) <= 40 * 1024);
   DH_ARG(noise_mode == DH_NOISE_DETERMINISTIC || noise_mode == DH_NOISE_INJECTED);
   LstmNext nx{};
   if (next) {
@@ -1065,7 +1070,7 @@ static int select_beam_step(const dh_vocab_sparse* cand, const dh_beam_state* st
   SelParams p{nullptr, 0, n_img * beam, 0, beam, top_k, unk, beam, temperature, noise_mode, seed, image_base, step,
               st->done, ind, val, status, dyn};
   StepParams sp{ind, val, n_img, beam, step, max_len, eos, lstm_semantics, temperature, noise_mode, seed, image_base, dyn};
-  return launch_select_beam(p, vs, n_img, 1, to_state(st), sp, (size_t)beam * st->seq_ld * sizeof(int), s, nx);
+  return launch_select_beam(p, vs, n_img, 1, to_state(st), sp, beam_smem_bytes(st, beam), s, nx);
 }
 
 extern "C" int dh_select_beam_step(const dh_vocab_sparse* cand, const dh_beam_state* st, int* ind, float* val, int* status,
