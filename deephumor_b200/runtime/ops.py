@@ -640,7 +640,12 @@ def resize_images(images, out_size=224):
     out = torch.empty(n, 3, out_size, out_size, dtype=torch.uint8, device=dev)
     if n == 0:
         return out
-    ts = [torch.as_tensor(np.ascontiguousarray(im)) if not torch.is_tensor(im) else im.contiguous() for im in images]
+    def as_tensor(im):
+        if torch.is_tensor(im):
+            return im.contiguous()
+        a = np.ascontiguousarray(im)
+        return torch.from_numpy(a if a.flags.writeable else a.copy())      # np.asarray(PIL image) is read-only
+    ts = [as_tensor(im) for im in images]
     for t in ts:
         if t.dtype != torch.uint8 or t.dim() != 3 or t.shape[2] != 3:
             raise ValueError('resize_images expects uint8 images of shape [H, W, 3] (RGB, as PIL.Image.convert("RGB") gives)')

@@ -103,3 +103,19 @@ def test_raw_photos_generate_the_same_captions_as_the_reference_preprocessing():
         ids_ref, len_ref = m.generate(ref_in, **kw)
         ids, lens = m.generate(m.preprocess(photos), **kw)
     assert torch.equal(ids, ids_ref) and torch.equal(lens, len_ref)
+
+
+@pytest.mark.gpu
+def test_preprocess_accepts_pil_images_of_any_mode():
+    """model.preprocess (the reference's Image.open + Resize((224,224)) on the device): PIL images in RGB, greyscale and
+    palette + alpha modes go through .convert('RGB') like a user of the reference would do before the transform; the result
+    equals torchvision's Resize on the converted image, bit for bit."""
+    import torchvision.transforms as T
+    from deephumor_b200.models import CaptioningLSTM
+    rgb = Image.fromarray(image(300, 420, 1))
+    grey = Image.fromarray(image(200, 150, 2)[..., 0], mode='L')
+    rgba = Image.fromarray(np.concatenate([image(333, 222, 3), np.full((333, 222, 1), 200, np.uint8)], -1), mode='RGBA')
+    out = CaptioningLSTM.preprocess([rgb, grey, rgba]).cpu()
+    for i, im in enumerate((rgb, grey, rgba)):
+        ref = T.PILToTensor()(T.Resize((224, 224))(im.convert('RGB')))
+        assert torch.equal(out[i], ref)
