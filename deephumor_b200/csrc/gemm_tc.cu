@@ -308,36 +308,49 @@ __device__ __forceinline__ uint32_t umma_idesc(int bn, int ab_dtype, int m = BM)
 // 256 x 256 pair tiles moves 512 KB from L2 per 67 MFLOP when A and W both stream -- 17 TB/s at the tensor peak, above what L2
 // delivers (~11.5 TB/s measured: profiles/r02_ncu_vocab_pass2_40960.csv shows 74 % tensor-active) -- and half of that with A
 // resident.
-template <int BN, bool PAIR = false, int EPI = 0, bool ARES = false>
+template <int BN, bool PAIR = false, int EPI = 0, bool ARES = false, int G2 = 0>
 struct Cfg {
   static constexpr int kMaxResChunks = 8;
   static constexpr int kAresBytes = ARES ? kMaxResChunks * BM * BK * 2 : 0;
   static constexpr int kStageBytes = ((ARES ? 0 : BM) + (PAIR ? BN / 2 : BN)) * BK * 2;
   // LayerNorm mode gives up ring stages for its parameter block (5 x 32 KB stages as a pair, 3 x 48 KB alone)
-  static constexpr int kStages = EPI == 5 ? (PAIR ? 5 : 3) : ARES ? (PAIR ? 5 : 3) : kSmemBudget / kStageBytes;
+  // plain stores with both epilogue groups and two slabs each (EPI 0, G2 == 2): four slabs, paid for with ring depth
+  static constexpr int kStages = EPI == 5 ? (PAIR ? 5 : 3) : ARES ? (PAIR ? 5 : 3) : (kSmemBudget - (EPI == 0 && G2 == 2 ? 2 * BM * 128 : 0)) / kStageBytes;
   static constexpr int kRingBytes = kAresBytes + kStages * kStageBytes;     // resident A block + ring
   static constexpr int kTmemCols = 2 * BN;
-  // two 128-row x 128 B slabs (TMA store) / per-warp transpose scratch; the selection epilogues (1, 2, 4) stage nothing
-  static constexpr int kStagingBytes = (EPI == 1 || EPI == 2 || EPI == 4) ? 0 : 2 * BM * 128;
+  // 128-row x 128 B slabs (TMA store; two per epilogue group in plain-store mode, one per group in LayerNorm mode) / per-warp
+  // transpose scratch; the selection epilogues (1, 2, 4) stage nothing
+  static constexpr int kStagingBytes = (EPI == 1 || EPI == 2 || EPI == 4) ? 0 : (EPI == 0 && G2 == 2 ? 4 : 2) * BM * 128;
   // bias slice of the current tile (BN <= 256 floats); double-buffered in the selection epilogues
-  static constexpr int kBiasBytes = (EPI == 1 || EPI == 2 || EPI == 4) ? 2048 : 1024;
+  // (plain stores: one copy per epilogue group)
+  static constexpr int kBiasBytes = (EPI == 1 || EPI == 2 || EPI == 4) ? 2048 : (EPI == 0 && G2 && BN == 256) ? 2048 : 1024;
   // LayerNorm mode: bias | gamma | beta of the whole 2 BN-wide row (fp32) + double-buffered per-row (mean, M2) partials of
   // the two column halves
   static constexpr int kLnBytes = EPI == 5 ? 3 * 2 * BN * 4 + 2 * 2 * BM * 2 * 4 : 0;
   static constexpr int kLnOff = kRingBytes + kStagingBytes + kBiasBytes + 256;
-  static constexpr int kSmemBytes = 1024 + kLnOff + kLnBytes;
+  // 1 KB of slack to align the ring to the 1024-byte swizzle atom -- except where that would exceed the 227 KB a CTA may own
+  // (<256, pair, plain stores>): there the kernel requires the dynamic shared memory window itself to be 1024-byte aligned
+  // (it is: the window starts right after the driver's 1 KB reservation) and traps with error code 6 otherwise
+  static constexpr int kAlignSlack = (kLnOff + kLnBytes + 1024 <= 232448) ? 1024 : 0;
+  static constexpr int kSmemBytes = kAlignSlack + kLnOff + kLnBytes;
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
 // EPI = TcParams::epi_mode as a compile-time constant: every epilogue is its own kernel (named in profiles, no dead code)
-template <int BN, bool PAIR, int EPI, bool ARES = false>
+template <int BN, bool PAIR, int EPI, bool ARES = false, int G2 = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
                const __grid_constant__ CUtensorMap map_i, const TcParams p) {
-  using C = Cfg<BN, PAIR, EPI, ARES>;
+  using C = Cfg<BN, PAIR, EPI, ARES, G2>;
   constexpr int CG = PAIR ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  if (C::kAlignSlack == 0 && base != smem_u32(smem_raw)) {
+    if (p.error) atomicExch(p.error, 6);
+    __threadfence_system();
+    __trap();
+  }
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t ares = base;                       // resident A block (ARES): chunk kc at ares + kc * 16 KB
   const uint32_t ring = base + C::kAresBytes;
@@ -384,7 +397,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), ((EPI && EPI != 5) ? 8 : 4) * CG);   // LayerNorm mode: one group drains each buffer   // the leader's barrier collects both CTAs' epilogue warps
+      // the leader's barrier collects both CTAs' epilogue warps: both groups except in LayerNorm mode (one group drains each
+      // buffer) and in the direct-store fallback of the plain epilogue (one group)
+      mbar_init(tempty_bar(s), ((EPI == 5 || (EPI == 0 && (!p.tma_store || !G2))) ? 4 : 8) * CG);
     }
     if (ARES) { mbar_init(afull_bar, 1); mbar_init(afree_bar, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -980,17 +995,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (etid < BN) bias_buf[(it + 1) & 1][etid] = bias_next;
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-    } else if (eh != 0) {
-      // second epilogue group: idle for plain stores
-    } else if (p.tma_store) {
+    } else if (p.tma_store && (eh == 0 || G2)) {
       // ---- slab epilogue: each thread owns one accumulator row; a round covers 128 B of every row (32 fp32 or
-      // 64 half columns), written 128B-swizzled into one of two 16 KB slabs and stored by one TMA instruction.
-      const uint32_t slabs = base + C::kRingBytes;
+      // 64 half columns), written 128B-swizzled into a 16 KB slab and stored by one TMA instruction.  The two epilogue
+      // groups (warps 4-7 / 8-11) take ALTERNATE rounds, each with its own two slabs, named barrier, bias copy and bulk groups:
+      // a round is one dependent chain (tensor-memory read -> bias / ReLU / rounding -> slab -> fence -> barrier -> store)
+      // and a lone warp per scheduler ran it at 15 % issue (ncu on l1.ds: 6.2 k cycles per 128 x 256 tile, which is what
+      // paced the contractions with K <= 768 and no residual traffic -- not HBM, not the tensor pipe); two warps per scheduler
+      // interleave two chains (template flag G2 == 2; l1.ds 148 -> 108 us, K = 512 decoder contractions +10 %).  The four
+      // slabs cost ring depth, which the HBM-bound K = 64 residual convolutions of layer1 need more (l1.c3: 157 us, against
+      // 143 us with G2 == 1: both groups, ONE slab each, full ring).  Long K loops hide the epilogue anyway and ran 4-6 %
+      // slower with both groups busy: they take G2 == 0, where the first group runs every round over two slabs and the second
+      // leaves at once (a warp spinning on the accumulator barrier costs the working warps issue slots).
+      constexpr int SPG = G2 == 1 ? 1 : 2;        // slabs per group
+      const uint32_t slabs = base + C::kRingBytes + (uint32_t)eh * (SPG * BM * 128);
+      float* bias_g = bias_s + (G2 ? eh * BN : 0);
+      const int bar_id = 1 + eh;
       const bool out32 = p.out_dtype == DH_F32;
       const int cpr = out32 ? 32 : 64;
+      const int rounds = BN / cpr;                // nominal rounds per tile: sets the group that takes round (it, rd)
       const int row_l = ew * 32 + lane;
       const uint32_t swz = (uint32_t)(row_l & 7);
-      const bool elected = (warp == 4 && lane == 0);
+      const bool elected = (ew == 0 && lane == 0);
       uint32_t round_ctr = 0;
       int last_n0 = -1;
       for (int it = 0, tile; (tile = tile_of(it)) < tiles; ++it) {
@@ -1000,7 +1026,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // global-load latency is off the per-tile critical path (all readers of the previous slice are past their last
         // round barrier)
         if (p.bias && n0 != last_n0) {
-          for (int i = row_l; i < BN; i += 128) bias_s[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+          for (int i = row_l; i < BN; i += 128) bias_g[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
           last_n0 = n0;
         }
         mbar_wait(tfull_bar(as), (it >> 1) & 1, p.error, 4);
@@ -1010,20 +1036,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int rd = 0; rd < BN / 32; ++rd) {
           const int col0 = n0 + rd * cpr;
           if (rd * cpr >= BN || col0 >= p.N) break;
-          const uint32_t slab = slabs + (round_ctr & 1u) * (BM * 128);
-          if (elected && round_ctr >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (G2 && ((it * rounds + rd) & 1) != eh) continue;
+          // the slab's previous TMA store (SPG rounds of this group ago) must have read it before it is rewritten
+          const uint32_t slab = slabs + (SPG == 2 ? (round_ctr & 1u) : 0u) * (BM * 128);
+          if (elected && round_ctr >= SPG) {
+            if (SPG == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
+          uint32_t v[64];
+          tc_ld32_nw(tmem_row + (uint32_t)(rd * cpr), v);
+          if (!out32) tc_ld32_nw(tmem_row + (uint32_t)(rd * cpr + 32), v + 32);
+          tc_wait_ld();
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // the slab is free (elected waited above); bias_g is set
           const uint32_t srow = slab + (uint32_t)row_l * 128u;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             if (out32 && h == 1) break;
-            uint32_t v[32];
-            tc_ld32(tmem_row + (uint32_t)(rd * cpr + h * 32), v);
             float x[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[h * 32 + j]);
             if (p.bias) {
-              const float4* bs = reinterpret_cast<const float4*>(bias_s + rd * cpr + h * 32);   // warp-uniform: broadcast
+              const float4* bs = reinterpret_cast<const float4*>(bias_g + rd * cpr + h * 32);   // warp-uniform: broadcast
 #pragma unroll
               for (int g = 0; g < 8; ++g) {
                 const float4 b4 = bs[g];
@@ -1063,7 +1096,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
           if (elected) {
             // split destinations (fused Q | K | V projection): the N tile lies entirely inside one of them
             const CUtensorMap* mc = &map_c;
@@ -1106,6 +1139,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar(as), 0)); else mbar_arrive(tempty_bar(as)); }
       }
       if (elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    } else if (eh != 0) {
+      // second epilogue group: idle in the one-group forms
     } else {
     float* st = staging + ew * 32 * kStageLd;
     const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
@@ -1280,13 +1315,13 @@ int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long col
   return DH_OK;
 }
 
-template <int BN, bool PAIR, int EPI, bool ARES = false>
+template <int BN, bool PAIR, int EPI, bool ARES = false, int G2 = 0>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mr, const CUtensorMap& mi,
            TcParams& p, cudaStream_t s) {
-  using C = Cfg<BN, PAIR, EPI, ARES>;
+  using C = Cfg<BN, PAIR, EPI, ARES, G2>;
   static bool attr = false;
   if (!attr) {
-    DH_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, PAIR, EPI, ARES>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    DH_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, PAIR, EPI, ARES, G2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr = true;
   }
   if (p.n_stride < 1) p.n_stride = 1;
@@ -1310,10 +1345,10 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, 
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    DH_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, PAIR, EPI, ARES>, ma, mb, mc, mr, mi, p));
+    DH_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, PAIR, EPI, ARES, G2>, ma, mb, mc, mr, mi, p));
   } else {
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    gemm_tc_kernel<BN, PAIR, EPI, ARES><<<grid, kThreads, C::kSmemBytes, s>>>(ma, mb, mc, mr, mi, p);
+    gemm_tc_kernel<BN, PAIR, EPI, ARES, G2><<<grid, kThreads, C::kSmemBytes, s>>>(ma, mb, mc, mr, mi, p);
   }
   DH_LAUNCH_OK();
   return DH_OK;
@@ -1321,7 +1356,13 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, 
 
 template <int EPI>
 int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mr, const CUtensorMap& mi,
-              TcParams& p, int bn, bool pair, cudaStream_t s) {
+              TcParams& p, int bn, bool pair, int g2, cudaStream_t s) {
+  if (EPI == 0 && g2 == 1) return launch<256, false, 0, false, 1>(ma, mb, mc, mr, mi, p, s);   // (dispatch: bn == 256, single CTA)
+  if (EPI == 0 && g2 == 2) {                                // plain stores with both epilogue groups at work
+    if (bn == 64) return launch<64, false, 0, false, 2>(ma, mb, mc, mr, mi, p, s);
+    if (bn == 128) return pair ? launch<128, true, 0, false, 2>(ma, mb, mc, mr, mi, p, s) : launch<128, false, 0, false, 2>(ma, mb, mc, mr, mi, p, s);
+    return pair ? launch<256, true, 0, false, 2>(ma, mb, mc, mr, mi, p, s) : launch<256, false, 0, false, 2>(ma, mb, mc, mr, mi, p, s);
+  }
   // full vocab-projection pass (143 N tiles per row block, K <= 512): A resident in shared memory, W streamed.  Measured at
   // 40 960 rows: 1109 vs 1159 us; the strided pass 1 (18 tiles per row block) re-loads A too often to gain and stays streamed.
   static const bool ares_ok = !getenv("DH_TC_NO_ARES");
@@ -1365,6 +1406,12 @@ int dispatch(const CUtensorMap& ma, const void* W, long long ldw, TcParams& p, i
   const bool res_ok = !p.res || (p.res_dtype == p.ab_dtype && (uintptr_t)p.res % 16 == 0 && (p.ldr * 2) % 16 == 0);
   p.tma_store = 0;
   p.res_chunks = 0;
+  // both epilogue groups for short K loops (measured: K = 512 decoder contractions +10 %, l1.c1 / l1.ds +17-29 %, neutral up
+  // to K = 1024; 8192^3 and K = 2048 lose 4-6 %); one slab per group for the single-CTA 256-wide residual launches (l1.c3:
+  // ring depth matters more there)
+  static const int groups_env = getenv("DH_TC_EPI_GROUPS") ? atoi(getenv("DH_TC_EPI_GROUPS")) : 0;
+  int g2 = p.k_chunks + (p.res ? bn / BK : 0) > 16 ? 0 : (p.res && !pair && bn == 256) ? 1 : 2;
+  if (groups_env) g2 = groups_env == 1 ? 0 : (groups_env == 3 && !pair && bn == 256) ? 1 : 2;
   if (p.epi_mode && p.epi_mode != 5) {
     // selection epilogues store nothing of C
   } else if (out_ok && res_ok) {
@@ -1381,14 +1428,14 @@ int dispatch(const CUtensorMap& ma, const void* W, long long ldw, TcParams& p, i
   }
   if (p.split_n && !p.tma_store) return dh_fail(DH_ERR_ARG, "split destinations need the TMA-store epilogue", __FILE__, __LINE__);
   switch (p.epi_mode) {
-    case 0: return launch_bn<0>(ma, mb, mc, mr, mi, p, bn, pair, s);
-    case 1: return launch_bn<1>(ma, mb, mc, mr, mi, p, bn, pair, s);
-    case 2: return launch_bn<2>(ma, mb, mc, mr, mi, p, bn, pair, s);
-    case 3: return launch_bn<3>(ma, mb, mc, mr, mi, p, bn, pair, s);
+    case 0: return launch_bn<0>(ma, mb, mc, mr, mi, p, bn, pair, g2, s);
+    case 1: return launch_bn<1>(ma, mb, mc, mr, mi, p, bn, pair, g2, s);
+    case 2: return launch_bn<2>(ma, mb, mc, mr, mi, p, bn, pair, g2, s);
+    case 3: return launch_bn<3>(ma, mb, mc, mr, mi, p, bn, pair, g2, s);
     case 5:
       if (!p.tma_store) return dh_fail(DH_ERR_ARG, "LayerNorm epilogue needs 16-byte aligned output / residual rows", __FILE__, __LINE__);
       return pair ? launch<256, true, 5>(ma, mb, mc, mr, mi, p, s) : launch<256, false, 5>(ma, mb, mc, mr, mi, p, s);
-    default: return launch_bn<4>(ma, mb, mc, mr, mi, p, bn, pair, s);
+    default: return launch_bn<4>(ma, mb, mc, mr, mi, p, bn, pair, g2, s);
   }
 }
 
