@@ -177,9 +177,41 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {   // arrives on `bar` in BOTH CTAs of the pair
+// Row statistics exchanged between the two CTAs of a cluster (LayerNorm split over the cluster, EPI 6): the partial lands in
+// the peer's shared memory and counts as transaction bytes on the peer's barrier; the reader acquires at cluster scope.
+// (st.async: the store itself completes 8 transaction bytes on the peer's barrier -- an explicit
+// mbarrier.arrive.release.cluster after a plain st.shared::cluster compiles to MEMBAR.ALL.GPU: 35 % of this epilogue's samples)
+__device__ __forceinline__ void st_async_f32x2(uint32_t cluster_addr, float a, float b, uint32_t cluster_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(cluster_addr),
+               "f"(a), "f"(b), "r"(cluster_bar)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int* error, int code) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {
+      if (error) atomicExch(error, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+// arrives on `bar` in BOTH CTAs of the pair (cluster ranks lead, lead + 1: mask 3 << lead)
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar, uint32_t lead = 0) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"((uint16_t)3)
+               "h"((uint16_t)(3u << lead))
                : "memory");
 }
 __device__ __forceinline__ void tc_mma_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -315,7 +347,7 @@ struct Cfg {
   static constexpr int kStageBytes = ((ARES ? 0 : BM) + (PAIR ? BN / 2 : BN)) * BK * 2;
   // LayerNorm mode gives up ring stages for its parameter block (5 x 32 KB stages as a pair, 3 x 48 KB alone)
   // plain stores with both epilogue groups and two slabs each (EPI 0, G2 == 2): four slabs, paid for with ring depth
-  static constexpr int kStages = EPI == 5 ? (PAIR ? 5 : 3) : ARES ? (PAIR ? 5 : 3) : (kSmemBudget - (EPI == 0 && G2 == 2 ? 2 * BM * 128 : 0)) / kStageBytes;
+  static constexpr int kStages = EPI == 6 ? (PAIR ? 5 : 3) : EPI == 5 ? (PAIR ? 5 : 3) : ARES ? (PAIR ? 5 : 3) : (kSmemBudget - (EPI == 0 && G2 == 2 ? 2 * BM * 128 : 0)) / kStageBytes;
   static constexpr int kRingBytes = kAresBytes + kStages * kStageBytes;     // resident A block + ring
   static constexpr int kTmemCols = 2 * BN;
   // 128-row x 128 B slabs (TMA store; two per epilogue group in plain-store mode, one per group in LayerNorm mode) / per-warp
@@ -326,7 +358,8 @@ struct Cfg {
   static constexpr int kBiasBytes = (EPI == 1 || EPI == 2 || EPI == 4) ? 2048 : (EPI == 0 && G2 && BN == 256) ? 2048 : 1024;
   // LayerNorm mode: bias | gamma | beta of the whole 2 BN-wide row (fp32) + double-buffered per-row (mean, M2) partials of
   // the two column halves
-  static constexpr int kLnBytes = EPI == 5 ? 3 * 2 * BN * 4 + 2 * 2 * BM * 2 * 4 : 0;
+  // (split form, EPI 6: four partials per row -- two column quarters of each of the cluster's two CTAs -- and two barriers)
+  static constexpr int kLnBytes = EPI == 5 ? 3 * 2 * BN * 4 + 2 * 2 * BM * 2 * 4 : EPI == 6 ? 3 * 2 * BN * 4 + 2 * 4 * BM * 2 * 4 + 64 : 0;
   static constexpr int kLnOff = kRingBytes + kStagingBytes + kBiasBytes + 256;
   // 1 KB of slack to align the ring to the 1024-byte swizzle atom -- except where that would exceed the 227 KB a CTA may own
   // (<256, pair, plain stores>): there the kernel requires the dynamic shared memory window itself to be 1024-byte aligned
@@ -402,6 +435,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_init(tempty_bar(s), ((EPI == 5 || (EPI == 0 && (!p.tma_store || !G2))) ? 4 : 8) * CG);
     }
     if (ARES) { mbar_init(afull_bar, 1); mbar_init(afree_bar, 1); }
+    if (EPI == 6) {                       // row-statistics barriers: 256 local arrivals + 256 x 8 bytes stored by the peer
+      const uint32_t sb = base + C::kLnOff + 3 * 2 * BN * 4 + 2 * 4 * BM * 2 * 4;
+      mbar_init(sb, 256); mbar_init(sb + 8, 256);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 2) {
     if (PAIR) {
@@ -417,11 +454,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   }
   tc_fence_before();
-  if (PAIR) cluster_sync_all(); else __syncthreads();
+  if (PAIR || EPI == 6) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_word);
   // tile = (M block of BM * CG rows, N block); a CTA pair walks the tiles together, CTA `rank` owning rows +rank * BM
-  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  // (a LayerNorm cluster holds TWO pairs, ranks {0, 1} and {2, 3}: `lead` is the rank of this CTA's pair leader)
+  const uint32_t cta_rank = PAIR ? (cluster_ctarank() & 1u) : 0u;
+  const uint32_t lead = (PAIR && EPI == 6) ? (cluster_ctarank() & 2u) : 0u;
   const int tiles = p.m_blocks * p.n_blocks * ((EPI == 3 && p.layers > 1) ? p.layers : 1);
   const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tstride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -470,7 +509,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (mb != ares_mb) {
             if (ares_mb >= 0) mbar_wait(afree_bar, (uint32_t)((ares_loads - 1) & 1), p.error, 1);
             if (cta_rank == 0) mbar_expect_tx(afull_bar, (uint32_t)(kch * p.bm_rows * BK * 2) * CG);
-            const uint32_t ab = PAIR ? mapa_u32(afull_bar, 0) : afull_bar;
+            const uint32_t ab = PAIR ? mapa_u32(afull_bar, lead) : afull_bar;
             for (int kc = 0; kc < kch; ++kc) {
               if (PAIR) tma_load_2d_pair(ares + kc * (BM * BK * 2), &map_a, ab, kc * BK, a_row);
               else tma_load_2d(ares + kc * (BM * BK * 2), &map_a, ab, kc * BK, a_row);
@@ -482,7 +521,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_wait(empty_bar(stage), phase ^ 1u, p.error, 1);
             const uint32_t sb = ring + stage * C::kStageBytes;
             if (cta_rank == 0) mbar_expect_tx(full_bar(stage), (uint32_t)C::kStageBytes * CG);
-            if (PAIR) tma_load_2d_pair(sb, &map_b, mapa_u32(full_bar(stage), 0), kc * BK, nb0);
+            if (PAIR) tma_load_2d_pair(sb, &map_b, mapa_u32(full_bar(stage), lead), kc * BK, nb0);
             else tma_load_2d(sb, &map_b, full_bar(stage), kc * BK, nb0);
             if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
           }
@@ -498,7 +537,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint32_t sa = ring + stage * C::kStageBytes, sb = sa + BM * BK * 2;
           if (cta_rank == 0) mbar_expect_tx(full_bar(stage), stage_tx * CG);
           if (PAIR) {
-            const uint32_t fb = mapa_u32(full_bar(stage), 0);
+            const uint32_t fb = mapa_u32(full_bar(stage), lead);
             if (p.conv && p.k1_chunks && kc >= p.k1_chunks) {
               // second source of a dual 1x1 convolution (the bottleneck's downsample branch, torchvision resnet.py:157-158)
               tma_load_im2col_pair(sa, &map_r, fb, (kc - p.k1_chunks) * BK, qw * p.stride2, ph * p.stride2, img, 0, 0);
@@ -532,7 +571,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint32_t sa = ring + stage * C::kStageBytes, sb = sa + BM * BK * 2;
           if (PAIR) {
             if (cta_rank == 0) mbar_expect_tx(full_bar(stage), stage_tx * CG);
-            const uint32_t fb = mapa_u32(full_bar(stage), 0);
+            const uint32_t fb = mapa_u32(full_bar(stage), lead);
             tma_load_2d_pair(sa, &map_r, fb, n0 + j * BK, m0l);
             tma_load_2d_pair(sb, &map_i, fb, j * BK, (int)cta_rank * (BN / CG));
           } else {
@@ -585,14 +624,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           }
           // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
-          if (PAIR) tc_commit_pair(empty_bar(stage)); else tc_commit(empty_bar(stage));
-          if (kc == chunks - 1) { if (PAIR) tc_commit_pair(tfull_bar(as)); else tc_commit(tfull_bar(as)); }
+          if (PAIR) tc_commit_pair(empty_bar(stage), lead); else tc_commit(empty_bar(stage));
+          if (kc == chunks - 1) { if (PAIR) tc_commit_pair(tfull_bar(as), lead); else tc_commit(tfull_bar(as)); }
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
         if (ARES) {
           // last tile of this row block in the run: once its MMAs retire the producer may overwrite the resident A
           const int nt = tile_of(it + 1);
-          if (nt >= tiles || nt / p.n_blocks != ares_mb) { if (PAIR) tc_commit_pair(afree_bar); else tc_commit(afree_bar); }
+          if (nt >= tiles || nt / p.n_blocks != ares_mb) { if (PAIR) tc_commit_pair(afree_bar, lead); else tc_commit(afree_bar); }
         }
       }
     }
@@ -675,7 +714,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               // and the global stores
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar(as), 0)); else mbar_arrive(tempty_bar(as)); }
+              if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar(as), lead)); else mbar_arrive(tempty_bar(as)); }
             }
             float c2[16];
             uint32_t hw[8];
@@ -749,6 +788,135 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
       }
+    } else if (EPI == 6) {
+      // ---- LayerNorm split over a cluster (x = LN(x + sublayer(x)), transformers.py:355-356,365-366,374-375): the two CTAs
+      // of a cluster compute the two 256-column halves of the SAME 128-row block (plain tile order, n fastest, even grid), so
+      // each needs only 256 tensor-memory columns per block and the accumulator is double-buffered -- the MMAs of block i + 1
+      // run under this epilogue (with the whole 512-wide row on one CTA, EPI 5, nothing overlaps: 55 us at 40 960 rows x
+      // K = 512 against 15 us of tensor work).  Each epilogue group owns 128 columns: pass 1 gives their (mean, M2), which goes
+      // to this CTA's shared memory (plain store + arrive) AND the peer's (st.async: data and barrier transaction in one),
+      // and the four partials of a row are merged pairwise (equal counts); pass 2 normalises from tensor memory.
+      constexpr int GW = BN / 2;                                 // columns per epilogue group
+      const int row_l = ew * 32 + lane;
+      float* lnp = reinterpret_cast<float*>(gen_base + C::kLnOff);          // [3][2 BN]: bias | gamma | beta of the whole row
+      float* part = lnp + 3 * 2 * BN;                                       // [2 buffers][4 quarters][BM][2]
+      const uint32_t part_u = base + C::kLnOff + 3 * 2 * BN * 4;
+      const uint32_t sbar = part_u + 2 * 4 * BM * 2 * 4;
+      // column half of this CTA (pair) and the CTA that holds the same rows of the other half
+      const uint32_t crank = PAIR ? cluster_ctarank() >> 1 : cluster_ctarank();
+      const uint32_t peer = cluster_ctarank() ^ (PAIR ? 2u : 1u);
+      const uint32_t slab = base + C::kRingBytes + (uint32_t)eh * (BM * 128);
+      const uint32_t srow = slab + (uint32_t)row_l * 128u;
+      const uint32_t swz = (uint32_t)(row_l & 7);
+      const bool elected = (ew == 0 && lane == 0);
+      const int bar_half = 2 + eh;
+      for (int i = etid; i < 2 * BN; i += 256) {
+        lnp[i] = p.bias ? __ldg(p.bias + i) : 0.f;
+        lnp[2 * BN + i] = __ldg(p.ln_gamma + i);
+        lnp[4 * BN + i] = __ldg(p.ln_beta + i);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int quarter = (int)crank * 2 + eh;                   // which 128 columns of the row this thread reduces
+      const int nq = quarter * GW;
+      const float2* bias2 = reinterpret_cast<const float2*>(lnp + nq);
+      const float2* gam2 = reinterpret_cast<const float2*>(lnp + 2 * BN + nq);
+      const float2* bet2 = reinterpret_cast<const float2*>(lnp + 4 * BN + nq);
+      bool slab_busy = false;
+      for (int it = 0, tile; (tile = tile_of(it)) < tiles; ++it) {
+        const int m0 = tile_m0(tile);
+        const int as = it & 1;
+        mbar_wait(tfull_bar(as), (it >> 1) & 1, p.error, 4);
+        tc_fence_after();
+        const uint32_t tmem_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN + eh * GW);
+        f32x2 s_a = pk2(0.f, 0.f), s_b = s_a, q_a = s_a, q_b = s_a, negp = s_a;
+        float pivot = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < GW / 64; ++c) {
+          uint32_t v[64];
+          tc_ld32_nw(tmem_row + (uint32_t)(c * 64), v);
+          tc_ld32_nw(tmem_row + (uint32_t)(c * 64 + 32), v + 32);
+          tc_wait_ld();
+          if (c == 0) {
+            pivot = __uint_as_float(v[0]) + bias2[0].x;
+            negp = pk2(-pivot, -pivot);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float2 b0 = bias2[c * 32 + j], b1 = bias2[c * 32 + j + 1];
+            const f32x2 d0 = add2(add2(pk2u(v[2 * j], v[2 * j + 1]), pk2(b0.x, b0.y)), negp);
+            const f32x2 d1 = add2(add2(pk2u(v[2 * j + 2], v[2 * j + 3]), pk2(b1.x, b1.y)), negp);
+            s_a = add2(s_a, d0); q_a = fma2(d0, d0, q_a);
+            s_b = add2(s_b, d1); q_b = fma2(d1, d1, q_b);
+          }
+        }
+        float s0, s1, q0, q1;
+        un2(add2(s_a, s_b), s0, s1);
+        un2(add2(q_a, q_b), q0, q1);
+        const float sh = s0 + s1, qh = q0 + q1;
+        const float mean_q = pivot + sh * (1.f / (float)GW);               // mean of this quarter
+        const float m2_q = qh - sh * sh * (1.f / (float)GW);               // sum of squared deviations about it
+        const uint32_t slot = (uint32_t)((((it & 1) * 4 + quarter) * BM + row_l) * 8);
+        const uint32_t sb_it = sbar + 8u * (uint32_t)(it & 1);
+        *reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(part) + slot) = make_float2(mean_q, m2_q);
+        st_async_f32x2(mapa_u32(part_u + slot, peer), mean_q, m2_q, mapa_u32(sb_it, peer));
+        if (etid == 0) mbar_expect_tx(sb_it, 256 * 8); else mbar_arrive(sb_it);
+        mbar_wait_cluster(sb_it, (uint32_t)((it >> 1) & 1), p.error, 7);
+        const float2* pp = reinterpret_cast<const float2*>(part) + (size_t)(it & 1) * 4 * BM + row_l;
+        const float2 p0 = pp[0], p1 = pp[BM], p2 = pp[2 * BM], p3 = pp[3 * BM];
+        const float mean = 0.25f * ((p0.x + p1.x) + (p2.x + p3.x));
+        const float d0 = p0.x - mean, d1 = p1.x - mean, d2 = p2.x - mean, d3 = p3.x - mean;
+        const float var = ((p0.y + p1.y) + (p2.y + p3.y) + (float)GW * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3))) * (1.f / (float)(4 * GW));
+        const float rstd = rsqrtf(fmaxf(var, 0.f) + p.ln_eps);
+        const f32x2 rr = pk2(rstd, rstd), negm = pk2(-mean, -mean);
+#pragma unroll 1
+        for (int rd = 0; rd < GW / 64; ++rd) {
+          // one slab per group: the previous round's TMA store must have read it before it is rewritten
+          if (elected && slab_busy) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          uint32_t v[64];
+          tc_ld32_nw(tmem_row + (uint32_t)(rd * 64), v);
+          tc_ld32_nw(tmem_row + (uint32_t)(rd * 64 + 32), v + 32);
+          tc_wait_ld();
+          if (rd == GW / 64 - 1) {
+            // the accumulator quarter now lives in registers: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar(as), lead)); else mbar_arrive(tempty_bar(as)); }
+          }
+          uint32_t w[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float2 b0 = bias2[rd * 32 + j], g0 = gam2[rd * 32 + j], e0 = bet2[rd * 32 + j];
+            const f32x2 a = mul2(rr, pk2(g0.x, g0.y));
+            const f32x2 k = fma2(add2(pk2(b0.x, b0.y), negm), a, pk2(e0.x, e0.y));
+            float y0, y1;
+            un2(fma2(pk2u(v[2 * j], v[2 * j + 1]), a, k), y0, y1);
+            if (p.out_dtype == DH_BF16) {
+              __nv_bfloat162 t = __floats2bfloat162_rn(y0, y1);
+              w[j] = *reinterpret_cast<uint32_t*>(&t);
+            } else {
+              __half2 t = __floats2half2_rn(y0, y1);
+              w[j] = *reinterpret_cast<uint32_t*>(&t);
+            }
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_half) : "memory");      // the slab is free (elected waited above)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (((uint32_t)j ^ swz) << 4)),
+                         "r"(w[4 * j]), "r"(w[4 * j + 1]), "r"(w[4 * j + 2]), "r"(w[4 * j + 3])
+                         : "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_half) : "memory");
+          if (elected) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(&map_c)),
+                         "r"(slab), "r"(nq + rd * 64), "r"(m0)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          slab_busy = true;
+        }
+      }
+      if (elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else if (EPI == 5) {
       // ---- LayerNorm epilogue (transformers.py:355-356,365-366,374-375: x = LN(x + sublayer(x))): accumulator buffer `eh`
       // holds columns [eh * BN, (eh + 1) * BN) of the row block (bias still to add; the residual already rode the tensor
@@ -825,7 +993,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // the accumulator half now lives in registers: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar(eh), 0)); else mbar_arrive(tempty_bar(eh)); }
+            if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar(eh), lead)); else mbar_arrive(tempty_bar(eh)); }
           }
           uint32_t w[32];
 #pragma unroll
@@ -986,7 +1154,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // the accumulator is drained: hand the TMEM buffer back to the MMA warp BEFORE any list traffic
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar(as), 0)); else mbar_arrive(tempty_bar(as)); }
+        if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar(as), lead)); else mbar_arrive(tempty_bar(as)); }
         if (EPI == 2 && emit) {
           p.hitmap[row * p.hit_ld + (long long)(((tile % p.n_blocks) * p.n_stride + p.n_offset) * 2 + eh)] = (unsigned char)bits;
           if (bits) atomicAdd(p.cand_count + row, __popc(bits));           // result unused: compiles to a fire-and-forget RED
@@ -1136,7 +1304,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar(as), 0)); else mbar_arrive(tempty_bar(as)); }
+        if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar(as), lead)); else mbar_arrive(tempty_bar(as)); }
       }
       if (elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else if (eh != 0) {
@@ -1238,12 +1406,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar(as), 0)); else mbar_arrive(tempty_bar(as)); }
+      if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar(as), lead)); else mbar_arrive(tempty_bar(as)); }
     }
     }
   }
   tc_fence_before();
-  if (PAIR) cluster_sync_all(); else __syncthreads();   // pair: the peer's MMAs / remote arrives target this CTA until here
+  if (PAIR || EPI == 6) cluster_sync_all(); else __syncthreads();   // pair: the peer's MMAs / remote arrives target this CTA until here
   if (warp == 2) {
     tc_fence_after();
     if (PAIR)
@@ -1333,10 +1501,46 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, 
   // LayerNorm mode schedules ROW BLOCKS (each CTA / pair runs both N halves of a block)
   const int tiles = EPI == 5 ? p.m_blocks : p.tiles_per_layer * ((EPI == 3 && p.layers > 1) ? p.layers : 1);
   if (p.res_chunks) p.res_chunks = BN / BK;
-  if (PAIR) {
+  if (PAIR && EPI == 6) {
+    // clusters of two CTA pairs: pair tiles 2 j and 2 j + 1 (the two column halves of a 256-row block) run side by side.
+    // The grid is what the device can hold of such clusters at once (GPCs whose SM count is not a multiple of 4 leave SMs out).
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = C::kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
+      cfg.gridDim = dim3(g_num_sms / 4 * 4);
+      int n = 0;
+      DH_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<BN, PAIR, EPI, ARES, G2>, &cfg));
+      max_clusters = n > 0 ? n : 1;
+    }
+    const int want = tiles / 2;                              // clusters that have work (tiles is even)
+    cfg.gridDim = dim3(4 * (want < max_clusters ? want : max_clusters));
+    DH_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, PAIR, EPI, ARES, G2>, ma, mb, mc, mr, mi, p));
+  } else if (PAIR) {
     const int pairs = g_num_sms / 2;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = C::kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    DH_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, PAIR, EPI, ARES, G2>, ma, mb, mc, mr, mi, p));
+  } else if (EPI == 6) {
+    // clusters of two plain CTAs: tiles 2 j and 2 j + 1 (the two column halves of row block j) run side by side
+    const int even_sms = g_num_sms & ~1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(tiles < even_sms ? tiles : even_sms);
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = C::kSmemBytes;
     cfg.stream = s;
@@ -1393,7 +1597,12 @@ int dispatch(const CUtensorMap& ma, const void* W, long long ldw, TcParams& p, i
   // GPU-scope membar, and lose on the 1-2 chunk store-bound tiles of layer1 (l1.c3 +8 % at a threshold of 4).
   static const int pair_min_chunks = getenv("DH_TC_PAIR_MIN_CHUNKS") ? atoi(getenv("DH_TC_PAIR_MIN_CHUNKS")) : 8;
   const int bm_rows = p.bm_rows > 0 ? p.bm_rows : BM;
-  const bool pair = pair_ok && bn >= 128 && p.M > bm_rows && p.k_chunks + (p.res ? bn / BK : 0) >= pair_min_chunks;
+  // LayerNorm launches split the row over a cluster of two plain CTAs (EPI 6) unless DH_TC_LN_UNSPLIT is set
+  static const bool ln_split_ok = !getenv("DH_TC_LN_UNSPLIT");
+  const bool ln_split = p.epi_mode == 5 && ln_split_ok && g_num_sms >= 2;
+  static const bool ln_pair_ok = !getenv("DH_TC_LN_NO_PAIR");
+  const bool pair = pair_ok && bn >= 128 && p.M > bm_rows && p.k_chunks + (p.res ? bn / BK : 0) >= pair_min_chunks &&
+                    (!ln_split || (ln_pair_ok && g_num_sms >= 4));
   const int b_rows = pair ? bn / 2 : bn;                   // W rows one CTA stages per K chunk
   const long long w_rows = (p.epi_mode == 3 && p.layers > 1) ? (long long)p.layers * p.w_layer_rows : p.N;
   int rc = make_map_2d(&mb, W, w_rows, p.K, ldw, b_rows, p.ab_dtype);
@@ -1434,6 +1643,7 @@ int dispatch(const CUtensorMap& ma, const void* W, long long ldw, TcParams& p, i
     case 3: return launch_bn<3>(ma, mb, mc, mr, mi, p, bn, pair, g2, s);
     case 5:
       if (!p.tma_store) return dh_fail(DH_ERR_ARG, "LayerNorm epilogue needs 16-byte aligned output / residual rows", __FILE__, __LINE__);
+      if (ln_split) return pair ? launch<256, true, 6>(ma, mb, mc, mr, mi, p, s) : launch<256, false, 6>(ma, mb, mc, mr, mi, p, s);
       return pair ? launch<256, true, 5>(ma, mb, mc, mr, mi, p, s) : launch<256, false, 5>(ma, mb, mc, mr, mi, p, s);
     default: return launch_bn<4>(ma, mb, mc, mr, mi, p, bn, pair, g2, s);
   }

@@ -453,6 +453,19 @@ def test_gemm_layernorm_epilogue(M, K, dt):
     assert H.rel_err(out2.float(), ref2) < tol
 
 
+@pytest.mark.parametrize('flag', ['DH_TC_LN_UNSPLIT', 'DH_TC_LN_NO_PAIR'])
+def test_gemm_layernorm_other_forms(flag):
+    """The LayerNorm contraction has three forms: the row split over a cluster of two CTA pairs (default), over two plain
+    CTAs (DH_TC_LN_NO_PAIR) and the whole row on one CTA / pair (DH_TC_LN_UNSPLIT).  The library reads the switches once, so the
+    other two run the same checks in a child process."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(root, 'tests', 'test_gpu_tc.py'), '-m', 'gpu', '-q', '-x',
+                        '-k', 'test_gemm_layernorm_epilogue'], env=dict(os.environ, **{flag: '1'}), cwd=root,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize('dt', [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize('n,H_,W_', [(2, 56, 56), (1, 32, 8), (3, 40, 24), (1, 56, 60), (5, 64, 16)])
 def test_bottleneck_tail_fused_conv2_conv3(n, H_, W_, dt):
