@@ -92,7 +92,15 @@ struct TcParams {
   // LayerNorm epilogue (epi_mode 5, dh_gemm_tc_ln): N == 2 * BN, a CTA computes BOTH N halves of its row block into the two
   // accumulator buffers, its two epilogue groups exchange row sums, and out = LN(A W^T + bias + residual) * gamma + beta
   const float* ln_gamma; const float* ln_beta; float ln_eps;
+  // Chained 1x1 convolution (dh_conv1x1_chain_tc, template flag G2 == 3): after tile P (this launch's C = act(...), N == BN) a
+  // CTA also computes tile Q = act2(C[m0 : m0 + 128, :] W2^T + bias2) for the SAME rows, reading C back through TMA while it is
+  // still in L2 -- the next bottleneck's conv1 without its HBM read.  W2 [N2, N] and the Q destination come in ChainMaps.
+  int N2, k2_chunks, relu2;
+  const float* bias2;
 };
+
+struct alignas(64) ChainMaps { CUtensorMap b2, c2; };
+thread_local const ChainMaps* tl_chain = nullptr;         // set by dh_conv1x1_chain_tc around its dispatch
 
 // ------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -374,7 +382,7 @@ template <int BN, bool PAIR, int EPI, bool ARES = false, int G2 = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
-               const __grid_constant__ CUtensorMap map_i, const TcParams p) {
+               const __grid_constant__ CUtensorMap map_i, const TcParams p, const __grid_constant__ ChainMaps cm) {
   using C = Cfg<BN, PAIR, EPI, ARES, G2>;
   constexpr int CG = PAIR ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
@@ -396,8 +404,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   auto tfull_bar = [&](int s) { return bars + 8u * (2 * C::kStages + s); };
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * C::kStages + 2 + s); };
   const uint32_t afull_bar = bars + 8u * (2 * C::kStages + 4), afree_bar = bars + 8u * (2 * C::kStages + 5);   // ARES only
+  const uint32_t stored_bar0 = bars + 8u * (2 * C::kStages + 6);                    // chain mode: two "tile P is in L2" barriers
   uint32_t* tmem_word = reinterpret_cast<uint32_t*>(gen_base + C::kRingBytes + C::kStagingBytes +
-                                                    C::kBiasBytes + 8 * (2 * C::kStages + 6));
+                                                    C::kBiasBytes + 8 * (2 * C::kStages + 8));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p.cond_mode) {
@@ -435,6 +444,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_init(tempty_bar(s), ((EPI == 5 || (EPI == 0 && (!p.tma_store || !G2))) ? 4 : 8) * CG);
     }
     if (ARES) { mbar_init(afull_bar, 1); mbar_init(afree_bar, 1); }
+    if (G2 == 3) { mbar_init(stored_bar0, 2); mbar_init(stored_bar0 + 8, 2); }   // one arrive per epilogue group
     if (EPI == 6) {                       // row-statistics barriers: 256 local arrivals + 256 x 8 bytes stored by the peer
       const uint32_t sb = base + C::kLnOff + 3 * 2 * BN * 4 + 2 * 4 * BM * 2 * 4;
       mbar_init(sb, 256); mbar_init(sb + 8, 256);
@@ -475,6 +485,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     return EPI == 5 ? 2 * (tile0 + (it >> 1) * tstride) + (it & 1) : tile0 + it * tstride;
   };
   auto tile_m0 = [&](int tile) { return (tile / p.n_blocks) * (p.bm_rows * CG) + (int)cta_rank * p.bm_rows; };
+  // Chain mode (G2 == 3, single CTA, N == BN): this CTA's own tiles t_j = tile0 + j * tstride, j < n_own, are walked as the
+  // virtual sequence P0 P1 Q0 P2 Q1 ... P(n-1) Q(n-2) Q(n-1) by all three roles -- Q_j (the second contraction over the rows of
+  // tile j) runs one tile behind P_j, so P_j's TMA stores have landed in L2 by the time Q_j's operand loads are issued.
+  const int n_own = (G2 == 3 && tile0 < tiles) ? (tiles - tile0 + tstride - 1) / tstride : 0;
+  auto chain_vt = [&](int v, bool& isq) {
+    if (v == 0) { isq = false; return 0; }
+    if (v == 2 * n_own - 1) { isq = true; return n_own - 1; }
+    if (v & 1) { isq = false; return (v + 1) >> 1; }
+    isq = true;
+    return (v >> 1) - 1;
+  };
 
   if (warp == 0) {
     if (lane == 0) {
@@ -482,6 +503,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int ares_mb = -1, ares_loads = 0;
+      if constexpr (G2 == 3) {
+        for (int v = 0; v < 2 * n_own; ++v) {
+          bool isq;
+          const int j = chain_vt(v, isq);
+          const int m0 = (tile0 + j * tstride) * p.bm_rows;
+          if (isq) {
+            // tile P_j is complete in L2 (both epilogue groups waited for their bulk stores): read it back as Q's A operand
+            mbar_wait(stored_bar0 + 8u * (uint32_t)(j & 1), (uint32_t)((j >> 1) & 1), p.error, 1);
+            fence_proxy_async_all();
+            for (int kc = 0; kc < p.k2_chunks; ++kc) {
+              mbar_wait(empty_bar(stage), phase ^ 1u, p.error, 1);
+              const uint32_t sa = ring + stage * C::kStageBytes, sb = sa + BM * BK * 2;
+              mbar_expect_tx(full_bar(stage), (uint32_t)(p.bm_rows + p.N2) * (BK * 2));
+              tma_load_2d(sa, &map_c, full_bar(stage), kc * BK, m0);
+              tma_load_2d(sb, &cm.b2, full_bar(stage), kc * BK, 0);
+              if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+            }
+            continue;
+          }
+          int img = 0, ph = 0, qw = 0;
+          if (p.conv) {
+            img = m0 / p.HoWo;
+            const int rem = m0 - img * p.HoWo;
+            ph = rem / p.Wo;
+            qw = rem - ph * p.Wo;
+          }
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
+            mbar_wait(empty_bar(stage), phase ^ 1u, p.error, 1);
+            const uint32_t sa = ring + stage * C::kStageBytes, sb = sa + BM * BK * 2;
+            mbar_expect_tx(full_bar(stage), (uint32_t)(p.bm_rows + BN) * (BK * 2));
+            if (p.conv && p.k1_chunks && kc >= p.k1_chunks)
+              tma_load_im2col(sa, &map_r, full_bar(stage), (kc - p.k1_chunks) * BK, qw * p.stride2, ph * p.stride2, img, 0, 0);
+            else if (p.conv)
+              tma_load_im2col(sa, &map_a, full_bar(stage), kc * BK, qw, ph, img, 0, 0);          // 1x1, stride 1, no padding
+            else
+              tma_load_2d(sa, &map_a, full_bar(stage), kc * BK, m0);
+            tma_load_2d(sb, &map_b, full_bar(stage), kc * BK, 0);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+          }
+          for (int r = 0; r < p.res_chunks; ++r) {
+            mbar_wait(empty_bar(stage), phase ^ 1u, p.error, 1);
+            const uint32_t sa = ring + stage * C::kStageBytes, sb = sa + BM * BK * 2;
+            mbar_expect_tx(full_bar(stage), p.bm_rows * BK * 2 + 64 * BK * 2);
+            tma_load_2d(sa, &map_r, full_bar(stage), r * BK, m0);
+            tma_load_2d(sb, &map_i, full_bar(stage), 0, 0);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      } else
       for (int it = 0, tile; (tile = tile_of(it)) < tiles; ++it) {
         int layer = 0, rt = tile;                                // EPI 3: layer-major tile order of a stacked LSTM step
         if (EPI == 3 && p.layers > 1) { layer = tile / p.tiles_per_layer; rt = tile - layer * p.tiles_per_layer; }
@@ -593,6 +663,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int ares_mb = -1, ares_cnt = 0;
+      if constexpr (G2 == 3) {
+        const uint32_t idesc2 = umma_idesc(p.N2, p.ab_dtype, BM);
+        for (int v = 0; v < 2 * n_own; ++v) {
+          bool isq;
+          chain_vt(v, isq);
+          const int as = v & 1;
+          mbar_wait(tempty_bar(as), ((v >> 1) & 1) ^ 1u, p.error, 2);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+          const int chunks = isq ? p.k2_chunks : p.k_chunks + p.res_chunks;
+          for (int kc = 0; kc < chunks; ++kc) {
+            mbar_wait(full_bar(stage), phase, p.error, 3);
+            tc_fence_after();
+            const uint32_t sa = ring + stage * C::kStageBytes, sb = sa + BM * BK * 2;
+            const uint64_t da = umma_desc(sa), db = umma_desc(sb);
+            if (isq) {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) tc_mma(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (kc | k) ? 1u : 0u);
+            } else if (kc >= p.k_chunks) {
+              const uint32_t td = tmem_d + (uint32_t)((kc - p.k_chunks) * 64);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) tc_mma(td, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc64, 1u);
+            } else {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) tc_mma(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
+            }
+            tc_commit(empty_bar(stage));
+            if (kc == chunks - 1) tc_commit(tfull_bar(as));
+            if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      } else
       for (int it = 0, tile; (tile = tile_of(it)) < tiles; ++it) {
         const int as = it & 1;
         mbar_wait(tempty_bar(as), ((it >> 1) & 1) ^ 1u, p.error, 2);
@@ -1163,6 +1265,102 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (etid < BN) bias_buf[(it + 1) & 1][etid] = bias_next;
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
+    } else if (G2 == 3) {
+      // ---- chained slab epilogue (dh_conv1x1_chain_tc): the slab rounds of the P tiles (BN columns -> map_c) and of the Q
+      // tiles (N2 columns -> cm.c2) alternate between the two epilogue groups by a running round count; before a group starts
+      // the virtual tile after a P tile its elected thread waits for the group's bulk stores to COMPLETE and arrives on that
+      // tile's "stored" barrier, which the producer needs before it reads the tile back for Q.
+      const uint32_t slab = base + C::kRingBytes + (uint32_t)eh * (BM * 128);
+      const int bar_id = 1 + eh;
+      const int row_l = ew * 32 + lane;
+      const uint32_t swz = (uint32_t)(row_l & 7);
+      const uint32_t srow = slab + (uint32_t)row_l * 128u;
+      const bool elected = (ew == 0 && lane == 0);
+      for (int i = etid; i < BN + p.N2; i += 256)
+        bias_s[i] = i < BN ? (p.bias ? __ldg(p.bias + i) : 0.f) : (p.bias2 ? __ldg(p.bias2 + i - BN) : 0.f);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      uint32_t rglob = 0;
+      bool slab_busy = false, prev_p = false;
+      int prev_j = 0;
+      for (int v = 0; v < 2 * n_own; ++v) {
+        bool isq;
+        const int j = chain_vt(v, isq);
+        const int m0 = (tile0 + j * tstride) * p.bm_rows;
+        const int as = v & 1;
+        if (prev_p && elected) {
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          mbar_arrive(stored_bar0 + 8u * (uint32_t)(prev_j & 1));
+          slab_busy = false;
+        }
+        prev_p = !isq;
+        prev_j = j;
+        mbar_wait(tfull_bar(as), (v >> 1) & 1, p.error, 4);
+        tc_fence_after();
+        const uint32_t tmem_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
+        const int nr = (isq ? p.N2 : BN) / 64;
+        const float* bias_t = bias_s + (isq ? BN : 0);
+        const bool relu = isq ? p.relu2 : p.relu;
+#pragma unroll 1
+        for (int rd = 0; rd < nr; ++rd) {
+          if (((rglob + rd) & 1u) != (uint32_t)eh) continue;
+          if (elected && slab_busy) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          uint32_t vv[64];
+          tc_ld32_nw(tmem_row + (uint32_t)(rd * 64), vv);
+          tc_ld32_nw(tmem_row + (uint32_t)(rd * 64 + 32), vv + 32);
+          tc_wait_ld();
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // the slab is free (elected waited above)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float x[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) x[q] = __uint_as_float(vv[h * 32 + q]);
+            const float4* bs = reinterpret_cast<const float4*>(bias_t + rd * 64 + h * 32);   // warp-uniform: broadcast
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float4 b4 = bs[g];
+              x[4 * g] += b4.x; x[4 * g + 1] += b4.y; x[4 * g + 2] += b4.z; x[4 * g + 3] += b4.w;
+            }
+            if (relu) {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) x[q] = fmaxf(x[q], 0.f);
+            }
+            uint32_t w[16];
+            if (p.out_dtype == DH_BF16) {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                __nv_bfloat162 t = __floats2bfloat162_rn(x[2 * q], x[2 * q + 1]);
+                w[q] = *reinterpret_cast<uint32_t*>(&t);
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                __half2 t = __floats2half2_rn(x[2 * q], x[2 * q + 1]);
+                w[q] = *reinterpret_cast<uint32_t*>(&t);
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (((uint32_t)(h * 4 + q) ^ swz) << 4)),
+                           "r"(w[4 * q]), "r"(w[4 * q + 1]), "r"(w[4 * q + 2]), "r"(w[4 * q + 3])
+                           : "memory");
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          if (elected) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(isq ? &cm.c2 : &map_c)),
+                         "r"(slab), "r"(rd * 64), "r"(m0)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            slab_busy = true;
+          }
+        }
+        rglob += (uint32_t)nr;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+      }
+      if (elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else if (p.tma_store && (eh == 0 || G2)) {
       // ---- slab epilogue: each thread owns one accumulator row; a round covers 128 B of every row (32 fp32 or
       // 64 half columns), written 128B-swizzled into a 16 KB slab and stored by one TMA instruction.  The two epilogue
@@ -1492,6 +1690,8 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, 
     DH_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, PAIR, EPI, ARES, G2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr = true;
   }
+  static const ChainMaps no_chain{};
+  const ChainMaps& cmaps = (G2 == 3 && tl_chain) ? *tl_chain : no_chain;
   if (p.n_stride < 1) p.n_stride = 1;
   p.n_blocks = dh_cdiv(dh_cdiv(p.N, BN) - p.n_offset, p.n_stride);
   if (p.bm_rows <= 0) p.bm_rows = BM;
@@ -1522,7 +1722,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, 
     }
     const int want = tiles / 2;                              // clusters that have work (tiles is even)
     cfg.gridDim = dim3(4 * (want < max_clusters ? want : max_clusters));
-    DH_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, PAIR, EPI, ARES, G2>, ma, mb, mc, mr, mi, p));
+    DH_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, PAIR, EPI, ARES, G2>, ma, mb, mc, mr, mi, p, cmaps));
   } else if (PAIR) {
     const int pairs = g_num_sms / 2;
     cudaLaunchConfig_t cfg{};
@@ -1535,7 +1735,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, 
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    DH_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, PAIR, EPI, ARES, G2>, ma, mb, mc, mr, mi, p));
+    DH_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, PAIR, EPI, ARES, G2>, ma, mb, mc, mr, mi, p, cmaps));
   } else if (EPI == 6) {
     // clusters of two plain CTAs: tiles 2 j and 2 j + 1 (the two column halves of row block j) run side by side
     const int even_sms = g_num_sms & ~1;
@@ -1549,10 +1749,10 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, 
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    DH_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, PAIR, EPI, ARES, G2>, ma, mb, mc, mr, mi, p));
+    DH_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, PAIR, EPI, ARES, G2>, ma, mb, mc, mr, mi, p, cmaps));
   } else {
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    gemm_tc_kernel<BN, PAIR, EPI, ARES, G2><<<grid, kThreads, C::kSmemBytes, s>>>(ma, mb, mc, mr, mi, p);
+    gemm_tc_kernel<BN, PAIR, EPI, ARES, G2><<<grid, kThreads, C::kSmemBytes, s>>>(ma, mb, mc, mr, mi, p, cmaps);
   }
   DH_LAUNCH_OK();
   return DH_OK;
@@ -1562,6 +1762,7 @@ template <int EPI>
 int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mr, const CUtensorMap& mi,
               TcParams& p, int bn, bool pair, int g2, cudaStream_t s) {
   if (EPI == 0 && g2 == 1) return launch<256, false, 0, false, 1>(ma, mb, mc, mr, mi, p, s);   // (dispatch: bn == 256, single CTA)
+  if (EPI == 0 && g2 == 3) return launch<256, false, 0, false, 3>(ma, mb, mc, mr, mi, p, s);   // chained second contraction
   if (EPI == 0 && g2 == 2) {                                // plain stores with both epilogue groups at work
     if (bn == 64) return launch<64, false, 0, false, 2>(ma, mb, mc, mr, mi, p, s);
     if (bn == 128) return pair ? launch<128, true, 0, false, 2>(ma, mb, mc, mr, mi, p, s) : launch<128, false, 0, false, 2>(ma, mb, mc, mr, mi, p, s);
@@ -1602,7 +1803,7 @@ int dispatch(const CUtensorMap& ma, const void* W, long long ldw, TcParams& p, i
   const bool ln_split = p.epi_mode == 5 && ln_split_ok && g_num_sms >= 2;
   static const bool ln_pair_ok = !getenv("DH_TC_LN_NO_PAIR");
   const bool pair = pair_ok && bn >= 128 && p.M > bm_rows && p.k_chunks + (p.res ? bn / BK : 0) >= pair_min_chunks &&
-                    (!ln_split || (ln_pair_ok && g_num_sms >= 4));
+                    (!ln_split || (ln_pair_ok && g_num_sms >= 4)) && p.N2 == 0;
   const int b_rows = pair ? bn / 2 : bn;                   // W rows one CTA stages per K chunk
   const long long w_rows = (p.epi_mode == 3 && p.layers > 1) ? (long long)p.layers * p.w_layer_rows : p.N;
   int rc = make_map_2d(&mb, W, w_rows, p.K, ldw, b_rows, p.ab_dtype);
@@ -1621,6 +1822,7 @@ int dispatch(const CUtensorMap& ma, const void* W, long long ldw, TcParams& p, i
   static const int groups_env = getenv("DH_TC_EPI_GROUPS") ? atoi(getenv("DH_TC_EPI_GROUPS")) : 0;
   int g2 = p.k_chunks + (p.res ? bn / BK : 0) > 16 ? 0 : (p.res && !pair && bn == 256) ? 1 : 2;
   if (groups_env) g2 = groups_env == 1 ? 0 : (groups_env == 3 && !pair && bn == 256) ? 1 : 2;
+  if (p.N2 > 0) g2 = 3;
   if (p.epi_mode && p.epi_mode != 5) {
     // selection epilogues store nothing of C
   } else if (out_ok && res_ok) {
@@ -2071,6 +2273,60 @@ extern "C" int dh_conv1x1_dual_tc(const void* x1, const void* x2, const void* w_
   rc = make_map_im2col(&ma2, x2, n, H2, W2, C2, 1, 1, stride2, 0, dtype);
   if (rc) return rc;
   return dispatch(ma, w_cat, p.K, p, tile_n ? tile_n : pick_bn(p.M, Cout), stream, &ma2);
+}
+
+// conv3 of a bottleneck AND conv1 of the NEXT bottleneck in one launch (torchvision resnet.py:154-161 then :146-148 of the
+// following block): out = relu(conv1x1(y2; W[:, :C1]) + (x2_is_source ? conv1x1(x2; W[:, C1:]) : x2) + bias) with Cout == 256,
+// and z = relu(conv1x1(out; w_next) + bias_next) with N2 = 64 / 128 / 256 output channels.  A CTA computes tile Q (128 pixels
+// of z) right after the tile P (the same 128 pixels of out) it has just stored, reading P back through TMA while it is still
+// in L2: the next block's conv1 costs no HBM read (layer1: 1.6 GB per 1024 images and block boundary).  Everything is 1x1 /
+// stride 1 on the same pixel grid (the layer1 shape); bit-identical to the two separate launches.
+extern "C" int dh_conv1x1_chain_tc(const void* y2, const void* x2, int x2_is_source, const void* w, const float* bias, void* out,
+                                   int n, int H, int W, int C1, int C2, const void* w_next, const float* bias_next, void* z,
+                                   int N2, int dtype, cudaStream_t stream) {
+  DH_ARG(dtype == DH_BF16 || dtype == DH_F16);
+  DH_ARG(y2 && x2 && w && out && w_next && z && n >= 0 && H > 0 && W > 0 && C1 > 0 && C1 % 64 == 0);
+  DH_ARG(x2_is_source ? (C2 > 0 && C2 % 64 == 0) : C2 == 256);
+  DH_ARG(N2 == 64 || N2 == 128 || N2 == 256);
+  DH_ARG(((uintptr_t)y2 % 16) == 0 && ((uintptr_t)x2 % 16) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)out % 16) == 0);
+  DH_ARG(((uintptr_t)w_next % 16) == 0 && ((uintptr_t)z % 16) == 0);
+  if (n == 0) return DH_OK;
+  int rc = tc_init();
+  if (rc) return rc;
+  const long long M = (long long)n * H * W;
+  DH_ARG(M < (1ll << 31));
+  const int Cout = 256;
+  TcParams p{};
+  p.M = (int)M; p.N = Cout; p.K = x2_is_source ? C1 + C2 : C1;
+  p.k_chunks = p.K / BK;
+  p.ab_dtype = dtype;
+  p.bias = bias;
+  p.out = out; p.ldc = Cout; p.out_dtype = dtype; p.relu = 1;
+  p.N2 = N2; p.k2_chunks = Cout / BK; p.relu2 = 1; p.bias2 = bias_next;
+  CUtensorMap ma, ma2;
+  ChainMaps cm;
+  rc = make_map_2d(&cm.b2, w_next, N2, Cout, Cout, N2, dtype);
+  if (rc) return rc;
+  rc = make_map_2d(&cm.c2, z, M, N2, N2, BM, dtype);
+  if (rc) return rc;
+  if (x2_is_source) {
+    // two sources along K through im2col maps (as dh_conv1x1_dual_tc, stride 1)
+    p.conv = 1; p.HoWo = H * W; p.Wo = W; p.c_chunks = C1 / BK; p.kw = 1; p.stride = 1; p.pad = 0;
+    p.k1_chunks = C1 / BK; p.stride2 = 1;
+    rc = make_map_im2col(&ma, y2, n, H, W, C1, 1, 1, 1, 0, dtype);
+    if (rc) return rc;
+    rc = make_map_im2col(&ma2, x2, n, H, W, C2, 1, 1, 1, 0, dtype);
+    if (rc) return rc;
+  } else {
+    p.res = x2; p.ldr = Cout; p.res_dtype = dtype;
+    rc = make_map_2d(&ma, y2, M, C1, C1, BM, dtype);
+    if (rc) return rc;
+  }
+  tl_chain = &cm;
+  rc = dispatch(ma, w, p.K, p, 256, stream, x2_is_source ? &ma2 : nullptr);
+  tl_chain = nullptr;
+  if (rc) return rc;
+  return p.tma_store ? DH_OK : dh_fail(DH_ERR_ARG, "chained convolution needs the TMA-store path", __FILE__, __LINE__);
 }
 
 // Non-zero after a watchdog trap inside gemm_tc_kernel: 1 producer, 2 MMA/accumulator, 3 MMA/operands, 4 epilogue.

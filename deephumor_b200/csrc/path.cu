@@ -107,12 +107,17 @@ extern "C" int dh_resnet50_forward(const dh_ctx* ctx, const void* images_nchw, i
     rc = dh_stem_pool_tc((const float*)images_nchw, w.stem_w, w.stem_b, xb[0], n, H, W, dt, stream);
   if (rc) return rc;
   // One bottleneck (torchvision resnet.py:143-163) for `cnt` images: x -> out, through the conv1 / conv2 scratch buffers
-  auto bottleneck = [&](int s, int b, int blk, const void* x, void* out, int cnt, int hw, int cin, float* pool) -> int {
+  // `c1_done`: conv1 of this block was already computed into y1 by the previous block's chained launch; `next_blk` >= 0: chain
+  // conv1 of block next_blk (of `next_mid` channels) behind this block's conv3 (dh_conv1x1_chain_tc; layer1's blocks only)
+  static const bool chain_ok = getenv("DH_NO_CHAIN") == nullptr;
+  auto bottleneck = [&](int s, int b, int blk, const void* x, void* out, int cnt, int hw, int cin, float* pool, bool c1_done,
+                        int next_blk, int next_mid) -> int {
     const int mid = 64 << s, cout = 4 * mid;
     const int stride = (b == 0 && s > 0) ? 2 : 1;
     const int ho = (hw + 2 - 3) / stride + 1;
     // conv1 1x1 + bn1 + relu (resnet.py:146-148)
-    int r = dh_conv2d_tc(x, w.conv_w[blk][0], w.conv_b[blk][0], nullptr, y1, cnt, hw, hw, cin, mid, 1, 1, 1, 0, 1, dt, 0, stream);
+    int r = c1_done ? DH_OK
+                    : dh_conv2d_tc(x, w.conv_w[blk][0], w.conv_b[blk][0], nullptr, y1, cnt, hw, hw, cin, mid, 1, 1, 1, 0, 1, dt, 0, stream);
     if (r) return r;
     // layer1 identity blocks: conv2 -> conv3 + identity in one launch, conv2's output stays on chip (dh_bottleneck_tail_tc).
     // Opt-in: correct (tests/test_gpu_tc.py) but not faster yet -- 590 us against 171 + 295 us for the two launches at 512
@@ -129,6 +134,9 @@ extern "C" int dh_resnet50_forward(const dh_ctx* ctx, const void* images_nchw, i
       r = dh_conv2d_tc(y1, w.conv_w[blk][1], w.conv_b[blk][1], nullptr, y2, cnt, hw, hw, mid, mid, 3, 3, stride, 1, 1, dt, 0, stream);
     if (r) return r;
     // conv3 1x1 + bn3 (+ downsample branch of a stage's first block, :157-158) + identity + relu (:154-161)
+    if (next_blk >= 0)   // ... and the next block's conv1 on the tile just stored, fed from L2 (y1 is free again: conv2 has run)
+      return dh_conv1x1_chain_tc(y2, x, b == 0, b == 0 ? w.dual_w[s] : w.conv_w[blk][2], b == 0 ? w.dual_b[s] : w.conv_b[blk][2], out,
+                                 cnt, ho, ho, mid, cin, w.conv_w[next_blk][0], w.conv_b[next_blk][0], y1, next_mid, dt, stream);
     if (b == 0)
       return dh_conv1x1_dual_tc(y2, x, w.dual_w[s], w.dual_b[s], out, cnt, ho, ho, mid, hw, hw, cin, stride, cout, 1, dt, 0, stream);
     if (pool)
@@ -137,6 +145,8 @@ extern "C" int dh_resnet50_forward(const dh_ctx* ctx, const void* images_nchw, i
     return dh_conv2d_tc(y2, w.conv_w[blk][2], w.conv_b[blk][2], x, out, cnt, ho, ho, mid, cout, 1, 1, 1, 0, 1, dt, 0, stream);
   };
   int cur = 0, hw = 56, cin = 64, blk = 0;
+  bool c1_done = false;
+  static const bool fused_tail_on = getenv("DH_FUSED_TAIL") != nullptr;
   // layer1 works on 56 x 56 maps of 64 - 256 channels (1.6 MB per image and tensor) and every one of its ten convolutions
   // runs at the HBM roofline when the batch goes through one layer at a time.  Taking `l2_chunk` images through the WHOLE
   // stage before the next ones keeps the block-to-block activations inside the 126 MB L2 (write-back): only the stage's
@@ -153,9 +163,9 @@ extern "C" int dh_resnet50_forward(const dh_ctx* ctx, const void* images_nchw, i
       void* sb = scratch + al((long long)l2_chunk * px * 256 * 2);
       const void* x = in0 + (long long)i0 * px * 64 * 2;
       void* outp = (unsigned char*)xb[1] + (long long)i0 * px * 256 * 2;
-      rc = bottleneck(0, 0, 0, x, sa, cnt, 56, 64, nullptr);
-      if (!rc) rc = bottleneck(0, 1, 1, sa, sb, cnt, 56, 256, nullptr);
-      if (!rc) rc = bottleneck(0, 2, 2, sb, outp, cnt, 56, 256, nullptr);
+      rc = bottleneck(0, 0, 0, x, sa, cnt, 56, 64, nullptr, false, -1, 0);
+      if (!rc) rc = bottleneck(0, 1, 1, sa, sb, cnt, 56, 256, nullptr, false, -1, 0);
+      if (!rc) rc = bottleneck(0, 2, 2, sb, outp, cnt, 56, 256, nullptr, false, -1, 0);
       if (rc) return rc;
     }
     cur = 1; cin = 256; blk = 3;
@@ -167,8 +177,14 @@ extern "C" int dh_resnet50_forward(const dh_ctx* ctx, const void* images_nchw, i
       const int ho = (hw + 2 - 3) / stride + 1;
       const bool last = (s == 3 && b == kBlocks[3] - 1);
       void* out = last ? feat : xb[cur ^ 1];
-      rc = bottleneck(s, b, blk, xb[cur], out, n, hw, cin, (last && pooled && ho * ho <= 128) ? pooled : nullptr);
+      // layer1 (Cout == 256, everything on the 56 x 56 grid): conv3 of a block carries conv1 of the next block -- also the
+      // first block of layer2, whose conv1 is 1x1 / stride 1 on the same grid (ResNet v1.5 strides conv2)
+      const bool chain = chain_ok && s == 0 && !fused_tail_on && blk + 1 < 16;
+      const int next_mid = (b + 1 < kBlocks[s]) ? mid : 2 * mid;
+      rc = bottleneck(s, b, blk, xb[cur], out, n, hw, cin, (last && pooled && ho * ho <= 128) ? pooled : nullptr, c1_done,
+                      chain ? blk + 1 : -1, next_mid);
       if (rc) return rc;
+      c1_done = chain;
       cur ^= 1;
       hw = ho;
       cin = cout;
