@@ -36,6 +36,7 @@ constexpr int kThreads = 384;            // warps 0-2 producer / MMA / TMEM, 4-7
 constexpr int kStageLd = 36;             // floats per staged row (32 + 4: conflict-free for 16 B accesses)
 constexpr int kSmemBudget = 196608;      // bytes of A/B ring
 constexpr int kMaxLayers = 8;            // LSTM layers one dh_lstm_stack_tc launch can chain
+constexpr int kChainLag = 2;             // chain mode: tile Q_j follows tile P_(j + kChainLag)
 
 struct TcParams {
   int M, N, K;
@@ -404,9 +405,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   auto tfull_bar = [&](int s) { return bars + 8u * (2 * C::kStages + s); };
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * C::kStages + 2 + s); };
   const uint32_t afull_bar = bars + 8u * (2 * C::kStages + 4), afree_bar = bars + 8u * (2 * C::kStages + 5);   // ARES only
-  const uint32_t stored_bar0 = bars + 8u * (2 * C::kStages + 6);                    // chain mode: two "tile P is in L2" barriers
+  const uint32_t stored_bar0 = bars + 8u * (2 * C::kStages + 6);                    // chain mode: four "tile P is in L2" barriers
   uint32_t* tmem_word = reinterpret_cast<uint32_t*>(gen_base + C::kRingBytes + C::kStagingBytes +
-                                                    C::kBiasBytes + 8 * (2 * C::kStages + 8));
+                                                    C::kBiasBytes + 8 * (2 * C::kStages + 10));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p.cond_mode) {
@@ -444,7 +445,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_init(tempty_bar(s), ((EPI == 5 || (EPI == 0 && (!p.tma_store || !G2))) ? 4 : 8) * CG);
     }
     if (ARES) { mbar_init(afull_bar, 1); mbar_init(afree_bar, 1); }
-    if (G2 == 3) { mbar_init(stored_bar0, 2); mbar_init(stored_bar0 + 8, 2); }   // one arrive per epilogue group
+    if (G2 == 3) { for (int b = 0; b < 4; ++b) mbar_init(stored_bar0 + 8u * b, 2); }   // one arrive per epilogue group
     if (EPI == 6) {                       // row-statistics barriers: 256 local arrivals + 256 x 8 bytes stored by the peer
       const uint32_t sb = base + C::kLnOff + 3 * 2 * BN * 4 + 2 * 4 * BM * 2 * 4;
       mbar_init(sb, 256); mbar_init(sb + 8, 256);
@@ -486,15 +487,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   };
   auto tile_m0 = [&](int tile) { return (tile / p.n_blocks) * (p.bm_rows * CG) + (int)cta_rank * p.bm_rows; };
   // Chain mode (G2 == 3, single CTA, N == BN): this CTA's own tiles t_j = tile0 + j * tstride, j < n_own, are walked as the
-  // virtual sequence P0 P1 Q0 P2 Q1 ... P(n-1) Q(n-2) Q(n-1) by all three roles -- Q_j (the second contraction over the rows of
-  // tile j) runs one tile behind P_j, so P_j's TMA stores have landed in L2 by the time Q_j's operand loads are issued.
+  // virtual sequence P0 P1 P2 Q0 P3 Q1 ... P(n-1) Q(n-3) Q(n-2) Q(n-1) by all three roles -- Q_j (the second contraction over
+  // the rows of tile j) runs kChainLag tiles behind P_j, so P_j's TMA stores have landed in L2, and the "stored" hand-off
+  // (store completion -> barrier -> producer -> operand loads -> MMAs) has two tiles' worth of epilogue work to hide behind.
   const int n_own = (G2 == 3 && tile0 < tiles) ? (tiles - tile0 + tstride - 1) / tstride : 0;
+  const int chain_lead = n_own < kChainLag + 1 ? n_own : kChainLag + 1;      // P tiles before the first Q
   auto chain_vt = [&](int v, bool& isq) {
-    if (v == 0) { isq = false; return 0; }
-    if (v == 2 * n_own - 1) { isq = true; return n_own - 1; }
-    if (v & 1) { isq = false; return (v + 1) >> 1; }
+    if (v < chain_lead) { isq = false; return v; }
+    const int w = v - chain_lead, pairs = n_own - chain_lead;               // then Q_k, P_(lead + k) alternate
+    if (w < 2 * pairs) { isq = !(w & 1); return (w & 1) ? chain_lead + (w >> 1) : (w >> 1); }
     isq = true;
-    return (v >> 1) - 1;
+    return pairs + (w - 2 * pairs);                                          // and the last Q tiles drain
   };
 
   if (warp == 0) {
@@ -510,7 +513,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int m0 = (tile0 + j * tstride) * p.bm_rows;
           if (isq) {
             // tile P_j is complete in L2 (both epilogue groups waited for their bulk stores): read it back as Q's A operand
-            mbar_wait(stored_bar0 + 8u * (uint32_t)(j & 1), (uint32_t)((j >> 1) & 1), p.error, 1);
+            mbar_wait(stored_bar0 + 8u * (uint32_t)(j & 3), (uint32_t)((j >> 2) & 1), p.error, 1);
             fence_proxy_async_all();
             for (int kc = 0; kc < p.k2_chunks; ++kc) {
               mbar_wait(empty_bar(stage), phase ^ 1u, p.error, 1);
@@ -1289,7 +1292,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int as = v & 1;
         if (prev_p && elected) {
           asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-          mbar_arrive(stored_bar0 + 8u * (uint32_t)(prev_j & 1));
+          mbar_arrive(stored_bar0 + 8u * (uint32_t)(prev_j & 3));
           slab_busy = false;
         }
         prev_p = !isq;
