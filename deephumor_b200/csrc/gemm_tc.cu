@@ -490,7 +490,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   // virtual sequence P0 P1 P2 Q0 P3 Q1 ... P(n-1) Q(n-3) Q(n-2) Q(n-1) by all three roles -- Q_j (the second contraction over
   // the rows of tile j) runs kChainLag tiles behind P_j, so P_j's TMA stores have landed in L2, and the "stored" hand-off
   // (store completion -> barrier -> producer -> operand loads -> MMAs) has two tiles' worth of epilogue work to hide behind.
-  const int n_own = (G2 == 3 && tile0 < tiles) ? (tiles - tile0 + tstride - 1) / tstride : 0;
+  // (a unit = one 128-row block: its P part is n_blocks tiles of BN columns, its Q part one tile of N2 columns)
+  const int n_own = (G2 == 3 && tile0 < p.m_blocks) ? (p.m_blocks - tile0 + tstride - 1) / tstride : 0;
   const int chain_lead = n_own < kChainLag + 1 ? n_own : kChainLag + 1;      // P tiles before the first Q
   auto chain_vt = [&](int v, bool& isq) {
     if (v < chain_lead) { isq = false; return v; }
@@ -532,26 +533,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             ph = rem / p.Wo;
             qw = rem - ph * p.Wo;
           }
-          for (int kc = 0; kc < p.k_chunks; ++kc) {
-            mbar_wait(empty_bar(stage), phase ^ 1u, p.error, 1);
-            const uint32_t sa = ring + stage * C::kStageBytes, sb = sa + BM * BK * 2;
-            mbar_expect_tx(full_bar(stage), (uint32_t)(p.bm_rows + BN) * (BK * 2));
-            if (p.conv && p.k1_chunks && kc >= p.k1_chunks)
-              tma_load_im2col(sa, &map_r, full_bar(stage), (kc - p.k1_chunks) * BK, qw * p.stride2, ph * p.stride2, img, 0, 0);
-            else if (p.conv)
-              tma_load_im2col(sa, &map_a, full_bar(stage), kc * BK, qw, ph, img, 0, 0);          // 1x1, stride 1, no padding
-            else
-              tma_load_2d(sa, &map_a, full_bar(stage), kc * BK, m0);
-            tma_load_2d(sb, &map_b, full_bar(stage), kc * BK, 0);
-            if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
-          }
-          for (int r = 0; r < p.res_chunks; ++r) {
-            mbar_wait(empty_bar(stage), phase ^ 1u, p.error, 1);
-            const uint32_t sa = ring + stage * C::kStageBytes, sb = sa + BM * BK * 2;
-            mbar_expect_tx(full_bar(stage), p.bm_rows * BK * 2 + 64 * BK * 2);
-            tma_load_2d(sa, &map_r, full_bar(stage), r * BK, m0);
-            tma_load_2d(sb, &map_i, full_bar(stage), 0, 0);
-            if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+          for (int sub = 0; sub < p.n_blocks; ++sub) {
+            const int n0 = sub * BN;
+            for (int kc = 0; kc < p.k_chunks; ++kc) {
+              mbar_wait(empty_bar(stage), phase ^ 1u, p.error, 1);
+              const uint32_t sa = ring + stage * C::kStageBytes, sb = sa + BM * BK * 2;
+              mbar_expect_tx(full_bar(stage), (uint32_t)(p.bm_rows + BN) * (BK * 2));
+              if (p.conv && p.k1_chunks && kc >= p.k1_chunks)
+                tma_load_im2col(sa, &map_r, full_bar(stage), (kc - p.k1_chunks) * BK, qw * p.stride2, ph * p.stride2, img, 0, 0);
+              else if (p.conv)
+                tma_load_im2col(sa, &map_a, full_bar(stage), kc * BK, qw, ph, img, 0, 0);          // 1x1, stride 1, no padding
+              else
+                tma_load_2d(sa, &map_a, full_bar(stage), kc * BK, m0);
+              tma_load_2d(sb, &map_b, full_bar(stage), kc * BK, n0);
+              if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+            }
+            for (int r = 0; r < p.res_chunks; ++r) {
+              mbar_wait(empty_bar(stage), phase ^ 1u, p.error, 1);
+              const uint32_t sa = ring + stage * C::kStageBytes, sb = sa + BM * BK * 2;
+              mbar_expect_tx(full_bar(stage), p.bm_rows * BK * 2 + 64 * BK * 2);
+              tma_load_2d(sa, &map_r, full_bar(stage), n0 + r * BK, m0);
+              tma_load_2d(sb, &map_i, full_bar(stage), 0, 0);
+              if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+            }
           }
         }
       } else
@@ -668,33 +672,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int ares_mb = -1, ares_cnt = 0;
       if constexpr (G2 == 3) {
         const uint32_t idesc2 = umma_idesc(p.N2, p.ab_dtype, BM);
+        int vc = 0;                                              // accumulator buffers alternate per (sub-)tile
         for (int v = 0; v < 2 * n_own; ++v) {
           bool isq;
           chain_vt(v, isq);
-          const int as = v & 1;
-          mbar_wait(tempty_bar(as), ((v >> 1) & 1) ^ 1u, p.error, 2);
-          tc_fence_after();
-          const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-          const int chunks = isq ? p.k2_chunks : p.k_chunks + p.res_chunks;
-          for (int kc = 0; kc < chunks; ++kc) {
-            mbar_wait(full_bar(stage), phase, p.error, 3);
+          for (int sub = 0; sub < (isq ? 1 : p.n_blocks); ++sub, ++vc) {
+            const int as = vc & 1;
+            mbar_wait(tempty_bar(as), ((vc >> 1) & 1) ^ 1u, p.error, 2);
             tc_fence_after();
-            const uint32_t sa = ring + stage * C::kStageBytes, sb = sa + BM * BK * 2;
-            const uint64_t da = umma_desc(sa), db = umma_desc(sb);
-            if (isq) {
+            const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+            const int chunks = isq ? p.k2_chunks : p.k_chunks + p.res_chunks;
+            for (int kc = 0; kc < chunks; ++kc) {
+              mbar_wait(full_bar(stage), phase, p.error, 3);
+              tc_fence_after();
+              const uint32_t sa = ring + stage * C::kStageBytes, sb = sa + BM * BK * 2;
+              const uint64_t da = umma_desc(sa), db = umma_desc(sb);
+              if (isq) {
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) tc_mma(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (kc | k) ? 1u : 0u);
-            } else if (kc >= p.k_chunks) {
-              const uint32_t td = tmem_d + (uint32_t)((kc - p.k_chunks) * 64);
+                for (int k = 0; k < BK / 16; ++k) tc_mma(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (kc | k) ? 1u : 0u);
+              } else if (kc >= p.k_chunks) {
+                const uint32_t td = tmem_d + (uint32_t)((kc - p.k_chunks) * 64);
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) tc_mma(td, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc64, 1u);
-            } else {
+                for (int k = 0; k < BK / 16; ++k) tc_mma(td, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc64, 1u);
+              } else {
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) tc_mma(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
+                for (int k = 0; k < BK / 16; ++k) tc_mma(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
+              }
+              tc_commit(empty_bar(stage));
+              if (kc == chunks - 1) tc_commit(tfull_bar(as));
+              if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
             }
-            tc_commit(empty_bar(stage));
-            if (kc == chunks - 1) tc_commit(tfull_bar(as));
-            if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
           }
         }
       } else
@@ -1279,89 +1286,97 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t swz = (uint32_t)(row_l & 7);
       const uint32_t srow = slab + (uint32_t)row_l * 128u;
       const bool elected = (ew == 0 && lane == 0);
-      for (int i = etid; i < BN + p.N2; i += 256)
-        bias_s[i] = i < BN ? (p.bias ? __ldg(p.bias + i) : 0.f) : (p.bias2 ? __ldg(p.bias2 + i - BN) : 0.f);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      float* bias_g = bias_s + eh * BN;                         // this group's copy of the current (sub-)tile's bias slice
       uint32_t rglob = 0;
       bool slab_busy = false, prev_p = false;
-      int prev_j = 0;
+      int prev_j = 0, vc = 0, bias_key = -1;
       for (int v = 0; v < 2 * n_own; ++v) {
         bool isq;
         const int j = chain_vt(v, isq);
         const int m0 = (tile0 + j * tstride) * p.bm_rows;
-        const int as = v & 1;
-        if (prev_p && elected) {
-          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-          mbar_arrive(stored_bar0 + 8u * (uint32_t)(prev_j & 3));
-          slab_busy = false;
-        }
-        prev_p = !isq;
-        prev_j = j;
-        mbar_wait(tfull_bar(as), (v >> 1) & 1, p.error, 4);
-        tc_fence_after();
-        const uint32_t tmem_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
-        const int nr = (isq ? p.N2 : BN) / 64;
-        const float* bias_t = bias_s + (isq ? BN : 0);
-        const bool relu = isq ? p.relu2 : p.relu;
+        for (int sub = 0; sub < (isq ? 1 : p.n_blocks); ++sub, ++vc) {
+          const int as = vc & 1;
+          if (prev_p && elected) {
+            // the unit before this (sub-)tile ended a P part: its rows must be complete in L2 before the producer reads them
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            mbar_arrive(stored_bar0 + 8u * (uint32_t)(prev_j & 3));
+            slab_busy = false;
+          }
+          prev_p = !isq && sub == p.n_blocks - 1;
+          prev_j = j;
+          const int n0 = isq ? 0 : sub * BN;
+          const int ncols = isq ? p.N2 : BN;
+          const int key = isq ? p.n_blocks : sub;
+          if (key != bias_key) {     // (readers of the previous slice are past their last round barrier)
+            const float* src = isq ? p.bias2 : p.bias;
+            for (int i = row_l; i < ncols; i += 128) bias_g[i] = src ? __ldg(src + n0 + i) : 0.f;
+            bias_key = key;
+          }
+          mbar_wait(tfull_bar(as), (vc >> 1) & 1, p.error, 4);
+          tc_fence_after();
+          const uint32_t tmem_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
+          const int nr = ncols / 64;
+          const bool relu = isq ? p.relu2 : p.relu;
 #pragma unroll 1
-        for (int rd = 0; rd < nr; ++rd) {
-          if (((rglob + rd) & 1u) != (uint32_t)eh) continue;
-          if (elected && slab_busy) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          uint32_t vv[64];
-          tc_ld32_nw(tmem_row + (uint32_t)(rd * 64), vv);
-          tc_ld32_nw(tmem_row + (uint32_t)(rd * 64 + 32), vv + 32);
-          tc_wait_ld();
-          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // the slab is free (elected waited above)
+          for (int rd = 0; rd < nr; ++rd) {
+            if (((rglob + rd) & 1u) != (uint32_t)eh) continue;
+            if (elected && slab_busy) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            uint32_t vv[64];
+            tc_ld32_nw(tmem_row + (uint32_t)(rd * 64), vv);
+            tc_ld32_nw(tmem_row + (uint32_t)(rd * 64 + 32), vv + 32);
+            tc_wait_ld();
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // the slab is free (elected waited above); bias_g is set
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            float x[32];
+            for (int h = 0; h < 2; ++h) {
+              float x[32];
 #pragma unroll
-            for (int q = 0; q < 32; ++q) x[q] = __uint_as_float(vv[h * 32 + q]);
-            const float4* bs = reinterpret_cast<const float4*>(bias_t + rd * 64 + h * 32);   // warp-uniform: broadcast
+              for (int q = 0; q < 32; ++q) x[q] = __uint_as_float(vv[h * 32 + q]);
+              const float4* bs = reinterpret_cast<const float4*>(bias_g + rd * 64 + h * 32);   // warp-uniform: broadcast
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const float4 b4 = bs[g];
-              x[4 * g] += b4.x; x[4 * g + 1] += b4.y; x[4 * g + 2] += b4.z; x[4 * g + 3] += b4.w;
-            }
-            if (relu) {
-#pragma unroll
-              for (int q = 0; q < 32; ++q) x[q] = fmaxf(x[q], 0.f);
-            }
-            uint32_t w[16];
-            if (p.out_dtype == DH_BF16) {
-#pragma unroll
-              for (int q = 0; q < 16; ++q) {
-                __nv_bfloat162 t = __floats2bfloat162_rn(x[2 * q], x[2 * q + 1]);
-                w[q] = *reinterpret_cast<uint32_t*>(&t);
+              for (int g = 0; g < 8; ++g) {
+                const float4 b4 = bs[g];
+                x[4 * g] += b4.x; x[4 * g + 1] += b4.y; x[4 * g + 2] += b4.z; x[4 * g + 3] += b4.w;
               }
-            } else {
+              if (relu) {
 #pragma unroll
-              for (int q = 0; q < 16; ++q) {
-                __half2 t = __floats2half2_rn(x[2 * q], x[2 * q + 1]);
-                w[q] = *reinterpret_cast<uint32_t*>(&t);
+                for (int q = 0; q < 32; ++q) x[q] = fmaxf(x[q], 0.f);
               }
-            }
+              uint32_t w[16];
+              if (p.out_dtype == DH_BF16) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (((uint32_t)(h * 4 + q) ^ swz) << 4)),
-                           "r"(w[4 * q]), "r"(w[4 * q + 1]), "r"(w[4 * q + 2]), "r"(w[4 * q + 3])
+                for (int q = 0; q < 16; ++q) {
+                  __nv_bfloat162 t = __floats2bfloat162_rn(x[2 * q], x[2 * q + 1]);
+                  w[q] = *reinterpret_cast<uint32_t*>(&t);
+                }
+              } else {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                  __half2 t = __floats2half2_rn(x[2 * q], x[2 * q + 1]);
+                  w[q] = *reinterpret_cast<uint32_t*>(&t);
+                }
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (((uint32_t)(h * 4 + q) ^ swz) << 4)),
+                             "r"(w[4 * q]), "r"(w[4 * q + 1]), "r"(w[4 * q + 2]), "r"(w[4 * q + 3])
+                             : "memory");
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            if (elected) {
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                               reinterpret_cast<uint64_t>(isq ? &cm.c2 : &map_c)),
+                           "r"(slab), "r"(n0 + rd * 64), "r"(m0)
                            : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              slab_busy = true;
+            }
           }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-          if (elected) {
-            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                             reinterpret_cast<uint64_t>(isq ? &cm.c2 : &map_c)),
-                         "r"(slab), "r"(rd * 64), "r"(m0)
-                         : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            slab_busy = true;
-          }
+          rglob += (uint32_t)nr;
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(as));
         }
-        rglob += (uint32_t)nr;
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(as));
       }
       if (elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else if (p.tma_store && (eh == 0 || G2)) {
@@ -1702,7 +1717,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, 
   p.tiles_per_layer = p.m_blocks * p.n_blocks;
   p.mb128 = dh_cdiv(p.M, BM);
   // LayerNorm mode schedules ROW BLOCKS (each CTA / pair runs both N halves of a block)
-  const int tiles = EPI == 5 ? p.m_blocks : p.tiles_per_layer * ((EPI == 3 && p.layers > 1) ? p.layers : 1);
+  const int tiles = (EPI == 5 || G2 == 3) ? p.m_blocks : p.tiles_per_layer * ((EPI == 3 && p.layers > 1) ? p.layers : 1);
   if (p.res_chunks) p.res_chunks = BN / BK;
   if (PAIR && EPI == 6) {
     // clusters of two CTA pairs: pair tiles 2 j and 2 j + 1 (the two column halves of a 256-row block) run side by side.
@@ -2279,17 +2294,19 @@ extern "C" int dh_conv1x1_dual_tc(const void* x1, const void* x2, const void* w_
 }
 
 // conv3 of a bottleneck AND conv1 of the NEXT bottleneck in one launch (torchvision resnet.py:154-161 then :146-148 of the
-// following block): out = relu(conv1x1(y2; W[:, :C1]) + (x2_is_source ? conv1x1(x2; W[:, C1:]) : x2) + bias) with Cout == 256,
-// and z = relu(conv1x1(out; w_next) + bias_next) with N2 = 64 / 128 / 256 output channels.  A CTA computes tile Q (128 pixels
-// of z) right after the tile P (the same 128 pixels of out) it has just stored, reading P back through TMA while it is still
-// in L2: the next block's conv1 costs no HBM read (layer1: 1.6 GB per 1024 images and block boundary).  Everything is 1x1 /
-// stride 1 on the same pixel grid (the layer1 shape); bit-identical to the two separate launches.
+// following block): out [n,H,W,Cout] = relu(conv1x1(y2; W[:, :C1]) + (x2_is_source ? conv1x1(x2 (stride2); W[:, C1:]) : x2) +
+// bias) with Cout a multiple of 256, and z = relu(conv1x1(out; w_next) + bias_next) with N2 = 64 / 128 / 256 output channels.
+// A CTA computes tile Q (128 pixels of z) two tiles after the tiles P (the same 128 pixels of out, Cout / 256 of them) it has
+// stored, reading P back through TMA while it is still in L2: the next block's conv1 costs no HBM read (layer1: 1.6 GB per
+// 1024 images and block boundary).  Bit-identical to the two separate launches.
 extern "C" int dh_conv1x1_chain_tc(const void* y2, const void* x2, int x2_is_source, const void* w, const float* bias, void* out,
-                                   int n, int H, int W, int C1, int C2, const void* w_next, const float* bias_next, void* z,
-                                   int N2, int dtype, cudaStream_t stream) {
+                                   int n, int H, int W, int C1, int C2, int H2, int W2, int stride2, int Cout, const void* w_next,
+                                   const float* bias_next, void* z, int N2, int dtype, cudaStream_t stream) {
   DH_ARG(dtype == DH_BF16 || dtype == DH_F16);
   DH_ARG(y2 && x2 && w && out && w_next && z && n >= 0 && H > 0 && W > 0 && C1 > 0 && C1 % 64 == 0);
-  DH_ARG(x2_is_source ? (C2 > 0 && C2 % 64 == 0) : C2 == 256);
+  DH_ARG(Cout > 0 && Cout % 256 == 0 && Cout <= 1024);
+  DH_ARG(x2_is_source ? (C2 > 0 && C2 % 64 == 0 && stride2 >= 1 && (H2 - 1) / stride2 + 1 == H && (W2 - 1) / stride2 + 1 == W)
+                      : C2 == Cout);
   DH_ARG(N2 == 64 || N2 == 128 || N2 == 256);
   DH_ARG(((uintptr_t)y2 % 16) == 0 && ((uintptr_t)x2 % 16) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)out % 16) == 0);
   DH_ARG(((uintptr_t)w_next % 16) == 0 && ((uintptr_t)z % 16) == 0);
@@ -2298,7 +2315,6 @@ extern "C" int dh_conv1x1_chain_tc(const void* y2, const void* x2, int x2_is_sou
   if (rc) return rc;
   const long long M = (long long)n * H * W;
   DH_ARG(M < (1ll << 31));
-  const int Cout = 256;
   TcParams p{};
   p.M = (int)M; p.N = Cout; p.K = x2_is_source ? C1 + C2 : C1;
   p.k_chunks = p.K / BK;
@@ -2313,12 +2329,12 @@ extern "C" int dh_conv1x1_chain_tc(const void* y2, const void* x2, int x2_is_sou
   rc = make_map_2d(&cm.c2, z, M, N2, N2, BM, dtype);
   if (rc) return rc;
   if (x2_is_source) {
-    // two sources along K through im2col maps (as dh_conv1x1_dual_tc, stride 1)
+    // two sources along K through im2col maps (as dh_conv1x1_dual_tc)
     p.conv = 1; p.HoWo = H * W; p.Wo = W; p.c_chunks = C1 / BK; p.kw = 1; p.stride = 1; p.pad = 0;
-    p.k1_chunks = C1 / BK; p.stride2 = 1;
+    p.k1_chunks = C1 / BK; p.stride2 = stride2;
     rc = make_map_im2col(&ma, y2, n, H, W, C1, 1, 1, 1, 0, dtype);
     if (rc) return rc;
-    rc = make_map_im2col(&ma2, x2, n, H, W, C2, 1, 1, 1, 0, dtype);
+    rc = make_map_im2col(&ma2, x2, n, H2, W2, C2, 1, 1, stride2, 0, dtype);
     if (rc) return rc;
   } else {
     p.res = x2; p.ldr = Cout; p.res_dtype = dtype;

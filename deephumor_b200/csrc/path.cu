@@ -136,7 +136,8 @@ extern "C" int dh_resnet50_forward(const dh_ctx* ctx, const void* images_nchw, i
     // conv3 1x1 + bn3 (+ downsample branch of a stage's first block, :157-158) + identity + relu (:154-161)
     if (next_blk >= 0)   // ... and the next block's conv1 on the tile just stored, fed from L2 (y1 is free again: conv2 has run)
       return dh_conv1x1_chain_tc(y2, x, b == 0, b == 0 ? w.dual_w[s] : w.conv_w[blk][2], b == 0 ? w.dual_b[s] : w.conv_b[blk][2], out,
-                                 cnt, ho, ho, mid, cin, w.conv_w[next_blk][0], w.conv_b[next_blk][0], y1, next_mid, dt, stream);
+                                 cnt, ho, ho, mid, cin, hw, hw, stride, cout, w.conv_w[next_blk][0], w.conv_b[next_blk][0], y1, next_mid,
+                                 dt, stream);
     if (b == 0)
       return dh_conv1x1_dual_tc(y2, x, w.dual_w[s], w.dual_b[s], out, cnt, ho, ho, mid, hw, hw, cin, stride, cout, 1, dt, 0, stream);
     if (pool)
@@ -146,6 +147,7 @@ extern "C" int dh_resnet50_forward(const dh_ctx* ctx, const void* images_nchw, i
   };
   int cur = 0, hw = 56, cin = 64, blk = 0;
   bool c1_done = false;
+  static const int chain_layers = getenv("DH_CHAIN_LAYERS") ? atoi(getenv("DH_CHAIN_LAYERS")) : 2;
   static const bool fused_tail_on = getenv("DH_FUSED_TAIL") != nullptr;
   // layer1 works on 56 x 56 maps of 64 - 256 channels (1.6 MB per image and tensor) and every one of its ten convolutions
   // runs at the HBM roofline when the batch goes through one layer at a time.  Taking `l2_chunk` images through the WHOLE
@@ -177,9 +179,9 @@ extern "C" int dh_resnet50_forward(const dh_ctx* ctx, const void* images_nchw, i
       const int ho = (hw + 2 - 3) / stride + 1;
       const bool last = (s == 3 && b == kBlocks[3] - 1);
       void* out = last ? feat : xb[cur ^ 1];
-      // layer1 (Cout == 256, everything on the 56 x 56 grid): conv3 of a block carries conv1 of the next block -- also the
-      // first block of layer2, whose conv1 is 1x1 / stride 1 on the same grid (ResNet v1.5 strides conv2)
-      const bool chain = chain_ok && s == 0 && !fused_tail_on && blk + 1 < 16;
+      // layer1 and layer2 (Cout == 256 / 512): conv3 of a block carries conv1 of the next block -- also the first block of the
+      // next stage, whose conv1 is 1x1 / stride 1 on the same grid (ResNet v1.5 strides conv2).  DH_CHAIN_LAYERS=1: layer1 only.
+      const bool chain = chain_ok && s < chain_layers && !fused_tail_on && blk + 1 < 16;
       const int next_mid = (b + 1 < kBlocks[s]) ? mid : 2 * mid;
       rc = bottleneck(s, b, blk, xb[cur], out, n, hw, cin, (last && pooled && ho * ho <= 128) ? pooled : nullptr, c1_done,
                       chain ? blk + 1 : -1, next_mid);

@@ -190,17 +190,19 @@ def conv1x1_dual(x1, x2, w_cat, bias, y, stride2, relu, tile_n=0):
              int(relu), code(x1), tile_n, stream())
 
 
-def conv1x1_chain(y2, x2, x2_is_source, w, bias, out, w_next, bias_next, z):
-    """out = relu(y2 * W[:, :C1] + (x2 * W[:, C1:] if x2_is_source else x2) + bias) and z = relu(out * w_next + bias_next) in
-    one launch (dh_conv1x1_chain_tc: a bottleneck's conv3 and the next bottleneck's conv1, the latter fed from L2)."""
+def conv1x1_chain(y2, x2, x2_is_source, w, bias, out, w_next, bias_next, z, stride2=1):
+    """out = relu(y2 * W[:, :C1] + (x2[::stride2, ::stride2] * W[:, C1:] if x2_is_source else x2) + bias) and
+    z = relu(out * w_next + bias_next) in one launch (dh_conv1x1_chain_tc: a bottleneck's conv3 and the next bottleneck's
+    conv1, the latter fed from L2)."""
     n, H, W, C1 = y2.shape
-    C2, N2 = x2.shape[3], w_next.shape[0]
+    _, H2, W2, C2 = x2.shape
+    Cout, N2 = w.shape[0], w_next.shape[0]
     assert all(t.is_contiguous() for t in (y2, x2, w, out, w_next, z))
-    assert out.shape == (n, H, W, 256) and z.shape == (n, H, W, N2) and x2.shape[:3] == (n, H, W) and w_next.shape[1] == 256
-    assert w.shape == (256, C1 + C2 if x2_is_source else C1)
+    assert out.shape == (n, H, W, Cout) and z.shape == (n, H, W, N2) and w_next.shape[1] == Cout
+    assert w.shape[1] == (C1 + C2 if x2_is_source else C1)
     assert y2.dtype == x2.dtype == w.dtype == out.dtype == w_next.dtype == z.dtype
-    LIB.call('dh_conv1x1_chain_tc', ptr(y2), ptr(x2), int(x2_is_source), ptr(w), ptr(bias), ptr(out), n, H, W, C1, C2,
-             ptr(w_next), ptr(bias_next), ptr(z), N2, code(y2), stream())
+    LIB.call('dh_conv1x1_chain_tc', ptr(y2), ptr(x2), int(x2_is_source), ptr(w), ptr(bias), ptr(out), n, H, W, C1, C2, H2, W2,
+             stride2, Cout, ptr(w_next), ptr(bias_next), ptr(z), N2, code(y2), stream())
 
 
 def bottleneck_tail(y1, w2, b2, w3, b3, x, y):

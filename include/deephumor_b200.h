@@ -119,16 +119,17 @@ int dh_conv1x1_dual_tc(const void* x1, const void* x2, const void* w_cat, const 
                        int C1, int H2, int W2, int C2, int stride2, int Cout, int relu, int dtype, int tile_n,
                        cudaStream_t stream);
 /* conv3 of a bottleneck AND conv1 of the next one in ONE launch (torchvision resnet.py:154-161, then :146-148 of the following
- * block; layer1's shape: everything 1x1 / stride 1 on the same H x W grid, Cout == 256):
- *   out [n,H,W,256] = relu(y2 [n,H,W,C1] * W[:, :C1]^T + (x2_is_source ? x2 [n,H,W,C2] * W[:, C1:]^T : x2 [n,H,W,256]) + bias)
- *   z   [n,H,W,N2]  = relu(out * w_next [N2][256]^T + bias_next),  N2 = 64, 128 or 256
- * x2 is the block input: the downsample branch's source (first block of a stage, W = [W3 | Wd], bias = b3 + bd) or the
- * identity.  A CTA computes the 128 pixels of z right after it has stored the same 128 pixels of out, reading them back
- * through TMA while they are still in L2, so the next block's conv1 has no HBM read.  Bit-identical to dh_conv2d_tc /
- * dh_conv1x1_dual_tc followed by dh_conv2d_tc. */
+ * block; the layer1 / layer2 shapes, Cout % 256 == 0):
+ *   out [n,H,W,Cout] = relu(y2 [n,H,W,C1] * W[:, :C1]^T + (x2_is_source ? x2 [n,H2,W2,C2] (1x1, stride2) * W[:, C1:]^T
+ *                                                                        : x2 [n,H,W,Cout]) + bias)
+ *   z   [n,H,W,N2]   = relu(out * w_next [N2][Cout]^T + bias_next),  N2 = 64, 128 or 256
+ * x2 is the block input: the downsample branch's source (first block of a stage, W = [W3 | Wd], bias = b3 + bd,
+ * (H2 - 1) / stride2 + 1 == H) or the identity (H2 / W2 / stride2 ignored).  A CTA computes the 128 pixels of z two tiles after
+ * it has stored the same 128 pixels of out, reading them back through TMA while they are still in L2, so the next block's
+ * conv1 has no HBM read.  Bit-identical to dh_conv2d_tc / dh_conv1x1_dual_tc followed by dh_conv2d_tc. */
 int dh_conv1x1_chain_tc(const void* y2, const void* x2, int x2_is_source, const void* w, const float* bias, void* out, int n,
-                        int H, int W, int C1, int C2, const void* w_next, const float* bias_next, void* z, int N2, int dtype,
-                        cudaStream_t stream);
+                        int H, int W, int C1, int C2, int H2, int W2, int stride2, int Cout, const void* w_next,
+                        const float* bias_next, void* z, int N2, int dtype, cudaStream_t stream);
 /* 3x3 / stride 1 / pad 1 convolution (+ bias + ReLU) that loads each input pixel ONCE per tile (torchvision resnet.py:146-148,
  * conv2 of the layer1 / layer2 bottlenecks): an 8 x 16 output rectangle per tile, its 10 x 18 halo fetched by one tiled TMA
  * load per 64-channel chunk, the nine taps contracted as shifted UMMA-descriptor views of the same shared memory

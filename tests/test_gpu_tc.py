@@ -104,34 +104,40 @@ def test_conv1x1_dual_conv3_plus_downsample(n, Ho, C1, C2, Cout, s2):
 
 
 @pytest.mark.parametrize('dt', [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize('n,H_,W_,C1,source,N2', [(3, 56, 56, 64, True, 64), (2, 56, 56, 64, False, 64), (5, 56, 56, 64, False, 128),
-                                                  (1, 8, 8, 64, False, 64), (1, 9, 7, 128, True, 256), (40, 56, 56, 64, False, 64),
-                                                  (37, 28, 20, 64, True, 128)])
-def test_conv1x1_chain_conv3_then_next_conv1(n, H_, W_, C1, source, N2, dt):
+@pytest.mark.parametrize('n,H_,W_,C1,source,Cout,N2,s2', [(3, 56, 56, 64, True, 256, 64, 1), (2, 56, 56, 64, False, 256, 64, 1),
+                                                          (5, 56, 56, 64, False, 256, 128, 1), (1, 8, 8, 64, False, 256, 64, 1),
+                                                          (1, 9, 7, 128, True, 256, 256, 1), (40, 56, 56, 64, False, 256, 64, 1),
+                                                          (37, 28, 20, 64, True, 256, 128, 1), (9, 28, 28, 128, True, 512, 128, 2),
+                                                          (33, 28, 28, 128, False, 512, 128, 1), (6, 28, 28, 128, False, 512, 256, 1),
+                                                          (2, 5, 5, 64, True, 768, 64, 2)])
+def test_conv1x1_chain_conv3_then_next_conv1(n, H_, W_, C1, source, Cout, N2, s2, dt):
     """dh_conv1x1_chain_tc (a bottleneck's conv3 + identity / downsample + ReLU and the next bottleneck's conv1 + ReLU in one
-    launch, the second contraction reading the first one's tile back from L2; torchvision resnet.py:154-161, :146-148) is
-    BIT-IDENTICAL to the separate launches, over one tile per CTA, many tiles per CTA and clipped last tiles."""
-    C2 = 64 if source else 256
+    launch, the second contraction reading the first one's tiles back from L2; torchvision resnet.py:154-161, :146-148) is
+    BIT-IDENTICAL to the separate launches: one unit per CTA, many units per CTA, clipped last tiles, Cout of 1 - 3 column
+    tiles (the layer1 / layer2 shapes) and a strided downsample source."""
+    C2 = 64 * s2 if source else Cout
+    H2, W2 = (H_ * s2 - (s2 - 1), W_ * s2 - (s2 - 1)) if source and s2 > 1 else (H_, W_)
     y2 = rnd(n, H_, W_, C1, seed=1).to(dt).to(DEV)
-    x2 = rnd(n, H_, W_, C2, seed=2).to(dt).to(DEV)
-    w = rnd(256, C1 + (C2 if source else 0), seed=3, scale=0.05).to(dt).to(DEV)
-    b, wn, bn_ = rnd(256, seed=4).to(DEV), rnd(N2, 256, seed=5, scale=0.05).to(dt).to(DEV), rnd(N2, seed=6).to(DEV)
-    out = torch.zeros(n, H_, W_, 256, dtype=dt, device=DEV)
+    x2 = rnd(n, H2, W2, C2, seed=2).to(dt).to(DEV)
+    w = rnd(Cout, C1 + (C2 if source else 0), seed=3, scale=0.05).to(dt).to(DEV)
+    b, wn, bn_ = rnd(Cout, seed=4).to(DEV), rnd(N2, Cout, seed=5, scale=0.05).to(dt).to(DEV), rnd(N2, seed=6).to(DEV)
+    out = torch.zeros(n, H_, W_, Cout, dtype=dt, device=DEV)
     z = torch.zeros(n, H_, W_, N2, dtype=dt, device=DEV)
-    ops.conv1x1_chain(y2, x2, source, w, b, out, wn, bn_, z)
+    ops.conv1x1_chain(y2, x2, source, w, b, out, wn, bn_, z, stride2=s2)
     out_ref = torch.zeros_like(out)
     z_ref = torch.zeros_like(z)
     if source:
-        ops.conv1x1_dual(y2, x2, w, b, out_ref, 1, True)
+        ops.conv1x1_dual(y2, x2, w, b, out_ref, s2, True)
     else:
-        ops.conv2d(y2, w.view(256, 1, 1, C1), b, out_ref, 1, 0, True, residual=x2)
-    ops.conv2d(out_ref, wn.view(N2, 1, 1, 256), bn_, z_ref, 1, 0, True)
+        ops.conv2d(y2, w.view(Cout, 1, 1, C1), b, out_ref, 1, 0, True, residual=x2)
+    ops.conv2d(out_ref, wn.view(N2, 1, 1, Cout), bn_, z_ref, 1, 0, True)
     torch.cuda.synchronize()
     assert torch.equal(out, out_ref)
     assert torch.equal(z, z_ref)
-    ref = F.relu(y2.double().view(-1, C1) @ w.double()[:, :C1].T + (x2.double().view(-1, C2) @ w.double()[:, C1:].T if source
-                                                                     else x2.double().view(-1, 256)) + b.double())
-    assert H.rel_err(out.float().view(-1, 256), ref.float()) < (5e-3 if dt == torch.bfloat16 else 6e-4)
+    xs = x2[:, ::s2, ::s2] if source else x2
+    ref = F.relu(y2.double().reshape(-1, C1) @ w.double()[:, :C1].T + (xs.double().reshape(-1, C2) @ w.double()[:, C1:].T if source
+                                                                        else xs.double().reshape(-1, Cout)) + b.double())
+    assert H.rel_err(out.float().view(-1, Cout), ref.float()) < (5e-3 if dt == torch.bfloat16 else 6e-4)
 
 
 @pytest.mark.parametrize('dt', [torch.float16, torch.bfloat16])
