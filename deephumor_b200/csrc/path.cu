@@ -147,7 +147,7 @@ extern "C" int dh_resnet50_forward(const dh_ctx* ctx, const void* images_nchw, i
   };
   int cur = 0, hw = 56, cin = 64, blk = 0;
   bool c1_done = false;
-  static const int chain_layers = getenv("DH_CHAIN_LAYERS") ? atoi(getenv("DH_CHAIN_LAYERS")) : 2;
+  static const int chain_layers = getenv("DH_CHAIN_LAYERS") ? atoi(getenv("DH_CHAIN_LAYERS")) : 1;
   static const bool fused_tail_on = getenv("DH_FUSED_TAIL") != nullptr;
   // layer1 works on 56 x 56 maps of 64 - 256 channels (1.6 MB per image and tensor) and every one of its ten convolutions
   // runs at the HBM roofline when the batch goes through one layer at a time.  Taking `l2_chunk` images through the WHOLE
@@ -179,8 +179,11 @@ extern "C" int dh_resnet50_forward(const dh_ctx* ctx, const void* images_nchw, i
       const int ho = (hw + 2 - 3) / stride + 1;
       const bool last = (s == 3 && b == kBlocks[3] - 1);
       void* out = last ? feat : xb[cur ^ 1];
-      // layer1 and layer2 (Cout == 256 / 512): conv3 of a block carries conv1 of the next block -- also the first block of the
-      // next stage, whose conv1 is 1x1 / stride 1 on the same grid (ResNet v1.5 strides conv2).  DH_CHAIN_LAYERS=1: layer1 only.
+      // layer1 (Cout == 256): conv3 of a block carries conv1 of the next block -- also the first block of layer2, whose conv1
+      // is 1x1 / stride 1 on the same grid (ResNet v1.5 strides conv2).  DH_CHAIN_LAYERS=2 chains layer2 (Cout == 512) as well:
+      // correct and tested, but measured equal to the separate launches (1021 against 1017 us per 512 images for the stage's
+      // four boundaries) -- with K = 128 + 256 residual columns and K2 = 512 a unit streams 640 KB of operands from L2 for
+      // 320 KB of HBM traffic, so the chained launch sits on the L2 -> SM operand rate instead of on HBM.
       const bool chain = chain_ok && s < chain_layers && !fused_tail_on && blk + 1 < 16;
       const int next_mid = (b + 1 < kBlocks[s]) ? mid : 2 * mid;
       rc = bottleneck(s, b, blk, xb[cur], out, n, hw, cin, (last && pooled && ho * ho <= 128) ? pooled : nullptr, c1_done,
