@@ -10,20 +10,29 @@
 //   warp 1 (1 lane)  : MMA issuer.  tcgen05.mma.cta_group::1.kind::f16, UMMA 128 x BN x 16, fp32 accumulators
 //                      in TMEM, double-buffered (2 x BN columns) so the epilogue of tile i overlaps tile i+1.
 //   warp 2           : TMEM allocator / deallocator.
-//   warps 4..7       : epilogue.  tcgen05.ld (32 lanes x 32 columns per warp) -> padded smem transpose ->
-//                      coalesced 16 B global stores with bias / residual / ReLU, fp32 or bf16 output.
+//   warps 4..11      : epilogue, two groups of four warps (a warp reads its own 32-lane quadrant of tensor memory, so a
+//                      group covers the tile's 128 rows).  tcgen05.ld -> bias / ReLU / rounding -> 128B-swizzled slab ->
+//                      TMA store, the slab rounds of a tile alternating between the groups (or, fallback for unaligned
+//                      outputs: padded smem transpose -> coalesced 16 B global stores, one group).
 //
 // Tiles are scheduled statically (tile = blockIdx.x + i * gridDim.x, n fastest so CTAs running together
 // share the A rows through L2); grid = min(tiles, #SMs).  M / N / K tails rely on TMA zero fill.
 //
-// Variants selected at compile time (template <BN, PAIR, EPI, ARES>), each its own kernel in profiles:
+// Variants selected at compile time (template <BN, PAIR, EPI, ARES, G2>), each its own kernel in profiles:
 //   PAIR   two CTAs of a cluster run one tcgen05.mma.cta_group::2 of M = 256, each staging half of the W tile
 //   EPI 0  bias / ReLU / residual (R x I chunks on the tensor core) -> swizzled slab -> TMA store; optional fused global
 //          average pool over image-aligned M tiles (dh_gemm_tc_pool); three destinations (dh_gemm_tc_split3)
 //   EPI 1  maxima of 32-column groups (sampled pass 1 of the vocab projection)        EPI 2  sparse materialisation (pass 2)
 //   EPI 3  LSTM cell update, all layers of a time step chained in one launch          EPI 4  log-softmax pieces (perplexity)
 //   EPI 5  LayerNorm over the full 512-wide row: both N halves of a row block on one CTA (pair), packed-fp32 epilogue
+//   EPI 6  the same with the row SPLIT over a cluster: two CTAs (or two CTA pairs, a 4-CTA cluster) hold the two 256-column
+//          halves of a row block, exchange per-row (mean, M2) through st.async + transaction barriers, and keep the
+//          accumulator double-buffered (the default form of dh_gemm_tc_ln)
 //   ARES   the A row block stays resident in shared memory, the CTA walks a contiguous run of N tiles (pass 2)
+//   G2     plain-store epilogue (EPI 0) form: 0 one group / two slabs (long K loops), 1 both groups / one slab each and the
+//          full ring (single-CTA 256-wide residual launches), 2 both groups / two slabs each (K <= 1024), 3 chain mode:
+//          after tile P a CTA also contracts the rows it has just stored with a second weight matrix (tile Q, operand read
+//          back from L2): a bottleneck's conv3 + the next bottleneck's conv1 in one launch (dh_conv1x1_chain_tc)
 #include <cuda.h>
 #include <stdlib.h>
 
