@@ -70,6 +70,28 @@ def test_library_exports_every_declared_symbol():
     assert 'sm_100a' in out
 
 
+def test_entry_points_validate_arguments_before_touching_the_device():
+    """The C entries check shapes / alignment first and return an argument error (no CUDA call, so this runs without a GPU):
+    the chained convolution and the LayerNorm contraction added in round 2."""
+    L = _lib.LIB
+    P = 1 << 20                                                   # a 16-byte aligned, never dereferenced "device pointer"
+    good = dict(y2=P, x2=P, src=0, w=P, bias=P, out=P, n=2, H=8, W=8, C1=64, C2=256, H2=8, W2=8, s2=1, Cout=256, wn=P, bn=P,
+                z=P, N2=64, dt=1, stream=None)
+
+    def chain(**kw):
+        a = dict(good, **kw)
+        L.call('dh_conv1x1_chain_tc', a['y2'], a['x2'], a['src'], a['w'], a['bias'], a['out'], a['n'], a['H'], a['W'], a['C1'],
+               a['C2'], a['H2'], a['W2'], a['s2'], a['Cout'], a['wn'], a['bn'], a['z'], a['N2'], a['dt'], a['stream'])
+
+    chain(n=0)                                                    # nothing to do: returns before any device work
+    for bad in (dict(N2=96), dict(Cout=300), dict(C1=60), dict(C2=128), dict(src=1, C2=64, H2=15, W2=15, s2=3), dict(y2=P + 8),
+                dict(dt=0), dict(z=None)):
+        with pytest.raises(_lib.DeepHumorLibError, match='argument error'):
+            chain(**bad)
+    with pytest.raises(_lib.DeepHumorLibError, match='argument error'):           # LayerNorm rows are 512 wide
+        L.call('dh_gemm_tc_ln', P, 512, P, 512, 1, P, P, 256, P, P, 1e-5, P, 256, 128, 256, 512, None)
+
+
 def test_vocab_tokenizers_and_text_helpers():
     wt, ct = WordPunctTokenizer(), CharTokenizer()
     assert wt.tokenize("don't <sep> stop!!") == ["don't", '<sep>', 'stop', '!!']
